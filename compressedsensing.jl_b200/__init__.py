@@ -1,0 +1,441 @@
+"""Host-side mirror of CompressedSensing.jl's greedy-pursuit call surface over libcsb200.so.
+
+Julia is not installed in this image, so the host layer that the north star asks for in Julia
+(`julia/CompressedSensingB200.jl`, written against the same C ABI) is
+mirrored here 1:1 in Python/ctypes so that it can be exercised end to end on the GPU box.
+Same names, argument meaning and error behaviour as the reference:
+
+    omp(A, b, k)            /root/reference/src/matchingpursuit.jl:84-86
+    omp(A, b, eps, k=M)     :73-82        (eps < 0 raises, as the reference throws)
+    omp(A, b; max_residual, sparsity)     :88-91
+    gomp(A, b, l, k) / gomp(A, b, l, eps, k=M) / gomp(A, b, l; max_residual, sparsity=N)   :126-148
+    mp(A, b, k, x=spzeros(N))             :34-40
+
+Every call returns a `SparseVector` (length N, `nzind` strictly ascending, Float64 `nzval`
+even for a Float32 dictionary -- `spzeros(N)` at :76).  Indices are 0-based on the Python side;
+the Julia shim adds 1.  Additive: `b` may be an M x B matrix (one signal per column), in which
+case a list of B SparseVectors is returned -- the column-wise map of the single-signal call.
+
+There is no CPU fallback: all arithmetic happens in the CUDA library; if it is missing or no
+sm_100 device is present the call raises.  Nothing here imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_void_p
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+__all__ = [
+    "SparseVector", "Dictionary", "Batch", "omp", "gomp", "mp", "lib", "LIB_PATH", "CSB200Error",
+    "device_count", "F64", "F32", "ShardComm", "omp_sharded",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcsb200.so")
+
+F64, F32 = 0, 1
+NCCL_ID_BYTES = 128
+
+_STATUS_NAMES = {
+    0: "OK", -1: "INVALID_ARG", -2: "NEGATIVE_EPS", -3: "NONFINITE_INPUT", -4: "CUDA", -5: "OOM",
+    -6: "UNSUPPORTED_ARCH", -7: "UNSUPPORTED", -8: "NCCL", -9: "DIM_MISMATCH",
+}
+
+
+class CSB200Error(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C compressedsensing.jl_b200/csrc`.  There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    i64p, f64p = POINTER(c_int64), POINTER(c_double)
+    sig = {
+        "csb200_version": (c_int, []),
+        "csb200_strerror": (c_char_p, [c_int]),
+        "csb200_last_error": (c_char_p, []),
+        "csb200_device_count": (c_int, []),
+        "csb200_dict_create": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, POINTER(c_void_p)]),
+        "csb200_dict_create_shard": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int64,
+                                             POINTER(c_void_p)]),
+        "csb200_dict_destroy": (c_int, [c_void_p]),
+        "csb200_dict_shape": (c_int, [c_void_p, i64p, i64p, POINTER(c_int), POINTER(c_int)]),
+        "csb200_batch_create": (c_int, [c_void_p, c_int64, c_int64, POINTER(c_void_p)]),
+        "csb200_batch_destroy": (c_int, [c_void_p]),
+        "csb200_batch_upload": (c_int, [c_void_p, c_void_p, c_int64, c_int64]),
+        "csb200_batch_upload_device": (c_int, [c_void_p, c_void_p, c_int64, c_int64]),
+        "csb200_batch_omp": (c_int, [c_void_p, c_int64, c_double]),
+        "csb200_batch_gomp": (c_int, [c_void_p, c_int64, c_int64, c_double]),
+        "csb200_batch_mp": (c_int, [c_void_p, c_int64, i64p, f64p, i64p, c_int64]),
+        "csb200_batch_download": (c_int, [c_void_p, c_int64, i64p, f64p, i64p, f64p, i64p]),
+        "csb200_batch_profile": (c_int, [c_void_p, c_int]),
+        "csb200_batch_corr_time": (c_int, [c_void_p, f64p, i64p, i64p]),
+        "csb200_batch_last_solve_ms": (c_int, [c_void_p, f64p]),
+        "csb200_omp": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_double, i64p, f64p, i64p, f64p, i64p]),
+        "csb200_gomp": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_double, i64p, f64p, i64p,
+                                f64p, i64p]),
+        "csb200_mp": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, i64p, f64p, i64p, c_int64, i64p, f64p,
+                              f64p]),
+        "csb200_comm_unique_id": (c_int, [c_void_p]),
+        "csb200_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
+        "csb200_comm_destroy": (c_int, [c_void_p]),
+        "csb200_omp_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, i64p, f64p, i64p, f64p, i64p,
+                                       f64p]),
+        "csb200_debug_corr_topk": (c_int, [c_void_p, c_int, c_int64, i64p, f64p]),
+        "csb200_debug_get_residual": (c_int, [c_void_p, c_void_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError here = the library does not export what csb200.h declares
+        fn.restype, fn.argtypes = res, args
+    return L
+
+
+lib = _load()
+EXPORTED_SYMBOLS = [
+    "csb200_version", "csb200_strerror", "csb200_last_error", "csb200_device_count", "csb200_dict_create",
+    "csb200_dict_create_shard", "csb200_dict_destroy", "csb200_dict_shape", "csb200_batch_create",
+    "csb200_batch_destroy", "csb200_batch_upload", "csb200_batch_upload_device", "csb200_batch_omp",
+    "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
+    "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp", "csb200_comm_unique_id",
+    "csb200_comm_create", "csb200_comm_destroy", "csb200_omp_sharded", "csb200_debug_corr_topk",
+    "csb200_debug_get_residual",
+]
+
+
+def _check(rc: int, eps: Optional[float] = None) -> None:
+    if rc == 0:
+        return
+    if rc == -2:
+        # the reference throws the String "ε = $ε has to be non-negative" (matchingpursuit.jl:74,127)
+        raise ValueError(f"ε = {eps} has to be non-negative")
+    detail = lib.csb200_last_error().decode() if rc in (-4, -5, -6, -7, -8, -1) else ""
+    msg = f"csb200: {lib.csb200_strerror(rc).decode()} [{_STATUS_NAMES.get(rc, rc)}]" + (f": {detail}" if detail else "")
+    if rc == -9:
+        raise ValueError(msg)          # Julia: DimensionMismatch
+    raise CSB200Error(rc, msg)
+
+
+def device_count() -> int:
+    n = lib.csb200_device_count()
+    if n < 0:
+        _check(n)
+    return n
+
+
+def _i64p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(POINTER(c_int64))
+
+
+def _f64p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(POINTER(c_double))
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SparseVector:
+    """Stand-in for Julia's `SparseVector{Float64,Int64}` (0-based `nzind`, ascending)."""
+    n: int
+    nzind: np.ndarray
+    nzval: np.ndarray
+
+    def nnz(self) -> int:
+        return int(self.nzind.size)
+
+    def dense(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.float64)
+        out[self.nzind] = self.nzval
+        return out
+
+    def __repr__(self) -> str:
+        return f"SparseVector(n={self.n}, nzind={self.nzind.tolist()}, nzval={self.nzval.tolist()})"
+
+
+def _as_matrix(A) -> np.ndarray:
+    A = np.asarray(A)
+    if A.ndim != 2:
+        raise ValueError("A must be a matrix")
+    if A.dtype not in (np.float64, np.float32):
+        A = A.astype(np.float64)                     # the shim copies anything that is not a strided Float32/64 matrix
+    return np.asfortranarray(A)
+
+
+class Dictionary:
+    """A dictionary resident on one B200 (`csb200_dict`).  Reuse it across solves to keep A in HBM/L2."""
+
+    def __init__(self, A, device: int = 0, n_offset: int = 0, n_total: Optional[int] = None):
+        A = _as_matrix(A)
+        self.M, self.N = int(A.shape[0]), int(A.shape[1])
+        self.dtype = A.dtype
+        self.device = device
+        self.n_offset = int(n_offset)
+        self.n_total = int(self.N if n_total is None else n_total)
+        h = c_void_p()
+        lda = A.strides[1] // A.itemsize if self.N > 1 else self.M
+        _check(lib.csb200_dict_create_shard(A.ctypes.data, self.M, self.N, max(lda, self.M),
+                                            F32 if A.dtype == np.float32 else F64, device, self.n_offset,
+                                            self.n_total, byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.csb200_dict_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class Batch:
+    """Device-resident solver state for up to `max_signals` right-hand sides (`csb200_batch`)."""
+
+    def __init__(self, dictionary: Dictionary, max_signals: int, max_sparsity: int):
+        self.dict = dictionary
+        self.max_signals, self.max_sparsity = int(max_signals), int(max_sparsity)
+        h = c_void_p()
+        _check(lib.csb200_batch_create(dictionary._h, self.max_signals, self.max_sparsity, byref(h)))
+        self._h = h
+        self.nsig = 0
+
+    def upload(self, B: np.ndarray) -> None:
+        B = self._signals(B)
+        self.nsig = B.shape[1]
+        _check(lib.csb200_batch_upload(self._h, B.ctypes.data, max(B.strides[1] // B.itemsize, B.shape[0]), self.nsig))
+
+    def upload_device(self, ptr: int, ldb: int, nsig: int) -> None:
+        self.nsig = int(nsig)
+        _check(lib.csb200_batch_upload_device(self._h, c_void_p(ptr), ldb, nsig))
+
+    def _signals(self, B) -> np.ndarray:
+        B = np.asarray(B)
+        if B.ndim == 1:
+            B = B.reshape(-1, 1)
+        if B.shape[0] != self.dict.M:
+            raise ValueError(f"DimensionMismatch: signal length {B.shape[0]} != {self.dict.M} rows of A")
+        return np.asfortranarray(B.astype(self.dict.dtype, copy=False))
+
+    def omp(self, k: int, eps: float) -> None:
+        _check(lib.csb200_batch_omp(self._h, int(k), float(eps)), eps)
+
+    def gomp(self, l: int, k: int, eps: float) -> None:
+        _check(lib.csb200_batch_gomp(self._h, int(l), int(k), float(eps)), eps)
+
+    def mp(self, iters: int, x0: Optional[Sequence[SparseVector]] = None) -> None:
+        if x0 is None:
+            _check(lib.csb200_batch_mp(self._h, int(iters), None, None, None, 0))
+            return
+        stride = max(1, max(v.nnz() for v in x0))
+        idx = np.zeros((self.nsig, stride), dtype=np.int64)
+        val = np.zeros((self.nsig, stride), dtype=np.float64)
+        nnz = np.zeros(self.nsig, dtype=np.int64)
+        for s, v in enumerate(x0):
+            nnz[s] = v.nnz()
+            idx[s, :v.nnz()] = v.nzind
+            val[s, :v.nnz()] = v.nzval
+        _check(lib.csb200_batch_mp(self._h, int(iters), _i64p(idx), _f64p(val), _i64p(nnz), stride))
+
+    def download(self, stride: int, want_coef: bool = True):
+        ns, stride = self.nsig, max(int(stride), 1)
+        sel = np.empty((ns, stride), dtype=np.int64)
+        coef = np.empty((ns, stride), dtype=np.float64) if want_coef else None
+        nnz = np.empty(ns, dtype=np.int64)
+        res = np.empty(ns, dtype=np.float64)
+        its = np.empty(ns, dtype=np.int64)
+        _check(lib.csb200_batch_download(self._h, stride, _i64p(sel), _f64p(coef), _i64p(nnz), _f64p(res), _i64p(its)))
+        return sel, coef, nnz, res, its
+
+    def profile(self, enable: bool) -> None:
+        _check(lib.csb200_batch_profile(self._h, 1 if enable else 0))
+
+    def corr_time(self):
+        ms, n, other = c_double(), c_int64(), c_int64()
+        _check(lib.csb200_batch_corr_time(self._h, byref(ms), byref(n), byref(other)))
+        return ms.value, n.value, other.value
+
+    def last_solve_ms(self) -> float:
+        ms = c_double()
+        _check(lib.csb200_batch_last_solve_ms(self._h, byref(ms)))
+        return ms.value
+
+    def debug_corr_topk(self, s: int, impl: int = 0):
+        idx = np.empty((self.nsig, s), dtype=np.int64)
+        val = np.empty((self.nsig, s), dtype=np.float64)
+        _check(lib.csb200_debug_corr_topk(self._h, impl, s, _i64p(idx), _f64p(val)))
+        return idx, val
+
+    def residual(self) -> np.ndarray:
+        out = np.empty((self.dict.M, self.nsig), dtype=self.dict.dtype, order="F")
+        _check(lib.csb200_debug_get_residual(self._h, out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.csb200_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+# ------------------------------------------------------------------------------------------------
+def _eps_of(dtype) -> float:
+    return float(np.finfo(np.dtype(dtype)).eps)
+
+
+def _dictionary(A, device):
+    if isinstance(A, Dictionary):
+        return A, False
+    return Dictionary(A, device=device), True
+
+
+def _to_sparse(n: int, sel_row: np.ndarray, coef_row: np.ndarray, nnz: int) -> SparseVector:
+    """Sort (index, coefficient) pairs ascending: the order `x[i] = NaN` keeps (`src/util.jl:120-122`)."""
+    idx, val = sel_row[:nnz], coef_row[:nnz]
+    order = np.argsort(idx, kind="stable")
+    return SparseVector(n, idx[order].astype(np.int64), val[order].astype(np.float64))
+
+
+def _solve(A, b, device, run, stride, merge=None):
+    b_arr = np.asarray(b)
+    single = b_arr.ndim == 1
+    D, owned = _dictionary(A, device)
+    try:
+        nsig = 1 if single else b_arr.shape[1]
+        with Batch(D, nsig, stride) as batch:
+            batch.upload(b_arr)
+            run(batch)
+            sel, coef, nnz, res, its = batch.download(stride)
+        if merge is not None:
+            out = [merge(D.n_total, sel[s], coef[s], int(nnz[s]), s) for s in range(nsig)]
+        else:
+            out = [_to_sparse(D.n_total, sel[s], coef[s], int(nnz[s])) for s in range(nsig)]
+    finally:
+        if owned:
+            D.close()
+    return out[0] if single else out
+
+
+def _is_int(v) -> bool:
+    return isinstance(v, (int, np.integer)) and not isinstance(v, bool)
+
+
+def omp(A, b, *args, max_residual=None, sparsity=None, device: int = 0):
+    """Orthogonal matching pursuit -- `omp` (`src/matchingpursuit.jl:73-91`).
+
+    omp(A, b, k) | omp(A, b, eps[, k]) | omp(A, b, max_residual=..., sparsity=...)
+    """
+    M, N = (A.M, A.n_total) if isinstance(A, Dictionary) else np.shape(A)
+    dt = A.dtype if isinstance(A, Dictionary) else (np.float32 if np.asarray(A).dtype == np.float32 else np.float64)
+    if len(args) == 1 and _is_int(args[0]):
+        eps, k = _eps_of(dt), int(args[0])                           # :84-86
+    elif len(args) >= 1:
+        eps, k = float(args[0]), (int(args[1]) if len(args) > 1 else M)   # :73
+    else:
+        eps = _eps_of(dt) if max_residual is None else float(max_residual)   # :88-91
+        k = min(M, N) if sparsity is None else int(sparsity)
+    if not eps >= 0:
+        raise ValueError(f"ε = {eps} has to be non-negative")
+    return _solve(A, b, device, lambda batch: batch.omp(k, eps), max(min(k, M, N), 1))
+
+
+def gomp(A, b, l: int, *args, max_residual=None, sparsity=None, device: int = 0):
+    """Generalized OMP, l atoms per update -- `gomp` (`src/matchingpursuit.jl:126-148`)."""
+    M, N = (A.M, A.n_total) if isinstance(A, Dictionary) else np.shape(A)
+    dt = A.dtype if isinstance(A, Dictionary) else (np.float32 if np.asarray(A).dtype == np.float32 else np.float64)
+    if len(args) == 1 and _is_int(args[0]):
+        eps, k = _eps_of(dt), int(args[0])                           # :141-143
+    elif len(args) >= 1:
+        eps, k = float(args[0]), (int(args[1]) if len(args) > 1 else M)   # :126
+    else:
+        eps = _eps_of(dt) if max_residual is None else float(max_residual)   # :145-148
+        k = N if sparsity is None else int(sparsity)
+    if not eps >= 0:
+        raise ValueError(f"ε = {eps} has to be non-negative")
+    return _solve(A, b, device, lambda batch: batch.gomp(int(l), k, eps), max(min(k, M, N), 1))
+
+
+def mp(A, b, k: int, x=None, device: int = 0):
+    """Matching pursuit, exactly k updates, optional warm start x -- `mp` (`src/matchingpursuit.jl:34-40`)."""
+    b_arr = np.asarray(b)
+    single = b_arr.ndim == 1
+    x0 = None
+    if x is not None:
+        x0 = [x] if isinstance(x, SparseVector) else list(x)
+
+    def merge(n, sel_row, coef_row, nnz, s):
+        # x[i] += <a_i, r> in iteration order (`:29`), starting from the warm start
+        acc = {}
+        if x0 is not None:
+            for i, v in zip(x0[s].nzind.tolist(), x0[s].nzval.tolist()):
+                acc[i] = v
+        for i, c in zip(sel_row[:nnz].tolist(), coef_row[:nnz].tolist()):
+            if i >= 0:
+                acc[i] = acc.get(i, 0.0) + c
+        idx = np.array(sorted(acc), dtype=np.int64)
+        return SparseVector(n, idx, np.array([acc[i] for i in idx.tolist()], dtype=np.float64))
+
+    return _solve(A, b, device, lambda batch: batch.mp(int(k), x0), max(int(k), 1), merge=merge)
+
+
+# ------------------------------------------------------------------------------------------------
+class ShardComm:
+    """NCCL communicator owned by the library (`csb200_comm`), one per process/GPU."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
+        _check(lib.csb200_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, unique_id: bytes, rank: int, nranks: int, device: int):
+        h = c_void_p()
+        buf = ctypes.create_string_buffer(unique_id, NCCL_ID_BYTES)
+        _check(lib.csb200_comm_create(buf, rank, nranks, device, byref(h)))
+        self._h, self.rank, self.nranks = h, rank, nranks
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.csb200_comm_destroy(self._h)
+            self._h = None
+
+
+def omp_sharded(shard: Dictionary, comm: ShardComm, b, k: int, eps: Optional[float] = None):
+    """Single-signal `omp` on a column-sharded dictionary; every rank returns the same SparseVector."""
+    eps = _eps_of(shard.dtype) if eps is None else float(eps)
+    b = np.ascontiguousarray(np.asarray(b, dtype=shard.dtype))
+    if b.shape != (shard.M,):
+        raise ValueError(f"DimensionMismatch: signal length {b.shape} != {shard.M} rows of A")
+    sel = np.empty(max(k, 1), dtype=np.int64)
+    coef = np.empty(max(k, 1), dtype=np.float64)
+    nnz, its = np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int64)
+    res, ms = np.zeros(1, dtype=np.float64), np.zeros(1, dtype=np.float64)
+    _check(lib.csb200_omp_sharded(shard._h, comm._h, b.ctypes.data, int(k), eps, _i64p(sel), _f64p(coef), _i64p(nnz),
+                                  _f64p(res), _i64p(its), _f64p(ms)), eps)
+    x = _to_sparse(shard.n_total, sel, coef, int(nnz[0]))
+    return x, {"resnorm": float(res[0]), "iters": int(its[0]), "corr_ms": float(ms[0]), "order": sel[:int(nnz[0])].copy()}

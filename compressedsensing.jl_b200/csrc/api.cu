@@ -1,0 +1,676 @@
+// C ABI of libcsb200.so (see include/csb200.h): handles, host<->device plumbing and the
+// iteration driver that sequences the kernels of one greedy-pursuit solve.
+//
+// One solve = reset, then per reference `update!` one correlation pass (corr_gemm_f64.cu for
+// FP64 batches, corr_gemv.cu otherwise) followed by one per-signal state update (update.cu),
+// all enqueued on the batch's stream with no host round trip; the host blocks once at the end.
+#include "../../include/csb200.h"
+#include "common.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace csb;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail_cuda(cudaError_t e, const char* what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    g_last_error = buf;
+    cudaGetLastError();   // clear sticky-less error state
+    return e == cudaErrorMemoryAllocation ? CSB200_ERR_OOM : CSB200_ERR_CUDA;
+}
+#define CU_TRY(expr)                                              \
+    do {                                                          \
+        cudaError_t e__ = (expr);                                 \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #expr);     \
+    } while (0)
+
+int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2-D FP64 tensor map over a column-major (ld x ncols) matrix: box = 16 rows (128 B) x 128 columns,
+// SWIZZLE_128B -- the operand tiles of corr_gemm_f64.cu.
+int make_operand_map(CUtensorMap* map, void* base, int64_t ld, int64_t ncols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { g_last_error = "cuTensorMapEncodeTiled entry point not found"; return CSB200_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)(ncols > 0 ? ncols : 1)};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {16, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        g_last_error = buf;
+        return CSB200_ERR_CUDA;
+    }
+    return CSB200_OK;
+}
+
+enum CorrImpl { IMPL_AUTO = 0, IMPL_GEMM = 1, IMPL_GEMV = 2, IMPL_NAIVE = 3 };
+constexpr int GEMM_MIN_SIGNALS = 24;   // below this the per-signal GEMV passes win over a padded 128-wide tile
+
+}  // namespace
+
+struct csb200_dict {
+    int device = 0;
+    int dtype = CSB200_F64;
+    int64_t M = 0, N = 0, ld = 0, n_offset = 0, n_total = 0;
+    void* dA = nullptr;
+    CUtensorMap mapA;
+    bool has_map = false;
+    int num_sms = 148;
+    std::mutex mu;
+    size_t esize() const { return dtype == CSB200_F32 ? 4 : 8; }
+};
+
+struct csb200_batch {
+    csb200_dict* dict = nullptr;
+    int64_t cap_sig = 0, kcap = 0, nsig = 0;
+    void *dB = nullptr, *dR = nullptr;
+    CUtensorMap mapR;
+    bool has_map = false;
+    double* pval = nullptr;
+    int* pidx = nullptr;
+    size_t pcap = 0;            // candidate slots allocated
+    int* nnz = nullptr; int* sel = nullptr; double* Rf = nullptr; double* z = nullptr; double* x = nullptr;
+    double* resnorm = nullptr; int* iters = nullptr; int* done = nullptr; int* flags = nullptr;
+    int* dflag = nullptr;       // non-finite scan result
+    cudaStream_t stream = nullptr;
+    bool profile = false;
+    std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
+    size_t ev_used = 0;
+    int64_t other_launches = 0;
+    cudaEvent_t ev_solve0 = nullptr, ev_solve1 = nullptr;   // bracket the last solve
+    bool solve_timed = false;
+    int corr_impl_env = IMPL_AUTO;
+    std::mutex mu;
+};
+
+namespace {
+
+void free_batch_mem(csb200_batch* b) {
+    cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->nnz); cudaFree(b->sel);
+    cudaFree(b->Rf); cudaFree(b->z); cudaFree(b->x); cudaFree(b->resnorm); cudaFree(b->iters); cudaFree(b->done);
+    cudaFree(b->flags); cudaFree(b->dflag);
+    for (auto e : b->ev) cudaEventDestroy(e);
+    if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
+    if (b->ev_solve1) cudaEventDestroy(b->ev_solve1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+}
+
+int ensure_partials(csb200_batch* b, int64_t P, int64_t S) {
+    const size_t need = (size_t)b->cap_sig * (size_t)P * (size_t)S;
+    if (need <= b->pcap) return CSB200_OK;
+    cudaFree(b->pval); cudaFree(b->pidx);
+    b->pval = nullptr; b->pidx = nullptr; b->pcap = 0;
+    CU_TRY(cudaMalloc(&b->pval, need * sizeof(double)));
+    CU_TRY(cudaMalloc(&b->pidx, need * sizeof(int)));
+    b->pcap = need;
+    return CSB200_OK;
+}
+
+int ensure_factor(csb200_batch* b) {
+    if (b->Rf) return CSB200_OK;
+    CU_TRY(cudaMalloc(&b->Rf, (size_t)b->cap_sig * b->kcap * b->kcap * sizeof(double)));
+    return CSB200_OK;
+}
+
+StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_done) {
+    csb200_dict* d = b->dict;
+    StateArgs a;
+    a.A = d->dA; a.B = b->dB; a.R = b->dR;
+    a.M = (int)d->M; a.ld = (int)d->ld; a.N = (int)d->N; a.nsig = (int)b->nsig; a.kcap = (int)b->kcap;
+    a.S = S; a.P = (int)((d->N + PBLK - 1) / PBLK); a.take = take; a.idx_offset = (int)d->n_offset;
+    a.ignore_done = ignore_done; a.eps = eps;
+    a.pval = b->pval; a.pidx = b->pidx; a.nnz = b->nnz; a.sel = b->sel; a.Rf = b->Rf; a.z = b->z; a.x = b->x;
+    a.resnorm = b->resnorm; a.iters = b->iters; a.done = b->done; a.flags = b->flags;
+    return a;
+}
+
+// One correlation pass over the current residuals, leaving top-S candidates per (atom block, signal).
+int run_corr(csb200_batch* b, int S, int impl) {
+    csb200_dict* d = b->dict;
+    const bool f32 = d->dtype == CSB200_F32;
+    const int64_t P = (d->N + PBLK - 1) / PBLK;
+    int rc = ensure_partials(b, P, S);
+    if (rc) return rc;
+    CorrArgs c;
+    c.A = d->dA; c.R = b->dR; c.M = (int)d->M; c.ld = (int)d->ld; c.N = (int)d->N; c.nsig = (int)b->nsig;
+    c.S = S; c.P = (int)P; c.idx_offset = (int)d->n_offset; c.pval = b->pval; c.pidx = b->pidx;
+    if (impl == IMPL_AUTO) impl = b->corr_impl_env;
+    if (impl == IMPL_AUTO) impl = (!f32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
+    if (impl == IMPL_GEMM && (f32 || !d->has_map || !b->has_map)) {
+        g_last_error = "DMMA GEMM path needs an FP64 dictionary";
+        return CSB200_ERR_UNSUPPORTED;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (b->profile) {
+        if (b->ev_used + 2 > b->ev.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); b->ev.push_back(e); }
+        }
+        e0 = b->ev[b->ev_used]; e1 = b->ev[b->ev_used + 1]; b->ev_used += 2;
+        CU_TRY(cudaEventRecord(e0, b->stream));
+    }
+    cudaError_t e;
+    if (impl == IMPL_GEMM) e = launch_corr_gemm_f64(&d->mapA, &b->mapR, c, d->num_sms, b->stream);
+    else if (impl == IMPL_GEMV) e = launch_corr_gemv(c, f32, b->stream);
+    else e = launch_corr_naive(c, f32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "correlation kernel launch");
+    if (b->profile) CU_TRY(cudaEventRecord(e1, b->stream));
+    return CSB200_OK;
+}
+
+int begin_solve(csb200_batch* b) {
+    b->solve_timed = false;
+    CU_TRY(cudaEventRecord(b->ev_solve0, b->stream));
+    return CSB200_OK;
+}
+
+int finish(csb200_batch* b, bool solve = false) {
+    if (solve) { CU_TRY(cudaEventRecord(b->ev_solve1, b->stream)); }
+    cudaError_t e = cudaStreamSynchronize(b->stream);
+    if (e == cudaSuccess && solve) b->solve_timed = true;
+    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+    return CSB200_OK;
+}
+
+int check_ready(csb200_batch* b) {
+    if (!b) return CSB200_ERR_INVALID_ARG;
+    if (b->nsig <= 0) { g_last_error = "no signals uploaded"; return CSB200_ERR_INVALID_ARG; }
+    return CSB200_OK;
+}
+
+int set_device(const csb200_dict* d) {
+    CU_TRY(cudaSetDevice(d->device));
+    return CSB200_OK;
+}
+
+int scan_nonfinite(csb200_batch* b, const void* p, size_t n, bool f32, cudaStream_t st, int* dflag) {
+    CU_TRY(cudaMemsetAsync(dflag, 0, sizeof(int), st));
+    cudaError_t e = launch_nonfinite_check(p, n, f32, dflag, st);
+    if (e != cudaSuccess) return fail_cuda(e, "nonfinite check");
+    int h = 0;
+    CU_TRY(cudaMemcpyAsync(&h, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    (void)b;
+    return h ? CSB200_ERR_NONFINITE_INPUT : CSB200_OK;
+}
+
+int after_upload(csb200_batch* b, int64_t nsig) {
+    csb200_dict* d = b->dict;
+    b->nsig = nsig;
+    if (d->dtype == CSB200_F64) {
+        int rc = make_operand_map(&b->mapR, b->dR, d->ld, nsig);
+        if (rc) return rc;
+        b->has_map = true;
+    }
+    int rc = scan_nonfinite(b, b->dB, (size_t)d->ld * nsig, d->dtype == CSB200_F32, b->stream, b->dflag);
+    if (rc) { b->nsig = 0; return rc; }
+    // r = b, counters cleared: the state a freshly constructed MP/OMP/GOMP object has
+    cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), d->dtype == CSB200_F32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    return finish(b);
+}
+
+}  // namespace
+
+extern "C" {
+
+int csb200_version(void) { return CSB200_VERSION; }
+
+const char* csb200_strerror(int status) {
+    switch (status) {
+        case CSB200_OK: return "ok";
+        case CSB200_ERR_INVALID_ARG: return "invalid argument";
+        case CSB200_ERR_NEGATIVE_EPS: return "eps has to be non-negative";
+        case CSB200_ERR_NONFINITE_INPUT: return "non-finite value in input";
+        case CSB200_ERR_CUDA: return "CUDA error";
+        case CSB200_ERR_OOM: return "out of device memory";
+        case CSB200_ERR_UNSUPPORTED_ARCH: return "device is not an sm_100 (B200-class) GPU";
+        case CSB200_ERR_UNSUPPORTED: return "unsupported shape or option";
+        case CSB200_ERR_NCCL: return "NCCL error";
+        case CSB200_ERR_DIM_MISMATCH: return "dimension mismatch";
+        default: return "unknown status";
+    }
+}
+
+const char* csb200_last_error(void) { return g_last_error.c_str(); }
+
+int csb200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    return n;
+}
+
+int csb200_dict_create_shard(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, int device,
+                             int64_t n_offset, int64_t n_total, csb200_dict** out) {
+    if (!A || !out || M <= 0 || N <= 0 || lda < M || (dtype != CSB200_F64 && dtype != CSB200_F32) || n_offset < 0 ||
+        n_total < n_offset + N)
+        return CSB200_ERR_INVALID_ARG;
+    if (N > (int64_t)INT_MAX - 256 || n_total > (int64_t)INT_MAX - 256 || M > (1 << 24)) return CSB200_ERR_UNSUPPORTED;
+    *out = nullptr;
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return CSB200_ERR_INVALID_ARG;
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        g_last_error = std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
+                       std::to_string(prop.minor) + "); this library contains sm_100a code only";
+        return CSB200_ERR_UNSUPPORTED_ARCH;
+    }
+    csb200_dict* d = new (std::nothrow) csb200_dict;
+    if (!d) return CSB200_ERR_OOM;
+    d->device = device; d->dtype = dtype; d->M = M; d->N = N; d->ld = round_up(M, ROW_ALIGN);
+    d->n_offset = n_offset; d->n_total = n_total; d->num_sms = prop.multiProcessorCount;
+    const size_t es = d->esize();
+    const size_t bytes = (size_t)d->ld * N * es;
+    cudaError_t e = cudaMalloc(&d->dA, bytes);
+    if (e != cudaSuccess) { delete d; return fail_cuda(e, "cudaMalloc(dictionary)"); }
+    int rc = CSB200_OK;
+    do {
+        if (d->ld != M) { e = cudaMemset(d->dA, 0, bytes); if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMemset"); break; } }
+        e = cudaMemcpy2D(d->dA, d->ld * es, A, lda * es, M * es, N, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMemcpy2D(dictionary)"); break; }
+        int* dflag = nullptr;
+        e = cudaMalloc(&dflag, sizeof(int));
+        if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMalloc"); break; }
+        rc = scan_nonfinite(nullptr, d->dA, (size_t)d->ld * N, dtype == CSB200_F32, nullptr, dflag);
+        cudaFree(dflag);
+        if (rc) break;
+        if (dtype == CSB200_F64) {
+            rc = make_operand_map(&d->mapA, d->dA, d->ld, N);
+            if (rc) break;
+            d->has_map = true;
+            e = corr_gemm_f64_setup();
+            if (e != cudaSuccess) { rc = fail_cuda(e, "cudaFuncSetAttribute(corr_gemm_f64)"); break; }
+        }
+    } while (0);
+    if (rc) { cudaFree(d->dA); delete d; return rc; }
+    *out = d;
+    return CSB200_OK;
+}
+
+int csb200_dict_create(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, int device, csb200_dict** out) {
+    return csb200_dict_create_shard(A, M, N, lda, dtype, device, 0, N, out);
+}
+
+int csb200_dict_destroy(csb200_dict* d) {
+    if (!d) return CSB200_OK;
+    cudaSetDevice(d->device);
+    cudaFree(d->dA);
+    delete d;
+    return CSB200_OK;
+}
+
+int csb200_dict_shape(const csb200_dict* d, int64_t* M, int64_t* N, int* dtype, int* device) {
+    if (!d) return CSB200_ERR_INVALID_ARG;
+    if (M) *M = d->M;
+    if (N) *N = d->N;
+    if (dtype) *dtype = d->dtype;
+    if (device) *device = d->device;
+    return CSB200_OK;
+}
+
+int csb200_batch_create(csb200_dict* d, int64_t max_signals, int64_t max_sparsity, csb200_batch** out) {
+    if (!d || !out || max_signals <= 0 || max_sparsity < 0) return CSB200_ERR_INVALID_ARG;
+    if (max_signals > (int64_t)INT_MAX / 2) return CSB200_ERR_UNSUPPORTED;
+    *out = nullptr;
+    int rc = set_device(d);
+    if (rc) return rc;
+    csb200_batch* b = new (std::nothrow) csb200_batch;
+    if (!b) return CSB200_ERR_OOM;
+    b->dict = d; b->cap_sig = max_signals;
+    b->kcap = max_sparsity < 1 ? 1 : max_sparsity;
+    const char* env = getenv("CSB200_CORR_IMPL");
+    if (env) {
+        if (!strcmp(env, "gemm")) b->corr_impl_env = IMPL_GEMM;
+        else if (!strcmp(env, "gemv")) b->corr_impl_env = IMPL_GEMV;
+        else if (!strcmp(env, "naive")) b->corr_impl_env = IMPL_NAIVE;
+    }
+    const size_t es = d->esize(), ns = (size_t)max_signals, kc = (size_t)b->kcap;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    alloc(&b->dB, (size_t)d->ld * ns * es);
+    alloc(&b->dR, (size_t)d->ld * ns * es);
+    alloc((void**)&b->nnz, ns * sizeof(int));
+    alloc((void**)&b->sel, ns * kc * sizeof(int));
+    alloc((void**)&b->z, ns * kc * sizeof(double));
+    alloc((void**)&b->x, ns * kc * sizeof(double));
+    alloc((void**)&b->resnorm, ns * sizeof(double));
+    alloc((void**)&b->iters, ns * sizeof(int));
+    alloc((void**)&b->done, ns * sizeof(int));
+    alloc((void**)&b->flags, ns * sizeof(int));
+    alloc((void**)&b->dflag, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_solve0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev_solve1);
+    if (e != cudaSuccess) { rc = fail_cuda(e, "batch allocation"); free_batch_mem(b); delete b; return rc; }
+    *out = b;
+    return CSB200_OK;
+}
+
+int csb200_batch_destroy(csb200_batch* b) {
+    if (!b) return CSB200_OK;
+    cudaSetDevice(b->dict->device);
+    cudaStreamSynchronize(b->stream);
+    free_batch_mem(b);
+    delete b;
+    return CSB200_OK;
+}
+
+static int upload_common(csb200_batch* b, const void* src, int64_t ldb, int64_t nsig, cudaMemcpyKind kind) {
+    if (!b || !src || nsig <= 0) return CSB200_ERR_INVALID_ARG;
+    csb200_dict* d = b->dict;
+    if (ldb < d->M) return CSB200_ERR_DIM_MISMATCH;
+    if (nsig > b->cap_sig) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    int rc = set_device(d);
+    if (rc) return rc;
+    const size_t es = d->esize();
+    if (d->ld != d->M) CU_TRY(cudaMemsetAsync(b->dB, 0, (size_t)d->ld * nsig * es, b->stream));
+    CU_TRY(cudaMemcpy2DAsync(b->dB, d->ld * es, src, ldb * es, d->M * es, nsig, kind, b->stream));
+    return after_upload(b, nsig);
+}
+
+int csb200_batch_upload(csb200_batch* b, const void* Bmat, int64_t ldb, int64_t nsig) {
+    return upload_common(b, Bmat, ldb, nsig, cudaMemcpyHostToDevice);
+}
+int csb200_batch_upload_device(csb200_batch* b, const void* dBmat, int64_t ldb, int64_t nsig) {
+    return upload_common(b, dBmat, ldb, nsig, cudaMemcpyDeviceToDevice);
+}
+
+int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (k < 0) return CSB200_ERR_INVALID_ARG;
+    if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    csb200_dict* d = b->dict;
+    int64_t need = k < d->M ? k : d->M;
+    if (d->n_total < need) need = d->n_total;
+    if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(d))) return rc;
+    if ((rc = ensure_factor(b))) return rc;
+    const bool f32 = d->dtype == CSB200_F32;
+    if ((rc = begin_solve(b))) return rc;
+    cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    for (int64_t it = 0; it < k; ++it) {
+        if ((rc = run_corr(b, 1, IMPL_AUTO))) return rc;
+        e = launch_omp_update(state_args(b, 1, 1, eps, 0), f32, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "omp_update");
+        b->other_launches++;
+    }
+    return finish(b, true);
+}
+
+int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    csb200_dict* d = b->dict;
+    if (k < 0 || l < 1 || l > d->n_total) return CSB200_ERR_INVALID_ARG;
+    if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    if (l > MAX_S) { g_last_error = "l > 64 atoms per update is not supported by the fused top-s epilogue"; return CSB200_ERR_UNSUPPORTED; }
+    int64_t need = k < d->M ? k : d->M;
+    if (d->n_total < need) need = d->n_total;
+    if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(d))) return rc;
+    if ((rc = ensure_factor(b))) return rc;
+    const bool f32 = d->dtype == CSB200_F32;
+    if ((rc = begin_solve(b))) return rc;
+    cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    for (int64_t it = 0; it < k / l; ++it) {
+        if ((rc = run_corr(b, (int)l, IMPL_AUTO))) return rc;
+        e = launch_omp_update(state_args(b, (int)l, (int)l, eps, 0), f32, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "gomp_update");
+        b->other_launches++;
+    }
+    const int rem = (int)(k % l);
+    if (rem > 0) {                                   // runs even after an eps-break (matchingpursuit.jl:134-137)
+        if ((rc = run_corr(b, rem, IMPL_AUTO))) return rc;
+        e = launch_omp_update(state_args(b, rem, rem, eps, 1), f32, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "gomp_update(rem)");
+        b->other_launches++;
+    }
+    return finish(b, true);
+}
+
+int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const double* x0_val,
+                    const int64_t* x0_nnz, int64_t x0_stride) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (iters < 0) return CSB200_ERR_INVALID_ARG;
+    if (iters > b->kcap) { g_last_error = "iters exceeds the batch's max_sparsity (history slots)"; return CSB200_ERR_INVALID_ARG; }
+    csb200_dict* d = b->dict;
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(d))) return rc;
+    const bool f32 = d->dtype == CSB200_F32;
+    if ((rc = begin_solve(b))) return rc;
+    cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), f32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    int *d_idx = nullptr, *d_nnz = nullptr;
+    double* d_val = nullptr;
+    if (x0_idx && x0_val && x0_nnz && x0_stride > 0) {
+        const size_t n = (size_t)b->nsig * x0_stride;
+        std::vector<int> hi(n, 0), hn(b->nsig);
+        for (int64_t s = 0; s < b->nsig; ++s) {
+            if (x0_nnz[s] < 0 || x0_nnz[s] > x0_stride) return CSB200_ERR_INVALID_ARG;
+            hn[s] = (int)x0_nnz[s];
+            for (int64_t j = 0; j < x0_nnz[s]; ++j) {
+                const int64_t v = x0_idx[s * x0_stride + j];
+                if (v < d->n_offset || v >= d->n_offset + d->N) return CSB200_ERR_INVALID_ARG;
+                hi[s * x0_stride + j] = (int)v;
+            }
+        }
+        CU_TRY(cudaMalloc(&d_idx, n * sizeof(int)));
+        CU_TRY(cudaMalloc(&d_val, n * sizeof(double)));
+        CU_TRY(cudaMalloc(&d_nnz, b->nsig * sizeof(int)));
+        CU_TRY(cudaMemcpyAsync(d_idx, hi.data(), n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+        CU_TRY(cudaMemcpyAsync(d_val, x0_val, n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CU_TRY(cudaMemcpyAsync(d_nnz, hn.data(), b->nsig * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+        e = launch_mp_warmstart(state_args(b, 1, 1, 0.0, 0), f32, d_idx, d_val, d_nnz, (int)x0_stride, b->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+        cudaFree(d_idx); cudaFree(d_val); cudaFree(d_nnz);
+        if (e != cudaSuccess) return fail_cuda(e, "mp_warmstart");
+    }
+    for (int64_t it = 0; it < iters; ++it) {
+        if ((rc = run_corr(b, 1, IMPL_AUTO))) return rc;
+        e = launch_mp_update(state_args(b, 1, 1, 0.0, 0), f32, (int)it, (int)b->kcap, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "mp_update");
+        b->other_launches++;
+    }
+    return finish(b, true);
+}
+
+int csb200_batch_download(csb200_batch* b, int64_t stride, int64_t* sel_idx, double* coef, int64_t* nnz,
+                          double* resnorm, int64_t* iters) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (stride < 0) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(b->dict))) return rc;
+    const size_t ns = (size_t)b->nsig, kc = (size_t)b->kcap;
+    std::vector<int> hn(ns), hs, hit;
+    std::vector<double> hx;
+    CU_TRY(cudaMemcpyAsync(hn.data(), b->nnz, ns * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    if (sel_idx) { hs.resize(ns * kc); CU_TRY(cudaMemcpyAsync(hs.data(), b->sel, ns * kc * sizeof(int), cudaMemcpyDeviceToHost, b->stream)); }
+    if (coef) { hx.resize(ns * kc); CU_TRY(cudaMemcpyAsync(hx.data(), b->x, ns * kc * sizeof(double), cudaMemcpyDeviceToHost, b->stream)); }
+    if (iters) { hit.resize(ns); CU_TRY(cudaMemcpyAsync(hit.data(), b->iters, ns * sizeof(int), cudaMemcpyDeviceToHost, b->stream)); }
+    if (resnorm) CU_TRY(cudaMemcpyAsync(resnorm, b->resnorm, ns * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    for (size_t s = 0; s < ns; ++s) {
+        const int64_t t = hn[s];
+        if (t > stride && (sel_idx || coef)) { g_last_error = "stride smaller than a signal's support"; return CSB200_ERR_INVALID_ARG; }
+        if (nnz) nnz[s] = t;
+        if (iters) iters[s] = hit[s];
+        for (int64_t j = 0; j < stride; ++j) {
+            if (sel_idx) sel_idx[s * stride + j] = j < t ? (int64_t)hs[s * kc + j] : -1;
+            if (coef) coef[s * stride + j] = j < t ? hx[s * kc + j] : 0.0;
+        }
+    }
+    return CSB200_OK;
+}
+
+int csb200_batch_profile(csb200_batch* b, int enable) {
+    if (!b) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    b->profile = enable != 0;
+    b->ev_used = 0;
+    b->other_launches = 0;
+    return CSB200_OK;
+}
+
+int csb200_batch_corr_time(csb200_batch* b, double* total_ms, int64_t* launches, int64_t* other_launches) {
+    if (!b) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    int rc = set_device(b->dict);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < b->ev_used; i += 2) {
+        float ms = 0.f;
+        CU_TRY(cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = (int64_t)(b->ev_used / 2);
+    if (other_launches) *other_launches = b->other_launches;
+    return CSB200_OK;
+}
+
+int csb200_batch_last_solve_ms(csb200_batch* b, double* ms) {
+    if (!b || !ms) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    if (!b->solve_timed) { g_last_error = "no completed solve on this batch"; return CSB200_ERR_INVALID_ARG; }
+    int rc = set_device(b->dict);
+    if (rc) return rc;
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, b->ev_solve0, b->ev_solve1));
+    *ms = f;
+    return CSB200_OK;
+}
+
+// ---- one-shot host-buffer entry points ---------------------------------------------------------
+static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t kcap, csb200_batch** out) {
+    if (!d || !Bmat || nsig <= 0) return CSB200_ERR_INVALID_ARG;
+    int64_t cap = kcap < d->M ? kcap : d->M;
+    if (d->n_total < cap) cap = d->n_total;
+    int rc = csb200_batch_create(d, nsig, cap, out);
+    if (rc) return rc;
+    rc = csb200_batch_upload(*out, Bmat, ldb, nsig);
+    if (rc) { csb200_batch_destroy(*out); *out = nullptr; }
+    return rc;
+}
+
+int csb200_omp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double eps,
+               int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
+    if (k < 0) return CSB200_ERR_INVALID_ARG;
+    if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    csb200_batch* b = nullptr;
+    int rc = one_shot(d, Bmat, ldb, nsig, k, &b);
+    if (rc) return rc;
+    rc = csb200_batch_omp(b, k, eps);
+    if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
+    csb200_batch_destroy(b);
+    return rc;
+}
+
+int csb200_gomp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t l, int64_t k, double eps,
+                int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
+    if (k < 0 || l < 1) return CSB200_ERR_INVALID_ARG;
+    if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    csb200_batch* b = nullptr;
+    int rc = one_shot(d, Bmat, ldb, nsig, k, &b);
+    if (rc) return rc;
+    rc = csb200_batch_gomp(b, l, k, eps);
+    if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
+    csb200_batch_destroy(b);
+    return rc;
+}
+
+int csb200_mp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k, const int64_t* x0_idx,
+              const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride, int64_t* sel_idx, double* coef,
+              double* resnorm) {
+    if (iters_k < 0) return CSB200_ERR_INVALID_ARG;
+    if (!d || !Bmat || nsig <= 0) return CSB200_ERR_INVALID_ARG;
+    csb200_batch* b = nullptr;
+    int rc = csb200_batch_create(d, nsig, iters_k, &b);
+    if (rc) return rc;
+    rc = csb200_batch_upload(b, Bmat, ldb, nsig);
+    if (!rc) rc = csb200_batch_mp(b, iters_k, x0_idx, x0_val, x0_nnz, x0_stride);
+    if (!rc) rc = csb200_batch_download(b, iters_k, sel_idx, coef, nullptr, resnorm, nullptr);
+    csb200_batch_destroy(b);
+    return rc;
+}
+
+// ---- test / debug hooks ------------------------------------------------------------------------
+int csb200_debug_corr_topk(csb200_batch* b, int impl, int64_t s, int64_t* idx, double* val) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (!idx || !val || s < 1 || s > MAX_S || impl < 0 || impl > 3) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(b->dict))) return rc;
+    if ((rc = run_corr(b, (int)s, impl))) return rc;
+    long long* d_idx = nullptr;
+    double* d_val = nullptr;
+    const size_t n = (size_t)b->nsig * s;
+    CU_TRY(cudaMalloc(&d_idx, n * sizeof(long long)));
+    CU_TRY(cudaMalloc(&d_val, n * sizeof(double)));
+    cudaError_t e = launch_topk_from_partials(state_args(b, (int)s, (int)s, 0.0, 0), (int)s, d_idx, d_val, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_idx, n * sizeof(long long), cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(val, d_val, n * sizeof(double), cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    cudaFree(d_idx); cudaFree(d_val);
+    if (e != cudaSuccess) return fail_cuda(e, "debug_corr_topk");
+    return CSB200_OK;
+}
+
+int csb200_debug_get_residual(csb200_batch* b, void* out) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (!out) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    csb200_dict* d = b->dict;
+    if ((rc = set_device(d))) return rc;
+    const size_t es = d->esize();
+    CU_TRY(cudaMemcpy2DAsync(out, d->M * es, b->dR, d->ld * es, d->M * es, b->nsig, cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    return CSB200_OK;
+}
+
+// ---- column-sharded mode: implemented in sharded.cu ---------------------------------------------
+
+}  // extern "C"

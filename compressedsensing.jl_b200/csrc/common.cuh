@@ -1,0 +1,77 @@
+// Shared declarations for libcsb200 (B200 / sm_100a greedy pursuit).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+
+namespace csb {
+
+// Atoms are grouped in blocks of PBLK for the fused |c| top-s epilogue: every correlation
+// kernel emits, per (atom block, signal), the top-s candidates of that block.  One record
+// per candidate: |c| as double (FP32 dictionaries widen) and the GLOBAL 0-based atom index.
+constexpr int PBLK = 64;
+constexpr int MAX_S = 64;          // atoms per gomp update handled by the fused epilogue
+constexpr int ROW_ALIGN = 16;      // leading dimensions are padded to 16 elements (128 B for f64)
+
+// Candidate order shared by every kernel: larger |c| first, lower index on ties
+// (Julia `argmax` = first maximal index, src/matchingpursuit.jl:184;
+//  `partialsortperm(.., rev=true)` = Base.Order.Perm tie-break, :192).
+__host__ __device__ __forceinline__ bool cand_better(double v, int i, double bv, int bi) {
+    return (v > bv) || (v == bv && i < bi);
+}
+
+struct CorrArgs {
+    const void* A;       // dictionary, ld x N
+    const void* R;       // residuals,  ld x nsig
+    int M, ld, N, nsig;
+    int S;               // candidates per atom block
+    int P;               // number of atom blocks = ceil(N / PBLK)
+    int idx_offset;      // global index of this shard's first atom
+    double* pval;        // [nsig][P][S]
+    int* pidx;           // [nsig][P][S]
+};
+
+// correlation kernels (corr_gemm_f64.cu, corr_gemv.cu)
+cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* mapR, const CorrArgs& a,
+                                 int num_sms, cudaStream_t st);
+cudaError_t corr_gemm_f64_setup();   // one-time cudaFuncSetAttribute
+cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st);
+cudaError_t launch_corr_naive(const CorrArgs& a, bool f32, cudaStream_t st);
+
+// per-signal state (update.cu)
+struct StateArgs {
+    const void* A;        // ld x N
+    const void* B;        // ld x nsig   right-hand sides
+    void* R;              // ld x nsig   residuals (output)
+    int M, ld, N, nsig, kcap;
+    int S;                // candidates stored per atom block in pval/pidx
+    int P;
+    int take;             // atoms to append in this update (1 for omp, l or k%l for gomp)
+    int idx_offset;       // this shard's first atom (A is indexed with global index - idx_offset)
+    int ignore_done;      // gomp remainder step runs even after an eps-break (matchingpursuit.jl:134-137)
+    double eps;
+    const double* pval;   // [nsig][P][S]
+    const int* pidx;
+    int* nnz;             // [nsig]
+    int* sel;             // [nsig][kcap]  support in selection order (global atom index)
+    double* Rf;           // [nsig][kcap*kcap] column-major upper-triangular factor (append order)
+    double* z;            // [nsig][kcap]  Q'b
+    double* x;            // [nsig][kcap]  coefficients aligned with sel
+    double* resnorm;      // [nsig]
+    int* iters;           // [nsig]
+    int* done;            // [nsig]  eps-break flag
+    int* flags;           // [nsig]  bit0: dependent atom skipped, bit1: no candidate
+};
+// Acache (optional): ld x kcap buffer holding the active atoms' columns in selection order, with the
+// candidate's column already stored in slot nnz (column-sharded mode: the atom may live on a peer).
+cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache = nullptr);
+cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st);
+cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);
+cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx, const double* x0_val,
+                                const int* x0_nnz, int x0_stride, cudaStream_t st);
+cudaError_t launch_topk_from_partials(const StateArgs& a, int s, long long* out_idx, double* out_val,
+                                      cudaStream_t st);
+cudaError_t launch_nonfinite_check(const void* p, size_t n, bool f32, int* flag, cudaStream_t st);
+
+}  // namespace csb

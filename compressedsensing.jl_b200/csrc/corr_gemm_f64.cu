@@ -1,0 +1,217 @@
+// Batched residual correlation  C = A' R  (FP64) with the |c| top-s selection fused into the
+// epilogue -- subsystems (1)+(2) of the north star for the many-signal path.
+//
+// Replaces, for B signals at once, `mul!(P.Ar, P.A', P.r); @. P.Ar = abs(P.Ar); argmax(P.Ar)` /
+// `partialsortperm(P.Ar, 1:k, rev=true)` (/root/reference/src/matchingpursuit.jl:181-193).
+// C (N x B doubles, 4 GiB at the headline config) is never written: each consumer warp reduces
+// its 64-atom x 32-signal accumulator block to the top-s (|c|, atom) records of that block.
+//
+// sm_100a design
+//   * tcgen05 has no f64 kind, so the FP64 tensor path is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4;
+//     ptxas lowers every wider f64 mma shape to it).  What is Blackwell/Hopper-class here is the
+//     data movement: both operands are K-contiguous (atoms and signals are columns), so one 2-D
+//     TMA box {16 doubles x 128 columns} per operand per k-chunk lands a 128 B-row, SWIZZLE_128B
+//     tile in shared memory; a dedicated producer warp runs a 4-stage mbarrier ring ahead of 8
+//     consumer warps, across tile boundaries (persistent CTAs, one per SM).
+//   * Fragment loads are LDS.128: lane (g = lane/4, q = lane%4) reads the 16 B chunk q of an
+//     8-double k-group for row g and feeds .x to one DMMA and .y to the next.  Both operands use
+//     the same k-permutation, so the contraction is unchanged, and with the 128 B swizzle the
+//     warp-wide 512 B request touches every bank exactly 4 times (the bandwidth floor).
+//   * CTA tile 128 atoms x 128 signals, warp tile 64 x 32 (64 accumulator doubles per thread):
+//     shared-memory traffic is 12 LDS.128 per 64 DMMA per warp, ~19 % of the LDS bandwidth at
+//     DMMA peak.  TMA zero-fills out-of-range rows/columns, so no shape padding is needed.
+#include "common.cuh"
+
+namespace csb {
+
+namespace {
+
+constexpr int TILE_N = 128;                 // atoms per CTA tile
+constexpr int TILE_B = 128;                 // signals per CTA tile
+constexpr int KCH = 16;                     // doubles per k-chunk: 128 B rows
+constexpr int STAGES = 4;
+constexpr int A_TILE_BYTES = TILE_N * KCH * 8;
+constexpr int R_TILE_BYTES = TILE_B * KCH * 8;
+constexpr int STAGE_BYTES = A_TILE_BYTES + R_TILE_BYTES;   // 32 KiB
+constexpr int CONSUMER_WARPS = 8;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__global__ void __maxnreg__(224)
+corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
+                     int N, int nsig, int kchunks, int tilesN, int tilesB, int S, int P, int idx_offset,
+                     double* __restrict__ pval, int* __restrict__ pidx) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+    uint8_t* sm = smem_raw + pad;                       // 1024 B aligned: required by SWIZZLE_128B
+    const uint32_t sm_base = smem_u32(sm);
+    const uint32_t bar_full = sm_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + STAGES * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = tilesN * tilesB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        // ------------------------------ TMA producer (one lane) ------------------------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapR) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int tn = tile % tilesN, tb = tile / tilesN;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(bar_empty + stage * 8, phase ^ 1u);
+                    mbar_arrive_expect_tx(bar_full + stage * 8, STAGE_BYTES);
+                    const uint32_t dst = sm_base + stage * STAGE_BYTES;
+                    tma_load_2d(dst, &mapA, bar_full + stage * 8, kc * KCH, tn * TILE_N);
+                    tma_load_2d(dst + A_TILE_BYTES, &mapR, bar_full + stage * 8, kc * KCH, tb * TILE_B);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- DMMA consumers -----------------------------------
+    const int wm = warp & 1;          // which 64-atom half of the tile
+    const int wn = warp >> 1;         // which 32-signal quarter
+    const int g = lane >> 2, q = lane & 3;
+    const uint32_t a_row = (uint32_t)(wm * 64 + g) * 128u;                   // + i*1024
+    const uint32_t r_row = (uint32_t)A_TILE_BYTES + (uint32_t)(wn * 32 + g) * 128u;   // + j*1024
+    int stage = 0;
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tn = tile % tilesN, tb = tile / tilesN;
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+        for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(bar_full + stage * 8, phase);
+            const uint8_t* st = sm + stage * STAGE_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t sw = (uint32_t)(((4 * h + q) ^ g) << 4);      // SWIZZLE_128B: chunk ^= row % 8
+                double2 af[8], bf[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) af[i] = *reinterpret_cast<const double2*>(st + a_row + i * 1024 + sw);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double2*>(st + r_row + j * 1024 + sw);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j], af[i].x, bf[j].x);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j], af[i].y, bf[j].y);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + stage * 8);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+
+        // ---- fused epilogue: top-S of |c| over this warp's 64 atoms, per signal column ----
+        // acc[i][j][e] = c[atom = wm*64 + i*8 + g][signal = wn*32 + j*8 + 2q + e]
+        const int atom0 = tn * TILE_N + wm * 64 + g;
+        const int p = tn * 2 + wm;
+        double pv[4][2];
+        int pi[4][2];
+        for (int s = 0; s < S; ++s) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double bv = -1.0;
+                    int bi = INT_MAX;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const double v = fabs(acc[i][j][e]);
+                        const int idx = atom0 + i * 8;
+                        bool ok = idx < N;
+                        if (s > 0) ok = ok && (v < pv[j][e] || (v == pv[j][e] && idx > pi[j][e]));
+                        if (ok && v > bv) { bv = v; bi = idx; }      // idx ascends with i: first max wins
+                    }
+#pragma unroll
+                    for (int off = 4; off < 32; off <<= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                    }
+                    pv[j][e] = bv;
+                    pi[j][e] = bi;
+                    const int sig = tb * TILE_B + wn * 32 + j * 8 + 2 * q + e;
+                    if (g == 0 && sig < nsig && p < P) {
+                        const size_t o = ((size_t)sig * P + p) * S + s;
+                        pval[o] = bv;
+                        pidx[o] = (bi == INT_MAX) ? -1 : bi + idx_offset;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t corr_gemm_f64_setup() {
+    return cudaFuncSetAttribute(corr_gemm_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* mapR, const CorrArgs& a,
+                                 int num_sms, cudaStream_t st) {
+    const int tilesN = (a.N + TILE_N - 1) / TILE_N;
+    const int tilesB = (a.nsig + TILE_B - 1) / TILE_B;
+    const long long ntiles = (long long)tilesN * tilesB;
+    if (ntiles <= 0) return cudaSuccess;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    corr_gemm_f64_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN, tilesB,
+                                                            a.S, a.P, a.idx_offset, a.pval, a.pidx);
+    return cudaGetLastError();
+}
+
+}  // namespace csb

@@ -1,0 +1,160 @@
+/* csb200.h -- C ABI of libcsb200.so: B200 (sm_100a) greedy pursuit (mp / omp / gomp).
+ *
+ * This is the drop-in boundary for the hot path of SebastianAment/CompressedSensing.jl.
+ * The reference has no FFI of its own (pure Julia over BLAS + UpdatableQRFactorizations);
+ * each entry point below replaces the Julia function cited next to it, and the Julia shim
+ * (compressedsensing.jl_b200/julia/CompressedSensingB200.jl) `ccall`s exactly these symbols.
+ * See INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *   - Plain C linkage, plain pointers and sizes; no C++/torch types; no exceptions escape.
+ *   - Matrices are column-major with a leading dimension in ELEMENTS (Julia `Matrix` layout:
+ *     each atom / each signal is one contiguous column).
+ *   - Indices crossing the boundary are 0-based int64; -1 pads unused slots.
+ *   - Every function returns CSB200_OK (0) or a negative csb200_status.
+ *   - The caller owns every host buffer; the library owns all device memory behind the
+ *     opaque handles.  Calls on different handles may run concurrently from different host
+ *     threads; calls on one handle are serialised internally.
+ *   - There is NO CPU fallback: without an sm_100 device the create calls fail with
+ *     CSB200_ERR_UNSUPPORTED_ARCH / CSB200_ERR_CUDA.
+ */
+#ifndef CSB200_H
+#define CSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSB200_VERSION 100 /* 0.1.0 */
+
+typedef enum csb200_status {
+    CSB200_OK = 0,
+    CSB200_ERR_INVALID_ARG = -1,      /* null pointer, negative size, k/l out of range            */
+    CSB200_ERR_NEGATIVE_EPS = -2,     /* eps < 0: the shim rethrows the reference's String
+                                         "ε = ... has to be non-negative" (matchingpursuit.jl:74,127) */
+    CSB200_ERR_NONFINITE_INPUT = -3,  /* NaN/Inf in A or b              */
+    CSB200_ERR_CUDA = -4,             /* a CUDA runtime call failed; csb200_last_error() has text */
+    CSB200_ERR_OOM = -5,              /* device allocation failed                                  */
+    CSB200_ERR_UNSUPPORTED_ARCH = -6, /* device is not compute capability 10.x                     */
+    CSB200_ERR_UNSUPPORTED = -7,      /* shape / option outside what this build handles            */
+    CSB200_ERR_NCCL = -8,             /* NCCL call failed (column-sharded mode)                    */
+    CSB200_ERR_DIM_MISMATCH = -9      /* signal length != rows of the dictionary (Julia: DimensionMismatch) */
+} csb200_status;
+
+typedef enum csb200_dtype { CSB200_F64 = 0, CSB200_F32 = 1 } csb200_dtype;
+
+typedef struct csb200_dict csb200_dict;   /* a dictionary A resident on one GPU                    */
+typedef struct csb200_batch csb200_batch; /* per-batch solver state (signals, residuals, QR, ...)  */
+
+int csb200_version(void);
+const char* csb200_strerror(int status);
+/* Text of the last CUDA/NCCL failure on the calling thread ("" if none). */
+const char* csb200_last_error(void);
+/* Number of visible CUDA devices, or a negative status. */
+int csb200_device_count(void);
+
+/* ---- dictionary ------------------------------------------------------------------------
+ * Replaces the `A` field captured by the constructors MP(A,b) / OMP(A,b,k) / GOMP(A,b,l)
+ * (src/matchingpursuit.jl:18-24, 54-60, 108-114).  A is M x N column-major (M rows =
+ * signal length, N atoms), lda >= M elements.  The dictionary is copied to `device`
+ * (HBM-resident for the life of the handle) and checked for NaN/Inf.
+ * n_offset / n_total describe a column shard: this handle holds atoms
+ * [n_offset, n_offset + N) of a dictionary with n_total atoms; pass 0 and N when unsharded.
+ */
+int csb200_dict_create(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, int device,
+                       csb200_dict** out);
+int csb200_dict_create_shard(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, int device,
+                             int64_t n_offset, int64_t n_total, csb200_dict** out);
+int csb200_dict_destroy(csb200_dict* dict);
+int csb200_dict_shape(const csb200_dict* dict, int64_t* M, int64_t* N, int* dtype, int* device);
+
+/* ---- batch state -----------------------------------------------------------------------
+ * One batch holds up to max_signals right-hand sides and, per signal, what the reference
+ * keeps in P.r, P.Ar, P.AiQR and x (src/matchingpursuit.jl:44-60): the residual, the
+ * support in selection order, the triangular factor of the active atoms, the coefficients.
+ * max_sparsity bounds the support size (the `k` of UpdatableQR(T, n, k), :58).
+ */
+int csb200_batch_create(csb200_dict* dict, int64_t max_signals, int64_t max_sparsity, csb200_batch** out);
+int csb200_batch_destroy(csb200_batch* batch);
+/* Copy nsig signals (columns of Bmat, M x nsig, ldb >= M elements, dict dtype) host -> device. */
+int csb200_batch_upload(csb200_batch* batch, const void* Bmat, int64_t ldb, int64_t nsig);
+/* Same, but Bmat is a DEVICE pointer on the dictionary's GPU (device -> device copy). */
+int csb200_batch_upload_device(csb200_batch* batch, const void* dBmat, int64_t ldb, int64_t nsig);
+
+/* Solve on the signals currently resident in the batch (no host<->device traffic).
+ *   omp  : src/matchingpursuit.jl:73-82   (k update!s, stop once ||r|| < eps; eps >= 0)
+ *   gomp : src/matchingpursuit.jl:126-139 (k / l update!s of l atoms, then one of k % l)
+ *   mp   : src/matchingpursuit.jl:34-40   (exactly `iters` update!s; optional warm start)
+ * Each call blocks until the device work has finished.
+ */
+int csb200_batch_omp(csb200_batch* batch, int64_t k, double eps);
+int csb200_batch_gomp(csb200_batch* batch, int64_t l, int64_t k, double eps);
+/* x0_*: optional warm start (may be NULL): x0_nnz[s] entries per signal, stored at
+ * x0_idx/x0_val[s * x0_stride + j] (0-based atom indices). */
+int csb200_batch_mp(csb200_batch* batch, int64_t iters, const int64_t* x0_idx, const double* x0_val,
+                    const int64_t* x0_nnz, int64_t x0_stride);
+
+/* Copy results device -> host.  `stride` = slots per signal in sel_idx / coef (>= the k or
+ * iters of the last solve).  Any output pointer may be NULL.
+ *   sel_idx[s*stride + j]  j-th atom appended for signal s, in SELECTION order (-1 padded).
+ *                          For mp: the atom chosen at iteration j (atoms may repeat).
+ *   coef[s*stride + j]     omp/gomp: least-squares coefficient of that atom;
+ *                          mp: the increment <a_i, r> added at iteration j (src/matchingpursuit.jl:29).
+ *   nnz[s]                 number of valid slots.
+ *   resnorm[s]             ||b - A x||_2 after the last update.
+ *   iters[s]               update!s executed for this signal (an eps-break stops the count).
+ */
+int csb200_batch_download(csb200_batch* batch, int64_t stride, int64_t* sel_idx, double* coef,
+                          int64_t* nnz, double* resnorm, int64_t* iters);
+
+/* Timing of the dominant kernel (the correlation pass), measured with CUDA events on the
+ * batch's own stream.  enable != 0 turns per-launch event recording on and clears the
+ * counters; csb200_batch_corr_time returns the summed duration (ms) and launch count since. */
+int csb200_batch_profile(csb200_batch* batch, int enable);
+int csb200_batch_corr_time(csb200_batch* batch, double* total_ms, int64_t* launches, int64_t* other_launches);
+/* Device time (ms, CUDA events on the batch's stream) of the last omp/gomp/mp solve on this batch:
+ * first kernel enqueued to last kernel finished; excludes upload/download. */
+int csb200_batch_last_solve_ms(csb200_batch* batch, double* ms);
+
+/* ---- one-shot host-buffer entry points (what `omp(A,b,k)` etc. bind to) ------------------
+ * upload + solve + download on a temporary batch.  Outputs as in csb200_batch_download with
+ * stride = k (omp/gomp) or iters (mp).
+ */
+int csb200_omp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double eps,
+               int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+int csb200_gomp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t l, int64_t k,
+                double eps, int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+int csb200_mp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k,
+              const int64_t* x0_idx, const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride,
+              int64_t* sel_idx, double* coef, double* resnorm);
+
+/* ---- column-sharded single-dictionary mode (one process per GPU, NCCL over NVLink) -------
+ * Each rank holds a csb200_dict_create_shard() slice.  csb200_comm_* wrap one NCCL
+ * communicator; the unique id (128 bytes) is produced on rank 0 and distributed by the host
+ * program (torch.distributed / MPI / files).  csb200_omp_sharded runs `omp` for ONE signal
+ * with the per-iteration exchange done on the device stream (no host round trip):
+ * all ranks return the same result.
+ */
+#define CSB200_NCCL_ID_BYTES 128
+typedef struct csb200_comm csb200_comm;
+int csb200_comm_unique_id(void* id_bytes);
+int csb200_comm_create(const void* id_bytes, int rank, int nranks, int device, csb200_comm** out);
+int csb200_comm_destroy(csb200_comm* comm);
+int csb200_omp_sharded(csb200_dict* shard, csb200_comm* comm, const void* b, int64_t k, double eps,
+                       int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters,
+                       double* corr_ms);
+
+/* ---- test / debug hooks ------------------------------------------------------------------
+ * One correlation pass over the current residuals with the production kernel (impl 0 = auto,
+ * 1 = DMMA GEMM, 2 = GEMV) or a naive one-thread-per-dot kernel (impl 3); returns, per signal,
+ * the top-`s` atoms (index, |c|) in (value desc, index asc) order.  Used by tests/ only. */
+int csb200_debug_corr_topk(csb200_batch* batch, int impl, int64_t s, int64_t* idx, double* val);
+/* Copy the current residual matrix (M x nsig, dict dtype, ld = M) to the host. */
+int csb200_debug_get_residual(csb200_batch* batch, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSB200_H */

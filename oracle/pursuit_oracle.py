@@ -1,0 +1,344 @@
+"""CPU oracle for the greedy-pursuit hot path of CompressedSensing.jl  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a line-by-line NumPy restatement of the reference algorithm
+(`/root/reference/src/matchingpursuit.jl:10-193`, `/root/reference/src/util.jl:118-134`).
+It is the *checker* for the CUDA product path and is imported only by `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs.
+Nothing under `compressedsensing.jl_b200/` may import it.
+
+PARITY STATUS: **value-level parity is unpinned.**  The reference ships no golden
+vectors, no seeds and no fixtures for this path, and Julia is not
+installed in this image, so the oracle cannot be compared with outputs of the reference
+itself.  What *is* pinned (tests/test_oracle.py): every property the reference's own tests
+assert for this path (`test/matchingpursuit.jl:15-45`, `test/forward.jl:24-28`) at the
+reference's shapes, plus the Julia stdlib semantics restated below (first-index `argmax`,
+`partialsortperm(..., rev=true)` ordering, ascending-index sparse AXPY in `residual!`).
+
+The one piece of arithmetic that lives in an un-vendored dependency is
+UpdatableQRFactorizations v1.0.0 (git-tree-sha1 dd1d0589f29fcac6f29bbeff2e3c698a4299c3db,
+`Manifest.toml:446-450`): `UpdatableQR(T,n,k)`, `add_column!(F,a,pos)`, `ldiv!(F,r)`.
+Its published contract is "QR of the active columns under column insertion, least-squares
+solve returned in logical (sorted) order".  Two interchangeable engines restate it here:
+  * ``ls="lapack"``  -- dense Householder LS on ``A[:, sort(S)]`` (ground truth), and
+  * ``ls="givens"``  -- an updatable thin QR with Givens-rotation column insertion
+                        (oracle/updatable_qr.py), the scheme the call-site comment at
+                        `src/util.jl:121` names.
+Both give the same answer to a few ulps; tests assert that (the property
+`test/forward.jl:24-28` pins).
+
+Indices are 0-based here; the reference is 1-based.  "first index on ties" is preserved.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .updatable_qr import UpdatableQR
+
+__all__ = [
+    "SparseVec", "Trace", "mp", "omp", "gomp", "residual", "argmaxinner", "argmaxinner_k",
+    "sparse_vector", "sparse_data", "perturb", "eps_of",
+]
+
+
+def eps_of(dtype) -> float:
+    """Julia `eps(T)` (`src/matchingpursuit.jl:85,142`)."""
+    return float(np.finfo(np.dtype(dtype)).eps)
+
+
+# ----------------------------------------------------------------------------------------
+# SparseVector{Float64,Int64} stand-in (what `spzeros(N)` returns, `src/matchingpursuit.jl:76`)
+# ----------------------------------------------------------------------------------------
+@dataclass
+class SparseVec:
+    """Sorted-index sparse vector; values are ALWAYS float64, as in the reference."""
+    n: int
+    nzind: List[int] = field(default_factory=list)
+    nzval: List[float] = field(default_factory=list)
+
+    def nnz(self) -> int:
+        return len(self.nzind)
+
+    def __contains__(self, i: int) -> bool:
+        return i in self.nzind
+
+    def setindex(self, i: int, v: float) -> None:
+        """`x[i] = v`: sorted insert, or overwrite when already stored (SparseArrays semantics)."""
+        lo = int(np.searchsorted(np.asarray(self.nzind, dtype=np.int64), i))
+        if lo < len(self.nzind) and self.nzind[lo] == i:
+            self.nzval[lo] = float(v)
+        else:
+            self.nzind.insert(lo, int(i))
+            self.nzval.insert(lo, float(v))
+
+    def getindex(self, i: int) -> float:
+        lo = int(np.searchsorted(np.asarray(self.nzind, dtype=np.int64), i))
+        if lo < len(self.nzind) and self.nzind[lo] == i:
+            return self.nzval[lo]
+        return 0.0
+
+    def dense(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.float64)
+        if self.nzind:
+            out[np.asarray(self.nzind)] = np.asarray(self.nzval)
+        return out
+
+    def copy(self) -> "SparseVec":
+        return SparseVec(self.n, list(self.nzind), list(self.nzval))
+
+
+@dataclass
+class Trace:
+    """Per-iteration record used by the parity tests (not part of the reference)."""
+    selected: List[List[int]] = field(default_factory=list)   # atoms picked by argmax, in order, per update!
+    added: List[List[int]] = field(default_factory=list)      # atoms actually appended (not already active)
+    margin: List[float] = field(default_factory=list)         # (top1 - top2)/top1 of |c| at each argmax
+    resnorm: List[float] = field(default_factory=list)        # ||r||_2 after each update!
+    iterations: int = 0
+
+    def order(self) -> List[int]:
+        return [j for step in self.added for j in step]
+
+
+# ----------------------------------------------------------------------------------------
+# helpers  (`src/matchingpursuit.jl:152-193`)
+# ----------------------------------------------------------------------------------------
+def residual(A: np.ndarray, x: SparseVec, b: np.ndarray) -> np.ndarray:
+    """`residual!` (`src/matchingpursuit.jl:158-161`): `copyto!(r,b); mul!(r, A, x, -1, 1)`.
+
+    SparseArrays' kernel walks the stored entries in ascending index order and does
+    `r[i] += A[i,j] * (x_j * -1)`; with a Float32 `A` the product is formed in Float64
+    (x is always Float64) and rounded to Float32 on store.
+    """
+    T = A.dtype
+    r = np.array(b, dtype=T, copy=True)
+    for j, v in zip(x.nzind, x.nzval):
+        av = np.float64(v) * -1.0
+        if T == np.float64:
+            r += A[:, j] * av
+        else:
+            r = (r.astype(np.float64) + A[:, j].astype(np.float64) * av).astype(T)
+    return r
+
+
+def _check_finite(*arrays: np.ndarray) -> None:
+    for a in arrays:
+        if not np.all(np.isfinite(a)):
+            raise ValueError("non-finite input (the replacement rejects NaN/Inf at the boundary; "
+                             "see SURVEY.md 8a row a14)")
+
+
+def correlations(A: np.ndarray, r: np.ndarray) -> np.ndarray:
+    """`mul!(P.Ar, P.A', P.r); @. P.Ar = abs(P.Ar)` (`src/matchingpursuit.jl:182-183`) -> BLAS gemv('T')."""
+    return np.abs(A.T @ r)
+
+
+def argmaxinner(A: np.ndarray, r: np.ndarray, trace: Optional[Trace] = None) -> int:
+    """`argmaxinner!(P)` (`src/matchingpursuit.jl:181-185`): lowest index among equal maxima."""
+    Ar = correlations(A, r)
+    i = int(np.argmax(Ar))                       # numpy: first occurrence, same as Julia for finite input
+    if trace is not None:
+        top = float(Ar[i])
+        if Ar.size > 1:
+            second = float(np.partition(Ar, -2)[-2])
+            trace.margin.append((top - second) / top if top > 0 else 0.0)
+        else:
+            trace.margin.append(1.0)
+    return i
+
+
+def argmaxinner_k(A: np.ndarray, r: np.ndarray, k: int, trace: Optional[Trace] = None) -> List[int]:
+    """`argmaxinner!(P,k)` (`src/matchingpursuit.jl:189-193`): `partialsortperm(Ar, 1:k, rev=true)`.
+
+    Indices of the k largest |c|, descending; `Base.Order.Perm` breaks ties by lower index.
+    """
+    Ar = correlations(A, r)
+    order = np.lexsort((np.arange(Ar.size), -Ar))  # primary: value descending; secondary: index ascending
+    sel = [int(j) for j in order[:k]]
+    if trace is not None:
+        if Ar.size > k:
+            kth, nxt = float(Ar[order[k - 1]]), float(Ar[order[k]])
+            trace.margin.append((kth - nxt) / kth if kth > 0 else 0.0)
+        else:
+            trace.margin.append(1.0)
+    return sel
+
+
+class _ActiveSetLS:
+    """The `AiQR` field (`src/matchingpursuit.jl:50,58,102,112`) behind `addindex!` / `ldiv!!`."""
+
+    def __init__(self, A: np.ndarray, engine: str, capacity: int):
+        self.A = A
+        self.engine = engine
+        if engine == "givens":
+            self.qr = UpdatableQR(A.dtype, A.shape[0], capacity)
+        elif engine != "lapack":
+            raise ValueError(f"unknown ls engine {engine!r}")
+
+    def add_column(self, x: SparseVec, j: int) -> bool:
+        """`addindex!(x, AiQR, a, i)` (`src/util.jl:118-126`)."""
+        if j in x:
+            return False
+        x.setindex(j, np.nan)                               # util.jl:120
+        pos = x.nzind.index(j)                              # util.jl:122  findfirst(==(i), x.nzind)
+        if self.engine == "givens":
+            self.qr.add_column(self.A[:, j], pos)           # util.jl:123
+        return True
+
+    def solve(self, x: SparseVec, b: np.ndarray) -> None:
+        """`ldiv!!(x.nzval, AiQR, b, r)` (`src/matchingpursuit.jl:170-176`): LS coefficients, sorted order."""
+        T = self.A.dtype
+        if self.engine == "givens":
+            y = self.qr.solve(np.asarray(b, dtype=T))
+        else:
+            AS = self.A[:, np.asarray(x.nzind, dtype=np.int64)]
+            y, *_ = np.linalg.lstsq(AS, np.asarray(b, dtype=T), rcond=None)
+        x.nzval = [float(v) for v in np.asarray(y, dtype=np.float64)]
+
+
+# ----------------------------------------------------------------------------------------
+# Matching pursuit  (`src/matchingpursuit.jl:10-40`)
+# ----------------------------------------------------------------------------------------
+def mp(A: np.ndarray, b: np.ndarray, k: int, x: Optional[SparseVec] = None,
+       trace: Optional[Trace] = None) -> SparseVec:
+    """`mp(A,b,k,x=spzeros(N))` (`src/matchingpursuit.jl:34-40`): exactly k updates, no stopping rule."""
+    _check_finite(A, b)
+    M, N = A.shape
+    x = SparseVec(N) if x is None else x
+    for _ in range(k):
+        r = residual(A, x, b)                                # :27
+        i = argmaxinner(A, r, trace)                         # :28
+        x.setindex(i, x.getindex(i) + float(np.dot(A[:, i], r)))   # :29  signed, recomputed dot
+        if trace is not None:
+            trace.selected.append([i])
+            trace.added.append([i])
+            trace.resnorm.append(float(np.linalg.norm(residual(A, x, b))))
+            trace.iterations += 1
+    return x
+
+
+# ----------------------------------------------------------------------------------------
+# Orthogonal matching pursuit  (`src/matchingpursuit.jl:44-91`)
+# ----------------------------------------------------------------------------------------
+def _omp_update(A, b, x: SparseVec, ls: _ActiveSetLS, trace: Optional[Trace]) -> None:
+    """`update!(P::OMP, x)` (`src/matchingpursuit.jl:62-70`)."""
+    if not x.nnz() < A.shape[0]:                             # :63
+        if trace is not None:
+            trace.selected.append([]); trace.added.append([])
+        return
+    r = residual(A, x, b)                                    # :64
+    i = argmaxinner(A, r, trace)                             # :65  over ALL atoms, active ones included
+    if trace is not None:
+        trace.selected.append([i])
+    if i in x:                                               # :66  iteration consumed, nothing changes
+        if trace is not None:
+            trace.added.append([])
+        return
+    ls.add_column(x, i)                                      # :67
+    ls.solve(x, b)                                           # :68
+    if trace is not None:
+        trace.added.append([i])
+
+
+def omp(A: np.ndarray, b: np.ndarray, k: Optional[int] = None, eps: Optional[float] = None,
+        ls: str = "lapack", trace: Optional[Trace] = None) -> SparseVec:
+    """`omp(A,b,eps,k=size(A,1))` / `omp(A,b,k)` (`src/matchingpursuit.jl:73-86`)."""
+    _check_finite(A, b)
+    M, N = A.shape
+    eps = eps_of(A.dtype) if eps is None else eps            # :85
+    k = M if k is None else k                                # :73 default
+    if not eps >= 0:
+        raise ValueError(f"ε = {eps} has to be non-negative")   # :74 (the reference throws a String)
+    engine = _ActiveSetLS(A, ls, k)                          # :75
+    x = SparseVec(N)                                         # :76
+    for _ in range(k):                                       # :77
+        _omp_update(A, b, x, engine, trace)                  # :78
+        nr = float(np.linalg.norm(residual(A, x, b)))        # :79
+        if trace is not None:
+            trace.resnorm.append(nr); trace.iterations += 1
+        if not nr >= eps:
+            break
+    return x
+
+
+# ----------------------------------------------------------------------------------------
+# Generalized OMP  (`src/matchingpursuit.jl:95-148`)
+# ----------------------------------------------------------------------------------------
+def _gomp_update(A, b, x: SparseVec, ls: _ActiveSetLS, l: int, trace: Optional[Trace]) -> None:
+    """`update!(P::GOMP, x, l)` (`src/matchingpursuit.jl:116-123`)."""
+    if not x.nnz() < A.shape[0]:                             # :117
+        if trace is not None:
+            trace.selected.append([]); trace.added.append([])
+        return
+    r = residual(A, x, b)                                    # :118
+    idx = argmaxinner_k(A, r, l, trace)                      # :119
+    added = []
+    for j in idx:                                            # :120 -> util.jl:129-134, in descending-|c| order
+        if ls.add_column(x, j):
+            added.append(j)
+    ls.solve(x, b)                                           # :121
+    if trace is not None:
+        trace.selected.append(list(idx)); trace.added.append(added)
+
+
+def gomp(A: np.ndarray, b: np.ndarray, l: int, k: Optional[int] = None, eps: Optional[float] = None,
+         ls: str = "lapack", trace: Optional[Trace] = None) -> SparseVec:
+    """`gomp(A,b,l,eps,k=size(A,1))` / `gomp(A,b,l,k)` (`src/matchingpursuit.jl:126-143`)."""
+    _check_finite(A, b)
+    M, N = A.shape
+    eps = eps_of(A.dtype) if eps is None else eps
+    k = M if k is None else k
+    if not eps >= 0:
+        raise ValueError(f"ε = {eps} has to be non-negative")   # :127
+    engine = _ActiveSetLS(A, ls, M)                          # :128  (k is NOT forwarded: capacity M)
+    x = SparseVec(N)                                         # :129
+    for _ in range(k // l):                                  # :130
+        _gomp_update(A, b, x, engine, l, trace)              # :131
+        nr = float(np.linalg.norm(residual(A, x, b)))        # :132
+        if trace is not None:
+            trace.resnorm.append(nr); trace.iterations += 1
+        if not nr >= eps:
+            break
+    rem = k % l                                              # :134
+    if rem > 0:                                              # :135-137  runs even after an eps-break
+        _gomp_update(A, b, x, engine, rem, trace)
+        if trace is not None:
+            trace.resnorm.append(float(np.linalg.norm(residual(A, x, b)))); trace.iterations += 1
+    return x
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic data  (`src/util.jl:13-33,50-55`) -- distribution restated, not Julia's RNG stream
+# ----------------------------------------------------------------------------------------
+def sparse_vector(rng: np.random.Generator, m: int, k: int, gaussian: bool = False) -> SparseVec:
+    """`sparse_vector(m,k,gaussian)` (`src/util.jl:13-19`)."""
+    if m < k:
+        raise ValueError(f"m = {m} < {k} = k")
+    ind = np.sort(rng.choice(m, size=k, replace=False))
+    val = rng.standard_normal(k) if gaussian else rng.choice(np.array([-1.0, 1.0]), size=k)
+    return SparseVec(m, [int(i) for i in ind], [float(v) for v in val])
+
+
+def gaussian_dictionary(rng: np.random.Generator, n: int, m: int, dtype=np.float64) -> np.ndarray:
+    """The dictionary part of `sparse_data` (`src/util.jl:21-28`): Gaussian, eps-mean-shifted, unit columns."""
+    A = rng.standard_normal((n, m))
+    A -= 1e-6 * A.mean(axis=0, keepdims=True)
+    A /= np.sqrt((A * A).sum(axis=0, keepdims=True))
+    return np.asfortranarray(A.astype(dtype))
+
+
+def sparse_data(rng: np.random.Generator, n: int = 32, m: int = 64, k: int = 3, dtype=np.float64):
+    """`sparse_data(n,m,k)` (`src/util.jl:21-33`): returns (A, x0, b = A*x0)."""
+    A = gaussian_dictionary(rng, n, m, dtype)
+    x = sparse_vector(rng, m, k)
+    b = (A[:, np.asarray(x.nzind)].astype(np.float64) @ np.asarray(x.nzval)).astype(dtype)
+    return A, x, b
+
+
+def perturb(rng: np.random.Generator, b: np.ndarray, delta: float) -> np.ndarray:
+    """`perturb(b, δ)` (`src/util.jl:50-55`): add Gaussian noise rescaled to norm exactly δ."""
+    e = rng.standard_normal(b.shape)
+    e *= delta / np.linalg.norm(e)
+    return (b + e).astype(b.dtype)

@@ -1,0 +1,70 @@
+"""Generates tests/golden/*.npz: seeded inputs (as bytes, not seeds-in-two-languages) and the oracle's outputs.
+
+The reference ships no golden vectors for this path and Julia is not available in this image, so the
+fixtures are produced by the CPU oracle (oracle/pursuit_oracle.py), which restates the reference line by
+line.  They pin (a) the oracle against silent changes and (b) the CUDA path against the oracle on the GPU
+box, where /root/reference and Julia do not exist either.      Run:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import pursuit_oracle as po  # noqa: E402
+
+
+def build(name, algo, M, N, k, B, seed, dtype=np.float64, l=None, noise=0.0, eps=None, planted=None):
+    rng = np.random.default_rng(seed)
+    A = po.gaussian_dictionary(rng, M, N, dtype)
+    planted = k if planted is None else planted
+    cols = []
+    for _ in range(B):
+        x0 = po.sparse_vector(rng, N, planted)
+        b = (A[:, x0.nzind].astype(np.float64) @ np.asarray(x0.nzval)).astype(dtype)
+        if noise:
+            b = po.perturb(rng, b, noise)
+        cols.append(b)
+    Bm = np.stack(cols, axis=1)
+    kk = k
+    nzind = -np.ones((B, kk), dtype=np.int64)
+    nzval = np.zeros((B, kk))
+    order = -np.ones((B, kk), dtype=np.int64)
+    nnz = np.zeros(B, dtype=np.int64)
+    resn = np.zeros(B)
+    margin = np.zeros(B)
+    for s in range(B):
+        t = po.Trace()
+        if algo == "omp":
+            x = po.omp(A, Bm[:, s], k, eps=eps, trace=t)
+        elif algo == "gomp":
+            x = po.gomp(A, Bm[:, s], l, k, eps=eps, trace=t)
+        else:
+            x = po.mp(A, Bm[:, s], k, trace=t)
+        n = x.nnz()
+        nnz[s] = n
+        nzind[s, :n] = x.nzind
+        nzval[s, :n] = x.nzval
+        o = t.order()
+        if algo != "mp":
+            order[s, :len(o)] = o
+        resn[s] = t.resnorm[-1]
+        margin[s] = min(t.margin)
+    meta = dict(algo=algo, M=M, N=N, k=k, B=B, seed=seed, dtype=np.dtype(dtype).name, l=l, noise=noise, eps=eps,
+                planted=planted)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), A=A, B=Bm, nzind=nzind, nzval=nzval, order=order, nnz=nnz,
+                        resnorm=resn, margin=margin, meta=json.dumps(meta))
+    print(name, "min margin", margin.min(), "max resnorm", resn.max())
+
+
+if __name__ == "__main__":
+    build("omp_c1_128x256_k8", "omp", 128, 256, 8, 4, seed=1234)                      # BASELINE config 1 (KAT-1)
+    build("omp_c1_noisy", "omp", 128, 256, 8, 4, seed=1235, noise=5e-3)                # KAT-2
+    build("omp_ref_32x48_k3", "omp", 32, 48, 3, 40, seed=1236)                         # reference test shape (KAT-3)
+    build("gomp_ref_32x48_l2_k3", "gomp", 32, 48, 3, 40, seed=1237, l=2)               # remainder step (KAT-7)
+    build("gomp_96x200_l4_k8", "gomp", 96, 200, 8, 8, seed=1238, l=4)
+    build("mp_ref_32x48_k30", "mp", 32, 48, 30, 8, seed=1239, planted=3)               # KAT-8
+    build("omp_f32_64x160_k5", "omp", 64, 160, 5, 8, seed=1240, dtype=np.float32)      # KAT-9
+    build("omp_ragged_70x130_k6", "omp", 70, 130, 6, 8, seed=1241)                     # M, N not multiples of 16 / 64

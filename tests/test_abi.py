@@ -1,0 +1,108 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/csb200.h declares,
+and fails loudly (no CPU fallback) when there is no GPU.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "csb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(csb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(cs):
+    names = _declared_symbols()
+    assert len(names) >= 25
+    L = ctypes.CDLL(cs.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/csb200.h but not exported by libcsb200.so"
+    assert sorted(cs.EXPORTED_SYMBOLS) == names
+
+
+def test_version_and_strerror(cs):
+    assert cs.lib.csb200_version() == 100
+    assert cs.lib.csb200_strerror(0) == b"ok"
+    assert b"non-negative" in cs.lib.csb200_strerror(-2)
+    assert b"unknown" in cs.lib.csb200_strerror(-99)
+
+
+def test_library_contains_only_sm100a_code(cs):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", cs.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_sass_has_dmma_and_tma(cs):
+    """Evidence that the batched kernel is the DMMA + TMA one (B200_PROFILING.md: UTMALDG = cp.async.bulk.tensor)."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", cs.LIB_PATH], capture_output=True, text=True).stdout
+    assert "DMMA.8x8x4" in sass
+    assert "UTMALDG" in sass
+    assert "SYNCS" in sass          # mbarrier
+
+
+def test_no_cpu_fallback_without_gpu(cs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    A = np.asfortranarray(np.eye(4))
+    with pytest.raises(cs.CSB200Error):
+        cs.omp(A, np.ones(4), 2)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "compressedsensing.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".jl", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace(
+                    "`oracle/`", ""), (dirpath, f)
+
+
+def test_argument_dispatch_mirrors_julia_methods(cs, monkeypatch):
+    """omp(A,b,k::Int) vs omp(A,b,eps::Real,k) vs keywords -- checked without touching the GPU."""
+    calls = []
+
+    class FakeBatch:
+        def __init__(self, *a): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): pass
+        def upload(self, B): self.n = 1 if np.ndim(B) == 1 else B.shape[1]
+        def omp(self, k, eps): calls.append(("omp", k, eps))
+        def gomp(self, l, k, eps): calls.append(("gomp", l, k, eps))
+        def download(self, stride):
+            return (-np.ones((self.n, stride), dtype=np.int64), np.zeros((self.n, stride)),
+                    np.zeros(self.n, dtype=np.int64), np.zeros(self.n), np.zeros(self.n, dtype=np.int64))
+
+    class FakeDict:
+        def __init__(self, A, device=0):
+            self.M, self.N = A.shape; self.n_total = self.N; self.dtype = A.dtype
+        def close(self): pass
+
+    monkeypatch.setattr(cs, "Batch", FakeBatch)
+    monkeypatch.setattr(cs, "Dictionary", FakeDict)
+    A = np.zeros((8, 12)); b = np.zeros(8)
+    eps64 = np.finfo(np.float64).eps
+    cs.omp(A, b, 3);                       assert calls[-1] == ("omp", 3, eps64)
+    cs.omp(A, b, 0.5);                     assert calls[-1] == ("omp", 8, 0.5)          # k defaults to size(A,1)
+    cs.omp(A, b, 0.5, 4);                  assert calls[-1] == ("omp", 4, 0.5)
+    cs.omp(A, b);                          assert calls[-1] == ("omp", 8, eps64)        # sparsity = min(size(A)...)
+    cs.omp(A, b, max_residual=0.1, sparsity=2); assert calls[-1] == ("omp", 2, 0.1)
+    cs.omp(A.astype(np.float32), b, 3);    assert calls[-1] == ("omp", 3, float(np.finfo(np.float32).eps))
+    cs.gomp(A, b, 2, 3);                   assert calls[-1] == ("gomp", 2, 3, eps64)
+    cs.gomp(A, b, 2, 0.25, 6);             assert calls[-1] == ("gomp", 2, 6, 0.25)
+    cs.gomp(A, b, 2);                      assert calls[-1] == ("gomp", 2, 12, eps64)   # sparsity = size(A,2)
+    with pytest.raises(ValueError, match="has to be non-negative"):
+        cs.omp(A, b, -1.0)
+    with pytest.raises(ValueError, match="has to be non-negative"):
+        cs.gomp(A, b, 2, -1.0, 3)
+    out = cs.omp(A, np.zeros((8, 5)), 3)
+    assert isinstance(out, list) and len(out) == 5 and out[0].n == 12

@@ -1,0 +1,346 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against the
+CPU oracle on the same bytes.  Bars (BASELINE.json north_star): selected support sequence bit-exact,
+coefficients and residual norms within 1e-10 relative in FP64; FP32 dictionaries: 2e-5 relative."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+RTOL64 = 1e-10
+RTOL32 = 2e-5
+IMPLS = {"auto": 0, "gemm": 1, "gemv": 2, "naive": 3}
+
+
+def _batch(cs, D, B, kcap, impl=None):
+    old = os.environ.pop("CSB200_CORR_IMPL", None)
+    if impl:
+        os.environ["CSB200_CORR_IMPL"] = impl
+    try:
+        batch = cs.Batch(D, B.shape[1], kcap)
+    finally:
+        os.environ.pop("CSB200_CORR_IMPL", None)
+        if old:
+            os.environ["CSB200_CORR_IMPL"] = old
+    batch.upload(B)
+    return batch
+
+
+def _sorted(sel_row, coef_row, n):
+    idx, val = sel_row[:n], coef_row[:n]
+    o = np.argsort(idx, kind="stable")
+    return idx[o], val[o]
+
+
+def _close(a, b, rtol):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(1.0, float(np.max(np.abs(b))) if b.size else 1.0)
+    return np.allclose(a, b, rtol=rtol, atol=rtol * scale)
+
+
+# ------------------------------------------------------------------ correlation kernels
+@pytest.mark.parametrize("M,N,B,s", [(128, 256, 48, 1), (70, 130, 33, 3), (1024, 700, 130, 4), (16, 64, 24, 1),
+                                     (33, 1000, 257, 8)])
+def test_corr_gemm_matches_numpy_topk(cs, po, M, N, B, s):
+    rng = np.random.default_rng(M * 7 + N)
+    A = po.gaussian_dictionary(rng, M, N)
+    R = np.asfortranarray(rng.standard_normal((M, B)))
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 4) as batch:
+        batch.upload(R)
+        got = {name: batch.debug_corr_topk(s, impl) for name, impl in IMPLS.items() if name != "auto"}
+    C = np.abs(A.T @ R)
+    for b in range(B):
+        order = np.lexsort((np.arange(N), -C[:, b]))[:s]
+        gap = np.min(np.abs(np.diff(np.sort(C[:, b])[::-1][: s + 1]))) if N > s else 1.0
+        for name, (idx, val) in got.items():
+            assert np.allclose(val[b], C[order, b], rtol=1e-12, atol=1e-13), (name, b)
+            if gap > 1e-11:
+                assert idx[b].tolist() == order.tolist(), (name, b)
+    # the production kernels must agree with each other exactly on the indices
+    assert np.array_equal(got["gemm"][0], got["gemv"][0])
+    assert np.array_equal(got["gemm"][0], got["naive"][0])
+
+
+def test_corr_ties_pick_lowest_index(cs, po):
+    """KAT-4: duplicate / negated duplicate atoms give bit-identical |c|: the lower index must win."""
+    rng = np.random.default_rng(11)
+    M, N, B = 64, 320, 40
+    A = po.gaussian_dictionary(rng, M, N)
+    A[:, 200] = A[:, 17]          # different atom block, different CTA tile half
+    A[:, 18] = -A[:, 17]          # same block
+    A[:, 300] = A[:, 129]
+    R = np.asfortranarray(np.stack([A[:, 17] * (1 + 0.1 * i) for i in range(B // 2)] +
+                                   [A[:, 129] * (1 + 0.1 * i) for i in range(B // 2)], axis=1))
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 4) as batch:
+        batch.upload(R)
+        for impl in (1, 2, 3):
+            idx, val = batch.debug_corr_topk(3, impl)
+            assert (idx[: B // 2, 0] == 17).all() and (idx[: B // 2, 1] == 18).all() and (idx[: B // 2, 2] == 200).all(), impl
+            assert (idx[B // 2:, 0] == 129).all() and (idx[B // 2:, 1] == 300).all(), impl
+            assert np.array_equal(val[: B // 2, 0], val[: B // 2, 2])
+
+
+@pytest.mark.parametrize("M,N,s", [(64, 160, 2), (8192, 640, 1), (100, 77, 5)])
+def test_corr_gemv_f32(cs, po, M, N, s):
+    rng = np.random.default_rng(N)
+    A = po.gaussian_dictionary(rng, M, N, np.float32)
+    R = np.asfortranarray(rng.standard_normal((M, 3)).astype(np.float32))
+    with cs.Dictionary(A) as D, cs.Batch(D, 3, 4) as batch:
+        batch.upload(R)
+        idx, val = batch.debug_corr_topk(s, 2)
+        idx_n, val_n = batch.debug_corr_topk(s, 3)
+    C = np.abs(A.astype(np.float64).T @ R.astype(np.float64))
+    assert np.array_equal(idx, idx_n)
+    for b in range(3):
+        order = np.lexsort((np.arange(N), -C[:, b]))[:s]
+        assert idx[b].tolist() == order.tolist()
+        assert np.allclose(val[b], C[order, b], rtol=1e-12)     # FP64 accumulation of exact float products
+
+
+# ------------------------------------------------------------------ golden fixtures
+def _fixtures():
+    return sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+@pytest.mark.parametrize("path", _fixtures(), ids=lambda p: os.path.basename(p)[:-4])
+@pytest.mark.parametrize("impl", ["gemm", "gemv"])
+def test_golden(cs, path, impl):
+    z = np.load(path, allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    A, Bm = np.asfortranarray(z["A"]), np.asfortranarray(z["B"])
+    f32 = A.dtype == np.float32
+    if f32 and impl == "gemm":
+        pytest.skip("the DMMA GEMM path is FP64-only")
+    rtol = RTOL32 if f32 else RTOL64
+    k = meta["k"]
+    eps = meta["eps"] if meta["eps"] is not None else float(np.finfo(A.dtype).eps)
+    with cs.Dictionary(A) as D:
+        batch = _batch(cs, D, Bm, k, impl)
+        if meta["algo"] == "omp":
+            batch.omp(k, eps)
+        elif meta["algo"] == "gomp":
+            batch.gomp(meta["l"], k, eps)
+        else:
+            batch.mp(k)
+        sel, coef, nnz, res, its = batch.download(k)
+        batch.close()
+    for s in range(Bm.shape[1]):
+        n = int(z["nnz"][s])
+        if meta["algo"] == "mp":
+            acc = {}
+            for i, c in zip(sel[s, :k].tolist(), coef[s, :k].tolist()):
+                acc[i] = acc.get(i, 0.0) + c
+            idx = np.array(sorted(acc))
+            val = np.array([acc[i] for i in idx.tolist()])
+            assert idx.tolist() == z["nzind"][s, :n].tolist(), (s, idx, z["nzind"][s, :n])
+            assert _close(val, z["nzval"][s, :n], 1e-9 if not f32 else RTOL32), s
+            continue
+        assert int(nnz[s]) == n, (s, nnz[s], n)
+        assert sel[s, :n].tolist() == z["order"][s, :n].tolist(), (s, "selection sequence")
+        idx, val = _sorted(sel[s], coef[s], n)
+        assert idx.tolist() == z["nzind"][s, :n].tolist()
+        assert _close(val, z["nzval"][s, :n], rtol), (s, val, z["nzval"][s, :n])
+        assert abs(res[s] - z["resnorm"][s]) <= rtol * max(1.0, np.linalg.norm(Bm[:, s])) + 50 * np.finfo(A.dtype).eps
+
+
+# ------------------------------------------------------------------ reference call surface + quirks
+def test_call_surface_and_quirks(cs, po):
+    rng = np.random.default_rng(3)
+    A, x0, b = po.sparse_data(rng, 32, 48, 3)
+    with cs.Dictionary(A) as D:
+        x = cs.omp(D, b, 3)
+        assert x.nzind.tolist() == x0.nzind and np.allclose(x.nzval, x0.nzval, rtol=1e-8)
+        assert x.nzval.dtype == np.float64 and x.n == 48
+        ref = po.omp(A, b, eps=0.5)
+        got = cs.omp(D, b, 0.5)                        # eps form, k = size(A,1): stops once ||r|| < 0.5
+        assert got.nzind.tolist() == ref.nzind and _close(got.nzval, ref.nzval, RTOL64)
+        got = cs.omp(D, b, max_residual=0.5, sparsity=2)
+        ref = po.omp(A, b, 2, eps=0.5)
+        assert got.nzind.tolist() == ref.nzind and _close(got.nzval, ref.nzval, RTOL64)
+        xg = cs.gomp(D, b, 2, 3)
+        ref = po.gomp(A, b, 2, 3)
+        assert xg.nzind.tolist() == ref.nzind and _close(xg.nzval, ref.nzval, RTOL64)
+        xm = cs.mp(D, b, 30)
+        ref = po.mp(A, b, 30)
+        assert xm.nzind.tolist() == ref.nzind and _close(xm.nzval, ref.nzval, 1e-9)
+        # warm start (mp's optional x argument, matchingpursuit.jl:34)
+        xw = cs.mp(D, b, 5, x=cs.mp(D, b, 25))
+        assert xw.nzind.tolist() == ref.nzind and _close(xw.nzval, ref.nzval, 1e-9)
+        with pytest.raises(ValueError, match="has to be non-negative"):
+            cs.omp(D, b, -1.0, 3)
+        with pytest.raises(ValueError):
+            cs.omp(D, np.ones(31), 3)                  # DimensionMismatch
+        bad = b.copy(); bad[3] = np.nan
+        with pytest.raises(cs.CSB200Error) as ei:
+            cs.omp(D, bad, 3)
+        assert ei.value.status == -3
+    Abad = A.copy(); Abad[0, 0] = np.inf
+    with pytest.raises(cs.CSB200Error):
+        cs.Dictionary(Abad)
+    # one-shot form: a plain matrix instead of a Dictionary
+    x = cs.omp(A, b, 3)
+    assert x.nzind.tolist() == x0.nzind
+
+
+def test_noop_iteration_zero_signal_and_remainder(cs, po):
+    A = np.asfortranarray(np.eye(6))
+    with cs.Dictionary(A) as D:
+        b = np.array([1.0, 1.0, 0, 0, 0, 0])
+        with cs.Batch(D, 1, 3) as batch:               # KAT-5: eps = 0, third update re-picks atom 0: no-op
+            batch.upload(b)
+            batch.omp(3, 0.0)
+            sel, coef, nnz, res, its = batch.download(3)
+        assert nnz[0] == 2 and sel[0, :2].tolist() == [0, 1] and its[0] == 3 and res[0] == 0.0
+        with cs.Batch(D, 1, 3) as batch:               # default eps: break after the second update
+            batch.upload(b)
+            batch.omp(3, float(np.finfo(float).eps))
+            sel, coef, nnz, res, its = batch.download(3)
+        assert nnz[0] == 2 and its[0] == 2
+        x = cs.omp(D, np.zeros(6), 3)                  # KAT-6
+        assert x.nzind.tolist() == [0] and x.nzval.tolist() == [0.0]
+        x = cs.gomp(D, np.array([0, 3.0, 2.0, 0, 0, 0]), 2, 5)     # KAT-7: remainder after an eps-break
+        ref = po.gomp(A, np.array([0, 3.0, 2.0, 0, 0, 0]), 2, 5)
+        assert x.nzind.tolist() == ref.nzind == [0, 1, 2] and x.nzval.tolist() == ref.nzval
+    # support can never exceed the number of rows (matchingpursuit.jl:63)
+    rng = np.random.default_rng(9)
+    A = po.gaussian_dictionary(rng, 6, 20)
+    b = rng.standard_normal(6)
+    got, ref = cs.omp(A, b, 0.0, 10), po.omp(A, b, 10, eps=0.0)
+    assert got.nzind.tolist() == ref.nzind and got.nnz() <= 6
+
+
+def test_dependent_atom_is_not_appended(cs):
+    """Duplicate columns: once one copy is active the other can only win on a zero residual; the update
+    must leave a finite state (the reference's QR would divide by a zero diagonal here)."""
+    A = np.asfortranarray(np.array([[1.0, 1.0, 0], [0, 0, 1.0], [0, 0, 0]]))
+    x = cs.gomp(A, np.array([2.0, 0, 0]), 2, 0.0, 2)      # top-2 = atoms 0 and 1 (a tie): atom 1 duplicates atom 0
+    assert x.nzind.tolist() == [0] and x.nzval.tolist() == [2.0]
+
+
+# ------------------------------------------------------------------ mid-size parity and properties
+def _planted(po, rng, A, k, B, noise=0.0):
+    N = A.shape[1]
+    X0, cols = [], []
+    for _ in range(B):
+        x0 = po.sparse_vector(rng, N, k)
+        b = A[:, x0.nzind] @ np.asarray(x0.nzval)
+        if noise:
+            b = po.perturb(rng, b, noise)
+        X0.append(x0); cols.append(b)
+    return X0, np.asfortranarray(np.stack(cols, axis=1))
+
+
+def test_c2_shape_reduced_batch_vs_oracle(cs, po):
+    """BASELINE config 2 shape (1024 x 8192, k = 32) on 192 signals: first 12 against the oracle, all
+    against the planted support (noiseless, k = planted sparsity: every decision has a wide margin)."""
+    rng = np.random.default_rng(1234)
+    M, N, k, B = 1024, 8192, 32, 192
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, B)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+        batch.upload(Bm)
+        batch.omp(k, float(np.finfo(float).eps))
+        sel, coef, nnz, res, its = batch.download(k)
+    for s in range(B):
+        idx, val = _sorted(sel[s], coef[s], int(nnz[s]))
+        assert idx.tolist() == X0[s].nzind, s
+        assert np.allclose(val, X0[s].nzval, rtol=1e-10, atol=1e-10), s
+        assert res[s] < 1e-12
+    for s in range(12):
+        t = po.Trace()
+        ref = po.omp(A, Bm[:, s], k, trace=t)
+        assert sel[s, :k].tolist() == t.order(), (s, "selection sequence", min(t.margin))
+        idx, val = _sorted(sel[s], coef[s], k)
+        assert _close(val, ref.nzval, RTOL64)
+
+
+def test_gomp_and_mp_midsize_vs_oracle(cs, po):
+    rng = np.random.default_rng(77)
+    M, N, k, B = 256, 2048, 16, 64
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, B, noise=5e-3)
+    with cs.Dictionary(A) as D:
+        xs = cs.gomp(D, Bm, 4, k)
+        xm = cs.mp(D, Bm[:, :32], 40)
+    for s in range(B):
+        ref = po.gomp(A, Bm[:, s], 4, k)
+        assert xs[s].nzind.tolist() == ref.nzind, s
+        assert _close(xs[s].nzval, ref.nzval, RTOL64), s
+    for s in range(8):
+        ref = po.mp(A, Bm[:, s], 40)
+        assert xm[s].nzind.tolist() == ref.nzind, s
+        assert _close(xm[s].nzval, ref.nzval, 1e-9), s
+
+
+def test_residual_orthogonality_and_idempotence(cs, po):
+    """Size-independent properties: r is orthogonal to the active atoms; re-solving the same batch gives
+    bit-identical output (deterministic kernels); signals are independent of their batch neighbours."""
+    rng = np.random.default_rng(5)
+    M, N, k, B = 512, 4096, 24, 300
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, B, noise=1e-2)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+        batch.upload(Bm)
+        batch.omp(k, 0.0)
+        out1 = batch.download(k)
+        R = batch.residual()
+        batch.omp(k, 0.0)
+        out2 = batch.download(k)
+        with cs.Batch(D, 40, k) as small:
+            small.upload(Bm[:, 100:140])
+            small.omp(k, 0.0)
+            out3 = small.download(k)
+    for a, b in zip(out1, out2):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out1[0][100:140], out3[0])
+    assert np.array_equal(out1[1][100:140], out3[1])
+    for s in range(0, B, 17):
+        S = out1[0][s, :k]
+        assert np.max(np.abs(A[:, S].T @ R[:, s])) < 1e-12
+        assert abs(np.linalg.norm(R[:, s]) - out1[3][s]) < 1e-12
+
+
+def test_f32_single_signal_omp(cs, po):
+    rng = np.random.default_rng(8)
+    M, N, k = 2048, 16384, 24
+    A = po.gaussian_dictionary(rng, M, N, np.float32)
+    x0 = po.sparse_vector(rng, N, k)
+    b = (A[:, x0.nzind].astype(np.float64) @ np.asarray(x0.nzval)).astype(np.float32)
+    x = cs.omp(A, b, k)
+    assert x.nzind.tolist() == x0.nzind
+    assert np.allclose(x.nzval, x0.nzval, atol=RTOL32)
+    assert x.nzval.dtype == np.float64
+
+
+@pytest.mark.slow
+def test_c2_full_size_properties(cs, po):
+    """BASELINE config 2 at full size (65 536 signals): planted supports recovered, coefficients +-1."""
+    rng = np.random.default_rng(1234)
+    M, N, k, B = 1024, 8192, 32, 65536
+    A = po.gaussian_dictionary(rng, M, N)
+    idx = rng.integers(0, N, size=(B, k))
+    while True:                                            # resample rows that drew an atom twice
+        srt = np.sort(idx, axis=1)
+        bad = np.nonzero((np.diff(srt, axis=1) == 0).any(axis=1))[0]
+        if bad.size == 0:
+            break
+        idx[bad] = rng.integers(0, N, size=(bad.size, k))
+    idx = np.sort(idx, axis=1)
+    sign = rng.choice(np.array([-1.0, 1.0]), size=(B, k))
+    Bm = np.empty((M, B), order="F")
+    for s0 in range(0, B, 512):
+        blk = slice(s0, min(B, s0 + 512))
+        Bm[:, blk] = np.einsum("mbk,bk->mb", A[:, idx[blk]], sign[blk])
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+        batch.upload(Bm)
+        batch.omp(k, float(np.finfo(float).eps))
+        sel, coef, nnz, res, its = batch.download(k)
+    assert (nnz == k).all()
+    order = np.argsort(sel, axis=1)
+    assert np.array_equal(np.take_along_axis(sel, order, axis=1), idx)
+    assert np.allclose(np.take_along_axis(coef, order, axis=1), sign, rtol=1e-10, atol=1e-10)
+    assert res.max() < 1e-12
