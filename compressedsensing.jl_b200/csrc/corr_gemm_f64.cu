@@ -11,8 +11,11 @@
 //     ptxas lowers every wider f64 mma shape to it).  What is Blackwell/Hopper-class here is the
 //     data movement: both operands are K-contiguous (atoms and signals are columns), so one 2-D
 //     TMA box {16 doubles x 128 columns} per operand per k-chunk lands a 128 B-row, SWIZZLE_128B
-//     tile in shared memory; a dedicated producer warp runs a 4-stage mbarrier ring ahead of 8
-//     consumer warps, across tile boundaries (persistent CTAs, one per SM).
+//     tile in shared memory, through a 4-stage full/empty mbarrier ring that runs 3 chunks ahead of
+//     the math and straight across tile boundaries (persistent CTAs, one per SM).  All 8 warps
+//     compute (256 threads x ~220 registers is the whole register file, and warps are allocated
+//     in groups of 4, so there is no room for a dedicated producer warp); lane 0 of warp 0 issues
+//     the TMA for chunk c+3 before it consumes chunk c.
 //   * Fragment loads are LDS.128: lane (g = lane/4, q = lane%4) reads the 16 B chunk q of an
 //     8-double k-group for row g and feeds .x to one DMMA and .y to the next.  Both operands use
 //     the same k-permutation, so the contraction is unchanged, and with the 128 B swizzle the
@@ -33,8 +36,8 @@ constexpr int STAGES = 4;
 constexpr int A_TILE_BYTES = TILE_N * KCH * 8;
 constexpr int R_TILE_BYTES = TILE_B * KCH * 8;
 constexpr int STAGE_BYTES = A_TILE_BYTES + R_TILE_BYTES;   // 32 KiB
-constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int WARPS = 8;                    // all 8 warps compute; lane 0 of warp 0 also drives TMA
+constexpr int THREADS = WARPS * 32;         // 256 threads x <=255 registers = the whole register file
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -69,7 +72,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-__global__ void __maxnreg__(224)
+__global__ void __launch_bounds__(THREADS, 1)
 corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
                      int N, int nsig, int kchunks, int tilesN, int tilesB, int S, int P, int idx_offset,
                      double* __restrict__ pval, int* __restrict__ pidx) {
@@ -81,36 +84,37 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const uint32_t bar_empty = bar_full + STAGES * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = tilesN * tilesB;
+    // k-chunks this CTA streams, over all of its tiles: one flat sequence through the stage ring
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_chunks = my_tiles * kchunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + s * 8, 1);
-            mbar_init(bar_empty + s * 8, CONSUMER_WARPS);
+            mbar_init(bar_empty + s * 8, WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapR) : "memory");
     }
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
-        // ------------------------------ TMA producer (one lane) ------------------------------
-        if (lane == 0) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapR) : "memory");
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int tn = tile % tilesN, tb = tile / tilesN;
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(bar_empty + stage * 8, phase ^ 1u);
-                    mbar_arrive_expect_tx(bar_full + stage * 8, STAGE_BYTES);
-                    const uint32_t dst = sm_base + stage * STAGE_BYTES;
-                    tma_load_2d(dst, &mapA, bar_full + stage * 8, kc * KCH, tn * TILE_N);
-                    tma_load_2d(dst + A_TILE_BYTES, &mapR, bar_full + stage * 8, kc * KCH, tb * TILE_B);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-        return;
+    // TMA producer step, executed by thread 0 only: load flat chunk c into stage c % STAGES once the
+    // consumers have released that stage's previous occupant (chunk c - STAGES).
+    auto issue_chunk = [&](int c) {
+        const int stg = c % STAGES;
+        const uint32_t par = (uint32_t)((c / STAGES) & 1) ^ 1u;
+        const int tseq = c / kchunks, kc = c - tseq * kchunks;
+        const int tile = (int)blockIdx.x + tseq * (int)gridDim.x;
+        const int tn = tile % tilesN, tb = tile / tilesN;
+        mbar_wait(bar_empty + stg * 8, par);
+        mbar_arrive_expect_tx(bar_full + stg * 8, STAGE_BYTES);
+        const uint32_t dst = sm_base + stg * STAGE_BYTES;
+        tma_load_2d(dst, &mapA, bar_full + stg * 8, kc * KCH, tn * TILE_N);
+        tma_load_2d(dst + A_TILE_BYTES, &mapR, bar_full + stg * 8, kc * KCH, tb * TILE_B);
+    };
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < STAGES - 1 && c < total_chunks; ++c) issue_chunk(c);
     }
 
     // ---------------------------------- DMMA consumers -----------------------------------
@@ -121,6 +125,7 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const uint32_t r_row = (uint32_t)A_TILE_BYTES + (uint32_t)(wn * 32 + g) * 128u;   // + j*1024
     int stage = 0;
     uint32_t phase = 0;
+    int chunk = 0;                     // flat chunk index being consumed
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tn = tile % tilesN, tb = tile / tilesN;
@@ -130,7 +135,11 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-        for (int kc = 0; kc < kchunks; ++kc) {
+        for (int kc = 0; kc < kchunks; ++kc, ++chunk) {
+            // keep STAGES-1 chunks in flight, across tile boundaries (the next tile's first chunks
+            // stream in during this tile's epilogue)
+            if (threadIdx.x == 0 && chunk + STAGES - 1 < total_chunks) issue_chunk(chunk + STAGES - 1);
+            __syncwarp();
             mbar_wait(bar_full + stage * 8, phase);
             const uint8_t* st = sm + stage * STAGE_BYTES;
 #pragma unroll

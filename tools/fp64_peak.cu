@@ -52,6 +52,40 @@ __global__ void __launch_bounds__(1024) dfma_kernel(double* out, int iters, doub
     if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Register-tiled DMMA (MI x NJ accumulators, MI a-fragments, NJ b-fragments: the operand pattern of a real
+// warp tile).  Block 0 also reports its clock64() span so that flop/clk/SM is known independently of DVFS.
+template <int MI, int NJ>
+__global__ void __launch_bounds__(1024) dmma_tile_kernel(double* out, long long* cyc, int iters, double seed) {
+    double a[MI], b[NJ], c[MI][NJ][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i) a[i] = seed + (threadIdx.x + i) * 1e-9;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) b[j] = seed * 0.5 + (threadIdx.x + 7 * j) * 1e-9;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { c[i][j][0] = 0.0; c[i][j][1] = 0.0; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s += c[i][j][0] + c[i][j][1];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 static void time_it(F&& launch, double flop_per_launch, double* burst, double* sustained, double sustain_s) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -93,6 +127,30 @@ int main(int argc, char** argv) {
         first = false;
     }
     printf("]");
+    // 1b. register-tiled DMMA with per-SM cycle counts
+    {
+        long long* cyc; CK(cudaMalloc(&cyc, 8));
+        printf(", \"dmma_tile\": [");
+        bool f2 = true;
+        auto run = [&](auto kern, int mi, int nj, int threads) {
+            double flop = (double)sms * (threads / 32) * (double)iters * mi * nj * 512.0;
+            double bu, su;
+            time_it([&] { kern<<<sms, threads>>>(out, cyc, iters, 1.0); }, flop, &bu, &su, 0.5);
+            long long h; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+            double fpc = (double)(threads / 32) * iters * mi * nj * 512.0 / (double)h;
+            printf("%s{\"mi\": %d, \"nj\": %d, \"threads\": %d, \"burst_tflops\": %.2f, \"sustained_tflops\": %.2f, \"flop_per_clk_per_sm\": %.1f}",
+                   f2 ? "" : ", ", mi, nj, threads, bu, su, fpc);
+            f2 = false;
+        };
+        run(dmma_tile_kernel<8, 4>, 8, 4, 256);
+        run(dmma_tile_kernel<8, 4>, 8, 4, 128);
+        run(dmma_tile_kernel<4, 4>, 4, 4, 256);
+        run(dmma_tile_kernel<4, 4>, 4, 4, 512);
+        run(dmma_tile_kernel<4, 2>, 4, 2, 1024);
+        run(dmma_tile_kernel<2, 2>, 2, 2, 1024);
+        printf("]");
+        CK(cudaFree(cyc));
+    }
     // 2. DFMA
     printf(", \"dfma\": [");
     first = true;
