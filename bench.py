@@ -45,8 +45,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--signals", type=int, default=65536, help="signals per GPU per step")
-    ap.add_argument("--ref-signals", type=int, default=4, help="signals per step of the CPU reference arm")
-    ap.add_argument("--cpu-signals", type=int, default=12, help="signals of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--ref-signals", type=int, default=96, help="signals per step of the CPU reference arm")
+    ap.add_argument("--cpu-signals", type=int, default=512, help="signals of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
     return ap.parse_args()
 

@@ -68,6 +68,7 @@ def _load() -> ctypes.CDLL:
         "csb200_dict_create_shard": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int64,
                                              POINTER(c_void_p)]),
         "csb200_dict_destroy": (c_int, [c_void_p]),
+        "csb200_dict_trim": (c_int, [c_void_p]),
         "csb200_dict_shape": (c_int, [c_void_p, i64p, i64p, POINTER(c_int), POINTER(c_int)]),
         "csb200_batch_create": (c_int, [c_void_p, c_int64, c_int64, POINTER(c_void_p)]),
         "csb200_batch_destroy": (c_int, [c_void_p]),
@@ -102,7 +103,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED_SYMBOLS = [
     "csb200_version", "csb200_strerror", "csb200_last_error", "csb200_device_count", "csb200_dict_create",
-    "csb200_dict_create_shard", "csb200_dict_destroy", "csb200_dict_shape", "csb200_batch_create",
+    "csb200_dict_create_shard", "csb200_dict_destroy", "csb200_dict_trim", "csb200_dict_shape", "csb200_batch_create",
     "csb200_batch_destroy", "csb200_batch_upload", "csb200_batch_upload_device", "csb200_batch_omp",
     "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
     "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp", "csb200_comm_unique_id",

@@ -88,6 +88,7 @@ struct csb200_dict {
     bool has_map = false;
     int num_sms = 148;
     std::mutex mu;
+    csb200_batch* workspace = nullptr;   // reused by the one-shot entry points (csb200_omp/gomp/mp)
     size_t esize() const { return dtype == CSB200_F32 ? 4 : 8; }
 };
 
@@ -325,9 +326,17 @@ int csb200_dict_create(const void* A, int64_t M, int64_t N, int64_t lda, int dty
     return csb200_dict_create_shard(A, M, N, lda, dtype, device, 0, N, out);
 }
 
+int csb200_dict_trim(csb200_dict* d) {
+    if (!d) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(d->mu);
+    if (d->workspace) { csb200_batch_destroy(d->workspace); d->workspace = nullptr; }
+    return CSB200_OK;
+}
+
 int csb200_dict_destroy(csb200_dict* d) {
     if (!d) return CSB200_OK;
     cudaSetDevice(d->device);
+    if (d->workspace) csb200_batch_destroy(d->workspace);
     cudaFree(d->dA);
     delete d;
     return CSB200_OK;
@@ -398,8 +407,12 @@ static int upload_common(csb200_batch* b, const void* src, int64_t ldb, int64_t 
     int rc = set_device(d);
     if (rc) return rc;
     const size_t es = d->esize();
-    if (d->ld != d->M) CU_TRY(cudaMemsetAsync(b->dB, 0, (size_t)d->ld * nsig * es, b->stream));
-    CU_TRY(cudaMemcpy2DAsync(b->dB, d->ld * es, src, ldb * es, d->M * es, nsig, kind, b->stream));
+    if (d->ld == d->M && ldb == d->M) {
+        CU_TRY(cudaMemcpyAsync(b->dB, src, (size_t)d->M * nsig * es, kind, b->stream));
+    } else {
+        if (d->ld != d->M) CU_TRY(cudaMemsetAsync(b->dB, 0, (size_t)d->ld * nsig * es, b->stream));
+        CU_TRY(cudaMemcpy2DAsync(b->dB, d->ld * es, src, ldb * es, d->M * es, nsig, kind, b->stream));
+    }
     return after_upload(b, nsig);
 }
 
@@ -584,55 +597,67 @@ int csb200_batch_last_solve_ms(csb200_batch* b, double* ms) {
 }
 
 // ---- one-shot host-buffer entry points ---------------------------------------------------------
+// The temporary batch of a one-shot call is kept on the dictionary handle and reused while it is large
+// enough (device allocation and release of ~2 GB per call would otherwise dominate small-k solves);
+// csb200_dict_trim() releases it.  The dictionary mutex serialises one-shot calls on one handle.
 static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t kcap, csb200_batch** out) {
     if (!d || !Bmat || nsig <= 0) return CSB200_ERR_INVALID_ARG;
-    int64_t cap = kcap < d->M ? kcap : d->M;
-    if (d->n_total < cap) cap = d->n_total;
-    int rc = csb200_batch_create(d, nsig, cap, out);
-    if (rc) return rc;
-    rc = csb200_batch_upload(*out, Bmat, ldb, nsig);
-    if (rc) { csb200_batch_destroy(*out); *out = nullptr; }
-    return rc;
+    int64_t cap = kcap < 1 ? 1 : kcap;
+    csb200_batch* w = d->workspace;
+    if (w && (w->cap_sig < nsig || w->kcap < cap || w->cap_sig > 4 * nsig + 1024)) {
+        csb200_batch_destroy(w);
+        d->workspace = w = nullptr;
+    }
+    if (!w) {
+        int rc = csb200_batch_create(d, nsig, cap, &w);
+        if (rc) return rc;
+        d->workspace = w;
+    }
+    *out = w;
+    return csb200_batch_upload(w, Bmat, ldb, nsig);
+}
+
+static int64_t support_cap(const csb200_dict* d, int64_t k) {
+    int64_t cap = k < d->M ? k : d->M;
+    return d->n_total < cap ? d->n_total : cap;
 }
 
 int csb200_omp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double eps,
                int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
-    if (k < 0) return CSB200_ERR_INVALID_ARG;
+    if (!d || k < 0) return CSB200_ERR_INVALID_ARG;
     if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
-    int rc = one_shot(d, Bmat, ldb, nsig, k, &b);
+    int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
     rc = csb200_batch_omp(b, k, eps);
     if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
-    csb200_batch_destroy(b);
     return rc;
 }
 
 int csb200_gomp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t l, int64_t k, double eps,
                 int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
-    if (k < 0 || l < 1) return CSB200_ERR_INVALID_ARG;
+    if (!d || k < 0 || l < 1) return CSB200_ERR_INVALID_ARG;
     if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
-    int rc = one_shot(d, Bmat, ldb, nsig, k, &b);
+    int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
     rc = csb200_batch_gomp(b, l, k, eps);
     if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
-    csb200_batch_destroy(b);
     return rc;
 }
 
 int csb200_mp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k, const int64_t* x0_idx,
               const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride, int64_t* sel_idx, double* coef,
               double* resnorm) {
-    if (iters_k < 0) return CSB200_ERR_INVALID_ARG;
-    if (!d || !Bmat || nsig <= 0) return CSB200_ERR_INVALID_ARG;
+    if (!d || iters_k < 0) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
-    int rc = csb200_batch_create(d, nsig, iters_k, &b);
+    int rc = one_shot(d, Bmat, ldb, nsig, iters_k, &b);
     if (rc) return rc;
-    rc = csb200_batch_upload(b, Bmat, ldb, nsig);
-    if (!rc) rc = csb200_batch_mp(b, iters_k, x0_idx, x0_val, x0_nnz, x0_stride);
+    rc = csb200_batch_mp(b, iters_k, x0_idx, x0_val, x0_nnz, x0_stride);
     if (!rc) rc = csb200_batch_download(b, iters_k, sel_idx, coef, nullptr, resnorm, nullptr);
-    csb200_batch_destroy(b);
     return rc;
 }
 

@@ -67,6 +67,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// Tile order.  Atom tiles are walked in bands of BAND tiles (BAND MiB of dictionary at M = 1024): within
+// a band the signal tile is the slow index, so the ~148 concurrently running CTAs share one band of A
+// (L2-resident, re-read by every signal tile) and a handful of residual tiles.  DRAM then sees the
+// residual matrix once per band instead of the whole dictionary once per wave.
+constexpr int BAND = 32;
+__device__ __forceinline__ void tile_coords(int tile, int tilesN, int tilesB, int& tn, int& tb) {
+    const int per_band = BAND * tilesB;
+    const int band = tile / per_band;
+    const int rem = tile - band * per_band;
+    const int left = tilesN - band * BAND;
+    const int bw = left < BAND ? left : BAND;
+    tb = rem / bw;
+    tn = band * BAND + (rem - tb * bw);
+}
+
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -106,7 +121,8 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const uint32_t par = (uint32_t)((c / STAGES) & 1) ^ 1u;
         const int tseq = c / kchunks, kc = c - tseq * kchunks;
         const int tile = (int)blockIdx.x + tseq * (int)gridDim.x;
-        const int tn = tile % tilesN, tb = tile / tilesN;
+        int tn, tb;
+        tile_coords(tile, tilesN, tilesB, tn, tb);
         mbar_wait(bar_empty + stg * 8, par);
         mbar_arrive_expect_tx(bar_full + stg * 8, STAGE_BYTES);
         const uint32_t dst = sm_base + stg * STAGE_BYTES;
@@ -128,7 +144,8 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     int chunk = 0;                     // flat chunk index being consumed
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tn = tile % tilesN, tb = tile / tilesN;
+        int tn, tb;
+        tile_coords(tile, tilesN, tilesB, tn, tb);
         double acc[8][4][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i)

@@ -9,9 +9,11 @@
 //   3. `add_column!(AiQR, a, pos)` (util.jl:123): orthogonalise the new atom against the
 //      active ones and append one column to the triangular factor R;
 //   4. `ldiv!(AiQR, b)` (:175): x_S = R^{-1} Q'b by back substitution;
-//   5. `residual!` (:152-161) and `norm(r)` for the eps test (:79,:132): r = b - A_S x_S,
-//      recomputed from b and the current coefficients exactly as the reference does, never
-//      down-dated.  r is written where the next correlation pass reads it.
+//   5. `residual!` (:152-161) and `norm(r)` for the eps test (:79,:132).  The reference recomputes
+//      r = b - A_S x_S from scratch; with x_S = R^{-1}Q'b that is r = b - QQ'b, which gains exactly
+//      one term per appended atom, so r <- r - q_t (q_t'b) is applied instead (one gather pass over
+//      A_S less; the two differ by rounding only, ~1e-16 ||b|| per step).  r is written where the
+//      next correlation pass reads it (subsystem (5): fused into the producer of the next pass).
 //
 // Orthogonalisation scheme.  UpdatableQRFactorizations.jl keeps an explicit (full) Q; at the
 // batched shapes a thin Q is 256 KiB..1 MiB per signal (16 GiB at the headline config), so Q is
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __
     int t = a.nnz[sig];
     int flags = 0;
     bool changed = false;
+    double nr2 = 0.0;
 
     for (int i = tid; i < t; i += UT) { ssel[i] = a.sel[(size_t)sig * kcap + i]; zs[i] = a.z[(size_t)sig * kcap + i]; }
     __syncthreads();
@@ -197,7 +200,17 @@ __global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __
             const double rho = sqrt(rho2);
             double sb = 0.0;
             for (int row = tid; row < ld; row += UT) sb += v[row] * (double)b[row];
-            const double zt = block_sum(sb, red) / rho;
+            const double zt = block_sum(sb, red) / rho;            // z_t = q_t' b
+            // residual: r = b - Q Q'b gains one term, r <- r - q_t z_t.  Identical to the reference's
+            // from-scratch b - A_S x_S (x_S = R^{-1} Q'b) up to rounding, at one pass less over A_S.
+            const double gam = zt / rho;
+            double s2r = 0.0;
+            for (int row = tid; row < ld; row += UT) {
+                const T rr = (T)((double)r[row] - gam * v[row]);
+                r[row] = rr;
+                s2r += (double)rr * (double)rr;
+            }
+            nr2 = block_sum(s2r, red);
             for (int i = tid; i < t; i += UT) Rf[i + (size_t)t * kcap] = h[i];
             if (tid == 0) { Rf[t + (size_t)t * kcap] = rho; zs[t] = zt; ssel[t] = j; }
             ++t;
@@ -208,21 +221,13 @@ __global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __
 
     double nr = a.resnorm[sig];
     if (changed) {
-        if (warp == 0) {                                           // x_S = R^{-1} Q'b
+        if (warp == 0) {                                           // x_S = R^{-1} Q'b  (`ldiv!`, :175)
             for (int i = lane; i < t; i += 32) w[i] = zs[i];
             __syncwarp();
             warp_backward_R(Rf, kcap, t, w, xs, lane);
         }
         __syncthreads();
-        double s2 = 0.0;
-        for (int row = tid; row < ld; row += UT) {                 // r = b - A_S x_S
-            double acc = (double)b[row];
-            for (int i = 0; i < t; ++i) acc -= (double)active_col(i)[row] * xs[i];
-            const T rr = (T)acc;
-            r[row] = rr;
-            s2 += (double)rr * (double)rr;
-        }
-        nr = sqrt(block_sum(s2, red));
+        nr = sqrt(nr2);
         for (int i = tid; i < t; i += UT) {
             a.sel[(size_t)sig * kcap + i] = ssel[i];
             a.z[(size_t)sig * kcap + i] = zs[i];

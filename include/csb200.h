@@ -68,6 +68,8 @@ int csb200_dict_create(const void* A, int64_t M, int64_t N, int64_t lda, int dty
 int csb200_dict_create_shard(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, int device,
                              int64_t n_offset, int64_t n_total, csb200_dict** out);
 int csb200_dict_destroy(csb200_dict* dict);
+/* Release the device workspace the one-shot calls (csb200_omp/gomp/mp) keep on the handle for reuse. */
+int csb200_dict_trim(csb200_dict* dict);
 int csb200_dict_shape(const csb200_dict* dict, int64_t* M, int64_t* N, int* dtype, int* device);
 
 /* ---- batch state -----------------------------------------------------------------------
