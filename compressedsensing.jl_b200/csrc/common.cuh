@@ -55,7 +55,7 @@ struct StateArgs {
     const int* pidx;
     int* nnz;             // [nsig]
     int* sel;             // [nsig][kcap]  support in selection order (global atom index)
-    double* Rf;           // [nsig][kcap*kcap] column-major upper-triangular factor (append order)
+    double* Rf;           // [nsig][kcap*kcap] column-major upper-triangular INVERSE factor R^{-1} (append order)
     double* z;            // [nsig][kcap]  Q'b
     double* x;            // [nsig][kcap]  coefficients aligned with sel
     double* resnorm;      // [nsig]

@@ -24,6 +24,7 @@
 //     shared-memory traffic is 12 LDS.128 per 64 DMMA per warp, ~19 % of the LDS bandwidth at
 //     DMMA peak.  TMA zero-fills out-of-range rows/columns, so no shape padding is needed.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace csb {
 
@@ -67,12 +68,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+constexpr int DEFAULT_BAND = 32;
 // Tile order.  Atom tiles are walked in bands of BAND tiles (BAND MiB of dictionary at M = 1024): within
 // a band the signal tile is the slow index, so the ~148 concurrently running CTAs share one band of A
 // (L2-resident, re-read by every signal tile) and a handful of residual tiles.  DRAM then sees the
 // residual matrix once per band instead of the whole dictionary once per wave.
-constexpr int BAND = 32;
-__device__ __forceinline__ void tile_coords(int tile, int tilesN, int tilesB, int& tn, int& tb) {
+__device__ __forceinline__ void tile_coords(int tile, int tilesN, int tilesB, int BAND, int& tn, int& tb) {
     const int per_band = BAND * tilesB;
     const int band = tile / per_band;
     const int rem = tile - band * per_band;
@@ -89,7 +90,7 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 
 __global__ void __launch_bounds__(THREADS, 1)
 corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
-                     int N, int nsig, int kchunks, int tilesN, int tilesB, int S, int P, int idx_offset,
+                     int N, int nsig, int kchunks, int tilesN, int tilesB, int band, int S, int P, int idx_offset,
                      double* __restrict__ pval, int* __restrict__ pidx) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -122,7 +123,7 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int tseq = c / kchunks, kc = c - tseq * kchunks;
         const int tile = (int)blockIdx.x + tseq * (int)gridDim.x;
         int tn, tb;
-        tile_coords(tile, tilesN, tilesB, tn, tb);
+        tile_coords(tile, tilesN, tilesB, band, tn, tb);
         mbar_wait(bar_empty + stg * 8, par);
         mbar_arrive_expect_tx(bar_full + stg * 8, STAGE_BYTES);
         const uint32_t dst = sm_base + stg * STAGE_BYTES;
@@ -145,7 +146,7 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int tn, tb;
-        tile_coords(tile, tilesN, tilesB, tn, tb);
+        tile_coords(tile, tilesN, tilesB, band, tn, tb);
         double acc[8][4][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -235,8 +236,11 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     const long long ntiles = (long long)tilesN * tilesB;
     if (ntiles <= 0) return cudaSuccess;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    static const int band_env = [] { const char* e = getenv("CSB200_GEMM_BAND"); return e ? atoi(e) : 0; }();
+    int band = band_env > 0 ? band_env : DEFAULT_BAND;
+    if (band > tilesN) band = tilesN;
     corr_gemm_f64_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN, tilesB,
-                                                            a.S, a.P, a.idx_offset, a.pval, a.pidx);
+                                                            band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
     return cudaGetLastError();
 }
 

@@ -22,11 +22,15 @@
 // run once, and a second time when ||v|| dropped below ||v_before||/sqrt(2) (Daniel-Gragg-
 // Kaufman-Stewart "twice is enough" re-orthogonalisation).  rho = ||v|| is computed from the
 // explicit vector (no 1 - h'h cancellation), R[:,t] = [h; rho], z_t = <v, b>/rho.
+// Instead of R the kernel stores T = R^{-1} (upper triangular, append order): appending the column
+// [h; rho] to R appends [-T h / rho; 1/rho] to T, and T h is the y above, already computed.  Every
+// triangular solve of the reference's `ldiv!` thereby becomes a triangular mat-vec whose output
+// elements are independent dot products -- no serial substitution chain inside the CTA.
 // The factor is kept in APPEND order; the reference keeps it in sorted-index order (insertion
 // at `findfirst(==(i), x.nzind)`), which is the same least-squares problem with its columns
 // permuted -- the host shim sorts (index, coefficient) pairs ascending when it builds the
-// SparseVector.  R (kcap x kcap), z and x live in global memory per signal and stay L2-resident
-// for the CTA that owns them; v (one signal-length vector) lives in shared memory.
+// SparseVector.  T (kcap x kcap), z and x live in global memory per signal; the CTA that owns a signal
+// stages T and one signal-length vector v in shared memory.
 #include "common.cuh"
 
 namespace csb {
@@ -91,40 +95,24 @@ __device__ void select_candidates(const double* __restrict__ pv, const int* __re
     __syncthreads();
 }
 
-// Column-oriented triangular solves on one warp; R is column-major with leading dimension kcap.
-// forward:  solve R' h = g   (g is destroyed);   backward: solve R y = w   (w is destroyed).
-__device__ __forceinline__ void warp_forward_RT(const double* R, int kcap, int t, double* g, double* h, int lane) {
-    for (int l = 0; l < t; ++l) {
-        const double hl = g[l] / R[l + (size_t)l * kcap];
-        __syncwarp();
-        if (lane == 0) h[l] = hl;
-        for (int i = l + 1 + lane; i < t; i += 32) g[i] -= R[l + (size_t)i * kcap] * hl;
-        __syncwarp();
-    }
-}
-__device__ __forceinline__ void warp_backward_R(const double* R, int kcap, int t, double* w, double* y, int lane) {
-    for (int l = t - 1; l >= 0; --l) {
-        const double yl = w[l] / R[l + (size_t)l * kcap];
-        __syncwarp();
-        if (lane == 0) y[l] = yl;
-        for (int i = lane; i < l; i += 32) w[i] -= R[i + (size_t)l * kcap] * yl;
-        __syncwarp();
-    }
-}
+// Shared-memory budget for keeping the inverse factor on chip (above it the kernel works on the copy in L2).
+constexpr int T_SMEM_MAX_K = 96;
 
 template <typename T>
-__global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __restrict__ Acache) {
+__global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem) {
     extern __shared__ double dsm[];
     const int ld = a.ld, kcap = a.kcap;
     double* v = dsm;                 // [ld]   working vector
-    double* g = v + ld;              // [kcap]
+    double* g = v + ld;              // [kcap]  A_S' v
     double* hh = g + kcap;           // [kcap]  Q'v of the current sweep
-    double* h = hh + kcap;           // [kcap]  accumulated Q'a  -> new column of R
-    double* w = h + kcap;            // [kcap]  scratch for back substitution
-    double* y = w + kcap;            // [kcap]
+    double* h = hh + kcap;           // [kcap]  accumulated Q'a
+    double* ys = h + kcap;           // [kcap]  accumulated R^{-1} Q'a
+    double* y = ys + kcap;           // [kcap]  R^{-1} Q'v of the current sweep
     double* zs = y + kcap;           // [kcap]  Q'b
     double* xs = zs + kcap;          // [kcap]  coefficients
-    int* ssel = reinterpret_cast<int*>(xs + kcap);   // [kcap] support, selection order
+    int* ssel = reinterpret_cast<int*>(xs + kcap);            // [kcap] support, selection order
+    const T** colp = reinterpret_cast<const T**>(ssel + ((kcap + 1) & ~1));   // [kcap] columns of the active atoms
+    double* Tsm = reinterpret_cast<double*>(colp + kcap);     // [kcap][ldT] inverse factor (optional)
     __shared__ double red[UW];
     __shared__ int red_i[UW];
     __shared__ int s_cand[MAX_S];
@@ -137,19 +125,24 @@ __global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __
     const T* A = static_cast<const T*>(a.A);
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
     T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
-    double* Rf = a.Rf + (size_t)sig * kcap * kcap;
+    double* Tg = a.Rf + (size_t)sig * kcap * kcap;                 // R^{-1}, column-major, ld = kcap
+    // working copy of R^{-1}: shared memory with an odd leading dimension (conflict-free column walks)
+    double* Tm = t_in_smem ? Tsm : Tg;
+    const int ldT = t_in_smem ? (kcap | 1) : kcap;
     int t = a.nnz[sig];
     int flags = 0;
     bool changed = false;
     double nr2 = 0.0;
 
-    for (int i = tid; i < t; i += UT) { ssel[i] = a.sel[(size_t)sig * kcap + i]; zs[i] = a.z[(size_t)sig * kcap + i]; }
+    for (int i = tid; i < t; i += UT) {
+        const int si = a.sel[(size_t)sig * kcap + i];
+        ssel[i] = si;
+        zs[i] = a.z[(size_t)sig * kcap + i];
+        colp[i] = Acache ? Acache + (size_t)i * ld : A + (size_t)(si - a.idx_offset) * ld;
+    }
+    if (t_in_smem)
+        for (int e = tid; e < t * kcap; e += UT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * ldT] = Tg[e]; }
     __syncthreads();
-
-    // column of the i-th active atom / of candidate j about to become the t-th
-    auto active_col = [&](int i) -> const T* {
-        return Acache ? Acache + (size_t)i * ld : A + (size_t)(ssel[i] - a.idx_offset) * ld;
-    };
 
     if (t < a.M) {                                                 // `nnz(x) < size(P.A, 1) || return x` (:63,:117)
         const size_t cbase = (size_t)sig * a.P * a.S;
@@ -170,28 +163,36 @@ __global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __
             double before2 = anorm2, rho2 = anorm2;
             for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
                 for (int i = warp; i < t; i += UW) {               // g = A_S' v
-                    const T* ai = active_col(i);
+                    const T* ai = colp[i];
                     double s = 0.0;
                     for (int row = lane; row < ld; row += 32) s += (double)ai[row] * v[row];
                     s = warp_sum(s);
                     if (lane == 0) g[i] = s;
                 }
                 __syncthreads();
-                if (warp == 0) {
-                    warp_forward_RT(Rf, kcap, t, g, hh, lane);     // hh = R^{-T} g = Q'v
-                    for (int i = lane; i < t; i += 32) w[i] = hh[i];
-                    __syncwarp();
-                    warp_backward_R(Rf, kcap, t, w, y, lane);      // y = R^{-1} hh
+                // hh = R^{-T} g = Q'v and y = R^{-1} hh as two triangular mat-vecs with the stored inverse:
+                // no substitution chain, every output element is an independent dot product.
+                for (int i = tid; i < t; i += UT) {
+                    double acc = 0.0;
+                    for (int l = 0; l <= i; ++l) acc = fma(Tm[l + i * ldT], g[l], acc);
+                    hh[i] = acc;
+                }
+                __syncthreads();
+                for (int i = tid; i < t; i += UT) {
+                    double acc = 0.0;
+                    for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], hh[l], acc);
+                    y[i] = acc;
+                    h[i] = sweep ? h[i] + hh[i] : hh[i];
+                    ys[i] = sweep ? ys[i] + acc : acc;
                 }
                 __syncthreads();
                 s2 = 0.0;
                 for (int row = tid; row < ld; row += UT) {         // v -= A_S y
                     double acc = v[row];
-                    for (int i = 0; i < t; ++i) acc -= (double)active_col(i)[row] * y[i];
+                    for (int i = 0; i < t; ++i) acc -= (double)colp[i][row] * y[i];
                     v[row] = acc;
                     s2 += acc * acc;
                 }
-                for (int i = tid; i < t; i += UT) h[i] = sweep ? h[i] + hh[i] : hh[i];
                 rho2 = block_sum(s2, red);
                 if (rho2 >= 0.5 * before2) break;                  // DGKS: one sweep was enough
                 before2 = rho2;
@@ -211,8 +212,18 @@ __global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __
                 s2r += (double)rr * (double)rr;
             }
             nr2 = block_sum(s2r, red);
-            for (int i = tid; i < t; i += UT) Rf[i + (size_t)t * kcap] = h[i];
-            if (tid == 0) { Rf[t + (size_t)t * kcap] = rho; zs[t] = zt; ssel[t] = j; }
+            // append the column [h; rho] to R  <=>  append [-R^{-1}h / rho; 1/rho] to R^{-1}
+            const double irho = 1.0 / rho;
+            for (int i = tid; i < t; i += UT) {
+                const double e = -ys[i] * irho;
+                Tg[i + (size_t)t * kcap] = e;
+                if (t_in_smem) Tsm[i + t * ldT] = e;
+            }
+            if (tid == 0) {
+                Tg[t + (size_t)t * kcap] = irho;
+                if (t_in_smem) Tsm[t + t * ldT] = irho;
+                zs[t] = zt; ssel[t] = j; colp[t] = aj;
+            }
             ++t;
             changed = true;
             __syncthreads();
@@ -221,18 +232,14 @@ __global__ void __launch_bounds__(UT) omp_update_kernel(StateArgs a, const T* __
 
     double nr = a.resnorm[sig];
     if (changed) {
-        if (warp == 0) {                                           // x_S = R^{-1} Q'b  (`ldiv!`, :175)
-            for (int i = lane; i < t; i += 32) w[i] = zs[i];
-            __syncwarp();
-            warp_backward_R(Rf, kcap, t, w, xs, lane);
-        }
-        __syncthreads();
-        nr = sqrt(nr2);
-        for (int i = tid; i < t; i += UT) {
+        for (int i = tid; i < t; i += UT) {                        // x_S = R^{-1} Q'b  (`ldiv!`, :175)
+            double acc = 0.0;
+            for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], zs[l], acc);
+            a.x[(size_t)sig * kcap + i] = acc;
             a.sel[(size_t)sig * kcap + i] = ssel[i];
             a.z[(size_t)sig * kcap + i] = zs[i];
-            a.x[(size_t)sig * kcap + i] = xs[i];
         }
+        nr = sqrt(nr2);
     }
     if (tid == 0) {
         a.nnz[sig] = t;
@@ -343,22 +350,28 @@ __global__ void nonfinite_check_kernel(const T* __restrict__ p, size_t n, int* f
     if (bad) atomicOr(flag, 1);
 }
 
-size_t update_smem_bytes(int ld, int kcap) { return (size_t)(ld + 7 * kcap) * sizeof(double) + (size_t)kcap * sizeof(int); }
+size_t update_smem_bytes(int ld, int kcap, bool t_in_smem) {
+    size_t bytes = (size_t)(ld + 7 * kcap) * sizeof(double) + (size_t)((kcap + 1) & ~1) * sizeof(int) +
+                   (size_t)kcap * sizeof(void*);
+    if (t_in_smem) bytes += (size_t)kcap * (kcap | 1) * sizeof(double);
+    return bytes;
+}
 
 }  // namespace
 
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
     if (a.nsig <= 0) return cudaSuccess;
-    const size_t smem = update_smem_bytes(a.ld, a.kcap);
+    const int t_in_smem = a.kcap <= T_SMEM_MAX_K ? 1 : 0;
+    const size_t smem = update_smem_bytes(a.ld, a.kcap, t_in_smem != 0);
     cudaError_t e;
     if (f32) {
         e = cudaFuncSetAttribute(omp_update_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        omp_update_kernel<float><<<a.nsig, UT, smem, st>>>(a, static_cast<const float*>(Acache));
+        omp_update_kernel<float><<<a.nsig, UT, smem, st>>>(a, static_cast<const float*>(Acache), t_in_smem);
     } else {
         e = cudaFuncSetAttribute(omp_update_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        omp_update_kernel<double><<<a.nsig, UT, smem, st>>>(a, static_cast<const double*>(Acache));
+        omp_update_kernel<double><<<a.nsig, UT, smem, st>>>(a, static_cast<const double*>(Acache), t_in_smem);
     }
     return cudaGetLastError();
 }

@@ -1,0 +1,143 @@
+# CompressedSensingB200.jl -- thin Julia shim over libcsb200.so (B200 / sm_100a greedy pursuit).
+#
+# Keeps the call surface of CompressedSensing.jl's greedy-pursuit path
+# (/root/reference/src/matchingpursuit.jl): `mp`, `omp`, `gomp` with the same positional and
+# keyword methods, returning the same `SparseVector{Float64,Int64}`.  Nothing is exported, as in
+# the reference (users write `using CompressedSensingB200: omp, gomp, mp`).  No CUDA.jl, no
+# kernels here: every call is one `ccall` into the C ABI declared in include/csb200.h.
+#
+# NOTE: Julia is not installed in the build image, so this file has been checked by reading only;
+# compressedsensing.jl_b200/__init__.py is the same shim over the same symbols in Python/ctypes
+# and is what the GPU tests exercise.  See INTEGRATION.md.
+module CompressedSensingB200
+
+using SparseArrays
+using Libdl
+
+const libcsb200 = get(ENV, "CSB200_LIB", joinpath(@__DIR__, "..", "libcsb200.so"))
+
+const CSB200_F64 = Cint(0)
+const CSB200_F32 = Cint(1)
+
+dtype_code(::Type{Float64}) = CSB200_F64
+dtype_code(::Type{Float32}) = CSB200_F32
+
+struct CSB200Error <: Exception
+    status::Cint
+    msg::String
+end
+Base.showerror(io::IO, e::CSB200Error) = print(io, "csb200 status $(e.status): $(e.msg)")
+
+function check(rc::Cint, ε = nothing)
+    rc == 0 && return
+    # the reference throws a String here (src/matchingpursuit.jl:74,127)
+    rc == -2 && throw("ε = $ε has to be non-negative")
+    rc == -9 && throw(DimensionMismatch(unsafe_string(ccall((:csb200_strerror, libcsb200), Cstring, (Cint,), rc))))
+    msg = unsafe_string(ccall((:csb200_strerror, libcsb200), Cstring, (Cint,), rc))
+    detail = unsafe_string(ccall((:csb200_last_error, libcsb200), Cstring, ()))
+    throw(CSB200Error(rc, isempty(detail) ? msg : "$msg: $detail"))
+end
+
+# ---------------------------------------------------------------------------------------------
+# Dictionary handle: A stays resident in HBM; reuse it across calls.
+mutable struct Dictionary{T<:Union{Float32,Float64}}
+    handle::Ptr{Cvoid}
+    M::Int
+    N::Int
+    function Dictionary(A::StridedMatrix{T}; device::Integer = 0) where {T<:Union{Float32,Float64}}
+        stride(A, 1) == 1 || (A = Matrix(A))
+        M, N = size(A)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve A check(ccall((:csb200_dict_create, libcsb200), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Ref{Ptr{Cvoid}}),
+            pointer(A), M, N, max(stride(A, 2), M), dtype_code(T), device, h))
+        d = new{T}(h[], M, N)
+        finalizer(d) do x
+            x.handle == C_NULL || ccall((:csb200_dict_destroy, libcsb200), Cint, (Ptr{Cvoid},), x.handle)
+            x.handle = C_NULL
+        end
+        return d
+    end
+end
+Dictionary(A::AbstractMatrix; kw...) = Dictionary(Matrix{Float64}(A); kw...)   # anything else is copied
+Base.size(D::Dictionary) = (D.M, D.N)
+Base.size(D::Dictionary, i::Int) = size(D)[i]
+Base.eltype(::Dictionary{T}) where {T} = T
+
+const MatOrDict = Union{AbstractMatrix,Dictionary}
+as_dictionary(A::Dictionary) = A
+as_dictionary(A::AbstractMatrix) = Dictionary(A)
+signal_eltype(A::Dictionary{T}) where {T} = T
+signals(D::Dictionary{T}, b::AbstractVecOrMat) where {T} = begin
+    size(b, 1) == D.M || throw(DimensionMismatch("A has $(D.M) rows, b has length $(size(b, 1))"))
+    B = Matrix{T}(reshape(b, size(b, 1), :))          # contiguous copy in the dictionary's element type
+    B
+end
+
+# (index, coefficient) pairs come back in SELECTION order, 0-based; the reference keeps x sorted by index
+# (`x[i] = NaN` sorted insert, src/util.jl:120-122)
+function to_sparse(N::Int, sel::AbstractVector{Int64}, coef::AbstractVector{Float64}, nnz::Integer)
+    idx = sel[1:nnz] .+ 1
+    p = sortperm(idx)
+    return SparseVector(N, idx[p], coef[1:nnz][p])
+end
+
+function run_omp_like(fn::Symbol, D::Dictionary, b, l::Int, ε::Real, k::Int)
+    B = signals(D, b)
+    nsig = size(B, 2)
+    stride = max(min(k, D.M, D.N), 1)
+    sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
+    nnz = Vector{Int64}(undef, nsig); res = Vector{Float64}(undef, nsig); its = Vector{Int64}(undef, nsig)
+    GC.@preserve B sel coef nnz res its begin
+        rc = if fn === :omp
+            ccall((:csb200_omp, libcsb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cdouble, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}),
+                D.handle, pointer(B), D.M, nsig, k, Float64(ε), sel, coef, nnz, res, its)
+        else
+            ccall((:csb200_gomp, libcsb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Cdouble, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}),
+                D.handle, pointer(B), D.M, nsig, l, k, Float64(ε), sel, coef, nnz, res, its)
+        end
+        check(rc, ε)
+    end
+    xs = [to_sparse(D.N, view(sel, :, s), view(coef, :, s), nnz[s]) for s in 1:nsig]
+    return b isa AbstractVector ? xs[1] : xs
+end
+
+# ---------------------------------------------------------------------------------------------
+# omp  (src/matchingpursuit.jl:73-91)
+function omp(A::MatOrDict, b::AbstractVecOrMat, ε::Real, k::Int = size(A, 1))
+    ε ≥ 0 || throw("ε = $ε has to be non-negative")
+    run_omp_like(:omp, as_dictionary(A), b, 1, ε, k)
+end
+omp(A::MatOrDict, b::AbstractVecOrMat, k::Int) = omp(A, b, eps(eltype(A)), k)
+omp(A::MatOrDict, b::AbstractVecOrMat; max_residual = eps(eltype(A)), sparsity = min(size(A)...)) =
+    omp(A, b, max_residual, sparsity)
+
+# gomp  (src/matchingpursuit.jl:126-148)
+function gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, ε::Real, k::Int = size(A, 1))
+    ε ≥ 0 || throw("ε = $ε has to be non-negative")
+    run_omp_like(:gomp, as_dictionary(A), b, l, ε, k)
+end
+gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, k::Int) = gomp(A, b, l, eps(eltype(A)), k)
+gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int; max_residual = eps(eltype(A)), sparsity = size(A, 2)) =
+    gomp(A, b, l, max_residual, sparsity)
+
+# mp  (src/matchingpursuit.jl:34-40); x is an optional warm start (single-signal form)
+function mp(A::MatOrDict, b::AbstractVector, k::Int, x::SparseVector = spzeros(size(A, 2)))
+    D = as_dictionary(A)
+    B = signals(D, b)
+    stride = max(k, 1)
+    sel = Vector{Int64}(undef, stride); coef = Vector{Float64}(undef, stride); res = Vector{Float64}(undef, 1)
+    x0i = Int64.(x.nzind .- 1); x0v = Float64.(x.nzval); x0n = Int64[length(x0i)]
+    GC.@preserve B sel coef res x0i x0v x0n check(ccall((:csb200_mp, libcsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}),
+        D.handle, pointer(B), D.M, 1, k, isempty(x0i) ? C_NULL : pointer(x0i), isempty(x0i) ? C_NULL : pointer(x0v),
+        isempty(x0i) ? C_NULL : pointer(x0n), max(length(x0i), 1), sel, coef, res))
+    for j in 1:k                      # x[i] += dot(view(A,:,i), r), in iteration order (:29)
+        sel[j] ≥ 0 && (x[sel[j] + 1] += coef[j])
+    end
+    return x
+end
+
+end # module
