@@ -31,7 +31,8 @@ import numpy as np
 
 __all__ = [
     "SparseVector", "Dictionary", "Batch", "omp", "gomp", "mp", "lib", "LIB_PATH", "CSB200Error",
-    "device_count", "F64", "F32", "ShardComm", "omp_sharded",
+    "device_count", "F64", "F32", "ShardComm", "omp_sharded", "shard_range", "owner_of", "pick_global",
+    "exchange_unique_id",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -405,6 +406,55 @@ def mp(A, b, k: int, x=None, device: int = 0):
 
 
 # ------------------------------------------------------------------------------------------------
+# Multi-GPU host logic (one process per GPU).  Independent signals are split with no communication;
+# a single huge dictionary is column-sharded.
+def shard_range(n: int, nranks: int, rank: int):
+    """Contiguous [lo, hi) slice of n units owned by `rank`: sizes differ by at most one, lower ranks first."""
+    if not (0 <= rank < nranks):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n, nranks)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def owner_of(index: int, n: int, nranks: int) -> int:
+    """Rank whose shard_range contains `index`."""
+    base, extra = divmod(n, nranks)
+    cut = extra * (base + 1)
+    return index // (base + 1) if index < cut else extra + (index - cut) // max(base, 1)
+
+
+def pick_global(records):
+    """The per-iteration exchange of the column-sharded solve, on the host: given every rank's best
+    (|c|, global atom index) choose the winner exactly as global_pick_kernel does -- largest |c|, lowest
+    index on ties (Julia `argmax`).  Returns (rank, value, index); index -1 if no rank has a candidate."""
+    best = (-1, -1.0, -1)
+    for g, (v, i) in enumerate(records):
+        if i < 0:
+            continue
+        if best[2] < 0 or v > best[1] or (v == best[1] and i < best[2]):
+            best = (g, float(v), int(i))
+    return best
+
+
+def exchange_unique_id(dist, rank: int, make_id=None) -> bytes:
+    """Rank 0 creates the 128-byte NCCL unique id, everyone receives it through torch.distributed
+    (any backend; the tests use gloo)."""
+    import torch
+    make_id = make_id or ShardComm.unique_id
+    buf = torch.zeros(NCCL_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        buf = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
+    if buf.device.type == "cpu" and dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = buf.to(dev)
+        dist.broadcast(buf, src=0)
+        buf = buf.cpu()
+    else:
+        dist.broadcast(buf, src=0)
+    return bytes(buf.numpy().tobytes())
+
+
 class ShardComm:
     """NCCL communicator owned by the library (`csb200_comm`), one per process/GPU."""
 

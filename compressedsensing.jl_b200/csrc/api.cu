@@ -696,6 +696,14 @@ int csb200_debug_get_residual(csb200_batch* b, void* out) {
     return CSB200_OK;
 }
 
-// ---- column-sharded mode: implemented in sharded.cu ---------------------------------------------
+// ---- column-sharded mode: implemented in sharded.cu; these are its (non-public) accessors ---------
+int csb200_internal_dict_info(const csb200_dict* d, const void** dA, int64_t* M, int64_t* N, int64_t* ld, int* dtype,
+                              int* device, int64_t* n_offset, int64_t* n_total) {
+    if (!d) return CSB200_ERR_INVALID_ARG;
+    *dA = d->dA; *M = d->M; *N = d->N; *ld = d->ld; *dtype = d->dtype; *device = d->device;
+    *n_offset = d->n_offset; *n_total = d->n_total;
+    return CSB200_OK;
+}
+void csb200_internal_set_error(const char* msg) { g_last_error = msg ? msg : ""; }
 
 }  // extern "C"

@@ -68,11 +68,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-constexpr int DEFAULT_BAND = 32;
-// Tile order.  Atom tiles are walked in bands of BAND tiles (BAND MiB of dictionary at M = 1024): within
-// a band the signal tile is the slow index, so the ~148 concurrently running CTAs share one band of A
-// (L2-resident, re-read by every signal tile) and a handful of residual tiles.  DRAM then sees the
-// residual matrix once per band instead of the whole dictionary once per wave.
+// Tile order.  Atom tiles are walked in bands of `band` tiles; within a band the signal tile is the slow
+// index.  band = tilesN (the default) is plain atom-fastest order: the ~148 concurrently running CTAs cover
+// every atom tile of ~2.3 signal tiles.  Measured on B200 at the headline shape (profiles/gemm_band_sweep_r01.md):
+// narrower bands cut DRAM reads from 6.0 GB to 1.55 GB per launch (the band stays L2-resident) but cost
+// 0.8-2.8 % of kernel time, and DRAM is at 2.3 % of its bandwidth either way on this tensor-bound kernel,
+// so the default keeps the faster order; CSB200_GEMM_BAND overrides it.
+constexpr int DEFAULT_BAND = 0;   // 0 = tilesN
 __device__ __forceinline__ void tile_coords(int tile, int tilesN, int tilesB, int BAND, int& tn, int& tb) {
     const int per_band = BAND * tilesB;
     const int band = tile / per_band;
@@ -238,7 +240,7 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     static const int band_env = [] { const char* e = getenv("CSB200_GEMM_BAND"); return e ? atoi(e) : 0; }();
     int band = band_env > 0 ? band_env : DEFAULT_BAND;
-    if (band > tilesN) band = tilesN;
+    if (band <= 0 || band > tilesN) band = tilesN;
     corr_gemm_f64_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN, tilesB,
                                                             band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
     return cudaGetLastError();

@@ -1,10 +1,312 @@
-// Column-sharded single-dictionary OMP (one process per GPU, NCCL over NVLink) -- placeholder
-// entry points; see include/csb200.h.  Filled in after the single-GPU path is parity-green.
+// Column-sharded single-dictionary OMP: one process per GPU, NCCL over NVLink (see include/csb200.h).
+//
+// BASELINE config 4 (8192 x 1 048 576 FP32 = 32 GiB) does not fit one GPU's sensible share, and the
+// correlation c = A'r is separable by columns: rank g owns atoms [n_offset, n_offset + N_local).
+// Everything else in `update!` is O(M k) and is REPLICATED: every rank keeps b, r, the support, R^{-1},
+// Q'b and runs the same deterministic update kernel on the same inputs, so replicas stay bit-identical
+// and nothing but the candidate atom ever crosses NVLink.
+//
+// Per iteration, all on one stream with no host round trip:
+//   1. fused GEMV + |c| argmax over the local shard                    (corr_gemv.cu)
+//   2. local_best: reduce the per-block candidates to one record  { |c|, global index, atom column }
+//   3. ncclAllGather of the records (16 B + M elements per rank; 8 x 32 KB at config 4).  NCCL has no
+//      MAXLOC and the winner's rank is data dependent, so a broadcast would need a host decision;
+//      gathering every rank's candidate column instead keeps the exchange root-free and on-stream.
+//   4. global_pick: every rank picks the same winner (largest |c|, lowest global index on ties -- Julia
+//      `argmax`, src/matchingpursuit.jl:184) and stores its column in slot nnz of the active-atom cache
+//   5. the per-signal update kernel (update.cu) reading atoms from that cache.
+// NCCL is dlopen'ed so that single-GPU users carry no dependency on it.
 #include "../../include/csb200.h"
+#include "common.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace csb;
+
+// accessors implemented in api.cu
 extern "C" {
-int csb200_comm_unique_id(void*) { return CSB200_ERR_UNSUPPORTED; }
-int csb200_comm_create(const void*, int, int, int, csb200_comm**) { return CSB200_ERR_UNSUPPORTED; }
-int csb200_comm_destroy(csb200_comm*) { return CSB200_OK; }
-int csb200_omp_sharded(csb200_dict*, csb200_comm*, const void*, int64_t, double, int64_t*, double*, int64_t*, double*,
-                       int64_t*, double*) { return CSB200_ERR_UNSUPPORTED; }
+int csb200_internal_dict_info(const csb200_dict* d, const void** dA, int64_t* M, int64_t* N, int64_t* ld, int* dtype,
+                              int* device, int64_t* n_offset, int64_t* n_total);
+void csb200_internal_set_error(const char* msg);
 }
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+    });
+    return api;
+}
+
+int fail_nccl(ncclResult_t r, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, nccl().GetErrorString ? nccl().GetErrorString(r) : "nccl error");
+    csb200_internal_set_error(buf);
+    return CSB200_ERR_NCCL;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    csb200_internal_set_error(buf);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? CSB200_ERR_OOM : CSB200_ERR_CUDA;
+}
+#define CU_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail_cuda(e__, #expr); } while (0)
+#define NC_TRY(expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) return fail_nccl(r__, #expr); } while (0)
+
+// One exchange record: header {|c| as double, global atom index, pad} followed by the atom's column.
+constexpr int REC_HDR = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) local_best_kernel(const double* __restrict__ pval, const int* __restrict__ pidx,
+                                                         int P, const T* __restrict__ A, int ld, int idx_offset,
+                                                         unsigned char* __restrict__ rec) {
+    __shared__ double sv[8];
+    __shared__ int si[8];
+    __shared__ int s_best;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double bv = -1.0;
+    int bi = INT_MAX;
+    for (int c = tid; c < P; c += 256) {
+        const int i = pidx[c];
+        if (i >= 0 && cand_better(pval[c], i, bv, bi)) { bv = pval[c]; bi = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        bv = sv[0]; bi = si[0];
+        for (int w = 1; w < 8; ++w) if (cand_better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+        *reinterpret_cast<double*>(rec) = bv;
+        *reinterpret_cast<int*>(rec + 8) = (bi == INT_MAX) ? -1 : bi;
+        *reinterpret_cast<int*>(rec + 12) = 0;
+        s_best = (bi == INT_MAX) ? -1 : bi;
+    }
+    __syncthreads();
+    T* col = reinterpret_cast<T*>(rec + REC_HDR);
+    if (s_best >= 0) {
+        const T* src = A + (size_t)(s_best - idx_offset) * ld;
+        for (int row = tid; row < ld; row += 256) col[row] = src[row];
+    } else {
+        for (int row = tid; row < ld; row += 256) col[row] = (T)0;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) global_pick_kernel(const unsigned char* __restrict__ recs, int nranks,
+                                                          size_t rec_bytes, int ld, const int* __restrict__ nnz,
+                                                          int kcap, T* __restrict__ Acache, double* __restrict__ cand_val,
+                                                          int* __restrict__ cand_idx) {
+    __shared__ int s_rank;
+    if (threadIdx.x == 0) {
+        double bv = -1.0;
+        int bi = INT_MAX, br = -1;
+        for (int g = 0; g < nranks; ++g) {
+            const unsigned char* rec = recs + (size_t)g * rec_bytes;
+            const double v = *reinterpret_cast<const double*>(rec);
+            const int i = *reinterpret_cast<const int*>(rec + 8);
+            if (i >= 0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; br = g; }
+        }
+        cand_val[0] = bv;
+        cand_idx[0] = (br < 0) ? -1 : bi;
+        s_rank = br;
+    }
+    __syncthreads();
+    const int t = nnz[0];
+    if (s_rank < 0 || t >= kcap) return;
+    const T* src = reinterpret_cast<const T*>(recs + (size_t)s_rank * rec_bytes + REC_HDR);
+    T* dst = Acache + (size_t)t * ld;
+    for (int row = threadIdx.x; row < ld; row += 256) dst[row] = src[row];
+}
+
+}  // namespace
+
+struct csb200_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1, device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+};
+
+extern "C" {
+
+int csb200_comm_unique_id(void* id_bytes) {
+    if (!id_bytes) return CSB200_ERR_INVALID_ARG;
+    if (!nccl().ok) { csb200_internal_set_error("libnccl.so.2 could not be loaded"); return CSB200_ERR_NCCL; }
+    static_assert(sizeof(ncclUniqueId) == CSB200_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC_TRY(nccl().GetUniqueId(&id));
+    memcpy(id_bytes, &id, sizeof id);
+    return CSB200_OK;
+}
+
+int csb200_comm_create(const void* id_bytes, int rank, int nranks, int device, csb200_comm** out) {
+    if (!id_bytes || !out || nranks < 1 || rank < 0 || rank >= nranks) return CSB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!nccl().ok) { csb200_internal_set_error("libnccl.so.2 could not be loaded"); return CSB200_ERR_NCCL; }
+    CU_TRY(cudaSetDevice(device));
+    csb200_comm* c = new (std::nothrow) csb200_comm;
+    if (!c) return CSB200_ERR_OOM;
+    c->rank = rank; c->nranks = nranks; c->device = device;
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclResult_t r = nccl().CommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) { delete c; return fail_nccl(r, "ncclCommInitRank"); }
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { nccl().CommDestroy(c->comm); delete c; return fail_cuda(e, "cudaStreamCreate"); }
+    *out = c;
+    return CSB200_OK;
+}
+
+int csb200_comm_destroy(csb200_comm* c) {
+    if (!c) return CSB200_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    delete c;
+    return CSB200_OK;
+}
+
+int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_t k, double eps, int64_t* sel_idx,
+                       double* coef, int64_t* nnz_out, double* resnorm, int64_t* iters_out, double* corr_ms) {
+    if (!shard || !c || !b || k < 0) return CSB200_ERR_INVALID_ARG;
+    if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    const void* dA; int64_t M, N, ld, n_offset, n_total; int dtype, device;
+    int rc = csb200_internal_dict_info(shard, &dA, &M, &N, &ld, &dtype, &device, &n_offset, &n_total);
+    if (rc) return rc;
+    if (device != c->device) { csb200_internal_set_error("shard and communicator live on different devices"); return CSB200_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(cudaSetDevice(device));
+    const bool f32 = dtype == CSB200_F32;
+    const size_t es = f32 ? 4 : 8;
+    int64_t kcap = k < M ? k : M;
+    if (n_total < kcap) kcap = n_total;
+    if (kcap < 1) kcap = 1;
+    const int P = (int)((N + PBLK - 1) / PBLK);
+    const size_t rec_bytes = (REC_HDR + (size_t)ld * es + 15) / 16 * 16;
+    cudaStream_t st = c->stream;
+
+    // device scratch (one allocation)
+    struct Off { size_t b, r, acache, pval, pidx, cval, cidx, nnz, sel, T, z, x, res, it, done, flags, send, recv, end; } o;
+    size_t p = 0;
+    auto take = [&](size_t bytes) { size_t at = p; p += (bytes + 255) / 256 * 256; return at; };
+    o.b = take(ld * es); o.r = take(ld * es); o.acache = take((size_t)ld * kcap * es);
+    o.pval = take((size_t)P * 8); o.pidx = take((size_t)P * 4); o.cval = take(8); o.cidx = take(4);
+    o.nnz = take(4); o.sel = take(kcap * 4); o.T = take((size_t)kcap * kcap * 8); o.z = take(kcap * 8); o.x = take(kcap * 8);
+    o.res = take(8); o.it = take(4); o.done = take(4); o.flags = take(4);
+    o.send = take(rec_bytes); o.recv = take(rec_bytes * c->nranks); o.end = p;
+    unsigned char* base = nullptr;
+    CU_TRY(cudaMalloc(&base, o.end));
+    std::vector<cudaEvent_t> ev(2 * (size_t)k);
+    int status = CSB200_OK;
+    auto cleanup = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); cudaFree(base); };
+    for (auto& e : ev) { e = nullptr; }
+    for (auto& e : ev) { cudaError_t ce = cudaEventCreate(&e); if (ce != cudaSuccess) { cleanup(); return fail_cuda(ce, "cudaEventCreate"); } }
+
+    do {
+        cudaError_t e = cudaMemsetAsync(base, 0, o.end, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(base + o.b, b, (size_t)M * es, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { status = fail_cuda(e, "upload signal"); break; }
+
+        CorrArgs ca;
+        ca.A = dA; ca.R = base + o.r; ca.M = (int)M; ca.ld = (int)ld; ca.N = (int)N; ca.nsig = 1; ca.S = 1; ca.P = P;
+        ca.idx_offset = (int)n_offset; ca.pval = (double*)(base + o.pval); ca.pidx = (int*)(base + o.pidx);
+        StateArgs sa;
+        sa.A = dA; sa.B = base + o.b; sa.R = base + o.r; sa.M = (int)M; sa.ld = (int)ld; sa.N = (int)N; sa.nsig = 1;
+        sa.kcap = (int)kcap; sa.S = 1; sa.P = 1; sa.take = 1; sa.idx_offset = (int)n_offset; sa.ignore_done = 0; sa.eps = eps;
+        sa.pval = (double*)(base + o.cval); sa.pidx = (int*)(base + o.cidx);
+        sa.nnz = (int*)(base + o.nnz); sa.sel = (int*)(base + o.sel); sa.Rf = (double*)(base + o.T);
+        sa.z = (double*)(base + o.z); sa.x = (double*)(base + o.x); sa.resnorm = (double*)(base + o.res);
+        sa.iters = (int*)(base + o.it); sa.done = (int*)(base + o.done); sa.flags = (int*)(base + o.flags);
+
+        int* dflag = (int*)(base + o.flags);
+        e = launch_nonfinite_check(base + o.b, (size_t)ld, f32, dflag, st);
+        int hflag = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hflag, dflag, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { status = fail_cuda(e, "nonfinite check"); break; }
+        if (hflag) { status = CSB200_ERR_NONFINITE_INPUT; break; }
+        e = launch_reset_state(sa, f32, st);
+        if (e != cudaSuccess) { status = fail_cuda(e, "reset_state"); break; }
+
+        for (int64_t it = 0; it < k && status == CSB200_OK; ++it) {
+            cudaEventRecord(ev[2 * it], st);
+            e = launch_corr_gemv(ca, f32, st);
+            cudaEventRecord(ev[2 * it + 1], st);
+            if (e != cudaSuccess) { status = fail_cuda(e, "corr_gemv"); break; }
+            if (f32) local_best_kernel<float><<<1, 256, 0, st>>>(ca.pval, ca.pidx, P, (const float*)dA, (int)ld, (int)n_offset, base + o.send);
+            else local_best_kernel<double><<<1, 256, 0, st>>>(ca.pval, ca.pidx, P, (const double*)dA, (int)ld, (int)n_offset, base + o.send);
+            ncclResult_t nr = nccl().AllGather(base + o.send, base + o.recv, rec_bytes, ncclChar, c->comm, st);
+            if (nr != ncclSuccess) { status = fail_nccl(nr, "ncclAllGather"); break; }
+            if (f32) global_pick_kernel<float><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (float*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+            else global_pick_kernel<double><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (double*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+            e = launch_omp_update(sa, f32, st, base + o.acache);
+            if (e != cudaSuccess) { status = fail_cuda(e, "omp_update"); break; }
+        }
+        if (status) break;
+        std::vector<int> hsel(kcap);
+        std::vector<double> hx(kcap);
+        int hn = 0, hit = 0;
+        double hres = 0;
+        e = cudaMemcpyAsync(hsel.data(), base + o.sel, kcap * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hx.data(), base + o.x, kcap * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hn, base + o.nnz, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hit, base + o.it, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hres, base + o.res, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { status = fail_cuda(e, "download"); break; }
+        for (int64_t j = 0; j < k; ++j) {
+            if (sel_idx) sel_idx[j] = j < hn ? hsel[j] : -1;
+            if (coef) coef[j] = j < hn ? hx[j] : 0.0;
+        }
+        if (nnz_out) *nnz_out = hn;
+        if (iters_out) *iters_out = hit;
+        if (resnorm) *resnorm = hres;
+        if (corr_ms) {
+            double tot = 0;
+            for (int64_t it = 0; it < k; ++it) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * it], ev[2 * it + 1]); tot += ms; }
+            *corr_ms = tot;
+        }
+    } while (0);
+    cudaStreamSynchronize(st);
+    cleanup();
+    return status;
+}
+
+}  // extern "C"

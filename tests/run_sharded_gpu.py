@@ -1,0 +1,63 @@
+"""torchrun entry: column-sharded OMP over N GPUs against the oracle and the single-GPU path.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/run_sharded_gpu.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+from oracle import pursuit_oracle as po  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cs = ge.load_package()
+    uid = cs.exchange_unique_id(dist, rank)
+    comm = cs.ShardComm(uid, rank, world, local)
+    ok = True
+    for dtype, M, N, k in [(np.float32, 512, 40000, 24), (np.float64, 256, 9001, 10)]:
+        rng = np.random.default_rng(5)                       # same bytes on every rank
+        A = po.gaussian_dictionary(rng, M, N, dtype)
+        A[:, N - 3] = A[:, 7]                                # a tie between the first and the last shard
+        x0 = po.sparse_vector(rng, N, k - 1)
+        x0.setindex(7, 1.5)
+        b = (A[:, x0.nzind].astype(np.float64) @ np.asarray(x0.nzval)).astype(dtype)
+        b = po.perturb(rng, b, 5e-3)
+        lo, hi = cs.shard_range(N, world, rank)
+        with cs.Dictionary(np.asfortranarray(A[:, lo:hi]), device=local, n_offset=lo, n_total=N) as shard:
+            x, info = cs.omp_sharded(shard, comm, b, k)
+        # every rank must hold the same answer
+        mine = torch.tensor(np.concatenate([x.nzind.astype(np.float64), x.nzval, [info["resnorm"]]]), device="cuda")
+        ref0 = mine.clone()
+        dist.broadcast(ref0, src=0)
+        ok &= bool(torch.equal(mine, ref0))
+        if rank == 0:
+            t = po.Trace()
+            ref = po.omp(A, b, k, trace=t)
+            with cs.Dictionary(A, device=local) as D:
+                x1 = cs.omp(D, b, k)
+            ok &= info["order"].tolist() == t.order()
+            ok &= x.nzind.tolist() == ref.nzind == x1.nzind.tolist()
+            ok &= bool(np.allclose(x.nzval, ref.nzval, rtol=2e-5 if dtype == np.float32 else 1e-10, atol=1e-6 if dtype == np.float32 else 1e-11))
+            ok &= bool(np.allclose(x.nzval, x1.nzval, rtol=1e-12, atol=1e-13))     # sharded == unsharded GPU
+            ok &= 7 in x.nzind.tolist() and (N - 3) not in x.nzind.tolist()
+            print(f"dtype={np.dtype(dtype).name} world={world} ok={ok} corr_ms={info['corr_ms']:.3f}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    comm.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SHARDED_OK" if int(flag.item()) == 1 else "SHARDED_FAIL", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
