@@ -1,0 +1,186 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE.json configs that are not the bench.py headline (C1, C3, C4, C5).
+
+    python tools/bench_configs.py --config c1|c3|c4|c5 [--scale f]
+    python -m torch.distributed.run --nproc-per-node 8 ... tools/bench_configs.py --config c4     (column-sharded)
+
+Prints one JSON line per config (rank 0).  These are NOT the driver's bench line; they back the numbers quoted in
+DESIGN.md.  Inputs are synthetic (Gaussian unit-norm atoms, planted k-sparse +-1 signals), generated on the GPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+HBM_PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+FP64_PEAK = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAK.json")))["peak_tflops"]
+
+
+def make_problem(M, N, k, B, dtype, dev, seed=1234, noise=0.0):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    A_t = torch.empty(N, M, dtype=torch.float64, device=dev)
+    for n0 in range(0, N, 65536):
+        n1 = min(N, n0 + 65536)
+        blk = torch.randn(n1 - n0, M, dtype=torch.float64, device=dev, generator=g)
+        blk -= 1e-6 * blk.mean(dim=1, keepdim=True)
+        blk /= blk.norm(dim=1, keepdim=True)
+        A_t[n0:n1] = blk
+    idx = torch.stack([torch.randperm(N, device=dev, generator=g)[:k] for _ in range(min(B, 64))])
+    if B > 64:
+        idx = torch.cat([idx, torch.randint(0, N, (B - 64, k), device=dev, generator=g)])   # rare repeats are harmless
+    sign = torch.randint(0, 2, (B, k), device=dev, generator=g).to(torch.float64) * 2 - 1
+    B_t = torch.empty(B, M, dtype=torch.float64, device=dev)
+    step = max(1, (1 << 26) // (k * M))
+    for s0 in range(0, B, step):
+        s1 = min(B, s0 + step)
+        B_t[s0:s1] = (A_t[idx[s0:s1]] * sign[s0:s1, :, None]).sum(dim=1)
+    if noise:
+        e = torch.randn(B, M, dtype=torch.float64, device=dev, generator=g)
+        B_t += e * (noise / e.norm(dim=1, keepdim=True))
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    A_np = A_t.to(td).cpu().numpy().T
+    B_np = B_t.to(td).cpu().numpy().T
+    return A_np, B_np, idx.cpu().numpy()
+
+
+def c1(cs, dev, args):
+    M, N, k = 128, 256, 8
+    A, Bm, idx = make_problem(M, N, k, 64, np.float64, dev)
+    out = {}
+    with cs.Dictionary(A) as D:
+        for name, nsig in [("single_signal", 1), ("batch64", 64)]:
+            with cs.Batch(D, nsig, k) as b:
+                b.upload(Bm[:, :nsig])
+                for _ in range(20):
+                    b.omp(k, 2.2e-16)
+                ms = []
+                for _ in range(200):
+                    b.omp(k, 2.2e-16)
+                    ms.append(b.last_solve_ms())
+                out[name + "_us_per_solve_call"] = 1e3 * float(np.median(ms))
+        t0 = time.perf_counter()
+        for _ in range(200):
+            cs.omp(D, Bm[:, 0], k)
+        out["one_shot_host_api_us"] = 1e6 * (time.perf_counter() - t0) / 200
+    out.update(config="c1 omp 128x256 k=8 f64", dict_bytes=M * N * 8, iterations=k)
+    return out
+
+
+def c3(cs, dev, args):
+    M, N, k, l, B = 2048, 32768, 64, 4, int(8192 * args.scale)
+    A, Bm, idx = make_problem(M, N, k, B, np.float64, dev)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as b:
+        b.upload(Bm)
+        b.gomp(l, k, 2.2e-16)
+        b.profile(True)
+        b.gomp(l, k, 2.2e-16)
+        ms = b.last_solve_ms()
+        corr_ms, n, _ = b.corr_time()
+        sel, coef, nnz, res, its = b.download(k)
+    rec = float(np.mean([(set(idx[s]) <= set(sel[s, :nnz[s]])) for s in range(0, B, 64)]))
+    tf = 2.0 * M * N * B * n / corr_ms / 1e9
+    return dict(config="c3 gomp l=4 2048x32768 k=64 f64", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
+                corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+                corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
+
+
+def c5(cs, dev, args):
+    M, N, iters, B = 4096, 65536, int(200 * args.scale), 4096
+    A, Bm, idx = make_problem(M, N, 32, B, np.float64, dev, noise=5e-3)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, iters) as b:
+        b.upload(Bm)
+        b.mp(2)
+        b.profile(True)
+        b.mp(iters)
+        ms = b.last_solve_ms()
+        corr_ms, n, _ = b.corr_time()
+        sel, coef, nnz, res, its = b.download(iters)
+    tf = 2.0 * M * N * B * n / corr_ms / 1e9
+    return dict(config="c5 mp 4096x65536 f64", iterations=iters, signals=B, solves_per_s=B / (ms * 1e-3),
+                ms_per_solve_batch=ms, corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+                corr_share=corr_ms / ms, median_resnorm=float(np.median(res)))
+
+
+def c4(cs, dev, args):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    M, k = 8192, int(128 * args.scale)
+    N_loc = 131072                                    # 4 GiB FP32 per GPU: 8 ranks = the 1 048 576-atom dictionary
+    N = N_loc * world
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        uid = cs.exchange_unique_id(dist, rank)
+    else:
+        uid = cs.ShardComm.unique_id()
+    comm = cs.ShardComm(uid, rank, world, local)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    A_t = torch.empty(N_loc, M, dtype=torch.float32, device=dev)
+    for n0 in range(0, N_loc, 16384):
+        blk = torch.randn(16384, M, dtype=torch.float32, device=dev, generator=g)
+        blk /= blk.norm(dim=1, keepdim=True)
+        A_t[n0:n0 + 16384] = blk
+    # planted signal: k atoms spread over all shards (every rank contributes k/world of its own atoms)
+    per = max(1, k // world)
+    gi = torch.Generator(device=dev).manual_seed(7)
+    loc_idx = torch.randperm(N_loc, device=dev, generator=gi)[:per]
+    part = A_t[loc_idx].to(torch.float64).sum(dim=0)
+    if world > 1:
+        dist.all_reduce(part)
+    b = part.to(torch.float32).cpu().numpy()
+    A_np = A_t.cpu().numpy().T
+    del A_t
+    torch.cuda.empty_cache()
+    shard = cs.Dictionary(A_np, device=local, n_offset=rank * N_loc, n_total=N)
+    del A_np
+    cs.omp_sharded(shard, comm, b, 4)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, info = cs.omp_sharded(shard, comm, b, k)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    tmax = torch.tensor([wall, info["corr_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    wall, corr_ms = float(tmax[0]), float(tmax[1])
+    planted = set((loc_idx.cpu().numpy() + rank * N_loc).tolist())
+    mine = len(planted & set(x.nzind.tolist()))
+    found = torch.tensor([mine], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(found)
+    gbs = N_loc * M * 4 * k / (corr_ms * 1e-3) / 1e9      # per-GPU shard bytes per correlation pass / its device time
+    out = dict(config=f"c4 omp 8192x{N} f32 k={k}, column-sharded over {world} GPU(s)", solves_per_s=1.0 / wall,
+               wall_s=wall, corr_ms_total=corr_ms, gemv_GBps_per_gpu=gbs, frac_of_hbm_peak=gbs / HBM_PEAK,
+               hbm_peak_GBps=HBM_PEAK, gemv_share_of_wall=corr_ms * 1e-3 / wall, planted_atoms_found=int(found.item()),
+               planted_atoms=per * world, resnorm=info["resnorm"])
+    comm.close(); shard.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    a = ap.parse_args()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cs = ge.load_package()
+    res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[a.config](cs, dev, a)
+    if res is not None:
+        print(json.dumps(res))
