@@ -75,7 +75,8 @@ int make_operand_map(CUtensorMap* map, void* base, int64_t ld, int64_t ncols) {
 }
 
 enum CorrImpl { IMPL_AUTO = 0, IMPL_GEMM = 1, IMPL_GEMV = 2, IMPL_NAIVE = 3 };
-constexpr int GEMM_MIN_SIGNALS = 24;   // below this the per-signal GEMV passes win over a padded 128-wide tile
+constexpr int GEMM_MIN_SIGNALS = 24;
+constexpr int CLUSTER_UPDATE_MAX_SIGNALS = 24;   // below this one CTA per signal leaves the GPU idle: use a cluster per signal   // below this the per-signal GEMV passes win over a padded 128-wide tile
 
 }  // namespace
 
@@ -187,6 +188,13 @@ int run_corr(csb200_batch* b, int S, int impl) {
     if (e != cudaSuccess) return fail_cuda(e, "correlation kernel launch");
     if (b->profile) CU_TRY(cudaEventRecord(e1, b->stream));
     return CSB200_OK;
+}
+
+cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
+    const char* env = getenv("CSB200_UPDATE_IMPL");      // test hook: force one of the two update kernels
+    const int force = !env ? 0 : !strcmp(env, "cluster") ? 1 : !strcmp(env, "cta") ? 2 : 0;
+    const bool cluster = force == 1 || (force == 0 && b->nsig < CLUSTER_UPDATE_MAX_SIGNALS);
+    return cluster ? launch_omp_update_cluster(a, f32, b->stream) : launch_omp_update(a, f32, b->stream);
 }
 
 int begin_solve(csb200_batch* b) {
@@ -441,7 +449,7 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     if (e != cudaSuccess) return fail_cuda(e, "reset_state");
     for (int64_t it = 0; it < k; ++it) {
         if ((rc = run_corr(b, 1, IMPL_AUTO))) return rc;
-        e = launch_omp_update(state_args(b, 1, 1, eps, 0), f32, b->stream);
+        e = update_launch(b, state_args(b, 1, 1, eps, 0), f32);
         if (e != cudaSuccess) return fail_cuda(e, "omp_update");
         b->other_launches++;
     }
@@ -467,14 +475,14 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     if (e != cudaSuccess) return fail_cuda(e, "reset_state");
     for (int64_t it = 0; it < k / l; ++it) {
         if ((rc = run_corr(b, (int)l, IMPL_AUTO))) return rc;
-        e = launch_omp_update(state_args(b, (int)l, (int)l, eps, 0), f32, b->stream);
+        e = update_launch(b, state_args(b, (int)l, (int)l, eps, 0), f32);
         if (e != cudaSuccess) return fail_cuda(e, "gomp_update");
         b->other_launches++;
     }
     const int rem = (int)(k % l);
     if (rem > 0) {                                   // runs even after an eps-break (matchingpursuit.jl:134-137)
         if ((rc = run_corr(b, rem, IMPL_AUTO))) return rc;
-        e = launch_omp_update(state_args(b, rem, rem, eps, 1), f32, b->stream);
+        e = update_launch(b, state_args(b, rem, rem, eps, 1), f32);
         if (e != cudaSuccess) return fail_cuda(e, "gomp_update(rem)");
         b->other_launches++;
     }

@@ -66,6 +66,8 @@ struct StateArgs {
 // Acache (optional): ld x kcap buffer holding the active atoms' columns in selection order, with the
 // candidate's column already stored in slot nnz (column-sharded mode: the atom may live on a peer).
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache = nullptr);
+// One 8-CTA cluster per signal (update_cluster.cu): the single-/few-signal paths.
+cudaError_t launch_omp_update_cluster(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache = nullptr);
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st);
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx, const double* x0_val,

@@ -276,7 +276,7 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
             if (nr != ncclSuccess) { status = fail_nccl(nr, "ncclAllGather"); break; }
             if (f32) global_pick_kernel<float><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (float*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
             else global_pick_kernel<double><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (double*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
-            e = launch_omp_update(sa, f32, st, base + o.acache);
+            e = launch_omp_update_cluster(sa, f32, st, base + o.acache);
             if (e != cudaSuccess) { status = fail_cuda(e, "omp_update"); break; }
         }
         if (status) break;

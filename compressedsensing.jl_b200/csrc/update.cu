@@ -32,68 +32,13 @@
 // SparseVector.  T (kcap x kcap), z and x live in global memory per signal; the CTA that owns a signal
 // stages T and one signal-length vector v in shared memory.
 #include "common.cuh"
+#include "update_common.cuh"
 
 namespace csb {
 namespace {
 
 constexpr int UT = 128;            // threads per CTA
 constexpr int UW = UT / 32;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
-// Deterministic block sum (fixed order); every thread receives the result.
-__device__ __forceinline__ double block_sum(double v, double* red) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < UW; ++w) s += red[w];
-    return s;
-}
-
-// Global top-`take` over this signal's P*S per-block candidates -> s_cand[0..take) (atom or -1).
-__device__ void select_candidates(const double* __restrict__ pv, const int* __restrict__ pi, int count, int take,
-                                  int* s_cand, double* s_cval, double* red_v, int* red_i) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double prev_v = 0.0;
-    int prev_i = -1;
-    for (int round = 0; round < take; ++round) {
-        double bv = -1.0;
-        int bi = INT_MAX;
-        for (int c = tid; c < count; c += UT) {
-            const double v = pv[c];
-            const int i = pi[c];
-            if (i < 0) continue;
-            const bool ok = (round == 0) || (v < prev_v) || (v == prev_v && i > prev_i);
-            if (ok && cand_better(v, i, bv, bi)) { bv = v; bi = i; }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-        }
-        __syncthreads();
-        if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
-        __syncthreads();
-        bv = red_v[0]; bi = red_i[0];
-#pragma unroll
-        for (int w = 1; w < UW; ++w)
-            if (cand_better(red_v[w], red_i[w], bv, bi)) { bv = red_v[w]; bi = red_i[w]; }
-        prev_v = bv; prev_i = bi;
-        if (tid == 0) { s_cand[round] = (bi == INT_MAX) ? -1 : bi; s_cval[round] = bv; }
-        if (bi == INT_MAX) {            // candidates exhausted: pad the rest
-            for (int r2 = round + 1 + tid; r2 < take; r2 += UT) s_cand[r2] = -1;
-            break;
-        }
-    }
-    __syncthreads();
-}
 
 // Shared-memory budget for keeping the inverse factor on chip (above it the kernel works on the copy in L2).
 constexpr int T_SMEM_MAX_K = 96;
@@ -146,7 +91,7 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
 
     if (t < a.M) {                                                 // `nnz(x) < size(P.A, 1) || return x` (:63,:117)
         const size_t cbase = (size_t)sig * a.P * a.S;
-        select_candidates(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
+        select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
 
         for (int round = 0; round < a.take; ++round) {
             const int j = s_cand[round];
@@ -159,7 +104,7 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
             const T* aj = Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld;
             double s2 = 0.0;
             for (int row = tid; row < ld; row += UT) { const double e = (double)aj[row]; v[row] = e; s2 += e * e; }
-            const double anorm2 = block_sum(s2, red);
+            const double anorm2 = block_sum<UT>(s2, red);
             double before2 = anorm2, rho2 = anorm2;
             for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
                 for (int i = warp; i < t; i += UW) {               // g = A_S' v
@@ -193,7 +138,7 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
                     v[row] = acc;
                     s2 += acc * acc;
                 }
-                rho2 = block_sum(s2, red);
+                rho2 = block_sum<UT>(s2, red);
                 if (rho2 >= 0.5 * before2) break;                  // DGKS: one sweep was enough
                 before2 = rho2;
             }
@@ -201,7 +146,7 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
             const double rho = sqrt(rho2);
             double sb = 0.0;
             for (int row = tid; row < ld; row += UT) sb += v[row] * (double)b[row];
-            const double zt = block_sum(sb, red) / rho;            // z_t = q_t' b
+            const double zt = block_sum<UT>(sb, red) / rho;            // z_t = q_t' b
             // residual: r = b - Q Q'b gains one term, r <- r - q_t z_t.  Identical to the reference's
             // from-scratch b - A_S x_S (x_S = R^{-1} Q'b) up to rounding, at one pass less over A_S.
             const double gam = zt / rho;
@@ -211,7 +156,7 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
                 r[row] = rr;
                 s2r += (double)rr * (double)rr;
             }
-            nr2 = block_sum(s2r, red);
+            nr2 = block_sum<UT>(s2r, red);
             // append the column [h; rho] to R  <=>  append [-R^{-1}h / rho; 1/rho] to R^{-1}
             const double irho = 1.0 / rho;
             for (int i = tid; i < t; i += UT) {
@@ -263,7 +208,7 @@ __global__ void __launch_bounds__(UT) mp_update_kernel(StateArgs a, int iter, in
     const T* A = static_cast<const T*>(a.A);
     T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
     const size_t cbase = (size_t)sig * a.P * a.S;
-    select_candidates(a.pval + cbase, a.pidx + cbase, a.P * a.S, 1, s_cand, s_cval, red, red_i);
+    select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, 1, s_cand, s_cval, red, red_i);
     const int j = s_cand[0];
     if (j < 0) {
         if (tid == 0) { a.flags[sig] |= 2; a.sel[(size_t)sig * stride + iter] = -1; a.x[(size_t)sig * stride + iter] = 0.0; }
@@ -272,14 +217,14 @@ __global__ void __launch_bounds__(UT) mp_update_kernel(StateArgs a, int iter, in
     const T* aj = A + (size_t)(j - a.idx_offset) * ld;
     double s = 0.0;
     for (int row = tid; row < ld; row += UT) s += (double)aj[row] * (double)r[row];
-    const double c = block_sum(s, red);                            // dot(view(A,:,i), r)  (:29)
+    const double c = block_sum<UT>(s, red);                            // dot(view(A,:,i), r)  (:29)
     double s2 = 0.0;
     for (int row = tid; row < ld; row += UT) {
         const T rr = (T)((double)r[row] - c * (double)aj[row]);
         r[row] = rr;
         s2 += (double)rr * (double)rr;
     }
-    const double nr = sqrt(block_sum(s2, red));
+    const double nr = sqrt(block_sum<UT>(s2, red));
     if (tid == 0) {
         a.sel[(size_t)sig * stride + iter] = j;
         a.x[(size_t)sig * stride + iter] = c;
@@ -298,7 +243,7 @@ __global__ void __launch_bounds__(UT) reset_state_kernel(StateArgs a) {
     T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
     double s2 = 0.0;
     for (int row = tid; row < ld; row += UT) { const T e = b[row]; r[row] = e; s2 += (double)e * (double)e; }
-    const double nr = sqrt(block_sum(s2, red));
+    const double nr = sqrt(block_sum<UT>(s2, red));
     if (tid == 0) { a.nnz[sig] = 0; a.iters[sig] = 0; a.done[sig] = 0; a.flags[sig] = 0; a.resnorm[sig] = nr; }
 }
 
@@ -324,7 +269,7 @@ __global__ void __launch_bounds__(UT) mp_warmstart_kernel(StateArgs a, const int
         r[row] = rr;
         s2 += (double)rr * (double)rr;
     }
-    const double nr = sqrt(block_sum(s2, red));
+    const double nr = sqrt(block_sum<UT>(s2, red));
     if (tid == 0) a.resnorm[sig] = nr;
 }
 
@@ -335,7 +280,7 @@ __global__ void __launch_bounds__(UT) topk_from_partials_kernel(StateArgs a, int
     __shared__ double s_cval[MAX_S];
     const int sig = blockIdx.x;
     const size_t cbase = (size_t)sig * a.P * a.S;
-    select_candidates(a.pval + cbase, a.pidx + cbase, a.P * a.S, s, s_cand, s_cval, red, red_i);
+    select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, s, s_cand, s_cval, red, red_i);
     for (int i = threadIdx.x; i < s; i += UT) {
         out_idx[(size_t)sig * s + i] = s_cand[i];
         out_val[(size_t)sig * s + i] = s_cand[i] < 0 ? 0.0 : s_cval[i];

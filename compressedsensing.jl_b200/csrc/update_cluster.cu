@@ -1,0 +1,264 @@
+// Per-signal state update for the SINGLE-SIGNAL (few-signal) paths: one thread-block CLUSTER per signal.
+//
+// Same mathematics as omp_update_kernel (update.cu: final selection, implicit-Q append with DGKS
+// re-orthogonalisation, R^{-1} update, coefficients, residual down-date -- reference
+// /root/reference/src/matchingpursuit.jl:62-70, 116-123, 152-176 and src/util.jl:118-126), but where the
+// batched path has tens of thousands of signals to fill the GPU with one CTA each, a single-signal solve
+// (BASELINE configs 1 and 4: M up to 8192, up to 128 active atoms) left ONE CTA to gather 2 t M elements per
+// iteration and the update took as long as the HBM-bound correlation pass it sits behind.
+//
+// Here the M rows are split over the CL = 8 CTAs of a cluster.  Each CTA keeps its slice of v / r / b, gathers
+// its slice of the active atoms, and the length-M reductions (A_S'v, ||v||^2, v'b, ||r||^2) are finished
+// across the cluster through distributed shared memory: every CTA stores its partials into every peer's
+// exchange buffer (`map_shared_rank`), `cluster.sync()`, then sums the 8 partials in rank order -- a
+// deterministic all-reduce that costs one hardware cluster barrier.  The small state (support, R^{-1}, Q'b)
+// is replicated per CTA and updated identically, so no broadcast is needed.  Three exchanges per appended
+// atom (five when a second orthogonalisation sweep is required).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "update_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace csb {
+namespace {
+
+constexpr int CT = 256;            // threads per CTA
+constexpr int CL = 8;              // CTAs per cluster (portable maximum)
+constexpr int T_SMEM_MAX_K_CL = 128;   // 128 x 129 doubles = 132 KB: fits beside the 1-CTA-per-SM working set
+
+struct Exchange {
+    double* buf;       // [2][CL][stride] in this CTA's shared memory
+    int stride;
+    int parity;
+};
+
+// Deterministic cluster-wide sum of n doubles held in `vals` (shared memory of each CTA); result in `out`
+// (shared memory), identical on every CTA.
+__device__ __forceinline__ void cluster_allreduce(cg::cluster_group& cl, Exchange& x, const double* vals, int n,
+                                                  double* out) {
+    const int tid = threadIdx.x;
+    const unsigned me = cl.block_rank();
+    double* mine = x.buf + (size_t)x.parity * CL * x.stride;
+    __syncthreads();                                   // vals complete
+    for (int dst = 0; dst < CL; ++dst) {
+        double* remote = cl.map_shared_rank(mine, dst);
+        for (int i = tid; i < n; i += CT) remote[me * x.stride + i] = vals[i];
+    }
+    cl.sync();                                         // release/acquire: peers' stores are visible
+    for (int i = tid; i < n; i += CT) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < CL; ++c) s += mine[c * x.stride + i];
+        out[i] = s;
+    }
+    x.parity ^= 1;
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, const T* __restrict__ Acache,
+                                                                   int t_in_smem) {
+    cg::cluster_group cl = cg::this_cluster();
+    extern __shared__ double dsm[];
+    const int ld = a.ld, kcap = a.kcap;
+    const int Mc = ld / CL;                                    // rows owned by this CTA (ld is a multiple of 16)
+    const int crank = (int)cl.block_rank();
+    const int row0 = crank * Mc;
+    const int xstride = kcap + 4;
+    double* v = dsm;                 // [Mc]
+    double* g = v + Mc;              // [kcap + 4] partials to exchange: g[0..t), then scalars
+    double* gs = g + xstride;        // [kcap + 4] reduced
+    double* hh = gs + xstride;       // [kcap]
+    double* ys = hh + kcap;          // [kcap]
+    double* y = ys + kcap;           // [kcap]
+    double* zs = y + kcap;           // [kcap]
+    double* xbuf = zs + kcap;        // [2][CL][xstride]
+    int* ssel = reinterpret_cast<int*>(xbuf + 2 * CL * xstride);
+    const T** colp = reinterpret_cast<const T**>(ssel + ((kcap + 1) & ~1));
+    double* Tsm = reinterpret_cast<double*>(colp + kcap);
+    __shared__ double red[CT / 32];
+    __shared__ int red_i[CT / 32];
+    __shared__ int s_cand[MAX_S];
+    __shared__ double s_cval[MAX_S];
+
+    const int sig = blockIdx.x / CL;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // uniform over the cluster: every CTA of a cluster reads the same flag
+    if (a.done[sig] && !a.ignore_done) return;
+
+    Exchange ex{xbuf, xstride, 0};
+    const T* A = static_cast<const T*>(a.A);
+    const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld + row0;
+    T* r = static_cast<T*>(a.R) + (size_t)sig * ld + row0;
+    double* Tg = a.Rf + (size_t)sig * kcap * kcap;
+    double* Tm = t_in_smem ? Tsm : Tg;
+    const int ldT = t_in_smem ? (kcap | 1) : kcap;
+    int t = a.nnz[sig];
+    int flags = 0;
+    bool changed = false;
+    double nr2 = 0.0;
+
+    for (int i = tid; i < t; i += CT) {
+        const int si = a.sel[(size_t)sig * kcap + i];
+        ssel[i] = si;
+        zs[i] = a.z[(size_t)sig * kcap + i];
+        colp[i] = (Acache ? Acache + (size_t)i * ld : A + (size_t)(si - a.idx_offset) * ld) + row0;
+    }
+    if (t_in_smem)
+        for (int e = tid; e < t * kcap; e += CT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * ldT] = Tg[e]; }
+    __syncthreads();
+
+    if (t < a.M) {
+        const size_t cbase = (size_t)sig * a.P * a.S;
+        select_candidates<CT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
+
+        for (int round = 0; round < a.take; ++round) {
+            const int j = s_cand[round];
+            if (j < 0) { flags |= 2; continue; }
+            int in = 0;
+            for (int i = tid; i < t; i += CT) in |= (ssel[i] == j);
+            if (__syncthreads_or(in)) continue;
+            if (t >= kcap || t >= a.M) break;
+
+            const T* aj = (Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld) + row0;
+            double s2 = 0.0;
+            for (int row = tid; row < Mc; row += CT) { const double e = (double)aj[row]; v[row] = e; s2 += e * e; }
+            s2 = block_sum<CT>(s2, red);               // this CTA's part of ||a||^2 (syncs: v is complete)
+            double anorm2 = 0.0, before2 = 0.0, rho2 = 0.0, sb = 0.0;
+            bool have_norm = false;
+            for (int sweep = 0; sweep < 2; ++sweep) {
+                if (t > 0) {
+                    for (int i = warp; i < t; i += CT / 32) {              // partial g = A_S[rows]' v[rows]
+                        const T* ai = colp[i];
+                        double s = 0.0;
+                        for (int row = lane; row < Mc; row += 32) s += (double)ai[row] * v[row];
+                        s = warp_sum(s);
+                        if (lane == 0) g[i] = s;
+                    }
+                }
+                if (tid == 0) g[t] = s2;                                   // rides along: ||a||^2 partial (sweep 0)
+                cluster_allreduce(cl, ex, g, t + 1, gs);
+                if (!have_norm) { anorm2 = gs[t]; before2 = anorm2; rho2 = anorm2; have_norm = true; }
+                if (t == 0) break;
+                for (int i = tid; i < t; i += CT) {                        // hh = R^{-T} g
+                    double acc = 0.0;
+                    for (int l = 0; l <= i; ++l) acc = fma(Tm[l + i * ldT], gs[l], acc);
+                    hh[i] = acc;
+                }
+                __syncthreads();
+                for (int i = tid; i < t; i += CT) {                        // y = R^{-1} hh
+                    double acc = 0.0;
+                    for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], hh[l], acc);
+                    y[i] = acc;
+                    ys[i] = sweep ? ys[i] + acc : acc;
+                }
+                __syncthreads();
+                double p2 = 0.0;
+                for (int row = tid; row < Mc; row += CT) {                 // v -= A_S y on the owned rows
+                    double acc = v[row];
+                    for (int i = 0; i < t; ++i) acc -= (double)colp[i][row] * y[i];
+                    v[row] = acc;
+                    p2 += acc * acc;
+                }
+                p2 = block_sum<CT>(p2, red);
+                if (tid == 0) g[0] = p2;
+                cluster_allreduce(cl, ex, g, 1, gs);
+                rho2 = gs[0];
+                if (rho2 >= 0.5 * before2) break;                          // DGKS: one sweep was enough
+                before2 = rho2;
+                s2 = 0.0;
+            }
+            if (!(rho2 > 1e-26 * anorm2)) { flags |= 1; continue; }        // numerically dependent atom
+            const double rho = sqrt(rho2);
+            for (int row = tid; row < Mc; row += CT) sb += v[row] * (double)b[row];
+            sb = block_sum<CT>(sb, red);
+            if (tid == 0) g[0] = sb;
+            cluster_allreduce(cl, ex, g, 1, gs);
+            const double zt = gs[0] / rho;                                 // z_t = q_t' b
+            const double gam = zt / rho;
+            double s2r = 0.0;
+            for (int row = tid; row < Mc; row += CT) {                     // r <- r - q_t z_t on the owned rows
+                const T rr = (T)((double)r[row] - gam * v[row]);
+                r[row] = rr;
+                s2r += (double)rr * (double)rr;
+            }
+            s2r = block_sum<CT>(s2r, red);
+            if (tid == 0) g[0] = s2r;
+            cluster_allreduce(cl, ex, g, 1, gs);
+            nr2 = gs[0];
+            const double irho = 1.0 / rho;
+            for (int i = tid; i < t; i += CT) {                            // new column of R^{-1}
+                const double e = -ys[i] * irho;
+                if (crank == 0) Tg[i + (size_t)t * kcap] = e;
+                if (t_in_smem) Tsm[i + t * ldT] = e;
+            }
+            if (tid == 0) {
+                if (crank == 0) Tg[t + (size_t)t * kcap] = irho;
+                if (t_in_smem) Tsm[t + t * ldT] = irho;
+                zs[t] = zt; ssel[t] = j; colp[t] = aj;
+            }
+            ++t;
+            changed = true;
+            __syncthreads();
+            if (!t_in_smem) cl.sync();     // the factor lives in global memory: peers must see rank 0's new column
+        }
+    }
+
+    if (crank == 0) {
+        double nr = a.resnorm[sig];
+        if (changed) {
+            for (int i = tid; i < t; i += CT) {                            // x_S = R^{-1} Q'b
+                double acc = 0.0;
+                for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], zs[l], acc);
+                a.x[(size_t)sig * kcap + i] = acc;
+                a.sel[(size_t)sig * kcap + i] = ssel[i];
+                a.z[(size_t)sig * kcap + i] = zs[i];
+            }
+            nr = sqrt(nr2);
+        }
+        if (tid == 0) {
+            a.nnz[sig] = t;
+            a.resnorm[sig] = nr;
+            a.iters[sig] += 1;
+            if (flags) a.flags[sig] |= flags;
+            if (!(nr >= a.eps)) a.done[sig] = 1;
+        }
+    }
+}
+
+size_t cluster_smem_bytes(int ld, int kcap, bool t_in_smem) {
+    const int xstride = kcap + 4;
+    size_t bytes = (size_t)(ld / CL + 2 * xstride + 4 * kcap + 2 * CL * xstride) * sizeof(double) +
+                   (size_t)((kcap + 1) & ~1) * sizeof(int) + (size_t)kcap * sizeof(void*);
+    if (t_in_smem) bytes += (size_t)kcap * (kcap | 1) * sizeof(double);
+    return bytes;
+}
+
+template <typename T>
+cudaError_t launch_t(const StateArgs& a, cudaStream_t st, const void* Acache) {
+    const int t_in_smem = a.kcap <= T_SMEM_MAX_K_CL ? 1 : 0;
+    const size_t smem = cluster_smem_bytes(a.ld, a.kcap, t_in_smem != 0);
+    cudaError_t e = cudaFuncSetAttribute(omp_update_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(a.nsig * CL));
+    cfg.blockDim = dim3(CT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, omp_update_cluster_kernel<T>, a, static_cast<const T*>(Acache), t_in_smem);
+}
+
+}  // namespace
+
+cudaError_t launch_omp_update_cluster(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
+    if (a.nsig <= 0) return cudaSuccess;
+    return f32 ? launch_t<float>(a, st, Acache) : launch_t<double>(a, st, Acache);
+}
+
+}  // namespace csb

@@ -108,7 +108,9 @@ def _fixtures():
 
 @pytest.mark.parametrize("path", _fixtures(), ids=lambda p: os.path.basename(p)[:-4])
 @pytest.mark.parametrize("impl", ["gemm", "gemv"])
-def test_golden(cs, path, impl):
+@pytest.mark.parametrize("update", ["cta", "cluster"])
+def test_golden(cs, path, impl, update, monkeypatch):
+    monkeypatch.setenv("CSB200_UPDATE_IMPL", update)        # one CTA per signal / one 8-CTA cluster per signal
     z = np.load(path, allow_pickle=False)
     meta = json.loads(str(z["meta"]))
     A, Bm = np.asfortranarray(z["A"]), np.asfortranarray(z["B"])
