@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // uniform over the cluster: every CTA of a cluster reads the same flag
     if (a.done[sig] && !a.ignore_done) return;
+    cl.sync();      // every CTA of the cluster is running (its shared memory exists) before any remote store
 
     Exchange ex{xbuf, xstride, 0};
     const T* A = static_cast<const T*>(a.A);
