@@ -102,6 +102,7 @@ struct csb200_batch {
     double* pval = nullptr;
     int* pidx = nullptr;
     size_t pcap = 0;            // candidate slots allocated
+    int cur_P = 0;              // atom blocks per signal written by the last correlation pass
     int* nnz = nullptr; int* sel = nullptr; double* Rf = nullptr; double* z = nullptr; double* x = nullptr;
     double* resnorm = nullptr; int* iters = nullptr; int* done = nullptr; int* flags = nullptr;
     int* dflag = nullptr;       // non-finite scan result
@@ -150,7 +151,7 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
     StateArgs a;
     a.A = d->dA; a.B = b->dB; a.R = b->dR;
     a.M = (int)d->M; a.ld = (int)d->ld; a.N = (int)d->N; a.nsig = (int)b->nsig; a.kcap = (int)b->kcap;
-    a.S = S; a.P = (int)((d->N + PBLK - 1) / PBLK); a.take = take; a.idx_offset = (int)d->n_offset;
+    a.S = S; a.P = b->cur_P > 0 ? b->cur_P : (int)((d->N + PBLK - 1) / PBLK); a.take = take; a.idx_offset = (int)d->n_offset;
     a.ignore_done = ignore_done; a.eps = eps;
     a.pval = b->pval; a.pidx = b->pidx; a.nnz = b->nnz; a.sel = b->sel; a.Rf = b->Rf; a.z = b->z; a.x = b->x;
     a.resnorm = b->resnorm; a.iters = b->iters; a.done = b->done; a.flags = b->flags;
@@ -161,14 +162,16 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
 int run_corr(csb200_batch* b, int S, int impl) {
     csb200_dict* d = b->dict;
     const bool f32 = d->dtype == CSB200_F32;
-    const int64_t P = (d->N + PBLK - 1) / PBLK;
+    if (impl == IMPL_AUTO) impl = b->corr_impl_env;
+    if (impl == IMPL_AUTO) impl = (!f32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
+    const int blk = impl == IMPL_GEMM ? corr_gemm_f64_block() : PBLK;
+    const int64_t P = (d->N + blk - 1) / blk;
     int rc = ensure_partials(b, P, S);
     if (rc) return rc;
+    b->cur_P = (int)P;
     CorrArgs c;
     c.A = d->dA; c.R = b->dR; c.M = (int)d->M; c.ld = (int)d->ld; c.N = (int)d->N; c.nsig = (int)b->nsig;
     c.S = S; c.P = (int)P; c.idx_offset = (int)d->n_offset; c.pval = b->pval; c.pidx = b->pidx;
-    if (impl == IMPL_AUTO) impl = b->corr_impl_env;
-    if (impl == IMPL_AUTO) impl = (!f32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
     if (impl == IMPL_GEMM && (f32 || !d->has_map || !b->has_map)) {
         g_last_error = "DMMA GEMM path needs an FP64 dictionary";
         return CSB200_ERR_UNSUPPORTED;

@@ -36,6 +36,7 @@ struct CorrArgs {
 cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* mapR, const CorrArgs& a,
                                  int num_sms, cudaStream_t st);
 cudaError_t corr_gemm_f64_setup();   // one-time cudaFuncSetAttribute
+int corr_gemm_f64_block();           // atoms per candidate block of the DMMA GEMM epilogue (32 or 64)
 cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_corr_naive(const CorrArgs& a, bool f32, cudaStream_t st);
 

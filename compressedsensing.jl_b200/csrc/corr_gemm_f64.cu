@@ -37,8 +37,6 @@ constexpr int STAGES = 4;
 constexpr int A_TILE_BYTES = TILE_N * KCH * 8;
 constexpr int R_TILE_BYTES = TILE_B * KCH * 8;
 constexpr int STAGE_BYTES = A_TILE_BYTES + R_TILE_BYTES;   // 32 KiB
-constexpr int WARPS = 8;                    // all 8 warps compute; lane 0 of warp 0 also drives TMA
-constexpr int THREADS = WARPS * 32;         // 256 threads x <=255 registers = the whole register file
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -75,6 +73,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // 0.8-2.8 % of kernel time, and DRAM is at 2.3 % of its bandwidth either way on this tensor-bound kernel,
 // so the default keeps the faster order; CSB200_GEMM_BAND overrides it.
 constexpr int DEFAULT_BAND = 0;   // 0 = tilesN
+constexpr int DEFAULT_VARIANT = 0;
 __device__ __forceinline__ void tile_coords(int tile, int tilesN, int tilesB, int BAND, int& tn, int& tb) {
     const int per_band = BAND * tilesB;
     const int band = tile / per_band;
@@ -90,7 +89,12 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// Warp layout variants (CTA tile is always 128 atoms x 128 signals):
+//   <8,4,2,4>  8 warps, warp tile 64 x 32, 64 accumulators/thread, ~228 registers (fills the register file)
+//   <4,4,4,4> 16 warps, warp tile 32 x 32, 32 accumulators/thread, <=128 registers: twice the warps per
+//             scheduler to cover LDS / mbarrier latency at the price of 8 instead of 6 LDS.128 per 32 DMMA
+template <int MI, int NJ, int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32, 1)
 corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
                      int N, int nsig, int kchunks, int tilesN, int tilesB, int band, int S, int P, int idx_offset,
                      double* __restrict__ pval, int* __restrict__ pidx) {
@@ -109,7 +113,7 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar_full + s * 8, 1);
-            mbar_init(bar_empty + s * 8, WARPS);
+            mbar_init(bar_empty + s * 8, WM * WN);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -137,11 +141,12 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
 
     // ---------------------------------- DMMA consumers -----------------------------------
-    const int wm = warp & 1;          // which 64-atom half of the tile
-    const int wn = warp >> 1;         // which 32-signal quarter
+    static_assert(8 * MI * WM == TILE_N && 8 * NJ * WN == TILE_B, "warp layout must cover the CTA tile");
+    const int wm = warp % WM;         // which (8*MI)-atom slice of the tile
+    const int wn = warp / WM;         // which (8*NJ)-signal slice
     const int g = lane >> 2, q = lane & 3;
-    const uint32_t a_row = (uint32_t)(wm * 64 + g) * 128u;                   // + i*1024
-    const uint32_t r_row = (uint32_t)A_TILE_BYTES + (uint32_t)(wn * 32 + g) * 128u;   // + j*1024
+    const uint32_t a_row = (uint32_t)(wm * 8 * MI + g) * 128u;                   // + i*1024
+    const uint32_t r_row = (uint32_t)A_TILE_BYTES + (uint32_t)(wn * 8 * NJ + g) * 128u;   // + j*1024
     int stage = 0;
     uint32_t phase = 0;
     int chunk = 0;                     // flat chunk index being consumed
@@ -149,11 +154,11 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int tn, tb;
         tile_coords(tile, tilesN, tilesB, band, tn, tb);
-        double acc[8][4][2];
+        double acc[MI][NJ][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+            for (int j = 0; j < NJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
         for (int kc = 0; kc < kchunks; ++kc, ++chunk) {
             // keep STAGES-1 chunks in flight, across tile boundaries (the next tile's first chunks
@@ -165,40 +170,40 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t sw = (uint32_t)(((4 * h + q) ^ g) << 4);      // SWIZZLE_128B: chunk ^= row % 8
-                double2 af[8], bf[4];
+                double2 af[MI], bf[NJ];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) af[i] = *reinterpret_cast<const double2*>(st + a_row + i * 1024 + sw);
+                for (int i = 0; i < MI; ++i) af[i] = *reinterpret_cast<const double2*>(st + a_row + i * 1024 + sw);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bf[j] = *reinterpret_cast<const double2*>(st + r_row + j * 1024 + sw);
+                for (int j = 0; j < NJ; ++j) bf[j] = *reinterpret_cast<const double2*>(st + r_row + j * 1024 + sw);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j], af[i].x, bf[j].x);
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j], af[i].x, bf[j].x);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j], af[i].y, bf[j].y);
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j], af[i].y, bf[j].y);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + stage * 8);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
 
-        // ---- fused epilogue: top-S of |c| over this warp's 64 atoms, per signal column ----
-        // acc[i][j][e] = c[atom = wm*64 + i*8 + g][signal = wn*32 + j*8 + 2q + e]
-        const int atom0 = tn * TILE_N + wm * 64 + g;
-        const int p = tn * 2 + wm;
-        double pv[4][2];
-        int pi[4][2];
+        // ---- fused epilogue: top-S of |c| over this warp's 8*MI atoms, per signal column ----
+        // acc[i][j][e] = c[atom = wm*8*MI + i*8 + g][signal = wn*8*NJ + j*8 + 2q + e]
+        const int atom0 = tn * TILE_N + wm * 8 * MI + g;
+        const int p = tn * WM + wm;
+        double pv[NJ][2];
+        int pi[NJ][2];
         for (int s = 0; s < S; ++s) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     double bv = -1.0;
                     int bi = INT_MAX;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < MI; ++i) {
                         const double v = fabs(acc[i][j][e]);
                         const int idx = atom0 + i * 8;
                         bool ok = idx < N;
@@ -213,7 +218,7 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                     }
                     pv[j][e] = bv;
                     pi[j][e] = bi;
-                    const int sig = tb * TILE_B + wn * 32 + j * 8 + 2 * q + e;
+                    const int sig = tb * TILE_B + wn * 8 * NJ + j * 8 + 2 * q + e;
                     if (g == 0 && sig < nsig && p < P) {
                         const size_t o = ((size_t)sig * P + p) * S + s;
                         pval[o] = bv;
@@ -227,8 +232,20 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
 }  // namespace
 
+namespace {
+int gemm_variant() {
+    static const int v = [] { const char* e = getenv("CSB200_GEMM_VARIANT"); return e ? atoi(e) : DEFAULT_VARIANT; }();
+    return v;
+}
+}  // namespace
+
+// atoms per candidate block emitted by the active variant (P = ceil(N / this))
+int corr_gemm_f64_block() { return gemm_variant() == 1 ? 32 : 64; }
+
 cudaError_t corr_gemm_f64_setup() {
-    return cudaFuncSetAttribute(corr_gemm_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(corr_gemm_f64_kernel<4, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
 cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* mapR, const CorrArgs& a,
@@ -241,8 +258,12 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     static const int band_env = [] { const char* e = getenv("CSB200_GEMM_BAND"); return e ? atoi(e) : 0; }();
     int band = band_env > 0 ? band_env : DEFAULT_BAND;
     if (band <= 0 || band > tilesN) band = tilesN;
-    corr_gemm_f64_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN, tilesB,
-                                                            band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+    if (gemm_variant() == 1)
+        corr_gemm_f64_kernel<4, 4, 4, 4><<<grid, 512, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN,
+                                                                        tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+    else
+        corr_gemm_f64_kernel<8, 4, 2, 4><<<grid, 256, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN,
+                                                                        tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
     return cudaGetLastError();
 }
 
