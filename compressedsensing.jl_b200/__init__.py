@@ -323,16 +323,30 @@ def _to_sparse(n: int, sel_row: np.ndarray, coef_row: np.ndarray, nnz: int) -> S
     return SparseVector(n, idx[order].astype(np.int64), val[order].astype(np.float64))
 
 
-def _solve(A, b, device, run, stride, merge=None):
-    b_arr = np.asarray(b)
-    single = b_arr.ndim == 1
+def _signals_for(D: "Dictionary", b) -> np.ndarray:
+    B = np.asarray(b)
+    if B.ndim == 1:
+        B = B.reshape(-1, 1)
+    if B.ndim != 2 or B.shape[0] != D.M:
+        raise ValueError(f"DimensionMismatch: signal length {B.shape[0]} != {D.M} rows of A")
+    return np.asfortranarray(B.astype(D.dtype, copy=False))
+
+
+def _solve(A, b, device, call, stride, eps=None, merge=None):
+    """One-shot solve through the host-buffer C entry points (csb200_omp / csb200_gomp / csb200_mp): upload,
+    solve and download happen inside one C call on a workspace cached on the dictionary handle."""
+    single = np.asarray(b).ndim == 1
     D, owned = _dictionary(A, device)
     try:
-        nsig = 1 if single else b_arr.shape[1]
-        with Batch(D, nsig, stride) as batch:
-            batch.upload(b_arr)
-            run(batch)
-            sel, coef, nnz, res, its = batch.download(stride)
+        B = _signals_for(D, b)
+        nsig = B.shape[1]
+        ldb = max(B.strides[1] // B.itemsize, D.M) if nsig > 1 else D.M
+        sel = np.empty((nsig, stride), dtype=np.int64)
+        coef = np.empty((nsig, stride), dtype=np.float64)
+        nnz = np.full(nsig, stride, dtype=np.int64)
+        res = np.empty(nsig, dtype=np.float64)
+        its = np.empty(nsig, dtype=np.int64)
+        _check(call(D, B, ldb, nsig, sel, coef, nnz, res, its), eps)
         if merge is not None:
             out = [merge(D.n_total, sel[s], coef[s], int(nnz[s]), s) for s in range(nsig)]
         else:
@@ -363,7 +377,15 @@ def omp(A, b, *args, max_residual=None, sparsity=None, device: int = 0):
         k = min(M, N) if sparsity is None else int(sparsity)
     if not eps >= 0:
         raise ValueError(f"ε = {eps} has to be non-negative")
-    return _solve(A, b, device, lambda batch: batch.omp(k, eps), max(min(k, M, N), 1))
+    if k < 0:
+        raise ValueError("k must be non-negative")
+    stride = max(k, 1)
+
+    def call(D, B, ldb, nsig, sel, coef, nnz, res, its):
+        return lib.csb200_omp(D._h, B.ctypes.data, ldb, nsig, k, eps, _i64p(sel), _f64p(coef), _i64p(nnz), _f64p(res),
+                              _i64p(its))
+
+    return _solve(A, b, device, call, stride, eps)
 
 
 def gomp(A, b, l: int, *args, max_residual=None, sparsity=None, device: int = 0):
@@ -379,7 +401,15 @@ def gomp(A, b, l: int, *args, max_residual=None, sparsity=None, device: int = 0)
         k = N if sparsity is None else int(sparsity)
     if not eps >= 0:
         raise ValueError(f"ε = {eps} has to be non-negative")
-    return _solve(A, b, device, lambda batch: batch.gomp(int(l), k, eps), max(min(k, M, N), 1))
+    if k < 0:
+        raise ValueError("k must be non-negative")
+    stride = max(k, 1)
+
+    def call(D, B, ldb, nsig, sel, coef, nnz, res, its):
+        return lib.csb200_gomp(D._h, B.ctypes.data, ldb, nsig, int(l), k, eps, _i64p(sel), _f64p(coef), _i64p(nnz),
+                               _f64p(res), _i64p(its))
+
+    return _solve(A, b, device, call, stride, eps)
 
 
 def mp(A, b, k: int, x=None, device: int = 0):
@@ -402,7 +432,27 @@ def mp(A, b, k: int, x=None, device: int = 0):
         idx = np.array(sorted(acc), dtype=np.int64)
         return SparseVector(n, idx, np.array([acc[i] for i in idx.tolist()], dtype=np.float64))
 
-    return _solve(A, b, device, lambda batch: batch.mp(int(k), x0), max(int(k), 1), merge=merge)
+    k = int(k)
+    stride = max(k, 1)
+
+    def call(D, B, ldb, nsig, sel, coef, nnz, res, its):
+        if x0 is None:
+            rc = lib.csb200_mp(D._h, B.ctypes.data, ldb, nsig, k, None, None, None, 0, _i64p(sel), _f64p(coef), _f64p(res))
+        else:
+            if len(x0) != nsig:
+                raise ValueError("one warm-start vector per signal is required")
+            st0 = max(1, max(v.nnz() for v in x0))
+            xi = np.zeros((nsig, st0), dtype=np.int64)
+            xv = np.zeros((nsig, st0), dtype=np.float64)
+            xn = np.zeros(nsig, dtype=np.int64)
+            for s_, v in enumerate(x0):
+                xn[s_] = v.nnz(); xi[s_, :v.nnz()] = v.nzind; xv[s_, :v.nnz()] = v.nzval
+            rc = lib.csb200_mp(D._h, B.ctypes.data, ldb, nsig, k, _i64p(xi), _f64p(xv), _i64p(xn), st0, _i64p(sel),
+                               _f64p(coef), _f64p(res))
+        nnz[:] = k                     # mp: one (atom, increment) record per iteration
+        return rc
+
+    return _solve(A, b, device, call, stride, merge=merge)
 
 
 # ------------------------------------------------------------------------------------------------

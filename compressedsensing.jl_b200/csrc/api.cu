@@ -103,8 +103,15 @@ struct csb200_batch {
     int* pidx = nullptr;
     size_t pcap = 0;            // candidate slots allocated
     int cur_P = 0;              // atom blocks per signal written by the last correlation pass
+    // per-signal state: one device block laid out [resnorm | x | nnz | iters | flags | done | sel | z] so that
+    // the results of a small solve come back in a single copy (state_result_bytes covers everything but z)
+    unsigned char* state_blk = nullptr;
+    size_t state_result_bytes = 0;
     int* nnz = nullptr; int* sel = nullptr; double* Rf = nullptr; double* z = nullptr; double* x = nullptr;
     double* resnorm = nullptr; int* iters = nullptr; int* done = nullptr; int* flags = nullptr;
+    unsigned char* host_stage = nullptr;   // pinned staging buffer for small uploads / packed downloads
+    size_t host_stage_bytes = 0;
+    bool lazy_input_check = false;         // upload skipped the NaN scan: the small solve kernel reports it
     int* dflag = nullptr;       // non-finite scan result
     cudaStream_t stream = nullptr;
     bool profile = false;
@@ -119,10 +126,12 @@ struct csb200_batch {
 
 namespace {
 
+int begin_solve_fwd(csb200_batch* b);
+
 void free_batch_mem(csb200_batch* b) {
-    cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->nnz); cudaFree(b->sel);
-    cudaFree(b->Rf); cudaFree(b->z); cudaFree(b->x); cudaFree(b->resnorm); cudaFree(b->iters); cudaFree(b->done);
-    cudaFree(b->flags); cudaFree(b->dflag);
+    cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->state_blk);
+    cudaFree(b->Rf); cudaFree(b->dflag);
+    if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
     if (b->ev_solve1) cudaEventDestroy(b->ev_solve1);
@@ -193,6 +202,28 @@ int run_corr(csb200_batch* b, int S, int impl) {
     return CSB200_OK;
 }
 
+// Small dictionaries: the whole solve in one launch (solve_small.cu).  CSB200_SMALL_SOLVE=0 disables it.
+bool use_small_solve(const csb200_batch* b) {
+    const char* env = getenv("CSB200_SMALL_SOLVE");
+    if (env && !strcmp(env, "0")) return false;
+    const csb200_dict* d = b->dict;
+    if (b->corr_impl_env != IMPL_AUTO) return false;            // a test forced a specific correlation kernel
+    return small_solve_eligible((int)d->ld, (int)d->N, (int)b->kcap, (int)b->nsig, d->dtype == CSB200_F32);
+}
+
+int run_small_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double eps, const int* x0_idx,
+                    const double* x0_val, const int* x0_nnz, int x0_stride) {
+    int rc = begin_solve_fwd(b);
+    if (rc) return rc;
+    SmallSolveArgs q;
+    q.mode = mode; q.k = (int)k; q.l = (int)l; q.eps = eps; q.stride = (int)b->kcap;
+    q.x0_idx = x0_idx; q.x0_val = x0_val; q.x0_nnz = x0_nnz; q.x0_stride = x0_stride;
+    cudaError_t e = launch_small_solve(state_args(b, 1, 1, eps, 0), q, b->dict->dtype == CSB200_F32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "small_solve");
+    b->other_launches++;
+    return CSB200_OK;
+}
+
 cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
     const char* env = getenv("CSB200_UPDATE_IMPL");      // test hook: force one of the two update kernels
     const int force = !env ? 0 : !strcmp(env, "cluster") ? 1 : !strcmp(env, "cta") ? 2 : 0;
@@ -205,6 +236,7 @@ int begin_solve(csb200_batch* b) {
     CU_TRY(cudaEventRecord(b->ev_solve0, b->stream));
     return CSB200_OK;
 }
+int begin_solve_fwd(csb200_batch* b) { return begin_solve(b); }
 
 int finish(csb200_batch* b, bool solve = false) {
     if (solve) { CU_TRY(cudaEventRecord(b->ev_solve1, b->stream)); }
@@ -236,15 +268,42 @@ int scan_nonfinite(csb200_batch* b, const void* p, size_t n, bool f32, cudaStrea
     return h ? CSB200_ERR_NONFINITE_INPUT : CSB200_OK;
 }
 
-int after_upload(csb200_batch* b, int64_t nsig) {
+int ensure_signal_map(csb200_batch* b) {
+    csb200_dict* d = b->dict;
+    if (d->dtype != CSB200_F64 || b->has_map) return CSB200_OK;
+    int rc = make_operand_map(&b->mapR, b->dR, d->ld, b->nsig);
+    if (rc) return rc;
+    b->has_map = true;
+    return CSB200_OK;
+}
+
+// Input validation + initial state (r = b) for the multi-launch paths.
+int settle_input(csb200_batch* b) {
+    int rc = ensure_signal_map(b);
+    if (rc) return rc;
+    if (!b->lazy_input_check) return CSB200_OK;
+    csb200_dict* d = b->dict;
+    b->lazy_input_check = false;
+    rc = scan_nonfinite(b, b->dB, (size_t)d->ld * b->nsig, d->dtype == CSB200_F32, b->stream, b->dflag);
+    if (rc) { b->nsig = 0; return rc; }
+    return CSB200_OK;
+}
+
+int after_upload(csb200_batch* b, int64_t nsig, bool allow_lazy) {
     csb200_dict* d = b->dict;
     b->nsig = nsig;
-    if (d->dtype == CSB200_F64) {
-        int rc = make_operand_map(&b->mapR, b->dR, d->ld, nsig);
-        if (rc) return rc;
-        b->has_map = true;
+    b->has_map = false;
+    b->cur_P = 0;
+    if (allow_lazy && use_small_solve(b)) {
+        // one-shot call on a small dictionary: the solve kernel itself checks b for NaN/Inf and sets r = b,
+        // so the upload needs no scan, no reset and no synchronisation
+        b->lazy_input_check = true;
+        return CSB200_OK;
     }
-    int rc = scan_nonfinite(b, b->dB, (size_t)d->ld * nsig, d->dtype == CSB200_F32, b->stream, b->dflag);
+    b->lazy_input_check = false;
+    int rc = ensure_signal_map(b);
+    if (rc) return rc;
+    rc = scan_nonfinite(b, b->dB, (size_t)d->ld * nsig, d->dtype == CSB200_F32, b->stream, b->dflag);
     if (rc) { b->nsig = 0; return rc; }
     // r = b, counters cleared: the state a freshly constructed MP/OMP/GOMP object has
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), d->dtype == CSB200_F32, b->stream);
@@ -383,14 +442,24 @@ int csb200_batch_create(csb200_dict* d, int64_t max_signals, int64_t max_sparsit
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     alloc(&b->dB, (size_t)d->ld * ns * es);
     alloc(&b->dR, (size_t)d->ld * ns * es);
-    alloc((void**)&b->nnz, ns * sizeof(int));
-    alloc((void**)&b->sel, ns * kc * sizeof(int));
-    alloc((void**)&b->z, ns * kc * sizeof(double));
-    alloc((void**)&b->x, ns * kc * sizeof(double));
-    alloc((void**)&b->resnorm, ns * sizeof(double));
-    alloc((void**)&b->iters, ns * sizeof(int));
-    alloc((void**)&b->done, ns * sizeof(int));
-    alloc((void**)&b->flags, ns * sizeof(int));
+    {
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { size_t at = off; off += (bytes + 15) / 16 * 16; return at; };
+        const size_t o_res = carve(ns * sizeof(double)), o_x = carve(ns * kc * sizeof(double));
+        const size_t o_nnz = carve(ns * sizeof(int)), o_it = carve(ns * sizeof(int)), o_fl = carve(ns * sizeof(int));
+        const size_t o_done = carve(ns * sizeof(int)), o_sel = carve(ns * kc * sizeof(int));
+        b->state_result_bytes = off;
+        const size_t o_z = carve(ns * kc * sizeof(double));
+        alloc((void**)&b->state_blk, off);
+        if (e == cudaSuccess) {
+            unsigned char* p = b->state_blk;
+            b->resnorm = (double*)(p + o_res); b->x = (double*)(p + o_x); b->nnz = (int*)(p + o_nnz);
+            b->iters = (int*)(p + o_it); b->flags = (int*)(p + o_fl); b->done = (int*)(p + o_done);
+            b->sel = (int*)(p + o_sel); b->z = (double*)(p + o_z);
+        }
+        b->host_stage_bytes = b->state_result_bytes <= (1u << 20) ? (1u << 20) : 0;
+        if (e == cudaSuccess && b->host_stage_bytes) e = cudaMallocHost((void**)&b->host_stage, b->host_stage_bytes);
+    }
     alloc((void**)&b->dflag, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_solve0);
@@ -409,7 +478,8 @@ int csb200_batch_destroy(csb200_batch* b) {
     return CSB200_OK;
 }
 
-static int upload_common(csb200_batch* b, const void* src, int64_t ldb, int64_t nsig, cudaMemcpyKind kind) {
+static int upload_common(csb200_batch* b, const void* src, int64_t ldb, int64_t nsig, cudaMemcpyKind kind,
+                         bool allow_lazy = false) {
     if (!b || !src || nsig <= 0) return CSB200_ERR_INVALID_ARG;
     csb200_dict* d = b->dict;
     if (ldb < d->M) return CSB200_ERR_DIM_MISMATCH;
@@ -424,7 +494,7 @@ static int upload_common(csb200_batch* b, const void* src, int64_t ldb, int64_t 
         if (d->ld != d->M) CU_TRY(cudaMemsetAsync(b->dB, 0, (size_t)d->ld * nsig * es, b->stream));
         CU_TRY(cudaMemcpy2DAsync(b->dB, d->ld * es, src, ldb * es, d->M * es, nsig, kind, b->stream));
     }
-    return after_upload(b, nsig);
+    return after_upload(b, nsig, allow_lazy);
 }
 
 int csb200_batch_upload(csb200_batch* b, const void* Bmat, int64_t ldb, int64_t nsig) {
@@ -445,6 +515,11 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
+    if (use_small_solve(b)) {
+        if ((rc = run_small_solve(b, 0, k, 1, eps, nullptr, nullptr, nullptr, 0))) return rc;
+        return finish(b, true);
+    }
+    if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
@@ -471,6 +546,11 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
+    if (use_small_solve(b)) {
+        if ((rc = run_small_solve(b, 1, k, l, eps, nullptr, nullptr, nullptr, 0))) return rc;
+        return finish(b, true);
+    }
+    if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
@@ -502,12 +582,13 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
     const bool f32 = d->dtype == CSB200_F32;
-    if ((rc = begin_solve(b))) return rc;
-    cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), f32, b->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
-    int *d_idx = nullptr, *d_nnz = nullptr;
-    double* d_val = nullptr;
-    if (x0_idx && x0_val && x0_nnz && x0_stride > 0) {
+    // optional warm start, copied to the device as (int index, double value) lists
+    struct DevX0 {
+        int* idx = nullptr; double* val = nullptr; int* nnz = nullptr;
+        ~DevX0() { cudaFree(idx); cudaFree(val); cudaFree(nnz); }
+    } x0;
+    const bool warm = x0_idx && x0_val && x0_nnz && x0_stride > 0;
+    if (warm) {
         const size_t n = (size_t)b->nsig * x0_stride;
         std::vector<int> hi(n, 0), hn(b->nsig);
         for (int64_t s = 0; s < b->nsig; ++s) {
@@ -519,15 +600,23 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
                 hi[s * x0_stride + j] = (int)v;
             }
         }
-        CU_TRY(cudaMalloc(&d_idx, n * sizeof(int)));
-        CU_TRY(cudaMalloc(&d_val, n * sizeof(double)));
-        CU_TRY(cudaMalloc(&d_nnz, b->nsig * sizeof(int)));
-        CU_TRY(cudaMemcpyAsync(d_idx, hi.data(), n * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-        CU_TRY(cudaMemcpyAsync(d_val, x0_val, n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-        CU_TRY(cudaMemcpyAsync(d_nnz, hn.data(), b->nsig * sizeof(int), cudaMemcpyHostToDevice, b->stream));
-        e = launch_mp_warmstart(state_args(b, 1, 1, 0.0, 0), f32, d_idx, d_val, d_nnz, (int)x0_stride, b->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
-        cudaFree(d_idx); cudaFree(d_val); cudaFree(d_nnz);
+        CU_TRY(cudaMalloc(&x0.idx, n * sizeof(int)));
+        CU_TRY(cudaMalloc(&x0.val, n * sizeof(double)));
+        CU_TRY(cudaMalloc(&x0.nnz, b->nsig * sizeof(int)));
+        CU_TRY(cudaMemcpy(x0.idx, hi.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(x0.val, x0_val, n * sizeof(double), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(x0.nnz, hn.data(), b->nsig * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (use_small_solve(b)) {
+        if ((rc = run_small_solve(b, 2, iters, 1, 0.0, x0.idx, x0.val, x0.nnz, (int)x0_stride))) return rc;
+        return finish(b, true);
+    }
+    if ((rc = settle_input(b))) return rc;
+    if ((rc = begin_solve(b))) return rc;
+    cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), f32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    if (warm) {
+        e = launch_mp_warmstart(state_args(b, 1, 1, 0.0, 0), f32, x0.idx, x0.val, x0.nnz, (int)x0_stride, b->stream);
         if (e != cudaSuccess) return fail_cuda(e, "mp_warmstart");
     }
     for (int64_t it = 0; it < iters; ++it) {
@@ -536,7 +625,7 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
         if (e != cudaSuccess) return fail_cuda(e, "mp_update");
         b->other_launches++;
     }
-    return finish(b, true);
+    return finish(b, true);      // synchronises before x0 is released
 }
 
 int csb200_batch_download(csb200_batch* b, int64_t stride, int64_t* sel_idx, double* coef, int64_t* nnz,
@@ -547,19 +636,41 @@ int csb200_batch_download(csb200_batch* b, int64_t stride, int64_t* sel_idx, dou
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(b->dict))) return rc;
     const size_t ns = (size_t)b->nsig, kc = (size_t)b->kcap;
-    std::vector<int> hn(ns), hs, hit;
-    std::vector<double> hx;
-    CU_TRY(cudaMemcpyAsync(hn.data(), b->nnz, ns * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-    if (sel_idx) { hs.resize(ns * kc); CU_TRY(cudaMemcpyAsync(hs.data(), b->sel, ns * kc * sizeof(int), cudaMemcpyDeviceToHost, b->stream)); }
-    if (coef) { hx.resize(ns * kc); CU_TRY(cudaMemcpyAsync(hx.data(), b->x, ns * kc * sizeof(double), cudaMemcpyDeviceToHost, b->stream)); }
-    if (iters) { hit.resize(ns); CU_TRY(cudaMemcpyAsync(hit.data(), b->iters, ns * sizeof(int), cudaMemcpyDeviceToHost, b->stream)); }
-    if (resnorm) CU_TRY(cudaMemcpyAsync(resnorm, b->resnorm, ns * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-    CU_TRY(cudaStreamSynchronize(b->stream));
+    std::vector<int> hn_v, hs_v, hit_v, hfl_v;
+    std::vector<double> hx_v, hres_v;
+    const int *hn, *hs = nullptr, *hit = nullptr, *hfl;
+    const double *hx = nullptr, *hres = nullptr;
+    if (b->host_stage && b->state_result_bytes <= b->host_stage_bytes) {
+        // small batch: the whole result block in one copy through the pinned staging buffer
+        CU_TRY(cudaMemcpyAsync(b->host_stage, b->state_blk, b->state_result_bytes, cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaStreamSynchronize(b->stream));
+        const unsigned char* p = b->host_stage;
+        hres = (const double*)(p + ((unsigned char*)b->resnorm - b->state_blk));
+        hx = (const double*)(p + ((unsigned char*)b->x - b->state_blk));
+        hn = (const int*)(p + ((unsigned char*)b->nnz - b->state_blk));
+        hit = (const int*)(p + ((unsigned char*)b->iters - b->state_blk));
+        hfl = (const int*)(p + ((unsigned char*)b->flags - b->state_blk));
+        hs = (const int*)(p + ((unsigned char*)b->sel - b->state_blk));
+    } else {
+        hn_v.resize(ns); hfl_v.resize(ns);
+        CU_TRY(cudaMemcpyAsync(hn_v.data(), b->nnz, ns * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaMemcpyAsync(hfl_v.data(), b->flags, ns * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        if (sel_idx) { hs_v.resize(ns * kc); CU_TRY(cudaMemcpyAsync(hs_v.data(), b->sel, ns * kc * sizeof(int), cudaMemcpyDeviceToHost, b->stream)); }
+        if (coef) { hx_v.resize(ns * kc); CU_TRY(cudaMemcpyAsync(hx_v.data(), b->x, ns * kc * sizeof(double), cudaMemcpyDeviceToHost, b->stream)); }
+        if (iters) { hit_v.resize(ns); CU_TRY(cudaMemcpyAsync(hit_v.data(), b->iters, ns * sizeof(int), cudaMemcpyDeviceToHost, b->stream)); }
+        if (resnorm) { hres_v.resize(ns); CU_TRY(cudaMemcpyAsync(hres_v.data(), b->resnorm, ns * sizeof(double), cudaMemcpyDeviceToHost, b->stream)); }
+        CU_TRY(cudaStreamSynchronize(b->stream));
+        hn = hn_v.data(); hfl = hfl_v.data(); hs = hs_v.data(); hx = hx_v.data(); hit = hit_v.data(); hres = hres_v.data();
+    }
+    if (b->lazy_input_check) {
+        for (size_t s = 0; s < ns; ++s) if (hfl[s] & 4) return CSB200_ERR_NONFINITE_INPUT;
+    }
     for (size_t s = 0; s < ns; ++s) {
         const int64_t t = hn[s];
         if (t > stride && (sel_idx || coef)) { g_last_error = "stride smaller than a signal's support"; return CSB200_ERR_INVALID_ARG; }
         if (nnz) nnz[s] = t;
         if (iters) iters[s] = hit[s];
+        if (resnorm) resnorm[s] = hres[s];
         for (int64_t j = 0; j < stride; ++j) {
             if (sel_idx) sel_idx[s * stride + j] = j < t ? (int64_t)hs[s * kc + j] : -1;
             if (coef) coef[s * stride + j] = j < t ? hx[s * kc + j] : 0.0;
@@ -625,7 +736,7 @@ static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig,
         d->workspace = w;
     }
     *out = w;
-    return csb200_batch_upload(w, Bmat, ldb, nsig);
+    return upload_common(w, Bmat, ldb, nsig, cudaMemcpyHostToDevice, /*allow_lazy=*/true);
 }
 
 static int64_t support_cap(const csb200_dict* d, int64_t k) {

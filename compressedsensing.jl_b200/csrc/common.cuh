@@ -69,6 +69,18 @@ struct StateArgs {
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache = nullptr);
 // One 8-CTA cluster per signal (update_cluster.cu): the single-/few-signal paths.
 cudaError_t launch_omp_update_cluster(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache = nullptr);
+// Whole-solve kernel for small dictionaries (solve_small.cu): mode 0 omp, 1 gomp, 2 mp.
+struct SmallSolveArgs {
+    int mode, k, l;
+    double eps;
+    int stride;                 // slots per signal in sel / x
+    const int* x0_idx;          // mp warm start (device pointers) or nullptr
+    const double* x0_val;
+    const int* x0_nnz;
+    int x0_stride;
+};
+bool small_solve_eligible(int ld, int N, int kcap, int nsig, bool f32);
+cudaError_t launch_small_solve(const StateArgs& a, const SmallSolveArgs& q, bool f32, cudaStream_t st);
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st);
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx, const double* x0_val,

@@ -1,0 +1,238 @@
+// Whole-solve kernel for SMALL dictionaries: one CTA carries one signal through every `update!` of an
+// omp / gomp / mp call in a single launch.
+//
+// At BASELINE config 1 (128 x 256 FP64, k = 8: a 256 KiB dictionary) the per-iteration pipeline of the
+// large paths (correlation kernel + update kernel per `update!`) is pure launch latency: 17 launches of a
+// few microseconds for 0.5 Mflop of arithmetic.  Here the loop of the reference
+// (/root/reference/src/matchingpursuit.jl:34-40, 73-82, 126-139) runs inside the kernel:
+//   correlation c = A'r: a warp takes 4 atoms at a time, lanes stride the rows (coalesced; the dictionary
+//     stays in L1/L2 across iterations), FP64 accumulation, fixed reduction order;
+//   |c| argmax / top-l by block reductions with exclusion (value desc, index asc: Julia `argmax`,
+//     `partialsortperm(rev = true)`);
+//   append_atom (update_common.cuh): implicit-Q orthogonalisation, R^{-1} column, residual down-date;
+//   eps test after the update, GOMP remainder update after an eps-break, MP increments.
+// Signal, residual, support, R^{-1} and Q'b stay in shared memory from the first iteration to the last;
+// the only global traffic besides the dictionary is b in and the results out.
+#include "common.cuh"
+#include "update_common.cuh"
+
+namespace csb {
+namespace {
+
+constexpr int ST = 256;     // threads per CTA
+constexpr int SW = ST / 32;
+
+template <typename T>
+__global__ void __launch_bounds__(ST, 2) small_solve_kernel(StateArgs a, SmallSolveArgs q) {
+    extern __shared__ double dsm[];
+    const int ld = a.ld, kcap = a.kcap, N = a.N;
+    const int ldT = kcap | 1;
+    PursuitSmem<T> S;
+    S.v = dsm;                                   // [ld]
+    double* bs = S.v + ld;                       // [ld]  signal
+    double* rs = bs + ld;                        // [ld]  residual (values are T-representable)
+    double* cv = rs + ld;                        // [N]   signed correlations
+    S.g = cv + N;
+    S.hh = S.g + kcap;
+    S.ys = S.hh + kcap;
+    S.y = S.ys + kcap;
+    S.zs = S.y + kcap;
+    double* Tsm = S.zs + kcap;                   // [kcap][ldT]
+    S.ssel = reinterpret_cast<int*>(Tsm + (size_t)kcap * ldT);
+    S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
+    __shared__ double red[SW];
+    __shared__ int red_i[SW];
+    __shared__ int s_cand[MAX_S];
+    S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red;
+
+    const int sig = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T* A = static_cast<const T*>(a.A);
+    const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
+    T* rg = static_cast<T*>(a.R) + (size_t)sig * ld;
+
+    // r = b (the state of a freshly constructed MP/OMP/GOMP object); reject NaN/Inf
+    double s2 = 0.0;
+    int bad = 0;
+    for (int row = tid; row < ld; row += ST) {
+        const double e = (double)b[row];
+        bs[row] = e; rs[row] = e;
+        s2 += e * e;
+        bad |= !isfinite(e);
+    }
+    double nr = sqrt(block_sum<ST>(s2, red));
+    if (__syncthreads_or(bad)) {
+        if (tid == 0) { a.flags[sig] = 4; a.nnz[sig] = 0; a.iters[sig] = 0; a.resnorm[sig] = nr; }
+        return;
+    }
+    int t = 0, flags = 0, iters = 0;
+    bool done = false;
+
+    if (q.mode == 2 && q.x0_nnz) {                                       // mp warm start: r = b - A x0
+        const int n0 = q.x0_nnz[sig];
+        s2 = 0.0;
+        for (int row = tid; row < ld; row += ST) {
+            double acc = bs[row];
+            for (int e = 0; e < n0; ++e)
+                acc -= (double)A[(size_t)(q.x0_idx[(size_t)sig * q.x0_stride + e] - a.idx_offset) * ld + row] *
+                       q.x0_val[(size_t)sig * q.x0_stride + e];
+            const T rr = (T)acc;
+            rs[row] = (double)rr;
+            s2 += (double)rr * (double)rr;
+        }
+        nr = sqrt(block_sum<ST>(s2, red));
+    }
+
+    const int loop_updates = q.mode == 1 ? q.k / q.l : q.k;
+    const int rem = q.mode == 1 ? q.k % q.l : 0;
+    const int total_updates = loop_updates + (rem > 0 ? 1 : 0);
+    for (int it = 0; it < total_updates; ++it) {
+        const bool is_rem = it == loop_updates;                          // gomp remainder: runs even after a break
+        if (done && !is_rem) continue;
+        const int take = q.mode == 1 ? (is_rem ? rem : q.l) : 1;
+        if (q.mode != 2 && !(t < a.M)) { ++iters; if (!(nr >= q.eps)) done = true; continue; }   // :63,:117
+
+        // ---- c = A'r : 4 atoms per warp at a time, lanes over rows ----
+        for (int j0 = warp * 4; j0 < N; j0 += SW * 4) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const T* col[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) col[c] = A + (size_t)(j0 + c < N ? j0 + c : N - 1) * ld;
+            for (int row = lane; row < ld; row += 32) {
+                const double rr = rs[row];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] = fma((double)col[c][row], rr, acc[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double s = warp_sum(acc[c]);
+                if (lane == 0 && j0 + c < N) cv[j0 + c] = s;
+            }
+        }
+        __syncthreads();
+
+        // ---- top-`take` of |c| (value desc, index asc) ----
+        double pv = 0.0;
+        int pi = -1;
+        for (int round = 0; round < take; ++round) {
+            double bv = -1.0;
+            int bi = INT_MAX;
+            for (int j = tid; j < N; j += ST) {
+                const double v = fabs(cv[j]);
+                const bool ok = (round == 0) || (v < pv) || (v == pv && j > pi);
+                if (ok && v > bv) { bv = v; bi = j; }                    // j ascends: first maximum wins; NaN never wins
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            __syncthreads();
+            if (lane == 0) { red[warp] = bv; red_i[warp] = bi; }
+            __syncthreads();
+            bv = red[0]; bi = red_i[0];
+#pragma unroll
+            for (int w = 1; w < SW; ++w)
+                if (cand_better(red[w], red_i[w], bv, bi)) { bv = red[w]; bi = red_i[w]; }
+            pv = bv; pi = bi;
+            if (tid == 0) s_cand[round] = (bi == INT_MAX) ? -1 : bi;
+            if (bi == INT_MAX) { for (int r2 = round + 1 + tid; r2 < take; r2 += ST) s_cand[r2] = -1; break; }
+        }
+        __syncthreads();
+
+        if (q.mode == 2) {
+            // ---- mp: x[i] += <a_i, r>;  r <- r - <a_i, r> a_i   (:26-31) ----
+            const int j = s_cand[0];
+            double c = 0.0;
+            if (j >= 0) {
+                c = cv[j];
+                const T* aj = A + (size_t)j * ld;
+                s2 = 0.0;
+                for (int row = tid; row < ld; row += ST) {
+                    const T rr = (T)(rs[row] - c * (double)aj[row]);
+                    rs[row] = (double)rr;
+                    s2 += (double)rr * (double)rr;
+                }
+                nr = sqrt(block_sum<ST>(s2, red));
+            } else {
+                flags |= 2;
+            }
+            if (tid == 0) {
+                a.sel[(size_t)sig * q.stride + it] = j < 0 ? -1 : j + a.idx_offset;
+                a.x[(size_t)sig * q.stride + it] = c;
+            }
+            ++iters;
+            t = iters;
+            __syncthreads();
+            continue;
+        }
+
+        // ---- omp / gomp: append the candidates that are not active yet ----
+        for (int round = 0; round < take; ++round) {
+            const int jl = s_cand[round];
+            if (jl < 0) { flags |= 2; continue; }
+            const int j = jl + a.idx_offset;
+            int in = 0;
+            for (int i = tid; i < t; i += ST) in |= (S.ssel[i] == j);
+            if (__syncthreads_or(in)) continue;                          // :66, util.jl:119
+            if (t >= kcap || t >= a.M) break;
+            double nr2 = 0.0;
+            const int dep = append_atom<T, ST>(
+                S, t, j, A + (size_t)jl * ld, ld, [&](int row) { return bs[row]; }, [&](int row) { return rs[row]; },
+                [&](int row, T val) { rs[row] = (double)val; }, nr2);
+            if (dep) flags |= 1; else nr = sqrt(nr2);
+        }
+        ++iters;
+        if (!(nr >= q.eps)) done = true;                                 // `norm(residual!(P, x)) >= eps || break`
+    }
+
+    // ---- results ----
+    if (q.mode != 2) {
+        for (int i = tid; i < t; i += ST) {                              // x_S = R^{-1} Q'b  (`ldiv!`, :175)
+            double acc = 0.0;
+            for (int l = i; l < t; ++l) acc = fma(Tsm[i + l * ldT], S.zs[l], acc);
+            a.x[(size_t)sig * q.stride + i] = acc;
+            a.sel[(size_t)sig * q.stride + i] = S.ssel[i];
+        }
+    }
+    for (int row = tid; row < ld; row += ST) rg[row] = (T)rs[row];
+    if (tid == 0) {
+        a.nnz[sig] = t;
+        a.iters[sig] = iters;
+        a.resnorm[sig] = nr;
+        a.flags[sig] = flags;
+        a.done[sig] = done ? 1 : 0;
+    }
+}
+
+size_t small_smem_bytes(int ld, int N, int kcap) {
+    return (size_t)(3 * ld + N + 5 * kcap + (size_t)kcap * (kcap | 1)) * sizeof(double) +
+           (size_t)((kcap + 1) & ~1) * sizeof(int) + (size_t)kcap * sizeof(void*);
+}
+
+}  // namespace
+
+bool small_solve_eligible(int ld, int N, int kcap, int nsig, bool f32) {
+    const size_t dict_bytes = (size_t)ld * N * (f32 ? 4 : 8);
+    return dict_bytes <= ((size_t)2 << 20) && N <= 4096 && kcap <= 64 && nsig <= 512 &&
+           small_smem_bytes(ld, N, kcap) <= 100 * 1024;
+}
+
+cudaError_t launch_small_solve(const StateArgs& a, const SmallSolveArgs& q, bool f32, cudaStream_t st) {
+    if (a.nsig <= 0) return cudaSuccess;
+    const size_t smem = small_smem_bytes(a.ld, a.N, a.kcap);
+    cudaError_t e;
+    if (f32) {
+        e = cudaFuncSetAttribute(small_solve_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        small_solve_kernel<float><<<a.nsig, ST, smem, st>>>(a, q);
+    } else {
+        e = cudaFuncSetAttribute(small_solve_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        small_solve_kernel<double><<<a.nsig, ST, smem, st>>>(a, q);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace csb

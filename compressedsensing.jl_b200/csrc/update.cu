@@ -47,33 +47,36 @@ template <typename T>
 __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem) {
     extern __shared__ double dsm[];
     const int ld = a.ld, kcap = a.kcap;
-    double* v = dsm;                 // [ld]   working vector
-    double* g = v + ld;              // [kcap]  A_S' v
-    double* hh = g + kcap;           // [kcap]  Q'v of the current sweep
-    double* h = hh + kcap;           // [kcap]  accumulated Q'a
-    double* ys = h + kcap;           // [kcap]  accumulated R^{-1} Q'a
-    double* y = ys + kcap;           // [kcap]  R^{-1} Q'v of the current sweep
-    double* zs = y + kcap;           // [kcap]  Q'b
-    double* xs = zs + kcap;          // [kcap]  coefficients
-    int* ssel = reinterpret_cast<int*>(xs + kcap);            // [kcap] support, selection order
-    const T** colp = reinterpret_cast<const T**>(ssel + ((kcap + 1) & ~1));   // [kcap] columns of the active atoms
-    double* Tsm = reinterpret_cast<double*>(colp + kcap);     // [kcap][ldT] inverse factor (optional)
+    PursuitSmem<T> S;
+    S.v = dsm;
+    S.g = S.v + ld;
+    S.hh = S.g + kcap;
+    S.ys = S.hh + kcap;
+    S.y = S.ys + kcap;
+    S.zs = S.y + kcap;
+    S.ssel = reinterpret_cast<int*>(S.zs + kcap);
+    S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
+    double* Tsm = reinterpret_cast<double*>(S.colp + kcap);        // [kcap][ldT] inverse factor (optional)
     __shared__ double red[UW];
     __shared__ int red_i[UW];
     __shared__ int s_cand[MAX_S];
     __shared__ double s_cval[MAX_S];
 
     const int sig = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (a.done[sig] && !a.ignore_done) return;                     // the reference `break`s (:79,:132)
 
     const T* A = static_cast<const T*>(a.A);
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
     T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
-    double* Tg = a.Rf + (size_t)sig * kcap * kcap;                 // R^{-1}, column-major, ld = kcap
-    // working copy of R^{-1}: shared memory with an odd leading dimension (conflict-free column walks)
-    double* Tm = t_in_smem ? Tsm : Tg;
-    const int ldT = t_in_smem ? (kcap | 1) : kcap;
+    // R^{-1}: global copy (column-major, ld = kcap) plus a shared working copy with an odd leading
+    // dimension (conflict-free column walks) when it fits
+    S.Tg = a.Rf + (size_t)sig * kcap * kcap;
+    S.Tsm = t_in_smem ? Tsm : nullptr;
+    S.Tm = t_in_smem ? Tsm : S.Tg;
+    S.ldT = t_in_smem ? (kcap | 1) : kcap;
+    S.kcap = kcap;
+    S.red = red;
     int t = a.nnz[sig];
     int flags = 0;
     bool changed = false;
@@ -81,12 +84,12 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
 
     for (int i = tid; i < t; i += UT) {
         const int si = a.sel[(size_t)sig * kcap + i];
-        ssel[i] = si;
-        zs[i] = a.z[(size_t)sig * kcap + i];
-        colp[i] = Acache ? Acache + (size_t)i * ld : A + (size_t)(si - a.idx_offset) * ld;
+        S.ssel[i] = si;
+        S.zs[i] = a.z[(size_t)sig * kcap + i];
+        S.colp[i] = Acache ? Acache + (size_t)i * ld : A + (size_t)(si - a.idx_offset) * ld;
     }
     if (t_in_smem)
-        for (int e = tid; e < t * kcap; e += UT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * ldT] = Tg[e]; }
+        for (int e = tid; e < t * kcap; e += UT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * S.ldT] = S.Tg[e]; }
     __syncthreads();
 
     if (t < a.M) {                                                 // `nnz(x) < size(P.A, 1) || return x` (:63,:117)
@@ -97,81 +100,14 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
             const int j = s_cand[round];
             if (j < 0) { flags |= 2; continue; }
             int in = 0;
-            for (int i = tid; i < t; i += UT) in |= (ssel[i] == j);
+            for (int i = tid; i < t; i += UT) in |= (S.ssel[i] == j);
             if (__syncthreads_or(in)) continue;                    // already active: nothing to add (:66, util.jl:119)
             if (t >= kcap || t >= a.M) break;                      // capacity of UpdatableQR(T, n, k)
-
             const T* aj = Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld;
-            double s2 = 0.0;
-            for (int row = tid; row < ld; row += UT) { const double e = (double)aj[row]; v[row] = e; s2 += e * e; }
-            const double anorm2 = block_sum<UT>(s2, red);
-            double before2 = anorm2, rho2 = anorm2;
-            for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
-                for (int i = warp; i < t; i += UW) {               // g = A_S' v
-                    const T* ai = colp[i];
-                    double s = 0.0;
-                    for (int row = lane; row < ld; row += 32) s += (double)ai[row] * v[row];
-                    s = warp_sum(s);
-                    if (lane == 0) g[i] = s;
-                }
-                __syncthreads();
-                // hh = R^{-T} g = Q'v and y = R^{-1} hh as two triangular mat-vecs with the stored inverse:
-                // no substitution chain, every output element is an independent dot product.
-                for (int i = tid; i < t; i += UT) {
-                    double acc = 0.0;
-                    for (int l = 0; l <= i; ++l) acc = fma(Tm[l + i * ldT], g[l], acc);
-                    hh[i] = acc;
-                }
-                __syncthreads();
-                for (int i = tid; i < t; i += UT) {
-                    double acc = 0.0;
-                    for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], hh[l], acc);
-                    y[i] = acc;
-                    h[i] = sweep ? h[i] + hh[i] : hh[i];
-                    ys[i] = sweep ? ys[i] + acc : acc;
-                }
-                __syncthreads();
-                s2 = 0.0;
-                for (int row = tid; row < ld; row += UT) {         // v -= A_S y
-                    double acc = v[row];
-                    for (int i = 0; i < t; ++i) acc -= (double)colp[i][row] * y[i];
-                    v[row] = acc;
-                    s2 += acc * acc;
-                }
-                rho2 = block_sum<UT>(s2, red);
-                if (rho2 >= 0.5 * before2) break;                  // DGKS: one sweep was enough
-                before2 = rho2;
-            }
-            if (!(rho2 > 1e-26 * anorm2)) { flags |= 1; continue; }   // numerically dependent atom: not appended
-            const double rho = sqrt(rho2);
-            double sb = 0.0;
-            for (int row = tid; row < ld; row += UT) sb += v[row] * (double)b[row];
-            const double zt = block_sum<UT>(sb, red) / rho;            // z_t = q_t' b
-            // residual: r = b - Q Q'b gains one term, r <- r - q_t z_t.  Identical to the reference's
-            // from-scratch b - A_S x_S (x_S = R^{-1} Q'b) up to rounding, at one pass less over A_S.
-            const double gam = zt / rho;
-            double s2r = 0.0;
-            for (int row = tid; row < ld; row += UT) {
-                const T rr = (T)((double)r[row] - gam * v[row]);
-                r[row] = rr;
-                s2r += (double)rr * (double)rr;
-            }
-            nr2 = block_sum<UT>(s2r, red);
-            // append the column [h; rho] to R  <=>  append [-R^{-1}h / rho; 1/rho] to R^{-1}
-            const double irho = 1.0 / rho;
-            for (int i = tid; i < t; i += UT) {
-                const double e = -ys[i] * irho;
-                Tg[i + (size_t)t * kcap] = e;
-                if (t_in_smem) Tsm[i + t * ldT] = e;
-            }
-            if (tid == 0) {
-                Tg[t + (size_t)t * kcap] = irho;
-                if (t_in_smem) Tsm[t + t * ldT] = irho;
-                zs[t] = zt; ssel[t] = j; colp[t] = aj;
-            }
-            ++t;
-            changed = true;
-            __syncthreads();
+            const int dep = append_atom<T, UT>(
+                S, t, j, aj, ld, [&](int row) { return (double)b[row]; }, [&](int row) { return (double)r[row]; },
+                [&](int row, T val) { r[row] = val; }, nr2);
+            if (dep) flags |= 1; else changed = true;
         }
     }
 
@@ -179,10 +115,10 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
     if (changed) {
         for (int i = tid; i < t; i += UT) {                        // x_S = R^{-1} Q'b  (`ldiv!`, :175)
             double acc = 0.0;
-            for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], zs[l], acc);
+            for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.zs[l], acc);
             a.x[(size_t)sig * kcap + i] = acc;
-            a.sel[(size_t)sig * kcap + i] = ssel[i];
-            a.z[(size_t)sig * kcap + i] = zs[i];
+            a.sel[(size_t)sig * kcap + i] = S.ssel[i];
+            a.z[(size_t)sig * kcap + i] = S.zs[i];
         }
         nr = sqrt(nr2);
     }
@@ -296,7 +232,7 @@ __global__ void nonfinite_check_kernel(const T* __restrict__ p, size_t n, int* f
 }
 
 size_t update_smem_bytes(int ld, int kcap, bool t_in_smem) {
-    size_t bytes = (size_t)(ld + 7 * kcap) * sizeof(double) + (size_t)((kcap + 1) & ~1) * sizeof(int) +
+    size_t bytes = (size_t)(ld + 5 * kcap) * sizeof(double) + (size_t)((kcap + 1) & ~1) * sizeof(int) +
                    (size_t)kcap * sizeof(void*);
     if (t_in_smem) bytes += (size_t)kcap * (kcap | 1) * sizeof(double);
     return bytes;

@@ -63,4 +63,104 @@ __device__ void select_candidates(const double* __restrict__ pv, const int* __re
 }
 
 
+// Shared-memory working set of one signal's pursuit state (pointers into the CTA's shared memory).
+template <typename T>
+struct PursuitSmem {
+    double* v;        // [ld]    working vector
+    double* g;        // [kcap]  A_S' v
+    double* hh;       // [kcap]  Q'v of the current sweep
+    double* ys;       // [kcap]  accumulated R^{-1} Q'a
+    double* y;        // [kcap]  R^{-1} Q'v of the current sweep
+    double* zs;       // [kcap]  Q'b
+    int* ssel;        // [kcap]  support, selection order
+    const T** colp;   // [kcap]  columns of the active atoms
+    double* Tm;       // inverse factor R^{-1} the mat-vecs read (shared or global), leading dimension ldT
+    int ldT;
+    double* Tsm;      // shared copy of R^{-1} or nullptr
+    double* Tg;       // global copy of R^{-1} (ld = kcap) or nullptr
+    int kcap;
+    double* red;      // [NT/32] reduction scratch
+};
+
+// `add_column!(AiQR, a, pos)` + the residual part of `ldiv!!` / `residual!` for ONE new atom (reference:
+// src/util.jl:118-126, src/matchingpursuit.jl:152-176), by the whole CTA:
+//   v = a_j;  (g = A_S'v, hh = R^{-T}g, y = R^{-1}hh, v -= A_S y) once, twice if ||v|| collapsed (DGKS);
+//   rho = ||v||;  z_t = v'b / rho;  r <- r - (z_t / rho) v;  R^{-1} gains the column [-y/rho; 1/rho].
+// b_at(row) / r_at(row) / r_set(row, val) abstract where the signal and residual live (global or shared).
+// Returns 0 when the atom was appended (t is incremented, nr2 = ||r||^2), 1 when it is numerically dependent.
+template <typename T, int NT, typename BAt, typename RAt, typename RSet>
+__device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
+                                           BAt b_at, RAt r_at, RSet r_set, double& nr2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double s2 = 0.0;
+    for (int row = tid; row < ld; row += NT) { const double e = (double)aj[row]; S.v[row] = e; s2 += e * e; }
+    const double anorm2 = block_sum<NT>(s2, S.red);
+    double before2 = anorm2, rho2 = anorm2;
+    for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
+        for (int i = warp; i < t; i += NT / 32) {                  // g = A_S' v
+            const T* ai = S.colp[i];
+            double s = 0.0;
+            for (int row = lane; row < ld; row += 32) s += (double)ai[row] * S.v[row];
+            s = warp_sum(s);
+            if (lane == 0) S.g[i] = s;
+        }
+        __syncthreads();
+        // hh = R^{-T} g = Q'v and y = R^{-1} hh as two triangular mat-vecs with the stored inverse:
+        // no substitution chain, every output element is an independent dot product.
+        for (int i = tid; i < t; i += NT) {
+            double acc = 0.0;
+            for (int l = 0; l <= i; ++l) acc = fma(S.Tm[l + i * S.ldT], S.g[l], acc);
+            S.hh[i] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < t; i += NT) {
+            double acc = 0.0;
+            for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.hh[l], acc);
+            S.y[i] = acc;
+            S.ys[i] = sweep ? S.ys[i] + acc : acc;
+        }
+        __syncthreads();
+        s2 = 0.0;
+        for (int row = tid; row < ld; row += NT) {                 // v -= A_S y
+            double acc = S.v[row];
+            for (int i = 0; i < t; ++i) acc -= (double)S.colp[i][row] * S.y[i];
+            S.v[row] = acc;
+            s2 += acc * acc;
+        }
+        rho2 = block_sum<NT>(s2, S.red);
+        if (rho2 >= 0.5 * before2) break;                          // DGKS: one sweep was enough
+        before2 = rho2;
+    }
+    if (!(rho2 > 1e-26 * anorm2)) return 1;                        // numerically dependent atom: not appended
+    const double rho = sqrt(rho2);
+    double sb = 0.0;
+    for (int row = tid; row < ld; row += NT) sb += S.v[row] * b_at(row);
+    const double zt = block_sum<NT>(sb, S.red) / rho;              // z_t = q_t' b
+    // residual: r = b - Q Q'b gains one term, r <- r - q_t z_t.  Identical to the reference's
+    // from-scratch b - A_S x_S (x_S = R^{-1} Q'b) up to rounding, at one pass less over A_S.
+    const double gam = zt / rho;
+    double s2r = 0.0;
+    for (int row = tid; row < ld; row += NT) {
+        const T rr = (T)(r_at(row) - gam * S.v[row]);
+        r_set(row, rr);
+        s2r += (double)rr * (double)rr;
+    }
+    nr2 = block_sum<NT>(s2r, S.red);
+    // append the column [h; rho] to R  <=>  append [-R^{-1}h / rho; 1/rho] to R^{-1}
+    const double irho = 1.0 / rho;
+    for (int i = tid; i < t; i += NT) {
+        const double e = -S.ys[i] * irho;
+        if (S.Tg) S.Tg[i + (size_t)t * S.kcap] = e;
+        if (S.Tsm) S.Tsm[i + t * S.ldT] = e;
+    }
+    if (tid == 0) {
+        if (S.Tg) S.Tg[t + (size_t)t * S.kcap] = irho;
+        if (S.Tsm) S.Tsm[t + t * S.ldT] = irho;
+        S.zs[t] = zt; S.ssel[t] = j; S.colp[t] = aj;
+    }
+    ++t;
+    __syncthreads();
+    return 0;
+}
+
 }  // namespace csb

@@ -71,24 +71,22 @@ def test_argument_dispatch_mirrors_julia_methods(cs, monkeypatch):
     """omp(A,b,k::Int) vs omp(A,b,eps::Real,k) vs keywords -- checked without touching the GPU."""
     calls = []
 
-    class FakeBatch:
-        def __init__(self, *a): pass
-        def __enter__(self): return self
-        def __exit__(self, *a): pass
-        def upload(self, B): self.n = 1 if np.ndim(B) == 1 else B.shape[1]
-        def omp(self, k, eps): calls.append(("omp", k, eps))
-        def gomp(self, l, k, eps): calls.append(("gomp", l, k, eps))
-        def download(self, stride):
-            return (-np.ones((self.n, stride), dtype=np.int64), np.zeros((self.n, stride)),
-                    np.zeros(self.n, dtype=np.int64), np.zeros(self.n), np.zeros(self.n, dtype=np.int64))
+    class FakeLib:
+        def __init__(self, real): self._real = real
+        def __getattr__(self, name): return getattr(self._real, name)
+        def csb200_omp(self, h, B, ldb, nsig, k, eps, sel, coef, nnz, res, its):
+            calls.append(("omp", k, eps)); return 0
+        def csb200_gomp(self, h, B, ldb, nsig, l, k, eps, sel, coef, nnz, res, its):
+            calls.append(("gomp", l, k, eps)); return 0
 
     class FakeDict:
         def __init__(self, A, device=0):
-            self.M, self.N = A.shape; self.n_total = self.N; self.dtype = A.dtype
+            self.M, self.N = A.shape; self.n_total = self.N; self.dtype = A.dtype; self._h = None
         def close(self): pass
 
-    monkeypatch.setattr(cs, "Batch", FakeBatch)
+    monkeypatch.setattr(cs, "lib", FakeLib(cs.lib))
     monkeypatch.setattr(cs, "Dictionary", FakeDict)
+    monkeypatch.setattr(cs, "_to_sparse", lambda n, sel, coef, nnz: cs.SparseVector(n, np.zeros(0, np.int64), np.zeros(0)))
     A = np.zeros((8, 12)); b = np.zeros(8)
     eps64 = np.finfo(np.float64).eps
     cs.omp(A, b, 3);                       assert calls[-1] == ("omp", 3, eps64)
@@ -104,5 +102,7 @@ def test_argument_dispatch_mirrors_julia_methods(cs, monkeypatch):
         cs.omp(A, b, -1.0)
     with pytest.raises(ValueError, match="has to be non-negative"):
         cs.gomp(A, b, 2, -1.0, 3)
+    with pytest.raises(ValueError):
+        cs.omp(A, np.zeros(7), 3)           # DimensionMismatch
     out = cs.omp(A, np.zeros((8, 5)), 3)
     assert isinstance(out, list) and len(out) == 5 and out[0].n == 12

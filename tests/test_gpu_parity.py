@@ -107,10 +107,14 @@ def _fixtures():
 
 
 @pytest.mark.parametrize("path", _fixtures(), ids=lambda p: os.path.basename(p)[:-4])
-@pytest.mark.parametrize("impl", ["gemm", "gemv"])
-@pytest.mark.parametrize("update", ["cta", "cluster"])
+@pytest.mark.parametrize("impl,update", [("gemm", "cta"), ("gemv", "cta"), ("gemm", "cluster"), ("gemv", "cluster"),
+                                         ("small", "cta")])
 def test_golden(cs, path, impl, update, monkeypatch):
-    monkeypatch.setenv("CSB200_UPDATE_IMPL", update)        # one CTA per signal / one 8-CTA cluster per signal
+    # correlation kernel: DMMA GEMM / GEMV (multi-launch path) or the whole-solve small-dictionary kernel;
+    # update kernel of the multi-launch path: one CTA per signal / one 8-CTA cluster per signal
+    monkeypatch.setenv("CSB200_UPDATE_IMPL", update)
+    if impl == "small":
+        impl = None
     z = np.load(path, allow_pickle=False)
     meta = json.loads(str(z["meta"]))
     A, Bm = np.asfortranarray(z["A"]), np.asfortranarray(z["B"])
@@ -150,7 +154,14 @@ def test_golden(cs, path, impl, update, monkeypatch):
 
 
 # ------------------------------------------------------------------ reference call surface + quirks
-def test_call_surface_and_quirks(cs, po):
+@pytest.fixture(params=["small_solve", "multi_launch"])
+def solve_path(request, monkeypatch):
+    """Small dictionaries normally take the whole-solve kernel; CSB200_SMALL_SOLVE=0 forces the per-iteration path."""
+    monkeypatch.setenv("CSB200_SMALL_SOLVE", "1" if request.param == "small_solve" else "0")
+    return request.param
+
+
+def test_call_surface_and_quirks(cs, po, solve_path):
     rng = np.random.default_rng(3)
     A, x0, b = po.sparse_data(rng, 32, 48, 3)
     with cs.Dictionary(A) as D:
@@ -189,7 +200,7 @@ def test_call_surface_and_quirks(cs, po):
     assert x.nzind.tolist() == x0.nzind
 
 
-def test_noop_iteration_zero_signal_and_remainder(cs, po):
+def test_noop_iteration_zero_signal_and_remainder(cs, po, solve_path):
     A = np.asfortranarray(np.eye(6))
     with cs.Dictionary(A) as D:
         b = np.array([1.0, 1.0, 0, 0, 0, 0])
@@ -216,7 +227,7 @@ def test_noop_iteration_zero_signal_and_remainder(cs, po):
     assert got.nzind.tolist() == ref.nzind and got.nnz() <= 6
 
 
-def test_dependent_atom_is_not_appended(cs):
+def test_dependent_atom_is_not_appended(cs, solve_path):
     """Duplicate columns: once one copy is active the other can only win on a zero residual; the update
     must leave a finite state (the reference's QR would divide by a zero diagonal here)."""
     A = np.asfortranarray(np.array([[1.0, 1.0, 0], [0, 0, 1.0], [0, 0, 0]]))
