@@ -260,8 +260,12 @@ def ours_arm(args):
     peak, peak_src = fp64_peak()
     flop_per_launch = 2.0 * M * N * B
     achieved = flop_per_launch * corr_launches / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "corr_gemm_traffic.json")
+    if os.path.exists(tpath) and B == 65536:          # the ncu capture was taken at exactly this shape
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "corr_gemm_f64_kernel", "launches": int(corr_launches),
+                "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/corr_gemm_traffic.json)", "kernel": "corr_gemm_f64_kernel", "launches": int(corr_launches),
                 "mean_launch_ms": corr_ms / max(1, corr_launches), "share_of_step": corr_ms / dev_ms if dev_ms else None,
                 "flop_per_launch": flop_per_launch, "peak_source": peak_src}
 
