@@ -76,7 +76,7 @@ int make_operand_map(CUtensorMap* map, void* base, int64_t ld, int64_t ncols) {
 
 enum CorrImpl { IMPL_AUTO = 0, IMPL_GEMM = 1, IMPL_GEMV = 2, IMPL_NAIVE = 3 };
 constexpr int GEMM_MIN_SIGNALS = 24;
-constexpr int CLUSTER_UPDATE_MAX_SIGNALS = 24;   // below this one CTA per signal leaves the GPU idle: use a cluster per signal   // below this the per-signal GEMV passes win over a padded 128-wide tile
+constexpr int CLUSTER_UPDATE_MAX_SIGNALS = 24;   // below this one CTA per signal leaves the GPU idle: use a cluster per signal
 
 }  // namespace
 
@@ -249,6 +249,23 @@ int finish(csb200_batch* b, bool solve = false) {
 int check_ready(csb200_batch* b) {
     if (!b) return CSB200_ERR_INVALID_ARG;
     if (b->nsig <= 0) { g_last_error = "no signals uploaded"; return CSB200_ERR_INVALID_ARG; }
+    return CSB200_OK;
+}
+
+// The update and GEMV kernels keep one signal-length vector (and the k x k inverse factor) in shared memory.
+int check_shape_fits(const csb200_batch* b, bool needs_factor) {
+    const csb200_dict* d = b->dict;
+    const size_t gemv = (size_t)d->ld * sizeof(double);
+    const size_t upd = !needs_factor ? 0
+                       : b->nsig < CLUSTER_UPDATE_MAX_SIGNALS ? omp_update_cluster_smem_bytes((int)d->ld, (int)b->kcap)
+                                                              : omp_update_smem_bytes((int)d->ld, (int)b->kcap);
+    if (gemv > MAX_DYN_SMEM || upd > MAX_DYN_SMEM) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "signal length %lld with max_sparsity %lld needs %zu bytes of shared memory per CTA "
+                 "(limit %zu)", (long long)d->M, (long long)b->kcap, gemv > upd ? gemv : upd, MAX_DYN_SMEM);
+        g_last_error = buf;
+        return CSB200_ERR_UNSUPPORTED;
+    }
     return CSB200_OK;
 }
 
@@ -519,6 +536,7 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
         if ((rc = run_small_solve(b, 0, k, 1, eps, nullptr, nullptr, nullptr, 0))) return rc;
         return finish(b, true);
     }
+    if ((rc = check_shape_fits(b, true))) return rc;
     if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
     const bool f32 = d->dtype == CSB200_F32;
@@ -550,6 +568,7 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
         if ((rc = run_small_solve(b, 1, k, l, eps, nullptr, nullptr, nullptr, 0))) return rc;
         return finish(b, true);
     }
+    if ((rc = check_shape_fits(b, true))) return rc;
     if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
     const bool f32 = d->dtype == CSB200_F32;
@@ -611,6 +630,7 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
         if ((rc = run_small_solve(b, 2, iters, 1, 0.0, x0.idx, x0.val, x0.nnz, (int)x0_stride))) return rc;
         return finish(b, true);
     }
+    if ((rc = check_shape_fits(b, false))) return rc;
     if ((rc = settle_input(b))) return rc;
     if ((rc = begin_solve(b))) return rc;
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), f32, b->stream);

@@ -81,6 +81,9 @@ struct SmallSolveArgs {
 };
 bool small_solve_eligible(int ld, int N, int kcap, int nsig, bool f32);
 cudaError_t launch_small_solve(const StateArgs& a, const SmallSolveArgs& q, bool f32, cudaStream_t st);
+size_t omp_update_smem_bytes(int ld, int kcap);            // dynamic shared memory the kernels above need
+size_t omp_update_cluster_smem_bytes(int ld, int kcap);
+constexpr size_t MAX_DYN_SMEM = 227 * 1024;
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st);
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx, const double* x0_val,

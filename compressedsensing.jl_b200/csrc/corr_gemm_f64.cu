@@ -33,11 +33,16 @@ namespace {
 constexpr int TILE_N = 128;                 // atoms per CTA tile
 constexpr int TILE_B = 128;                 // signals per CTA tile
 constexpr int KCH = 16;                     // doubles per k-chunk: 128 B rows
-constexpr int STAGES = 4;
 constexpr int A_TILE_BYTES = TILE_N * KCH * 8;
 constexpr int R_TILE_BYTES = TILE_B * KCH * 8;
-constexpr int STAGE_BYTES = A_TILE_BYTES + R_TILE_BYTES;   // 32 KiB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+constexpr int BOX_PAIR_BYTES = A_TILE_BYTES + R_TILE_BYTES;   // one 16-deep k-slice of both operands: 32 KiB
+// A pipeline stage holds SUB such slices (SUB = 1: 4 stages x 32 KiB, SUB = 2: 3 stages x 64 KiB): fewer, longer
+// stages halve the number of mbarrier round trips per flop.
+template <int SUB> struct Pipe {
+    static constexpr int STAGES = SUB == 1 ? 4 : 3;
+    static constexpr int STAGE_BYTES = SUB * BOX_PAIR_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -73,7 +78,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // 0.8-2.8 % of kernel time, and DRAM is at 2.3 % of its bandwidth either way on this tensor-bound kernel,
 // so the default keeps the faster order; CSB200_GEMM_BAND overrides it.
 constexpr int DEFAULT_BAND = 0;   // 0 = tilesN
-constexpr int DEFAULT_VARIANT = 0;
+constexpr int DEFAULT_VARIANT = -1;   // -1 = choose by shape
 __device__ __forceinline__ void tile_coords(int tile, int tilesN, int tilesB, int BAND, int& tn, int& tb) {
     const int per_band = BAND * tilesB;
     const int band = tile / per_band;
@@ -93,11 +98,13 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 //   <8,4,2,4>  8 warps, warp tile 64 x 32, 64 accumulators/thread, ~228 registers (fills the register file)
 //   <4,4,4,4> 16 warps, warp tile 32 x 32, 32 accumulators/thread, <=128 registers: twice the warps per
 //             scheduler to cover LDS / mbarrier latency at the price of 8 instead of 6 LDS.128 per 32 DMMA
-template <int MI, int NJ, int WM, int WN>
+template <int MI, int NJ, int WM, int WN, int SUB>
 __global__ void __launch_bounds__(WM * WN * 32, 1)
 corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
                      int N, int nsig, int kchunks, int tilesN, int tilesB, int band, int S, int P, int idx_offset,
                      double* __restrict__ pval, int* __restrict__ pidx) {
+    constexpr int STAGES = Pipe<SUB>::STAGES;
+    constexpr int STAGE_BYTES = Pipe<SUB>::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
     uint8_t* sm = smem_raw + pad;                       // 1024 B aligned: required by SWIZZLE_128B
@@ -133,8 +140,11 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         mbar_wait(bar_empty + stg * 8, par);
         mbar_arrive_expect_tx(bar_full + stg * 8, STAGE_BYTES);
         const uint32_t dst = sm_base + stg * STAGE_BYTES;
-        tma_load_2d(dst, &mapA, bar_full + stg * 8, kc * KCH, tn * TILE_N);
-        tma_load_2d(dst + A_TILE_BYTES, &mapR, bar_full + stg * 8, kc * KCH, tb * TILE_B);
+#pragma unroll
+        for (int u = 0; u < SUB; ++u) {          // k-slices past the end of the matrix are zero-filled by TMA
+            tma_load_2d(dst + u * BOX_PAIR_BYTES, &mapA, bar_full + stg * 8, (kc * SUB + u) * KCH, tn * TILE_N);
+            tma_load_2d(dst + u * BOX_PAIR_BYTES + A_TILE_BYTES, &mapR, bar_full + stg * 8, (kc * SUB + u) * KCH, tb * TILE_B);
+        }
     };
     if (threadIdx.x == 0) {
         for (int c = 0; c < STAGES - 1 && c < total_chunks; ++c) issue_chunk(c);
@@ -166,9 +176,11 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             if (threadIdx.x == 0 && chunk + STAGES - 1 < total_chunks) issue_chunk(chunk + STAGES - 1);
             __syncwarp();
             mbar_wait(bar_full + stage * 8, phase);
-            const uint8_t* st = sm + stage * STAGE_BYTES;
+            const uint8_t* st0 = sm + stage * STAGE_BYTES;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int hh = 0; hh < 2 * SUB; ++hh) {
+                const int h = hh & 1;
+                const uint8_t* st = st0 + (hh >> 1) * BOX_PAIR_BYTES;
                 const uint32_t sw = (uint32_t)(((4 * h + q) ^ g) << 4);      // SWIZZLE_128B: chunk ^= row % 8
                 double2 af[MI], bf[NJ];
 #pragma unroll
@@ -243,9 +255,11 @@ int gemm_variant() {
 int corr_gemm_f64_block() { return gemm_variant() == 1 ? 32 : 64; }
 
 cudaError_t corr_gemm_f64_setup() {
-    cudaError_t e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(corr_gemm_f64_kernel<4, 4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(corr_gemm_f64_kernel<4, 4, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
 }
 
 cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* mapR, const CorrArgs& a,
@@ -258,12 +272,20 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     static const int band_env = [] { const char* e = getenv("CSB200_GEMM_BAND"); return e ? atoi(e) : 0; }();
     int band = band_env > 0 ? band_env : DEFAULT_BAND;
     if (band <= 0 || band > tilesN) band = tilesN;
-    if (gemm_variant() == 1)
-        corr_gemm_f64_kernel<4, 4, 4, 4><<<grid, 512, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN,
-                                                                        tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+    const int kslices = a.ld / KCH;
+    int variant = gemm_variant();
+    // default: 64 KiB stages (2 k-slices per mbarrier round trip; measured 2.7 % faster at K = 1024) unless an odd
+    // slice count would make the zero-filled tail slice a noticeable share of the work
+    if (variant < 0) variant = (kslices % 2 == 0 || kslices >= 16) ? 2 : 0;
+    if (variant == 1)
+        corr_gemm_f64_kernel<4, 4, 4, 4, 1><<<grid, 512, Pipe<1>::SMEM_BYTES, st>>>(
+            *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+    else if (variant == 2)
+        corr_gemm_f64_kernel<8, 4, 2, 4, 2><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
+            *mapA, *mapR, a.N, a.nsig, (kslices + 1) / 2, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
     else
-        corr_gemm_f64_kernel<8, 4, 2, 4><<<grid, 256, SMEM_BYTES, st>>>(*mapA, *mapR, a.N, a.nsig, a.ld / KCH, tilesN,
-                                                                        tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+        corr_gemm_f64_kernel<8, 4, 2, 4, 1><<<grid, 256, Pipe<1>::SMEM_BYTES, st>>>(
+            *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
     return cudaGetLastError();
 }
 

@@ -240,6 +240,8 @@ size_t update_smem_bytes(int ld, int kcap, bool t_in_smem) {
 
 }  // namespace
 
+size_t omp_update_smem_bytes(int ld, int kcap) { return update_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K); }
+
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
     if (a.nsig <= 0) return cudaSuccess;
     const int t_in_smem = a.kcap <= T_SMEM_MAX_K ? 1 : 0;

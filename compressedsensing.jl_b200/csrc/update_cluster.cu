@@ -257,6 +257,8 @@ cudaError_t launch_t(const StateArgs& a, cudaStream_t st, const void* Acache) {
 
 }  // namespace
 
+size_t omp_update_cluster_smem_bytes(int ld, int kcap) { return cluster_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K_CL); }
+
 cudaError_t launch_omp_update_cluster(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
     if (a.nsig <= 0) return cudaSuccess;
     return f32 ? launch_t<float>(a, st, Acache) : launch_t<double>(a, st, Acache);
