@@ -32,7 +32,7 @@ import numpy as np
 __all__ = [
     "SparseVector", "Dictionary", "Batch", "omp", "gomp", "mp", "lib", "LIB_PATH", "CSB200Error",
     "device_count", "F64", "F32", "ShardComm", "omp_sharded", "shard_range", "owner_of", "pick_global",
-    "exchange_unique_id",
+    "exchange_unique_id", "assemble_csc",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -87,6 +87,7 @@ def _load() -> ctypes.CDLL:
                                 f64p, i64p]),
         "csb200_mp": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, i64p, f64p, i64p, c_int64, i64p, f64p,
                               f64p]),
+        "csb200_assemble_csc": (c_int, [c_int64, c_int64, i64p, f64p, i64p, c_int64, i64p, i64p, f64p]),
         "csb200_comm_unique_id": (c_int, [c_void_p]),
         "csb200_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
         "csb200_comm_destroy": (c_int, [c_void_p]),
@@ -107,7 +108,8 @@ EXPORTED_SYMBOLS = [
     "csb200_dict_create_shard", "csb200_dict_destroy", "csb200_dict_trim", "csb200_dict_shape", "csb200_batch_create",
     "csb200_batch_destroy", "csb200_batch_upload", "csb200_batch_upload_device", "csb200_batch_omp",
     "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
-    "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp", "csb200_comm_unique_id",
+    "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp",
+    "csb200_assemble_csc", "csb200_comm_unique_id",
     "csb200_comm_create", "csb200_comm_destroy", "csb200_omp_sharded", "csb200_debug_corr_topk",
     "csb200_debug_get_residual",
 ]
@@ -332,9 +334,25 @@ def _signals_for(D: "Dictionary", b) -> np.ndarray:
     return np.asfortranarray(B.astype(D.dtype, copy=False))
 
 
-def _solve(A, b, device, call, stride, eps=None, merge=None):
+def assemble_csc(n: int, sel: np.ndarray, coef: np.ndarray, nnz: np.ndarray):
+    """(colptr, rowval, nzval) of the n x nsig coefficient matrix, 0-based, rows ascending within each column --
+    the batched result format (what the Julia shim wraps in a SparseMatrixCSC)."""
+    nsig, stride = sel.shape
+    colptr = np.empty(nsig + 1, dtype=np.int64)
+    total = int(nnz.sum())
+    rowval = np.empty(max(total, 1), dtype=np.int64)
+    nzval = np.empty(max(total, 1), dtype=np.float64)
+    sel = np.ascontiguousarray(sel, dtype=np.int64); coef = np.ascontiguousarray(coef, dtype=np.float64)
+    nnz = np.ascontiguousarray(nnz, dtype=np.int64)
+    _check(lib.csb200_assemble_csc(nsig, stride, _i64p(sel), _f64p(coef), _i64p(nnz), 0, _i64p(colptr), _i64p(rowval),
+                                   _f64p(nzval)))
+    return colptr, rowval[:total], nzval[:total]
+
+
+def _solve(A, b, device, call, stride, eps=None, merge=None, result="vectors"):
     """One-shot solve through the host-buffer C entry points (csb200_omp / csb200_gomp / csb200_mp): upload,
-    solve and download happen inside one C call on a workspace cached on the dictionary handle."""
+    solve and download happen inside one C call on a workspace cached on the dictionary handle.
+    result = "vectors": SparseVector (or a list of them); "csc": scipy.sparse.csc_matrix (N x nsig), assembled in C."""
     single = np.asarray(b).ndim == 1
     D, owned = _dictionary(A, device)
     try:
@@ -347,6 +365,10 @@ def _solve(A, b, device, call, stride, eps=None, merge=None):
         res = np.empty(nsig, dtype=np.float64)
         its = np.empty(nsig, dtype=np.int64)
         _check(call(D, B, ldb, nsig, sel, coef, nnz, res, its), eps)
+        if result == "csc" and merge is None:
+            import scipy.sparse as sp
+            colptr, rowval, nzval = assemble_csc(D.n_total, sel, coef, nnz)
+            return sp.csc_matrix((nzval, rowval, colptr), shape=(D.n_total, nsig))
         if merge is not None:
             out = [merge(D.n_total, sel[s], coef[s], int(nnz[s]), s) for s in range(nsig)]
         else:
@@ -361,7 +383,7 @@ def _is_int(v) -> bool:
     return isinstance(v, (int, np.integer)) and not isinstance(v, bool)
 
 
-def omp(A, b, *args, max_residual=None, sparsity=None, device: int = 0):
+def omp(A, b, *args, max_residual=None, sparsity=None, device: int = 0, result: str = "vectors"):
     """Orthogonal matching pursuit -- `omp` (`src/matchingpursuit.jl:73-91`).
 
     omp(A, b, k) | omp(A, b, eps[, k]) | omp(A, b, max_residual=..., sparsity=...)
@@ -385,10 +407,10 @@ def omp(A, b, *args, max_residual=None, sparsity=None, device: int = 0):
         return lib.csb200_omp(D._h, B.ctypes.data, ldb, nsig, k, eps, _i64p(sel), _f64p(coef), _i64p(nnz), _f64p(res),
                               _i64p(its))
 
-    return _solve(A, b, device, call, stride, eps)
+    return _solve(A, b, device, call, stride, eps, result=result)
 
 
-def gomp(A, b, l: int, *args, max_residual=None, sparsity=None, device: int = 0):
+def gomp(A, b, l: int, *args, max_residual=None, sparsity=None, device: int = 0, result: str = "vectors"):
     """Generalized OMP, l atoms per update -- `gomp` (`src/matchingpursuit.jl:126-148`)."""
     M, N = (A.M, A.n_total) if isinstance(A, Dictionary) else np.shape(A)
     dt = A.dtype if isinstance(A, Dictionary) else (np.float32 if np.asarray(A).dtype == np.float32 else np.float64)
@@ -409,7 +431,7 @@ def gomp(A, b, l: int, *args, max_residual=None, sparsity=None, device: int = 0)
         return lib.csb200_gomp(D._h, B.ctypes.data, ldb, nsig, int(l), k, eps, _i64p(sel), _f64p(coef), _i64p(nnz),
                                _f64p(res), _i64p(its))
 
-    return _solve(A, b, device, call, stride, eps)
+    return _solve(A, b, device, call, stride, eps, result=result)
 
 
 def mp(A, b, k: int, x=None, device: int = 0):

@@ -7,12 +7,14 @@
 #include "../../include/csb200.h"
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace csb;
@@ -801,6 +803,28 @@ int csb200_mp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64
     rc = csb200_batch_mp(b, iters_k, x0_idx, x0_val, x0_nnz, x0_stride);
     if (!rc) rc = csb200_batch_download(b, iters_k, sel_idx, coef, nullptr, resnorm, nullptr);
     return rc;
+}
+
+// ---- batched result format ---------------------------------------------------------------------
+int csb200_assemble_csc(int64_t nsig, int64_t stride, const int64_t* sel_idx, const double* coef, const int64_t* nnz,
+                        int64_t index_base, int64_t* colptr, int64_t* rowval, double* nzval) {
+    if (nsig < 0 || stride < 0 || !sel_idx || !coef || !nnz || !colptr || (index_base != 0 && index_base != 1))
+        return CSB200_ERR_INVALID_ARG;
+    int64_t at = 0;
+    std::vector<std::pair<int64_t, double>> tmp;
+    for (int64_t s = 0; s < nsig; ++s) {
+        colptr[s] = at + index_base;
+        const int64_t t = nnz[s];
+        if (t < 0 || t > stride) return CSB200_ERR_INVALID_ARG;
+        if (t > 0 && (!rowval || !nzval)) return CSB200_ERR_INVALID_ARG;
+        tmp.clear();
+        for (int64_t j = 0; j < t; ++j) tmp.emplace_back(sel_idx[s * stride + j], coef[s * stride + j]);
+        std::sort(tmp.begin(), tmp.end(), [](const std::pair<int64_t, double>& a, const std::pair<int64_t, double>& b) { return a.first < b.first; });
+        for (int64_t j = 0; j < t; ++j) { rowval[at + j] = tmp[j].first + index_base; nzval[at + j] = tmp[j].second; }
+        at += t;
+    }
+    colptr[nsig] = at + index_base;
+    return CSB200_OK;
 }
 
 // ---- test / debug hooks ------------------------------------------------------------------------

@@ -82,10 +82,10 @@ function to_sparse(N::Int, sel::AbstractVector{Int64}, coef::AbstractVector{Floa
     return SparseVector(N, idx[p], coef[1:nnz][p])
 end
 
-function run_omp_like(fn::Symbol, D::Dictionary, b, l::Int, ε::Real, k::Int)
+function run_omp_like(fn::Symbol, D::Dictionary, b, l::Int, ε::Real, k::Int; csc::Bool = false)
     B = signals(D, b)
     nsig = size(B, 2)
-    stride = max(min(k, D.M, D.N), 1)
+    stride = max(k, 1)                 # the C call writes k slots per signal
     sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
     nnz = Vector{Int64}(undef, nsig); res = Vector{Float64}(undef, nsig); its = Vector{Int64}(undef, nsig)
     GC.@preserve B sel coef nnz res its begin
@@ -100,15 +100,27 @@ function run_omp_like(fn::Symbol, D::Dictionary, b, l::Int, ε::Real, k::Int)
         end
         check(rc, ε)
     end
+    csc && return assemble_csc(D.N, sel, coef, nnz)
     xs = [to_sparse(D.N, view(sel, :, s), view(coef, :, s), nnz[s]) for s in 1:nsig]
     return b isa AbstractVector ? xs[1] : xs
 end
 
+# batched result format: the N x nsig coefficient matrix as a SparseMatrixCSC (assembled by the library)
+function assemble_csc(N::Int, sel::Matrix{Int64}, coef::Matrix{Float64}, nnz::Vector{Int64})
+    stride, nsig = size(sel)
+    colptr = Vector{Int64}(undef, nsig + 1); total = sum(nnz)
+    rowval = Vector{Int64}(undef, total); nzval = Vector{Float64}(undef, total)
+    check(ccall((:csb200_assemble_csc, libcsb200), Cint,
+        (Int64, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}),
+        nsig, stride, sel, coef, nnz, 1, colptr, rowval, nzval))
+    return SparseMatrixCSC(N, nsig, colptr, rowval, nzval)
+end
+
 # ---------------------------------------------------------------------------------------------
 # omp  (src/matchingpursuit.jl:73-91)
-function omp(A::MatOrDict, b::AbstractVecOrMat, ε::Real, k::Int = size(A, 1))
+function omp(A::MatOrDict, b::AbstractVecOrMat, ε::Real, k::Int = size(A, 1); csc::Bool = false)
     ε ≥ 0 || throw("ε = $ε has to be non-negative")
-    run_omp_like(:omp, as_dictionary(A), b, 1, ε, k)
+    run_omp_like(:omp, as_dictionary(A), b, 1, ε, k; csc = csc)     # csc = true: N x nsig SparseMatrixCSC (additive)
 end
 omp(A::MatOrDict, b::AbstractVecOrMat, k::Int) = omp(A, b, eps(eltype(A)), k)
 omp(A::MatOrDict, b::AbstractVecOrMat; max_residual = eps(eltype(A)), sparsity = min(size(A)...)) =

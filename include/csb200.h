@@ -132,6 +132,14 @@ int csb200_mp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, in
               const int64_t* x0_idx, const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride,
               int64_t* sel_idx, double* coef, double* resnorm);
 
+/* ---- batched result format (host-side helper, no GPU work) ---------------------------------
+ * Assemble the selection-order outputs of csb200_omp / csb200_gomp (sel_idx, coef, nnz with `stride` slots per
+ * signal) into compressed-sparse-column arrays of the N x nsig coefficient matrix -- Julia's SparseMatrixCSC
+ * (colptr, rowval, nzval): within each column (signal) row indices ascend, as in the reference's SparseVector.
+ * index_base = 1 for Julia, 0 for C / Python.  colptr has nsig + 1 entries; rowval / nzval need sum(nnz). */
+int csb200_assemble_csc(int64_t nsig, int64_t stride, const int64_t* sel_idx, const double* coef, const int64_t* nnz,
+                        int64_t index_base, int64_t* colptr, int64_t* rowval, double* nzval);
+
 /* ---- column-sharded single-dictionary mode (one process per GPU, NCCL over NVLink) -------
  * Each rank holds a csb200_dict_create_shard() slice.  csb200_comm_* wrap one NCCL
  * communicator; the unique id (128 bytes) is produced on rank 0 and distributed by the host

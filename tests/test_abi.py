@@ -106,3 +106,13 @@ def test_argument_dispatch_mirrors_julia_methods(cs, monkeypatch):
         cs.omp(A, np.zeros(7), 3)           # DimensionMismatch
     out = cs.omp(A, np.zeros((8, 5)), 3)
     assert isinstance(out, list) and len(out) == 5 and out[0].n == 12
+
+
+def test_assemble_csc_host_helper(cs):
+    """Batched result format: selection-order outputs -> CSC arrays, rows ascending per column."""
+    sel = np.array([[5, 2, 9, -1], [-1, -1, -1, -1], [7, 0, -1, -1]], dtype=np.int64)
+    coef = np.array([[1.0, 2.0, 3.0, 0], [0, 0, 0, 0], [4.0, 5.0, 0, 0]])
+    nnz = np.array([3, 0, 2], dtype=np.int64)
+    colptr, rowval, nzval = cs.assemble_csc(12, sel, coef, nnz)
+    assert colptr.tolist() == [0, 3, 3, 5]
+    assert rowval.tolist() == [2, 5, 9, 0, 7] and nzval.tolist() == [2.0, 1.0, 3.0, 5.0, 4.0]
