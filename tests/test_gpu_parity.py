@@ -400,3 +400,60 @@ def test_sharded_multi_gpu(cs):
                         "--master-addr", "127.0.0.1", "--master-port", "29617", script], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ------------------------------------------------------------------ BASELINE configs 3 and 5 at their full dictionary shapes
+@pytest.mark.slow
+def test_c3_gomp_full_dictionary_shape(cs, po):
+    """BASELINE config 3: gomp (l = 4) on a 2048 x 32768 FP64 dictionary, k = 64; 256 signals on the GPU
+    (DMMA GEMM path), the first 3 against the oracle, all against the planted support."""
+    rng = np.random.default_rng(33)
+    M, N, k, l, B = 2048, 32768, 64, 4, 256
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, B)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+        batch.upload(Bm)
+        batch.gomp(l, k, float(np.finfo(float).eps))
+        sel, coef, nnz, res, its = batch.download(k)
+    for s in range(B):
+        idx, val = _sorted(sel[s], coef[s], int(nnz[s]))
+        assert idx.tolist() == X0[s].nzind, s
+        assert np.allclose(val, X0[s].nzval, rtol=1e-10, atol=1e-10), s
+    for s in range(3):
+        t = po.Trace()
+        ref = po.gomp(A, Bm[:, s], l, k, trace=t)
+        assert sel[s, :k].tolist() == t.order(), (s, "selection sequence", min(t.margin))
+        idx, val = _sorted(sel[s], coef[s], k)
+        assert idx.tolist() == ref.nzind and _close(val, ref.nzval, RTOL64)
+        assert int(its[s]) == t.iterations
+
+
+@pytest.mark.slow
+def test_c5_mp_full_dictionary_shape(cs, po):
+    """BASELINE config 5: mp on a 4096 x 65536 FP64 dictionary (2 GiB); 64 signals, 24 iterations (the config's 200
+    are a matter of time, not of code path), 2 signals against the oracle; residual norms decrease monotonically."""
+    rng = np.random.default_rng(55)
+    M, N, iters, B = 4096, 65536, 24, 64
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, 16, B, noise=1e-2)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, iters) as batch:
+        batch.upload(Bm)
+        batch.mp(iters)
+        sel, coef, nnz, res, its = batch.download(iters)
+        R = batch.residual()
+    assert (nnz == iters).all()
+    for s in range(2):
+        t = po.Trace()
+        ref = po.mp(A, Bm[:, s], iters, trace=t)
+        assert sel[s, :iters].tolist() == t.order(), (s, min(t.margin))
+        acc = {}
+        for i, c in zip(sel[s].tolist(), coef[s].tolist()):
+            acc[i] = acc.get(i, 0.0) + c
+        assert sorted(acc) == ref.nzind
+        assert _close([acc[i] for i in sorted(acc)], ref.nzval, 1e-9)
+        assert abs(res[s] - t.resnorm[-1]) < 1e-10
+    for s in range(B):
+        x = np.zeros(N)
+        np.add.at(x, sel[s], coef[s])
+        assert np.linalg.norm(Bm[:, s] - A @ x - R[:, s]) < 1e-11          # r really is b - A x
+        assert res[s] < np.linalg.norm(Bm[:, s])
