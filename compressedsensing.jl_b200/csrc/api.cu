@@ -91,7 +91,10 @@ struct csb200_dict {
     bool has_map = false;
     int num_sms = 148;
     std::mutex mu;
+    std::mutex gram_mu;
     csb200_batch* workspace = nullptr;   // reused by the one-shot entry points (csb200_omp/gomp/mp)
+    double* gram = nullptr;              // A'A (N x N, FP64), built on first use by a large batched omp/gomp
+    bool gram_failed = false;
     size_t esize() const { return dtype == CSB200_F32 ? 4 : 8; }
 };
 
@@ -105,6 +108,7 @@ struct csb200_batch {
     int* pidx = nullptr;
     size_t pcap = 0;            // candidate slots allocated
     int cur_P = 0;              // atom blocks per signal written by the last correlation pass
+    bool use_gram = false;      // this solve takes A_S'a_j from the dictionary's Gram matrix
     // per-signal state: one device block laid out [resnorm | x | nnz | iters | flags | done | sel | z] so that
     // the results of a small solve come back in a single copy (state_result_bytes covers everything but z)
     unsigned char* state_blk = nullptr;
@@ -166,6 +170,7 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
     a.ignore_done = ignore_done; a.eps = eps;
     a.pval = b->pval; a.pidx = b->pidx; a.nnz = b->nnz; a.sel = b->sel; a.Rf = b->Rf; a.z = b->z; a.x = b->x;
     a.resnorm = b->resnorm; a.iters = b->iters; a.done = b->done; a.flags = b->flags;
+    a.gram = b->use_gram ? d->gram : nullptr;
     return a;
 }
 
@@ -224,6 +229,30 @@ int run_small_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double eps,
     if (e != cudaSuccess) return fail_cuda(e, "small_solve");
     b->other_launches++;
     return CSB200_OK;
+}
+
+// Gram matrix A'A for the batched update kernel: with it the first orthogonalisation sweep reads t numbers
+// instead of gathering t atoms.  Worth its 2 N^2 M flop only for large batches; cached on the dictionary.
+constexpr int64_t GRAM_MAX_ATOMS = 16384;            // 2 GiB
+constexpr int64_t GRAM_MIN_SIGNAL_ITERS = 1 << 18;   // nsig * k below which building it does not pay
+void decide_gram(csb200_batch* b, int64_t k) {
+    csb200_dict* d = b->dict;
+    b->use_gram = false;
+    const char* env = getenv("CSB200_GRAM");
+    if (env && !strcmp(env, "0")) return;
+    const bool force = env && !strcmp(env, "1");
+    if (d->dtype != CSB200_F64 || d->n_total != d->N || d->N > GRAM_MAX_ATOMS || !d->has_map || d->gram_failed) return;
+    if (!force && (b->nsig * k < GRAM_MIN_SIGNAL_ITERS || b->nsig < CLUSTER_UPDATE_MAX_SIGNALS)) return;
+    std::lock_guard<std::mutex> lk(d->gram_mu);
+    if (!d->gram) {
+        double* g = nullptr;
+        if (cudaMalloc(&g, (size_t)d->N * d->N * sizeof(double)) != cudaSuccess) { cudaGetLastError(); d->gram_failed = true; return; }
+        cudaError_t e = launch_gemm_f64_store(&d->mapA, &d->mapA, (int)d->N, (int)d->N, (int)d->ld, g, d->N, d->num_sms, b->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+        if (e != cudaSuccess) { cudaGetLastError(); cudaFree(g); d->gram_failed = true; return; }
+        d->gram = g;
+    }
+    b->use_gram = true;
 }
 
 cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
@@ -426,6 +455,7 @@ int csb200_dict_destroy(csb200_dict* d) {
     if (!d) return CSB200_OK;
     cudaSetDevice(d->device);
     if (d->workspace) csb200_batch_destroy(d->workspace);
+    cudaFree(d->gram);
     cudaFree(d->dA);
     delete d;
     return CSB200_OK;
@@ -541,6 +571,7 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     if ((rc = check_shape_fits(b, true))) return rc;
     if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
+    decide_gram(b, k);
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
@@ -573,6 +604,7 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     if ((rc = check_shape_fits(b, true))) return rc;
     if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
+    decide_gram(b, k);
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);

@@ -37,6 +37,9 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
                                  int num_sms, cudaStream_t st);
 cudaError_t corr_gemm_f64_setup();   // one-time cudaFuncSetAttribute
 int corr_gemm_f64_block();           // atoms per candidate block of the DMMA GEMM epilogue (32 or 64)
+// Plain store epilogue of the same DMMA GEMM: C[sig + atom * ldc] = <A[:, atom], R[:, sig]> (used for A'A).
+cudaError_t launch_gemm_f64_store(const CUtensorMap* mapA, const CUtensorMap* mapR, int N, int nsig, int ld,
+                                  double* C, long long ldc, int num_sms, cudaStream_t st);
 cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_corr_naive(const CorrArgs& a, bool f32, cudaStream_t st);
 
@@ -62,7 +65,8 @@ struct StateArgs {
     double* resnorm;      // [nsig]
     int* iters;           // [nsig]
     int* done;            // [nsig]  eps-break flag
-    int* flags;           // [nsig]  bit0: dependent atom skipped, bit1: no candidate
+    int* flags;           // [nsig]  bit0: dependent atom skipped, bit1: no candidate, bit2: non-finite input
+    const double* gram;   // optional N x N Gram matrix A'A (ld = N), FP64 dictionaries only; nullptr = not available
 };
 // Acache (optional): ld x kcap buffer holding the active atoms' columns in selection order, with the
 // candidate's column already stored in slot nnz (column-sharded mode: the atom may live on a peer).

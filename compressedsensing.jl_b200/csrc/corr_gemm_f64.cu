@@ -98,11 +98,11 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 //   <8,4,2,4>  8 warps, warp tile 64 x 32, 64 accumulators/thread, ~228 registers (fills the register file)
 //   <4,4,4,4> 16 warps, warp tile 32 x 32, 32 accumulators/thread, <=128 registers: twice the warps per
 //             scheduler to cover LDS / mbarrier latency at the price of 8 instead of 6 LDS.128 per 32 DMMA
-template <int MI, int NJ, int WM, int WN, int SUB>
+template <int MI, int NJ, int WM, int WN, int SUB, bool STORE = false>
 __global__ void __launch_bounds__(WM * WN * 32, 1)
 corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
                      int N, int nsig, int kchunks, int tilesN, int tilesB, int band, int S, int P, int idx_offset,
-                     double* __restrict__ pval, int* __restrict__ pidx) {
+                     double* __restrict__ pval, int* __restrict__ pidx, long long ldc = 0) {
     constexpr int STAGES = Pipe<SUB>::STAGES;
     constexpr int STAGE_BYTES = Pipe<SUB>::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -201,6 +201,23 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
 
+        if constexpr (STORE) {
+            // ---- plain store epilogue: C[sig + atom * ldc]; a thread's (e = 0, 1) pair is one 16 B store ----
+#pragma unroll
+            for (int i = 0; i < MI; ++i) {
+                const int atom = tn * TILE_N + wm * 8 * MI + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int sig = tb * TILE_B + wn * 8 * NJ + j * 8 + 2 * q;
+                    if (atom < N) {
+                        double* dst = pval + (size_t)atom * ldc + sig;
+                        if (sig + 1 < nsig && (ldc & 1) == 0) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        else { if (sig < nsig) dst[0] = acc[i][j][0]; if (sig + 1 < nsig) dst[1] = acc[i][j][1]; }
+                    }
+                }
+            }
+            continue;
+        }
         // ---- fused epilogue: top-S of |c| over this warp's 8*MI atoms, per signal column ----
         // acc[i][j][e] = c[atom = wm*8*MI + i*8 + g][signal = wn*8*NJ + j*8 + 2q + e]
         const int atom0 = tn * TILE_N + wm * 8 * MI + g;
@@ -259,6 +276,8 @@ cudaError_t corr_gemm_f64_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(corr_gemm_f64_kernel<4, 4, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
 }
 
@@ -286,6 +305,18 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     else
         corr_gemm_f64_kernel<8, 4, 2, 4, 1><<<grid, 256, Pipe<1>::SMEM_BYTES, st>>>(
             *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_f64_store(const CUtensorMap* mapA, const CUtensorMap* mapR, int N, int nsig, int ld,
+                                  double* C, long long ldc, int num_sms, cudaStream_t st) {
+    const int tilesN = (N + TILE_N - 1) / TILE_N;
+    const int tilesB = (nsig + TILE_B - 1) / TILE_B;
+    const long long ntiles = (long long)tilesN * tilesB;
+    if (ntiles <= 0) return cudaSuccess;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    corr_gemm_f64_kernel<8, 4, 2, 4, 1, true><<<grid, 256, Pipe<1>::SMEM_BYTES, st>>>(
+        *mapA, *mapR, N, nsig, ld / KCH, tilesN, tilesB, tilesN, 1, 1, 0, C, nullptr, ldc);
     return cudaGetLastError();
 }
 

@@ -254,6 +254,7 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
         sa.nnz = (int*)(base + o.nnz); sa.sel = (int*)(base + o.sel); sa.Rf = (double*)(base + o.T);
         sa.z = (double*)(base + o.z); sa.x = (double*)(base + o.x); sa.resnorm = (double*)(base + o.res);
         sa.iters = (int*)(base + o.it); sa.done = (int*)(base + o.done); sa.flags = (int*)(base + o.flags);
+        sa.gram = nullptr;
 
         int* dflag = (int*)(base + o.flags);
         e = launch_nonfinite_check(base + o.b, (size_t)ld, f32, dflag, st);

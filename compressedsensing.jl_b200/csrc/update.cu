@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
             const T* aj = Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld;
             const int dep = append_atom<T, UT>(
                 S, t, j, aj, ld, [&](int row) { return (double)b[row]; }, [&](int row) { return (double)r[row]; },
-                [&](int row, T val) { r[row] = val; }, nr2);
+                [&](int row, T val) { r[row] = val; }, nr2,
+                (a.gram && !Acache) ? a.gram + (size_t)(j - a.idx_offset) * a.N : nullptr, a.idx_offset);
             if (dep) flags |= 1; else changed = true;
         }
     }

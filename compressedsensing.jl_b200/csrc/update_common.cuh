@@ -88,21 +88,28 @@ struct PursuitSmem {
 //   rho = ||v||;  z_t = v'b / rho;  r <- r - (z_t / rho) v;  R^{-1} gains the column [-y/rho; 1/rho].
 // b_at(row) / r_at(row) / r_set(row, val) abstract where the signal and residual live (global or shared).
 // Returns 0 when the atom was appended (t is incremented, nr2 = ||r||^2), 1 when it is numerically dependent.
+// gcol (optional): column j of the precomputed Gram matrix A'A indexed by LOCAL atom index; when given, the first
+// sweep takes g = A_S'a_j from it (t scattered 8-byte loads) instead of gathering the t active atoms.
 template <typename T, int NT, typename BAt, typename RAt, typename RSet>
 __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
-                                           BAt b_at, RAt r_at, RSet r_set, double& nr2) {
+                                           BAt b_at, RAt r_at, RSet r_set, double& nr2,
+                                           const double* __restrict__ gcol = nullptr, int idx_offset = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double s2 = 0.0;
     for (int row = tid; row < ld; row += NT) { const double e = (double)aj[row]; S.v[row] = e; s2 += e * e; }
     const double anorm2 = block_sum<NT>(s2, S.red);
     double before2 = anorm2, rho2 = anorm2;
     for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
-        for (int i = warp; i < t; i += NT / 32) {                  // g = A_S' v
-            const T* ai = S.colp[i];
-            double s = 0.0;
-            for (int row = lane; row < ld; row += 32) s += (double)ai[row] * S.v[row];
-            s = warp_sum(s);
-            if (lane == 0) S.g[i] = s;
+        if (sweep == 0 && gcol) {
+            for (int i = tid; i < t; i += NT) S.g[i] = gcol[S.ssel[i] - idx_offset];   // g = (A'A)[S, j]
+        } else {
+            for (int i = warp; i < t; i += NT / 32) {              // g = A_S' v
+                const T* ai = S.colp[i];
+                double s = 0.0;
+                for (int row = lane; row < ld; row += 32) s += (double)ai[row] * S.v[row];
+                s = warp_sum(s);
+                if (lane == 0) S.g[i] = s;
+            }
         }
         __syncthreads();
         // hh = R^{-T} g = Q'v and y = R^{-1} hh as two triangular mat-vecs with the stored inverse:

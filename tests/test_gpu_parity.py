@@ -272,6 +272,35 @@ def test_c2_shape_reduced_batch_vs_oracle(cs, po):
         assert _close(val, ref.nzval, RTOL64)
 
 
+@pytest.mark.parametrize("gram", ["0", "1"])
+def test_gram_matrix_path_matches_oracle(cs, po, gram, monkeypatch):
+    """The batched update can take A_S'a_j from a cached Gram matrix (CSB200_GRAM=1 forces it, =0 forbids it):
+    same selection sequence, same coefficients, ragged shape, omp and gomp."""
+    monkeypatch.setenv("CSB200_GRAM", gram)
+    monkeypatch.setenv("CSB200_SMALL_SOLVE", "0")
+    rng = np.random.default_rng(99)
+    M, N, k, B = 200, 1111, 14, 70
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, B, noise=5e-3)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+        batch.upload(Bm)
+        batch.omp(k, 0.0)
+        sel, coef, nnz, res, its = batch.download(k)
+        batch.gomp(3, k, 0.0)
+        gsel, gcoef, gnnz, gres, gits = batch.download(k)
+    for s in range(0, B, 5):
+        t = po.Trace()
+        ref = po.omp(A, Bm[:, s], k, eps=0.0, trace=t)
+        assert sel[s, :k].tolist() == t.order(), s
+        idx, val = _sorted(sel[s], coef[s], k)
+        assert _close(val, ref.nzval, RTOL64) and abs(res[s] - t.resnorm[-1]) < 1e-10
+        t = po.Trace()
+        ref = po.gomp(A, Bm[:, s], 3, k, eps=0.0, trace=t)
+        assert gsel[s, :int(gnnz[s])].tolist() == t.order(), s
+        idx, val = _sorted(gsel[s], gcoef[s], int(gnnz[s]))
+        assert idx.tolist() == ref.nzind and _close(val, ref.nzval, RTOL64)
+
+
 def test_gomp_and_mp_midsize_vs_oracle(cs, po):
     rng = np.random.default_rng(77)
     M, N, k, B = 256, 2048, 16, 64
