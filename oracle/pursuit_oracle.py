@@ -18,12 +18,15 @@ The one piece of arithmetic that lives in an un-vendored dependency is
 UpdatableQRFactorizations v1.0.0 (git-tree-sha1 dd1d0589f29fcac6f29bbeff2e3c698a4299c3db,
 `Manifest.toml:446-450`): `UpdatableQR(T,n,k)`, `add_column!(F,a,pos)`, `ldiv!(F,r)`.
 Its published contract is "QR of the active columns under column insertion, least-squares
-solve returned in logical (sorted) order".  Two interchangeable engines restate it here:
-  * ``ls="lapack"``  -- dense Householder LS on ``A[:, sort(S)]`` (ground truth), and
+solve returned in logical (sorted) order".  Three interchangeable engines restate it here:
+  * ``ls="lapack"``  -- dense Householder LS on ``A[:, sort(S)]`` (ground truth),
   * ``ls="givens"``  -- an updatable thin QR with Givens-rotation column insertion
                         (oracle/updatable_qr.py), the scheme the call-site comment at
-                        `src/util.jl:121` names.
-Both give the same answer to a few ulps; tests assert that (the property
+                        `src/util.jl:121` names, and
+  * ``ls="scipy"``   -- a full M x M Q (what the package's call sites reveal it keeps) updated
+                        by `scipy.linalg.qr_insert`, an independent published implementation of the same
+                        Givens column-insertion primitive.
+All three give the same answer to a few ulps; tests assert that (the property
 `test/forward.jl:24-28` pins).
 
 Indices are 0-based here; the reference is 1-based.  "first index on ties" is preserved.
@@ -174,6 +177,11 @@ class _ActiveSetLS:
         self.engine = engine
         if engine == "givens":
             self.qr = UpdatableQR(A.dtype, A.shape[0], capacity)
+        elif engine == "scipy":
+            # full (M x M) Q and M x t R updated by SciPy's Givens-based column insertion: an independent,
+            # published implementation of the same primitive (the call sites show the package keeps a full Q)
+            self.Q = np.eye(A.shape[0], dtype=A.dtype)
+            self.R = np.zeros((A.shape[0], 0), dtype=A.dtype)
         elif engine != "lapack":
             raise ValueError(f"unknown ls engine {engine!r}")
 
@@ -185,6 +193,9 @@ class _ActiveSetLS:
         pos = x.nzind.index(j)                              # util.jl:122  findfirst(==(i), x.nzind)
         if self.engine == "givens":
             self.qr.add_column(self.A[:, j], pos)           # util.jl:123
+        elif self.engine == "scipy":
+            from scipy.linalg import qr_insert
+            self.Q, self.R = qr_insert(self.Q, self.R, self.A[:, j], pos, which="col")
         return True
 
     def solve(self, x: SparseVec, b: np.ndarray) -> None:
@@ -192,6 +203,10 @@ class _ActiveSetLS:
         T = self.A.dtype
         if self.engine == "givens":
             y = self.qr.solve(np.asarray(b, dtype=T))
+        elif self.engine == "scipy":
+            from scipy.linalg import solve_triangular
+            t = self.R.shape[1]
+            y = solve_triangular(self.R[:t, :t], (self.Q.T @ np.asarray(b, dtype=T))[:t])
         else:
             AS = self.A[:, np.asarray(x.nzind, dtype=np.int64)]
             y, *_ = np.linalg.lstsq(AS, np.asarray(b, dtype=T), rcond=None)

@@ -57,7 +57,7 @@ def test_mp_properties(seed):
 
 
 @pytest.mark.parametrize("seed", SEEDS)
-@pytest.mark.parametrize("ls", ["lapack", "givens"])
+@pytest.mark.parametrize("ls", ["lapack", "givens", "scipy"])
 def test_omp_properties(seed, ls):
     """test/matchingpursuit.jl:21-29"""
     A, x, b, y = _problem(seed)
@@ -102,6 +102,21 @@ def test_updatable_qr_equals_dense_ls():
         assert np.allclose(F.solve(y), ref, rtol=1e-12, atol=1e-13)
         assert np.allclose(F.Q @ F.R, A[:, S], atol=1e-13)
         assert np.allclose(np.tril(F.R, -1), 0)
+
+
+def test_three_ls_engines_agree_on_every_iterate():
+    """LAPACK least squares, the thin Givens-insertion QR and SciPy's full-Q qr_insert give the same omp/gomp result."""
+    for seed in SEEDS[:8]:
+        rng = np.random.default_rng(1000 + seed)
+        A, x, b = po.sparse_data(rng, 40, 90, 6)
+        y = po.perturb(rng, b, 1e-2)
+        ref = po.omp(A, y, 8, ls="lapack")
+        for ls in ("givens", "scipy"):
+            got = po.omp(A, y, 8, ls=ls)
+            assert got.nzind == ref.nzind and np.allclose(got.nzval, ref.nzval, rtol=1e-11, atol=1e-13), ls
+            gg = po.gomp(A, y, 3, 8, ls=ls)
+            gr = po.gomp(A, y, 3, 8, ls="lapack")
+            assert gg.nzind == gr.nzind and np.allclose(gg.nzval, gr.nzval, rtol=1e-11, atol=1e-13), ls
 
 
 def test_argmax_first_index_on_ties_and_sign():
