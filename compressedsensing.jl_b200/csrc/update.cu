@@ -33,6 +33,7 @@
 // stages T and one signal-length vector v in shared memory.
 #include "common.cuh"
 #include "update_common.cuh"
+#include <cstdlib>
 
 namespace csb {
 namespace {
@@ -43,24 +44,39 @@ constexpr int UW = UT / 32;
 // Shared-memory budget for keeping the inverse factor on chip (above it the kernel works on the copy in L2).
 constexpr int T_SMEM_MAX_K = 96;
 
-template <typename T>
-__global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem) {
+// NT = 128 threads, 8 CTAs/SM for one atom per update (omp); NT = 256 with the block-append working set
+// (BLOCK: up to `bm` new atoms orthogonalised together, update_common.cuh append_block) for gomp.
+template <typename T, int NT, bool BLOCK>
+__global__ void __launch_bounds__(NT, BLOCK ? 2 : 8)
+omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int bm) {
     extern __shared__ double dsm[];
     const int ld = a.ld, kcap = a.kcap;
     PursuitSmem<T> S;
-    S.v = dsm;
-    S.g = S.v + ld;
-    S.hh = S.g + kcap;
-    S.ys = S.hh + kcap;
-    S.y = S.ys + kcap;
-    S.zs = S.y + kcap;
-    S.ssel = reinterpret_cast<int*>(S.zs + kcap);
+    double* p = dsm;
+    double* Vb = nullptr; double* Gm = nullptr; double* Ym = nullptr; double* sc = nullptr;
+    if constexpr (BLOCK) {
+        Vb = p; p += (size_t)bm * ld;                 // [bm][ld] block of new atoms / directions
+        S.v = Vb;                                     // the one-by-one fallback reuses a row of the block
+        Gm = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
+        Ym = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
+        sc = p; p += 4 * BLOCK_MAX;
+    } else {
+        S.v = p; p += ld;
+    }
+    S.g = p; p += kcap;
+    S.hh = p; p += kcap;
+    S.ys = p; p += kcap;
+    S.y = p; p += kcap;
+    S.zs = p; p += kcap;
+    S.ssel = reinterpret_cast<int*>(p);
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
     double* Tsm = reinterpret_cast<double*>(S.colp + kcap);        // [kcap][ldT] inverse factor (optional)
-    __shared__ double red[UW];
-    __shared__ int red_i[UW];
+    __shared__ double red[NT / 32];
+    __shared__ int red_i[NT / 32];
     __shared__ int s_cand[MAX_S];
     __shared__ double s_cval[MAX_S];
+    __shared__ int s_J[BLOCK_MAX];
+    __shared__ const T* s_Jcol[BLOCK_MAX];
 
     const int sig = blockIdx.x;
     const int tid = threadIdx.x;
@@ -81,40 +97,72 @@ __global__ void __launch_bounds__(UT, 8) omp_update_kernel(StateArgs a, const T*
     int flags = 0;
     bool changed = false;
     double nr2 = 0.0;
+    auto b_at = [&](int row) { return (double)b[row]; };
+    auto r_at = [&](int row) { return (double)r[row]; };
+    auto r_set = [&](int row, T val) { r[row] = val; };
 
-    for (int i = tid; i < t; i += UT) {
+    for (int i = tid; i < t; i += NT) {
         const int si = a.sel[(size_t)sig * kcap + i];
         S.ssel[i] = si;
         S.zs[i] = a.z[(size_t)sig * kcap + i];
         S.colp[i] = Acache ? Acache + (size_t)i * ld : A + (size_t)(si - a.idx_offset) * ld;
     }
     if (t_in_smem)
-        for (int e = tid; e < t * kcap; e += UT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * S.ldT] = S.Tg[e]; }
+        for (int e = tid; e < t * kcap; e += NT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * S.ldT] = S.Tg[e]; }
     __syncthreads();
 
     if (t < a.M) {                                                 // `nnz(x) < size(P.A, 1) || return x` (:63,:117)
         const size_t cbase = (size_t)sig * a.P * a.S;
-        select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
+        select_candidates<NT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
 
-        for (int round = 0; round < a.take; ++round) {
-            const int j = s_cand[round];
-            if (j < 0) { flags |= 2; continue; }
-            int in = 0;
-            for (int i = tid; i < t; i += UT) in |= (S.ssel[i] == j);
-            if (__syncthreads_or(in)) continue;                    // already active: nothing to add (:66, util.jl:119)
-            if (t >= kcap || t >= a.M) break;                      // capacity of UpdatableQR(T, n, k)
-            const T* aj = Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld;
-            const int dep = append_atom<T, UT>(
-                S, t, j, aj, ld, [&](int row) { return (double)b[row]; }, [&](int row) { return (double)r[row]; },
-                [&](int row, T val) { r[row] = val; }, nr2,
-                (a.gram && !Acache) ? a.gram + (size_t)(j - a.idx_offset) * a.N : nullptr, a.idx_offset);
-            if (dep) flags |= 1; else changed = true;
+        int round = 0;
+        while (round < a.take) {
+            if constexpr (BLOCK) {
+                // gather the next group of up to bm candidates that are not active yet (in |c| order)
+                int m = 0;
+                bool full = false;
+                while (round < a.take && m < bm) {
+                    const int j = s_cand[round];
+                    if (j < 0) { flags |= 2; ++round; continue; }
+                    int in = 0;
+                    for (int i = tid; i < t; i += NT) in |= (S.ssel[i] == j);
+                    if (__syncthreads_or(in)) { ++round; continue; }      // already active (:66, util.jl:119)
+                    if (t + m >= kcap || t + m >= a.M) { full = true; break; }   // capacity of UpdatableQR(T, n, k)
+                    if (tid == 0) { s_J[m] = j; s_Jcol[m] = A + (size_t)(j - a.idx_offset) * ld; }
+                    ++m; ++round;
+                }
+                __syncthreads();
+                if (m > 0) {
+                    int done_b = 0;
+                    if (m > 1) {
+                        done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2);
+                        if (done_b) changed = true;
+                    }
+                    for (int c = done_b; c < m; ++c) {                   // one by one: single atom, or DGKS fallback
+                        const int dep = append_atom<T, NT>(S, t, s_J[c], s_Jcol[c], ld, b_at, r_at, r_set, nr2);
+                        if (dep) flags |= 1; else changed = true;
+                    }
+                }
+                if (full) break;
+            } else {
+                const int j = s_cand[round++];
+                if (j < 0) { flags |= 2; continue; }
+                int in = 0;
+                for (int i = tid; i < t; i += NT) in |= (S.ssel[i] == j);
+                if (__syncthreads_or(in)) continue;                // already active: nothing to add (:66, util.jl:119)
+                if (t >= kcap || t >= a.M) break;                  // capacity of UpdatableQR(T, n, k)
+                const T* aj = Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld;
+                const int dep = append_atom<T, NT>(
+                    S, t, j, aj, ld, b_at, r_at, r_set, nr2,
+                    (a.gram && !Acache) ? a.gram + (size_t)(j - a.idx_offset) * a.N : nullptr, a.idx_offset);
+                if (dep) flags |= 1; else changed = true;
+            }
         }
     }
 
     double nr = a.resnorm[sig];
     if (changed) {
-        for (int i = tid; i < t; i += UT) {                        // x_S = R^{-1} Q'b  (`ldiv!`, :175)
+        for (int i = tid; i < t; i += NT) {                        // x_S = R^{-1} Q'b  (`ldiv!`, :175)
             double acc = 0.0;
             for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.zs[l], acc);
             a.x[(size_t)sig * kcap + i] = acc;
@@ -232,32 +280,50 @@ __global__ void nonfinite_check_kernel(const T* __restrict__ p, size_t n, int* f
     if (bad) atomicOr(flag, 1);
 }
 
-size_t update_smem_bytes(int ld, int kcap, bool t_in_smem) {
-    size_t bytes = (size_t)(ld + 5 * kcap) * sizeof(double) + (size_t)((kcap + 1) & ~1) * sizeof(int) +
+size_t update_smem_bytes(int ld, int kcap, bool t_in_smem, int bm) {
+    size_t bytes = (size_t)(5 * kcap) * sizeof(double) + (size_t)((kcap + 1) & ~1) * sizeof(int) +
                    (size_t)kcap * sizeof(void*);
+    if (bm > 0) bytes += ((size_t)bm * ld + 2 * (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX + 4 * BLOCK_MAX) * sizeof(double);
+    else bytes += (size_t)ld * sizeof(double);
     if (t_in_smem) bytes += (size_t)kcap * (kcap | 1) * sizeof(double);
     return bytes;
 }
 
+// atoms orthogonalised together by the block path for this shape (0 = block path not used)
+int block_width(int ld, int kcap, int take) {
+    if (take < 2) return 0;
+    const bool t_in = kcap <= T_SMEM_MAX_K;
+    int bm = take < BLOCK_MAX ? take : BLOCK_MAX;
+    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > 112 * 1024) --bm;   // keep 2 CTAs per SM
+    return bm >= 2 ? bm : 0;
+}
+
+template <typename T>
+cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void* Acache) {
+    const int t_in_smem = a.kcap <= T_SMEM_MAX_K ? 1 : 0;
+    const char* env = getenv("CSB200_GOMP_BLOCK");             // test hook: 0 disables the block append
+    const int bm = (Acache || (env && env[0] == '0')) ? 0 : block_width(a.ld, a.kcap, a.take);
+    const size_t smem = update_smem_bytes(a.ld, a.kcap, t_in_smem != 0, bm);
+    cudaError_t e;
+    if (bm > 0) {
+        e = cudaFuncSetAttribute(omp_update_kernel<T, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        omp_update_kernel<T, 256, true><<<a.nsig, 256, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, bm);
+    } else {
+        e = cudaFuncSetAttribute(omp_update_kernel<T, UT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        omp_update_kernel<T, UT, false><<<a.nsig, UT, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, 0);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace
 
-size_t omp_update_smem_bytes(int ld, int kcap) { return update_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K); }
+size_t omp_update_smem_bytes(int ld, int kcap) { return update_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K, 0); }
 
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
     if (a.nsig <= 0) return cudaSuccess;
-    const int t_in_smem = a.kcap <= T_SMEM_MAX_K ? 1 : 0;
-    const size_t smem = update_smem_bytes(a.ld, a.kcap, t_in_smem != 0);
-    cudaError_t e;
-    if (f32) {
-        e = cudaFuncSetAttribute(omp_update_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        omp_update_kernel<float><<<a.nsig, UT, smem, st>>>(a, static_cast<const float*>(Acache), t_in_smem);
-    } else {
-        e = cudaFuncSetAttribute(omp_update_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        omp_update_kernel<double><<<a.nsig, UT, smem, st>>>(a, static_cast<const double*>(Acache), t_in_smem);
-    }
-    return cudaGetLastError();
+    return f32 ? launch_omp_update_t<float>(a, st, Acache) : launch_omp_update_t<double>(a, st, Acache);
 }
 
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st) {

@@ -170,4 +170,151 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Block append for GOMP (`addindex!(x, AiQR, A, indices)`, src/util.jl:129-134: l atoms per update!).
+// Appending the m new atoms one at a time gathers the t active atoms 2 m times; here they are gathered
+// twice per UPDATE: one sweep forms every inner product the m appends will need,
+//     Gm = [A_S  a_J]' a_J                     ((t + m) x m),
+// the m sequential factor updates then run on small matrices only -- for atom c (factor size tc = t + c):
+//     hh = T' Gm[0:tc, c],  y = T hh,  rho^2 = ||a_c||^2 - ||hh||^2,  T gains [-y / rho; 1 / rho]
+// -- and a second sweep forms all m orthogonalised directions at once,
+//     v_c = a_c - A_S y_c[0:t] - sum_{c' < c} a_{c'} y_c[t + c'].
+// rho^2 comes from Pythagoras instead of the explicit vector, which is only safe while the atom is not nearly
+// dependent: the block stops at the first atom with rho^2 < ||a||^2 / 2 (the DGKS threshold) and the caller
+// appends that atom and the rest one by one with append_atom (explicit norm, re-orthogonalisation).
+// Vb: [BM][ld] shared block (the new atoms on entry, their orthogonalised directions on exit);
+// Gm, Ym: [(kcap + BM)][BM] shared scratch.  Returns the number of atoms appended (<= m).
+constexpr int BLOCK_MAX = 8;
+
+template <typename T, int NT, typename BAt, typename RAt, typename RSet>
+__device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, const int* __restrict__ J,
+                                            const T* const* __restrict__ Jcol, int ld, double* __restrict__ Vb,
+                                            double* __restrict__ Gm, double* __restrict__ Ym, double* __restrict__ sc,
+                                            BAt b_at, RAt r_at, RSet r_set, double& nr2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = t;
+    // sc: [0, BM) ||a_c||^2, [BM, 2BM) rho_c, [2BM, 3BM) v_c'b, [3BM, 4BM) ||v_c||^2
+    double part[BLOCK_MAX];
+#pragma unroll
+    for (int c = 0; c < BLOCK_MAX; ++c) part[c] = 0.0;
+    for (int row = tid; row < ld; row += NT) {
+#pragma unroll
+        for (int c = 0; c < BLOCK_MAX; ++c)
+            if (c < m) { const double e = (double)Jcol[c][row]; Vb[c * ld + row] = e; part[c] += e * e; }
+    }
+#pragma unroll
+    for (int c = 0; c < BLOCK_MAX; ++c)
+        if (c < m) { const double s = block_sum<NT>(part[c], S.red); if (tid == 0) sc[c] = s; }
+    __syncthreads();
+    // sweep 1: Gm[i][c] = <column i, a_c>, columns i < t0 from the dictionary, i >= t0 from the block itself
+    for (int i = warp; i < t0 + m; i += NT / 32) {
+        double acc[BLOCK_MAX];
+#pragma unroll
+        for (int c = 0; c < BLOCK_MAX; ++c) acc[c] = 0.0;
+        if (i < t0) {
+            const T* ai = S.colp[i];
+            for (int row = lane; row < ld; row += 32) {
+                const double a = (double)ai[row];
+#pragma unroll
+                for (int c = 0; c < BLOCK_MAX; ++c) if (c < m) acc[c] = fma(a, Vb[c * ld + row], acc[c]);
+            }
+        } else {
+            const double* ai = Vb + (size_t)(i - t0) * ld;
+            for (int row = lane; row < ld; row += 32) {
+                const double a = ai[row];
+#pragma unroll
+                for (int c = 0; c < BLOCK_MAX; ++c) if (c < m) acc[c] = fma(a, Vb[c * ld + row], acc[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < BLOCK_MAX; ++c)
+            if (c < m) { const double s = warp_sum(acc[c]); if (lane == 0) Gm[i * BLOCK_MAX + c] = s; }
+    }
+    __syncthreads();
+    // the m factor updates, on small matrices only
+    int done = 0;
+    for (int c = 0; c < m; ++c) {
+        const int tc = t0 + c;
+        for (int i = tid; i < tc; i += NT) {
+            double acc = 0.0;
+            for (int l = 0; l <= i; ++l) acc = fma(S.Tm[l + i * S.ldT], Gm[l * BLOCK_MAX + c], acc);
+            S.hh[i] = acc;
+        }
+        __syncthreads();
+        double hn = 0.0;
+        for (int i = tid; i < tc; i += NT) {
+            double acc = 0.0;
+            for (int l = i; l < tc; ++l) acc = fma(S.Tm[i + l * S.ldT], S.hh[l], acc);
+            S.y[i] = acc;
+            hn += S.hh[i] * S.hh[i];
+        }
+        const double hn2 = block_sum<NT>(hn, S.red);
+        const double an2 = sc[c];
+        const double rho2 = an2 - hn2;
+        if (!(rho2 >= 0.5 * an2)) break;                       // nearly dependent: leave it to append_atom
+        const double rho = sqrt(rho2), irho = 1.0 / rho;
+        for (int i = tid; i < tc; i += NT) {
+            const double e = -S.y[i] * irho;
+            if (S.Tg) S.Tg[i + (size_t)tc * S.kcap] = e;
+            if (S.Tsm) S.Tsm[i + tc * S.ldT] = e;
+            Ym[i * BLOCK_MAX + c] = S.y[i];
+        }
+        if (tid == 0) {
+            if (S.Tg) S.Tg[tc + (size_t)tc * S.kcap] = irho;
+            if (S.Tsm) S.Tsm[tc + tc * S.ldT] = irho;
+            sc[BLOCK_MAX + c] = rho;
+            S.ssel[tc] = J[c]; S.colp[tc] = Jcol[c];
+        }
+        ++done;
+        __syncthreads();
+    }
+    if (done == 0) return 0;
+    // sweep 2: all `done` directions at once (in place: a row's originals are held in registers)
+    double pb[BLOCK_MAX], pn[BLOCK_MAX];
+#pragma unroll
+    for (int c = 0; c < BLOCK_MAX; ++c) { pb[c] = 0.0; pn[c] = 0.0; }
+    for (int row = tid; row < ld; row += NT) {
+        double v0[BLOCK_MAX], acc[BLOCK_MAX];
+#pragma unroll
+        for (int c = 0; c < BLOCK_MAX; ++c) { v0[c] = c < done ? Vb[c * ld + row] : 0.0; acc[c] = v0[c]; }
+        for (int i = 0; i < t0; ++i) {
+            const double a = (double)S.colp[i][row];
+#pragma unroll
+            for (int c = 0; c < BLOCK_MAX; ++c) if (c < done) acc[c] = fma(-a, Ym[i * BLOCK_MAX + c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 1; c < BLOCK_MAX; ++c)
+#pragma unroll
+            for (int cp = 0; cp < c; ++cp)
+                if (c < done) acc[c] = fma(-v0[cp], Ym[(t0 + cp) * BLOCK_MAX + c], acc[c]);
+        const double bb = b_at(row);
+#pragma unroll
+        for (int c = 0; c < BLOCK_MAX; ++c)
+            if (c < done) { Vb[c * ld + row] = acc[c]; pb[c] = fma(acc[c], bb, pb[c]); pn[c] = fma(acc[c], acc[c], pn[c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < BLOCK_MAX; ++c)
+        if (c < done) {
+            const double sb = block_sum<NT>(pb[c], S.red);
+            const double sn = block_sum<NT>(pn[c], S.red);
+            if (tid == 0) { sc[2 * BLOCK_MAX + c] = sb; sc[3 * BLOCK_MAX + c] = sn; S.zs[t0 + c] = sb / sc[BLOCK_MAX + c]; }
+        }
+    __syncthreads();
+    // r <- r - sum_c q_c (q_c'b), with the explicit norms ||v_c||^2
+    double s2r = 0.0;
+    for (int row = tid; row < ld; row += NT) {
+        double acc = r_at(row);
+#pragma unroll
+        for (int c = 0; c < BLOCK_MAX; ++c)
+            if (c < done) acc = fma(-sc[2 * BLOCK_MAX + c] / sc[3 * BLOCK_MAX + c], Vb[c * ld + row], acc);
+        const T rr = (T)acc;
+        r_set(row, rr);
+        s2r += (double)rr * (double)rr;
+    }
+    nr2 = block_sum<NT>(s2r, S.red);
+    t = t0 + done;
+    __syncthreads();
+    return done;
+}
+
 }  // namespace csb

@@ -301,6 +301,35 @@ def test_gram_matrix_path_matches_oracle(cs, po, gram, monkeypatch):
         assert idx.tolist() == ref.nzind and _close(val, ref.nzval, RTOL64)
 
 
+@pytest.mark.parametrize("block", ["0", "1"])
+def test_gomp_block_append_and_near_dependent_atoms(cs, po, block, monkeypatch):
+    """gomp appends its l atoms as one block (two gather sweeps per update instead of 2 l); a nearly dependent
+    atom inside a block must fall back to the explicit, re-orthogonalised append.  CSB200_GOMP_BLOCK=0 forces the
+    one-by-one path: both must agree with the oracle."""
+    monkeypatch.setenv("CSB200_GOMP_BLOCK", block)
+    monkeypatch.setenv("CSB200_SMALL_SOLVE", "0")
+    rng = np.random.default_rng(123)
+    M, N, k, l, B = 300, 2500, 20, 5, 60
+    A = po.gaussian_dictionary(rng, M, N)
+    twin = A[:, 100] + 2e-3 * rng.standard_normal(M)              # atom 101 ~ atom 100: cond(A_S) ~ 1e3
+    A[:, 101] = twin / np.linalg.norm(twin)
+    X0, Bm = _planted(po, rng, A, k, B, noise=5e-3)
+    Bm[:, 0] = 3.0 * A[:, 100] + 2.9 * A[:, 101] + 0.5 * A[:, 7]    # both twins in the first top-l
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+        batch.upload(Bm)
+        batch.gomp(l, k, 0.0)
+        sel, coef, nnz, res, its = batch.download(k)
+    for s in range(0, B, 3):
+        t = po.Trace()
+        ref = po.gomp(A, Bm[:, s], l, k, eps=0.0, trace=t)
+        n = int(nnz[s])
+        assert sel[s, :n].tolist() == t.order(), (s, sel[s, :n], t.order())
+        idx, val = _sorted(sel[s], coef[s], n)
+        assert idx.tolist() == ref.nzind
+        assert _close(val, ref.nzval, 1e-6 if s == 0 else RTOL64), (s, val, ref.nzval)
+        assert abs(res[s] - t.resnorm[-1]) < 1e-9
+
+
 def test_gomp_and_mp_midsize_vs_oracle(cs, po):
     rng = np.random.default_rng(77)
     M, N, k, B = 256, 2048, 16, 64
