@@ -63,6 +63,24 @@ __device__ void select_candidates(const double* __restrict__ pv, const int* __re
 }
 
 
+// 16-byte loads of W consecutive rows of a dictionary column, widened to double: the gather sweeps below are
+// latency-bound (a few CTAs per SM, one dependent chain per thread), so bytes in flight per load matter.
+template <typename T> struct RowVec;
+template <> struct RowVec<double> {
+    static constexpr int W = 2;
+    static __device__ __forceinline__ void load(const double* p, double (&o)[2]) {
+        const double2 x = *reinterpret_cast<const double2*>(p);
+        o[0] = x.x; o[1] = x.y;
+    }
+};
+template <> struct RowVec<float> {
+    static constexpr int W = 4;
+    static __device__ __forceinline__ void load(const float* p, double (&o)[4]) {
+        const float4 x = *reinterpret_cast<const float4*>(p);
+        o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+    }
+};
+
 // Shared-memory working set of one signal's pursuit state (pointers into the CTA's shared memory).
 template <typename T>
 struct PursuitSmem {
@@ -94,6 +112,7 @@ template <typename T, int NT, typename BAt, typename RAt, typename RSet>
 __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
                                            BAt b_at, RAt r_at, RSet r_set, double& nr2,
                                            const double* __restrict__ gcol = nullptr, int idx_offset = 0) {
+    constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double s2 = 0.0;
     for (int row = tid; row < ld; row += NT) { const double e = (double)aj[row]; S.v[row] = e; s2 += e * e; }
@@ -106,7 +125,13 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
             for (int i = warp; i < t; i += NT / 32) {              // g = A_S' v
                 const T* ai = S.colp[i];
                 double s = 0.0;
-                for (int row = lane; row < ld; row += 32) s += (double)ai[row] * S.v[row];
+#pragma unroll 4
+                for (int row = lane * W; row < ld; row += 32 * W) {
+                    double a[W];
+                    RowVec<T>::load(ai + row, a);
+#pragma unroll
+                    for (int e = 0; e < W; ++e) s = fma(a[e], S.v[row + e], s);
+                }
                 s = warp_sum(s);
                 if (lane == 0) S.g[i] = s;
             }
@@ -128,11 +153,20 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
         }
         __syncthreads();
         s2 = 0.0;
-        for (int row = tid; row < ld; row += NT) {                 // v -= A_S y
-            double acc = S.v[row];
-            for (int i = 0; i < t; ++i) acc -= (double)S.colp[i][row] * S.y[i];
-            S.v[row] = acc;
-            s2 += acc * acc;
+        for (int row = tid * W; row < ld; row += NT * W) {         // v -= A_S y, W rows per thread per 16 B load
+            double acc[W];
+#pragma unroll
+            for (int e = 0; e < W; ++e) acc[e] = S.v[row + e];
+#pragma unroll 4
+            for (int i = 0; i < t; ++i) {
+                double a[W];
+                RowVec<T>::load(S.colp[i] + row, a);
+                const double yi = S.y[i];
+#pragma unroll
+                for (int e = 0; e < W; ++e) acc[e] = fma(-a[e], yi, acc[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < W; ++e) { S.v[row + e] = acc[e]; s2 = fma(acc[e], acc[e], s2); }
         }
         rho2 = block_sum<NT>(s2, S.red);
         if (rho2 >= 0.5 * before2) break;                          // DGKS: one sweep was enough
@@ -191,6 +225,7 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
                                             const T* const* __restrict__ Jcol, int ld, double* __restrict__ Vb,
                                             double* __restrict__ Gm, double* __restrict__ Ym, double* __restrict__ sc,
                                             BAt b_at, RAt r_at, RSet r_set, double& nr2) {
+    constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = t;
     // sc: [0, BM) ||a_c||^2, [BM, 2BM) rho_c, [2BM, 3BM) v_c'b, [3BM, 4BM) ||v_c||^2
@@ -213,10 +248,16 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
         for (int c = 0; c < BLOCK_MAX; ++c) acc[c] = 0.0;
         if (i < t0) {
             const T* ai = S.colp[i];
-            for (int row = lane; row < ld; row += 32) {
-                const double a = (double)ai[row];
+#pragma unroll 2
+            for (int row = lane * W; row < ld; row += 32 * W) {
+                double a[W];
+                RowVec<T>::load(ai + row, a);
 #pragma unroll
-                for (int c = 0; c < BLOCK_MAX; ++c) if (c < m) acc[c] = fma(a, Vb[c * ld + row], acc[c]);
+                for (int c = 0; c < BLOCK_MAX; ++c)
+                    if (c < m) {
+#pragma unroll
+                        for (int e = 0; e < W; ++e) acc[c] = fma(a[e], Vb[c * ld + row + e], acc[c]);
+                    }
             }
         } else {
             const double* ai = Vb + (size_t)(i - t0) * ld;
@@ -277,6 +318,7 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
         double v0[BLOCK_MAX], acc[BLOCK_MAX];
 #pragma unroll
         for (int c = 0; c < BLOCK_MAX; ++c) { v0[c] = c < done ? Vb[c * ld + row] : 0.0; acc[c] = v0[c]; }
+#pragma unroll 8
         for (int i = 0; i < t0; ++i) {
             const double a = (double)S.colp[i][row];
 #pragma unroll
