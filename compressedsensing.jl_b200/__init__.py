@@ -32,7 +32,7 @@ import numpy as np
 __all__ = [
     "SparseVector", "Dictionary", "Batch", "omp", "gomp", "mp", "lib", "LIB_PATH", "CSB200Error",
     "device_count", "F64", "F32", "ShardComm", "omp_sharded", "shard_range", "owner_of", "pick_global",
-    "exchange_unique_id", "assemble_csc",
+    "exchange_unique_id", "assemble_csc", "fr", "ols", "oomp", "ormp",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -78,6 +78,9 @@ def _load() -> ctypes.CDLL:
         "csb200_batch_omp": (c_int, [c_void_p, c_int64, c_double]),
         "csb200_batch_gomp": (c_int, [c_void_p, c_int64, c_int64, c_double]),
         "csb200_batch_mp": (c_int, [c_void_p, c_int64, i64p, f64p, i64p, c_int64]),
+        "csb200_batch_fr": (c_int, [c_void_p, c_int64, c_double, c_double]),
+        "csb200_fr": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_double, c_double, i64p, f64p, i64p, f64p,
+                              i64p]),
         "csb200_batch_download": (c_int, [c_void_p, c_int64, i64p, f64p, i64p, f64p, i64p]),
         "csb200_batch_profile": (c_int, [c_void_p, c_int]),
         "csb200_batch_corr_time": (c_int, [c_void_p, f64p, i64p, i64p]),
@@ -109,7 +112,7 @@ EXPORTED_SYMBOLS = [
     "csb200_batch_destroy", "csb200_batch_upload", "csb200_batch_upload_device", "csb200_batch_omp",
     "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
     "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp",
-    "csb200_assemble_csc", "csb200_comm_unique_id",
+    "csb200_assemble_csc", "csb200_comm_unique_id", "csb200_batch_fr", "csb200_fr",
     "csb200_comm_create", "csb200_comm_destroy", "csb200_omp_sharded", "csb200_debug_corr_topk",
     "csb200_debug_get_residual",
 ]
@@ -240,6 +243,9 @@ class Batch:
 
     def gomp(self, l: int, k: int, eps: float) -> None:
         _check(lib.csb200_batch_gomp(self._h, int(l), int(k), float(eps)), eps)
+
+    def fr(self, k: int, max_eps: float = 0.0, min_delta: float = 0.0) -> None:
+        _check(lib.csb200_batch_fr(self._h, int(k), float(max_eps), float(min_delta)))
 
     def mp(self, iters: int, x0: Optional[Sequence[SparseVector]] = None) -> None:
         if x0 is None:
@@ -432,6 +438,35 @@ def gomp(A, b, l: int, *args, max_residual=None, sparsity=None, device: int = 0,
                                _f64p(res), _i64p(its))
 
     return _solve(A, b, device, call, stride, eps, result=result)
+
+
+def fr(A, b, *args, max_residual: float = 0.0, min_decrease: float = 0.0, sparsity=None, device: int = 0,
+       result: str = "vectors"):
+    """Forward regression a.k.a. OLS / OOMP / ORMP -- `fr` (`src/forward.jl:33-54`).
+
+    fr(A, b, max_eps, min_delta[, k = M])  |  fr(A, b, max_residual=0, min_decrease=0, sparsity=N)
+    """
+    M, N = (A.M, A.n_total) if isinstance(A, Dictionary) else np.shape(A)
+    if len(args) >= 2:
+        max_eps, min_delta = float(args[0]), float(args[1])              # :44
+        k = int(args[2]) if len(args) > 2 else M
+    elif len(args) == 0:
+        max_eps, min_delta = float(max_residual), float(min_decrease)    # :33-36
+        k = N if sparsity is None else int(sparsity)
+    else:
+        raise TypeError("fr(A, b, max_eps, min_delta[, k]) or fr(A, b, max_residual=, min_decrease=, sparsity=)")
+    if k < 0:
+        raise ValueError("k must be non-negative")
+    stride = max(min(k, M, N), 1)
+
+    def call(D, B, ldb, nsig, sel, coef, nnz, res, its):
+        return lib.csb200_fr(D._h, B.ctypes.data, ldb, nsig, min(k, M, N), max_eps, min_delta, _i64p(sel), _f64p(coef),
+                             _i64p(nnz), _f64p(res), _i64p(its))
+
+    return _solve(A, b, device, call, stride, result=result)
+
+
+ols = oomp = ormp = fr            # `const ols = fr` etc. (src/forward.jl:52-54)
 
 
 def mp(A, b, k: int, x=None, device: int = 0):

@@ -57,12 +57,12 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D FP64 tensor map over a column-major (ld x ncols) matrix: box = 16 rows (128 B) x 128 columns,
 // SWIZZLE_128B -- the operand tiles of corr_gemm_f64.cu.
-int make_operand_map(CUtensorMap* map, void* base, int64_t ld, int64_t ncols) {
+int make_operand_map(CUtensorMap* map, void* base, int64_t ld, int64_t ncols, int box_cols = 128) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { g_last_error = "cuTensorMapEncodeTiled entry point not found"; return CSB200_ERR_CUDA; }
     cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)(ncols > 0 ? ncols : 1)};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
-    cuuint32_t box[2] = {16, 128};
+    cuuint32_t box[2] = {16, (cuuint32_t)box_cols};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -119,6 +119,10 @@ struct csb200_batch {
     size_t host_stage_bytes = 0;
     bool lazy_input_check = false;         // upload skipped the NaN scan: the small solve kernel reports it
     int* dflag = nullptr;       // non-finite scan result
+    // forward regression (csb200_batch_fr): allocated on first use
+    double* resc = nullptr;     // [cap_sig][N] OLS rescaling
+    double* qnew = nullptr;     // [cap_sig][ld] newest orthonormal direction per signal
+    double* cn2 = nullptr;      // [N] squared column norms
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -136,7 +140,7 @@ int begin_solve_fwd(csb200_batch* b);
 
 void free_batch_mem(csb200_batch* b) {
     cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->state_blk);
-    cudaFree(b->Rf); cudaFree(b->dflag);
+    cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2);
     if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
@@ -625,6 +629,70 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     return finish(b, true);
 }
 
+// Forward regression / OLS / OOMP / ORMP: `fr(A, b, max_eps, min_delta, k)` (src/forward.jl:44-51).  Per step one
+// DMMA pass computes <a_j, r> and <a_j, q_new> for every (atom, signal), down-dates the rescaling and reduces
+// delta2 = <a_j, r>^2 / rescaling_j to per-block candidates; the update kernel then runs `forward_step!`'s tail.
+int csb200_batch_fr(csb200_batch* b, int64_t k, double max_eps, double min_delta) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (k < 0 || !(max_eps == max_eps) || !(min_delta == min_delta)) return CSB200_ERR_INVALID_ARG;
+    csb200_dict* d = b->dict;
+    if (d->dtype != CSB200_F64 || !d->has_map || d->n_total != d->N) {
+        g_last_error = "forward regression needs an unsharded FP64 dictionary (DMMA path)";
+        return CSB200_ERR_UNSUPPORTED;
+    }
+    int64_t need = k < d->M ? k : d->M;
+    if (d->N < need) need = d->N;
+    if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(d))) return rc;
+    if (omp_update_smem_bytes((int)d->ld, (int)b->kcap) > MAX_DYN_SMEM) {
+        g_last_error = "signal length / max_sparsity exceed the update kernel's shared memory";
+        return CSB200_ERR_UNSUPPORTED;
+    }
+    if ((rc = settle_input(b))) return rc;
+    if ((rc = ensure_factor(b))) return rc;
+    if (!b->resc) {
+        CU_TRY(cudaMalloc(&b->resc, (size_t)b->cap_sig * d->N * sizeof(double)));
+        CU_TRY(cudaMalloc(&b->qnew, (size_t)b->cap_sig * d->ld * sizeof(double)));
+        CU_TRY(cudaMalloc(&b->cn2, (size_t)d->N * sizeof(double)));
+    }
+    CUtensorMap mapR64, mapQ64;
+    if ((rc = make_operand_map(&mapR64, b->dR, d->ld, b->nsig, 64))) return rc;
+    if ((rc = make_operand_map(&mapQ64, b->qnew, d->ld, b->nsig, 64))) return rc;
+    b->use_gram = false;
+    const int64_t P = (d->N + PBLK - 1) / PBLK;
+    if ((rc = ensure_partials(b, P, 1))) return rc;
+    b->cur_P = (int)P;
+    StateArgs sa = state_args(b, 1, 1, 0.0, 0);
+    sa.resc = b->resc; sa.qnew = b->qnew; sa.max_eps = max_eps; sa.min_delta2 = min_delta * min_delta;
+    CorrArgs c;
+    c.A = d->dA; c.R = b->dR; c.M = (int)d->M; c.ld = (int)d->ld; c.N = (int)d->N; c.nsig = (int)b->nsig;
+    c.S = 1; c.P = (int)P; c.idx_offset = 0; c.pval = b->pval; c.pidx = b->pidx;
+    if ((rc = begin_solve(b))) return rc;
+    cudaError_t e = launch_reset_state(sa, false, b->stream);
+    if (e == cudaSuccess) e = launch_ols_init(sa, b->cn2, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "fr init");
+    for (int64_t it = 0; it < k; ++it) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (b->profile) {
+            if (b->ev_used + 2 > b->ev.size()) {
+                for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); b->ev.push_back(ev); }
+            }
+            e0 = b->ev[b->ev_used]; e1 = b->ev[b->ev_used + 1]; b->ev_used += 2;
+            CU_TRY(cudaEventRecord(e0, b->stream));
+        }
+        e = launch_corr_gemm_f64_ols(&d->mapA, it == 0 ? &b->mapR : &mapR64, it == 0 ? nullptr : &mapQ64, c, b->resc,
+                                     d->num_sms, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "fr correlation pass");
+        if (b->profile) CU_TRY(cudaEventRecord(e1, b->stream));
+        e = launch_omp_update(sa, false, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "fr update");
+        b->other_launches++;
+    }
+    return finish(b, true);
+}
+
 int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const double* x0_val,
                     const int64_t* x0_nnz, int64_t x0_stride) {
     int rc = check_ready(b);
@@ -776,7 +844,8 @@ int csb200_batch_last_solve_ms(csb200_batch* b, double* ms) {
 // The temporary batch of a one-shot call is kept on the dictionary handle and reused while it is large
 // enough (device allocation and release of ~2 GB per call would otherwise dominate small-k solves);
 // csb200_dict_trim() releases it.  The dictionary mutex serialises one-shot calls on one handle.
-static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t kcap, csb200_batch** out) {
+static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t kcap, csb200_batch** out,
+                    bool allow_lazy = true) {
     if (!d || !Bmat || nsig <= 0) return CSB200_ERR_INVALID_ARG;
     int64_t cap = kcap < 1 ? 1 : kcap;
     csb200_batch* w = d->workspace;
@@ -790,7 +859,7 @@ static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig,
         d->workspace = w;
     }
     *out = w;
-    return upload_common(w, Bmat, ldb, nsig, cudaMemcpyHostToDevice, /*allow_lazy=*/true);
+    return upload_common(w, Bmat, ldb, nsig, cudaMemcpyHostToDevice, allow_lazy);
 }
 
 static int64_t support_cap(const csb200_dict* d, int64_t k) {
@@ -820,6 +889,19 @@ int csb200_gomp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int
     int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
     rc = csb200_batch_gomp(b, l, k, eps);
+    if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
+    return rc;
+}
+
+int csb200_fr(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double max_eps, double min_delta,
+              int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
+    if (!d || k < 0) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(d->mu);
+    csb200_batch* b = nullptr;
+    int64_t cap = support_cap(d, k);
+    int rc = one_shot(d, Bmat, ldb, nsig, cap, &b, /*allow_lazy=*/false);
+    if (rc) return rc;
+    rc = csb200_batch_fr(b, k, max_eps, min_delta);
     if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
     return rc;
 }

@@ -98,11 +98,20 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 //   <8,4,2,4>  8 warps, warp tile 64 x 32, 64 accumulators/thread, ~228 registers (fills the register file)
 //   <4,4,4,4> 16 warps, warp tile 32 x 32, 32 accumulators/thread, <=128 registers: twice the warps per
 //             scheduler to cover LDS / mbarrier latency at the price of 8 instead of 6 LDS.128 per 32 DMMA
-template <int MI, int NJ, int WM, int WN, int SUB, bool STORE = false>
+// Epilogues: EPI_TOPS = |c| top-S per (64-atom block, signal); EPI_STORE = plain C store (A'A);
+// EPI_OLS = forward-regression criterion c^2 / rescaling with the rescaling down-date fused in (see below).
+enum { EPI_TOPS = 0, EPI_STORE = 1, EPI_OLS = 2 };
+// DUAL (EPI_OLS only): the 128 "signal" columns of a CTA tile are 64 residuals r_s (from mapR) followed by the newest
+// orthonormal directions q_s of the SAME 64 signals (from mapQ), arranged so that a thread's accumulators
+// acc[i][j] (j < NJ/2) = <a, r_s> and acc[i][j + NJ/2] = <a, q_s> belong to the same (atom, signal) pairs.
+template <int MI, int NJ, int WM, int WN, int SUB, int EPI = EPI_TOPS, bool DUAL = false>
 __global__ void __launch_bounds__(WM * WN * 32, 1)
 corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
                      int N, int nsig, int kchunks, int tilesN, int tilesB, int band, int S, int P, int idx_offset,
-                     double* __restrict__ pval, int* __restrict__ pidx, long long ldc = 0) {
+                     double* __restrict__ pval, int* __restrict__ pidx, long long ldc,
+                     const __grid_constant__ CUtensorMap mapQ, double* __restrict__ resc) {
+    constexpr bool STORE = EPI == EPI_STORE;
+    constexpr int SIG_PER_TILE = DUAL ? TILE_B / 2 : TILE_B;        // distinct signals per CTA tile
     constexpr int STAGES = Pipe<SUB>::STAGES;
     constexpr int STAGE_BYTES = Pipe<SUB>::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -143,7 +152,12 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
         for (int u = 0; u < SUB; ++u) {          // k-slices past the end of the matrix are zero-filled by TMA
             tma_load_2d(dst + u * BOX_PAIR_BYTES, &mapA, bar_full + stg * 8, (kc * SUB + u) * KCH, tn * TILE_N);
-            tma_load_2d(dst + u * BOX_PAIR_BYTES + A_TILE_BYTES, &mapR, bar_full + stg * 8, (kc * SUB + u) * KCH, tb * TILE_B);
+            if constexpr (DUAL) {       // two {16 x 64} boxes: residuals into rows 0-63, directions into rows 64-127
+                tma_load_2d(dst + u * BOX_PAIR_BYTES + A_TILE_BYTES, &mapR, bar_full + stg * 8, (kc * SUB + u) * KCH, tb * SIG_PER_TILE);
+                tma_load_2d(dst + u * BOX_PAIR_BYTES + A_TILE_BYTES + R_TILE_BYTES / 2, &mapQ, bar_full + stg * 8, (kc * SUB + u) * KCH, tb * SIG_PER_TILE);
+            } else {
+                tma_load_2d(dst + u * BOX_PAIR_BYTES + A_TILE_BYTES, &mapR, bar_full + stg * 8, (kc * SUB + u) * KCH, tb * TILE_B);
+            }
         }
     };
     if (threadIdx.x == 0) {
@@ -156,7 +170,12 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const int wn = warp / WM;         // which (8*NJ)-signal slice
     const int g = lane >> 2, q = lane & 3;
     const uint32_t a_row = (uint32_t)(wm * 8 * MI + g) * 128u;                   // + i*1024
-    const uint32_t r_row = (uint32_t)A_TILE_BYTES + (uint32_t)(wn * 8 * NJ + g) * 128u;   // + j*1024
+    // signal-side fragment rows: j-th 8-column group of this warp (DUAL: groups j >= NJ/2 are the q half of the tile)
+    auto r_off = [&](int j) -> uint32_t {
+        const int row = DUAL ? (j / (NJ / 2)) * (TILE_B / 2) + wn * 8 * (NJ / 2) + (j % (NJ / 2)) * 8 + g
+                             : wn * 8 * NJ + j * 8 + g;
+        return (uint32_t)A_TILE_BYTES + (uint32_t)row * 128u;
+    };
     int stage = 0;
     uint32_t phase = 0;
     int chunk = 0;                     // flat chunk index being consumed
@@ -186,7 +205,7 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
                 for (int i = 0; i < MI; ++i) af[i] = *reinterpret_cast<const double2*>(st + a_row + i * 1024 + sw);
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) bf[j] = *reinterpret_cast<const double2*>(st + r_row + j * 1024 + sw);
+                for (int j = 0; j < NJ; ++j) bf[j] = *reinterpret_cast<const double2*>(st + r_off(j) + sw);
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -213,6 +232,55 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                         double* dst = pval + (size_t)atom * ldc + sig;
                         if (sig + 1 < nsig && (ldc & 1) == 0) *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
                         else { if (sig < nsig) dst[0] = acc[i][j][0]; if (sig + 1 < nsig) dst[1] = acc[i][j][1]; }
+                    }
+                }
+            }
+            continue;
+        }
+        if constexpr (EPI == EPI_OLS) {
+            // ---- forward-regression criterion (src/forward.jl:69-76, 97-114): delta2_j = <a_j, r>^2 / resc_j with
+            // resc_j = ||a_j||^2 - ||Q1'a_j||^2 kept per (signal, atom) in HBM and down-dated here by <a_j, q_new>^2.
+            // Active atoms hold resc = +Inf, so their delta2 is exactly 0, which is what `P.δ²[x.nzind] = 0` sets.
+            // One (delta2, atom) record per (64-atom block, signal); NaN / negative quotients never win
+            // (the package's findmax override skips NaN, src/util.jl:173-189; a non-negative entry always exists).
+            const int atom0 = tn * TILE_N + wm * 8 * MI + g;
+            const int p = tn * WM + wm;
+            constexpr int NS = DUAL ? NJ / 2 : NJ;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int sig = tb * SIG_PER_TILE + wn * 8 * NS + j * 8 + 2 * q + e;
+                    double bv = -1.0;
+                    int bi = INT_MAX;
+                    if (sig < nsig) {
+                        double* rs = resc + (size_t)sig * ldc;
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) {
+                            const int idx = atom0 + i * 8;
+                            if (idx < N) {
+                                double rv = rs[idx];
+                                if constexpr (DUAL) {
+                                    const double d = acc[i][j + NJ / 2][e];
+                                    rv = fma(-d, d, rv);
+                                    rs[idx] = rv;
+                                }
+                                const double c = acc[i][j][e];
+                                const double v = c * c / rv;
+                                if (v >= 0.0 && v > bv) { bv = v; bi = idx; }   // idx ascends with i: first max wins
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int off = 4; off < 32; off <<= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                    }
+                    if (g == 0 && sig < nsig && p < P) {
+                        const size_t o = (size_t)sig * P + p;
+                        pval[o] = bv;
+                        pidx[o] = (bi == INT_MAX) ? -1 : bi + idx_offset;
                     }
                 }
             }
@@ -276,7 +344,11 @@ cudaError_t corr_gemm_f64_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
+    e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 1, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(corr_gemm_f64_kernel<4, 4, 4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
 }
@@ -298,13 +370,13 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     if (variant < 0) variant = (kslices % 2 == 0 || kslices >= 16) ? 2 : 0;
     if (variant == 1)
         corr_gemm_f64_kernel<4, 4, 4, 4, 1><<<grid, 512, Pipe<1>::SMEM_BYTES, st>>>(
-            *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+            *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx, 0, *mapR, nullptr);
     else if (variant == 2)
         corr_gemm_f64_kernel<8, 4, 2, 4, 2><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
-            *mapA, *mapR, a.N, a.nsig, (kslices + 1) / 2, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+            *mapA, *mapR, a.N, a.nsig, (kslices + 1) / 2, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx, 0, *mapR, nullptr);
     else
         corr_gemm_f64_kernel<8, 4, 2, 4, 1><<<grid, 256, Pipe<1>::SMEM_BYTES, st>>>(
-            *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx);
+            *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx, 0, *mapR, nullptr);
     return cudaGetLastError();
 }
 
@@ -315,8 +387,29 @@ cudaError_t launch_gemm_f64_store(const CUtensorMap* mapA, const CUtensorMap* ma
     const long long ntiles = (long long)tilesN * tilesB;
     if (ntiles <= 0) return cudaSuccess;
     const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
-    corr_gemm_f64_kernel<8, 4, 2, 4, 1, true><<<grid, 256, Pipe<1>::SMEM_BYTES, st>>>(
-        *mapA, *mapR, N, nsig, ld / KCH, tilesN, tilesB, tilesN, 1, 1, 0, C, nullptr, ldc);
+    corr_gemm_f64_kernel<8, 4, 2, 4, 1, EPI_STORE><<<grid, 256, Pipe<1>::SMEM_BYTES, st>>>(
+        *mapA, *mapR, N, nsig, ld / KCH, tilesN, tilesB, tilesN, 1, 1, 0, C, nullptr, ldc, *mapR, nullptr);
+    return cudaGetLastError();
+}
+
+// Forward-regression pass: one (delta2, atom) candidate per (64-atom block, signal).  mapQ == nullptr: first
+// step (no direction yet; mapR has 128-column boxes).  Otherwise mapR / mapQ have 64-column boxes and resc is
+// down-dated by <a_j, q_s>^2 in the same launch.  resc: [nsig][N].
+cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap* mapR, const CUtensorMap* mapQ,
+                                     const CorrArgs& a, double* resc, int num_sms, cudaStream_t st) {
+    const int sig_per_tile = mapQ ? TILE_B / 2 : TILE_B;
+    const int tilesN = (a.N + TILE_N - 1) / TILE_N;
+    const int tilesB = (a.nsig + sig_per_tile - 1) / sig_per_tile;
+    const long long ntiles = (long long)tilesN * tilesB;
+    if (ntiles <= 0) return cudaSuccess;
+    const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    const int kchunks = (a.ld / KCH + 1) / 2;
+    if (mapQ)
+        corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, true><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
+            *mapA, *mapR, a.N, a.nsig, kchunks, tilesN, tilesB, tilesN, 1, a.P, a.idx_offset, a.pval, a.pidx, a.N, *mapQ, resc);
+    else
+        corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, false><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
+            *mapA, *mapR, a.N, a.nsig, kchunks, tilesN, tilesB, tilesN, 1, a.P, a.idx_offset, a.pval, a.pidx, a.N, *mapR, resc);
     return cudaGetLastError();
 }
 

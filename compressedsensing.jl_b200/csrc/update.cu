@@ -81,6 +81,13 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     const int sig = blockIdx.x;
     const int tid = threadIdx.x;
     if (a.done[sig] && !a.ignore_done) return;                     // the reference `break`s (:79,:132)
+    // forward regression (`forward_step!`, src/forward.jl:56-67): same append / solve tail as omp, different
+    // acquisition (candidates carry delta2 = <a,r>^2 / rescaling) and stopping rules
+    const bool ols = a.resc != nullptr;
+    if (ols && !(a.nnz[sig] < a.M && a.resnorm[sig] > a.max_eps)) {          // forward.jl:57,60 -> return false
+        if (tid == 0) { a.done[sig] = 1; a.iters[sig] += 1; }
+        return;
+    }
 
     const T* A = static_cast<const T*>(a.A);
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
@@ -147,6 +154,10 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
             } else {
                 const int j = s_cand[round++];
                 if (j < 0) { flags |= 2; continue; }
+                if (ols && !(a.min_delta2 < s_cval[0])) {          // forward.jl:63,68: no admissible atom -> false
+                    if (tid == 0) { a.done[sig] = 1; a.iters[sig] += 1; }
+                    return;
+                }
                 int in = 0;
                 for (int i = tid; i < t; i += NT) in |= (S.ssel[i] == j);
                 if (__syncthreads_or(in)) continue;                // already active: nothing to add (:66, util.jl:119)
@@ -156,8 +167,20 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
                     S, t, j, aj, ld, b_at, r_at, r_set, nr2,
                     (a.gram && !Acache) ? a.gram + (size_t)(j - a.idx_offset) * a.N : nullptr, a.idx_offset);
                 if (dep) flags |= 1; else changed = true;
+                if (ols) {
+                    // the atom leaves the passive set (`P.δ²[x.nzind] = 0`, :74): c^2 / Inf == 0 from now on;
+                    // q_t = v / rho feeds the rescaling down-date fused into the next correlation pass
+                    const double irho = dep ? 0.0 : S.Tm[(t - 1) + (t - 1) * S.ldT];
+                    double* qn = a.qnew + (size_t)sig * ld;
+                    for (int row = tid; row < ld; row += NT) qn[row] = S.v[row] * irho;
+                    if (tid == 0) a.resc[(size_t)sig * a.N + (j - a.idx_offset)] = __longlong_as_double(0x7ff0000000000000LL);
+                }
             }
         }
+    }
+    if (ols && !changed) {
+        double* qn = a.qnew + (size_t)sig * ld;
+        for (int row = tid; row < ld; row += NT) qn[row] = 0.0;
     }
 
     double nr = a.resnorm[sig];
@@ -272,6 +295,23 @@ __global__ void __launch_bounds__(UT) topk_from_partials_kernel(StateArgs a, int
     }
 }
 
+// ||a_j||^2 for every atom, one warp per column (`colnorms(A)` / `sum!(abs2, ...)`, src/forward.jl:28,105).
+__global__ void __launch_bounds__(256) colnorm2_kernel(const double* __restrict__ A, int ld, int N, double* __restrict__ out) {
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= N) return;
+    const double* a = A + (size_t)j * ld;
+    double s = 0.0;
+    for (int row = lane; row < ld; row += 32) s = fma(a[row], a[row], s);
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
+}
+__global__ void __launch_bounds__(256) ols_init_kernel(const double* __restrict__ cn2, int N, int ld, double* __restrict__ resc,
+                                                       double* __restrict__ qnew) {
+    const int sig = blockIdx.x;
+    for (int j = threadIdx.x; j < N; j += 256) resc[(size_t)sig * N + j] = cn2[j];
+    for (int row = threadIdx.x; row < ld; row += 256) qnew[(size_t)sig * ld + row] = 0.0;
+}
+
 template <typename T>
 __global__ void nonfinite_check_kernel(const T* __restrict__ p, size_t n, int* flag) {
     bool bad = false;
@@ -324,6 +364,13 @@ size_t omp_update_smem_bytes(int ld, int kcap) { return update_smem_bytes(ld, kc
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
     if (a.nsig <= 0) return cudaSuccess;
     return f32 ? launch_omp_update_t<float>(a, st, Acache) : launch_omp_update_t<double>(a, st, Acache);
+}
+
+cudaError_t launch_ols_init(const StateArgs& a, double* colnorm2, cudaStream_t st) {
+    if (a.nsig <= 0) return cudaSuccess;
+    colnorm2_kernel<<<(a.N + 7) / 8, 256, 0, st>>>(static_cast<const double*>(a.A), a.ld, a.N, colnorm2);
+    ols_init_kernel<<<a.nsig, 256, 0, st>>>(colnorm2, a.N, a.ld, a.resc, a.qnew);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st) {

@@ -135,6 +135,28 @@ gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, k::Int) = gomp(A, b, l, eps(elty
 gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int; max_residual = eps(eltype(A)), sparsity = size(A, 2)) =
     gomp(A, b, l, max_residual, sparsity)
 
+# fr == ols == oomp == ormp  (src/forward.jl:33-54): forward regression; FP64 dictionaries
+function fr(A::MatOrDict, b::AbstractVecOrMat, max_ε::Real, min_δ::Real, k::Int = size(A, 1); csc::Bool = false)
+    D = as_dictionary(A)
+    B = signals(D, b)
+    nsig = size(B, 2)
+    k = min(k, size(D)...)
+    stride = max(k, 1)
+    sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
+    nnz = Vector{Int64}(undef, nsig); res = Vector{Float64}(undef, nsig); its = Vector{Int64}(undef, nsig)
+    GC.@preserve B sel coef nnz res its check(ccall((:csb200_fr, libcsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cdouble, Cdouble, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}),
+        D.handle, pointer(B), D.M, nsig, k, Float64(max_ε), Float64(min_δ), sel, coef, nnz, res, its))
+    csc && return assemble_csc(D.N, sel, coef, nnz)
+    xs = [to_sparse(D.N, view(sel, :, s), view(coef, :, s), nnz[s]) for s in 1:nsig]
+    return b isa AbstractVector ? xs[1] : xs
+end
+fr(A::MatOrDict, b::AbstractVecOrMat; max_residual::Real = 0., min_decrease::Real = 0., sparsity::Int = size(A, 2)) =
+    fr(A, b, max_residual, min_decrease, sparsity)
+const ols = fr
+const oomp = fr
+const ormp = fr
+
 # mp  (src/matchingpursuit.jl:34-40); x is an optional warm start (single-signal form)
 function mp(A::MatOrDict, b::AbstractVector, k::Int, x::SparseVector = spzeros(size(A, 2)))
     D = as_dictionary(A)

@@ -98,6 +98,13 @@ int csb200_batch_gomp(csb200_batch* batch, int64_t l, int64_t k, double eps);
 int csb200_batch_mp(csb200_batch* batch, int64_t iters, const int64_t* x0_idx, const double* x0_val,
                     const int64_t* x0_nnz, int64_t x0_stride);
 
+/* Forward regression == OLS == OOMP == ORMP: `fr(A, b, max_eps, min_delta, k)`,
+ * src/forward.jl:44-51, each step being `forward_step!` (:56-67): stop unless nnz < M and ||r|| > max_eps; pick
+ * argmax_j <a_j, r>^2 / (||a_j||^2 - ||Q1'a_j||^2) over the passive atoms (first index on ties, :62 with the
+ * findmax override of src/util.jl:173-189); append it if min_delta^2 < that maximum, else stop.  FP64, unsharded
+ * dictionaries only (CSB200_ERR_UNSUPPORTED otherwise).  Outputs as for omp (selection order). */
+int csb200_batch_fr(csb200_batch* batch, int64_t k, double max_eps, double min_delta);
+
 /* Copy results device -> host.  `stride` = slots per signal in sel_idx / coef (>= the k or
  * iters of the last solve).  Any output pointer may be NULL.
  *   sel_idx[s*stride + j]  j-th atom appended for signal s, in SELECTION order (-1 padded).
@@ -128,6 +135,8 @@ int csb200_omp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, i
                int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
 int csb200_gomp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t l, int64_t k,
                 double eps, int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+int csb200_fr(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double max_eps,
+              double min_delta, int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
 int csb200_mp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k,
               const int64_t* x0_idx, const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride,
               int64_t* sel_idx, double* coef, double* resnorm);

@@ -42,7 +42,8 @@ from .updatable_qr import UpdatableQR
 
 __all__ = [
     "SparseVec", "Trace", "mp", "omp", "gomp", "residual", "argmaxinner", "argmaxinner_k",
-    "sparse_vector", "sparse_data", "perturb", "eps_of",
+    "sparse_vector", "sparse_data", "perturb", "eps_of", "fr", "ols", "oomp", "ormp", "forward_delta", "ols_rescaling",
+    "findmax_first",
 ]
 
 
@@ -322,6 +323,82 @@ def gomp(A: np.ndarray, b: np.ndarray, l: int, k: Optional[int] = None, eps: Opt
         if trace is not None:
             trace.resnorm.append(float(np.linalg.norm(residual(A, x, b)))); trace.iterations += 1
     return x
+
+
+# ----------------------------------------------------------------------------------------
+# Forward regression / OLS / OOMP / ORMP  (`src/forward.jl:1-114`)  -- SURVEY.md 8(f) rank 1
+# ----------------------------------------------------------------------------------------
+def findmax_first(v: np.ndarray):
+    """The package's own `Base.findmax(f, x::AbstractVector)` override (`src/util.jl:173-189`): a strict-`<` scan of
+    `-f(x)` starting from `(k, m) = (0, Inf)`: first index among equal maxima, NaN entries never win.
+    Returns (max, index); index -1 if nothing compared below Inf (all NaN / -Inf... the reference would index x[0])."""
+    k, m = -1, np.inf
+    for i, vi in enumerate(v):
+        g = -vi
+        if g < m:
+            k, m = i, g
+    return -m, k
+
+
+def ols_rescaling(A: np.ndarray, x: SparseVec) -> np.ndarray:
+    """`ols_rescaling!(P, x)` (`src/forward.jl:97-114`): squared norm of every atom after projecting out the active set,
+    `sum(abs2, A[:, j]) - sum(abs2, (Q'A)[1:nnz(x), j])` with Q the orthogonal factor of the active columns."""
+    T = A.dtype
+    resc = (A * A).sum(axis=0).astype(T)                                  # :105
+    if x.nnz():
+        Q1, _ = np.linalg.qr(A[:, np.asarray(x.nzind, dtype=np.int64)])   # P.AiQR.Q, first nnz(x) columns (:99,:106)
+        QA = (Q1.T @ A).astype(T)                                         # :104
+        for i in range(QA.shape[0]):                                      # :108-112
+            resc = resc - QA[i, :] ** 2
+    return resc
+
+
+def forward_delta(A: np.ndarray, b: np.ndarray, x: SparseVec) -> np.ndarray:
+    """`forward_δ!(P, x)` (`src/forward.jl:69-76`): decrease of the SQUARED residual norm for every passive atom."""
+    r = residual(A, x, b)                                                 # :70
+    d = (A.T @ r).astype(np.float64)                                      # :71  (P.δ² is a Float64 vector, :29)
+    resc = ols_rescaling(A, x)                                            # :72
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = d * d / resc                                                  # :73
+    if x.nnz():
+        d[np.asarray(x.nzind, dtype=np.int64)] = 0.0                      # :74
+    return d
+
+
+def fr(A: np.ndarray, b: np.ndarray, max_eps: float = 0.0, min_delta: float = 0.0, k: Optional[int] = None,
+       ls: str = "lapack", trace: Optional[Trace] = None) -> SparseVec:
+    """`fr(A, b, max_ε, min_δ, k=size(A,1))` (`src/forward.jl:44-51`) == ols == oomp == ormp (:52-54);
+    the keyword form `fr(A, b; max_residual=0, min_decrease=0, sparsity=size(A,2))` (:33-36) maps onto it."""
+    _check_finite(A, b)
+    M, N = A.shape
+    k = M if k is None else k
+    engine = _ActiveSetLS(A, ls, M)                                       # :27  UpdatableQR(A[:, nzind])
+    x = SparseVec(N)
+    for _ in range(k):                                                    # :47
+        # ---- forward_step!(P, x, max_ε, min_δ)  (:56-67) ----
+        if not x.nnz() < M:                                               # :57
+            break
+        normr = float(np.linalg.norm(residual(A, x, b)))                  # :58-59
+        if not normr > max_eps:                                           # :60
+            break
+        d2 = forward_delta(A, b, x)                                       # :61
+        max_d2, i = findmax_first(d2)                                     # :62
+        if min_delta ** 2 < max_d2:                                       # :63
+            engine.add_column(x, i)                                       # :65
+            engine.solve(x, b)                                            # :66
+            if trace is not None:
+                top = np.sort(d2[np.isfinite(d2)])[::-1]
+                trace.margin.append(float((top[0] - top[1]) / top[0]) if top.size > 1 and top[0] > 0 else 1.0)
+                trace.selected.append([i]); trace.added.append([i])
+                trace.resnorm.append(float(np.linalg.norm(residual(A, x, b)))); trace.iterations += 1
+        else:
+            if x.nnz():
+                engine.solve(x, b)                                        # :68
+            break                                                         # :69 returns false
+    return x
+
+
+ols = oomp = ormp = fr
 
 
 # ----------------------------------------------------------------------------------------

@@ -16,9 +16,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import pursuit_oracle as po  # noqa: E402
 
 
-def build(name, algo, M, N, k, B, seed, dtype=np.float64, l=None, noise=0.0, eps=None, planted=None):
+def build(name, algo, M, N, k, B, seed, dtype=np.float64, l=None, noise=0.0, eps=None, planted=None, colscale=False,
+          max_eps=0.0, min_delta=0.0):
     rng = np.random.default_rng(seed)
     A = po.gaussian_dictionary(rng, M, N, dtype)
+    if colscale:                     # un-normalised atoms: the OLS rescaling ||a||^2 - ||Q'a||^2 starts away from 1
+        A = np.asfortranarray(A * rng.uniform(0.5, 2.0, size=(1, N)).astype(dtype))
     planted = k if planted is None else planted
     cols = []
     for _ in range(B):
@@ -41,6 +44,8 @@ def build(name, algo, M, N, k, B, seed, dtype=np.float64, l=None, noise=0.0, eps
             x = po.omp(A, Bm[:, s], k, eps=eps, trace=t)
         elif algo == "gomp":
             x = po.gomp(A, Bm[:, s], l, k, eps=eps, trace=t)
+        elif algo == "fr":
+            x = po.fr(A, Bm[:, s], max_eps, min_delta, k, trace=t)
         else:
             x = po.mp(A, Bm[:, s], k, trace=t)
         n = x.nnz()
@@ -50,16 +55,27 @@ def build(name, algo, M, N, k, B, seed, dtype=np.float64, l=None, noise=0.0, eps
         o = t.order()
         if algo != "mp":
             order[s, :len(o)] = o
-        resn[s] = t.resnorm[-1]
-        margin[s] = min(t.margin)
+        resn[s] = t.resnorm[-1] if t.resnorm else float(np.linalg.norm(Bm[:, s]))
+        margin[s] = min(t.margin) if t.margin else 1.0
     meta = dict(algo=algo, M=M, N=N, k=k, B=B, seed=seed, dtype=np.dtype(dtype).name, l=l, noise=noise, eps=eps,
-                planted=planted)
+                planted=planted, colscale=colscale, max_eps=max_eps, min_delta=min_delta)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), A=A, B=Bm, nzind=nzind, nzval=nzval, order=order, nnz=nnz,
                         resnorm=resn, margin=margin, meta=json.dumps(meta))
     print(name, "min margin", margin.min(), "max resnorm", resn.max())
 
 
+def build_fr():
+    """Forward regression / OLS (src/forward.jl): reference test shape, un-normalised atoms, both stopping rules."""
+    build("fr_ref_32x48_k3", "fr", 32, 48, 3, 40, seed=1250)                             # test/forward.jl:15-17
+    build("fr_noisy_96x200_k8", "fr", 96, 200, 8, 12, seed=1251, noise=5e-3, colscale=True)
+    build("fr_stop_eps_70x130", "fr", 70, 130, 20, 8, seed=1252, planted=6, noise=5e-3, max_eps=0.05, colscale=True)
+    build("fr_stop_delta_70x130", "fr", 70, 130, 20, 8, seed=1253, planted=6, noise=5e-3, min_delta=0.05)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fr":
+        build_fr()
+        sys.exit(0)
     build("omp_c1_128x256_k8", "omp", 128, 256, 8, 4, seed=1234)                      # BASELINE config 1 (KAT-1)
     build("omp_c1_noisy", "omp", 128, 256, 8, 4, seed=1235, noise=5e-3)                # KAT-2
     build("omp_ref_32x48_k3", "omp", 32, 48, 3, 40, seed=1236)                         # reference test shape (KAT-3)

@@ -117,6 +117,8 @@ def test_golden(cs, path, impl, update, monkeypatch):
         impl = None
     z = np.load(path, allow_pickle=False)
     meta = json.loads(str(z["meta"]))
+    if meta["algo"] == "fr" and (impl, update) != ("gemm", "cta"):
+        pytest.skip("forward regression has one kernel combination (DMMA pass + CTA update)")
     A, Bm = np.asfortranarray(z["A"]), np.asfortranarray(z["B"])
     f32 = A.dtype == np.float32
     if f32 and impl == "gemm":
@@ -130,6 +132,8 @@ def test_golden(cs, path, impl, update, monkeypatch):
             batch.omp(k, eps)
         elif meta["algo"] == "gomp":
             batch.gomp(meta["l"], k, eps)
+        elif meta["algo"] == "fr":
+            batch.fr(k, meta["max_eps"], meta["min_delta"])
         else:
             batch.mp(k)
         sel, coef, nnz, res, its = batch.download(k)
@@ -233,6 +237,60 @@ def test_dependent_atom_is_not_appended(cs, solve_path):
     A = np.asfortranarray(np.array([[1.0, 1.0, 0], [0, 0, 1.0], [0, 0, 0]]))
     x = cs.gomp(A, np.array([2.0, 0, 0]), 2, 0.0, 2)      # top-2 = atoms 0 and 1 (a tie): atom 1 duplicates atom 0
     assert x.nzind.tolist() == [0] and x.nzval.tolist() == [2.0]
+
+
+# ------------------------------------------------------------------ forward regression / OLS
+def test_fr_call_surface(cs, po):
+    """`fr` / `ols` / `oomp` / `ormp` (src/forward.jl:33-54) through the one-shot C entry point, against the oracle:
+    positional and keyword forms, both stopping rules, zero signal, single signal and a small batch."""
+    rng = np.random.default_rng(21)
+    A, x0, b = po.sparse_data(rng, 40, 90, 4)
+    A = np.asfortranarray(A * rng.uniform(0.5, 2.0, size=(1, 90)))
+    b = A[:, x0.nzind] @ np.asarray(x0.nzval)
+    y = po.perturb(rng, b, 1e-2)
+    with cs.Dictionary(A) as D:
+        for args, kw, oargs in [((), dict(sparsity=4), (0.0, 0.0, 4)), ((0.05, 0.0), {}, (0.05, 0.0, None)),
+                                ((0.0, 0.05), {}, (0.0, 0.05, None)), ((0.0, 0.0, 7), {}, (0.0, 0.0, 7)),
+                                ((), dict(max_residual=0.05), (0.05, 0.0, 90))]:
+            got = cs.fr(D, y, *args, **kw)
+            ref = po.fr(A, y, *oargs)
+            assert got.nzind.tolist() == ref.nzind, (args, kw)
+            assert _close(got.nzval, ref.nzval, RTOL64), (args, kw)
+        assert cs.ols is cs.fr and cs.oomp is cs.fr and cs.ormp is cs.fr
+        assert cs.fr(D, np.zeros(40)).nnz() == 0
+        Bm = np.asfortranarray(np.stack([y, b, 2 * y - b], axis=1))
+        out = cs.fr(D, Bm, sparsity=4)
+        for s in range(3):
+            ref = po.fr(A, Bm[:, s], 0.0, 0.0, 4)
+            assert out[s].nzind.tolist() == ref.nzind and _close(out[s].nzval, ref.nzval, RTOL64)
+    with pytest.raises(cs.CSB200Error) as ei:
+        cs.fr(A.astype(np.float32), y.astype(np.float32), sparsity=3)
+    assert ei.value.status == -7
+
+
+def test_fr_midsize_batch_vs_oracle(cs, po):
+    """Ragged mid-size batch, un-normalised atoms, noisy signals: selection sequence bit-exact on a sample,
+    coefficients / residual norms within 1e-10, planted support recovered for every signal."""
+    rng = np.random.default_rng(77)
+    M, N, k, B = 200, 1111, 12, 150
+    A = po.gaussian_dictionary(rng, M, N)
+    A = np.asfortranarray(A * rng.uniform(0.5, 2.0, size=(1, N)))
+    X0, Bm = _planted(po, rng, A, k, B, noise=5e-3)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+        batch.upload(Bm)
+        batch.fr(k)
+        sel, coef, nnz, res, its = batch.download(k)
+        batch.fr(k)                                                     # bit-identical re-solve on the same batch
+        sel2, coef2, *_ = batch.download(k)
+    assert np.array_equal(sel, sel2) and np.array_equal(coef, coef2)
+    for s in range(B):
+        assert sorted(sel[s, :k].tolist()) == X0[s].nzind, s
+    for s in range(0, B, 10):
+        t = po.Trace()
+        ref = po.fr(A, Bm[:, s], 0.0, 0.0, k, trace=t)
+        assert sel[s, :k].tolist() == t.order(), (s, min(t.margin))
+        idx, val = _sorted(sel[s], coef[s], k)
+        assert _close(val, ref.nzval, RTOL64) and abs(res[s] - t.resnorm[-1]) < 1e-10
 
 
 # ------------------------------------------------------------------ mid-size parity and properties

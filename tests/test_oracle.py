@@ -189,6 +189,57 @@ def test_negative_eps_throws():
         po.gomp(A, b, 2, 3, eps=-1.0)
 
 
+# ------------------------------------------------------------------ forward regression
+@pytest.mark.parametrize("seed", SEEDS)
+@pytest.mark.parametrize("ls", ["lapack", "givens"])
+def test_fr_properties(seed, ls):
+    """test/forward.jl:15-22: `fr(A, b, sparsity = k)` recovers support and coefficients, noiseless and noisy."""
+    A, x, b, y = _problem(seed)
+    xf = po.fr(A, b, 0.0, 0.0, 3, ls=ls)
+    assert xf.nzind == x.nzind
+    assert np.allclose(xf.nzval, x.nzval, rtol=np.sqrt(np.finfo(float).eps))
+    xf = po.fr(A, y, 0.0, 0.0, 3, ls=ls)
+    assert xf.nzind == x.nzind
+    assert np.linalg.norm(np.array(xf.nzval) - np.array(x.nzval)) <= 2e-2
+
+
+def test_fr_criterion_is_the_residual_decrease():
+    """`forward_δ!` (src/forward.jl:69-76) is, for every passive atom, exactly the decrease of ||r||^2 obtained by
+    adding that atom and re-solving -- checked against brute-force least squares; active atoms read 0."""
+    rng = np.random.default_rng(5)
+    A = po.gaussian_dictionary(rng, 24, 40) * rng.uniform(0.5, 2.0, size=(1, 40))
+    b = rng.standard_normal(24)
+    x = po.SparseVec(40)
+    eng = po._ActiveSetLS(A, "lapack", 24)
+    for j in (3, 17, 29):
+        eng.add_column(x, j)
+    eng.solve(x, b)
+    d2 = po.forward_delta(A, b, x)
+    r0 = np.linalg.norm(po.residual(A, x, b)) ** 2
+    for j in range(40):
+        if j in x.nzind:
+            assert d2[j] == 0.0
+            continue
+        S = sorted(x.nzind + [j])
+        c, *_ = np.linalg.lstsq(A[:, S], b, rcond=None)
+        assert np.isclose(r0 - np.linalg.norm(b - A[:, S] @ c) ** 2, d2[j], rtol=1e-9, atol=1e-12), j
+
+
+def test_fr_stopping_rules_and_findmax():
+    rng = np.random.default_rng(8)
+    A, x0, b = po.sparse_data(rng, 40, 90, 4)
+    y = po.perturb(rng, b, 1e-2)
+    assert po.fr(A, y, 0.05, 0.0).nzind == x0.nzind                   # ||r|| > max_eps fails after 4 atoms (:60)
+    assert po.fr(A, y, 0.0, 0.05).nzind == x0.nzind                   # min_delta^2 < max delta2 fails (:63)
+    assert po.fr(A, y, 0.0, 0.0, 2).nnz() == 2                        # sparsity cap
+    assert po.fr(A, np.zeros(40)).nnz() == 0                          # r = 0: normr > 0 fails at once
+    assert po.findmax_first(np.array([1.0, np.nan, 3.0, 3.0, -1.0])) == (3.0, 2)   # util.jl:173-189: NaN skipped
+    A6 = np.asfortranarray(np.eye(6))                                 # ties -> first index
+    t = po.Trace()
+    po.fr(A6, np.array([0, 2.0, 2.0, 0, 1.0, 0]), trace=t)
+    assert t.order() == [1, 2, 4]
+
+
 def test_golden_fixtures_reproduce():
     """The committed fixtures (tests/golden/make_golden.py) are what the oracle produces today."""
     files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
@@ -203,6 +254,8 @@ def test_golden_fixtures_reproduce():
                 x = po.omp(A, Bm[:, s], meta["k"], eps=meta.get("eps"))
             elif meta["algo"] == "gomp":
                 x = po.gomp(A, Bm[:, s], meta["l"], meta["k"], eps=meta.get("eps"))
+            elif meta["algo"] == "fr":
+                x = po.fr(A, Bm[:, s], meta["max_eps"], meta["min_delta"], meta["k"])
             else:
                 x = po.mp(A, Bm[:, s], meta["k"])
             n = int(z["nnz"][s])

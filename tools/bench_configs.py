@@ -95,6 +95,27 @@ def c3(cs, dev, args):
                 corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
 
 
+def fr2(cs, dev, args):
+    """Forward regression / OLS at the config-2 shape: per step one DMMA pass over
+    [residuals | newest directions] (4 M N B flop after the first step) + the per-signal update."""
+    M, N, k, B = 1024, 8192, 32, int(65536 * args.scale)
+    A, Bm, idx = make_problem(M, N, k, B, np.float64, dev)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, k) as b:
+        b.upload(Bm)
+        b.fr(k)
+        b.profile(True)
+        b.fr(k)
+        ms = b.last_solve_ms()
+        corr_ms, n, _ = b.corr_time()
+        sel, coef, nnz, res, its = b.download(k)
+    rec = float(np.mean([(set(idx[s]) <= set(sel[s, :nnz[s]])) for s in range(0, B, 64)]))
+    flop = 2.0 * M * N * B * (2 * n - 1)                     # the first pass has no direction half
+    tf = flop / corr_ms / 1e9
+    return dict(config="fr/ols 1024x8192 k=32 f64", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
+                corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+                corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
+
+
 def c5(cs, dev, args):
     M, N, iters, B = 4096, 65536, int(200 * args.scale), 4096
     A, Bm, idx = make_problem(M, N, 32, B, np.float64, dev, noise=5e-3)
@@ -174,13 +195,13 @@ def c4(cs, dev, args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5", "fr2"])
     ap.add_argument("--scale", type=float, default=1.0)
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     cs = ge.load_package()
-    res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[a.config](cs, dev, a)
+    res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "fr2": fr2}[a.config](cs, dev, a)
     if res is not None:
         print(json.dumps(res))
