@@ -120,7 +120,7 @@ struct csb200_batch {
     bool lazy_input_check = false;         // upload skipped the NaN scan: the small solve kernel reports it
     int* dflag = nullptr;       // non-finite scan result
     // forward regression (csb200_batch_fr): allocated on first use
-    double* resc = nullptr;     // [cap_sig][N] OLS rescaling
+    double* resc = nullptr;     // [N][round_up(nsig, 2)] OLS rescaling
     double* qnew = nullptr;     // [cap_sig][ld] newest orthonormal direction per signal
     double* cn2 = nullptr;      // [N] squared column norms
     cudaStream_t stream = nullptr;
@@ -653,7 +653,7 @@ int csb200_batch_fr(csb200_batch* b, int64_t k, double max_eps, double min_delta
     if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
     if (!b->resc) {
-        CU_TRY(cudaMalloc(&b->resc, (size_t)b->cap_sig * d->N * sizeof(double)));
+        CU_TRY(cudaMalloc(&b->resc, (size_t)round_up(b->cap_sig, 2) * d->N * sizeof(double)));
         CU_TRY(cudaMalloc(&b->qnew, (size_t)b->cap_sig * d->ld * sizeof(double)));
         CU_TRY(cudaMalloc(&b->cn2, (size_t)d->N * sizeof(double)));
     }
@@ -665,7 +665,7 @@ int csb200_batch_fr(csb200_batch* b, int64_t k, double max_eps, double min_delta
     if ((rc = ensure_partials(b, P, 1))) return rc;
     b->cur_P = (int)P;
     StateArgs sa = state_args(b, 1, 1, 0.0, 0);
-    sa.resc = b->resc; sa.qnew = b->qnew; sa.max_eps = max_eps; sa.min_delta2 = min_delta * min_delta;
+    sa.resc = b->resc; sa.ldr = round_up(b->nsig, 2); sa.qnew = b->qnew; sa.max_eps = max_eps; sa.min_delta2 = min_delta * min_delta;
     CorrArgs c;
     c.A = d->dA; c.R = b->dR; c.M = (int)d->M; c.ld = (int)d->ld; c.N = (int)d->N; c.nsig = (int)b->nsig;
     c.S = 1; c.P = (int)P; c.idx_offset = 0; c.pval = b->pval; c.pidx = b->pidx;
@@ -683,7 +683,7 @@ int csb200_batch_fr(csb200_batch* b, int64_t k, double max_eps, double min_delta
             CU_TRY(cudaEventRecord(e0, b->stream));
         }
         e = launch_corr_gemm_f64_ols(&d->mapA, it == 0 ? &b->mapR : &mapR64, it == 0 ? nullptr : &mapQ64, c, b->resc,
-                                     d->num_sms, b->stream);
+                                     sa.ldr, d->num_sms, b->stream);
         if (e != cudaSuccess) return fail_cuda(e, "fr correlation pass");
         if (b->profile) CU_TRY(cudaEventRecord(e1, b->stream));
         e = launch_omp_update(sa, false, b->stream);

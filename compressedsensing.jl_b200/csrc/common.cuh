@@ -42,7 +42,7 @@ cudaError_t launch_gemm_f64_store(const CUtensorMap* mapA, const CUtensorMap* ma
                                   double* C, long long ldc, int num_sms, cudaStream_t st);
 // Forward-regression pass (EPI_OLS epilogue): candidates are (delta2, atom); mapQ == nullptr on the first step.
 cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap* mapR, const CUtensorMap* mapQ,
-                                     const CorrArgs& a, double* resc, int num_sms, cudaStream_t st);
+                                     const CorrArgs& a, double* resc, long long ldr, int num_sms, cudaStream_t st);
 cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_corr_naive(const CorrArgs& a, bool f32, cudaStream_t st);
 
@@ -71,7 +71,8 @@ struct StateArgs {
     int* flags;           // [nsig]  bit0: dependent atom skipped, bit1: no candidate, bit2: non-finite input
     const double* gram;   // optional N x N Gram matrix A'A (ld = N), FP64 dictionaries only; nullptr = not available
     // forward regression (src/forward.jl): non-null resc switches the update kernel to `forward_step!` semantics
-    double* resc = nullptr;     // [nsig][N]  OLS rescaling ||a_j||^2 - ||Q1'a_j||^2 (+Inf marks active atoms)
+    double* resc = nullptr;     // [N][ldr]  OLS rescaling ||a_j||^2 - ||Q1'a_j||^2 per (atom, signal); +Inf marks active atoms
+    long long ldr = 0;          // leading dimension of resc (even, >= nsig)
     double* qnew = nullptr;     // [nsig][ld] newest orthonormal direction q_t of each signal (zero if none was added)
     double max_eps = 0.0;       // forward_step! returns false unless ||r|| > max_eps   (:60)
     double min_delta2 = 0.0;    // ... and unless min_delta^2 < max_j delta2_j          (:63)
@@ -96,7 +97,7 @@ cudaError_t launch_small_solve(const StateArgs& a, const SmallSolveArgs& q, bool
 size_t omp_update_smem_bytes(int ld, int kcap);            // dynamic shared memory the kernels above need
 size_t omp_update_cluster_smem_bytes(int ld, int kcap);
 constexpr size_t MAX_DYN_SMEM = 227 * 1024;
-// resc[s][j] = ||a_j||^2 for every signal (`sum!(abs2, P.rescaling', P.A)`, src/forward.jl:105), qnew = 0
+// resc[j][s] = ||a_j||^2 for every signal (`sum!(abs2, P.rescaling', P.A)`, src/forward.jl:105), qnew = 0
 cudaError_t launch_ols_init(const StateArgs& a, double* colnorm2, cudaStream_t st);
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st);
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);

@@ -246,29 +246,42 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             const int atom0 = tn * TILE_N + wm * 8 * MI + g;
             const int p = tn * WM + wm;
             constexpr int NS = DUAL ? NJ / 2 : NJ;
+            // resc is [atom][signal] (leading dimension ldc, even): a thread's two signals (e = 0, 1) are one 16 B
+            // streaming load / store, and the 8 atoms of a j-group are loaded together (one DRAM round trip per group)
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
+                const int sig0 = tb * SIG_PER_TILE + wn * 8 * NS + j * 8 + 2 * q;
+                double2 rv[MI];
+                if (sig0 < nsig) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int sig = tb * SIG_PER_TILE + wn * 8 * NS + j * 8 + 2 * q + e;
-                    double bv = -1.0;
-                    int bi = INT_MAX;
-                    if (sig < nsig) {
-                        double* rs = resc + (size_t)sig * ldc;
+                    for (int i = 0; i < MI; ++i) {
+                        const int idx = atom0 + i * 8;
+                        rv[i] = idx < N ? __ldcs(reinterpret_cast<const double2*>(resc + (size_t)idx * ldc + sig0))
+                                        : make_double2(1.0, 1.0);
+                    }
+                    if constexpr (DUAL) {
 #pragma unroll
                         for (int i = 0; i < MI; ++i) {
                             const int idx = atom0 + i * 8;
-                            if (idx < N) {
-                                double rv = rs[idx];
-                                if constexpr (DUAL) {
-                                    const double d = acc[i][j + NJ / 2][e];
-                                    rv = fma(-d, d, rv);
-                                    rs[idx] = rv;
-                                }
-                                const double c = acc[i][j][e];
-                                const double v = c * c / rv;
-                                if (v >= 0.0 && v > bv) { bv = v; bi = idx; }   // idx ascends with i: first max wins
-                            }
+                            const double d0 = acc[i][j + NJ / 2][0], d1 = acc[i][j + NJ / 2][1];
+                            rv[i].x = fma(-d0, d0, rv[i].x);
+                            rv[i].y = fma(-d1, d1, rv[i].y);
+                            if (idx < N) __stcs(reinterpret_cast<double2*>(resc + (size_t)idx * ldc + sig0), rv[i]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int sig = sig0 + e;
+                    double bv = -1.0;
+                    int bi = INT_MAX;
+                    if (sig < nsig) {
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) {
+                            const int idx = atom0 + i * 8;
+                            const double c = acc[i][j][e];
+                            const double v = c * c / (e ? rv[i].y : rv[i].x);
+                            if (idx < N && v >= 0.0 && v > bv) { bv = v; bi = idx; }   // idx ascends with i: first max wins
                         }
                     }
 #pragma unroll
@@ -394,9 +407,9 @@ cudaError_t launch_gemm_f64_store(const CUtensorMap* mapA, const CUtensorMap* ma
 
 // Forward-regression pass: one (delta2, atom) candidate per (64-atom block, signal).  mapQ == nullptr: first
 // step (no direction yet; mapR has 128-column boxes).  Otherwise mapR / mapQ have 64-column boxes and resc is
-// down-dated by <a_j, q_s>^2 in the same launch.  resc: [nsig][N].
+// down-dated by <a_j, q_s>^2 in the same launch.  resc: [N][ldr] (atom-major, ldr even >= nsig).
 cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap* mapR, const CUtensorMap* mapQ,
-                                     const CorrArgs& a, double* resc, int num_sms, cudaStream_t st) {
+                                     const CorrArgs& a, double* resc, long long ldr, int num_sms, cudaStream_t st) {
     const int sig_per_tile = mapQ ? TILE_B / 2 : TILE_B;
     const int tilesN = (a.N + TILE_N - 1) / TILE_N;
     const int tilesB = (a.nsig + sig_per_tile - 1) / sig_per_tile;
@@ -406,10 +419,10 @@ cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap*
     const int kchunks = (a.ld / KCH + 1) / 2;
     if (mapQ)
         corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, true><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
-            *mapA, *mapR, a.N, a.nsig, kchunks, tilesN, tilesB, tilesN, 1, a.P, a.idx_offset, a.pval, a.pidx, a.N, *mapQ, resc);
+            *mapA, *mapR, a.N, a.nsig, kchunks, tilesN, tilesB, tilesN, 1, a.P, a.idx_offset, a.pval, a.pidx, ldr, *mapQ, resc);
     else
         corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, false><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
-            *mapA, *mapR, a.N, a.nsig, kchunks, tilesN, tilesB, tilesN, 1, a.P, a.idx_offset, a.pval, a.pidx, a.N, *mapR, resc);
+            *mapA, *mapR, a.N, a.nsig, kchunks, tilesN, tilesB, tilesN, 1, a.P, a.idx_offset, a.pval, a.pidx, ldr, *mapR, resc);
     return cudaGetLastError();
 }
 

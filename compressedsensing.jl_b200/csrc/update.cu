@@ -173,7 +173,7 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
                     const double irho = dep ? 0.0 : S.Tm[(t - 1) + (t - 1) * S.ldT];
                     double* qn = a.qnew + (size_t)sig * ld;
                     for (int row = tid; row < ld; row += NT) qn[row] = S.v[row] * irho;
-                    if (tid == 0) a.resc[(size_t)sig * a.N + (j - a.idx_offset)] = __longlong_as_double(0x7ff0000000000000LL);
+                    if (tid == 0) a.resc[(size_t)(j - a.idx_offset) * a.ldr + sig] = __longlong_as_double(0x7ff0000000000000LL);
                 }
             }
         }
@@ -305,11 +305,11 @@ __global__ void __launch_bounds__(256) colnorm2_kernel(const double* __restrict_
     s = warp_sum(s);
     if (lane == 0) out[j] = s;
 }
-__global__ void __launch_bounds__(256) ols_init_kernel(const double* __restrict__ cn2, int N, int ld, double* __restrict__ resc,
-                                                       double* __restrict__ qnew) {
-    const int sig = blockIdx.x;
-    for (int j = threadIdx.x; j < N; j += 256) resc[(size_t)sig * N + j] = cn2[j];
-    for (int row = threadIdx.x; row < ld; row += 256) qnew[(size_t)sig * ld + row] = 0.0;
+__global__ void __launch_bounds__(256) ols_init_kernel(const double* __restrict__ cn2, int N, long long ldr,
+                                                       double* __restrict__ resc, size_t nq, double* __restrict__ qnew) {
+    const size_t stride = (size_t)gridDim.x * 256, t0 = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (size_t i = t0; i < (size_t)N * ldr; i += stride) resc[i] = cn2[i / ldr];
+    for (size_t i = t0; i < nq; i += stride) qnew[i] = 0.0;
 }
 
 template <typename T>
@@ -369,7 +369,7 @@ cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, con
 cudaError_t launch_ols_init(const StateArgs& a, double* colnorm2, cudaStream_t st) {
     if (a.nsig <= 0) return cudaSuccess;
     colnorm2_kernel<<<(a.N + 7) / 8, 256, 0, st>>>(static_cast<const double*>(a.A), a.ld, a.N, colnorm2);
-    ols_init_kernel<<<a.nsig, 256, 0, st>>>(colnorm2, a.N, a.ld, a.resc, a.qnew);
+    ols_init_kernel<<<148 * 8, 256, 0, st>>>(colnorm2, a.N, a.ldr, a.resc, (size_t)a.nsig * a.ld, a.qnew);
     return cudaGetLastError();
 }
 
