@@ -32,7 +32,7 @@ import numpy as np
 __all__ = [
     "SparseVector", "Dictionary", "Batch", "omp", "gomp", "mp", "lib", "LIB_PATH", "CSB200Error",
     "device_count", "F64", "F32", "ShardComm", "omp_sharded", "shard_range", "owner_of", "pick_global",
-    "exchange_unique_id", "assemble_csc", "fr", "ols", "oomp", "ormp",
+    "exchange_unique_id", "assemble_csc", "fr", "ols", "oomp", "ormp", "sp", "oblivious",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -79,6 +79,11 @@ def _load() -> ctypes.CDLL:
         "csb200_batch_gomp": (c_int, [c_void_p, c_int64, c_int64, c_double]),
         "csb200_batch_mp": (c_int, [c_void_p, c_int64, i64p, f64p, i64p, c_int64]),
         "csb200_batch_fr": (c_int, [c_void_p, c_int64, c_double, c_double]),
+        "csb200_batch_sp": (c_int, [c_void_p, c_int64, c_double, c_int64]),
+        "csb200_batch_oblivious": (c_int, [c_void_p, c_int64]),
+        "csb200_sp": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_double, c_int64, i64p, f64p, i64p, f64p,
+                              i64p]),
+        "csb200_oblivious": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, i64p, f64p, i64p, f64p]),
         "csb200_fr": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_double, c_double, i64p, f64p, i64p, f64p,
                               i64p]),
         "csb200_batch_download": (c_int, [c_void_p, c_int64, i64p, f64p, i64p, f64p, i64p]),
@@ -113,6 +118,7 @@ EXPORTED_SYMBOLS = [
     "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
     "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp",
     "csb200_assemble_csc", "csb200_comm_unique_id", "csb200_batch_fr", "csb200_fr",
+    "csb200_batch_sp", "csb200_batch_oblivious", "csb200_sp", "csb200_oblivious",
     "csb200_comm_create", "csb200_comm_destroy", "csb200_omp_sharded", "csb200_debug_corr_topk",
     "csb200_debug_get_residual",
 ]
@@ -246,6 +252,12 @@ class Batch:
 
     def fr(self, k: int, max_eps: float = 0.0, min_delta: float = 0.0) -> None:
         _check(lib.csb200_batch_fr(self._h, int(k), float(max_eps), float(min_delta)))
+
+    def sp(self, k: int, delta: float = 1e-12, maxiter: Optional[int] = None) -> None:
+        _check(lib.csb200_batch_sp(self._h, int(k), float(delta), int(16 * k if maxiter is None else maxiter)))
+
+    def oblivious(self, k: int) -> None:
+        _check(lib.csb200_batch_oblivious(self._h, int(k)))
 
     def mp(self, iters: int, x0: Optional[Sequence[SparseVector]] = None) -> None:
         if x0 is None:
@@ -467,6 +479,33 @@ def fr(A, b, *args, max_residual: float = 0.0, min_decrease: float = 0.0, sparsi
 
 
 ols = oomp = ormp = fr            # `const ols = fr` etc. (src/forward.jl:52-54)
+
+
+def sp(A, b, k: int, delta: float = 1e-12, maxiter: Optional[int] = None, device: int = 0, result: str = "vectors"):
+    """Subspace pursuit -- `sp(A, b, k, δ = 1e-12; maxiter = 16k)` (`src/twostage.jl:105-117`)."""
+    M = A.M if isinstance(A, Dictionary) else np.shape(A)[0]
+    k = int(k)
+    if 2 * k > M:
+        raise ValueError(f"2k = {2 * k} > {M} = length(b) is invalid for Subspace Pursuit")     # twostage.jl:62
+    mi = 16 * k if maxiter is None else int(maxiter)
+
+    def call(D, B, ldb, nsig, sel, coef, nnz, res, its):
+        return lib.csb200_sp(D._h, B.ctypes.data, ldb, nsig, k, float(delta), mi, _i64p(sel), _f64p(coef), _i64p(nnz),
+                             _f64p(res), _i64p(its))
+
+    return _solve(A, b, device, call, max(k, 1), result=result)
+
+
+def oblivious(A, b, k: int, device: int = 0, result: str = "vectors"):
+    """Oblivious selection -- `oblivious(A, b, k)` (`src/oblivious.jl:3-8`): the k atoms most correlated with b.
+    (The reference allocates its result with `spzeros(size(b))`, i.e. length M; this returns length N.)"""
+    k = int(k)
+
+    def call(D, B, ldb, nsig, sel, coef, nnz, res, its):
+        its[:] = 1
+        return lib.csb200_oblivious(D._h, B.ctypes.data, ldb, nsig, k, _i64p(sel), _f64p(coef), _i64p(nnz), _f64p(res))
+
+    return _solve(A, b, device, call, max(k, 1), result=result)
 
 
 def mp(A, b, k: int, x=None, device: int = 0):

@@ -123,6 +123,7 @@ struct csb200_batch {
     double* resc = nullptr;     // [N][round_up(nsig, 2)] OLS rescaling
     double* qnew = nullptr;     // [cap_sig][ld] newest orthonormal direction per signal
     double* cn2 = nullptr;      // [N] squared column norms
+    int* ndone = nullptr;       // subspace pursuit: number of signals whose stopping test has fired
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -140,7 +141,7 @@ int begin_solve_fwd(csb200_batch* b);
 
 void free_batch_mem(csb200_batch* b) {
     cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->state_blk);
-    cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2);
+    cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2); cudaFree(b->ndone);
     if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
@@ -693,6 +694,61 @@ int csb200_batch_fr(csb200_batch* b, int64_t k, double max_eps, double min_delta
     return finish(b, true);
 }
 
+// Subspace pursuit `sp(A, b, k, delta; maxiter = 16k)` (src/twostage.jl:105-117) and, with maxiter < 0, the
+// oblivious selection `oblivious(A, b, k)` (src/oblivious.jl:3-8), which is SP's initial acquisition alone.
+static int run_sp(csb200_batch* b, int64_t k, double delta, int64_t maxiter) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    csb200_dict* d = b->dict;
+    const bool obl = maxiter < 0;
+    if (k < 1 || k > d->N || !(delta == delta)) return CSB200_ERR_INVALID_ARG;
+    if (d->n_total != d->N) { g_last_error = "sp / oblivious need an unsharded dictionary"; return CSB200_ERR_UNSUPPORTED; }
+    if (!obl && 2 * k > d->M) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "2k = %lld > %lld = length(b) is invalid for Subspace Pursuit", (long long)(2 * k), (long long)d->M);
+        g_last_error = buf;                                   // the reference `error`s with this text (twostage.jl:62)
+        return CSB200_ERR_INVALID_ARG;
+    }
+    if (obl && k > d->M) { g_last_error = "oblivious: k > size(A, 1) (underdetermined least squares) is not supported"; return CSB200_ERR_UNSUPPORTED; }
+    if (k > SP_MAX_K) { g_last_error = "sp / oblivious: k > 256 is not supported"; return CSB200_ERR_UNSUPPORTED; }
+    if ((obl ? k : 2 * k) > b->kcap) { g_last_error = "batch max_sparsity too small (sp needs 2k, oblivious k)"; return CSB200_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(d))) return rc;
+    if ((size_t)d->ld * sizeof(double) > MAX_DYN_SMEM || sp_update_smem_bytes((int)d->ld, (int)b->kcap) > MAX_DYN_SMEM) {
+        g_last_error = "signal length / max_sparsity exceed the update kernel's shared memory";
+        return CSB200_ERR_UNSUPPORTED;
+    }
+    if ((rc = settle_input(b))) return rc;
+    if ((rc = ensure_factor(b))) return rc;
+    if (!b->ndone) CU_TRY(cudaMalloc(&b->ndone, sizeof(int)));
+    b->use_gram = false;
+    const bool f32 = d->dtype == CSB200_F32;
+    const int S = (int)(k < PBLK ? k : PBLK);                 // per 64-atom block the whole top-k can sit in one block
+    if ((rc = begin_solve(b))) return rc;
+    CU_TRY(cudaMemsetAsync(b->ndone, 0, sizeof(int), b->stream));
+    cudaError_t e = launch_reset_state(state_args(b, S, S, 0.0, 0), f32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    for (int64_t it = 0; it <= (obl ? 0 : maxiter); ++it) {
+        if ((rc = run_corr(b, S, IMPL_AUTO))) return rc;
+        e = launch_sp_update(state_args(b, S, S, 0.0, 0), f32, (int)k, delta, it == 0 ? 1 : 0, b->ndone, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "sp_update");
+        b->other_launches++;
+        if (it > 0) {                                         // every signal stopped?  (4-byte read back per update!)
+            int h = 0;
+            CU_TRY(cudaMemcpyAsync(&h, b->ndone, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+            CU_TRY(cudaStreamSynchronize(b->stream));
+            if (h >= b->nsig) break;
+        }
+    }
+    return finish(b, true);
+}
+
+int csb200_batch_sp(csb200_batch* b, int64_t k, double delta, int64_t maxiter) {
+    if (maxiter < 0) return CSB200_ERR_INVALID_ARG;
+    return run_sp(b, k, delta, maxiter);
+}
+int csb200_batch_oblivious(csb200_batch* b, int64_t k) { return run_sp(b, k, 0.0, -1); }
+
 int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const double* x0_val,
                     const int64_t* x0_nnz, int64_t x0_stride) {
     int rc = check_ready(b);
@@ -903,6 +959,30 @@ int csb200_fr(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64
     if (rc) return rc;
     rc = csb200_batch_fr(b, k, max_eps, min_delta);
     if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
+    return rc;
+}
+
+int csb200_sp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double delta, int64_t maxiter,
+              int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
+    if (!d || k < 1 || maxiter < 0) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(d->mu);
+    csb200_batch* b = nullptr;
+    int rc = one_shot(d, Bmat, ldb, nsig, 2 * k, &b, /*allow_lazy=*/false);
+    if (rc) return rc;
+    rc = csb200_batch_sp(b, k, delta, maxiter);
+    if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
+    return rc;
+}
+
+int csb200_oblivious(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, int64_t* sel_idx,
+                     double* coef, int64_t* nnz, double* resnorm) {
+    if (!d || k < 1) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(d->mu);
+    csb200_batch* b = nullptr;
+    int rc = one_shot(d, Bmat, ldb, nsig, k, &b, /*allow_lazy=*/false);
+    if (rc) return rc;
+    rc = csb200_batch_oblivious(b, k);
+    if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, nullptr);
     return rc;
 }
 

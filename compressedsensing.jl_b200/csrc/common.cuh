@@ -100,6 +100,10 @@ constexpr size_t MAX_DYN_SMEM = 227 * 1024;
 // resc[j][s] = ||a_j||^2 for every signal (`sum!(abs2, P.rescaling', P.A)`, src/forward.jl:105), qnew = 0
 cudaError_t launch_ols_init(const StateArgs& a, double* colnorm2, cudaStream_t st);
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st);
+// Subspace pursuit `update!` / oblivious selection (update.cu sp_update_kernel); k <= SP_MAX_K atoms per acquisition.
+constexpr int SP_MAX_K = 256;
+cudaError_t launch_sp_update(const StateArgs& a, bool f32, int k, double delta, int first, int* ndone, cudaStream_t st);
+size_t sp_update_smem_bytes(int ld, int kcap);
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx, const double* x0_val,
                                 const int* x0_nnz, int x0_stride, cudaStream_t st);

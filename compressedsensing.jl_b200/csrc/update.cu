@@ -203,6 +203,169 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Subspace pursuit / oblivious selection (/root/reference/src/twostage.jl:67-117,
+// src/oblivious.jl:3-8).  One CTA per signal runs the body of one `update!(P::SP, x)`:
+//   sp_acquisition! (:87-92)   top-k of |A'r| joins the support (atoms already in it are not duplicated),
+//                              least squares on the <= 2k atoms (`solve!`, :120-123)
+//   pruning (:97-101)          the nnz - k entries of smallest |x| leave (`partialsortperm(abs.(x.nzval), ..)`:
+//                              ties go to the lower position, i.e. the lower atom index since nzind is sorted)
+//   solve! on the k kept atoms, residual, and the stopping test of `sp` (:113-115).
+// first = 1 is the initial `sp_acquisition!(P, x, P.k)` of `sp` (:108) -- which is also all of `oblivious`.
+// Both least-squares problems reuse the block append of gomp (two gather sweeps per 8 atoms); the pruned
+// problem is re-factorised from scratch from r = b, as the reference's `factorize!` does (qr! on a copy).
+constexpr int MAX_TAKE = 256;       // atoms per acquisition handled by this kernel (k of sp / oblivious)
+
+template <typename T, int NT, typename BAt, typename RAt, typename RSet>
+__device__ __forceinline__ int append_list(PursuitSmem<T>& S, int& t, const int* list, int count, bool skip_active,
+                                           int bm, int cap, const T* __restrict__ A, int idx_offset, int ld, double* Vb,
+                                           double* Gm, double* Ym, double* sc, int* s_J, const T** s_Jcol, BAt b_at,
+                                           RAt r_at, RSet r_set, double& nr2, bool& changed) {
+    const int tid = threadIdx.x;
+    int flags = 0, round = 0;
+    while (round < count) {
+        int m = 0;
+        bool full = false;
+        while (round < count && m < bm) {
+            const int j = list[round];
+            if (j < 0) { flags |= 2; ++round; continue; }
+            if (skip_active) {
+                int in = 0;
+                for (int i = tid; i < t; i += NT) in |= (S.ssel[i] == j);
+                if (__syncthreads_or(in)) { ++round; continue; }
+            }
+            if (t + m >= cap) { full = true; break; }
+            if (tid == 0) { s_J[m] = j; s_Jcol[m] = A + (size_t)(j - idx_offset) * ld; }
+            ++m; ++round;
+        }
+        __syncthreads();
+        if (m > 0) {
+            int done_b = 0;
+            if (m > 1) {
+                done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2);
+                if (done_b) changed = true;
+            }
+            for (int c = done_b; c < m; ++c) {
+                const int dep = append_atom<T, NT>(S, t, s_J[c], s_Jcol[c], ld, b_at, r_at, r_set, nr2);
+                if (dep) flags |= 1; else changed = true;
+            }
+        }
+        if (full) break;
+    }
+    return flags;
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT, 2)
+sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int first, int* __restrict__ ndone) {
+    extern __shared__ double dsm[];
+    const int ld = a.ld, kcap = a.kcap;
+    PursuitSmem<T> S;
+    double* p = dsm;
+    double* Vb = p; p += (size_t)bm * ld;
+    S.v = Vb;
+    double* Gm = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
+    double* Ym = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
+    double* sc = p; p += 4 * BLOCK_MAX;
+    S.g = p; p += kcap;
+    S.hh = p; p += kcap;
+    S.ys = p; p += kcap;
+    S.y = p; p += kcap;
+    S.zs = p; p += kcap;
+    S.ssel = reinterpret_cast<int*>(p);
+    S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
+    double* Tsm = reinterpret_cast<double*>(S.colp + kcap);
+    __shared__ double red[NT / 32];
+    __shared__ int red_i[NT / 32];
+    __shared__ int s_cand[MAX_TAKE];
+    __shared__ double s_cval[MAX_TAKE];
+    __shared__ int s_keep[MAX_TAKE];
+    __shared__ int s_nkeep;
+    __shared__ int s_J[BLOCK_MAX];
+    __shared__ const T* s_Jcol[BLOCK_MAX];
+
+    const int sig = blockIdx.x, tid = threadIdx.x;
+    if (a.done[sig]) return;
+    const T* A = static_cast<const T*>(a.A);
+    const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
+    T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
+    S.Tg = a.Rf + (size_t)sig * kcap * kcap;
+    S.Tsm = t_in_smem ? Tsm : nullptr;
+    S.Tm = t_in_smem ? Tsm : S.Tg;
+    S.ldT = t_in_smem ? (kcap | 1) : kcap;
+    S.kcap = kcap;
+    S.red = red;
+    int t = first ? 0 : a.nnz[sig];
+    int flags = 0;
+    bool changed = false;
+    double nr2 = a.resnorm[sig] * a.resnorm[sig];
+    auto b_at = [&](int row) { return (double)b[row]; };
+    auto r_at = [&](int row) { return (double)r[row]; };
+    auto r_set = [&](int row, T val) { r[row] = val; };
+    for (int i = tid; i < t; i += NT) {
+        const int si = a.sel[(size_t)sig * kcap + i];
+        S.ssel[i] = si;
+        S.zs[i] = a.z[(size_t)sig * kcap + i];
+        S.colp[i] = A + (size_t)(si - a.idx_offset) * ld;
+    }
+    if (t_in_smem)
+        for (int e = tid; e < t * kcap; e += NT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * S.ldT] = S.Tg[e]; }
+    __syncthreads();
+
+    const size_t cbase = (size_t)sig * a.P * a.S;
+    select_candidates<NT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, k, s_cand, s_cval, red, red_i);
+    const int cap = kcap < a.M ? kcap : a.M;
+    flags |= append_list<T, NT>(S, t, s_cand, k, true, bm, cap, A, a.idx_offset, ld, Vb, Gm, Ym, sc, s_J, s_Jcol,
+                                b_at, r_at, r_set, nr2, changed);
+    if (!first && t > k) {
+        for (int i = tid; i < t; i += NT) {                       // x' = R^{-1} Q'b on the enlarged support
+            double acc = 0.0;
+            for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.zs[l], acc);
+            S.y[i] = fabs(acc);
+        }
+        __syncthreads();
+        const int drop = t - k;
+        for (int i = tid; i < t; i += NT) {                       // rank by (|x|, atom index): the `drop` smallest leave
+            const double vi = S.y[i];
+            const int ji = S.ssel[i];
+            int rank = 0;
+            for (int l = 0; l < t; ++l) rank += (S.y[l] < vi) || (S.y[l] == vi && S.ssel[l] < ji);
+            S.g[i] = rank < drop ? 0.0 : 1.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int n = 0;
+            for (int i = 0; i < t; ++i) if (S.g[i] != 0.0) s_keep[n++] = S.ssel[i];
+            s_nkeep = n;
+        }
+        __syncthreads();
+        // `solve!` on the kept atoms: fresh factorisation, residual restarted from b
+        double s2 = 0.0;
+        for (int row = tid; row < ld; row += NT) { const T e = b[row]; r[row] = e; s2 += (double)e * (double)e; }
+        nr2 = block_sum<NT>(s2, red);
+        t = 0;
+        __syncthreads();
+        flags |= append_list<T, NT>(S, t, s_keep, s_nkeep, false, bm, cap, A, a.idx_offset, ld, Vb, Gm, Ym, sc, s_J,
+                                    s_Jcol, b_at, r_at, r_set, nr2, changed);
+    }
+    for (int i = tid; i < t; i += NT) {                            // x_S = R^{-1} Q'b
+        double acc = 0.0;
+        for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.zs[l], acc);
+        a.x[(size_t)sig * kcap + i] = acc;
+        a.sel[(size_t)sig * kcap + i] = S.ssel[i];
+        a.z[(size_t)sig * kcap + i] = S.zs[i];
+    }
+    if (tid == 0) {
+        const double old = a.resnorm[sig], nr = sqrt(nr2);
+        a.nnz[sig] = t;
+        a.resnorm[sig] = nr;
+        a.iters[sig] += 1;
+        if (flags) a.flags[sig] |= flags;
+        // `if resnorm <= delta || oldnorm <= resnorm break` (twostage.jl:113-115); the new x is kept either way
+        if (!first && (nr <= delta || old <= nr)) { a.done[sig] = 1; if (ndone) atomicAdd(ndone, 1); }
+    }
+}
+
 // Matching pursuit step (/root/reference/src/matchingpursuit.jl:26-31): i = argmax |A'r|,
 // x[i] += <a_i, r>.  The reference recomputes r = b - A x from scratch at the next step; because
 // x changes in one entry only, that is r <- r - <a_i, r> a_i, which is what is applied here.
@@ -364,6 +527,36 @@ size_t omp_update_smem_bytes(int ld, int kcap) { return update_smem_bytes(ld, kc
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
     if (a.nsig <= 0) return cudaSuccess;
     return f32 ? launch_omp_update_t<float>(a, st, Acache) : launch_omp_update_t<double>(a, st, Acache);
+}
+
+int sp_block_width(int ld, int kcap) {
+    const bool t_in = kcap <= T_SMEM_MAX_K;
+    int bm = BLOCK_MAX;
+    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > 112 * 1024) --bm;      // 2 CTAs per SM when possible
+    if (bm < 2) { bm = 2; }
+    return bm;
+}
+
+size_t sp_update_smem_bytes(int ld, int kcap) {
+    return update_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K, sp_block_width(ld, kcap));
+}
+
+cudaError_t launch_sp_update(const StateArgs& a, bool f32, int k, double delta, int first, int* ndone, cudaStream_t st) {
+    if (a.nsig <= 0) return cudaSuccess;
+    const int t_in_smem = a.kcap <= T_SMEM_MAX_K ? 1 : 0;
+    const int bm = sp_block_width(a.ld, a.kcap);
+    const size_t smem = update_smem_bytes(a.ld, a.kcap, t_in_smem != 0, bm);
+    cudaError_t e;
+    if (f32) {
+        e = cudaFuncSetAttribute(sp_update_kernel<float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sp_update_kernel<float, 256><<<a.nsig, 256, smem, st>>>(a, t_in_smem, bm, k, delta, first, ndone);
+    } else {
+        e = cudaFuncSetAttribute(sp_update_kernel<double, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        sp_update_kernel<double, 256><<<a.nsig, 256, smem, st>>>(a, t_in_smem, bm, k, delta, first, ndone);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_ols_init(const StateArgs& a, double* colnorm2, cudaStream_t st) {

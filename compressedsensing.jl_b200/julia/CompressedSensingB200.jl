@@ -157,6 +157,31 @@ const ols = fr
 const oomp = fr
 const ormp = fr
 
+# sp  (src/twostage.jl:105-117) and oblivious  (src/oblivious.jl:3-8)
+function sp(A::MatOrDict, b::AbstractVecOrMat, k::Int, δ::Real = 1e-12; maxiter = 16k)
+    D = as_dictionary(A)
+    2k > D.M && error("2k = $(2k) > $(D.M) = length(b) is invalid for Subspace Pursuit")
+    B = signals(D, b); nsig = size(B, 2); stride = max(k, 1)
+    sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
+    nnz = Vector{Int64}(undef, nsig); res = Vector{Float64}(undef, nsig); its = Vector{Int64}(undef, nsig)
+    GC.@preserve B sel coef nnz res its check(ccall((:csb200_sp, libcsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Cdouble, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}),
+        D.handle, pointer(B), D.M, nsig, k, Float64(δ), Int64(maxiter), sel, coef, nnz, res, its))
+    xs = [to_sparse(D.N, view(sel, :, s), view(coef, :, s), nnz[s]) for s in 1:nsig]
+    return b isa AbstractVector ? xs[1] : xs
+end
+function oblivious(A::MatOrDict, b::AbstractVecOrMat, k::Int)
+    D = as_dictionary(A)
+    B = signals(D, b); nsig = size(B, 2); stride = max(k, 1)
+    sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
+    nnz = Vector{Int64}(undef, nsig); res = Vector{Float64}(undef, nsig)
+    GC.@preserve B sel coef nnz res check(ccall((:csb200_oblivious, libcsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}),
+        D.handle, pointer(B), D.M, nsig, k, sel, coef, nnz, res))
+    xs = [to_sparse(D.N, view(sel, :, s), view(coef, :, s), nnz[s]) for s in 1:nsig]   # length N (the reference: length M)
+    return b isa AbstractVector ? xs[1] : xs
+end
+
 # mp  (src/matchingpursuit.jl:34-40); x is an optional warm start (single-signal form)
 function mp(A::MatOrDict, b::AbstractVector, k::Int, x::SparseVector = spzeros(size(A, 2)))
     D = as_dictionary(A)

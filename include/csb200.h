@@ -105,6 +105,17 @@ int csb200_batch_mp(csb200_batch* batch, int64_t iters, const int64_t* x0_idx, c
  * dictionaries only (CSB200_ERR_UNSUPPORTED otherwise).  Outputs as for omp (selection order). */
 int csb200_batch_fr(csb200_batch* batch, int64_t k, double max_eps, double min_delta);
 
+/* Subspace pursuit and oblivious selection.
+ *   sp        : `sp(A, b, k, delta = 1e-12; maxiter = 16k)`, src/twostage.jl:105-117 -- initial top-k acquisition,
+ *               then up to maxiter `update!`s (:94-103: add the top-k of |A'r|, least squares on <= 2k atoms, keep the
+ *               k largest |x|, least squares again) until ||r|| <= delta or ||r|| stops decreasing, per signal.
+ *               Needs 2k <= M (the reference errors otherwise) and a batch with max_sparsity >= 2k; k <= 256.
+ *   oblivious : `oblivious(A, b, k)`, src/oblivious.jl:3-8 -- the k atoms most correlated with b and their
+ *               least-squares coefficients (k <= min(M, 256)).
+ * Outputs as for omp; a signal's support is reported in the order the final factorisation appended it. */
+int csb200_batch_sp(csb200_batch* batch, int64_t k, double delta, int64_t maxiter);
+int csb200_batch_oblivious(csb200_batch* batch, int64_t k);
+
 /* Copy results device -> host.  `stride` = slots per signal in sel_idx / coef (>= the k or
  * iters of the last solve).  Any output pointer may be NULL.
  *   sel_idx[s*stride + j]  j-th atom appended for signal s, in SELECTION order (-1 padded).
@@ -137,6 +148,10 @@ int csb200_gomp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, 
                 double eps, int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
 int csb200_fr(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double max_eps,
               double min_delta, int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+int csb200_sp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double delta,
+              int64_t maxiter, int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+int csb200_oblivious(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k,
+                     int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm);
 int csb200_mp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k,
               const int64_t* x0_idx, const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride,
               int64_t* sel_idx, double* coef, double* resnorm);

@@ -43,7 +43,7 @@ from .updatable_qr import UpdatableQR
 __all__ = [
     "SparseVec", "Trace", "mp", "omp", "gomp", "residual", "argmaxinner", "argmaxinner_k",
     "sparse_vector", "sparse_data", "perturb", "eps_of", "fr", "ols", "oomp", "ormp", "forward_delta", "ols_rescaling",
-    "findmax_first",
+    "findmax_first", "sp", "oblivious",
 ]
 
 
@@ -399,6 +399,75 @@ def fr(A: np.ndarray, b: np.ndarray, max_eps: float = 0.0, min_delta: float = 0.
 
 
 ols = oomp = ormp = fr
+
+
+# ----------------------------------------------------------------------------------------
+# Oblivious selection and subspace pursuit  (`src/oblivious.jl:3-8`, `src/twostage.jl:49-123`)  -- SURVEY.md 8(f) rank 2
+# ----------------------------------------------------------------------------------------
+def _dense_ls(A: np.ndarray, nzind: Sequence[int], b: np.ndarray) -> List[float]:
+    """`solve!(P, x)` (`src/twostage.jl:120-123`) = `ldiv!(x.nzval, qr!(A[:, nzind]), b)` / `A[:, nzind] \\ b`."""
+    y, *_ = np.linalg.lstsq(A[:, np.asarray(nzind, dtype=np.int64)], np.asarray(b, dtype=A.dtype), rcond=None)
+    return [float(v) for v in np.asarray(y, dtype=np.float64)]
+
+
+def oblivious(A: np.ndarray, b: np.ndarray, k: int) -> SparseVec:
+    """`oblivious(A, b, k)` (`src/oblivious.jl:3-8`).  The reference sizes its result `spzeros(size(b))` (length M,
+    a latent bug for indices > M); the restatement uses length N like every other algorithm."""
+    _check_finite(A, b)
+    nzind = argmaxinner_k(A, np.asarray(b, dtype=A.dtype), k)             # :4  partialsortperm(abs.(A'b), 1:k, rev=true)
+    x = SparseVec(A.shape[1])
+    for j in nzind:
+        x.setindex(j, np.nan)
+    x.nzval = _dense_ls(A, x.nzind, b)                                    # :6
+    return x
+
+
+def _sp_acquisition(A, b, x: SparseVec, k: int, trace: Optional[Trace]) -> None:
+    """`sp_acquisition!(P, x, k)` (`src/twostage.jl:87-92`)."""
+    r = residual(A, x, b)                                                 # :88
+    idx = argmaxinner_k(A, r, k, trace)                                   # :89
+    for j in idx:
+        x.setindex(j, np.nan)                                             # :90  (an active atom is overwritten, not duplicated)
+    x.nzval = _dense_ls(A, x.nzind, b)                                    # :91
+    if trace is not None:
+        trace.selected.append(list(idx))
+
+
+def sp(A: np.ndarray, b: np.ndarray, k: int, delta: float = 1e-12, maxiter: Optional[int] = None,
+       trace: Optional[Trace] = None) -> SparseVec:
+    """`sp(A, b, k, δ = 1e-12; maxiter = 16k)` (`src/twostage.jl:105-117`) with `update!(P::SP, x)` (:94-103)."""
+    _check_finite(A, b)
+    M, N = A.shape
+    if 2 * k > M:
+        raise ValueError(f"2k = {2 * k} > {M} = length(b) is invalid for Subspace Pursuit")   # :62
+    maxiter = 16 * k if maxiter is None else maxiter
+    x = SparseVec(N)
+    _sp_acquisition(A, b, x, k, trace)                                    # :108
+    resnorm = float(np.linalg.norm(residual(A, x, b)))                    # :109
+    if trace is not None:
+        trace.resnorm.append(resnorm)
+    for _ in range(maxiter):                                              # :110
+        oldnorm = resnorm
+        if x.nnz() != k:
+            raise ValueError(f"nnz(x) = {x.nnz()} ≠ {k} = k")             # :95
+        _sp_acquisition(A, b, x, k, trace)                                # :96
+        absval = np.abs(np.asarray(x.nzval))
+        ndrop = x.nnz() - k
+        order = np.lexsort((np.arange(absval.size), absval))
+        drop = order[:ndrop]                                              # :97 partialsortperm: smallest, ties -> lower position
+        if trace is not None and 0 < ndrop < absval.size:                 # how decisive the pruning was
+            lo, hi = float(absval[order[ndrop - 1]]), float(absval[order[ndrop]])
+            trace.margin.append((hi - lo) / hi if hi > 0 else 0.0)
+        for i in sorted(drop.tolist(), reverse=True):                     # :98-100
+            del x.nzind[i]; del x.nzval[i]
+        x.nzval = _dense_ls(A, x.nzind, b)                                # :101
+        resnorm = float(np.linalg.norm(residual(A, x, b)))                # :112
+        if trace is not None:
+            trace.resnorm.append(resnorm); trace.iterations += 1
+            trace.added.append(list(x.nzind))
+        if resnorm <= delta or oldnorm <= resnorm:                        # :113
+            break
+    return x
 
 
 # ----------------------------------------------------------------------------------------

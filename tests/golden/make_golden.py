@@ -38,6 +38,7 @@ def build(name, algo, M, N, k, B, seed, dtype=np.float64, l=None, noise=0.0, eps
     nnz = np.zeros(B, dtype=np.int64)
     resn = np.zeros(B)
     margin = np.zeros(B)
+    iters_out = np.zeros(B, dtype=np.int64)
     for s in range(B):
         t = po.Trace()
         if algo == "omp":
@@ -46,21 +47,28 @@ def build(name, algo, M, N, k, B, seed, dtype=np.float64, l=None, noise=0.0, eps
             x = po.gomp(A, Bm[:, s], l, k, eps=eps, trace=t)
         elif algo == "fr":
             x = po.fr(A, Bm[:, s], max_eps, min_delta, k, trace=t)
+        elif algo == "sp":
+            x = po.sp(A, Bm[:, s], k, delta=(1e-12 if eps is None else eps), trace=t)
+        elif algo == "oblivious":
+            x = po.oblivious(A, Bm[:, s], k)
         else:
             x = po.mp(A, Bm[:, s], k, trace=t)
         n = x.nnz()
         nnz[s] = n
         nzind[s, :n] = x.nzind
         nzval[s, :n] = x.nzval
-        o = t.order()
+        o = t.order() if algo not in ("sp", "oblivious") else []
+        iters_out[s] = t.iterations
         if algo != "mp":
             order[s, :len(o)] = o
         resn[s] = t.resnorm[-1] if t.resnorm else float(np.linalg.norm(Bm[:, s]))
+        if algo == "oblivious":
+            resn[s] = float(np.linalg.norm(po.residual(A, x, Bm[:, s])))
         margin[s] = min(t.margin) if t.margin else 1.0
     meta = dict(algo=algo, M=M, N=N, k=k, B=B, seed=seed, dtype=np.dtype(dtype).name, l=l, noise=noise, eps=eps,
                 planted=planted, colscale=colscale, max_eps=max_eps, min_delta=min_delta)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), A=A, B=Bm, nzind=nzind, nzval=nzval, order=order, nnz=nnz,
-                        resnorm=resn, margin=margin, meta=json.dumps(meta))
+                        resnorm=resn, margin=margin, iters=iters_out, meta=json.dumps(meta))
     print(name, "min margin", margin.min(), "max resnorm", resn.max())
 
 
@@ -72,9 +80,21 @@ def build_fr():
     build("fr_stop_delta_70x130", "fr", 70, 130, 20, 8, seed=1253, planted=6, noise=5e-3, min_delta=0.05)
 
 
+def build_sp():
+    """Subspace pursuit / oblivious selection (src/twostage.jl, src/oblivious.jl)."""
+    build("sp_ref_32x48_k3", "sp", 32, 48, 3, 40, seed=1260)                             # test/twostage.jl:42-46
+    build("sp_noisy_64x256_k16", "sp", 64, 256, 16, 16, seed=1261, noise=1e-2, eps=1e-2)  # several update!s per signal
+    build("sp_noisy_96x400_k24", "sp", 96, 400, 24, 8, seed=1262, noise=1e-2)
+    build("sp_f32_64x160_k5", "sp", 64, 160, 5, 8, seed=1263, dtype=np.float32, noise=1e-2, eps=1e-2)
+    build("oblivious_70x130_k9", "oblivious", 70, 130, 9, 8, seed=1264, noise=1e-2)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "fr":
         build_fr()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "sp":
+        build_sp()
         sys.exit(0)
     build("omp_c1_128x256_k8", "omp", 128, 256, 8, 4, seed=1234)                      # BASELINE config 1 (KAT-1)
     build("omp_c1_noisy", "omp", 128, 256, 8, 4, seed=1235, noise=5e-3)                # KAT-2

@@ -119,6 +119,8 @@ def test_golden(cs, path, impl, update, monkeypatch):
     meta = json.loads(str(z["meta"]))
     if meta["algo"] == "fr" and (impl, update) != ("gemm", "cta"):
         pytest.skip("forward regression has one kernel combination (DMMA pass + CTA update)")
+    if meta["algo"] in ("sp", "oblivious") and (update != "cta" or impl is None):
+        pytest.skip("sp / oblivious have their own update kernel; correlation kernel: gemm or gemv")
     A, Bm = np.asfortranarray(z["A"]), np.asfortranarray(z["B"])
     f32 = A.dtype == np.float32
     if f32 and impl == "gemm":
@@ -134,6 +136,12 @@ def test_golden(cs, path, impl, update, monkeypatch):
             batch.gomp(meta["l"], k, eps)
         elif meta["algo"] == "fr":
             batch.fr(k, meta["max_eps"], meta["min_delta"])
+        elif meta["algo"] == "sp":
+            batch.close()
+            batch = _batch(cs, D, Bm, 2 * k, impl)
+            batch.sp(k, 1e-12 if meta["eps"] is None else meta["eps"])
+        elif meta["algo"] == "oblivious":
+            batch.oblivious(k)
         else:
             batch.mp(k)
         sel, coef, nnz, res, its = batch.download(k)
@@ -150,7 +158,11 @@ def test_golden(cs, path, impl, update, monkeypatch):
             assert _close(val, z["nzval"][s, :n], 1e-9 if not f32 else RTOL32), s
             continue
         assert int(nnz[s]) == n, (s, nnz[s], n)
-        assert sel[s, :n].tolist() == z["order"][s, :n].tolist(), (s, "selection sequence")
+        if meta["algo"] in ("sp", "oblivious"):             # no selection sequence: the support is a set per update!
+            if meta["algo"] == "sp":
+                assert int(its[s]) == int(z["iters"][s]) + 1, (s, its[s], z["iters"][s])   # + the initial acquisition
+        else:
+            assert sel[s, :n].tolist() == z["order"][s, :n].tolist(), (s, "selection sequence")
         idx, val = _sorted(sel[s], coef[s], n)
         assert idx.tolist() == z["nzind"][s, :n].tolist()
         assert _close(val, z["nzval"][s, :n], rtol), (s, val, z["nzval"][s, :n])
@@ -291,6 +303,59 @@ def test_fr_midsize_batch_vs_oracle(cs, po):
         assert sel[s, :k].tolist() == t.order(), (s, min(t.margin))
         idx, val = _sorted(sel[s], coef[s], k)
         assert _close(val, ref.nzval, RTOL64) and abs(res[s] - t.resnorm[-1]) < 1e-10
+
+
+# ------------------------------------------------------------------ subspace pursuit / oblivious
+def test_sp_and_oblivious_call_surface(cs, po):
+    rng = np.random.default_rng(31)
+    A, x0, b = po.sparse_data(rng, 64, 256, 16)
+    y = po.perturb(rng, b, 1e-2)
+    with cs.Dictionary(A) as D:
+        for args in [(16,), (16, 1e-2), (16, 1e-12, 1), (16, 1e-12, 0), (5,)]:
+            got = cs.sp(D, y, *args)
+            ref = po.sp(A, y, *args)
+            assert got.nzind.tolist() == ref.nzind, args
+            assert _close(got.nzval, ref.nzval, RTOL64), args
+        got, ref = cs.oblivious(D, y, 7), po.oblivious(A, y, 7)
+        assert got.nzind.tolist() == ref.nzind and _close(got.nzval, ref.nzval, RTOL64)
+        with pytest.raises(ValueError, match="invalid for Subspace Pursuit"):
+            cs.sp(D, y, 33)
+        Bm = np.asfortranarray(np.stack([y, b, 0.5 * (y + b)], axis=1))
+        out = cs.sp(D, Bm, 16)
+        for s in range(3):
+            ref = po.sp(A, Bm[:, s], 16)
+            assert out[s].nzind.tolist() == ref.nzind and _close(out[s].nzval, ref.nzval, 1e-9)
+
+
+def test_sp_midsize_batch_vs_oracle(cs, po):
+    """Mid-size batch (DMMA correlation path, block appends, k > 64-atom candidate blocks exercised via N ragged):
+    per-signal iteration counts, supports and coefficients against the oracle; bit-identical re-solve."""
+    rng = np.random.default_rng(177)
+    M, N, k, B = 160, 1000, 30, 96
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, B, noise=1e-2)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 2 * k) as batch:
+        batch.upload(Bm)
+        batch.sp(k)
+        sel, coef, nnz, res, its = batch.download(k)
+        batch.sp(k)
+        sel2, coef2, *_ = batch.download(k)
+        batch.oblivious(k)
+        osel, ocoef, onnz, ores, _ = batch.download(k)
+    assert np.array_equal(sel, sel2) and np.array_equal(coef, coef2)
+    assert (nnz == k).all() and len(set(its.tolist())) > 1            # signals stop after different numbers of update!s
+    for s in range(0, B, 6):
+        t = po.Trace()
+        ref = po.sp(A, Bm[:, s], k, trace=t)
+        if min(t.margin) < 1e-7:
+            continue
+        idx, val = _sorted(sel[s], coef[s], k)
+        assert idx.tolist() == ref.nzind, (s, min(t.margin))
+        assert _close(val, ref.nzval, 1e-9) and abs(res[s] - t.resnorm[-1]) < 1e-9
+        assert int(its[s]) == t.iterations + 1
+        ref = po.oblivious(A, Bm[:, s], k)
+        idx, val = _sorted(osel[s], ocoef[s], k)
+        assert idx.tolist() == ref.nzind and _close(val, ref.nzval, 1e-9)
 
 
 # ------------------------------------------------------------------ mid-size parity and properties

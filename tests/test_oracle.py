@@ -240,6 +240,39 @@ def test_fr_stopping_rules_and_findmax():
     assert t.order() == [1, 2, 4]
 
 
+# ------------------------------------------------------------------ subspace pursuit / oblivious
+@pytest.mark.parametrize("seed", SEEDS)
+def test_sp_properties(seed):
+    """test/twostage.jl:42-52: `sp(A, b, k)` recovers support and coefficients; `sp(A, y, k, δ)` within 3δ."""
+    A, x, b, y = _problem(seed)
+    xs = po.sp(A, b, 3)
+    assert xs.nzind == x.nzind
+    assert np.allclose(xs.nzval, x.nzval, rtol=np.sqrt(np.finfo(float).eps))
+    xs = po.sp(A, y, 3, 1e-2)
+    assert xs.nzind == x.nzind
+    assert np.linalg.norm(np.array(xs.nzval) - np.array(x.nzval)) <= 3e-2
+
+
+def test_sp_semantics():
+    rng = np.random.default_rng(4)
+    A, x0, b = po.sparse_data(rng, 64, 256, 16)
+    y = po.perturb(rng, b, 1e-2)
+    t = po.Trace()
+    xs = po.sp(A, y, 16, trace=t)
+    assert xs.nnz() == 16 and t.iterations >= 2
+    # the loop stops at the first update! that does not decrease ||r|| (twostage.jl:113) and keeps THAT iterate
+    assert t.resnorm[-1] >= t.resnorm[-2] or t.resnorm[-1] <= 1e-12
+    assert all(t.resnorm[i + 1] < t.resnorm[i] for i in range(len(t.resnorm) - 2))
+    assert po.sp(A, y, 16, maxiter=0).nzind == po.oblivious(A, y, 16).nzind       # initial acquisition == oblivious
+    with pytest.raises(ValueError, match="invalid for Subspace Pursuit"):
+        po.sp(A, y, 33)
+    xo = po.oblivious(A, y, 5)
+    top = np.argsort(-np.abs(A.T @ y), kind="stable")[:5]
+    assert xo.nzind == sorted(top.tolist())
+    c, *_ = np.linalg.lstsq(A[:, xo.nzind], y, rcond=None)
+    assert np.allclose(xo.nzval, c)
+
+
 def test_golden_fixtures_reproduce():
     """The committed fixtures (tests/golden/make_golden.py) are what the oracle produces today."""
     files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
@@ -256,6 +289,10 @@ def test_golden_fixtures_reproduce():
                 x = po.gomp(A, Bm[:, s], meta["l"], meta["k"], eps=meta.get("eps"))
             elif meta["algo"] == "fr":
                 x = po.fr(A, Bm[:, s], meta["max_eps"], meta["min_delta"], meta["k"])
+            elif meta["algo"] == "sp":
+                x = po.sp(A, Bm[:, s], meta["k"], delta=(1e-12 if meta["eps"] is None else meta["eps"]))
+            elif meta["algo"] == "oblivious":
+                x = po.oblivious(A, Bm[:, s], meta["k"])
             else:
                 x = po.mp(A, Bm[:, s], meta["k"])
             n = int(z["nnz"][s])

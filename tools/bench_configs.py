@@ -116,6 +116,27 @@ def fr2(cs, dev, args):
                 corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
 
 
+def sp2(cs, dev, args):
+    """Subspace pursuit at the config-2 shape, noisy signals (several update!s per signal)."""
+    M, N, k, B = 1024, 8192, 32, int(16384 * args.scale)
+    A, Bm, idx = make_problem(M, N, k, B, np.float64, dev, noise=1e-2)
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 2 * k) as b:
+        b.upload(Bm)
+        b.sp(k, 1e-12, 2)
+        b.profile(True)
+        b.sp(k)
+        ms = b.last_solve_ms()
+        corr_ms, n, other = b.corr_time()
+        sel, coef, nnz, res, its = b.download(k)
+    rec = float(np.mean([(set(idx[s]) <= set(sel[s, :nnz[s]])) for s in range(0, B, 64)]))
+    tf = 2.0 * M * N * B * n / corr_ms / 1e9
+    return dict(config="sp 1024x8192 k=32 f64 noisy", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
+                corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+                corr_share=corr_ms / ms, update_ms_per_launch=(ms - corr_ms) / max(other, 1),
+                updates_per_signal_mean=float(its.mean()), updates_per_signal_max=int(its.max()),
+                support_recovered_frac=rec, median_resnorm=float(np.median(res)))
+
+
 def c5(cs, dev, args):
     M, N, iters, B = 4096, 65536, int(200 * args.scale), 4096
     A, Bm, idx = make_problem(M, N, 32, B, np.float64, dev, noise=5e-3)
@@ -195,13 +216,13 @@ def c4(cs, dev, args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5", "fr2"])
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5", "fr2", "sp2"])
     ap.add_argument("--scale", type=float, default=1.0)
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     cs = ge.load_package()
-    res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "fr2": fr2}[a.config](cs, dev, a)
+    res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "fr2": fr2, "sp2": sp2}[a.config](cs, dev, a)
     if res is not None:
         print(json.dumps(res))
