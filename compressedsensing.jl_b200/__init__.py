@@ -32,7 +32,8 @@ import numpy as np
 __all__ = [
     "SparseVector", "Dictionary", "Batch", "omp", "gomp", "mp", "lib", "LIB_PATH", "CSB200Error",
     "device_count", "F64", "F32", "ShardComm", "omp_sharded", "shard_range", "owner_of", "pick_global",
-    "exchange_unique_id", "assemble_csc", "fr", "ols", "oomp", "ormp", "sp", "oblivious",
+    "exchange_unique_id", "assemble_csc", "fr", "ols", "oomp", "ormp", "sp", "oblivious", "colnorms", "normalize",
+    "cumbabel", "babel", "coherence",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -95,6 +96,8 @@ def _load() -> ctypes.CDLL:
                                 f64p, i64p]),
         "csb200_mp": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, i64p, f64p, i64p, c_int64, i64p, f64p,
                               f64p]),
+        "csb200_dict_colnorms": (c_int, [c_void_p, f64p]),
+        "csb200_dict_cumbabel": (c_int, [c_void_p, c_int64, f64p]),
         "csb200_assemble_csc": (c_int, [c_int64, c_int64, i64p, f64p, i64p, c_int64, i64p, i64p, f64p]),
         "csb200_comm_unique_id": (c_int, [c_void_p]),
         "csb200_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
@@ -118,7 +121,8 @@ EXPORTED_SYMBOLS = [
     "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
     "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp",
     "csb200_assemble_csc", "csb200_comm_unique_id", "csb200_batch_fr", "csb200_fr",
-    "csb200_batch_sp", "csb200_batch_oblivious", "csb200_sp", "csb200_oblivious",
+    "csb200_batch_sp", "csb200_batch_oblivious", "csb200_sp", "csb200_oblivious", "csb200_dict_colnorms",
+    "csb200_dict_cumbabel",
     "csb200_comm_create", "csb200_comm_destroy", "csb200_omp_sharded", "csb200_debug_corr_topk",
     "csb200_debug_get_residual",
 ]
@@ -549,6 +553,48 @@ def mp(A, b, k: int, x=None, device: int = 0):
         return rc
 
     return _solve(A, b, device, call, stride, merge=merge)
+
+
+# ------------------------------------------------------------------------------------------------
+# Dictionary analysis (`src/util.jl:2, 59-61, 96-117`)
+def colnorms(A, device: int = 0) -> np.ndarray:
+    """`colnorms(A)` (`src/util.jl:2`): 2-norm of every column."""
+    D, owned = _dictionary(A, device)
+    try:
+        out = np.empty(D.N, dtype=np.float64)
+        _check(lib.csb200_dict_colnorms(D._h, _f64p(out)))
+    finally:
+        if owned:
+            D.close()
+    return out
+
+
+def normalize(A: np.ndarray, device: int = 0) -> np.ndarray:
+    """`normalize!(A)` (`src/util.jl:59-61`): `A ./= colnorms(A)'`, in place on the caller's (host) matrix."""
+    A /= colnorms(A, device).astype(A.dtype)[None, :]
+    return A
+
+
+def cumbabel(A, k: int, device: int = 0) -> np.ndarray:
+    """`cumbabel(A, k)` (`src/util.jl:106-117`): Babel function values mu_1(1..k)."""
+    D, owned = _dictionary(A, device)
+    try:
+        mu = np.empty(int(k), dtype=np.float64)
+        _check(lib.csb200_dict_cumbabel(D._h, int(k), _f64p(mu)))
+    finally:
+        if owned:
+            D.close()
+    return mu.astype(D.dtype)             # `zeros(eltype(A), k)` (:107)
+
+
+def babel(A, k: int, device: int = 0):
+    """`babel(A, k) = cumbabel(A, k)[k]` (`src/util.jl:101`)."""
+    return cumbabel(A, k, device)[k - 1]
+
+
+def coherence(A, device: int = 0):
+    """Mutual coherence, `coherence(A) = babel(A, 1)` (`src/util.jl:98`)."""
+    return babel(A, 1, device)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -999,6 +999,65 @@ int csb200_mp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64
     return rc;
 }
 
+// ---- dictionary analysis -------------------------------------------------
+int csb200_dict_colnorms(csb200_dict* d, double* out) {
+    if (!d || !out) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(d->mu);
+    int rc = set_device(d);
+    if (rc) return rc;
+    double* dn = nullptr;
+    CU_TRY(cudaMalloc(&dn, (size_t)d->N * sizeof(double)));
+    cudaError_t e = launch_colnorms(d->dA, d->dtype == CSB200_F32, (int)d->ld, (int)d->N, dn, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dn, (size_t)d->N * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dn);
+    if (e != cudaSuccess) return fail_cuda(e, "colnorms");
+    return CSB200_OK;
+}
+
+// `cumbabel(A, k)` (src/util.jl:106-117): the atoms themselves are the right-hand sides of the batched correlation
+// pass (|A'A| row top-(k+1) from the fused epilogue), processed in chunks of at most 16 384 atoms.
+int csb200_dict_cumbabel(csb200_dict* d, int64_t k, double* mu_out) {
+    if (!d || !mu_out || k < 1) return CSB200_ERR_INVALID_ARG;
+    if (d->n_total != d->N) { g_last_error = "cumbabel needs an unsharded dictionary"; return CSB200_ERR_UNSUPPORTED; }
+    if (k > d->N) return CSB200_ERR_INVALID_ARG;                       // partialsort!(inner, 1:k) would throw
+    if (k + 1 > SP_MAX_K) { g_last_error = "cumbabel: k > 255 is not supported"; return CSB200_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lk(d->mu);
+    int rc = set_device(d);
+    if (rc) return rc;
+    if ((size_t)d->ld * sizeof(double) > MAX_DYN_SMEM) { g_last_error = "signal length exceeds the GEMV kernel's shared memory"; return CSB200_ERR_UNSUPPORTED; }
+    const int64_t chunk = d->N < 16384 ? d->N : 16384;
+    csb200_batch* b = nullptr;
+    if ((rc = csb200_batch_create(d, chunk, 1, &b))) return rc;
+    double* dmu = nullptr;
+    cudaError_t e = cudaMalloc(&dmu, (size_t)k * sizeof(double));
+    if (e != cudaSuccess) { csb200_batch_destroy(b); return fail_cuda(e, "cudaMalloc"); }
+    const int S = (int)(k + 1 < PBLK ? k + 1 : PBLK);
+    const size_t es = d->esize();
+    do {
+        e = cudaMemsetAsync(dmu, 0, (size_t)k * sizeof(double), b->stream);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "memset"); break; }
+        for (int64_t c0 = 0; c0 < d->N && !rc; c0 += chunk) {
+            const int64_t nc = d->N - c0 < chunk ? d->N - c0 : chunk;
+            // residual matrix := the chunk's atoms (padded rows are zero in the dictionary already)
+            e = cudaMemcpyAsync(b->dR, (const char*)d->dA + (size_t)c0 * d->ld * es, (size_t)nc * d->ld * es,
+                                cudaMemcpyDeviceToDevice, b->stream);
+            if (e != cudaSuccess) { rc = fail_cuda(e, "copy atoms"); break; }
+            b->nsig = nc; b->has_map = false; b->cur_P = 0;
+            if ((rc = ensure_signal_map(b))) break;
+            if ((rc = run_corr(b, S, IMPL_AUTO))) break;
+            e = launch_babel_reduce(state_args(b, S, S, 0.0, 0), (int)k, (int)c0, dmu, b->stream);
+            if (e != cudaSuccess) { rc = fail_cuda(e, "babel_reduce"); break; }
+        }
+        if (rc) break;
+        e = cudaMemcpyAsync(mu_out, dmu, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, b->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+        if (e != cudaSuccess) rc = fail_cuda(e, "cumbabel");
+    } while (0);
+    cudaFree(dmu);
+    csb200_batch_destroy(b);
+    return rc;
+}
+
 // ---- batched result format ---------------------------------------------------------------------
 int csb200_assemble_csc(int64_t nsig, int64_t stride, const int64_t* sel_idx, const double* coef, const int64_t* nnz,
                         int64_t index_base, int64_t* colptr, int64_t* rowval, double* nzval) {

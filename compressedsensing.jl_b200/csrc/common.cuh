@@ -104,6 +104,9 @@ cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride,
 constexpr int SP_MAX_K = 256;
 cudaError_t launch_sp_update(const StateArgs& a, bool f32, int k, double delta, int first, int* ndone, cudaStream_t st);
 size_t sp_update_smem_bytes(int ld, int kcap);
+// dictionary analysis (src/util.jl:2, 96-117): column 2-norms; Babel-function fold over a chunk of atoms
+cudaError_t launch_colnorms(const void* A, bool f32, int ld, int N, double* out, cudaStream_t st);
+cudaError_t launch_babel_reduce(const StateArgs& a, int k, int col0, double* mu, cudaStream_t st);
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx, const double* x0_val,
                                 const int* x0_nnz, int x0_stride, cudaStream_t st);

@@ -458,16 +458,41 @@ __global__ void __launch_bounds__(UT) topk_from_partials_kernel(StateArgs a, int
     }
 }
 
-// ||a_j||^2 for every atom, one warp per column (`colnorms(A)` / `sum!(abs2, ...)`, src/forward.jl:28,105).
-__global__ void __launch_bounds__(256) colnorm2_kernel(const double* __restrict__ A, int ld, int N, double* __restrict__ out) {
+// ||a_j||^2 for every atom, one warp per column (`colnorms(A)` / `sum!(abs2, ...)`, src/util.jl:2, src/forward.jl:28,105).
+template <typename T>
+__global__ void __launch_bounds__(256) colnorm2_kernel(const T* __restrict__ A, int ld, int N, double* __restrict__ out, int take_sqrt) {
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= N) return;
-    const double* a = A + (size_t)j * ld;
+    const T* a = A + (size_t)j * ld;
     double s = 0.0;
-    for (int row = lane; row < ld; row += 32) s = fma(a[row], a[row], s);
+    for (int row = lane; row < ld; row += 32) { const double e = (double)a[row]; s = fma(e, e, s); }
     s = warp_sum(s);
-    if (lane == 0) out[j] = s;
+    if (lane == 0) out[j] = take_sqrt ? sqrt(s) : s;
 }
+
+// Babel function (`cumbabel`, src/util.jl:106-117).  "Signal" s of the batch is atom col0 + s of the dictionary and its
+// candidates are the per-block top-(k+1) of |A'a_i|: merge them, drop the atom itself (`inner[i] = 0`), keep the k
+// largest, prefix-sum them and fold into mu[0..k) with max (non-negative doubles order like their bit patterns).
+__global__ void __launch_bounds__(UT) babel_reduce_kernel(StateArgs a, int k, int col0, unsigned long long* __restrict__ mu) {
+    __shared__ double red[UW];
+    __shared__ int red_i[UW];
+    __shared__ int s_cand[MAX_TAKE];
+    __shared__ double s_cval[MAX_TAKE];
+    const int sig = blockIdx.x;
+    const size_t cbase = (size_t)sig * a.P * a.S;
+    select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, k + 1, s_cand, s_cval, red, red_i);
+    if (threadIdx.x == 0) {
+        double run = 0.0;
+        int out = 0;
+        for (int c = 0; c < k + 1 && out < k; ++c) {
+            if (s_cand[c] == col0 + sig) continue;                 // inner product with self does not count
+            if (s_cand[c] >= 0) run += s_cval[c];                  // fewer than k other atoms: the tail adds zeros
+            atomicMax(mu + out, (unsigned long long)__double_as_longlong(run));
+            ++out;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) ols_init_kernel(const double* __restrict__ cn2, int N, long long ldr,
                                                        double* __restrict__ resc, size_t nq, double* __restrict__ qnew) {
     const size_t stride = (size_t)gridDim.x * 256, t0 = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -559,9 +584,22 @@ cudaError_t launch_sp_update(const StateArgs& a, bool f32, int k, double delta, 
     return cudaGetLastError();
 }
 
+cudaError_t launch_colnorms(const void* A, bool f32, int ld, int N, double* out, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    if (f32) colnorm2_kernel<float><<<(N + 7) / 8, 256, 0, st>>>(static_cast<const float*>(A), ld, N, out, 1);
+    else colnorm2_kernel<double><<<(N + 7) / 8, 256, 0, st>>>(static_cast<const double*>(A), ld, N, out, 1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_babel_reduce(const StateArgs& a, int k, int col0, double* mu, cudaStream_t st) {
+    if (a.nsig <= 0) return cudaSuccess;
+    babel_reduce_kernel<<<a.nsig, UT, 0, st>>>(a, k, col0, reinterpret_cast<unsigned long long*>(mu));
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ols_init(const StateArgs& a, double* colnorm2, cudaStream_t st) {
     if (a.nsig <= 0) return cudaSuccess;
-    colnorm2_kernel<<<(a.N + 7) / 8, 256, 0, st>>>(static_cast<const double*>(a.A), a.ld, a.N, colnorm2);
+    colnorm2_kernel<double><<<(a.N + 7) / 8, 256, 0, st>>>(static_cast<const double*>(a.A), a.ld, a.N, colnorm2, 0);
     ols_init_kernel<<<148 * 8, 256, 0, st>>>(colnorm2, a.N, a.ldr, a.resc, (size_t)a.nsig * a.ld, a.qnew);
     return cudaGetLastError();
 }

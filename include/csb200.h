@@ -156,6 +156,13 @@ int csb200_mp(csb200_dict* dict, const void* Bmat, int64_t ldb, int64_t nsig, in
               const int64_t* x0_idx, const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride,
               int64_t* sel_idx, double* coef, double* resnorm);
 
+/* ---- dictionary analysis (src/util.jl:2, 96-117) ----------------------------
+ * colnorms : out[j] = ||A[:, j]||_2 (what `normalize!` divides by, src/util.jl:59-61).
+ * cumbabel : mu[i-1] = Babel function mu_1(i) for i = 1..k -- max over atoms of the sum of the i largest
+ *            |<a_j, a_l>|, l != j; `coherence(A)` = `babel(A, 1)` = mu[0].  1 <= k <= min(N, 255). */
+int csb200_dict_colnorms(csb200_dict* dict, double* out);
+int csb200_dict_cumbabel(csb200_dict* dict, int64_t k, double* mu);
+
 /* ---- batched result format (host-side helper, no GPU work) ---------------------------------
  * Assemble the selection-order outputs of csb200_omp / csb200_gomp (sel_idx, coef, nnz with `stride` slots per
  * signal) into compressed-sparse-column arrays of the N x nsig coefficient matrix -- Julia's SparseMatrixCSC

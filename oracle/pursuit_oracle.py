@@ -43,7 +43,7 @@ from .updatable_qr import UpdatableQR
 __all__ = [
     "SparseVec", "Trace", "mp", "omp", "gomp", "residual", "argmaxinner", "argmaxinner_k",
     "sparse_vector", "sparse_data", "perturb", "eps_of", "fr", "ols", "oomp", "ormp", "forward_delta", "ols_rescaling",
-    "findmax_first", "sp", "oblivious",
+    "findmax_first", "sp", "oblivious", "colnorms", "normalize", "cumbabel", "babel", "coherence",
 ]
 
 
@@ -468,6 +468,41 @@ def sp(A: np.ndarray, b: np.ndarray, k: int, delta: float = 1e-12, maxiter: Opti
         if resnorm <= delta or oldnorm <= resnorm:                        # :113
             break
     return x
+
+
+# ----------------------------------------------------------------------------------------
+# Dictionary analysis  (`src/util.jl:2, 59-61, 96-117`)  -- SURVEY.md 8(f) rank 4
+# ----------------------------------------------------------------------------------------
+def colnorms(A: np.ndarray) -> np.ndarray:
+    """`colnorms(A) = [norm(a) for a in eachcol(A)]` (`src/util.jl:2`)."""
+    return np.array([np.linalg.norm(A[:, j]) for j in range(A.shape[1])], dtype=A.dtype)
+
+
+def normalize(A: np.ndarray) -> np.ndarray:
+    """`normalize!(A)` (`src/util.jl:59-61`)."""
+    A /= colnorms(A)[None, :]
+    return A
+
+
+def cumbabel(A: np.ndarray, k: int) -> np.ndarray:
+    """`cumbabel(A, k)` (`src/util.jl:106-117`): all Babel-function values mu_1(1..k)."""
+    mu = np.zeros(k, dtype=A.dtype)                                       # :107
+    for i in range(A.shape[1]):                                           # :109
+        inner = np.abs(A.T @ A[:, i])                                     # :110-111
+        inner[i] = 0                                                      # :112
+        top = np.sort(inner)[::-1][:k]                                    # :113 partialsort!(inner, 1:k, rev=true)
+        mu = np.maximum(mu, np.cumsum(top))                               # :114-115
+    return mu
+
+
+def babel(A: np.ndarray, k: int):
+    """`babel(A, k) = cumbabel(A, k)[k]` (`src/util.jl:101`)."""
+    return cumbabel(A, k)[k - 1]
+
+
+def coherence(A: np.ndarray):
+    """`coherence(A) = babel(A, 1)` (`src/util.jl:98`)."""
+    return babel(A, 1)
 
 
 # ----------------------------------------------------------------------------------------

@@ -358,6 +358,29 @@ def test_sp_midsize_batch_vs_oracle(cs, po):
         assert idx.tolist() == ref.nzind and _close(val, ref.nzval, 1e-9)
 
 
+# ------------------------------------------------------------------ dictionary analysis
+@pytest.mark.parametrize("M,N,k,dtype", [(64, 128, 16, np.float64), (70, 333, 40, np.float64), (32, 20, 19, np.float64),
+                                         (64, 160, 8, np.float32), (100, 1500, 70, np.float64)])
+def test_cumbabel_coherence_colnorms(cs, po, M, N, k, dtype):
+    """`cumbabel` / `babel` / `coherence` / `colnorms` / `normalize!` against the oracle (test/util.jl:7-20 properties)."""
+    rng = np.random.default_rng(N + k)
+    A = po.gaussian_dictionary(rng, M, N, dtype)
+    if N == 333:
+        A = np.asfortranarray(A * rng.uniform(0.5, 2.0, size=(1, N)))      # un-normalised: self product is not the maximum
+    rt = 1e-12 if dtype == np.float64 else 1e-5
+    with cs.Dictionary(A) as D:
+        mu1 = cs.cumbabel(D, k)
+        assert mu1.dtype == dtype
+        assert np.allclose(mu1, po.cumbabel(A, k), rtol=rt)
+        mu = cs.coherence(D)
+        assert np.isclose(mu, po.coherence(A), rtol=rt) and np.isclose(cs.babel(D, 1), mu)
+        assert np.isclose(cs.babel(D, k), mu1[k - 1], rtol=rt)
+        assert all(mu1[i] <= (i + 1) * mu * (1 + 1e-6) + 1e-12 for i in range(k))
+        assert np.allclose(cs.colnorms(D), po.colnorms(A), rtol=1e-6 if dtype == np.float32 else 1e-14)
+    B = np.asfortranarray(A * 3.0)
+    assert np.allclose(po.colnorms(cs.normalize(B)), 1.0, rtol=1e-6)
+
+
 # ------------------------------------------------------------------ mid-size parity and properties
 def _planted(po, rng, A, k, B, noise=0.0):
     N = A.shape[1]

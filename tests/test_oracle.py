@@ -273,6 +273,23 @@ def test_sp_semantics():
     assert np.allclose(xo.nzval, c)
 
 
+# ------------------------------------------------------------------ dictionary analysis
+def test_dictionary_analysis_properties():
+    """test/util.jl:7-20: coherence == babel(A, 1); cumbabel == babel.(1:k); mu_1(i) <= i * mu."""
+    rng = np.random.default_rng(12)
+    A = po.gaussian_dictionary(rng, 64, 128)
+    k = 16
+    mu = po.coherence(A)
+    assert 0 < mu < 1 and np.isclose(po.babel(A, 1), mu)
+    mu1 = po.cumbabel(A, k)
+    assert np.allclose(mu1, [po.babel(A, i) for i in range(1, k + 1)])
+    assert all(mu1[i] <= (i + 1) * mu + 1e-12 for i in range(k))
+    G = np.abs(A.T @ A); np.fill_diagonal(G, 0)
+    assert np.isclose(mu, G.max())
+    B = rng.standard_normal((10, 7)) * 3
+    assert np.allclose(po.colnorms(po.normalize(B.copy())), 1.0)
+
+
 def test_golden_fixtures_reproduce():
     """The committed fixtures (tests/golden/make_golden.py) are what the oracle produces today."""
     files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
