@@ -106,8 +106,9 @@ struct csb200_batch {
     bool has_map = false;
     double* pval = nullptr;
     int* pidx = nullptr;
-    size_t pcap = 0;            // candidate slots allocated
+    size_t pcap = 0, icap = 0;  // candidate value / index slots allocated
     int cur_P = 0;              // atom blocks per signal written by the last correlation pass
+    int cur_dense_ld = 0;       // > 0: the last pass stored the dense |A'r| matrix with this leading dimension
     bool use_gram = false;      // this solve takes A_S'a_j from the dictionary's Gram matrix
     // per-signal state: one device block laid out [resnorm | x | nnz | iters | flags | done | sel | z] so that
     // the results of a small solve come back in a single copy (state_result_bytes covers everything but z)
@@ -149,14 +150,20 @@ void free_batch_mem(csb200_batch* b) {
     if (b->stream) cudaStreamDestroy(b->stream);
 }
 
-int ensure_partials(csb200_batch* b, int64_t P, int64_t S) {
+int ensure_partials(csb200_batch* b, int64_t P, int64_t S, bool need_idx = true) {
     const size_t need = (size_t)b->cap_sig * (size_t)P * (size_t)S;
-    if (need <= b->pcap) return CSB200_OK;
-    cudaFree(b->pval); cudaFree(b->pidx);
-    b->pval = nullptr; b->pidx = nullptr; b->pcap = 0;
-    CU_TRY(cudaMalloc(&b->pval, need * sizeof(double)));
-    CU_TRY(cudaMalloc(&b->pidx, need * sizeof(int)));
-    b->pcap = need;
+    if (need > b->pcap) {
+        cudaFree(b->pval);
+        b->pval = nullptr; b->pcap = 0;
+        CU_TRY(cudaMalloc(&b->pval, need * sizeof(double)));
+        b->pcap = need;
+    }
+    if (need_idx && need > b->icap) {
+        cudaFree(b->pidx);
+        b->pidx = nullptr; b->icap = 0;
+        CU_TRY(cudaMalloc(&b->pidx, need * sizeof(int)));
+        b->icap = need;
+    }
     return CSB200_OK;
 }
 
@@ -176,21 +183,29 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
     a.pval = b->pval; a.pidx = b->pidx; a.nnz = b->nnz; a.sel = b->sel; a.Rf = b->Rf; a.z = b->z; a.x = b->x;
     a.resnorm = b->resnorm; a.iters = b->iters; a.done = b->done; a.flags = b->flags;
     a.gram = b->use_gram ? d->gram : nullptr;
+    a.dense_ld = b->cur_dense_ld;
     return a;
 }
 
-// One correlation pass over the current residuals, leaving top-S candidates per (atom block, signal).
-int run_corr(csb200_batch* b, int S, int impl) {
+// One correlation pass over the current residuals, leaving top-S candidates per (atom block, signal) -- or, when the
+// caller can consume it (allow_dense) and S is large, the dense |A'r| matrix: S selection rounds in the DMMA epilogue
+// cost as much as the contraction itself at S = 32, a plain store costs nothing.
+constexpr int DENSE_MIN_S = 8;
+int run_corr(csb200_batch* b, int S, int impl, bool allow_dense = false) {
     csb200_dict* d = b->dict;
     const bool f32 = d->dtype == CSB200_F32;
     if (impl == IMPL_AUTO) impl = b->corr_impl_env;
     if (impl == IMPL_AUTO) impl = (!f32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
     const int blk = impl == IMPL_GEMM ? corr_gemm_f64_block() : PBLK;
     const int64_t P = (d->N + blk - 1) / blk;
-    int rc = ensure_partials(b, P, S);
+    static const bool dense_off = [] { const char* e = getenv("CSB200_DENSE_TOPK"); return e && e[0] == '0'; }();
+    const bool dense = allow_dense && !dense_off && impl == IMPL_GEMM && S >= DENSE_MIN_S && !f32 && d->has_map && b->has_map;
+    int rc = dense ? ensure_partials(b, (d->N + 63) / 64, 64, false) : ensure_partials(b, P, S);
     if (rc) return rc;
     b->cur_P = (int)P;
+    b->cur_dense_ld = dense ? (int)((d->N + 63) / 64 * 64) : 0;
     CorrArgs c;
+    c.dense_ld = b->cur_dense_ld;
     c.A = d->dA; c.R = b->dR; c.M = (int)d->M; c.ld = (int)d->ld; c.N = (int)d->N; c.nsig = (int)b->nsig;
     c.S = S; c.P = (int)P; c.idx_offset = (int)d->n_offset; c.pval = b->pval; c.pidx = b->pidx;
     if (impl == IMPL_GEMM && (f32 || !d->has_map || !b->has_map)) {
@@ -260,11 +275,13 @@ void decide_gram(csb200_batch* b, int64_t k) {
     b->use_gram = true;
 }
 
-cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
+bool uses_cluster_update(const csb200_batch* b) {
     const char* env = getenv("CSB200_UPDATE_IMPL");      // test hook: force one of the two update kernels
     const int force = !env ? 0 : !strcmp(env, "cluster") ? 1 : !strcmp(env, "cta") ? 2 : 0;
-    const bool cluster = force == 1 || (force == 0 && b->nsig < CLUSTER_UPDATE_MAX_SIGNALS);
-    return cluster ? launch_omp_update_cluster(a, f32, b->stream) : launch_omp_update(a, f32, b->stream);
+    return force == 1 || (force == 0 && b->nsig < CLUSTER_UPDATE_MAX_SIGNALS);
+}
+cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
+    return uses_cluster_update(b) ? launch_omp_update_cluster(a, f32, b->stream) : launch_omp_update(a, f32, b->stream);
 }
 
 int begin_solve(csb200_batch* b) {
@@ -614,15 +631,18 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     if ((rc = begin_solve(b))) return rc;
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    // the block-append CTA update kernel can select from the dense |A'r| matrix
+    const bool dense_ok = !uses_cluster_update(b) && omp_update_uses_block((int)d->ld, (int)b->kcap, (int)l) &&
+                          (k % l == 0 || omp_update_uses_block((int)d->ld, (int)b->kcap, (int)(k % l)));
     for (int64_t it = 0; it < k / l; ++it) {
-        if ((rc = run_corr(b, (int)l, IMPL_AUTO))) return rc;
+        if ((rc = run_corr(b, (int)l, IMPL_AUTO, dense_ok))) return rc;
         e = update_launch(b, state_args(b, (int)l, (int)l, eps, 0), f32);
         if (e != cudaSuccess) return fail_cuda(e, "gomp_update");
         b->other_launches++;
     }
     const int rem = (int)(k % l);
     if (rem > 0) {                                   // runs even after an eps-break (matchingpursuit.jl:134-137)
-        if ((rc = run_corr(b, rem, IMPL_AUTO))) return rc;
+        if ((rc = run_corr(b, rem, IMPL_AUTO, dense_ok))) return rc;
         e = update_launch(b, state_args(b, rem, rem, eps, 1), f32);
         if (e != cudaSuccess) return fail_cuda(e, "gomp_update(rem)");
         b->other_launches++;
@@ -665,6 +685,7 @@ int csb200_batch_fr(csb200_batch* b, int64_t k, double max_eps, double min_delta
     const int64_t P = (d->N + PBLK - 1) / PBLK;
     if ((rc = ensure_partials(b, P, 1))) return rc;
     b->cur_P = (int)P;
+    b->cur_dense_ld = 0;
     StateArgs sa = state_args(b, 1, 1, 0.0, 0);
     sa.resc = b->resc; sa.ldr = round_up(b->nsig, 2); sa.qnew = b->qnew; sa.max_eps = max_eps; sa.min_delta2 = min_delta * min_delta;
     CorrArgs c;
@@ -729,7 +750,7 @@ static int run_sp(csb200_batch* b, int64_t k, double delta, int64_t maxiter) {
     cudaError_t e = launch_reset_state(state_args(b, S, S, 0.0, 0), f32, b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "reset_state");
     for (int64_t it = 0; it <= (obl ? 0 : maxiter); ++it) {
-        if ((rc = run_corr(b, S, IMPL_AUTO))) return rc;
+        if ((rc = run_corr(b, S, IMPL_AUTO, true))) return rc;
         e = launch_sp_update(state_args(b, S, S, 0.0, 0), f32, (int)k, delta, it == 0 ? 1 : 0, b->ndone, b->stream);
         if (e != cudaSuccess) return fail_cuda(e, "sp_update");
         b->other_launches++;
@@ -1044,7 +1065,7 @@ int csb200_dict_cumbabel(csb200_dict* d, int64_t k, double* mu_out) {
             if (e != cudaSuccess) { rc = fail_cuda(e, "copy atoms"); break; }
             b->nsig = nc; b->has_map = false; b->cur_P = 0;
             if ((rc = ensure_signal_map(b))) break;
-            if ((rc = run_corr(b, S, IMPL_AUTO))) break;
+            if ((rc = run_corr(b, S, IMPL_AUTO, true))) break;
             e = launch_babel_reduce(state_args(b, S, S, 0.0, 0), (int)k, (int)c0, dmu, b->stream);
             if (e != cudaSuccess) { rc = fail_cuda(e, "babel_reduce"); break; }
         }
@@ -1087,7 +1108,7 @@ int csb200_debug_corr_topk(csb200_batch* b, int impl, int64_t s, int64_t* idx, d
     if (!idx || !val || s < 1 || s > MAX_S || impl < 0 || impl > 3) return CSB200_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(b->dict))) return rc;
-    if ((rc = run_corr(b, (int)s, impl))) return rc;
+    if ((rc = run_corr(b, (int)s, impl, true))) return rc;
     long long* d_idx = nullptr;
     double* d_val = nullptr;
     const size_t n = (size_t)b->nsig * s;

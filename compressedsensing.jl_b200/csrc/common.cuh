@@ -30,6 +30,7 @@ struct CorrArgs {
     int idx_offset;      // global index of this shard's first atom
     double* pval;        // [nsig][P][S]
     int* pidx;           // [nsig][P][S]
+    int dense_ld = 0;    // > 0: store |c| itself, pval[sig * dense_ld + atom] (DMMA path only), and leave pidx alone
 };
 
 // correlation kernels (corr_gemm_f64.cu, corr_gemv.cu)
@@ -74,6 +75,7 @@ struct StateArgs {
     double* resc = nullptr;     // [N][ldr]  OLS rescaling ||a_j||^2 - ||Q1'a_j||^2 per (atom, signal); +Inf marks active atoms
     long long ldr = 0;          // leading dimension of resc (even, >= nsig)
     double* qnew = nullptr;     // [nsig][ld] newest orthonormal direction q_t of each signal (zero if none was added)
+    int dense_ld = 0;           // > 0: pval is the dense |A'r| matrix [nsig][dense_ld] (no pidx); 0: per-block candidates
     double max_eps = 0.0;       // forward_step! returns false unless ||r|| > max_eps   (:60)
     double min_delta2 = 0.0;    // ... and unless min_delta^2 < max_j delta2_j          (:63)
 };
@@ -95,6 +97,7 @@ struct SmallSolveArgs {
 bool small_solve_eligible(int ld, int N, int kcap, int nsig, bool f32);
 cudaError_t launch_small_solve(const StateArgs& a, const SmallSolveArgs& q, bool f32, cudaStream_t st);
 size_t omp_update_smem_bytes(int ld, int kcap);            // dynamic shared memory the kernels above need
+bool omp_update_uses_block(int ld, int kcap, int take);    // gomp: the block-append variant (which can read dense |A'r|) runs
 size_t omp_update_cluster_smem_bytes(int ld, int kcap);
 constexpr size_t MAX_DYN_SMEM = 227 * 1024;
 // resc[j][s] = ||a_j||^2 for every signal (`sum!(abs2, P.rescaling', P.A)`, src/forward.jl:105), qnew = 0

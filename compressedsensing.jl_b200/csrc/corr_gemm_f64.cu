@@ -100,7 +100,8 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 //             scheduler to cover LDS / mbarrier latency at the price of 8 instead of 6 LDS.128 per 32 DMMA
 // Epilogues: EPI_TOPS = |c| top-S per (64-atom block, signal); EPI_STORE = plain C store (A'A);
 // EPI_OLS = forward-regression criterion c^2 / rescaling with the rescaling down-date fused in (see below).
-enum { EPI_TOPS = 0, EPI_STORE = 1, EPI_OLS = 2 };
+// EPI_ABS = dense |c| store, signal-major (pval[sig * ldc + atom]): the large-S paths select from it with a radix select.
+enum { EPI_TOPS = 0, EPI_STORE = 1, EPI_OLS = 2, EPI_ABS = 3 };
 // DUAL (EPI_OLS only): the 128 "signal" columns of a CTA tile are 64 residuals r_s (from mapR) followed by the newest
 // orthonormal directions q_s of the SAME 64 signals (from mapQ), arranged so that a thread's accumulators
 // acc[i][j] (j < NJ/2) = <a, r_s> and acc[i][j + NJ/2] = <a, q_s> belong to the same (atom, signal) pairs.
@@ -237,6 +238,23 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             }
             continue;
         }
+        if constexpr (EPI == EPI_ABS) {
+            // lanes g = 0..7 hold 8 consecutive atoms of one signal: 64-byte segments per (i, j, e)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int sig = tb * TILE_B + wn * 8 * NJ + j * 8 + 2 * q + e;
+                    if (sig < nsig) {
+                        double* dst = pval + (size_t)sig * ldc + tn * TILE_N + wm * 8 * MI + g;
+#pragma unroll
+                        for (int i = 0; i < MI; ++i)
+                            if (tn * TILE_N + wm * 8 * MI + g + i * 8 < N) __stcs(dst + i * 8, fabs(acc[i][j][e]));
+                    }
+                }
+            }
+            continue;
+        }
         if constexpr (EPI == EPI_OLS) {
             // ---- forward-regression criterion (src/forward.jl:69-76, 97-114): delta2_j = <a_j, r>^2 / resc_j with
             // resc_j = ||a_j||^2 - ||Q1'a_j||^2 kept per (signal, atom) in HBM and down-dated here by <a_j, q_new>^2.
@@ -359,6 +377,8 @@ cudaError_t corr_gemm_f64_setup() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 1, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<1>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_OLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Pipe<2>::SMEM_BYTES);
@@ -377,6 +397,12 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     int band = band_env > 0 ? band_env : DEFAULT_BAND;
     if (band <= 0 || band > tilesN) band = tilesN;
     const int kslices = a.ld / KCH;
+    if (a.dense_ld > 0) {
+        corr_gemm_f64_kernel<8, 4, 2, 4, 2, EPI_ABS><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
+            *mapA, *mapR, a.N, a.nsig, (kslices + 1) / 2, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx,
+            a.dense_ld, *mapR, nullptr);
+        return cudaGetLastError();
+    }
     int variant = gemm_variant();
     // default: 64 KiB stages (2 k-slices per mbarrier round trip; measured 2.7 % faster at K = 1024) unless an odd
     // slice count would make the zero-filled tail slice a noticeable share of the work

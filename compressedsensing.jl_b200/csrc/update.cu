@@ -38,6 +38,13 @@
 namespace csb {
 namespace {
 
+// The block-append working set [bm][ld] doubles as histogram (first DENSE_HIST ints) + staging area of the dense
+// top-k selection, which runs before any atom is appended: never smaller than the histogram.
+__host__ __device__ inline size_t block_region_elems(int bm, int ld) {
+    const size_t e = (size_t)bm * ld;
+    return e < (size_t)DENSE_HIST / 2 ? (size_t)DENSE_HIST / 2 : e;
+}
+
 constexpr int UT = 128;            // threads per CTA
 constexpr int UW = UT / 32;
 
@@ -55,7 +62,7 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     double* p = dsm;
     double* Vb = nullptr; double* Gm = nullptr; double* Ym = nullptr; double* sc = nullptr;
     if constexpr (BLOCK) {
-        Vb = p; p += (size_t)bm * ld;                 // [bm][ld] block of new atoms / directions
+        Vb = p; p += block_region_elems(bm, ld);      // [bm][ld] block of new atoms / directions
         S.v = Vb;                                     // the one-by-one fallback reuses a row of the block
         Gm = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
         Ym = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
@@ -119,8 +126,14 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     __syncthreads();
 
     if (t < a.M) {                                                 // `nnz(x) < size(P.A, 1) || return x` (:63,:117)
-        const size_t cbase = (size_t)sig * a.P * a.S;
-        select_candidates<NT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
+        if constexpr (BLOCK) {
+            // the block working set is idle during the selection: its first 8 KB serve as histogram, the rest as staging
+            select_any<NT>(a, sig, a.take, MAX_S, s_cand, s_cval, red, red_i, reinterpret_cast<int*>(Vb),
+                           Vb + DENSE_HIST / 2, (int)block_region_elems(bm, ld) - DENSE_HIST / 2);
+        } else {                                                   // one atom per update: always per-block candidates
+            const size_t cbase = (size_t)sig * a.P * a.S;
+            select_candidates<NT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
+        }
 
         int round = 0;
         while (round < a.take) {
@@ -262,7 +275,7 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
     const int ld = a.ld, kcap = a.kcap;
     PursuitSmem<T> S;
     double* p = dsm;
-    double* Vb = p; p += (size_t)bm * ld;
+    double* Vb = p; p += block_region_elems(bm, ld);
     S.v = Vb;
     double* Gm = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
     double* Ym = p; p += (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX;
@@ -312,8 +325,8 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
         for (int e = tid; e < t * kcap; e += NT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * S.ldT] = S.Tg[e]; }
     __syncthreads();
 
-    const size_t cbase = (size_t)sig * a.P * a.S;
-    select_candidates<NT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, k, s_cand, s_cval, red, red_i);
+    select_any<NT>(a, sig, k, MAX_TAKE, s_cand, s_cval, red, red_i, reinterpret_cast<int*>(Vb), Vb + DENSE_HIST / 2,
+                   (int)block_region_elems(bm, ld) - DENSE_HIST / 2);
     const int cap = kcap < a.M ? kcap : a.M;
     flags |= append_list<T, NT>(S, t, s_cand, k, true, bm, cap, A, a.idx_offset, ld, Vb, Gm, Ym, sc, s_J, s_Jcol,
                                 b_at, r_at, r_set, nr2, changed);
@@ -449,9 +462,9 @@ __global__ void __launch_bounds__(UT) topk_from_partials_kernel(StateArgs a, int
     __shared__ int red_i[UW];
     __shared__ int s_cand[MAX_S];
     __shared__ double s_cval[MAX_S];
+    __shared__ int s_hist[DENSE_HIST];
     const int sig = blockIdx.x;
-    const size_t cbase = (size_t)sig * a.P * a.S;
-    select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, s, s_cand, s_cval, red, red_i);
+    select_any<UT>(a, sig, s, MAX_S, s_cand, s_cval, red, red_i, s_hist);
     for (int i = threadIdx.x; i < s; i += UT) {
         out_idx[(size_t)sig * s + i] = s_cand[i];
         out_val[(size_t)sig * s + i] = s_cand[i] < 0 ? 0.0 : s_cval[i];
@@ -478,9 +491,9 @@ __global__ void __launch_bounds__(UT) babel_reduce_kernel(StateArgs a, int k, in
     __shared__ int red_i[UW];
     __shared__ int s_cand[MAX_TAKE];
     __shared__ double s_cval[MAX_TAKE];
+    __shared__ int s_hist[DENSE_HIST];
     const int sig = blockIdx.x;
-    const size_t cbase = (size_t)sig * a.P * a.S;
-    select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, k + 1, s_cand, s_cval, red, red_i);
+    select_any<UT>(a, sig, k + 1, MAX_TAKE, s_cand, s_cval, red, red_i, s_hist);
     if (threadIdx.x == 0) {
         double run = 0.0;
         int out = 0;
@@ -511,18 +524,22 @@ __global__ void nonfinite_check_kernel(const T* __restrict__ p, size_t n, int* f
 size_t update_smem_bytes(int ld, int kcap, bool t_in_smem, int bm) {
     size_t bytes = (size_t)(5 * kcap) * sizeof(double) + (size_t)((kcap + 1) & ~1) * sizeof(int) +
                    (size_t)kcap * sizeof(void*);
-    if (bm > 0) bytes += ((size_t)bm * ld + 2 * (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX + 4 * BLOCK_MAX) * sizeof(double);
+    if (bm > 0) bytes += (block_region_elems(bm, ld) + 2 * (size_t)(kcap + BLOCK_MAX) * BLOCK_MAX + 4 * BLOCK_MAX) * sizeof(double);
     else bytes += (size_t)ld * sizeof(double);
     if (t_in_smem) bytes += (size_t)kcap * (kcap | 1) * sizeof(double);
     return bytes;
 }
 
 // atoms orthogonalised together by the block path for this shape (0 = block path not used)
+// Dynamic shared memory one CTA may use if two are to fit on an SM: 228 KB per SM, 1 KB reserved per CTA, minus the
+// kernel's static shared memory (ptxas -v: 960 B for the gomp block kernel, 4304 B for sp_update_kernel).
+constexpr size_t two_cta_dyn_smem(size_t static_bytes) { return (228 * 1024 - 2 * 1024) / 2 - static_bytes; }
+
 int block_width(int ld, int kcap, int take) {
     if (take < 2) return 0;
     const bool t_in = kcap <= T_SMEM_MAX_K;
     int bm = take < BLOCK_MAX ? take : BLOCK_MAX;
-    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > 112 * 1024) --bm;   // keep 2 CTAs per SM
+    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > two_cta_dyn_smem(1024)) --bm;   // keep 2 CTAs per SM
     return bm >= 2 ? bm : 0;
 }
 
@@ -547,6 +564,11 @@ cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void*
 
 }  // namespace
 
+bool omp_update_uses_block(int ld, int kcap, int take) {
+    const char* env = getenv("CSB200_GOMP_BLOCK");
+    return !(env && env[0] == '0') && block_width(ld, kcap, take) > 0;
+}
+
 size_t omp_update_smem_bytes(int ld, int kcap) { return update_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K, 0); }
 
 cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
@@ -557,7 +579,7 @@ cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, con
 int sp_block_width(int ld, int kcap) {
     const bool t_in = kcap <= T_SMEM_MAX_K;
     int bm = BLOCK_MAX;
-    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > 112 * 1024) --bm;      // 2 CTAs per SM when possible
+    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > two_cta_dyn_smem(4608)) --bm;   // 2 CTAs per SM when possible
     if (bm < 2) { bm = 2; }
     return bm;
 }

@@ -63,6 +63,145 @@ __device__ void select_candidates(const double* __restrict__ pv, const int* __re
 }
 
 
+// Global top-`take` of one signal's DENSE |c| row (v[0..n), atom index = position + idx_offset), for the large-S
+// paths (sp, oblivious, cumbabel, gomp with many atoms per update) where the correlation pass stores |A'r| itself
+// instead of per-block candidates.  MSB-first radix select on the bit patterns (non-negative doubles order like
+// unsigned integers) with 11-bit digits: a histogram pass finds the bucket holding the take-th largest value; as soon
+// as everything at or above that bucket fits into the `cap` output slots (typically after the exponent pass and one
+// mantissa pass) it is collected and a bitonic sort orders it by (value descending, index ascending) -- the order
+// select_candidates produces -- and the first `take` entries are the answer.  Only massive exact ties (e.g. an
+// all-zero residual) go the whole 64 bits and take the lowest indices by an ordered compaction.
+// stage (optional): shared scratch of stage_elems doubles; the row is copied there once when it fits.
+// hist: DENSE_HIST ints of shared memory, misc: >= 4 ints.  s_cand / s_cval: cap slots, cap a power of two >= take.
+constexpr int DENSE_HIST_BITS = 11;
+constexpr int DENSE_HIST = 1 << DENSE_HIST_BITS;
+
+template <int NT>
+__device__ void select_dense(const double* __restrict__ v, int n, int idx_offset, int take, int cap, int* s_cand,
+                             double* s_cval, int* hist, int* misc, double* stage, int stage_elems) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int want = take;
+    if (take > n) take = n;
+    const double* src = v;
+    if (stage && stage_elems > 0 && n <= stage_elems) {
+        for (int c = tid; c < n; c += NT) stage[c] = v[c];
+        src = stage;
+    }
+    __syncthreads();
+    unsigned long long prefix = 0, mask = 0;
+    int rem = take, above = 0;
+    bool fits = false, full = false;
+    int shift = 64;
+    while (!fits && shift > 0 && take > 0) {
+        const int bits = shift >= DENSE_HIST_BITS + 1 ? DENSE_HIST_BITS : shift;      // 63 = 11*5 + 8: the sign bit is never set
+        shift = shift == 64 ? 52 : shift - bits;
+        const int nb = 1 << bits;
+        for (int i = tid; i < nb; i += NT) hist[i] = 0;
+        __syncthreads();
+        for (int c = tid; c < n; c += NT) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(src[c]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & (unsigned long long)(nb - 1))], 1);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // bins are scanned from the top; lane L owns the descending range [hi - L*per - per + 1, hi - L*per]
+            const int per = (nb + 31) / 32, top = nb - 1 - lane * per;
+            int mine = 0;
+            for (int b = top; b > top - per && b >= 0; --b) mine += hist[b];
+            int incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += o; }
+            const int excl = incl - mine;
+            if (excl < rem && rem <= incl) {
+                int cum = excl, b = top;
+                for (; b > top - per && b > 0; --b) { if (cum + hist[b] >= rem) break; cum += hist[b]; }
+                misc[0] = b; misc[1] = rem - cum; misc[2] = hist[b]; misc[3] = cum;
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)misc[0] << shift;
+        mask |= (unsigned long long)(nb - 1) << shift;
+        rem = misc[1];                                // still to take from inside the bucket
+        above = take - rem;                           // elements strictly above the bucket
+        fits = above + misc[2] <= cap;
+        full = shift == 0;
+        __syncthreads();
+    }
+    if (tid == 0) misc[3] = 0;
+    __syncthreads();
+    int count = 0;
+    if (fits || take == 0) {
+        for (int c = tid; c < n && take > 0; c += NT) {
+            const double val = src[c];
+            if (((unsigned long long)__double_as_longlong(val) & mask) >= prefix) {
+                const int pos = atomicAdd(&misc[3], 1);
+                s_cand[pos] = c + idx_offset; s_cval[pos] = val;
+            }
+        }
+        __syncthreads();
+        count = misc[3];
+    } else {
+        // more exact ties at the threshold than output slots: everything above it, then the lowest tied indices
+        for (int c = tid; c < n; c += NT) {
+            const double val = src[c];
+            if ((unsigned long long)__double_as_longlong(val) > prefix) {
+                const int pos = atomicAdd(&misc[3], 1);
+                s_cand[pos] = c + idx_offset; s_cval[pos] = val;
+            }
+        }
+        const int chunk = (n + NT - 1) / NT, lo = tid * chunk, hi = min(n, lo + chunk);
+        int mine = 0;
+        for (int c = lo; c < hi; ++c) mine += ((unsigned long long)__double_as_longlong(src[c]) == prefix);
+        __syncthreads();
+        hist[tid] = mine;
+        __syncthreads();
+        if (tid == 0) { int run = 0; for (int t = 0; t < NT; ++t) { const int x = hist[t]; hist[t] = run; run += x; } }
+        __syncthreads();
+        int rank = hist[tid];
+        const int base = take - rem;
+        for (int c = lo; c < hi && rank < rem; ++c)
+            if ((unsigned long long)__double_as_longlong(src[c]) == prefix) { s_cand[base + rank] = c + idx_offset; s_cval[base + rank] = src[c]; ++rank; }
+        __syncthreads();
+        count = take;
+        (void)full;
+    }
+    int p2 = 1;
+    while (p2 < count) p2 <<= 1;
+    for (int i = count + tid; i < p2; i += NT) { s_cand[i] = INT_MAX; s_cval[i] = -1.0; }
+    __syncthreads();
+    for (int k2 = 2; k2 <= p2; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < p2; i += NT) {
+                const int o = i ^ j;
+                if (o > i) {
+                    const double va = s_cval[i], vb = s_cval[o];
+                    const int ia = s_cand[i], ib = s_cand[o];
+                    const bool first_half = (i & k2) == 0;           // "better first" in ascending halves
+                    const bool swap = first_half ? cand_better(vb, ib, va, ia) : cand_better(va, ia, vb, ib);
+                    if (swap) { s_cval[i] = vb; s_cand[i] = ib; s_cval[o] = va; s_cand[o] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = take + tid; i < want; i += NT) s_cand[i] = -1;      // fewer than `want` atoms exist
+    __syncthreads();
+}
+
+// Either form of the candidates a correlation pass left for signal `sig`.
+template <int NT>
+__device__ __forceinline__ void select_any(const StateArgs& a, int sig, int take, int cap, int* s_cand, double* s_cval,
+                                           double* red_v, int* red_i, int* hist, double* stage = nullptr,
+                                           int stage_elems = 0) {
+    if (a.dense_ld > 0) {
+        select_dense<NT>(a.pval + (size_t)sig * a.dense_ld, a.N, a.idx_offset, take, cap, s_cand, s_cval, hist, red_i,
+                         stage, stage_elems);
+    } else {
+        const size_t cbase = (size_t)sig * a.P * a.S;
+        select_candidates<NT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, take, s_cand, s_cval, red_v, red_i);
+    }
+}
+
 // 16-byte loads of W consecutive rows of a dictionary column, widened to double: the gather sweeps below are
 // latency-bound (a few CTAs per SM, one dependent chain per thread), so bytes in flight per load matter.
 template <typename T> struct RowVec;

@@ -84,6 +84,37 @@ def test_corr_ties_pick_lowest_index(cs, po):
             assert np.array_equal(val[: B // 2, 0], val[: B // 2, 2])
 
 
+@pytest.mark.parametrize("M,N,B,s", [(96, 700, 50, 16), (64, 1000, 130, 33), (128, 333, 24, 64), (32, 40, 30, 64)])
+def test_dense_topk_radix_select(cs, po, M, N, B, s, monkeypatch):
+    """Large-s path: the DMMA pass stores |A'r| and the selection is a radix select + bitonic sort.  Same (value desc,
+    index asc) order as numpy and as the per-block candidate path (CSB200_DENSE_TOPK=0); exact ties (duplicate /
+    negated atoms, an all-zero residual) go to the lowest indices."""
+    rng = np.random.default_rng(M + N + s)
+    A = po.gaussian_dictionary(rng, M, N)
+    A[:, N - 1] = A[:, 3]
+    A[:, N // 2] = -A[:, 3]
+    A[:, 7] = A[:, 5]
+    R = np.asfortranarray(rng.standard_normal((M, B)))
+    R[:, 1] = 0.0
+    R[:, 2] = A[:, 3] * 2.0
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 4) as batch:
+        batch.upload(R)
+        idx, val = batch.debug_corr_topk(s, 1)
+        idx_v, val_v = batch.debug_corr_topk(s, 2)            # GEMV kernel: per-block candidates
+    C = np.abs(A.T @ R)
+    take = min(s, N)
+    assert idx[1, :take].tolist() == list(range(take)) and (val[1, :take] == 0).all()
+    assert idx[2, :3].tolist() == [3, N // 2, N - 1]
+    for b in range(B):
+        order = np.lexsort((np.arange(N), -C[:, b]))[:take]
+        assert np.allclose(val[b, :take], C[order, b], rtol=1e-12, atol=1e-13), b
+        assert (idx[b, take:] == -1).all()
+        srt = np.sort(C[:, b])[::-1][: take + 1]
+        if b not in (1, 2) and np.min(np.abs(np.diff(srt))) > 1e-11:
+            assert idx[b, :take].tolist() == order.tolist(), b
+    assert np.array_equal(idx, idx_v)
+
+
 @pytest.mark.parametrize("M,N,s", [(64, 160, 2), (8192, 640, 1), (100, 77, 5)])
 def test_corr_gemv_f32(cs, po, M, N, s):
     rng = np.random.default_rng(N)
