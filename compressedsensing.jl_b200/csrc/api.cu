@@ -253,7 +253,7 @@ int run_small_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double eps,
 
 // Gram matrix A'A for the batched update kernel: with it the first orthogonalisation sweep reads t numbers
 // instead of gathering t atoms.  Worth its 2 N^2 M flop only for large batches; cached on the dictionary.
-constexpr int64_t GRAM_MAX_ATOMS = 16384;            // 2 GiB
+constexpr int64_t GRAM_MAX_ATOMS = 32768;            // 8 GiB; taken only while it is < 1/8 of the free device memory
 constexpr int64_t GRAM_MIN_SIGNAL_ITERS = 1 << 18;   // nsig * k below which building it does not pay
 void decide_gram(csb200_batch* b, int64_t k) {
     csb200_dict* d = b->dict;
@@ -265,6 +265,8 @@ void decide_gram(csb200_batch* b, int64_t k) {
     if (!force && (b->nsig * k < GRAM_MIN_SIGNAL_ITERS || b->nsig < CLUSTER_UPDATE_MAX_SIGNALS)) return;
     std::lock_guard<std::mutex> lk(d->gram_mu);
     if (!d->gram) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (size_t)d->N * d->N * sizeof(double) > free_b / 8) { cudaGetLastError(); return; }
         double* g = nullptr;
         if (cudaMalloc(&g, (size_t)d->N * d->N * sizeof(double)) != cudaSuccess) { cudaGetLastError(); d->gram_failed = true; return; }
         cudaError_t e = launch_gemm_f64_store(&d->mapA, &d->mapA, (int)d->N, (int)d->N, (int)d->ld, g, d->N, d->num_sms, b->stream);
@@ -742,7 +744,7 @@ static int run_sp(csb200_batch* b, int64_t k, double delta, int64_t maxiter) {
     if ((rc = settle_input(b))) return rc;
     if ((rc = ensure_factor(b))) return rc;
     if (!b->ndone) CU_TRY(cudaMalloc(&b->ndone, sizeof(int)));
-    b->use_gram = false;
+    decide_gram(b, obl ? k : 4 * k);                          // sp: a few update!s of ~2k appends each
     const bool f32 = d->dtype == CSB200_F32;
     const int S = (int)(k < PBLK ? k : PBLK);                 // per 64-atom block the whole top-k can sit in one block
     if ((rc = begin_solve(b))) return rc;

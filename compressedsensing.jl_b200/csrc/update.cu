@@ -155,7 +155,8 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
                 if (m > 0) {
                     int done_b = 0;
                     if (m > 1) {
-                        done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2);
+                        done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2,
+                                                     a.gram, a.N, a.idx_offset);
                         if (done_b) changed = true;
                     }
                     for (int c = done_b; c < m; ++c) {                   // one by one: single atom, or DGKS fallback
@@ -233,7 +234,8 @@ template <typename T, int NT, typename BAt, typename RAt, typename RSet>
 __device__ __forceinline__ int append_list(PursuitSmem<T>& S, int& t, const int* list, int count, bool skip_active,
                                            int bm, int cap, const T* __restrict__ A, int idx_offset, int ld, double* Vb,
                                            double* Gm, double* Ym, double* sc, int* s_J, const T** s_Jcol, BAt b_at,
-                                           RAt r_at, RSet r_set, double& nr2, bool& changed) {
+                                           RAt r_at, RSet r_set, double& nr2, bool& changed,
+                                           const double* __restrict__ gram = nullptr, int gramN = 0) {
     const int tid = threadIdx.x;
     int flags = 0, round = 0;
     while (round < count) {
@@ -255,7 +257,8 @@ __device__ __forceinline__ int append_list(PursuitSmem<T>& S, int& t, const int*
         if (m > 0) {
             int done_b = 0;
             if (m > 1) {
-                done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2);
+                done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2, gram, gramN,
+                                             idx_offset);
                 if (done_b) changed = true;
             }
             for (int c = done_b; c < m; ++c) {
@@ -329,7 +332,7 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
                    (int)block_region_elems(bm, ld) - DENSE_HIST / 2);
     const int cap = kcap < a.M ? kcap : a.M;
     flags |= append_list<T, NT>(S, t, s_cand, k, true, bm, cap, A, a.idx_offset, ld, Vb, Gm, Ym, sc, s_J, s_Jcol,
-                                b_at, r_at, r_set, nr2, changed);
+                                b_at, r_at, r_set, nr2, changed, a.gram, a.N);
     if (!first && t > k) {
         for (int i = tid; i < t; i += NT) {                       // x' = R^{-1} Q'b on the enlarged support
             double acc = 0.0;
@@ -359,7 +362,7 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
         t = 0;
         __syncthreads();
         flags |= append_list<T, NT>(S, t, s_keep, s_nkeep, false, bm, cap, A, a.idx_offset, ld, Vb, Gm, Ym, sc, s_J,
-                                    s_Jcol, b_at, r_at, r_set, nr2, changed);
+                                    s_Jcol, b_at, r_at, r_set, nr2, changed, a.gram, a.N);
     }
     for (int i = tid; i < t; i += NT) {                            // x_S = R^{-1} Q'b
         double acc = 0.0;

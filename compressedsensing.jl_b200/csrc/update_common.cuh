@@ -363,7 +363,8 @@ template <typename T, int NT, typename BAt, typename RAt, typename RSet>
 __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, const int* __restrict__ J,
                                             const T* const* __restrict__ Jcol, int ld, double* __restrict__ Vb,
                                             double* __restrict__ Gm, double* __restrict__ Ym, double* __restrict__ sc,
-                                            BAt b_at, RAt r_at, RSet r_set, double& nr2) {
+                                            BAt b_at, RAt r_at, RSet r_set, double& nr2,
+                                            const double* __restrict__ gram = nullptr, int gramN = 0, int idx_offset = 0) {
     constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = t;
@@ -380,7 +381,15 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
     for (int c = 0; c < BLOCK_MAX; ++c)
         if (c < m) { const double s = block_sum<NT>(part[c], S.red); if (tid == 0) sc[c] = s; }
     __syncthreads();
-    // sweep 1: Gm[i][c] = <column i, a_c>, columns i < t0 from the dictionary, i >= t0 from the block itself
+    // sweep 1: Gm[i][c] = <column i, a_c>, columns i < t0 from the dictionary, i >= t0 from the block itself --
+    // or, when the dictionary's Gram matrix A'A is cached, (t0 + m) m scattered 8-byte loads and no gather at all
+    if (gram) {
+        for (int e = tid; e < (t0 + m) * m; e += NT) {
+            const int i = e / m, c = e - i * m;
+            const int col = (i < t0 ? S.ssel[i] : J[i - t0]) - idx_offset;
+            Gm[i * BLOCK_MAX + c] = gram[(size_t)(J[c] - idx_offset) * gramN + col];
+        }
+    } else
     for (int i = warp; i < t0 + m; i += NT / 32) {
         double acc[BLOCK_MAX];
 #pragma unroll

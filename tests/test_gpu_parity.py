@@ -358,7 +358,13 @@ def test_sp_and_oblivious_call_surface(cs, po):
             assert out[s].nzind.tolist() == ref.nzind and _close(out[s].nzval, ref.nzval, 1e-9)
 
 
-def test_sp_midsize_batch_vs_oracle(cs, po):
+@pytest.mark.parametrize("gram", ["0", "1"])
+def test_sp_midsize_batch_vs_oracle(cs, po, gram, monkeypatch):
+    monkeypatch.setenv("CSB200_GRAM", gram)
+    _sp_midsize(cs, po)
+
+
+def _sp_midsize(cs, po):
     """Mid-size batch (DMMA correlation path, block appends, k > 64-atom candidate blocks exercised via N ragged):
     per-signal iteration counts, supports and coefficients against the oracle; bit-identical re-solve."""
     rng = np.random.default_rng(177)
