@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -93,6 +94,7 @@ struct csb200_dict {
     std::mutex mu;
     std::mutex gram_mu;
     csb200_batch* workspace = nullptr;   // reused by the one-shot entry points (csb200_omp/gomp/mp)
+    csb200_batch* pipe_ws[2] = {nullptr, nullptr};   // ping-pong workspaces of the pipelined one-shot path (large batches)
     double* gram = nullptr;              // A'A (N x N, FP64), built on first use by a large batched omp/gomp
     bool gram_failed = false;
     size_t esize() const { return dtype == CSB200_F32 ? 4 : 8; }
@@ -133,6 +135,7 @@ struct csb200_batch {
     cudaEvent_t ev_solve0 = nullptr, ev_solve1 = nullptr;   // bracket the last solve
     bool solve_timed = false;
     int corr_impl_env = IMPL_AUTO;
+    bool defer_finish = false;  // pipelined one-shot path: a solve only enqueues its work, the caller synchronises later
     std::mutex mu;
 };
 
@@ -295,9 +298,27 @@ int begin_solve_fwd(csb200_batch* b) { return begin_solve(b); }
 
 int finish(csb200_batch* b, bool solve = false) {
     if (solve) { CU_TRY(cudaEventRecord(b->ev_solve1, b->stream)); }
+    if (solve && b->defer_finish) return CSB200_OK;
     cudaError_t e = cudaStreamSynchronize(b->stream);
     if (e == cudaSuccess && solve) b->solve_timed = true;
     if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+    return CSB200_OK;
+}
+
+// device-side result arrays (int32 indices, kcap slots per signal) -> the caller's layout (int64, `stride` slots, padded)
+int convert_results(size_t ns, size_t kc, int64_t stride, const int* hn, const int* hs, const int* hit, const double* hx,
+                    const double* hres, int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
+    for (size_t s = 0; s < ns; ++s) {
+        const int64_t t = hn[s];
+        if (t > stride && (sel_idx || coef)) { g_last_error = "stride smaller than a signal's support"; return CSB200_ERR_INVALID_ARG; }
+        if (nnz) nnz[s] = t;
+        if (iters) iters[s] = hit[s];
+        if (resnorm) resnorm[s] = hres[s];
+        for (int64_t j = 0; j < stride; ++j) {
+            if (sel_idx) sel_idx[s * stride + j] = j < t ? (int64_t)hs[s * kc + j] : -1;
+            if (coef) coef[s * stride + j] = j < t ? hx[s * kc + j] : 0.0;
+        }
+    }
     return CSB200_OK;
 }
 
@@ -472,6 +493,7 @@ int csb200_dict_trim(csb200_dict* d) {
     if (!d) return CSB200_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(d->mu);
     if (d->workspace) { csb200_batch_destroy(d->workspace); d->workspace = nullptr; }
+    for (auto& w : d->pipe_ws) if (w) { csb200_batch_destroy(w); w = nullptr; }
     return CSB200_OK;
 }
 
@@ -479,6 +501,7 @@ int csb200_dict_destroy(csb200_dict* d) {
     if (!d) return CSB200_OK;
     cudaSetDevice(d->device);
     if (d->workspace) csb200_batch_destroy(d->workspace);
+    for (auto& w : d->pipe_ws) if (w) csb200_batch_destroy(w);
     cudaFree(d->gram);
     cudaFree(d->dA);
     delete d;
@@ -866,18 +889,7 @@ int csb200_batch_download(csb200_batch* b, int64_t stride, int64_t* sel_idx, dou
     if (b->lazy_input_check) {
         for (size_t s = 0; s < ns; ++s) if (hfl[s] & 4) return CSB200_ERR_NONFINITE_INPUT;
     }
-    for (size_t s = 0; s < ns; ++s) {
-        const int64_t t = hn[s];
-        if (t > stride && (sel_idx || coef)) { g_last_error = "stride smaller than a signal's support"; return CSB200_ERR_INVALID_ARG; }
-        if (nnz) nnz[s] = t;
-        if (iters) iters[s] = hit[s];
-        if (resnorm) resnorm[s] = hres[s];
-        for (int64_t j = 0; j < stride; ++j) {
-            if (sel_idx) sel_idx[s * stride + j] = j < t ? (int64_t)hs[s * kc + j] : -1;
-            if (coef) coef[s * stride + j] = j < t ? hx[s * kc + j] : 0.0;
-        }
-    }
-    return CSB200_OK;
+    return convert_results(ns, kc, stride, hn, hs, hit, hx, hres, sel_idx, coef, nnz, resnorm, iters);
 }
 
 int csb200_batch_profile(csb200_batch* b, int enable) {
@@ -941,6 +953,130 @@ static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig,
     return upload_common(w, Bmat, ldb, nsig, cudaMemcpyHostToDevice, allow_lazy);
 }
 
+// ---- pipelined one-shot path -------------------------------------------------------------------
+// Large host batches are cut into chunks that ping-pong between two workspaces, each with its own stream: while chunk
+// c is being solved, chunk c+1 is uploaded (copy engine) and chunk c-1's results are downloaded and converted on the
+// host, so only the first upload and the last download stay outside the compute time.  The kernels of the two
+// streams also dovetail at the ends of each launch.  Signals are independent, so chunking does not change results.
+constexpr int64_t PIPE_MIN_SIGNALS = 32768;     // below this a single upload is cheaper than the bookkeeping
+
+// Chunk size: the persistent DMMA kernel takes ceil(tiles / SMs) tile times, so a chunk should be a whole number of
+// waves -- (atom tiles) x (signal tiles of the chunk) a multiple of the SM count -- or chunking adds a partial wave
+// per launch.  q = signal tiles per whole-wave group; the chunk is the multiple of 128 q closest to 16 384 signals.
+static int64_t pipe_chunk_signals(const csb200_dict* d) {
+    const int64_t tilesN = (d->N + 127) / 128;
+    int64_t a = d->num_sms, b = tilesN;
+    while (b) { const int64_t t = a % b; a = b; b = t; }
+    const int64_t q = d->num_sms / a;
+    int64_t m = (16384 + 64 * q) / (128 * q);
+    if (m < 1) m = 1;
+    return 128 * q * m;
+}
+
+static bool pipeline_enabled() {
+    const char* e = getenv("CSB200_PIPELINE");      // test hook: 0 forces the single-upload path
+    return !(e && e[0] == '0');
+}
+
+struct PipeOut { int64_t* sel_idx; double* coef; int64_t* nnz; double* resnorm; int64_t* iters; };
+
+static int pipe_upload_async(csb200_batch* w, const void* src, int64_t ldb, int64_t nsig) {
+    csb200_dict* d = w->dict;
+    const size_t es = d->esize();
+    if (d->ld == d->M && ldb == d->M) {
+        CU_TRY(cudaMemcpyAsync(w->dB, src, (size_t)d->M * nsig * es, cudaMemcpyHostToDevice, w->stream));
+    } else {
+        if (d->ld != d->M) CU_TRY(cudaMemsetAsync(w->dB, 0, (size_t)d->ld * nsig * es, w->stream));
+        CU_TRY(cudaMemcpy2DAsync(w->dB, d->ld * es, src, ldb * es, d->M * es, nsig, cudaMemcpyHostToDevice, w->stream));
+    }
+    w->nsig = nsig; w->has_map = false; w->cur_P = 0; w->lazy_input_check = false;
+    int rc = ensure_signal_map(w);
+    if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(w->dflag, 0, sizeof(int), w->stream));
+    cudaError_t e = launch_nonfinite_check(w->dB, (size_t)d->ld * nsig, d->dtype == CSB200_F32, w->dflag, w->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "nonfinite check");
+    return CSB200_OK;
+}
+
+static int pipe_complete(csb200_batch* w, int64_t stride, const PipeOut& o, int64_t s0) {
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    if (*reinterpret_cast<const int*>(w->host_stage + w->state_result_bytes)) return CSB200_ERR_NONFINITE_INPUT;
+    const unsigned char* p = w->host_stage;
+    auto at = [&](const void* dev) { return p + ((const unsigned char*)dev - w->state_blk); };
+    return convert_results((size_t)w->nsig, (size_t)w->kcap, stride, (const int*)at(w->nnz), (const int*)at(w->sel),
+                           (const int*)at(w->iters), (const double*)at(w->x), (const double*)at(w->resnorm),
+                           o.sel_idx ? o.sel_idx + s0 * stride : nullptr, o.coef ? o.coef + s0 * stride : nullptr,
+                           o.nnz ? o.nnz + s0 : nullptr, o.resnorm ? o.resnorm + s0 : nullptr,
+                           o.iters ? o.iters + s0 : nullptr);
+}
+
+// solve(w) must only ENQUEUE the solve on w->stream (w->defer_finish is set around it).
+static int one_shot_pipelined(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t kcap, int64_t stride,
+                              const std::function<int(csb200_batch*)>& solve, const PipeOut& out) {
+    int rc = set_device(d);
+    if (rc) return rc;
+    const int64_t cap = kcap < 1 ? 1 : kcap;
+    const int64_t PIPE_CHUNK = pipe_chunk_signals(d);
+    for (int i = 0; i < 2; ++i) {
+        csb200_batch*& w = d->pipe_ws[i];
+        if (w && (w->cap_sig != PIPE_CHUNK || w->kcap < cap)) { csb200_batch_destroy(w); w = nullptr; }
+        if (!w) {
+            if ((rc = csb200_batch_create(d, PIPE_CHUNK, cap, &w))) return rc;
+            if (w->host_stage_bytes < w->state_result_bytes + 16) {      // pinned landing zone: result block + input flag
+                if (w->host_stage) cudaFreeHost(w->host_stage);
+                w->host_stage = nullptr; w->host_stage_bytes = 0;
+                CU_TRY(cudaMallocHost((void**)&w->host_stage, w->state_result_bytes + 16));
+                w->host_stage_bytes = w->state_result_bytes + 16;
+            }
+        }
+    }
+    const size_t es = d->esize();
+    const int64_t nchunks = (nsig + PIPE_CHUNK - 1) / PIPE_CHUNK;
+    csb200_batch* prev = nullptr;               // the solves run one after the other; only copies overlap them
+    int64_t started[2] = {-1, -1};              // first signal of the chunk in flight on each workspace
+    int first_err = CSB200_OK;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        csb200_batch* w = d->pipe_ws[c & 1];
+        if (started[c & 1] >= 0) {
+            rc = pipe_complete(w, stride, out, started[c & 1]);
+            started[c & 1] = -1;
+            if (rc && !first_err) first_err = rc;
+        }
+        if (first_err) break;
+        const int64_t s0 = c * PIPE_CHUNK, nc = nsig - s0 < PIPE_CHUNK ? nsig - s0 : PIPE_CHUNK;
+        rc = pipe_upload_async(w, (const char*)Bmat + (size_t)s0 * ldb * es, ldb, nc);
+        if (!rc && prev) {
+            cudaError_t e = cudaStreamWaitEvent(w->stream, prev->ev_solve1, 0);
+            if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
+        }
+        if (!rc) {
+            w->defer_finish = true;
+            rc = solve(w);
+            w->defer_finish = false;
+        }
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(w->host_stage, w->state_blk, w->state_result_bytes, cudaMemcpyDeviceToHost, w->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(w->host_stage + w->state_result_bytes, w->dflag, sizeof(int), cudaMemcpyDeviceToHost, w->stream);
+            if (e != cudaSuccess) rc = fail_cuda(e, "result download");
+        }
+        if (rc) { first_err = rc; cudaStreamSynchronize(w->stream); break; }
+        started[c & 1] = s0;
+        prev = w;
+    }
+    for (int i = 0; i < 2; ++i) {
+        const int64_t which = (nchunks + i) & 1;            // drain in submission order
+        if (started[which] >= 0) {
+            rc = pipe_complete(d->pipe_ws[which], stride, out, started[which]);
+            if (rc && !first_err) first_err = rc;
+        }
+    }
+    return first_err;
+}
+
+static bool use_pipeline(const csb200_dict* d, int64_t nsig) {
+    return pipeline_enabled() && nsig >= PIPE_MIN_SIGNALS && d->n_total == d->N;
+}
+
 static int64_t support_cap(const csb200_dict* d, int64_t k) {
     int64_t cap = k < d->M ? k : d->M;
     return d->n_total < cap ? d->n_total : cap;
@@ -951,6 +1087,10 @@ int csb200_omp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int6
     if (!d || k < 0) return CSB200_ERR_INVALID_ARG;
     if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
     std::lock_guard<std::mutex> lk(d->mu);
+    if (Bmat && use_pipeline(d, nsig) && ldb >= d->M)
+        return one_shot_pipelined(d, Bmat, ldb, nsig, support_cap(d, k), k,
+                                  [&](csb200_batch* w) { return csb200_batch_omp(w, k, eps); },
+                                  PipeOut{sel_idx, coef, nnz, resnorm, iters});
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
@@ -964,6 +1104,10 @@ int csb200_gomp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int
     if (!d || k < 0 || l < 1) return CSB200_ERR_INVALID_ARG;
     if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
     std::lock_guard<std::mutex> lk(d->mu);
+    if (Bmat && use_pipeline(d, nsig) && ldb >= d->M)
+        return one_shot_pipelined(d, Bmat, ldb, nsig, support_cap(d, k), k,
+                                  [&](csb200_batch* w) { return csb200_batch_gomp(w, l, k, eps); },
+                                  PipeOut{sel_idx, coef, nnz, resnorm, iters});
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
@@ -978,6 +1122,10 @@ int csb200_fr(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64
     std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
     int64_t cap = support_cap(d, k);
+    if (Bmat && use_pipeline(d, nsig) && ldb >= d->M)
+        return one_shot_pipelined(d, Bmat, ldb, nsig, cap, k,
+                                  [&](csb200_batch* w) { return csb200_batch_fr(w, k, max_eps, min_delta); },
+                                  PipeOut{sel_idx, coef, nnz, resnorm, iters});
     int rc = one_shot(d, Bmat, ldb, nsig, cap, &b, /*allow_lazy=*/false);
     if (rc) return rc;
     rc = csb200_batch_fr(b, k, max_eps, min_delta);

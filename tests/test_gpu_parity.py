@@ -282,6 +282,35 @@ def test_dependent_atom_is_not_appended(cs, solve_path):
     assert x.nzind.tolist() == [0] and x.nzval.tolist() == [2.0]
 
 
+def test_pipelined_one_shot_matches_single_upload(cs, po, monkeypatch):
+    """Host batches of >= 32 768 signals are cut into whole-wave chunks whose uploads / downloads overlap the solves
+    (csb200_omp / _gomp / _fr one-shot calls).  Results must be bit-identical to the single-upload path, ragged last
+    chunk included, and a NaN anywhere in the batch must still be reported."""
+    rng = np.random.default_rng(5)
+    M, N, k, B = 64, 300, 4, 40001
+    A = po.gaussian_dictionary(rng, M, N)
+    idx = rng.integers(0, N, size=(B, k))
+    Bm = np.asfortranarray((A[:, idx] * rng.choice([-1.0, 1.0], size=(1, B, k))).sum(axis=2) + 1e-3 * rng.standard_normal((M, B)))
+    with cs.Dictionary(A) as D:
+        out = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("CSB200_PIPELINE", mode)
+            out[mode] = (cs.omp(D, Bm, 0.0, k, result="csc"), cs.gomp(D, Bm, 2, 0.0, k, result="csc"),
+                         cs.fr(D, Bm, 0.0, 0.0, k, result="csc"))
+        for a, b in zip(out["1"], out["0"]):
+            assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+            assert np.array_equal(a.data, b.data)
+        for s in (0, 18943, 18944, 40000):
+            ref = po.omp(A, Bm[:, s], k, eps=0.0)
+            col = out["1"][0][:, s]
+            assert col.indices.tolist() == ref.nzind and np.allclose(col.data, ref.nzval, rtol=1e-10, atol=1e-12)
+        monkeypatch.setenv("CSB200_PIPELINE", "1")
+        Bm[5, 30000] = np.nan
+        with pytest.raises(cs.CSB200Error) as ei:
+            cs.omp(D, Bm, 0.0, k)
+        assert ei.value.status == -3
+
+
 # ------------------------------------------------------------------ forward regression / OLS (SURVEY 8f rank 1)
 def test_fr_call_surface(cs, po):
     """`fr` / `ols` / `oomp` / `ormp` (src/forward.jl:33-54) through the one-shot C entry point, against the oracle:
