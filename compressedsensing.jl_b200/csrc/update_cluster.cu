@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
 
     const int sig = blockIdx.x / CL;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int W = RowVec<T>::W;                            // elements per 16-byte load
+    const bool vec = (Mc % W) == 0;                            // every CTA's row slice starts 16-byte aligned
     // uniform over the cluster: every CTA of a cluster reads the same flag
     if (a.done[sig] && !a.ignore_done) return;
     cl.sync();      // every CTA of the cluster is running (its shared memory exists) before any remote store
@@ -130,8 +132,34 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
             double anorm2 = 0.0, before2 = 0.0, rho2 = 0.0, sb = 0.0;
             bool have_norm = false;
             for (int sweep = 0; sweep < 2; ++sweep) {
-                if (t > 0) {
-                    for (int i = warp; i < t; i += CT / 32) {              // partial g = A_S[rows]' v[rows]
+                if (t > 0 && vec) {
+                    // partial g = A_S[rows]' v[rows]: 16-byte loads, four atoms per warp in flight (the sweep is
+                    // latency-bound: 8 CTAs pull t x Mc elements out of L2 with one dependent chain per lane)
+                    for (int i0 = warp * 4; i0 < t; i0 += (CT / 32) * 4) {
+                        double s[4] = {0.0, 0.0, 0.0, 0.0};
+                        const T* ai[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) ai[c] = colp[i0 + c < t ? i0 + c : t - 1];
+#pragma unroll 2
+                        for (int row = lane * W; row < Mc; row += 32 * W) {
+                            double av[4][W];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) RowVec<T>::load(ai[c] + row, av[c]);
+#pragma unroll
+                            for (int e = 0; e < W; ++e) {
+                                const double ve = v[row + e];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) s[c] = fma(av[c][e], ve, s[c]);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const double r4 = warp_sum(s[c]);
+                            if (lane == 0 && i0 + c < t) g[i0 + c] = r4;
+                        }
+                    }
+                } else if (t > 0) {
+                    for (int i = warp; i < t; i += CT / 32) {
                         const T* ai = colp[i];
                         double s = 0.0;
                         for (int row = lane; row < Mc; row += 32) s += (double)ai[row] * v[row];
@@ -157,11 +185,29 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                 }
                 __syncthreads();
                 double p2 = 0.0;
-                for (int row = tid; row < Mc; row += CT) {                 // v -= A_S y on the owned rows
-                    double acc = v[row];
-                    for (int i = 0; i < t; ++i) acc -= (double)colp[i][row] * y[i];
-                    v[row] = acc;
-                    p2 += acc * acc;
+                if (vec) {
+                    for (int row = tid * W; row < Mc; row += CT * W) {     // v -= A_S y on the owned rows, W rows per 16 B load
+                        double acc[W];
+#pragma unroll
+                        for (int e = 0; e < W; ++e) acc[e] = v[row + e];
+#pragma unroll 8
+                        for (int i = 0; i < t; ++i) {
+                            double av[W];
+                            RowVec<T>::load(colp[i] + row, av);
+                            const double yi = y[i];
+#pragma unroll
+                            for (int e = 0; e < W; ++e) acc[e] = fma(-av[e], yi, acc[e]);
+                        }
+#pragma unroll
+                        for (int e = 0; e < W; ++e) { v[row + e] = acc[e]; p2 = fma(acc[e], acc[e], p2); }
+                    }
+                } else {
+                    for (int row = tid; row < Mc; row += CT) {
+                        double acc = v[row];
+                        for (int i = 0; i < t; ++i) acc -= (double)colp[i][row] * y[i];
+                        v[row] = acc;
+                        p2 += acc * acc;
+                    }
                 }
                 p2 = block_sum<CT>(p2, red);
                 if (tid == 0) g[0] = p2;

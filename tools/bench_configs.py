@@ -54,6 +54,17 @@ def make_problem(M, N, k, B, dtype, dev, seed=1234, noise=0.0):
     return A_np, B_np, idx.cpu().numpy()
 
 
+def cpu_oracle(fn, n):
+    """CPU restatement of the reference (oracle/, NumPy + multi-threaded OpenBLAS) timed on n signals of the same
+    workload on this box's host cores: the reported CPU baseline beside each GPU number (kind = "port")."""
+    from oracle import pursuit_oracle  # noqa: F401  (checker used as the CPU baseline only)
+    t0 = time.perf_counter()
+    for s in range(n):
+        fn(s)
+    dt = time.perf_counter() - t0
+    return {"solves_per_s": n / dt, "signals": n, "seconds": dt, "cores": os.cpu_count(), "kind": "port"}
+
+
 def c1(cs, dev, args):
     M, N, k = 128, 256, 8
     A, Bm, idx = make_problem(M, N, k, 64, np.float64, dev)
@@ -74,6 +85,10 @@ def c1(cs, dev, args):
             cs.omp(D, Bm[:, 0], k)
         out["one_shot_host_api_us"] = 1e6 * (time.perf_counter() - t0) / 200
     out.update(config="c1 omp 128x256 k=8 f64", dict_bytes=M * N * 8, iterations=k)
+    if args.cpu:
+        from oracle import pursuit_oracle as po
+        out["cpu_baseline"] = cpu_oracle(lambda s: po.omp(A, Bm[:, s % 64], k, ls="givens"), 256)
+        out["cpu_baseline_us_per_solve"] = 1e6 / out["cpu_baseline"]["solves_per_s"]
     return out
 
 
@@ -90,9 +105,13 @@ def c3(cs, dev, args):
         sel, coef, nnz, res, its = b.download(k)
     rec = float(np.mean([(set(idx[s]) <= set(sel[s, :nnz[s]])) for s in range(0, B, 64)]))
     tf = 2.0 * M * N * B * n / corr_ms / 1e9
-    return dict(config="c3 gomp l=4 2048x32768 k=64 f64", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
-                corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
-                corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
+    out = dict(config="c3 gomp l=4 2048x32768 k=64 f64", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
+               corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+               corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
+    if args.cpu:
+        from oracle import pursuit_oracle as po
+        out["cpu_baseline"] = cpu_oracle(lambda s: po.gomp(A, Bm[:, s], l, k, ls="givens"), 12)
+    return out
 
 
 def fr2(cs, dev, args):
@@ -111,9 +130,13 @@ def fr2(cs, dev, args):
     rec = float(np.mean([(set(idx[s]) <= set(sel[s, :nnz[s]])) for s in range(0, B, 64)]))
     flop = 2.0 * M * N * B * (2 * n - 1)                     # the first pass has no direction half
     tf = flop / corr_ms / 1e9
-    return dict(config="fr/ols 1024x8192 k=32 f64", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
-                corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
-                corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
+    out = dict(config="fr/ols 1024x8192 k=32 f64", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
+               corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+               corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
+    if args.cpu:
+        from oracle import pursuit_oracle as po
+        out["cpu_baseline"] = cpu_oracle(lambda s: po.fr(A, Bm[:, s], 0.0, 0.0, k), 6)
+    return out
 
 
 def sp2(cs, dev, args):
@@ -130,11 +153,15 @@ def sp2(cs, dev, args):
         sel, coef, nnz, res, its = b.download(k)
     rec = float(np.mean([(set(idx[s]) <= set(sel[s, :nnz[s]])) for s in range(0, B, 64)]))
     tf = 2.0 * M * N * B * n / corr_ms / 1e9
-    return dict(config="sp 1024x8192 k=32 f64 noisy", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
-                corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
-                corr_share=corr_ms / ms, update_ms_per_launch=(ms - corr_ms) / max(other, 1),
-                updates_per_signal_mean=float(its.mean()), updates_per_signal_max=int(its.max()),
-                support_recovered_frac=rec, median_resnorm=float(np.median(res)))
+    out = dict(config="sp 1024x8192 k=32 f64 noisy", signals=B, solves_per_s=B / (ms * 1e-3), ms_per_solve_batch=ms,
+               corr_launches=int(n), corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+               corr_share=corr_ms / ms, update_ms_per_launch=(ms - corr_ms) / max(other, 1),
+               updates_per_signal_mean=float(its.mean()), updates_per_signal_max=int(its.max()),
+               support_recovered_frac=rec, median_resnorm=float(np.median(res)))
+    if args.cpu:
+        from oracle import pursuit_oracle as po
+        out["cpu_baseline"] = cpu_oracle(lambda s: po.sp(A, Bm[:, s], k), 48)
+    return out
 
 
 def c5(cs, dev, args):
@@ -149,9 +176,13 @@ def c5(cs, dev, args):
         corr_ms, n, _ = b.corr_time()
         sel, coef, nnz, res, its = b.download(iters)
     tf = 2.0 * M * N * B * n / corr_ms / 1e9
-    return dict(config="c5 mp 4096x65536 f64", iterations=iters, signals=B, solves_per_s=B / (ms * 1e-3),
-                ms_per_solve_batch=ms, corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
-                corr_share=corr_ms / ms, median_resnorm=float(np.median(res)))
+    out = dict(config="c5 mp 4096x65536 f64", iterations=iters, signals=B, solves_per_s=B / (ms * 1e-3),
+               ms_per_solve_batch=ms, corr_ms=corr_ms, corr_tflops=tf, frac_of_fp64_peak=tf / FP64_PEAK,
+               corr_share=corr_ms / ms, median_resnorm=float(np.median(res)))
+    if args.cpu:
+        from oracle import pursuit_oracle as po
+        out["cpu_baseline"] = cpu_oracle(lambda s: po.mp(A, Bm[:, s], iters), 2)
+    return out
 
 
 def c4(cs, dev, args):
@@ -218,6 +249,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5", "fr2", "sp2"])
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a bounded sample (reported baseline)")
     a = ap.parse_args()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
