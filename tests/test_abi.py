@@ -108,6 +108,52 @@ def test_argument_dispatch_mirrors_julia_methods(cs, monkeypatch):
     assert isinstance(out, list) and len(out) == 5 and out[0].n == 12
 
 
+def test_widened_front_ends_dispatch(cs, monkeypatch):
+    """fr / ols / oomp / ormp (src/forward.jl:33-54), sp (src/twostage.jl:105), oblivious (src/oblivious.jl:3):
+    argument forms of the Julia methods, checked without touching the GPU; null handles are rejected by the C ABI."""
+    calls = []
+
+    class FakeLib:
+        def __init__(self, real): self._real = real
+        def __getattr__(self, name): return getattr(self._real, name)
+        def csb200_fr(self, h, B, ldb, nsig, k, max_eps, min_delta, sel, coef, nnz, res, its):
+            calls.append(("fr", k, max_eps, min_delta)); return 0
+        def csb200_sp(self, h, B, ldb, nsig, k, delta, maxiter, sel, coef, nnz, res, its):
+            calls.append(("sp", k, delta, maxiter)); return 0
+        def csb200_oblivious(self, h, B, ldb, nsig, k, sel, coef, nnz, res):
+            calls.append(("oblivious", k)); return 0
+
+    class FakeDict:
+        def __init__(self, A, device=0):
+            self.M, self.N = A.shape; self.n_total = self.N; self.dtype = A.dtype; self._h = None
+        def close(self): pass
+
+    real = cs.lib
+    monkeypatch.setattr(cs, "lib", FakeLib(real))
+    monkeypatch.setattr(cs, "Dictionary", FakeDict)
+    monkeypatch.setattr(cs, "_to_sparse", lambda n, sel, coef, nnz: cs.SparseVector(n, np.zeros(0, np.int64), np.zeros(0)))
+    A = np.zeros((8, 12)); b = np.zeros(8)
+    cs.fr(A, b);                                   assert calls[-1] == ("fr", 8, 0.0, 0.0)      # sparsity = size(A,2), capped at M
+    cs.fr(A, b, sparsity=3);                       assert calls[-1] == ("fr", 3, 0.0, 0.0)
+    cs.fr(A, b, 0.1, 0.2);                         assert calls[-1] == ("fr", 8, 0.1, 0.2)      # k defaults to size(A,1)
+    cs.ols(A, b, 0.1, 0.2, 5);                     assert calls[-1] == ("fr", 5, 0.1, 0.2)
+    cs.oomp(A, b, max_residual=0.3, min_decrease=0.4); assert calls[-1] == ("fr", 8, 0.3, 0.4)
+    with pytest.raises(TypeError):
+        cs.ormp(A, b, 0.1)
+    cs.sp(A, b, 3);                                assert calls[-1] == ("sp", 3, 1e-12, 48)     # maxiter = 16k
+    cs.sp(A, b, 2, 1e-3, maxiter=5);               assert calls[-1] == ("sp", 2, 1e-3, 5)
+    with pytest.raises(ValueError, match="invalid for Subspace Pursuit"):
+        cs.sp(A, b, 5)                                                                        # 2k > M
+    cs.oblivious(A, b, 4);                         assert calls[-1] == ("oblivious", 4)
+    # the real library: null handles / bad arguments come back as status codes, never a crash
+    assert real.csb200_fr(None, None, 8, 1, 3, 0.0, 0.0, None, None, None, None, None) == -1
+    assert real.csb200_sp(None, None, 8, 1, 3, 1e-12, 10, None, None, None, None, None) == -1
+    assert real.csb200_oblivious(None, None, 8, 1, 3, None, None, None, None) == -1
+    assert real.csb200_dict_cumbabel(None, 3, None) == -1 and real.csb200_dict_colnorms(None, None) == -1
+    assert real.csb200_batch_fr(None, 3, 0.0, 0.0) == -1 and real.csb200_batch_sp(None, 3, 0.0, 4) == -1
+    assert real.csb200_batch_oblivious(None, 3) == -1
+
+
 def test_assemble_csc_host_helper(cs):
     """Batched result format: selection-order outputs -> CSC arrays, rows ascending per column."""
     sel = np.array([[5, 2, 9, -1], [-1, -1, -1, -1], [7, 0, -1, -1]], dtype=np.int64)

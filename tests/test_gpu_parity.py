@@ -282,6 +282,51 @@ def test_dependent_atom_is_not_appended(cs, solve_path):
     assert x.nzind.tolist() == [0] and x.nzval.tolist() == [2.0]
 
 
+def test_concurrent_host_threads(cs, po):
+    """SURVEY 8b threading contract: calls on different handles run concurrently from different host threads; calls on
+    one handle are serialised by its mutex.  ctypes releases the GIL for the duration of each C call."""
+    import threading
+    rng = np.random.default_rng(17)
+    M, N, k, B = 96, 400, 6, 64
+    probs = []
+    for _ in range(4):
+        A = po.gaussian_dictionary(rng, M, N)
+        X0, Bm = _planted(po, rng, A, k, B, noise=5e-3)
+        probs.append((A, Bm))
+    shared = cs.Dictionary(probs[0][0])
+    own = [cs.Dictionary(A) for A, _ in probs]
+    results, errors = {}, []
+
+    def work(t):
+        try:
+            A, Bm = probs[t]
+            for rep in range(6):
+                results[(t, "own", rep)] = cs.omp(own[t], Bm, 0.0, k, result="csc")
+                results[(t, "shared", rep)] = cs.gomp(shared, probs[0][1], 2, 0.0, k, result="csc")
+                results[(t, "fr", rep)] = cs.fr(own[t], Bm, sparsity=k, result="csc")
+        except Exception as e:                                   # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads: th.start()
+    for th in threads: th.join()
+    assert not errors, errors
+    for t in range(4):
+        A, Bm = probs[t]
+        for key in ("own", "fr"):
+            first = results[(t, key, 0)]
+            for rep in range(1, 6):
+                other = results[(t, key, rep)]
+                assert np.array_equal(first.indices, other.indices) and np.array_equal(first.data, other.data)
+        ref = po.omp(A, Bm[:, 3], k, eps=0.0)
+        col = results[(t, "own", 0)][:, 3]
+        assert col.indices.tolist() == ref.nzind and np.allclose(col.data, ref.nzval, rtol=1e-10, atol=1e-12)
+        sh = results[(t, "shared", 5)]
+        assert np.array_equal(sh.indices, results[(0, "shared", 0)].indices) and np.array_equal(sh.data, results[(0, "shared", 0)].data)
+    for D in own + [shared]:
+        D.close()
+
+
 def test_pipelined_one_shot_matches_single_upload(cs, po, monkeypatch):
     """Host batches of >= 32 768 signals are cut into whole-wave chunks whose uploads / downloads overlap the solves
     (csb200_omp / _gomp / _fr one-shot calls).  Results must be bit-identical to the single-upload path, ragged last
