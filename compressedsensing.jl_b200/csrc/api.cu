@@ -200,7 +200,7 @@ int run_corr(csb200_batch* b, int S, int impl, bool allow_dense = false) {
     if (impl == IMPL_AUTO) impl = b->corr_impl_env;
     if (impl == IMPL_AUTO) impl = (!f32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
     const int blk = impl == IMPL_GEMM ? corr_gemm_f64_block() : PBLK;
-    const int64_t P = (d->N + blk - 1) / blk;
+    const int64_t P = impl == IMPL_GEMV ? corr_gemv_blocks((int)d->N, (int)d->ld, f32, S, d->num_sms) : (d->N + blk - 1) / blk;
     static const bool dense_off = [] { const char* e = getenv("CSB200_DENSE_TOPK"); return e && e[0] == '0'; }();
     const bool dense = allow_dense && !dense_off && impl == IMPL_GEMM && S >= DENSE_MIN_S && !f32 && d->has_map && b->has_map;
     int rc = dense ? ensure_partials(b, (d->N + 63) / 64, 64, false) : ensure_partials(b, P, S);
@@ -331,7 +331,7 @@ int check_ready(csb200_batch* b) {
 // The update and GEMV kernels keep one signal-length vector (and the k x k inverse factor) in shared memory.
 int check_shape_fits(const csb200_batch* b, bool needs_factor) {
     const csb200_dict* d = b->dict;
-    const size_t gemv = (size_t)d->ld * sizeof(double);
+    const size_t gemv = (size_t)d->ld * sizeof(double) + 2048 * sizeof(double);
     const size_t upd = !needs_factor ? 0
                        : b->nsig < CLUSTER_UPDATE_MAX_SIGNALS ? omp_update_cluster_smem_bytes((int)d->ld, (int)b->kcap)
                                                               : omp_update_smem_bytes((int)d->ld, (int)b->kcap);

@@ -44,6 +44,8 @@ cudaError_t launch_gemm_f64_store(const CUtensorMap* mapA, const CUtensorMap* ma
 // Forward-regression pass (EPI_OLS epilogue): candidates are (delta2, atom); mapQ == nullptr on the first step.
 cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap* mapR, const CUtensorMap* mapQ,
                                      const CorrArgs& a, double* resc, long long ldr, int num_sms, cudaStream_t st);
+// GEMV pass: a.P = corr_gemv_blocks(...) CTAs per signal, each emitting the top-S of its contiguous atom range.
+int corr_gemv_blocks(int N, int ld, bool f32, int S, int num_sms);
 cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st);
 cudaError_t launch_corr_naive(const CorrArgs& a, bool f32, cudaStream_t st);
 

@@ -4,14 +4,13 @@
 // Replaces `mul!(P.Ar, P.A', P.r)` -> BLAS gemv('T'), `@. P.Ar = abs(P.Ar)`, `argmax` /
 // `partialsortperm` (/root/reference/src/matchingpursuit.jl:181-193) for one right-hand side.
 //
-// Layout / mapping.  A is column-major, so the 64 atoms of one atom block are one contiguous
-// run of 64*ld elements: a CTA (8 warps) streams that run once, warp w owning atoms 8w..8w+7 in
-// two register-blocked groups of 4 columns (4 independent 16 B loads in flight per lane per step,
-// the residual chunk loaded once from shared memory and reused by the 4 columns).  Every dot
+// Layout / mapping.  A is column-major, so a CTA's atom range is one contiguous run of the dictionary: its 8 warps
+// stream it once, a warp taking one register-blocked group of 4 columns at a time (4 independent 16 B loads in
+// flight per lane per step, the residual chunk loaded once from shared memory and reused by the 4 columns).  Every dot
 // product is reduced wholly inside one warp in a fixed order and accumulated in FP64 even for an
 // FP32 dictionary (float x float is exact in double; the FP64 pipe is idle on a bandwidth-bound
 // kernel), so c_j does not depend on how atoms are partitioned over CTAs, shards or GPUs.
-// The residual is staged once per CTA in shared memory as doubles.
+// The residual is staged once per CTA in shared memory.
 #include "common.cuh"
 
 namespace csb {
@@ -43,25 +42,44 @@ __device__ __forceinline__ void fma_vec(double& acc, const double2& a, const dou
     acc = fma(a.x, r[0], acc); acc = fma(a.y, r[1], acc);
 }
 
+// Work distribution.  The first version gave every 64-atom block its own CTA: 2048 CTAs of 155 us each on 444 CTA
+// slots is 4.6 waves, i.e. 8 % of the kernel ran with a partly empty GPU (measured 0.92 of the HBM peak).  Now the
+// grid is ONE wave (SMs x resident CTAs, `corr_gemv_blocks`), CTA c owns the contiguous atom range
+// [c Ng / P, (c + 1) Ng / P) in units of 4-column groups (Ng = ceil(N / 4)), and its warps pull groups from a
+// shared-memory counter, so every CTA -- and every warp inside it -- finishes within one group of the others.
+// One candidate record set per (CTA, signal): P = gridDim.x replaces the per-64-atom blocks of the DMMA path.
+constexpr int GEMV_MAX_RANGE = 2048;   // atoms per CTA the top-s (s > 1) scratch can hold
+
 template <typename T>
 __global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
     using V = typename Vec<T>::type;
     constexpr int W = Vec<T>::W;
-    extern __shared__ double rs[];                 // [ld] residual as doubles
-    __shared__ double cv[PBLK];
-    const int p = blockIdx.x, sig = blockIdx.y;
+    extern __shared__ unsigned char gsm[];
+    T* rs = reinterpret_cast<T*>(gsm);                               // [ld] residual
+    double* cv = reinterpret_cast<double*>(gsm + (((size_t)a.ld * sizeof(T) + 15) / 16) * 16);   // [range] |c| (S > 1 only)
+    __shared__ int next_group;
+    __shared__ double red_v[GW];
+    __shared__ int red_i[GW];
+    const int p = blockIdx.x, sig = blockIdx.y, P = gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld;
     const T* A = static_cast<const T*>(a.A);
     const T* r = static_cast<const T*>(a.R) + (size_t)sig * ld;
-    for (int row = tid; row < ld; row += GT) rs[row] = (double)r[row];
+    const long long Ng = (a.N + 3) / 4;
+    const int g_lo = (int)(Ng * p / P), g_hi = (int)(Ng * (p + 1) / P);
+    for (int row = tid; row < ld; row += GT) rs[row] = r[row];
+    if (tid == 0) next_group = g_lo;
     __syncthreads();
 
     const int nvec = ld / W;                       // ld is a multiple of 16 elements
-#pragma unroll
-    for (int grp = 0; grp < CPW / 4; ++grp) {
-        const int local0 = warp * CPW + grp * 4;
-        const int atom0 = p * PBLK + local0;
+    double best_v = -1.0;                          // this warp's running (|c|, atom), warp-uniform
+    int best_i = INT_MAX;
+    for (;;) {
+        int grp = 0;
+        if (lane == 0) grp = atomicAdd(&next_group, 1);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if (grp >= g_hi) break;
+        const int atom0 = grp * 4;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         const V* col[4];
 #pragma unroll
@@ -76,7 +94,7 @@ __global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
             for (int c = 0; c < 4; ++c) x[c] = ldg_stream(col[c] + i);
             double rr[W];
 #pragma unroll
-            for (int e = 0; e < W; ++e) rr[e] = rs[i * W + e];
+            for (int e = 0; e < W; ++e) rr[e] = (double)rs[i * W + e];
 #pragma unroll
             for (int c = 0; c < 4; ++c) fma_vec(acc[c], x[c], rr);
         }
@@ -85,39 +103,64 @@ __global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
             double s = acc[c];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) cv[local0 + c] = (atom0 + c < a.N) ? fabs(s) : -1.0;
+            const double v = fabs(s);
+            const int atom = atom0 + c;
+            if (atom < a.N) {
+                if (a.S == 1) { if (v >= 0.0 && cand_better(v, atom, best_v, best_i)) { best_v = v; best_i = atom; } }   // NaN never wins
+                else if (lane == 0) cv[atom - g_lo * 4] = v;
+            }
         }
     }
-    __syncthreads();
 
-    if (warp == 0) {                               // top-S of the block's 64 |c| values
-        const int base = p * PBLK;
-        double pv = 0.0;
-        int pi = -1;
-        for (int s = 0; s < a.S; ++s) {
-            double bv = -1.0;
-            int bi = INT_MAX;
+    if (a.S == 1) {
+        if (lane == 0) { red_v[warp] = best_v; red_i[warp] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            double bv = red_v[0];
+            int bi = red_i[0];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int local = lane + 32 * e;
-                const double v = cv[local];
-                const int idx = base + local;
-                bool ok = v >= 0.0;                                        // excludes out-of-range atoms and NaN
-                if (s > 0) ok = ok && (v < pv || (v == pv && idx > pi));
-                if (ok && cand_better(v, idx, bv, bi)) { bv = v; bi = idx; }
-            }
+            for (int w = 1; w < GW; ++w)
+                if (cand_better(red_v[w], red_i[w], bv, bi)) { bv = red_v[w]; bi = red_i[w]; }
+            const size_t o = (size_t)sig * P + p;
+            a.pval[o] = bv;
+            a.pidx[o] = (bi == INT_MAX) ? -1 : bi + a.idx_offset;
+        }
+        return;
+    }
+    // top-S of this CTA's range: S block-wide argmax rounds with exclusion (value desc, index asc)
+    __syncthreads();
+    const int base = g_lo * 4;
+    const int range = min(g_hi * 4, a.N) - base;
+    double pv = 0.0;
+    int pi = -1;
+    for (int s = 0; s < a.S; ++s) {
+        double bv = -1.0;
+        int bi = INT_MAX;
+        for (int l = tid; l < range; l += GT) {
+            const double v = cv[l];
+            const int idx = base + l;
+            bool ok = v >= 0.0;                                        // excludes NaN
+            if (s > 0) ok = ok && (v < pv || (v == pv && idx > pi));
+            if (ok && cand_better(v, idx, bv, bi)) { bv = v; bi = idx; }
+        }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-            }
-            pv = bv; pi = bi;
-            if (lane == 0) {
-                const size_t o = ((size_t)sig * a.P + p) * a.S + s;
-                a.pval[o] = bv;
-                a.pidx[o] = (bi == INT_MAX) ? -1 : bi + a.idx_offset;
-            }
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+        __syncthreads();
+        bv = red_v[0]; bi = red_i[0];
+#pragma unroll
+        for (int w = 1; w < GW; ++w)
+            if (cand_better(red_v[w], red_i[w], bv, bi)) { bv = red_v[w]; bi = red_i[w]; }
+        pv = bv; pi = bi;
+        if (tid == 0) {
+            const size_t o = ((size_t)sig * P + p) * a.S + s;
+            a.pval[o] = bv;
+            a.pidx[o] = (bi == INT_MAX) ? -1 : bi + a.idx_offset;
         }
     }
 }
@@ -163,9 +206,40 @@ __global__ void __launch_bounds__(PBLK) corr_naive_kernel(CorrArgs a) {
 
 }  // namespace
 
+namespace {
+size_t gemv_smem_bytes(int ld, bool f32, int S, int range) {
+    size_t bytes = (((size_t)ld * (f32 ? 4 : 8) + 15) / 16) * 16;
+    if (S > 1) bytes += (size_t)range * sizeof(double);
+    return bytes;
+}
+}  // namespace
+
+// Number of CTAs (= candidate record sets per signal) of the GEMV pass: one wave of resident CTAs, but at least 8
+// column groups per CTA and at most GEMV_MAX_RANGE atoms per CTA.
+int corr_gemv_blocks(int N, int ld, bool f32, int S, int num_sms) {
+    const long long Ng = ((long long)N + 3) / 4;
+    int occ = 1;
+    const size_t smem = gemv_smem_bytes(ld, f32, S, GEMV_MAX_RANGE);
+    cudaError_t e;
+    if (f32) {
+        cudaFuncSetAttribute(corr_gemv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, corr_gemv_kernel<float>, GT, smem);
+    } else {
+        cudaFuncSetAttribute(corr_gemv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, corr_gemv_kernel<double>, GT, smem);
+    }
+    if (e != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    long long P = (long long)num_sms * occ;
+    if (P > (Ng + 7) / 8) P = (Ng + 7) / 8;
+    const long long pmin = ((long long)N + GEMV_MAX_RANGE - 8) / (GEMV_MAX_RANGE - 7);   // ranges are uneven by < 8 atoms
+    if (P < pmin) P = pmin;
+    if (P < 1) P = 1;
+    return (int)P;
+}
+
 cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st) {
     if (a.nsig <= 0 || a.P <= 0) return cudaSuccess;
-    const size_t smem = (size_t)a.ld * sizeof(double);
+    const size_t smem = gemv_smem_bytes(a.ld, f32, a.S, GEMV_MAX_RANGE);
     cudaError_t e;
     for (int s0 = 0; s0 < a.nsig; s0 += 65535) {          // gridDim.y limit
         CorrArgs b = a;

@@ -218,7 +218,9 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
     int64_t kcap = k < M ? k : M;
     if (n_total < kcap) kcap = n_total;
     if (kcap < 1) kcap = 1;
-    const int P = (int)((N + PBLK - 1) / PBLK);
+    int num_sms = 148;
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
+    const int P = corr_gemv_blocks((int)N, (int)ld, dtype == CSB200_F32, 1, num_sms);
     const size_t rec_bytes = (REC_HDR + (size_t)ld * es + 15) / 16 * 16;
     cudaStream_t st = c->stream;
 
