@@ -235,7 +235,9 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
     o.send = take(rec_bytes); o.recv = take(rec_bytes * c->nranks); o.end = p;
     unsigned char* base = nullptr;
     CU_TRY(cudaMalloc(&base, o.end));
-    std::vector<cudaEvent_t> ev(2 * (size_t)k);
+    const char* tenv = getenv("CSB200_SHARD_TIMING");           // debug: per-phase device times on stderr
+    const bool timing = tenv && tenv[0] == '1';
+    std::vector<cudaEvent_t> ev((timing ? 4 : 2) * (size_t)k);
     int status = CSB200_OK;
     auto cleanup = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); cudaFree(base); };
     for (auto& e : ev) { e = nullptr; }
@@ -279,7 +281,9 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
             if (nr != ncclSuccess) { status = fail_nccl(nr, "ncclAllGather"); break; }
             if (f32) global_pick_kernel<float><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (float*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
             else global_pick_kernel<double><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (double*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+            if (timing) cudaEventRecord(ev[2 * k + 2 * it], st);
             e = launch_omp_update_cluster(sa, f32, st, base + o.acache);
+            if (timing) cudaEventRecord(ev[2 * k + 2 * it + 1], st);
             if (e != cudaSuccess) { status = fail_cuda(e, "omp_update"); break; }
         }
         if (status) break;
@@ -305,6 +309,18 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
             double tot = 0;
             for (int64_t it = 0; it < k; ++it) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * it], ev[2 * it + 1]); tot += ms; }
             *corr_ms = tot;
+        }
+        if (timing && k > 0) {
+            double gemv = 0, exch = 0, upd = 0, gap = 0;
+            for (int64_t it = 0; it < k; ++it) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ev[2 * it], ev[2 * it + 1]); gemv += ms;
+                cudaEventElapsedTime(&ms, ev[2 * it + 1], ev[2 * k + 2 * it]); exch += ms;
+                cudaEventElapsedTime(&ms, ev[2 * k + 2 * it], ev[2 * k + 2 * it + 1]); upd += ms;
+                if (it + 1 < k) { cudaEventElapsedTime(&ms, ev[2 * k + 2 * it + 1], ev[2 * (it + 1)]); gap += ms; }
+            }
+            fprintf(stderr, "[csb200 shard rank %d/%d] per iteration (us): gemv %.1f  local-best+allgather+pick %.1f  update %.1f  gap %.1f\n",
+                    c->rank, c->nranks, 1e3 * gemv / k, 1e3 * exch / k, 1e3 * upd / k, 1e3 * gap / k);
         }
     } while (0);
     cudaStreamSynchronize(st);
