@@ -675,6 +675,44 @@ def test_c2_full_size_properties(cs, po):
     assert res.max() < 1e-12
 
 
+@pytest.mark.slow
+def test_widened_rows_full_c2_shape_properties(cs, po):
+    """fr, sp and oblivious at the config-2 dictionary shape on 16 384 signals (the sizes the oracle cannot reach):
+    size-independent properties -- planted supports recovered with coefficients +-1 (fr, sp), the residual orthogonal
+    to the active atoms, oblivious = the k largest |A'b|, and the one-shot (pipelined) call agreeing with the batch API."""
+    rng = np.random.default_rng(4321)
+    M, N, k, B = 1024, 8192, 24, 16384
+    A = po.gaussian_dictionary(rng, M, N)
+    idx = np.sort(np.stack([rng.choice(N, size=k, replace=False) for _ in range(B)]), axis=1)
+    sign = rng.choice(np.array([-1.0, 1.0]), size=(B, k))
+    Bm = np.empty((M, B), order="F")
+    for s0 in range(0, B, 512):
+        blk = slice(s0, min(B, s0 + 512))
+        Bm[:, blk] = np.einsum("mbk,bk->mb", A[:, idx[blk]], sign[blk])
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 2 * k) as batch:
+        batch.upload(Bm)
+        for algo in ("fr", "sp"):
+            getattr(batch, algo)(k)
+            sel, coef, nnz, res, its = batch.download(k)
+            assert (nnz == k).all(), algo
+            order = np.argsort(sel, axis=1)
+            assert np.array_equal(np.take_along_axis(sel, order, axis=1), idx), algo
+            assert np.allclose(np.take_along_axis(coef, order, axis=1), sign, rtol=1e-9, atol=1e-9), algo
+            assert res.max() < 1e-11, algo
+            R = batch.residual()
+            for s in range(0, B, 1024):
+                assert np.abs(A[:, idx[s]].T @ R[:, s]).max() < 1e-12
+        batch.oblivious(k)
+        osel, ocoef, onnz, ores, _ = batch.download(k)
+        C = np.abs(A.T @ Bm[:, :64])
+        for s in range(64):
+            assert sorted(osel[s].tolist()) == sorted(np.argsort(-C[:, s], kind="stable")[:k].tolist())
+            c, *_ = np.linalg.lstsq(A[:, osel[s]], Bm[:, s], rcond=None)
+            assert np.allclose(ocoef[s], c, rtol=1e-9, atol=1e-11)
+        X = cs.fr(D, Bm, sparsity=k, result="csc")
+        assert np.array_equal(X.indices.reshape(B, k), idx) and np.allclose(X.data.reshape(B, k), sign, rtol=1e-9)
+
+
 # ------------------------------------------------------------------ column-sharded mode
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_sharded_single_rank_matches_oracle(cs, po, dtype):
