@@ -193,7 +193,7 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
 // One correlation pass over the current residuals, leaving top-S candidates per (atom block, signal) -- or, when the
 // caller can consume it (allow_dense) and S is large, the dense |A'r| matrix: S selection rounds in the DMMA epilogue
 // cost as much as the contraction itself at S = 32, a plain store costs nothing.
-constexpr int DENSE_MIN_S = 8;
+constexpr int DENSE_MIN_S = 2;      // S = 1 keeps the fused per-block argmax (no N x nsig matrix); from 2 on the store wins
 int run_corr(csb200_batch* b, int S, int impl, bool allow_dense = false) {
     csb200_dict* d = b->dict;
     const bool f32 = d->dtype == CSB200_F32;
@@ -202,7 +202,8 @@ int run_corr(csb200_batch* b, int S, int impl, bool allow_dense = false) {
     const int blk = impl == IMPL_GEMM ? corr_gemm_f64_block() : PBLK;
     const int64_t P = impl == IMPL_GEMV ? corr_gemv_blocks((int)d->N, (int)d->ld, f32, S, d->num_sms) : (d->N + blk - 1) / blk;
     static const bool dense_off = [] { const char* e = getenv("CSB200_DENSE_TOPK"); return e && e[0] == '0'; }();
-    const bool dense = allow_dense && !dense_off && impl == IMPL_GEMM && S >= DENSE_MIN_S && !f32 && d->has_map && b->has_map;
+    static const int dense_min_s = [] { const char* e = getenv("CSB200_DENSE_MIN_S"); return e ? atoi(e) : DENSE_MIN_S; }();
+    const bool dense = allow_dense && !dense_off && impl == IMPL_GEMM && S >= dense_min_s && !f32 && d->has_map && b->has_map;
     int rc = dense ? ensure_partials(b, (d->N + 63) / 64, 64, false) : ensure_partials(b, P, S);
     if (rc) return rc;
     b->cur_P = (int)P;

@@ -188,12 +188,75 @@ __device__ void select_dense(const double* __restrict__ v, int n, int idx_offset
     __syncthreads();
 }
 
+// Small `take` (<= DENSE_SMALL_TAKE, gomp with a few atoms per update): ONE streaming pass over the dense row.  Every
+// thread keeps the `take` best of its strided share in registers (sorted, insertion is rare after the first few
+// elements), the NT x take survivors go to shared scratch and select_candidates merges them.  The top-`take` of the
+// row is contained in the union of the per-thread top-`take` lists, so the result is exact, ties included.
+constexpr int DENSE_SMALL_TAKE = 8;
+
+template <int NT, int TK>
+__device__ __forceinline__ void select_dense_small_t(const double* __restrict__ v, int n, int idx_offset, int* s_cand,
+                                                     double* s_cval, double* red_v, int* red_i, double* scratch) {
+    const int tid = threadIdx.x;
+    double bv[TK];
+    int bi[TK];
+#pragma unroll
+    for (int q = 0; q < TK; ++q) { bv[q] = -1.0; bi[q] = INT_MAX; }
+    constexpr int U = 8;                                             // independent loads in flight per thread
+    for (int c0 = tid; c0 < n; c0 += NT * U) {
+        double vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int c = c0 + u * NT; vv[u] = c < n ? fabs(v[c]) : -1.0; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double val = vv[u];
+            const int c = c0 + u * NT;
+            if (val >= 0.0 && cand_better(val, c, bv[TK - 1], bi[TK - 1])) {   // beats the worst entry kept so far
+                double cv = val;
+                int ci = c;
+#pragma unroll
+                for (int q = 0; q < TK; ++q) {                                 // bubble the newcomer down the sorted list
+                    if (cand_better(cv, ci, bv[q], bi[q])) {
+                        const double tv = bv[q]; const int ti = bi[q];
+                        bv[q] = cv; bi[q] = ci; cv = tv; ci = ti;
+                    }
+                }
+            }
+        }
+    }
+    double* cval = scratch;                                         // [NT * TK]
+    int* cidx = reinterpret_cast<int*>(scratch + (size_t)NT * TK);  // [NT * TK]
+#pragma unroll
+    for (int q = 0; q < TK; ++q) { cval[tid * TK + q] = bv[q]; cidx[tid * TK + q] = bi[q] == INT_MAX ? -1 : bi[q] + idx_offset; }
+    __syncthreads();
+    select_candidates<NT>(cval, cidx, NT * TK, TK, s_cand, s_cval, red_v, red_i);
+}
+
+template <int NT>
+__device__ void select_dense_small(const double* __restrict__ v, int n, int idx_offset, int take, int* s_cand,
+                                   double* s_cval, double* red_v, int* red_i, double* scratch) {
+    switch (take) {
+        case 1: select_dense_small_t<NT, 1>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+        case 2: select_dense_small_t<NT, 2>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+        case 3: select_dense_small_t<NT, 3>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+        case 4: select_dense_small_t<NT, 4>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+        case 5: select_dense_small_t<NT, 5>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+        case 6: select_dense_small_t<NT, 6>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+        case 7: select_dense_small_t<NT, 7>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+        default: select_dense_small_t<NT, 8>(v, n, idx_offset, s_cand, s_cval, red_v, red_i, scratch); break;
+    }
+}
+
 // Either form of the candidates a correlation pass left for signal `sig`.
 template <int NT>
 __device__ __forceinline__ void select_any(const StateArgs& a, int sig, int take, int cap, int* s_cand, double* s_cval,
                                            double* red_v, int* red_i, int* hist, double* stage = nullptr,
                                            int stage_elems = 0) {
-    if (a.dense_ld > 0) {
+    if (a.dense_ld > 0 && take <= DENSE_SMALL_TAKE && stage && stage_elems + DENSE_HIST / 2 >= NT * take * 2) {
+        // the scratch handed in as histogram + staging area is one contiguous region starting at `hist`
+        select_dense_small<NT>(a.pval + (size_t)sig * a.dense_ld, a.N, a.idx_offset, take, s_cand, s_cval, red_v, red_i,
+                               reinterpret_cast<double*>(hist));
+    } else if (a.dense_ld > 0) {
         select_dense<NT>(a.pval + (size_t)sig * a.dense_ld, a.N, a.idx_offset, take, cap, s_cand, s_cval, hist, red_i,
                          stage, stage_elems);
     } else {
