@@ -96,6 +96,11 @@ struct csb200_dict {
     csb200_batch* workspace = nullptr;   // reused by the one-shot entry points (csb200_omp/gomp/mp)
     csb200_batch* pipe_ws[2] = {nullptr, nullptr};   // ping-pong workspaces of the pipelined one-shot path (large batches)
     double* gram = nullptr;              // A'A (N x N, FP64), built on first use by a large batched omp/gomp
+    // FP32 dictionaries: batched solves (>= GEMM_MIN_SIGNALS signals) run on an FP64 twin of the dictionary so that
+    // they take the DMMA path (float x float products are exact in double: at least as accurate as an FP32 gemv)
+    csb200_dict* twin64 = nullptr;
+    std::mutex twin_mu;
+    bool twin_failed = false;
     bool gram_failed = false;
     size_t esize() const { return dtype == CSB200_F32 ? 4 : 8; }
 };
@@ -135,6 +140,8 @@ struct csb200_batch {
     cudaEvent_t ev_solve0 = nullptr, ev_solve1 = nullptr;   // bracket the last solve
     bool solve_timed = false;
     int corr_impl_env = IMPL_AUTO;
+    bool src_f32 = false;       // the batch lives on the FP64 twin of an FP32 dictionary: uploads arrive as FP32
+    float* stage32 = nullptr;   // device staging for those uploads (ld x cap_sig floats)
     bool defer_finish = false;  // pipelined one-shot path: a solve only enqueues its work, the caller synchronises later
     std::mutex mu;
 };
@@ -145,7 +152,7 @@ int begin_solve_fwd(csb200_batch* b);
 
 void free_batch_mem(csb200_batch* b) {
     cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->state_blk);
-    cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2); cudaFree(b->ndone);
+    cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->stage32); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2); cudaFree(b->ndone);
     if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
@@ -503,6 +510,7 @@ int csb200_dict_destroy(csb200_dict* d) {
     cudaSetDevice(d->device);
     if (d->workspace) csb200_batch_destroy(d->workspace);
     for (auto& w : d->pipe_ws) if (w) csb200_batch_destroy(w);
+    if (d->twin64) csb200_dict_destroy(d->twin64);
     cudaFree(d->gram);
     cudaFree(d->dA);
     delete d;
@@ -518,15 +526,50 @@ int csb200_dict_shape(const csb200_dict* d, int64_t* M, int64_t* N, int* dtype, 
     return CSB200_OK;
 }
 
+// FP64 twin of an FP32 dictionary (built on the device, cached on the handle); nullptr if it does not fit.
+static csb200_dict* promoted_dict(csb200_dict* d) {
+    const char* env = getenv("CSB200_PROMOTE_F32");              // test hook: 0 keeps FP32 batches on the GEMV path
+    if (env && env[0] == '0') return nullptr;
+    if (d->dtype != CSB200_F32 || d->n_total != d->N) return nullptr;
+    std::lock_guard<std::mutex> lk(d->twin_mu);
+    if (d->twin64 || d->twin_failed) return d->twin64;
+    if (cudaSetDevice(d->device) != cudaSuccess) return nullptr;
+    const size_t bytes = (size_t)d->ld * d->N * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || bytes > free_b / 4) { cudaGetLastError(); d->twin_failed = true; return nullptr; }
+    csb200_dict* t = new (std::nothrow) csb200_dict;
+    if (!t) return nullptr;
+    t->device = d->device; t->dtype = CSB200_F64; t->M = d->M; t->N = d->N; t->ld = d->ld;
+    t->n_offset = 0; t->n_total = d->N; t->num_sms = d->num_sms;
+    cudaError_t e = cudaMalloc(&t->dA, bytes);
+    if (e == cudaSuccess) e = launch_widen_f32(static_cast<const float*>(d->dA), d->ld, static_cast<double*>(t->dA), t->ld, (int)d->ld, d->N, nullptr);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && make_operand_map(&t->mapA, t->dA, t->ld, t->N) == CSB200_OK) t->has_map = true;
+    if (e == cudaSuccess && t->has_map) e = corr_gemm_f64_setup();
+    if (e != cudaSuccess || !t->has_map) { cudaGetLastError(); cudaFree(t->dA); delete t; d->twin_failed = true; return nullptr; }
+    d->twin64 = t;
+    return t;
+}
+
+static int batch_create_ex(csb200_dict* d, int64_t max_signals, int64_t max_sparsity, bool force_promote, csb200_batch** out);
+
 int csb200_batch_create(csb200_dict* d, int64_t max_signals, int64_t max_sparsity, csb200_batch** out) {
+    return batch_create_ex(d, max_signals, max_sparsity, false, out);
+}
+
+static int batch_create_ex(csb200_dict* d, int64_t max_signals, int64_t max_sparsity, bool force_promote, csb200_batch** out) {
     if (!d || !out || max_signals <= 0 || max_sparsity < 0) return CSB200_ERR_INVALID_ARG;
     if (max_signals > (int64_t)INT_MAX / 2) return CSB200_ERR_UNSUPPORTED;
     *out = nullptr;
     int rc = set_device(d);
     if (rc) return rc;
+    bool src_f32 = false;
+    if (d->dtype == CSB200_F32 && (force_promote || max_signals >= GEMM_MIN_SIGNALS)) {
+        if (csb200_dict* t = promoted_dict(d)) { d = t; src_f32 = true; }
+    }
     csb200_batch* b = new (std::nothrow) csb200_batch;
     if (!b) return CSB200_ERR_OOM;
-    b->dict = d; b->cap_sig = max_signals;
+    b->dict = d; b->cap_sig = max_signals; b->src_f32 = src_f32;
     b->kcap = max_sparsity < 1 ? 1 : max_sparsity;
     const char* env = getenv("CSB200_CORR_IMPL");
     if (env) {
@@ -558,6 +601,7 @@ int csb200_batch_create(csb200_dict* d, int64_t max_signals, int64_t max_sparsit
         if (e == cudaSuccess && b->host_stage_bytes) e = cudaMallocHost((void**)&b->host_stage, b->host_stage_bytes);
     }
     alloc((void**)&b->dflag, sizeof(int));
+    if (src_f32) alloc((void**)&b->stage32, (size_t)d->ld * ns * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_solve0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev_solve1);
@@ -575,6 +619,31 @@ int csb200_batch_destroy(csb200_batch* b) {
     return CSB200_OK;
 }
 
+// Signals (M x nsig, leading dimension ldb, the element type the caller's dictionary has) -> b->dB, on b->stream.
+static int copy_signals_in(csb200_batch* b, const void* src, int64_t ldb, int64_t nsig, cudaMemcpyKind kind) {
+    csb200_dict* d = b->dict;
+    if (b->src_f32) {                           // FP32 signals for the FP64 twin: stage, then widen on the device
+        const float* in = static_cast<const float*>(src);
+        long long ld_in = ldb;
+        if (kind == cudaMemcpyHostToDevice) {
+            CU_TRY(cudaMemcpy2DAsync(b->stage32, d->ld * sizeof(float), src, ldb * sizeof(float), d->M * sizeof(float), nsig, kind, b->stream));
+            in = b->stage32; ld_in = d->ld;
+        }
+        if (d->ld != d->M) CU_TRY(cudaMemsetAsync(b->dB, 0, (size_t)d->ld * nsig * sizeof(double), b->stream));
+        cudaError_t e = launch_widen_f32(in, ld_in, static_cast<double*>(b->dB), d->ld, (int)d->M, nsig, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "widen signals");
+        return CSB200_OK;
+    }
+    const size_t es = d->esize();
+    if (d->ld == d->M && ldb == d->M) {
+        CU_TRY(cudaMemcpyAsync(b->dB, src, (size_t)d->M * nsig * es, kind, b->stream));
+    } else {
+        if (d->ld != d->M) CU_TRY(cudaMemsetAsync(b->dB, 0, (size_t)d->ld * nsig * es, b->stream));
+        CU_TRY(cudaMemcpy2DAsync(b->dB, d->ld * es, src, ldb * es, d->M * es, nsig, kind, b->stream));
+    }
+    return CSB200_OK;
+}
+
 static int upload_common(csb200_batch* b, const void* src, int64_t ldb, int64_t nsig, cudaMemcpyKind kind,
                          bool allow_lazy = false) {
     if (!b || !src || nsig <= 0) return CSB200_ERR_INVALID_ARG;
@@ -584,13 +653,7 @@ static int upload_common(csb200_batch* b, const void* src, int64_t ldb, int64_t 
     std::lock_guard<std::mutex> lk(b->mu);
     int rc = set_device(d);
     if (rc) return rc;
-    const size_t es = d->esize();
-    if (d->ld == d->M && ldb == d->M) {
-        CU_TRY(cudaMemcpyAsync(b->dB, src, (size_t)d->M * nsig * es, kind, b->stream));
-    } else {
-        if (d->ld != d->M) CU_TRY(cudaMemsetAsync(b->dB, 0, (size_t)d->ld * nsig * es, b->stream));
-        CU_TRY(cudaMemcpy2DAsync(b->dB, d->ld * es, src, ldb * es, d->M * es, nsig, kind, b->stream));
-    }
+    if ((rc = copy_signals_in(b, src, ldb, nsig, kind))) return rc;
     return after_upload(b, nsig, allow_lazy);
 }
 
@@ -937,16 +1000,18 @@ int csb200_batch_last_solve_ms(csb200_batch* b, double* ms) {
 // enough (device allocation and release of ~2 GB per call would otherwise dominate small-k solves);
 // csb200_dict_trim() releases it.  The dictionary mutex serialises one-shot calls on one handle.
 static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t kcap, csb200_batch** out,
-                    bool allow_lazy = true) {
+                    bool allow_lazy = true, bool force_promote = false) {
     if (!d || !Bmat || nsig <= 0) return CSB200_ERR_INVALID_ARG;
     int64_t cap = kcap < 1 ? 1 : kcap;
     csb200_batch* w = d->workspace;
-    if (w && (w->cap_sig < nsig || w->kcap < cap || w->cap_sig > 4 * nsig + 1024)) {
+    const bool want_f64 = d->dtype == CSB200_F32 && (force_promote || nsig >= GEMM_MIN_SIGNALS);
+    if (w && (w->cap_sig < nsig || w->kcap < cap || w->cap_sig > 4 * nsig + 1024 ||
+              (d->dtype == CSB200_F32 && w->src_f32 != want_f64 && !(want_f64 && d->twin_failed)))) {
         csb200_batch_destroy(w);
         d->workspace = w = nullptr;
     }
     if (!w) {
-        int rc = csb200_batch_create(d, nsig, cap, &w);
+        int rc = batch_create_ex(d, nsig, cap, force_promote, &w);
         if (rc) return rc;
         d->workspace = w;
     }
@@ -983,13 +1048,8 @@ struct PipeOut { int64_t* sel_idx; double* coef; int64_t* nnz; double* resnorm; 
 
 static int pipe_upload_async(csb200_batch* w, const void* src, int64_t ldb, int64_t nsig) {
     csb200_dict* d = w->dict;
-    const size_t es = d->esize();
-    if (d->ld == d->M && ldb == d->M) {
-        CU_TRY(cudaMemcpyAsync(w->dB, src, (size_t)d->M * nsig * es, cudaMemcpyHostToDevice, w->stream));
-    } else {
-        if (d->ld != d->M) CU_TRY(cudaMemsetAsync(w->dB, 0, (size_t)d->ld * nsig * es, w->stream));
-        CU_TRY(cudaMemcpy2DAsync(w->dB, d->ld * es, src, ldb * es, d->M * es, nsig, cudaMemcpyHostToDevice, w->stream));
-    }
+    int rc0 = copy_signals_in(w, src, ldb, nsig, cudaMemcpyHostToDevice);
+    if (rc0) return rc0;
     w->nsig = nsig; w->has_map = false; w->cur_P = 0; w->lazy_input_check = false;
     int rc = ensure_signal_map(w);
     if (rc) return rc;
@@ -998,6 +1058,7 @@ static int pipe_upload_async(csb200_batch* w, const void* src, int64_t ldb, int6
     if (e != cudaSuccess) return fail_cuda(e, "nonfinite check");
     return CSB200_OK;
 }
+static size_t caller_esize(const csb200_dict* d) { return d->dtype == CSB200_F32 ? 4 : 8; }
 
 static int pipe_complete(csb200_batch* w, int64_t stride, const PipeOut& o, int64_t s0) {
     CU_TRY(cudaStreamSynchronize(w->stream));
@@ -1045,7 +1106,7 @@ static int one_shot_pipelined(csb200_dict* d, const void* Bmat, int64_t ldb, int
         }
         if (first_err) break;
         const int64_t s0 = c * PIPE_CHUNK, nc = nsig - s0 < PIPE_CHUNK ? nsig - s0 : PIPE_CHUNK;
-        rc = pipe_upload_async(w, (const char*)Bmat + (size_t)s0 * ldb * es, ldb, nc);
+        rc = pipe_upload_async(w, (const char*)Bmat + (size_t)s0 * ldb * caller_esize(d), ldb, nc);
         if (!rc && prev) {
             cudaError_t e = cudaStreamWaitEvent(w->stream, prev->ev_solve1, 0);
             if (e != cudaSuccess) rc = fail_cuda(e, "cudaStreamWaitEvent");
@@ -1127,7 +1188,7 @@ int csb200_fr(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64
         return one_shot_pipelined(d, Bmat, ldb, nsig, cap, k,
                                   [&](csb200_batch* w) { return csb200_batch_fr(w, k, max_eps, min_delta); },
                                   PipeOut{sel_idx, coef, nnz, resnorm, iters});
-    int rc = one_shot(d, Bmat, ldb, nsig, cap, &b, /*allow_lazy=*/false);
+    int rc = one_shot(d, Bmat, ldb, nsig, cap, &b, /*allow_lazy=*/false, /*force_promote=*/true);
     if (rc) return rc;
     rc = csb200_batch_fr(b, k, max_eps, min_delta);
     if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
@@ -1204,14 +1265,15 @@ int csb200_dict_cumbabel(csb200_dict* d, int64_t k, double* mu_out) {
     cudaError_t e = cudaMalloc(&dmu, (size_t)k * sizeof(double));
     if (e != cudaSuccess) { csb200_batch_destroy(b); return fail_cuda(e, "cudaMalloc"); }
     const int S = (int)(k + 1 < PBLK ? k + 1 : PBLK);
-    const size_t es = d->esize();
+    const csb200_dict* dd = b->dict;                 // the FP64 twin when the dictionary is FP32 and the chunk is a batch
+    const size_t es = dd->esize();
     do {
         e = cudaMemsetAsync(dmu, 0, (size_t)k * sizeof(double), b->stream);
         if (e != cudaSuccess) { rc = fail_cuda(e, "memset"); break; }
         for (int64_t c0 = 0; c0 < d->N && !rc; c0 += chunk) {
             const int64_t nc = d->N - c0 < chunk ? d->N - c0 : chunk;
             // residual matrix := the chunk's atoms (padded rows are zero in the dictionary already)
-            e = cudaMemcpyAsync(b->dR, (const char*)d->dA + (size_t)c0 * d->ld * es, (size_t)nc * d->ld * es,
+            e = cudaMemcpyAsync(b->dR, (const char*)dd->dA + (size_t)c0 * dd->ld * es, (size_t)nc * dd->ld * es,
                                 cudaMemcpyDeviceToDevice, b->stream);
             if (e != cudaSuccess) { rc = fail_cuda(e, "copy atoms"); break; }
             b->nsig = nc; b->has_map = false; b->cur_P = 0;
@@ -1282,6 +1344,14 @@ int csb200_debug_get_residual(csb200_batch* b, void* out) {
     csb200_dict* d = b->dict;
     if ((rc = set_device(d))) return rc;
     const size_t es = d->esize();
+    if (b->src_f32) {                           // the caller's dictionary is FP32: hand the residual back in that type
+        std::vector<double> tmp((size_t)d->M * b->nsig);
+        CU_TRY(cudaMemcpy2DAsync(tmp.data(), d->M * es, b->dR, d->ld * es, d->M * es, b->nsig, cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaStreamSynchronize(b->stream));
+        float* o = static_cast<float*>(out);
+        for (size_t i = 0; i < tmp.size(); ++i) o[i] = (float)tmp[i];
+        return CSB200_OK;
+    }
     CU_TRY(cudaMemcpy2DAsync(out, d->M * es, b->dR, d->ld * es, d->M * es, b->nsig, cudaMemcpyDeviceToHost, b->stream));
     CU_TRY(cudaStreamSynchronize(b->stream));
     return CSB200_OK;

@@ -118,5 +118,8 @@ cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx,
 cudaError_t launch_topk_from_partials(const StateArgs& a, int s, long long* out_idx, double* out_val,
                                       cudaStream_t st);
 cudaError_t launch_nonfinite_check(const void* p, size_t n, bool f32, int* flag, cudaStream_t st);
+// FP32 -> FP64 copy of a column-major matrix (batched solves on FP32 dictionaries run on an FP64 twin)
+cudaError_t launch_widen_f32(const float* in, long long ld_in, double* out, long long ld_out, int rows, long long cols,
+                             cudaStream_t st);
 
 }  // namespace csb

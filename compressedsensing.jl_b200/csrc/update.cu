@@ -657,6 +657,22 @@ cudaError_t launch_topk_from_partials(const StateArgs& a, int s, long long* out_
     return cudaGetLastError();
 }
 
+// out[col * ld_out + row] = (double) in[col * ld_in + row] for row < rows (rows >= `rows` of `out` are left alone)
+__global__ void widen_f32_kernel(const float* __restrict__ in, long long ld_in, double* __restrict__ out, long long ld_out,
+                                 int rows, long long cols) {
+    for (long long col = blockIdx.y; col < cols; col += gridDim.y)
+        for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += gridDim.x * blockDim.x)
+            out[col * ld_out + row] = (double)in[col * ld_in + row];
+}
+
+cudaError_t launch_widen_f32(const float* in, long long ld_in, double* out, long long ld_out, int rows, long long cols,
+                             cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((rows + 255) / 256 < 8 ? (rows + 255) / 256 : 8), (unsigned)(cols < 32768 ? cols : 32768));
+    widen_f32_kernel<<<grid, 256, 0, st>>>(in, ld_in, out, ld_out, rows, cols);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_nonfinite_check(const void* p, size_t n, bool f32, int* flag, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);

@@ -60,6 +60,9 @@ int csb200_device_count(void);
  * (src/matchingpursuit.jl:18-24, 54-60, 108-114).  A is M x N column-major (M rows =
  * signal length, N atoms), lda >= M elements.  The dictionary is copied to `device`
  * (HBM-resident for the life of the handle) and checked for NaN/Inf.
+ * FP32 dictionaries: batches created with max_signals >= 24 (and csb200_fr) are solved on an FP64 copy of the
+ * dictionary kept on the handle (built on first use; exact float x float products, FP64 accumulation); signals are
+ * still passed as FP32.  Smaller batches stream the FP32 dictionary (HBM-bound GEMV path).
  * n_offset / n_total describe a column shard: this handle holds atoms
  * [n_offset, n_offset + N) of a dictionary with n_total atoms; pass 0 and N when unsharded.
  */

@@ -282,6 +282,52 @@ def test_dependent_atom_is_not_appended(cs, solve_path):
     assert x.nzind.tolist() == [0] and x.nzval.tolist() == [2.0]
 
 
+def test_f32_dictionary_batches_take_the_dmma_path(cs, po, monkeypatch):
+    """FP32 dictionaries: a batch of >= 24 signals runs on an FP64 twin of the dictionary (exact float x float products,
+    DMMA path) -- against the FP32 oracle within the FP32 bound, against the per-signal GEMV path (CSB200_PROMOTE_F32=0),
+    Float64 result vectors either way; fr becomes available for FP32 input through the one-shot call."""
+    rng = np.random.default_rng(41)
+    M, N, k, B = 96, 400, 7, 64
+    A = po.gaussian_dictionary(rng, M, N, np.float32)
+    X0, Bm = _planted(po, rng, A.astype(np.float64), k, B, noise=1e-2)
+    Bm = np.asfortranarray(Bm.astype(np.float32))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CSB200_PROMOTE_F32", mode)
+        with cs.Dictionary(A) as D, cs.Batch(D, B, k) as batch:
+            batch.upload(Bm)
+            batch.omp(k, 0.0)
+            out[mode] = batch.download(k) + (batch.residual(),)
+            batch.gomp(3, k, 0.0)
+            out["g" + mode] = batch.download(k)
+    monkeypatch.setenv("CSB200_PROMOTE_F32", "1")
+    sel, coef, nnz, res, its, R = out["1"]
+    assert R.dtype == np.float32 and coef.dtype == np.float64
+    for s in range(B):
+        t = po.Trace()
+        ref = po.omp(A, Bm[:, s], k, eps=0.0, trace=t)
+        if min(t.margin) < 1e-4:
+            continue
+        assert sel[s, :k].tolist() == t.order(), s
+        assert out["0"][0][s, :k].tolist() == t.order(), s
+        idx, val = _sorted(sel[s], coef[s], k)
+        assert _close(val, ref.nzval, RTOL32), s
+        assert _close(out["0"][1][s], coef[s], RTOL32)
+        assert abs(res[s] - t.resnorm[-1]) < 1e-5
+        assert np.allclose(R[:, s], Bm[:, s].astype(np.float64) - A[:, idx].astype(np.float64) @ val, atol=1e-5)
+        t = po.Trace()
+        ref = po.gomp(A, Bm[:, s], 3, k, eps=0.0, trace=t)
+        if min(t.margin) > 1e-4:
+            assert out["g1"][0][s, :k].tolist() == t.order() == out["g0"][0][s, :k].tolist(), s
+    with cs.Dictionary(A) as D:
+        xs = cs.fr(D, Bm[:, :5], sparsity=k)                 # fewer than 24 signals: the one-shot fr call still promotes
+        for s in range(5):
+            ref = po.fr(A.astype(np.float64), Bm[:, s].astype(np.float64), 0.0, 0.0, k)
+            assert xs[s].nzind.tolist() == ref.nzind and _close(xs[s].nzval, ref.nzval, 1e-9)
+        mu = cs.cumbabel(D, 5)
+        assert np.allclose(mu, po.cumbabel(A, 5), rtol=1e-5)
+
+
 def test_concurrent_host_threads(cs, po):
     """SURVEY 8b threading contract: calls on different handles run concurrently from different host threads; calls on
     one handle are serialised by its mutex.  ctypes releases the GIL for the duration of each C call."""
@@ -380,9 +426,9 @@ def test_fr_call_surface(cs, po):
         for s in range(3):
             ref = po.fr(A, Bm[:, s], 0.0, 0.0, 4)
             assert out[s].nzind.tolist() == ref.nzind and _close(out[s].nzval, ref.nzval, RTOL64)
-    with pytest.raises(cs.CSB200Error) as ei:
-        cs.fr(A.astype(np.float32), y.astype(np.float32), sparsity=3)
-    assert ei.value.status == -7
+    got = cs.fr(A.astype(np.float32), y.astype(np.float32), sparsity=4)      # FP32 input: solved on the FP64 twin
+    ref = po.fr(A.astype(np.float32).astype(np.float64), y.astype(np.float32).astype(np.float64), 0.0, 0.0, 4)
+    assert got.nzind.tolist() == ref.nzind and _close(got.nzval, ref.nzval, 1e-9)
 
 
 def test_fr_midsize_batch_vs_oracle(cs, po):
