@@ -102,10 +102,12 @@ def _load() -> ctypes.CDLL:
         "csb200_comm_unique_id": (c_int, [c_void_p]),
         "csb200_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
         "csb200_comm_destroy": (c_int, [c_void_p]),
+        "csb200_comm_exchange_mode": (c_int, [c_void_p]),
         "csb200_omp_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, i64p, f64p, i64p, f64p, i64p,
                                        f64p]),
         "csb200_debug_corr_topk": (c_int, [c_void_p, c_int, c_int64, i64p, f64p]),
         "csb200_debug_get_residual": (c_int, [c_void_p, c_void_p]),
+        "csb200_debug_graph_replays": (c_int, [c_void_p, POINTER(c_int64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here = the library does not export what csb200.h declares
@@ -123,8 +125,8 @@ EXPORTED_SYMBOLS = [
     "csb200_assemble_csc", "csb200_comm_unique_id", "csb200_batch_fr", "csb200_fr",
     "csb200_batch_sp", "csb200_batch_oblivious", "csb200_sp", "csb200_oblivious", "csb200_dict_colnorms",
     "csb200_dict_cumbabel",
-    "csb200_comm_create", "csb200_comm_destroy", "csb200_omp_sharded", "csb200_debug_corr_topk",
-    "csb200_debug_get_residual",
+    "csb200_comm_create", "csb200_comm_destroy", "csb200_comm_exchange_mode", "csb200_omp_sharded", "csb200_debug_corr_topk",
+    "csb200_debug_get_residual", "csb200_debug_graph_replays",
 ]
 
 
@@ -310,6 +312,12 @@ class Batch:
         out = np.empty((self.dict.M, self.nsig), dtype=self.dict.dtype, order="F")
         _check(lib.csb200_debug_get_residual(self._h, out.ctypes.data))
         return out
+
+    def graph_replays(self) -> int:
+        """Solves of this batch that ran as a CUDA-graph launch (few-signal paths; debug hook)."""
+        n = c_int64()
+        _check(lib.csb200_debug_graph_replays(self._h, byref(n)))
+        return n.value
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -681,4 +689,5 @@ def omp_sharded(shard: Dictionary, comm: ShardComm, b, k: int, eps: Optional[flo
     _check(lib.csb200_omp_sharded(shard._h, comm._h, b.ctypes.data, int(k), eps, _i64p(sel), _f64p(coef), _i64p(nnz),
                                   _f64p(res), _i64p(its), _f64p(ms)), eps)
     x = _to_sparse(shard.n_total, sel, coef, int(nnz[0]))
-    return x, {"resnorm": float(res[0]), "iters": int(its[0]), "corr_ms": float(ms[0]), "order": sel[:int(nnz[0])].copy()}
+    return x, {"resnorm": float(res[0]), "iters": int(its[0]), "corr_ms": float(ms[0]), "order": sel[:int(nnz[0])].copy(),
+               "exchange": "peer-memory" if lib.csb200_comm_exchange_mode(comm._h) == 1 else "nccl"}

@@ -143,6 +143,24 @@ struct csb200_batch {
     bool src_f32 = false;       // the batch lives on the FP64 twin of an FP32 dictionary: uploads arrive as FP32
     float* stage32 = nullptr;   // device staging for those uploads (ld x cap_sig floats)
     bool defer_finish = false;  // pipelined one-shot path: a solve only enqueues its work, the caller synchronises later
+    // Few-signal solves are launch-bound (tens of microseconds of kernels per update!): the second solve with the same
+    // shape on this batch is captured into a CUDA graph, later ones replay it (see run_graphed).
+    struct SolveKey {
+        int algo = 0;
+        int64_t k = 0, l = 0, nsig = 0;
+        double eps = 0.0;
+        const void* ptr[8] = {};
+        size_t pcap = 0, icap = 0;
+        bool operator==(const SolveKey& o) const {
+            return algo == o.algo && k == o.k && l == o.l && nsig == o.nsig && memcmp(&eps, &o.eps, sizeof eps) == 0 &&
+                   memcmp(ptr, o.ptr, sizeof ptr) == 0 && pcap == o.pcap && icap == o.icap;
+        }
+    };
+    SolveKey graph_key, graph_seen;
+    bool graph_seen_valid = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;     // update launches one replay stands for (other_launches accounting)
+    int64_t graph_replays = 0;
     std::mutex mu;
 };
 
@@ -157,6 +175,7 @@ void free_batch_mem(csb200_batch* b) {
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
     if (b->ev_solve1) cudaEventDestroy(b->ev_solve1);
+    if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
     if (b->stream) cudaStreamDestroy(b->stream);
 }
 
@@ -295,6 +314,80 @@ bool uses_cluster_update(const csb200_batch* b) {
 }
 cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
     return uses_cluster_update(b) ? launch_omp_update_cluster(a, f32, b->stream) : launch_omp_update(a, f32, b->stream);
+}
+
+// ---- CUDA-graph replay of few-signal solves ---------------------------------------------------------------------
+// A single-signal update! is ~10 us of GEMV plus ~10 us of cluster update; issued as individual launches (each with
+// its attribute / occupancy calls) the host cannot keep the stream fed and the solve runs at launch rate.  The loop has
+// no host decision in it (stopping rules live in device flags), so the whole solve -- reset + k x (correlation,
+// update) -- is captured once per (batch, algorithm, k, l, eps, signal count, buffers) and replayed.  Capture happens on
+// the SECOND solve with the same key (the first one has sized every buffer and a one-off solve pays nothing).
+// Off whenever a test hook selects kernels through the environment, while profiling, and with CSB200_GRAPH=0.
+constexpr int64_t GRAPH_MAX_UPDATES = 512;
+bool graph_eligible(const csb200_batch* b, int64_t updates) {
+    static const bool off = [] {
+        const char* e = getenv("CSB200_GRAPH");
+        return e && e[0] == '0';
+    }();
+    if (off || b->profile || b->defer_finish || b->corr_impl_env != IMPL_AUTO) return false;
+    if (b->nsig >= CLUSTER_UPDATE_MAX_SIGNALS || updates < 2 || updates > GRAPH_MAX_UPDATES) return false;
+    for (const char* hook : {"CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM"})
+        if (getenv(hook)) return false;
+    return true;
+}
+csb200_batch::SolveKey graph_key_of(const csb200_batch* b, int algo, int64_t k, int64_t l, double eps) {
+    csb200_batch::SolveKey key;
+    key.algo = algo; key.k = k; key.l = l; key.nsig = b->nsig; key.eps = eps;
+    key.ptr[0] = b->dB; key.ptr[1] = b->dR; key.ptr[2] = b->pval; key.ptr[3] = b->pidx; key.ptr[4] = b->state_blk;
+    key.ptr[5] = b->Rf; key.ptr[6] = b->dict->dA; key.ptr[7] = b->dict->gram;
+    key.pcap = b->pcap; key.icap = b->icap;
+    return key;
+}
+void graph_drop(csb200_batch* b) {
+    if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); b->graph_exec = nullptr; }
+    b->graph_seen_valid = false;
+}
+// body() enqueues the solve's kernels on b->stream and returns a status; `updates` = update launches it makes.
+template <class Body>
+int run_graphed(csb200_batch* b, int algo, int64_t k, int64_t l, double eps, int64_t updates, Body body) {
+    if (!graph_eligible(b, updates)) return body();
+    const csb200_batch::SolveKey key = graph_key_of(b, algo, k, l, eps);
+    if (b->graph_exec && b->graph_key == key) {
+        CU_TRY(cudaGraphLaunch(b->graph_exec, b->stream));
+        b->other_launches += b->graph_launches;
+        b->graph_replays++;
+        return CSB200_OK;
+    }
+    if (!(b->graph_seen_valid && b->graph_seen == key)) {          // first sighting: run directly, remember the key
+        const int rc = body();
+        b->graph_seen = graph_key_of(b, algo, k, l, eps);           // taken afterwards: the first run sizes the buffers
+        b->graph_seen_valid = rc == CSB200_OK;
+        return rc;
+    }
+    graph_drop(b);
+    if (cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return body(); }
+    const int64_t before = b->other_launches;
+    const int rc = body();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
+    const int64_t launches = b->other_launches - before;
+    b->other_launches = before;
+    if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    const bool same = graph_key_of(b, algo, k, l, eps) == key;      // a buffer grew during capture: do not keep the graph
+    if (e != cudaSuccess || !graph || !same) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return body();
+    }
+    e = cudaGraphInstantiate(&b->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); b->graph_exec = nullptr; return body(); }
+    b->graph_key = key;
+    b->graph_launches = launches;
+    CU_TRY(cudaGraphLaunch(b->graph_exec, b->stream));
+    b->other_launches += launches;
+    b->graph_replays++;
+    return CSB200_OK;
 }
 
 int begin_solve(csb200_batch* b) {
@@ -685,14 +778,19 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     decide_gram(b, k);
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
-    cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
-    for (int64_t it = 0; it < k; ++it) {
-        if ((rc = run_corr(b, 1, IMPL_AUTO))) return rc;
-        e = update_launch(b, state_args(b, 1, 1, eps, 0), f32);
-        if (e != cudaSuccess) return fail_cuda(e, "omp_update");
-        b->other_launches++;
-    }
+    rc = run_graphed(b, 0, k, 1, eps, k, [&]() -> int {
+        cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+        for (int64_t it = 0; it < k; ++it) {
+            int rc2 = run_corr(b, 1, IMPL_AUTO);
+            if (rc2) return rc2;
+            e = update_launch(b, state_args(b, 1, 1, eps, 0), f32);
+            if (e != cudaSuccess) return fail_cuda(e, "omp_update");
+            b->other_launches++;
+        }
+        return CSB200_OK;
+    });
+    if (rc) return rc;
     return finish(b, true);
 }
 
@@ -718,24 +816,30 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     decide_gram(b, k);
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
-    cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
     // the block-append CTA update kernel can select from the dense |A'r| matrix
     const bool dense_ok = !uses_cluster_update(b) && omp_update_uses_block((int)d->ld, (int)b->kcap, (int)l) &&
                           (k % l == 0 || omp_update_uses_block((int)d->ld, (int)b->kcap, (int)(k % l)));
-    for (int64_t it = 0; it < k / l; ++it) {
-        if ((rc = run_corr(b, (int)l, IMPL_AUTO, dense_ok))) return rc;
-        e = update_launch(b, state_args(b, (int)l, (int)l, eps, 0), f32);
-        if (e != cudaSuccess) return fail_cuda(e, "gomp_update");
-        b->other_launches++;
-    }
     const int rem = (int)(k % l);
-    if (rem > 0) {                                   // runs even after an eps-break (matchingpursuit.jl:134-137)
-        if ((rc = run_corr(b, rem, IMPL_AUTO, dense_ok))) return rc;
-        e = update_launch(b, state_args(b, rem, rem, eps, 1), f32);
-        if (e != cudaSuccess) return fail_cuda(e, "gomp_update(rem)");
-        b->other_launches++;
-    }
+    rc = run_graphed(b, 1, k, l, eps, k / l + (rem > 0), [&]() -> int {
+        cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+        for (int64_t it = 0; it < k / l; ++it) {
+            int rc2 = run_corr(b, (int)l, IMPL_AUTO, dense_ok);
+            if (rc2) return rc2;
+            e = update_launch(b, state_args(b, (int)l, (int)l, eps, 0), f32);
+            if (e != cudaSuccess) return fail_cuda(e, "gomp_update");
+            b->other_launches++;
+        }
+        if (rem > 0) {                               // runs even after an eps-break (matchingpursuit.jl:134-137)
+            int rc2 = run_corr(b, rem, IMPL_AUTO, dense_ok);
+            if (rc2) return rc2;
+            e = update_launch(b, state_args(b, rem, rem, eps, 1), f32);
+            if (e != cudaSuccess) return fail_cuda(e, "gomp_update(rem)");
+            b->other_launches++;
+        }
+        return CSB200_OK;
+    });
+    if (rc) return rc;
     return finish(b, true);
 }
 
@@ -901,18 +1005,24 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
     if ((rc = check_shape_fits(b, false))) return rc;
     if ((rc = settle_input(b))) return rc;
     if ((rc = begin_solve(b))) return rc;
-    cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), f32, b->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
-    if (warm) {
-        e = launch_mp_warmstart(state_args(b, 1, 1, 0.0, 0), f32, x0.idx, x0.val, x0.nnz, (int)x0_stride, b->stream);
-        if (e != cudaSuccess) return fail_cuda(e, "mp_warmstart");
-    }
-    for (int64_t it = 0; it < iters; ++it) {
-        if ((rc = run_corr(b, 1, IMPL_AUTO))) return rc;
-        e = launch_mp_update(state_args(b, 1, 1, 0.0, 0), f32, (int)it, (int)b->kcap, b->stream);
-        if (e != cudaSuccess) return fail_cuda(e, "mp_update");
-        b->other_launches++;
-    }
+    // a warm start reads temporary buffers: only the plain form is replayable
+    rc = run_graphed(b, 2, iters, 1, 0.0, warm ? 0 : iters, [&]() -> int {
+        cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), f32, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+        if (warm) {
+            e = launch_mp_warmstart(state_args(b, 1, 1, 0.0, 0), f32, x0.idx, x0.val, x0.nnz, (int)x0_stride, b->stream);
+            if (e != cudaSuccess) return fail_cuda(e, "mp_warmstart");
+        }
+        for (int64_t it = 0; it < iters; ++it) {
+            int rc2 = run_corr(b, 1, IMPL_AUTO);
+            if (rc2) return rc2;
+            e = launch_mp_update(state_args(b, 1, 1, 0.0, 0), f32, (int)it, (int)b->kcap, b->stream);
+            if (e != cudaSuccess) return fail_cuda(e, "mp_update");
+            b->other_launches++;
+        }
+        return CSB200_OK;
+    });
+    if (rc) return rc;
     return finish(b, true);      // synchronises before x0 is released
 }
 
@@ -980,6 +1090,13 @@ int csb200_batch_corr_time(csb200_batch* b, double* total_ms, int64_t* launches,
     if (total_ms) *total_ms = tot;
     if (launches) *launches = (int64_t)(b->ev_used / 2);
     if (other_launches) *other_launches = b->other_launches;
+    return CSB200_OK;
+}
+
+int csb200_debug_graph_replays(csb200_batch* b, int64_t* replays) {
+    if (!b || !replays) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    *replays = b->graph_replays;
     return CSB200_OK;
 }
 

@@ -13,12 +13,13 @@
 // The residual is staged once per CTA in shared memory.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace csb {
 namespace {
 
-constexpr int GT = 256;            // threads per CTA (8 warps x 8 atoms = PBLK)
-constexpr int GW = GT / 32;
-constexpr int CPW = PBLK / GW;     // atoms per warp (8)
+constexpr int GT = 256;            // threads per CTA, HBM regime (4+ CTAs per SM)
+constexpr int GT_L2 = 1024;        // threads per CTA, L2 regime (one CTA per SM: the residual is staged once per SM)
 
 template <typename T> struct Vec;
 template <> struct Vec<float> { using type = float4; static constexpr int W = 4; };
@@ -50,8 +51,19 @@ __device__ __forceinline__ void fma_vec(double& acc, const double2& a, const dou
 // One candidate record set per (CTA, signal): P = gridDim.x replaces the per-64-atom blocks of the DMMA path.
 constexpr int GEMV_MAX_RANGE = 2048;   // atoms per CTA the top-s (s > 1) scratch can hold
 
-template <typename T>
-__global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
+// Two instantiations per element type.
+//  * HBM regime <UNR 2, NT 256, CG 4>: dictionaries streamed from HBM; 8 x 16 B in flight per lane at 4+ CTAs per SM
+//    saturate the memory system (measured 1.0 of the HBM copy peak).
+//  * L2 regime <UNR 4, NT 1024, CG 2>: dictionaries that fit the L2.  The pass lasts ~10 us and a 1024 x 8192 dictionary
+//    has only ~14 four-column groups per SM, so the same kernel ran latency-bound (3.6 TB/s).  Two-column groups and
+//    32 warps per CTA put twice as many warps -- and twice the bytes in flight -- on every SM, one CTA per SM stages
+//    the residual once per SM, and the grid is a whole multiple of the SM count (a second CTA on some SMs only would be
+//    a 2x tail on so short a kernel).
+// Each column has its own accumulator and is reduced inside one warp in the same order in both, so c_j is bit-identical
+// whichever instantiation (and whichever shard / GPU count) computes it.
+template <typename T, int UNR, int NT, int CG>
+__global__ void __launch_bounds__(NT) corr_gemv_kernel(CorrArgs a) {
+    constexpr int GW = NT / 32;
     using V = typename Vec<T>::type;
     constexpr int W = Vec<T>::W;
     extern __shared__ unsigned char gsm[];
@@ -65,9 +77,9 @@ __global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
     const int ld = a.ld;
     const T* A = static_cast<const T*>(a.A);
     const T* r = static_cast<const T*>(a.R) + (size_t)sig * ld;
-    const long long Ng = (a.N + 3) / 4;
+    const long long Ng = (a.N + CG - 1) / CG;
     const int g_lo = (int)(Ng * p / P), g_hi = (int)(Ng * (p + 1) / P);
-    for (int row = tid; row < ld; row += GT) rs[row] = r[row];
+    for (int row = tid; row < ld; row += NT) rs[row] = r[row];
     if (tid == 0) next_group = g_lo;
     __syncthreads();
 
@@ -79,27 +91,28 @@ __global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
         if (lane == 0) grp = atomicAdd(&next_group, 1);
         grp = __shfl_sync(0xffffffffu, grp, 0);
         if (grp >= g_hi) break;
-        const int atom0 = grp * 4;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        const V* col[4];
+        const int atom0 = grp * CG;
+        double acc[CG];
+        const V* col[CG];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CG; ++c) {
             const int atom = (atom0 + c < a.N) ? atom0 + c : a.N - 1;      // clamp: stay in bounds, result discarded
             col[c] = reinterpret_cast<const V*>(A + (size_t)atom * ld);
+            acc[c] = 0.0;
         }
-#pragma unroll 2
+#pragma unroll UNR
         for (int i = lane; i < nvec; i += 32) {
-            V x[4];
+            V x[CG];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) x[c] = ldg_stream(col[c] + i);
+            for (int c = 0; c < CG; ++c) x[c] = ldg_stream(col[c] + i);
             double rr[W];
 #pragma unroll
             for (int e = 0; e < W; ++e) rr[e] = (double)rs[i * W + e];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) fma_vec(acc[c], x[c], rr);
+            for (int c = 0; c < CG; ++c) fma_vec(acc[c], x[c], rr);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CG; ++c) {
             double s = acc[c];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -107,7 +120,7 @@ __global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
             const int atom = atom0 + c;
             if (atom < a.N) {
                 if (a.S == 1) { if (v >= 0.0 && cand_better(v, atom, best_v, best_i)) { best_v = v; best_i = atom; } }   // NaN never wins
-                else if (lane == 0) cv[atom - g_lo * 4] = v;
+                else if (lane == 0) cv[atom - g_lo * CG] = v;
             }
         }
     }
@@ -129,14 +142,14 @@ __global__ void __launch_bounds__(GT) corr_gemv_kernel(CorrArgs a) {
     }
     // top-S of this CTA's range: S block-wide argmax rounds with exclusion (value desc, index asc)
     __syncthreads();
-    const int base = g_lo * 4;
-    const int range = min(g_hi * 4, a.N) - base;
+    const int base = g_lo * CG;
+    const int range = min(g_hi * CG, a.N) - base;
     double pv = 0.0;
     int pi = -1;
     for (int s = 0; s < a.S; ++s) {
         double bv = -1.0;
         int bi = INT_MAX;
-        for (int l = tid; l < range; l += GT) {
+        for (int l = tid; l < range; l += NT) {
             const double v = cv[l];
             const int idx = base + l;
             bool ok = v >= 0.0;                                        // excludes NaN
@@ -212,25 +225,50 @@ size_t gemv_smem_bytes(int ld, bool f32, int S, int range) {
     if (S > 1) bytes += (size_t)range * sizeof(double);
     return bytes;
 }
+
+// Dictionaries up to this size are treated as L2-resident (126 MB L2; the residual, candidates and the update
+// kernel's working set share it).
+constexpr size_t GEMV_L2_RESIDENT_BYTES = (size_t)96 << 20;
+bool gemv_l2_regime(int N, int ld, bool f32) {
+    const char* env = getenv("CSB200_GEMV_L2");            // test hook: 0 / 1 force the instantiation
+    if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
+    return (size_t)N * ld * (f32 ? 4 : 8) <= GEMV_L2_RESIDENT_BYTES;
+}
+
+template <typename T, int UNR, int NT, int CG>
+cudaError_t gemv_prepare(size_t smem, int* occ) {
+    cudaError_t e = cudaFuncSetAttribute(corr_gemv_kernel<T, UNR, NT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && occ) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, corr_gemv_kernel<T, UNR, NT, CG>, NT, smem);
+    return e;
+}
+cudaError_t gemv_prepare_any(bool f32, bool l2, size_t smem, int* occ) {
+    if (l2) return f32 ? gemv_prepare<float, 4, GT_L2, 2>(smem, occ) : gemv_prepare<double, 4, GT_L2, 2>(smem, occ);
+    return f32 ? gemv_prepare<float, 2, GT, 4>(smem, occ) : gemv_prepare<double, 2, GT, 4>(smem, occ);
+}
 }  // namespace
 
-// Number of CTAs (= candidate record sets per signal) of the GEMV pass: one wave of resident CTAs, but at least 8
-// column groups per CTA and at most GEMV_MAX_RANGE atoms per CTA.
+// Number of CTAs (= candidate record sets per signal) of the GEMV pass: one wave of resident CTAs, at most
+// GEMV_MAX_RANGE atoms per CTA.  HBM regime: at least 8 column groups per CTA.  L2 regime: a whole multiple of the SM
+// count, about one column group per warp.
 int corr_gemv_blocks(int N, int ld, bool f32, int S, int num_sms) {
-    const long long Ng = ((long long)N + 3) / 4;
+    const bool l2 = gemv_l2_regime(N, ld, f32);
+    const int cg = l2 ? 2 : 4;
+    const long long Ng = ((long long)N + cg - 1) / cg;
     int occ = 1;
     const size_t smem = gemv_smem_bytes(ld, f32, S, GEMV_MAX_RANGE);
-    cudaError_t e;
-    if (f32) {
-        cudaFuncSetAttribute(corr_gemv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, corr_gemv_kernel<float>, GT, smem);
-    } else {
-        cudaFuncSetAttribute(corr_gemv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, corr_gemv_kernel<double>, GT, smem);
-    }
+    cudaError_t e = gemv_prepare_any(f32, l2, smem, &occ);
     if (e != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
     long long P = (long long)num_sms * occ;
-    if (P > (Ng + 7) / 8) P = (Ng + 7) / 8;
+    if (l2) {
+        const long long slots = (long long)num_sms * (GT_L2 / 32);
+        long long per_sm = (Ng + slots - 1) / slots;
+        if (per_sm > occ) per_sm = occ;
+        if (per_sm < 1) per_sm = 1;
+        P = (long long)num_sms * per_sm;
+        if (P > Ng) P = Ng;
+    } else if (P > (Ng + 7) / 8) {
+        P = (Ng + 7) / 8;
+    }
     const long long pmin = ((long long)N + GEMV_MAX_RANGE - 8) / (GEMV_MAX_RANGE - 7);   // ranges are uneven by < 8 atoms
     if (P < pmin) P = pmin;
     if (P < 1) P = 1;
@@ -240,7 +278,9 @@ int corr_gemv_blocks(int N, int ld, bool f32, int S, int num_sms) {
 cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st) {
     if (a.nsig <= 0 || a.P <= 0) return cudaSuccess;
     const size_t smem = gemv_smem_bytes(a.ld, f32, a.S, GEMV_MAX_RANGE);
-    cudaError_t e;
+    const bool l2 = gemv_l2_regime(a.N, a.ld, f32);
+    cudaError_t e = gemv_prepare_any(f32, l2, smem, nullptr);
+    if (e != cudaSuccess) return e;
     for (int s0 = 0; s0 < a.nsig; s0 += 65535) {          // gridDim.y limit
         CorrArgs b = a;
         const int ns = a.nsig - s0 < 65535 ? a.nsig - s0 : 65535;
@@ -249,14 +289,12 @@ cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st) {
         b.pval = a.pval + (size_t)s0 * a.P * a.S;
         b.pidx = a.pidx + (size_t)s0 * a.P * a.S;
         dim3 grid(a.P, ns);
-        if (f32) {
-            e = cudaFuncSetAttribute(corr_gemv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            corr_gemv_kernel<float><<<grid, GT, smem, st>>>(b);
+        if (l2) {
+            if (f32) corr_gemv_kernel<float, 4, GT_L2, 2><<<grid, GT_L2, smem, st>>>(b);
+            else corr_gemv_kernel<double, 4, GT_L2, 2><<<grid, GT_L2, smem, st>>>(b);
         } else {
-            e = cudaFuncSetAttribute(corr_gemv_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            corr_gemv_kernel<double><<<grid, GT, smem, st>>>(b);
+            if (f32) corr_gemv_kernel<float, 2, GT, 4><<<grid, GT, smem, st>>>(b);
+            else corr_gemv_kernel<double, 2, GT, 4><<<grid, GT, smem, st>>>(b);
         }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -15,6 +15,16 @@
 //   4. global_pick: every rank picks the same winner (largest |c|, lowest global index on ties -- Julia
 //      `argmax`, src/matchingpursuit.jl:184) and stores its column in slot nnz of the active-atom cache
 //   5. the per-signal update kernel (update.cu) reading atoms from that cache.
+//
+// Steps 2-4 are ONE kernel when the ranks can map each other's memory (`peer_exchange_kernel`, the default):
+// every rank owns a mailbox in device memory, exported with cudaIpcGetMemHandle and mapped by all peers
+// (NVLink / NVSwitch peer access).  The kernel reduces the local candidates, stores its record straight
+// into slot [parity][rank] of EVERY rank's mailbox, publishes a sequence number with st.release.sys,
+// spins (ld.acquire.sys, bounded by a timeout) until all ranks' numbers have arrived in its own mailbox and
+// picks the winner -- no NCCL launch, no staging copy, one NVLink one-way latency per iteration.  Two
+// parity slots suffice: a rank cannot publish iteration s + 1 before every peer has published s, and a
+// peer publishes s only after it has consumed s - 1.  NCCL remains the bootstrap (the handles travel
+// through one all-gather) and the transport of last resort (CSB200_SHARD_EXCHANGE=nccl, or no peer access).
 // NCCL is dlopen'ed so that single-GPU users carry no dependency on it.
 #include "../../include/csb200.h"
 #include "common.cuh"
@@ -155,6 +165,129 @@ __global__ void __launch_bounds__(256) global_pick_kernel(const unsigned char* _
     for (int row = threadIdx.x; row < ld; row += 256) dst[row] = src[row];
 }
 
+
+// ---- peer-memory exchange (see the header comment) ---------------------------------------------------------------
+constexpr int MAX_PEERS = 16;
+constexpr size_t BOX_ERR_OFF = 128;        // int: a wait timed out
+constexpr size_t BOX_DATA_OFF = 256;       // flags: unsigned long long [MAX_PEERS] at offset 0
+constexpr int PX_THREADS = 1024;
+
+struct PeerArgs {
+    unsigned char* box[MAX_PEERS];         // every rank's mailbox as mapped in this process (box[rank] = own)
+    int rank, nranks;
+    unsigned long long seq;                // sequence number of this exchange (monotone over the communicator's life)
+    unsigned long long slot_bytes;         // capacity of one record slot
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PX_THREADS) peer_exchange_kernel(PeerArgs pa, const double* __restrict__ pval,
+                                                                   const int* __restrict__ pidx, int P,
+                                                                   const T* __restrict__ A, int ld, int idx_offset,
+                                                                   const int* __restrict__ nnz, int kcap,
+                                                                   T* __restrict__ Acache, double* __restrict__ cand_val,
+                                                                   int* __restrict__ cand_idx) {
+    __shared__ double sv[PX_THREADS / 32];
+    __shared__ int si[PX_THREADS / 32];
+    __shared__ double s_bv;
+    __shared__ int s_best, s_rank;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (a) local best of the GEMV's per-CTA candidates
+    double bv = -1.0;
+    int bi = INT_MAX;
+    for (int c = tid; c < P; c += PX_THREADS) {
+        const int i = pidx[c];
+        if (i >= 0 && cand_better(pval[c], i, bv, bi)) { bv = pval[c]; bi = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        bv = sv[0]; bi = si[0];
+        for (int w = 1; w < PX_THREADS / 32; ++w) if (cand_better(sv[w], si[w], bv, bi)) { bv = sv[w]; bi = si[w]; }
+        s_bv = bv;
+        s_best = (bi == INT_MAX) ? -1 : bi;
+    }
+    __syncthreads();
+    // (b) push {|c|, index, column} into slot [parity][rank] of every rank's mailbox (remote stores over NVLink)
+    const int best = s_best;
+    const size_t slot = BOX_DATA_OFF + ((size_t)(pa.seq & 1) * pa.nranks + pa.rank) * pa.slot_bytes;
+    const int nvec = (int)((size_t)ld * sizeof(T) / 16);            // ld is a multiple of 16 elements
+    const uint4* src = best >= 0 ? reinterpret_cast<const uint4*>(A + (size_t)(best - idx_offset) * ld) : nullptr;
+    for (int v = tid; v < nvec; v += PX_THREADS) {
+        const uint4 x = src ? __ldg(src + v) : make_uint4(0u, 0u, 0u, 0u);
+        for (int g = 0; g < pa.nranks; ++g)
+            *reinterpret_cast<uint4*>(pa.box[g] + slot + REC_HDR + (size_t)v * 16) = x;
+    }
+    if (tid < pa.nranks) {
+        const unsigned long long vb = (unsigned long long)__double_as_longlong(s_bv);
+        uint4 h;
+        h.x = (unsigned)vb; h.y = (unsigned)(vb >> 32); h.z = (unsigned)best; h.w = 0u;
+        *reinterpret_cast<uint4*>(pa.box[tid] + slot) = h;
+    }
+    __threadfence_system();
+    __syncthreads();
+    unsigned char* mine = pa.box[pa.rank];
+    if (tid < pa.nranks) {
+        // (c) publish: my record for exchange `seq` is complete in rank tid's mailbox
+        st_release_sys(reinterpret_cast<unsigned long long*>(pa.box[tid]) + pa.rank, pa.seq);
+        // (d) wait for rank tid's record in my own mailbox
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine) + tid;
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(f) < pa.seq) {
+            if (global_timer_ns() - t0 > pa.timeout_ns) { atomicExch(reinterpret_cast<int*>(mine + BOX_ERR_OFF), 1); break; }
+        }
+    }
+    __syncthreads();
+    // (e) every rank picks the same winner from identical records (value desc, global index asc)
+    const unsigned char* recs = mine + BOX_DATA_OFF + (size_t)(pa.seq & 1) * pa.nranks * pa.slot_bytes;
+    if (tid == 0) {
+        double wv = -1.0;
+        int wi = INT_MAX, wr = -1;
+        for (int g = 0; g < pa.nranks; ++g) {
+            const uint4 h = __ldcg(reinterpret_cast<const uint4*>(recs + (size_t)g * pa.slot_bytes));
+            const double v = __longlong_as_double((long long)(((unsigned long long)h.y << 32) | h.x));
+            const int i = (int)h.z;
+            if (i >= 0 && cand_better(v, i, wv, wi)) { wv = v; wi = i; wr = g; }
+        }
+        cand_val[0] = wv;
+        cand_idx[0] = (wr < 0) ? -1 : wi;
+        s_rank = wr;
+    }
+    __syncthreads();
+    const int t = nnz[0];
+    if (s_rank < 0 || t >= kcap) return;
+    const uint4* wsrc = reinterpret_cast<const uint4*>(recs + (size_t)s_rank * pa.slot_bytes + REC_HDR);
+    uint4* dst = reinterpret_cast<uint4*>(Acache + (size_t)t * ld);
+    for (int v = tid; v < nvec; v += PX_THREADS) dst[v] = __ldcg(wsrc + v);      // L1 may hold the slot's previous use
+}
+
+struct PeerBox {
+    unsigned char* local = nullptr;
+    unsigned char* peer[MAX_PEERS] = {};
+    size_t slot_bytes = 0, total_bytes = 0;
+    unsigned long long seq = 0;
+    bool tried = false, ready = false;
+};
+
 }  // namespace
 
 struct csb200_comm {
@@ -162,7 +295,95 @@ struct csb200_comm {
     int rank = 0, nranks = 1, device = 0;
     cudaStream_t stream = nullptr;
     std::mutex mu;
+    PeerBox px;
+    int last_mode = 0;          // exchange used by the last solve: 0 NCCL all-gather, 1 peer-memory mailboxes
 };
+
+namespace {
+
+void peerbox_release(csb200_comm* c) {
+    PeerBox& px = c->px;
+    for (int g = 0; g < c->nranks && g < MAX_PEERS; ++g)
+        if (px.peer[g] && g != c->rank) cudaIpcCloseMemHandle(px.peer[g]);
+    if (px.local) cudaFree(px.local);
+    for (auto& q : px.peer) q = nullptr;
+    px.local = nullptr;
+    px.ready = false;
+    cudaGetLastError();
+}
+
+// Collective (every rank of the communicator calls it from its first sharded solve): allocate the mailbox, swap IPC
+// handles through one NCCL all-gather, map the peers, agree through a second all-gather on whether EVERY rank
+// succeeded.  Any failure on any rank leaves all ranks on the NCCL exchange -- never a mixed state.
+int peerbox_setup(csb200_comm* c, size_t rec_bytes) {
+    PeerBox& px = c->px;
+    px.tried = true;
+    if (c->nranks > MAX_PEERS) return CSB200_OK;
+    struct Hello { cudaIpcMemHandle_t h; unsigned long long slot; int ok; int pad; };
+    static_assert(sizeof(Hello) % 8 == 0, "Hello layout");
+    const int G = c->nranks;
+    cudaStream_t st = c->stream;
+    size_t slot = rec_bytes > ((size_t)1 << 20) ? rec_bytes : ((size_t)1 << 20);
+    slot = (slot + 255) / 256 * 256;
+    Hello me;
+    memset(&me, 0, sizeof me);
+    me.slot = slot;
+    px.total_bytes = BOX_DATA_OFF + 2 * (size_t)G * slot;
+    bool ok = cudaMalloc(&px.local, px.total_bytes) == cudaSuccess;
+    if (!ok) px.local = nullptr;
+    ok = ok && cudaMemset(px.local, 0, px.total_bytes) == cudaSuccess;
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+    ok = ok && (G == 1 || cudaIpcGetMemHandle(&me.h, px.local) == cudaSuccess);
+    cudaGetLastError();
+    me.ok = ok ? 1 : 0;
+
+    Hello* dbuf = nullptr;                       // [1 + G]: send, recv
+    CU_TRY(cudaMalloc(&dbuf, sizeof(Hello) * (size_t)(1 + G)));
+    std::vector<Hello> all(G);
+    auto gather = [&]() -> int {
+        cudaError_t e = cudaMemcpyAsync(dbuf, &me, sizeof me, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return fail_cuda(e, "peer exchange setup: upload");
+        ncclResult_t nr = nccl().AllGather(dbuf, dbuf + 1, sizeof(Hello), ncclChar, c->comm, st);
+        if (nr != ncclSuccess) return fail_nccl(nr, "peer exchange setup: ncclAllGather");
+        e = cudaMemcpyAsync(all.data(), dbuf + 1, sizeof(Hello) * (size_t)G, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail_cuda(e, "peer exchange setup: download");
+        return CSB200_OK;
+    };
+    int rc = gather();
+    if (rc) { cudaFree(dbuf); peerbox_release(c); return rc; }
+    bool all_ok = true;
+    for (int g = 0; g < G; ++g) all_ok = all_ok && all[g].ok == 1 && all[g].slot == slot;
+    if (all_ok) {
+        for (int g = 0; g < G; ++g) {
+            if (g == c->rank) { px.peer[g] = px.local; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[g].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                all_ok = false;
+                break;
+            }
+            px.peer[g] = static_cast<unsigned char*>(ptr);
+        }
+    }
+    me.ok = all_ok ? 1 : 0;
+    rc = gather();                               // also orders every rank's memset before any peer's first store
+    cudaFree(dbuf);
+    if (rc) { peerbox_release(c); return rc; }
+    for (int g = 0; g < G; ++g) all_ok = all_ok && all[g].ok == 1;
+    if (!all_ok) { peerbox_release(c); return CSB200_OK; }
+    px.slot_bytes = slot;
+    px.seq = 0;
+    px.ready = true;
+    return CSB200_OK;
+}
+
+bool want_peer_exchange() {
+    const char* e = getenv("CSB200_SHARD_EXCHANGE");        // "nccl" forces the all-gather; must agree on all ranks
+    return !(e && (strcmp(e, "nccl") == 0 || strcmp(e, "NCCL") == 0));
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -198,10 +419,13 @@ int csb200_comm_destroy(csb200_comm* c) {
     if (!c) return CSB200_OK;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    peerbox_release(c);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     delete c;
     return CSB200_OK;
 }
+
+int csb200_comm_exchange_mode(const csb200_comm* c) { return c ? c->last_mode : CSB200_ERR_INVALID_ARG; }
 
 int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_t k, double eps, int64_t* sel_idx,
                        double* coef, int64_t* nnz_out, double* resnorm, int64_t* iters_out, double* corr_ms) {
@@ -223,6 +447,19 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
     const int P = corr_gemv_blocks((int)N, (int)ld, dtype == CSB200_F32, 1, num_sms);
     const size_t rec_bytes = (REC_HDR + (size_t)ld * es + 15) / 16 * 16;
     cudaStream_t st = c->stream;
+    bool peer = want_peer_exchange();
+    if (peer && !c->px.tried) { rc = peerbox_setup(c, rec_bytes); if (rc) return rc; }
+    peer = peer && c->px.ready && rec_bytes <= c->px.slot_bytes;
+    c->last_mode = peer ? 1 : 0;
+    PeerArgs pa;
+    memset(&pa, 0, sizeof pa);
+    if (peer) {
+        for (int g = 0; g < c->nranks; ++g) pa.box[g] = c->px.peer[g];
+        pa.rank = c->rank; pa.nranks = c->nranks; pa.slot_bytes = c->px.slot_bytes;
+        const char* te = getenv("CSB200_PEER_TIMEOUT_S");
+        const double ts = te ? atof(te) : 60.0;
+        pa.timeout_ns = (unsigned long long)((ts > 0 ? ts : 60.0) * 1e9);
+    }
 
     // device scratch (one allocation)
     struct Off { size_t b, r, acache, pval, pidx, cval, cidx, nnz, sel, T, z, x, res, it, done, flags, send, recv, end; } o;
@@ -275,12 +512,20 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
             e = launch_corr_gemv(ca, f32, st);
             cudaEventRecord(ev[2 * it + 1], st);
             if (e != cudaSuccess) { status = fail_cuda(e, "corr_gemv"); break; }
-            if (f32) local_best_kernel<float><<<1, 256, 0, st>>>(ca.pval, ca.pidx, P, (const float*)dA, (int)ld, (int)n_offset, base + o.send);
-            else local_best_kernel<double><<<1, 256, 0, st>>>(ca.pval, ca.pidx, P, (const double*)dA, (int)ld, (int)n_offset, base + o.send);
-            ncclResult_t nr = nccl().AllGather(base + o.send, base + o.recv, rec_bytes, ncclChar, c->comm, st);
-            if (nr != ncclSuccess) { status = fail_nccl(nr, "ncclAllGather"); break; }
-            if (f32) global_pick_kernel<float><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (float*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
-            else global_pick_kernel<double><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (double*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+            if (peer) {
+                pa.seq = ++c->px.seq;
+                if (f32) peer_exchange_kernel<float><<<1, PX_THREADS, 0, st>>>(pa, ca.pval, ca.pidx, P, (const float*)dA, (int)ld, (int)n_offset, sa.nnz, (int)kcap, (float*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+                else peer_exchange_kernel<double><<<1, PX_THREADS, 0, st>>>(pa, ca.pval, ca.pidx, P, (const double*)dA, (int)ld, (int)n_offset, sa.nnz, (int)kcap, (double*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+                e = cudaGetLastError();
+                if (e != cudaSuccess) { status = fail_cuda(e, "peer_exchange"); break; }
+            } else {
+                if (f32) local_best_kernel<float><<<1, 256, 0, st>>>(ca.pval, ca.pidx, P, (const float*)dA, (int)ld, (int)n_offset, base + o.send);
+                else local_best_kernel<double><<<1, 256, 0, st>>>(ca.pval, ca.pidx, P, (const double*)dA, (int)ld, (int)n_offset, base + o.send);
+                ncclResult_t nr = nccl().AllGather(base + o.send, base + o.recv, rec_bytes, ncclChar, c->comm, st);
+                if (nr != ncclSuccess) { status = fail_nccl(nr, "ncclAllGather"); break; }
+                if (f32) global_pick_kernel<float><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (float*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+                else global_pick_kernel<double><<<1, 256, 0, st>>>(base + o.recv, c->nranks, rec_bytes, (int)ld, sa.nnz, (int)kcap, (double*)(base + o.acache), (double*)(base + o.cval), (int*)(base + o.cidx));
+            }
             if (timing) cudaEventRecord(ev[2 * k + 2 * it], st);
             e = launch_omp_update_cluster(sa, f32, st, base + o.acache);
             if (timing) cudaEventRecord(ev[2 * k + 2 * it + 1], st);
@@ -296,8 +541,16 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
         if (e == cudaSuccess) e = cudaMemcpyAsync(&hn, base + o.nnz, 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&hit, base + o.it, 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&hres, base + o.res, 8, cudaMemcpyDeviceToHost, st);
+        int perr = 0;
+        if (peer && e == cudaSuccess) e = cudaMemcpyAsync(&perr, c->px.local + BOX_ERR_OFF, 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { status = fail_cuda(e, "download"); break; }
+        if (perr) {
+            cudaMemsetAsync(c->px.local + BOX_ERR_OFF, 0, 4, st);
+            csb200_internal_set_error("peer-memory exchange timed out waiting for a rank (CSB200_PEER_TIMEOUT_S)");
+            status = CSB200_ERR_NCCL;
+            break;
+        }
         for (int64_t j = 0; j < k; ++j) {
             if (sel_idx) sel_idx[j] = j < hn ? hsel[j] : -1;
             if (coef) coef[j] = j < hn ? hx[j] : 0.0;
@@ -319,8 +572,8 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
                 cudaEventElapsedTime(&ms, ev[2 * k + 2 * it], ev[2 * k + 2 * it + 1]); upd += ms;
                 if (it + 1 < k) { cudaEventElapsedTime(&ms, ev[2 * k + 2 * it + 1], ev[2 * (it + 1)]); gap += ms; }
             }
-            fprintf(stderr, "[csb200 shard rank %d/%d] per iteration (us): gemv %.1f  local-best+allgather+pick %.1f  update %.1f  gap %.1f\n",
-                    c->rank, c->nranks, 1e3 * gemv / k, 1e3 * exch / k, 1e3 * upd / k, 1e3 * gap / k);
+            fprintf(stderr, "[csb200 shard rank %d/%d] per iteration (us): gemv %.1f  exchange[%s] %.1f  update %.1f  gap %.1f\n",
+                    c->rank, c->nranks, 1e3 * gemv / k, peer ? "peer-memory" : "local-best+allgather+pick", 1e3 * exch / k, 1e3 * upd / k, 1e3 * gap / k);
         }
     } while (0);
     cudaStreamSynchronize(st);

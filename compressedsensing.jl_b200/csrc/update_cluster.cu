@@ -7,7 +7,8 @@
 // (BASELINE configs 1 and 4: M up to 8192, up to 128 active atoms) left ONE CTA to gather 2 t M elements per
 // iteration and the update took as long as the HBM-bound correlation pass it sits behind.
 //
-// Here the M rows are split over the CL = 8 CTAs of a cluster.  Each CTA keeps its slice of v / r / b, gathers
+// Here the M rows are split over the CL CTAs of a cluster (8, the portable maximum, or 16 = the opt-in non-portable
+// size for single-signal solves on long atoms, where the gather sweeps are bound by how many SMs pull from L2).  Each CTA keeps its slice of v / r / b, gathers
 // its slice of the active atoms, and the length-M reductions (A_S'v, ||v||^2, v'b, ||r||^2) are finished
 // across the cluster through distributed shared memory: every CTA stores its partials into every peer's
 // exchange buffer (`map_shared_rank`), `cluster.sync()`, then sums the 8 partials in rank order -- a
@@ -15,6 +16,11 @@
 // is replicated per CTA and updated identically, so no broadcast is needed.  Three exchanges per appended
 // atom (five when a second orthogonalisation sweep is required).
 #include <cooperative_groups.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "update_common.cuh"
@@ -25,7 +31,6 @@ namespace csb {
 namespace {
 
 constexpr int CT = 256;            // threads per CTA
-constexpr int CL = 8;              // CTAs per cluster (portable maximum)
 constexpr int T_SMEM_MAX_K_CL = 128;   // 128 x 129 doubles = 132 KB: fits beside the 1-CTA-per-SM working set
 
 struct Exchange {
@@ -36,6 +41,7 @@ struct Exchange {
 
 // Deterministic cluster-wide sum of n doubles held in `vals` (shared memory of each CTA); result in `out`
 // (shared memory), identical on every CTA.
+template <int CL>
 __device__ __forceinline__ void cluster_allreduce(cg::cluster_group& cl, Exchange& x, const double* vals, int n,
                                                   double* out) {
     const int tid = threadIdx.x;
@@ -57,7 +63,7 @@ __device__ __forceinline__ void cluster_allreduce(cg::cluster_group& cl, Exchang
     __syncthreads();
 }
 
-template <typename T>
+template <typename T, int CL>
 __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, const T* __restrict__ Acache,
                                                                    int t_in_smem) {
     cg::cluster_group cl = cg::this_cluster();
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                     }
                 }
                 if (tid == 0) g[t] = s2;                                   // rides along: ||a||^2 partial (sweep 0)
-                cluster_allreduce(cl, ex, g, t + 1, gs);
+                cluster_allreduce<CL>(cl, ex, g, t + 1, gs);
                 if (!have_norm) { anorm2 = gs[t]; before2 = anorm2; rho2 = anorm2; have_norm = true; }
                 if (t == 0) break;
                 for (int i = tid; i < t; i += CT) {                        // hh = R^{-T} g
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                 }
                 p2 = block_sum<CT>(p2, red);
                 if (tid == 0) g[0] = p2;
-                cluster_allreduce(cl, ex, g, 1, gs);
+                cluster_allreduce<CL>(cl, ex, g, 1, gs);
                 rho2 = gs[0];
                 if (rho2 >= 0.5 * before2) break;                          // DGKS: one sweep was enough
                 before2 = rho2;
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
             for (int row = tid; row < Mc; row += CT) sb += v[row] * (double)b[row];
             sb = block_sum<CT>(sb, red);
             if (tid == 0) g[0] = sb;
-            cluster_allreduce(cl, ex, g, 1, gs);
+            cluster_allreduce<CL>(cl, ex, g, 1, gs);
             const double zt = gs[0] / rho;                                 // z_t = q_t' b
             const double gam = zt / rho;
             double s2r = 0.0;
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
             }
             s2r = block_sum<CT>(s2r, red);
             if (tid == 0) g[0] = s2r;
-            cluster_allreduce(cl, ex, g, 1, gs);
+            cluster_allreduce<CL>(cl, ex, g, 1, gs);
             nr2 = gs[0];
             const double irho = 1.0 / rho;
             for (int i = tid; i < t; i += CT) {                            // new column of R^{-1}
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
     }
 }
 
-size_t cluster_smem_bytes(int ld, int kcap, bool t_in_smem) {
+size_t cluster_smem_bytes(int ld, int kcap, bool t_in_smem, int CL) {
     const int xstride = kcap + 4;
     size_t bytes = (size_t)(ld / CL + 2 * xstride + 4 * kcap + 2 * CL * xstride) * sizeof(double) +
                    (size_t)((kcap + 1) & ~1) * sizeof(int) + (size_t)kcap * sizeof(void*);
@@ -283,12 +289,17 @@ size_t cluster_smem_bytes(int ld, int kcap, bool t_in_smem) {
     return bytes;
 }
 
-template <typename T>
-cudaError_t launch_t(const StateArgs& a, cudaStream_t st, const void* Acache) {
+template <typename T, int CL>
+cudaError_t launch_cl(const StateArgs& a, cudaStream_t st, const void* Acache, bool probe_only) {
     const int t_in_smem = a.kcap <= T_SMEM_MAX_K_CL ? 1 : 0;
-    const size_t smem = cluster_smem_bytes(a.ld, a.kcap, t_in_smem != 0);
-    cudaError_t e = cudaFuncSetAttribute(omp_update_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = cluster_smem_bytes(a.ld, a.kcap, t_in_smem != 0, CL);
+    if (smem > MAX_DYN_SMEM) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(omp_update_cluster_kernel<T, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (CL > 8) {
+        e = cudaFuncSetAttribute(omp_update_cluster_kernel<T, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(a.nsig * CL));
     cfg.blockDim = dim3(CT);
@@ -298,12 +309,50 @@ cudaError_t launch_t(const StateArgs& a, cudaStream_t st, const void* Acache) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, omp_update_cluster_kernel<T>, a, static_cast<const T*>(Acache), t_in_smem);
+    if (probe_only) {                                  // can the device co-schedule one such cluster at all?
+        int n = 0;
+        e = cudaOccupancyMaxActiveClusters(&n, omp_update_cluster_kernel<T, CL>, &cfg);
+        if (e != cudaSuccess) return e;
+        return n >= 1 ? cudaSuccess : cudaErrorInvalidConfiguration;
+    }
+    return cudaLaunchKernelEx(&cfg, omp_update_cluster_kernel<T, CL>, a, static_cast<const T*>(Acache), t_in_smem);
+}
+
+// 16-CTA clusters: few signals (the grid stays within one wave), long atoms (each CTA still streams >= 256 rows per
+// atom with 16-byte loads), and a device that can place such a cluster (cudaOccupancyMaxActiveClusters).
+// CSB200_CLUSTER=8|16 overrides the size rule.
+template <typename T>
+bool wide_cluster(const StateArgs& a) {
+    // placement depends on the per-CTA shared memory only: remember the largest size that fitted, the smallest that did not
+    static std::atomic<size_t> ok_upto{0}, bad_from{SIZE_MAX};
+    const char* env = getenv("CSB200_CLUSTER");
+    if (env && !strcmp(env, "8")) return false;
+    const bool forced = env && !strcmp(env, "16");
+    constexpr int W = RowVec<T>::W;
+    if (a.ld % (16 * W) != 0) return false;
+    if (!forced && !(a.nsig <= 4 && a.ld >= 4096)) return false;
+    const size_t smem = cluster_smem_bytes(a.ld, a.kcap, a.kcap <= T_SMEM_MAX_K_CL, 16);
+    if (smem <= ok_upto.load()) return true;
+    if (smem >= bad_from.load()) return false;
+    const cudaError_t e = launch_cl<T, 16>(a, nullptr, nullptr, true);
+    if (e != cudaSuccess) { cudaGetLastError(); if (smem < bad_from.load()) bad_from.store(smem); return false; }
+    if (smem > ok_upto.load()) ok_upto.store(smem);
+    return true;
+}
+
+template <typename T>
+cudaError_t launch_t(const StateArgs& a, cudaStream_t st, const void* Acache) {
+    if (wide_cluster<T>(a)) {
+        const cudaError_t e = launch_cl<T, 16>(a, st, Acache, false);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();                            // placement refused at launch time: the portable size always fits
+    }
+    return launch_cl<T, 8>(a, st, Acache, false);
 }
 
 }  // namespace
 
-size_t omp_update_cluster_smem_bytes(int ld, int kcap) { return cluster_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K_CL); }
+size_t omp_update_cluster_smem_bytes(int ld, int kcap) { return cluster_smem_bytes(ld, kcap, kcap <= T_SMEM_MAX_K_CL, 8); }
 
 cudaError_t launch_omp_update_cluster(const StateArgs& a, bool f32, cudaStream_t st, const void* Acache) {
     if (a.nsig <= 0) return cudaSuccess;

@@ -180,12 +180,19 @@ int csb200_assemble_csc(int64_t nsig, int64_t stride, const int64_t* sel_idx, co
  * program (torch.distributed / MPI / files).  csb200_omp_sharded runs `omp` for ONE signal
  * with the per-iteration exchange done on the device stream (no host round trip):
  * all ranks return the same result.
+ * Exchange transport: by default the ranks map each other's mailboxes (CUDA IPC over NVLink peer access, set up
+ * collectively inside the first csb200_omp_sharded call) and one kernel per iteration stores the candidate record
+ * into every peer, publishes a sequence number and picks the winner; if any rank cannot map its peers, or
+ * CSB200_SHARD_EXCHANGE=nccl is set (on ALL ranks), the records travel through ncclAllGather instead.  Both
+ * transports give bit-identical results.  csb200_comm_exchange_mode: transport of the last solve (1 peer memory,
+ * 0 NCCL).  A rank that waits longer than CSB200_PEER_TIMEOUT_S (default 60) for a peer fails with CSB200_ERR_NCCL.
  */
 #define CSB200_NCCL_ID_BYTES 128
 typedef struct csb200_comm csb200_comm;
 int csb200_comm_unique_id(void* id_bytes);
 int csb200_comm_create(const void* id_bytes, int rank, int nranks, int device, csb200_comm** out);
 int csb200_comm_destroy(csb200_comm* comm);
+int csb200_comm_exchange_mode(const csb200_comm* comm);
 int csb200_omp_sharded(csb200_dict* shard, csb200_comm* comm, const void* b, int64_t k, double eps,
                        int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters,
                        double* corr_ms);
@@ -197,6 +204,10 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* comm, const void* b, int
 int csb200_debug_corr_topk(csb200_batch* batch, int impl, int64_t s, int64_t* idx, double* val);
 /* Copy the current residual matrix (M x nsig, dict dtype, ld = M) to the host. */
 int csb200_debug_get_residual(csb200_batch* batch, void* out);
+/* Few-signal solves (< 24 signals) are captured into a CUDA graph on their second run with the same algorithm, k,
+ * l, eps and signal count on a batch and replayed afterwards (CSB200_GRAPH=0 disables it).  Number of solves of this
+ * batch that ran as a graph launch. */
+int csb200_debug_graph_replays(csb200_batch* batch, int64_t* replays);
 
 #ifdef __cplusplus
 }

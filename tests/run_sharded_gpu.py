@@ -33,7 +33,16 @@ def main():
         b = po.perturb(rng, b, 5e-3)
         lo, hi = cs.shard_range(N, world, rank)
         with cs.Dictionary(np.asfortranarray(A[:, lo:hi]), device=local, n_offset=lo, n_total=N) as shard:
-            x, info = cs.omp_sharded(shard, comm, b, k)
+            x, info = cs.omp_sharded(shard, comm, b, k)                 # default transport: peer-memory mailboxes
+            os.environ["CSB200_SHARD_EXCHANGE"] = "nccl"
+            xn, infon = cs.omp_sharded(shard, comm, b, k)               # same solve through ncclAllGather
+            del os.environ["CSB200_SHARD_EXCHANGE"]
+            x2, info2 = cs.omp_sharded(shard, comm, b, k)               # and back (sequence numbers keep counting)
+        want = os.environ.get("CSB200_EXPECT_EXCHANGE", "peer-memory")
+        ok &= info["exchange"] == want and infon["exchange"] == "nccl" and info2["exchange"] == want
+        for y, iy in ((xn, infon), (x2, info2)):                       # transports are bit-identical
+            ok &= y.nzind.tolist() == x.nzind.tolist() and bool(np.array_equal(y.nzval, x.nzval))
+            ok &= iy["order"].tolist() == info["order"].tolist() and iy["resnorm"] == info["resnorm"]
         # every rank must hold the same answer
         mine = torch.tensor(np.concatenate([x.nzind.astype(np.float64), x.nzval, [info["resnorm"]]]), device="cuda")
         ref0 = mine.clone()
@@ -49,7 +58,7 @@ def main():
             ok &= bool(np.allclose(x.nzval, ref.nzval, rtol=2e-5 if dtype == np.float32 else 1e-10, atol=1e-6 if dtype == np.float32 else 1e-11))
             ok &= bool(np.allclose(x.nzval, x1.nzval, rtol=1e-12, atol=1e-13))     # sharded == unsharded GPU
             ok &= 7 in x.nzind.tolist() and (N - 3) not in x.nzind.tolist()
-            print(f"dtype={np.dtype(dtype).name} world={world} ok={ok} corr_ms={info['corr_ms']:.3f}", flush=True)
+            print(f"dtype={np.dtype(dtype).name} world={world} ok={ok} exchange={info['exchange']} corr_ms={info['corr_ms']:.3f}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     comm.close()

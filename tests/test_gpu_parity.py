@@ -115,6 +115,36 @@ def test_dense_topk_radix_select(cs, po, M, N, B, s, monkeypatch):
     assert np.array_equal(idx, idx_v)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("M,N,B,s", [(1024, 8192, 1, 1), (1024, 3000, 3, 1), (200, 5003, 2, 4), (4096, 333, 1, 2),
+                                     (48, 70001, 1, 1)])
+def test_corr_gemv_regimes_are_bit_identical(cs, po, dtype, M, N, B, s, monkeypatch):
+    """The GEMV kernel has an HBM instantiation (256 threads, 4-column groups) and an L2 one (1024 threads, 2-column
+    groups, grid = multiple of the SM count).  Every dot product keeps its summation order, so |c| and the selection
+    must be BIT-identical between them, and equal to the naive kernel's selection."""
+    rng = np.random.default_rng(M + N)
+    A = po.gaussian_dictionary(rng, M, N, dtype)
+    A[:, N - 1] = A[:, 2]                                     # an exact tie across the whole atom range
+    R = np.asfortranarray(rng.standard_normal((M, B)).astype(dtype))
+    R[:, 0] = A[:, 2] * 3
+    got = {}
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 4) as batch:
+        batch.upload(R)
+        for regime in ("0", "1"):
+            monkeypatch.setenv("CSB200_GEMV_L2", regime)
+            got[regime] = batch.debug_corr_topk(s, 2)
+        monkeypatch.delenv("CSB200_GEMV_L2")
+        idx_n, val_n = batch.debug_corr_topk(s, 3)
+    assert np.array_equal(got["0"][0], got["1"][0]) and np.array_equal(got["0"][1], got["1"][1])
+    assert got["0"][0][0, 0] == 2 and (s < 2 or got["0"][0][0, 1] == N - 1)
+    C = np.abs(A.astype(np.float64).T @ R.astype(np.float64))
+    for b in range(B):
+        order = np.lexsort((np.arange(N), -C[:, b]))[:s]
+        assert np.allclose(got["1"][1][b], C[order, b], rtol=1e-12, atol=1e-13)
+        if b > 0:
+            assert got["1"][0][b].tolist() == order.tolist() == idx_n[b].tolist()
+
+
 @pytest.mark.parametrize("M,N,s", [(64, 160, 2), (8192, 640, 1), (100, 77, 5)])
 def test_corr_gemv_f32(cs, po, M, N, s):
     rng = np.random.default_rng(N)
@@ -139,10 +169,13 @@ def _fixtures():
 
 @pytest.mark.parametrize("path", _fixtures(), ids=lambda p: os.path.basename(p)[:-4])
 @pytest.mark.parametrize("impl,update", [("gemm", "cta"), ("gemv", "cta"), ("gemm", "cluster"), ("gemv", "cluster"),
-                                         ("small", "cta")])
+                                         ("gemv", "cluster16"), ("small", "cta")])
 def test_golden(cs, path, impl, update, monkeypatch):
     # correlation kernel: DMMA GEMM / GEMV (multi-launch path) or the whole-solve small-dictionary kernel;
-    # update kernel of the multi-launch path: one CTA per signal / one 8-CTA cluster per signal
+    # update kernel of the multi-launch path: one CTA per signal / one 8-CTA (or 16-CTA) cluster per signal
+    monkeypatch.setenv("CSB200_CLUSTER", "16" if update == "cluster16" else "8")
+    if update == "cluster16":
+        update = "cluster"
     monkeypatch.setenv("CSB200_UPDATE_IMPL", update)
     if impl == "small":
         impl = None
@@ -759,11 +792,78 @@ def test_widened_rows_full_c2_shape_properties(cs, po):
         assert np.array_equal(X.indices.reshape(B, k), idx) and np.allclose(X.data.reshape(B, k), sign, rtol=1e-9)
 
 
+# ------------------------------------------------------------------ CUDA-graph replay of few-signal solves
+@pytest.mark.parametrize("algo", ["omp", "gomp", "mp"])
+@pytest.mark.parametrize("dtype,nsig", [(np.float64, 1), (np.float32, 3), (np.float64, 23)])
+def test_few_signal_solves_replay_a_cuda_graph(cs, po, algo, dtype, nsig, monkeypatch):
+    """A solve with < 24 signals is captured into a CUDA graph the second time it runs with the same (algorithm, k, l,
+    eps, signal count) on a batch and replayed afterwards.  Every run -- direct, captured, replayed, and direct again
+    after the key changes -- must reproduce the oracle on fresh signals."""
+    for hook in ("CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM", "CSB200_GRAPH", "CSB200_CORR_IMPL"):
+        monkeypatch.delenv(hook, raising=False)
+    rng = np.random.default_rng(77 + nsig)
+    M, N, k, l = 96, 4500, 6, 2                       # N > 4096: not the whole-solve small-dictionary kernel
+    A = po.gaussian_dictionary(rng, M, N, dtype)
+    rtol = RTOL32 if dtype == np.float32 else RTOL64
+    eps = float(np.finfo(dtype).eps)
+
+    def run_and_check(batch, kk):
+        X0, Bm = _planted(po, rng, A.astype(np.float64), kk, nsig, noise=1e-3)
+        Bm = np.asfortranarray(Bm.astype(dtype))
+        batch.upload(Bm)
+        if algo == "omp":
+            batch.omp(kk, eps)
+        elif algo == "gomp":
+            batch.gomp(l, kk, eps)
+        else:
+            batch.mp(kk)
+        sel, coef, nnz, res, its = batch.download(kk)
+        for s in range(min(nsig, 4)):
+            t = po.Trace()
+            if algo == "omp":
+                ref = po.omp(A, Bm[:, s], kk, trace=t)
+            elif algo == "gomp":
+                ref = po.gomp(A, Bm[:, s], l, kk, trace=t)
+            else:
+                ref = po.mp(A, Bm[:, s], kk, trace=t)
+            if algo == "mp":
+                acc = {}
+                for i, c in zip(sel[s, :kk].tolist(), coef[s, :kk].tolist()):
+                    acc[i] = acc.get(i, 0.0) + c
+                assert sorted(acc) == ref.nzind
+                assert _close(np.array([acc[i] for i in sorted(acc)]), ref.nzval, max(rtol, 1e-9))
+            else:
+                n = int(nnz[s])
+                assert sel[s, :n].tolist() == t.order(), (s, "selection sequence")
+                idx, val = _sorted(sel[s], coef[s], n)
+                assert idx.tolist() == ref.nzind and _close(val, ref.nzval, rtol)
+
+    with cs.Dictionary(A) as D, cs.Batch(D, nsig, k) as batch:
+        for rep in range(4):
+            run_and_check(batch, k)
+        assert batch.graph_replays() == 3             # rep 0 direct, rep 1 captured + launched, reps 2-3 replayed
+        run_and_check(batch, k - 2)                   # another key: direct again
+        assert batch.graph_replays() == 3
+        run_and_check(batch, k - 2)                   # ... captured
+        run_and_check(batch, k)                       # the first key is seen anew (one graph is kept per batch)
+        assert batch.graph_replays() == 4
+    monkeypatch.setenv("CSB200_UPDATE_IMPL", "cluster")   # a test hook in the environment switches replay off
+    with cs.Dictionary(A) as D, cs.Batch(D, nsig, k) as batch:
+        for rep in range(3):
+            run_and_check(batch, k)
+        assert batch.graph_replays() == 0
+
+
 # ------------------------------------------------------------------ column-sharded mode
+@pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_sharded_single_rank_matches_oracle(cs, po, dtype):
-    """The whole sharded code path (GEMV -> local best -> NCCL all-gather -> global pick -> cached-atom update)
-    with a communicator of one rank: must equal the oracle and the unsharded GPU path."""
+def test_sharded_single_rank_matches_oracle(cs, po, dtype, exchange, monkeypatch):
+    """The whole sharded code path (GEMV -> exchange [mailbox kernel | local best + NCCL all-gather + global pick] ->
+    cached-atom update) with a communicator of one rank: must equal the oracle and the unsharded GPU path."""
+    if exchange == "nccl":
+        monkeypatch.setenv("CSB200_SHARD_EXCHANGE", "nccl")
+    else:
+        monkeypatch.delenv("CSB200_SHARD_EXCHANGE", raising=False)
     rng = np.random.default_rng(21)
     M, N, k = 256, 3000, 12
     A = po.gaussian_dictionary(rng, M, N, dtype)
@@ -777,6 +877,7 @@ def test_sharded_single_rank_matches_oracle(cs, po, dtype):
             x1 = cs.omp(shard, b, k)
     finally:
         comm.close()
+    assert info["exchange"] == exchange
     t = po.Trace()
     ref = po.omp(A, b, k, trace=t)
     assert info["order"].tolist() == t.order()

@@ -92,6 +92,43 @@ def c1(cs, dev, args):
     return out
 
 
+def c2s(cs, dev, args):
+    """Single-signal omp on the config-2 dictionary (1024 x 8192: 64 MiB FP64 / 32 MiB FP32 -- smaller than the
+    126 MB L2): the GEMV path with the dictionary L2-resident.  GB/s above the HBM peak = served from L2."""
+    M, N, k = 1024, 8192, 32
+    out = dict(config="c2s single-signal omp 1024x8192 k=32 (dictionary L2-resident)", hbm_peak_GBps=HBM_PEAK)
+    for dt, name in [(np.float64, "f64"), (np.float32, "f32")]:
+        A, Bm, idx = make_problem(M, N, k, 4, dt, dev)
+        with cs.Dictionary(A) as D, cs.Batch(D, 1, k) as b:
+            b.upload(Bm[:, :1])
+            for _ in range(5):
+                b.omp(k, 1e-30)
+            b.profile(True)
+            ms, corr, nl = [], 0.0, 0
+            for _ in range(20):
+                b.omp(k, 1e-30)
+                ms.append(b.last_solve_ms())
+            corr, nl, other = b.corr_time()
+            b.profile(False)
+            plain = []
+            for _ in range(50):
+                b.omp(k, 1e-30)
+                plain.append(b.last_solve_ms())
+            sel, coef, nnz, res, its = b.download(k)
+        gemv_us = 1e3 * corr / max(1, nl)
+        gbs = M * N * A.itemsize / (gemv_us * 1e-6) / 1e9
+        out[name] = dict(us_per_solve=1e3 * float(np.median(plain)), us_per_solve_profiled=1e3 * float(np.median(ms)),
+                         gemv_us_per_launch=gemv_us, gemv_GBps=gbs, gemv_vs_hbm_peak=gbs / HBM_PEAK,
+                         gemv_share=corr / float(np.sum(ms)), dict_bytes=M * N * A.itemsize,
+                         support_recovered=bool(set(idx[0]) == set(sel[0, :nnz[0]].tolist())))
+        if args.cpu:
+            from oracle import pursuit_oracle as po
+            c = cpu_oracle(lambda s: po.omp(A, Bm[:, s % 4], k), 16)
+            out[name]["cpu_baseline_us_per_solve"] = 1e6 / c["solves_per_s"]
+            out[name]["cpu_cores"] = c["cores"]
+    return out
+
+
 def c3(cs, dev, args):
     M, N, k, l, B = 2048, 32768, 64, 4, int(8192 * args.scale)
     A, Bm, idx = make_problem(M, N, k, B, np.float64, dev)
@@ -238,7 +275,7 @@ def c4(cs, dev, args):
     out = dict(config=f"c4 omp 8192x{N} f32 k={k}, column-sharded over {world} GPU(s)", solves_per_s=1.0 / wall,
                wall_s=wall, corr_ms_total=corr_ms, gemv_GBps_per_gpu=gbs, frac_of_hbm_peak=gbs / HBM_PEAK,
                hbm_peak_GBps=HBM_PEAK, gemv_share_of_wall=corr_ms * 1e-3 / wall, planted_atoms_found=int(found.item()),
-               planted_atoms=per * world, resnorm=info["resnorm"])
+               planted_atoms=per * world, resnorm=info["resnorm"], exchange=info["exchange"])
     comm.close(); shard.close()
     if world > 1:
         dist.destroy_process_group()
@@ -247,7 +284,7 @@ def c4(cs, dev, args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4", "c5", "fr2", "sp2"])
+    ap.add_argument("--config", required=True, choices=["c1", "c2s", "c3", "c4", "c5", "fr2", "sp2"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cpu", action="store_true", help="also time the CPU oracle on a bounded sample (reported baseline)")
     a = ap.parse_args()
@@ -255,6 +292,6 @@ if __name__ == "__main__":
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     cs = ge.load_package()
-    res = {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "fr2": fr2, "sp2": sp2}[a.config](cs, dev, a)
+    res = {"c1": c1, "c2s": c2s, "c3": c3, "c4": c4, "c5": c5, "fr2": fr2, "sp2": sp2}[a.config](cs, dev, a)
     if res is not None:
         print(json.dumps(res))
