@@ -31,6 +31,7 @@ struct CorrArgs {
     double* pval;        // [nsig][P][S]
     int* pidx;           // [nsig][P][S]
     int dense_ld = 0;    // > 0: store |c| itself, pval[sig * dense_ld + atom] (DMMA path only), and leave pidx alone
+    int l2_policy = 0;   // GEMV: L2 cache policy of the dictionary loads (set by the launcher; see corr_gemv.cu)
 };
 
 // correlation kernels (corr_gemm_f64.cu, corr_gemv.cu)

@@ -14,6 +14,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 namespace csb {
 namespace {
@@ -34,6 +35,30 @@ __device__ __forceinline__ double2 ldg_stream(const double2* p) {
     double2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
+}
+// Loads carrying an explicit L2 cache policy (createpolicy descriptor).  Measured on the single-signal 1024 x 8192
+// solve (tools/keep_sweep.sh, profiles/): the same streaming loads run the pass in 9.4 us with an evict_normal
+// descriptor against 15.1 us without one (FP64; 8.2 vs 11.0 us FP32) although both miss the L2 alike -- the policy-less
+// .nc/no_allocate load is the slow path on this part.  Marking a fraction of the dictionary evict_last (to pin it
+// across passes) did not produce hits and was slower for every fraction below 1.
+enum : int { L2POL_NONE = 0, L2POL_NORMAL = 1, L2POL_FIRST = 2, L2POL_LAST = 3 };
+__device__ __forceinline__ float4 ldg_stream(const float4* p, unsigned long long pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double2 ldg_stream(const double2* p, unsigned long long pol) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ unsigned long long l2_policy(int which) {
+    unsigned long long pol;
+    if (which == L2POL_FIRST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (which == L2POL_LAST) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 __device__ __forceinline__ void fma_vec(double& acc, const float4& a, const double* r) {
     acc = fma((double)a.x, r[0], acc); acc = fma((double)a.y, r[1], acc);
@@ -61,9 +86,11 @@ constexpr int GEMV_MAX_RANGE = 2048;   // atoms per CTA the top-s (s > 1) scratc
 //    a 2x tail on so short a kernel).
 // Each column has its own accumulator and is reduced inside one warp in the same order in both, so c_j is bit-identical
 // whichever instantiation (and whichever shard / GPU count) computes it.
-template <typename T, int UNR, int NT, int CG>
+template <typename T, int UNR, int NT, int CG, bool HINT>
 __global__ void __launch_bounds__(NT) corr_gemv_kernel(CorrArgs a) {
     constexpr int GW = NT / 32;
+    unsigned long long pol = 0;                    // HINT: dictionary loads carry an L2 cache policy (compile-time: a
+    if (HINT) pol = l2_policy(a.l2_policy);        // run-time branch in the streaming loop cost the HBM pass 13 %)
     using V = typename Vec<T>::type;
     constexpr int W = Vec<T>::W;
     extern __shared__ unsigned char gsm[];
@@ -104,7 +131,7 @@ __global__ void __launch_bounds__(NT) corr_gemv_kernel(CorrArgs a) {
         for (int i = lane; i < nvec; i += 32) {
             V x[CG];
 #pragma unroll
-            for (int c = 0; c < CG; ++c) x[c] = ldg_stream(col[c] + i);
+            for (int c = 0; c < CG; ++c) x[c] = HINT ? ldg_stream(col[c] + i, pol) : ldg_stream(col[c] + i);
             double rr[W];
 #pragma unroll
             for (int e = 0; e < W; ++e) rr[e] = (double)rs[i * W + e];
@@ -235,15 +262,36 @@ bool gemv_l2_regime(int N, int ld, bool f32) {
     return (size_t)N * ld * (f32 ? 4 : 8) <= GEMV_L2_RESIDENT_BYTES;
 }
 
-template <typename T, int UNR, int NT, int CG>
+int gemv_l2_policy(bool l2_regime) {
+    const char* env = getenv("CSB200_GEMV_POLICY");        // experiment hook: none | normal | first | last
+    if (env) return !strcmp(env, "none") ? L2POL_NONE : !strcmp(env, "first") ? L2POL_FIRST : !strcmp(env, "last") ? L2POL_LAST : L2POL_NORMAL;
+    return l2_regime ? L2POL_NORMAL : L2POL_NONE;
+}
+
+template <typename T, int UNR, int NT, int CG, bool HINT>
 cudaError_t gemv_prepare(size_t smem, int* occ) {
-    cudaError_t e = cudaFuncSetAttribute(corr_gemv_kernel<T, UNR, NT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess && occ) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, corr_gemv_kernel<T, UNR, NT, CG>, NT, smem);
+    cudaError_t e = cudaFuncSetAttribute(corr_gemv_kernel<T, UNR, NT, CG, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && occ) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, corr_gemv_kernel<T, UNR, NT, CG, HINT>, NT, smem);
     return e;
 }
+template <typename T, int UNR, int NT, int CG, bool HINT>
+void gemv_launch(dim3 grid, size_t smem, cudaStream_t st, const CorrArgs& b) {
+    corr_gemv_kernel<T, UNR, NT, CG, HINT><<<grid, NT, smem, st>>>(b);
+}
+// the four shapes of the kernel: {HBM, L2 regime} x {loads with / without an L2 policy}, per element type
+template <typename T>
+cudaError_t gemv_prepare_t(bool l2, bool hint, size_t smem, int* occ) {
+    if (l2) return hint ? gemv_prepare<T, 4, GT_L2, 2, true>(smem, occ) : gemv_prepare<T, 4, GT_L2, 2, false>(smem, occ);
+    return hint ? gemv_prepare<T, 2, GT, 4, true>(smem, occ) : gemv_prepare<T, 2, GT, 4, false>(smem, occ);
+}
+template <typename T>
+void gemv_launch_t(bool l2, bool hint, dim3 grid, size_t smem, cudaStream_t st, const CorrArgs& b) {
+    if (l2) { if (hint) gemv_launch<T, 4, GT_L2, 2, true>(grid, smem, st, b); else gemv_launch<T, 4, GT_L2, 2, false>(grid, smem, st, b); }
+    else { if (hint) gemv_launch<T, 2, GT, 4, true>(grid, smem, st, b); else gemv_launch<T, 2, GT, 4, false>(grid, smem, st, b); }
+}
 cudaError_t gemv_prepare_any(bool f32, bool l2, size_t smem, int* occ) {
-    if (l2) return f32 ? gemv_prepare<float, 4, GT_L2, 2>(smem, occ) : gemv_prepare<double, 4, GT_L2, 2>(smem, occ);
-    return f32 ? gemv_prepare<float, 2, GT, 4>(smem, occ) : gemv_prepare<double, 2, GT, 4>(smem, occ);
+    const bool hint = gemv_l2_policy(l2) != L2POL_NONE;
+    return f32 ? gemv_prepare_t<float>(l2, hint, smem, occ) : gemv_prepare_t<double>(l2, hint, smem, occ);
 }
 }  // namespace
 
@@ -288,14 +336,10 @@ cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st) {
         b.R = static_cast<const char*>(a.R) + (size_t)s0 * a.ld * (f32 ? 4 : 8);
         b.pval = a.pval + (size_t)s0 * a.P * a.S;
         b.pidx = a.pidx + (size_t)s0 * a.P * a.S;
+        b.l2_policy = gemv_l2_policy(l2);
         dim3 grid(a.P, ns);
-        if (l2) {
-            if (f32) corr_gemv_kernel<float, 4, GT_L2, 2><<<grid, GT_L2, smem, st>>>(b);
-            else corr_gemv_kernel<double, 4, GT_L2, 2><<<grid, GT_L2, smem, st>>>(b);
-        } else {
-            if (f32) corr_gemv_kernel<float, 2, GT, 4><<<grid, GT, smem, st>>>(b);
-            else corr_gemv_kernel<double, 2, GT, 4><<<grid, GT, smem, st>>>(b);
-        }
+        if (f32) gemv_launch_t<float>(l2, b.l2_policy != L2POL_NONE, grid, smem, st, b);
+        else gemv_launch_t<double>(l2, b.l2_policy != L2POL_NONE, grid, smem, st, b);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
