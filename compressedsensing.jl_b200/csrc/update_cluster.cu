@@ -14,7 +14,7 @@
 // exchange buffer (`map_shared_rank`), `cluster.sync()`, then sums the 8 partials in rank order -- a
 // deterministic all-reduce that costs one hardware cluster barrier.  The small state (support, R^{-1}, Q'b)
 // is replicated per CTA and updated identically, so no broadcast is needed.  Three exchanges per appended
-// atom (five when a second orthogonalisation sweep is required).
+// atom (four when a second orthogonalisation sweep is required): {A_S'v, ||a||^2}, {||v||^2, v'b}, {||r||^2}.
 #include <cooperative_groups.h>
 
 #include <atomic>
@@ -132,10 +132,15 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
             if (t >= kcap || t >= a.M) break;
 
             const T* aj = (Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld) + row0;
-            double s2 = 0.0;
-            for (int row = tid; row < Mc; row += CT) { const double e = (double)aj[row]; v[row] = e; s2 += e * e; }
+            double s2 = 0.0, sb0 = 0.0;
+            for (int row = tid; row < Mc; row += CT) {
+                const double e = (double)aj[row];
+                v[row] = e; s2 += e * e;
+                if (t == 0) sb0 = fma(e, (double)b[row], sb0);             // first atom: v = a_j is final, v'b rides along
+            }
             s2 = block_sum<CT>(s2, red);               // this CTA's part of ||a||^2 (syncs: v is complete)
-            double anorm2 = 0.0, before2 = 0.0, rho2 = 0.0, sb = 0.0;
+            if (t == 0) sb0 = block_sum<CT>(sb0, red);
+            double anorm2 = 0.0, before2 = 0.0, rho2 = 0.0, vb = 0.0;
             bool have_norm = false;
             for (int sweep = 0; sweep < 2; ++sweep) {
                 if (t > 0 && vec) {
@@ -173,10 +178,10 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                         if (lane == 0) g[i] = s;
                     }
                 }
-                if (tid == 0) g[t] = s2;                                   // rides along: ||a||^2 partial (sweep 0)
-                cluster_allreduce<CL>(cl, ex, g, t + 1, gs);
+                if (tid == 0) { g[t] = s2; g[t + 1] = sb0; }               // ride along: ||a||^2 partial (sweep 0), v'b (t = 0)
+                cluster_allreduce<CL>(cl, ex, g, t + 2, gs);
                 if (!have_norm) { anorm2 = gs[t]; before2 = anorm2; rho2 = anorm2; have_norm = true; }
-                if (t == 0) break;
+                if (t == 0) { vb = gs[1]; break; }
                 for (int i = tid; i < t; i += CT) {                        // hh = R^{-T} g
                     double acc = 0.0;
                     for (int l = 0; l <= i; ++l) acc = fma(Tm[l + i * ldT], gs[l], acc);
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                     ys[i] = sweep ? ys[i] + acc : acc;
                 }
                 __syncthreads();
-                double p2 = 0.0;
+                double p2 = 0.0, pb = 0.0;                                 // ||v||^2 and v'b partials of the swept v
                 if (vec) {
                     for (int row = tid * W; row < Mc; row += CT * W) {     // v -= A_S y on the owned rows, W rows per 16 B load
                         double acc[W];
@@ -205,7 +210,11 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                             for (int e = 0; e < W; ++e) acc[e] = fma(-av[e], yi, acc[e]);
                         }
 #pragma unroll
-                        for (int e = 0; e < W; ++e) { v[row + e] = acc[e]; p2 = fma(acc[e], acc[e], p2); }
+                        for (int e = 0; e < W; ++e) {
+                            v[row + e] = acc[e];
+                            p2 = fma(acc[e], acc[e], p2);
+                            pb = fma(acc[e], (double)b[row + e], pb);
+                        }
                     }
                 } else {
                     for (int row = tid; row < Mc; row += CT) {
@@ -213,23 +222,22 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                         for (int i = 0; i < t; ++i) acc -= (double)colp[i][row] * y[i];
                         v[row] = acc;
                         p2 += acc * acc;
+                        pb = fma(acc, (double)b[row], pb);
                     }
                 }
                 p2 = block_sum<CT>(p2, red);
-                if (tid == 0) g[0] = p2;
-                cluster_allreduce<CL>(cl, ex, g, 1, gs);
+                pb = block_sum<CT>(pb, red);
+                if (tid == 0) { g[0] = p2; g[1] = pb; }                    // one exchange for rho^2 and v'b
+                cluster_allreduce<CL>(cl, ex, g, 2, gs);
                 rho2 = gs[0];
+                vb = gs[1];
                 if (rho2 >= 0.5 * before2) break;                          // DGKS: one sweep was enough
                 before2 = rho2;
                 s2 = 0.0;
             }
             if (!(rho2 > 1e-26 * anorm2)) { flags |= 1; continue; }        // numerically dependent atom
             const double rho = sqrt(rho2);
-            for (int row = tid; row < Mc; row += CT) sb += v[row] * (double)b[row];
-            sb = block_sum<CT>(sb, red);
-            if (tid == 0) g[0] = sb;
-            cluster_allreduce<CL>(cl, ex, g, 1, gs);
-            const double zt = gs[0] / rho;                                 // z_t = q_t' b
+            const double zt = vb / rho;                                    // z_t = q_t' b
             const double gam = zt / rho;
             double s2r = 0.0;
             for (int row = tid; row < Mc; row += CT) {                     // r <- r - q_t z_t on the owned rows
