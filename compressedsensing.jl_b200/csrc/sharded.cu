@@ -297,6 +297,11 @@ struct csb200_comm {
     std::mutex mu;
     PeerBox px;
     int last_mode = 0;          // exchange used by the last solve: 0 NCCL all-gather, 1 peer-memory mailboxes
+    // per-solve resources kept across solves (allocation, 2-4 events per iteration and their release cost a 128-iteration
+    // solve 4-14 % of its wall time when they were created and destroyed inside every call)
+    unsigned char* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace {
@@ -419,6 +424,8 @@ int csb200_comm_destroy(csb200_comm* c) {
     if (!c) return CSB200_OK;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->scratch) cudaFree(c->scratch);
     peerbox_release(c);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     delete c;
@@ -470,15 +477,22 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
     o.nnz = take(4); o.sel = take(kcap * 4); o.T = take((size_t)kcap * kcap * 8); o.z = take(kcap * 8); o.x = take(kcap * 8);
     o.res = take(8); o.it = take(4); o.done = take(4); o.flags = take(4);
     o.send = take(rec_bytes); o.recv = take(rec_bytes * c->nranks); o.end = p;
-    unsigned char* base = nullptr;
-    CU_TRY(cudaMalloc(&base, o.end));
+    if (o.end > c->scratch_bytes) {                              // grow-only scratch owned by the communicator
+        if (c->scratch) { cudaStreamSynchronize(st); cudaFree(c->scratch); c->scratch = nullptr; c->scratch_bytes = 0; }
+        CU_TRY(cudaMalloc(&c->scratch, o.end));
+        c->scratch_bytes = o.end;
+    }
+    unsigned char* base = c->scratch;
     const char* tenv = getenv("CSB200_SHARD_TIMING");           // debug: per-phase device times on stderr
     const bool timing = tenv && tenv[0] == '1';
-    std::vector<cudaEvent_t> ev((timing ? 4 : 2) * (size_t)k);
+    const size_t nev = (timing ? 4 : 2) * (size_t)k;
+    while (c->ev_pool.size() < nev) {
+        cudaEvent_t e = nullptr;
+        CU_TRY(cudaEventCreate(&e));
+        c->ev_pool.push_back(e);
+    }
+    cudaEvent_t* ev = c->ev_pool.data();
     int status = CSB200_OK;
-    auto cleanup = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); cudaFree(base); };
-    for (auto& e : ev) { e = nullptr; }
-    for (auto& e : ev) { cudaError_t ce = cudaEventCreate(&e); if (ce != cudaSuccess) { cleanup(); return fail_cuda(ce, "cudaEventCreate"); } }
 
     do {
         cudaError_t e = cudaMemsetAsync(base, 0, o.end, st);
@@ -577,7 +591,6 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
         }
     } while (0);
     cudaStreamSynchronize(st);
-    cleanup();
     return status;
 }
 

@@ -254,7 +254,7 @@ def c4(cs, dev, args):
     torch.cuda.empty_cache()
     shard = cs.Dictionary(A_np, device=local, n_offset=rank * N_loc, n_total=N)
     del A_np
-    cs.omp_sharded(shard, comm, b, 4)
+    cs.omp_sharded(shard, comm, b, k)                 # warm-up: the same call (sizes the communicator's scratch, sets up the exchange)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
