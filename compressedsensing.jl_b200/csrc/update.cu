@@ -155,8 +155,10 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
                 if (m > 0) {
                     int done_b = 0;
                     if (m > 1) {
-                        done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2,
-                                                     a.gram, a.N, a.idx_offset);
+                        done_b = m <= 4 ? append_block<T, NT, 4>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2,
+                                                                 a.gram, a.N, a.idx_offset)
+                                        : append_block<T, NT, BLOCK_MAX>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at,
+                                                                         r_set, nr2, a.gram, a.N, a.idx_offset);
                         if (done_b) changed = true;
                     }
                     for (int c = done_b; c < m; ++c) {                   // one by one: single atom, or DGKS fallback
@@ -257,8 +259,10 @@ __device__ __forceinline__ int append_list(PursuitSmem<T>& S, int& t, const int*
         if (m > 0) {
             int done_b = 0;
             if (m > 1) {
-                done_b = append_block<T, NT>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2, gram, gramN,
-                                             idx_offset);
+                done_b = m <= 4 ? append_block<T, NT, 4>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set, nr2, gram,
+                                                         gramN, idx_offset)
+                                : append_block<T, NT, BLOCK_MAX>(S, t, m, s_J, s_Jcol, ld, Vb, Gm, Ym, sc, b_at, r_at, r_set,
+                                                                 nr2, gram, gramN, idx_offset);
                 if (done_b) changed = true;
             }
             for (int c = done_b; c < m; ++c) {

@@ -203,27 +203,31 @@ __device__ __forceinline__ void select_dense_small_t(const double* __restrict__ 
 #pragma unroll
     for (int q = 0; q < TK; ++q) { bv[q] = -1.0; bi[q] = INT_MAX; }
     constexpr int U = 8;                                             // independent loads in flight per thread
-    for (int c0 = tid; c0 < n; c0 += NT * U) {
-        double vv[U];
+    // The row holds |A'r| (the DMMA pass's EPI_ABS store): no fabs.  A thread meets its columns in ascending order, so a
+    // newcomer displaces the worst kept entry only when it is strictly larger (an equal value has the higher index):
+    // the common path is one compare per element; NaN never passes it.
+    auto offer = [&](double val, int c) {
+        if (val > bv[TK - 1]) {                                      // beats the worst entry kept so far
+            double cv = val;
+            int ci = c;
 #pragma unroll
-        for (int u = 0; u < U; ++u) { const int c = c0 + u * NT; vv[u] = c < n ? fabs(v[c]) : -1.0; }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const double val = vv[u];
-            const int c = c0 + u * NT;
-            if (val >= 0.0 && cand_better(val, c, bv[TK - 1], bi[TK - 1])) {   // beats the worst entry kept so far
-                double cv = val;
-                int ci = c;
-#pragma unroll
-                for (int q = 0; q < TK; ++q) {                                 // bubble the newcomer down the sorted list
-                    if (cand_better(cv, ci, bv[q], bi[q])) {
-                        const double tv = bv[q]; const int ti = bi[q];
-                        bv[q] = cv; bi[q] = ci; cv = tv; ci = ti;
-                    }
+            for (int q = 0; q < TK; ++q) {                           // bubble the newcomer down the sorted list
+                if (cand_better(cv, ci, bv[q], bi[q])) {
+                    const double tv = bv[q]; const int ti = bi[q];
+                    bv[q] = cv; bi[q] = ci; cv = tv; ci = ti;
                 }
             }
         }
+    };
+    const int n_full = n - n % (NT * U);                             // whole chunks: no bounds checks
+    for (int c0 = tid; c0 < n_full; c0 += NT * U) {
+        double vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) vv[u] = v[c0 + u * NT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) offer(vv[u], c0 + u * NT);
     }
+    for (int c = n_full + tid; c < n; c += NT) offer(v[c], c);
     double* cval = scratch;                                         // [NT * TK]
     int* cidx = reinterpret_cast<int*>(scratch + (size_t)NT * TK);  // [NT * TK]
 #pragma unroll
@@ -280,6 +284,22 @@ template <> struct RowVec<float> {
     static __device__ __forceinline__ void load(const float* p, double (&o)[4]) {
         const float4 x = *reinterpret_cast<const float4*>(p);
         o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;
+    }
+};
+
+// Two consecutive rows per load (16 bytes of an FP64 column, 8 of an FP32 one): the block-append sweeps keep
+// [atoms][rows] accumulators in registers and have no room for four rows per thread.
+template <typename T> struct RowPair;
+template <> struct RowPair<double> {
+    static __device__ __forceinline__ void load(const double* p, double (&o)[2]) {
+        const double2 x = *reinterpret_cast<const double2*>(p);
+        o[0] = x.x; o[1] = x.y;
+    }
+};
+template <> struct RowPair<float> {
+    static __device__ __forceinline__ void load(const float* p, double (&o)[2]) {
+        const float2 x = *reinterpret_cast<const float2*>(p);
+        o[0] = x.x; o[1] = x.y;
     }
 };
 
@@ -422,26 +442,36 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
 // Gm, Ym: [(kcap + BM)][BM] shared scratch.  Returns the number of atoms appended (<= m).
 constexpr int BLOCK_MAX = 8;
 
-template <typename T, int NT, typename BAt, typename RAt, typename RSet>
+// BMR: size of the per-thread register arrays (>= m; 4 or 8): with the arrays sized for 8 atoms the 16-byte loads of the
+// sweeps do not fit the 128 registers two CTAs per SM allow.  Shared-memory strides stay BLOCK_MAX.
+template <typename T, int NT, int BMR, typename BAt, typename RAt, typename RSet>
 __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, const int* __restrict__ J,
                                             const T* const* __restrict__ Jcol, int ld, double* __restrict__ Vb,
                                             double* __restrict__ Gm, double* __restrict__ Ym, double* __restrict__ sc,
                                             BAt b_at, RAt r_at, RSet r_set, double& nr2,
                                             const double* __restrict__ gram = nullptr, int gramN = 0, int idx_offset = 0) {
     constexpr int W = RowVec<T>::W;
+    constexpr int WP = 2;                                      // rows per thread and step in the copy and in sweep 2
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = t;
     // sc: [0, BM) ||a_c||^2, [BM, 2BM) rho_c, [2BM, 3BM) v_c'b, [3BM, 4BM) ||v_c||^2
-    double part[BLOCK_MAX];
+    double part[BMR];
 #pragma unroll
-    for (int c = 0; c < BLOCK_MAX; ++c) part[c] = 0.0;
-    for (int row = tid; row < ld; row += NT) {
+    for (int c = 0; c < BMR; ++c) part[c] = 0.0;
+    for (int row = tid * WP; row < ld; row += NT * WP) {           // the new atoms: two rows per load, all m in flight
+        double e[BMR][WP];
 #pragma unroll
-        for (int c = 0; c < BLOCK_MAX; ++c)
-            if (c < m) { const double e = (double)Jcol[c][row]; Vb[c * ld + row] = e; part[c] += e * e; }
+        for (int c = 0; c < BMR; ++c)
+            if (c < m) RowPair<T>::load(Jcol[c] + row, e[c]);
+#pragma unroll
+        for (int c = 0; c < BMR; ++c)
+            if (c < m) {
+#pragma unroll
+                for (int w = 0; w < WP; ++w) { Vb[c * ld + row + w] = e[c][w]; part[c] = fma(e[c][w], e[c][w], part[c]); }
+            }
     }
 #pragma unroll
-    for (int c = 0; c < BLOCK_MAX; ++c)
+    for (int c = 0; c < BMR; ++c)
         if (c < m) { const double s = block_sum<NT>(part[c], S.red); if (tid == 0) sc[c] = s; }
     __syncthreads();
     // sweep 1: Gm[i][c] = <column i, a_c>, columns i < t0 from the dictionary, i >= t0 from the block itself --
@@ -454,9 +484,9 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
         }
     } else
     for (int i = warp; i < t0 + m; i += NT / 32) {
-        double acc[BLOCK_MAX];
+        double acc[BMR];
 #pragma unroll
-        for (int c = 0; c < BLOCK_MAX; ++c) acc[c] = 0.0;
+        for (int c = 0; c < BMR; ++c) acc[c] = 0.0;
         if (i < t0) {
             const T* ai = S.colp[i];
 #pragma unroll 2
@@ -464,7 +494,7 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
                 double a[W];
                 RowVec<T>::load(ai + row, a);
 #pragma unroll
-                for (int c = 0; c < BLOCK_MAX; ++c)
+                for (int c = 0; c < BMR; ++c)
                     if (c < m) {
 #pragma unroll
                         for (int e = 0; e < W; ++e) acc[c] = fma(a[e], Vb[c * ld + row + e], acc[c]);
@@ -475,11 +505,11 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
             for (int row = lane; row < ld; row += 32) {
                 const double a = ai[row];
 #pragma unroll
-                for (int c = 0; c < BLOCK_MAX; ++c) if (c < m) acc[c] = fma(a, Vb[c * ld + row], acc[c]);
+                for (int c = 0; c < BMR; ++c) if (c < m) acc[c] = fma(a, Vb[c * ld + row], acc[c]);
             }
         }
 #pragma unroll
-        for (int c = 0; c < BLOCK_MAX; ++c)
+        for (int c = 0; c < BMR; ++c)
             if (c < m) { const double s = warp_sum(acc[c]); if (lane == 0) Gm[i * BLOCK_MAX + c] = s; }
     }
     __syncthreads();
@@ -521,32 +551,54 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
         __syncthreads();
     }
     if (done == 0) return 0;
-    // sweep 2: all `done` directions at once (in place: a row's originals are held in registers)
-    double pb[BLOCK_MAX], pn[BLOCK_MAX];
+    // sweep 2: all `done` directions at once, two rows per thread and step (16-byte gathers of FP64 atoms).  In
+    // place: a thread owns its rows, and the originals a_c are read from Vb before the row's results overwrite them.
+    double pb[BMR], pn[BMR];
 #pragma unroll
-    for (int c = 0; c < BLOCK_MAX; ++c) { pb[c] = 0.0; pn[c] = 0.0; }
-    for (int row = tid; row < ld; row += NT) {
-        double v0[BLOCK_MAX], acc[BLOCK_MAX];
+    for (int c = 0; c < BMR; ++c) { pb[c] = 0.0; pn[c] = 0.0; }
+    for (int row = tid * WP; row < ld; row += NT * WP) {
+        double acc[BMR][WP];
 #pragma unroll
-        for (int c = 0; c < BLOCK_MAX; ++c) { v0[c] = c < done ? Vb[c * ld + row] : 0.0; acc[c] = v0[c]; }
+        for (int c = 0; c < BMR; ++c)
+#pragma unroll
+            for (int w = 0; w < WP; ++w) acc[c][w] = c < done ? Vb[c * ld + row + w] : 0.0;
 #pragma unroll 8
         for (int i = 0; i < t0; ++i) {
-            const double a = (double)S.colp[i][row];
+            double a[WP];
+            RowPair<T>::load(S.colp[i] + row, a);
 #pragma unroll
-            for (int c = 0; c < BLOCK_MAX; ++c) if (c < done) acc[c] = fma(-a, Ym[i * BLOCK_MAX + c], acc[c]);
+            for (int c = 0; c < BMR; ++c)
+                if (c < done) {
+                    const double yc = Ym[i * BLOCK_MAX + c];
+#pragma unroll
+                    for (int w = 0; w < WP; ++w) acc[c][w] = fma(-a[w], yc, acc[c][w]);
+                }
         }
 #pragma unroll
-        for (int c = 1; c < BLOCK_MAX; ++c)
+        for (int c = 1; c < BMR; ++c)
 #pragma unroll
             for (int cp = 0; cp < c; ++cp)
-                if (c < done) acc[c] = fma(-v0[cp], Ym[(t0 + cp) * BLOCK_MAX + c], acc[c]);
-        const double bb = b_at(row);
+                if (c < done) {
+                    const double yc = Ym[(t0 + cp) * BLOCK_MAX + c];
 #pragma unroll
-        for (int c = 0; c < BLOCK_MAX; ++c)
-            if (c < done) { Vb[c * ld + row] = acc[c]; pb[c] = fma(acc[c], bb, pb[c]); pn[c] = fma(acc[c], acc[c], pn[c]); }
+                    for (int w = 0; w < WP; ++w) acc[c][w] = fma(-Vb[cp * ld + row + w], yc, acc[c][w]);
+                }
+#pragma unroll
+        for (int w = 0; w < WP; ++w) {
+            const double bb = b_at(row + w);
+#pragma unroll
+            for (int c = 0; c < BMR; ++c)
+                if (c < done) { pb[c] = fma(acc[c][w], bb, pb[c]); pn[c] = fma(acc[c][w], acc[c][w], pn[c]); }
+        }
+#pragma unroll
+        for (int c = 0; c < BMR; ++c)
+            if (c < done) {
+#pragma unroll
+                for (int w = 0; w < WP; ++w) Vb[c * ld + row + w] = acc[c][w];
+            }
     }
 #pragma unroll
-    for (int c = 0; c < BLOCK_MAX; ++c)
+    for (int c = 0; c < BMR; ++c)
         if (c < done) {
             const double sb = block_sum<NT>(pb[c], S.red);
             const double sn = block_sum<NT>(pn[c], S.red);
@@ -558,7 +610,7 @@ __device__ __forceinline__ int append_block(PursuitSmem<T>& S, int& t, int m, co
     for (int row = tid; row < ld; row += NT) {
         double acc = r_at(row);
 #pragma unroll
-        for (int c = 0; c < BLOCK_MAX; ++c)
+        for (int c = 0; c < BMR; ++c)
             if (c < done) acc = fma(-sc[2 * BLOCK_MAX + c] / sc[3 * BLOCK_MAX + c], Vb[c * ld + row], acc);
         const T rr = (T)acc;
         r_set(row, rr);
