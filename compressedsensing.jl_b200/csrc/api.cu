@@ -159,6 +159,7 @@ struct csb200_batch {
     SolveKey graph_key, graph_seen;
     bool graph_seen_valid = false;
     cudaGraphExec_t graph_exec = nullptr;
+    bool persist_set = false;       // CSB200_GEMV_PERSIST experiment: access-policy window installed on the stream
     int64_t graph_launches = 0;     // update launches one replay stands for (other_launches accounting)
     int64_t graph_replays = 0;
     std::mutex mu;
@@ -220,11 +221,41 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
 // caller can consume it (allow_dense) and S is large, the dense |A'r| matrix: S selection rounds in the DMMA epilogue
 // cost as much as the contraction itself at S = 32, a plain store costs nothing.
 constexpr int DENSE_MIN_S = 2;      // S = 1 keeps the fused per-block argmax (no N x nsig matrix); from 2 on the store wins
+// Experiment hook (CSB200_GEMV_PERSIST=<MiB>): pin that much of the dictionary in the L2's persisting carve-out through
+// a stream access-policy window (hitRatio = MiB / dictionary size, misses stream), for few-signal GEMV solves on
+// dictionaries around the L2 size.  Logs what the device granted on stderr once.
+void maybe_persist_dictionary(csb200_batch* b) {
+    static const double want_mib = [] { const char* e = getenv("CSB200_GEMV_PERSIST"); return e ? atof(e) : 0.0; }();
+    if (want_mib <= 0.0 || b->persist_set) return;
+    b->persist_set = true;
+    csb200_dict* d = b->dict;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) { cudaGetLastError(); return; }
+    size_t carve = (size_t)(want_mib * (1 << 20));
+    if (carve > (size_t)prop.persistingL2CacheMaxSize) carve = (size_t)prop.persistingL2CacheMaxSize;
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    const size_t bytes = (size_t)d->ld * d->N * d->esize();
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = d->dA;
+    attr.accessPolicyWindow.num_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+    double ratio = (double)carve / (double)attr.accessPolicyWindow.num_bytes;
+    attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (e == cudaSuccess) e = cudaStreamSetAttribute(b->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    fprintf(stderr, "[csb200] L2 persistence: carve-out %.1f MiB (device max %.1f), window %.1f MiB (max %.1f), hitRatio %.3f: %s\n",
+            carve / 1048576.0, prop.persistingL2CacheMaxSize / 1048576.0, attr.accessPolicyWindow.num_bytes / 1048576.0,
+            prop.accessPolicyMaxWindowSize / 1048576.0, attr.accessPolicyWindow.hitRatio, cudaGetErrorString(e));
+    cudaGetLastError();
+}
+
 int run_corr(csb200_batch* b, int S, int impl, bool allow_dense = false) {
     csb200_dict* d = b->dict;
     const bool f32 = d->dtype == CSB200_F32;
     if (impl == IMPL_AUTO) impl = b->corr_impl_env;
     if (impl == IMPL_AUTO) impl = (!f32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
+    if (impl == IMPL_GEMV) maybe_persist_dictionary(b);
     const int blk = impl == IMPL_GEMM ? corr_gemm_f64_block() : PBLK;
     const int64_t P = impl == IMPL_GEMV ? corr_gemv_blocks((int)d->N, (int)d->ld, f32, S, d->num_sms) : (d->N + blk - 1) / blk;
     static const bool dense_off = [] { const char* e = getenv("CSB200_DENSE_TOPK"); return e && e[0] == '0'; }();
