@@ -67,6 +67,16 @@ Base.eltype(::Dictionary{T}) where {T} = T
 const MatOrDict = Union{AbstractMatrix,Dictionary}
 as_dictionary(A::Dictionary) = A
 as_dictionary(A::AbstractMatrix) = Dictionary(A)
+# A raw matrix is uploaded for this one call: its device copy is released when the call returns, not whenever Julia's
+# GC -- which does not see device memory -- gets to the finalizer (a loop of omp(A, b, k) calls would fill the GPU).
+function with_dictionary(f, A::MatOrDict)
+    D = as_dictionary(A)
+    try
+        return f(D)
+    finally
+        A isa Dictionary || finalize(D)
+    end
+end
 signal_eltype(A::Dictionary{T}) where {T} = T
 signals(D::Dictionary{T}, b::AbstractVecOrMat) where {T} = begin
     size(b, 1) == D.M || throw(DimensionMismatch("A has $(D.M) rows, b has length $(size(b, 1))"))
@@ -120,7 +130,7 @@ end
 # omp  (src/matchingpursuit.jl:73-91)
 function omp(A::MatOrDict, b::AbstractVecOrMat, ε::Real, k::Int = size(A, 1); csc::Bool = false)
     ε ≥ 0 || throw("ε = $ε has to be non-negative")
-    run_omp_like(:omp, as_dictionary(A), b, 1, ε, k; csc = csc)     # csc = true: N x nsig SparseMatrixCSC (additive)
+    with_dictionary(D -> run_omp_like(:omp, D, b, 1, ε, k; csc = csc), A)   # csc = true: N x nsig SparseMatrixCSC (additive)
 end
 omp(A::MatOrDict, b::AbstractVecOrMat, k::Int) = omp(A, b, eps(eltype(A)), k)
 omp(A::MatOrDict, b::AbstractVecOrMat; max_residual = eps(eltype(A)), sparsity = min(size(A)...)) =
@@ -129,15 +139,16 @@ omp(A::MatOrDict, b::AbstractVecOrMat; max_residual = eps(eltype(A)), sparsity =
 # gomp  (src/matchingpursuit.jl:126-148)
 function gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, ε::Real, k::Int = size(A, 1))
     ε ≥ 0 || throw("ε = $ε has to be non-negative")
-    run_omp_like(:gomp, as_dictionary(A), b, l, ε, k)
+    with_dictionary(D -> run_omp_like(:gomp, D, b, l, ε, k), A)
 end
 gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, k::Int) = gomp(A, b, l, eps(eltype(A)), k)
 gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int; max_residual = eps(eltype(A)), sparsity = size(A, 2)) =
     gomp(A, b, l, max_residual, sparsity)
 
 # fr == ols == oomp == ormp  (src/forward.jl:33-54): forward regression; FP64 dictionaries
-function fr(A::MatOrDict, b::AbstractVecOrMat, max_ε::Real, min_δ::Real, k::Int = size(A, 1); csc::Bool = false)
-    D = as_dictionary(A)
+fr(A::MatOrDict, b::AbstractVecOrMat, max_ε::Real, min_δ::Real, k::Int = size(A, 1); csc::Bool = false) =
+    with_dictionary(D -> fr_on(D, b, max_ε, min_δ, k; csc = csc), A)
+function fr_on(D::Dictionary, b::AbstractVecOrMat, max_ε::Real, min_δ::Real, k::Int; csc::Bool = false)
     B = signals(D, b)
     nsig = size(B, 2)
     k = min(k, size(D)...)
@@ -158,8 +169,9 @@ const oomp = fr
 const ormp = fr
 
 # sp  (src/twostage.jl:105-117) and oblivious  (src/oblivious.jl:3-8)
-function sp(A::MatOrDict, b::AbstractVecOrMat, k::Int, δ::Real = 1e-12; maxiter = 16k)
-    D = as_dictionary(A)
+sp(A::MatOrDict, b::AbstractVecOrMat, k::Int, δ::Real = 1e-12; maxiter = 16k) =
+    with_dictionary(D -> sp_on(D, b, k, δ; maxiter = maxiter), A)
+function sp_on(D::Dictionary, b::AbstractVecOrMat, k::Int, δ::Real; maxiter = 16k)
     2k > D.M && error("2k = $(2k) > $(D.M) = length(b) is invalid for Subspace Pursuit")
     B = signals(D, b); nsig = size(B, 2); stride = max(k, 1)
     sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
@@ -170,8 +182,8 @@ function sp(A::MatOrDict, b::AbstractVecOrMat, k::Int, δ::Real = 1e-12; maxiter
     xs = [to_sparse(D.N, view(sel, :, s), view(coef, :, s), nnz[s]) for s in 1:nsig]
     return b isa AbstractVector ? xs[1] : xs
 end
-function oblivious(A::MatOrDict, b::AbstractVecOrMat, k::Int)
-    D = as_dictionary(A)
+oblivious(A::MatOrDict, b::AbstractVecOrMat, k::Int) = with_dictionary(D -> oblivious_on(D, b, k), A)
+function oblivious_on(D::Dictionary, b::AbstractVecOrMat, k::Int)
     B = signals(D, b); nsig = size(B, 2); stride = max(k, 1)
     sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
     nnz = Vector{Int64}(undef, nsig); res = Vector{Float64}(undef, nsig)
@@ -183,8 +195,9 @@ function oblivious(A::MatOrDict, b::AbstractVecOrMat, k::Int)
 end
 
 # mp  (src/matchingpursuit.jl:34-40); x is an optional warm start (single-signal form)
-function mp(A::MatOrDict, b::AbstractVector, k::Int, x::SparseVector = spzeros(size(A, 2)))
-    D = as_dictionary(A)
+mp(A::MatOrDict, b::AbstractVector, k::Int, x::SparseVector = spzeros(size(A, 2))) =
+    with_dictionary(D -> mp_on(D, b, k, x), A)
+function mp_on(D::Dictionary, b::AbstractVector, k::Int, x::SparseVector)
     B = signals(D, b)
     stride = max(k, 1)
     sel = Vector{Int64}(undef, stride); coef = Vector{Float64}(undef, stride); res = Vector{Float64}(undef, 1)
