@@ -94,3 +94,25 @@ def test_c_oracle_quirks(po):
     assert got["nzind"][0, :got["nnz"][0]].tolist() == ref.nzind and got["iters"][0] == 2
     with pytest.raises(ValueError):
         c_oracle.solve_batch("omp", A, Bm, 3, eps=-1.0)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract's
+    keys; under torchrun every rank but 0 exits without output."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--ref-signals", "8"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "solves/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("OMP solves/sec at 1024x8192,k=32") and line["value"] > 0
+    assert line["steps"] == 1 and line["warmup"] == 1 and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
