@@ -19,7 +19,7 @@
 // Steps 2-4 are ONE kernel when the ranks can map each other's memory (`peer_exchange_kernel`, the default):
 // every rank owns a mailbox in device memory, exported with cudaIpcGetMemHandle and mapped by all peers
 // (NVLink / NVSwitch peer access).  The kernel reduces the local candidates, stores its record straight
-// into slot [parity][rank] of EVERY rank's mailbox, publishes a sequence number with st.release.sys,
+// into slot [parity][rank] of EVERY rank's mailbox, publishes a sequence number (bar.sync, fence.sys, st.release.sys),
 // spins (ld.acquire.sys, bounded by a timeout) until all ranks' numbers have arrived in its own mailbox and
 // picks the winner -- no NCCL launch, no staging copy, one NVLink one-way latency per iteration.  Two
 // parity slots suffice: a rank cannot publish iteration s + 1 before every peer has published s, and a
@@ -243,11 +243,13 @@ __global__ void __launch_bounds__(PX_THREADS) peer_exchange_kernel(PeerArgs pa, 
         h.x = (unsigned)vb; h.y = (unsigned)(vb >> 32); h.z = (unsigned)best; h.w = 0u;
         *reinterpret_cast<uint4*>(pa.box[tid] + slot) = h;
     }
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                       // CTA-scope order: every thread's stores precede the publishing threads' fence
     unsigned char* mine = pa.box[pa.rank];
     if (tid < pa.nranks) {
-        // (c) publish: my record for exchange `seq` is complete in rank tid's mailbox
+        // (c) publish: my record for exchange `seq` is complete in rank tid's mailbox.  The system-scope fence is
+        // cumulative over the stores the barrier ordered before it, so only the <= 16 publishing threads pay for it
+        // (all 1024 threads fencing made membar the kernel's top stall: ncu, profiles/c4_exchange_r01f.md).
+        __threadfence_system();
         st_release_sys(reinterpret_cast<unsigned long long*>(pa.box[tid]) + pa.rank, pa.seq);
         // (d) wait for rank tid's record in my own mailbox
         const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine) + tid;
