@@ -65,6 +65,25 @@ def cpu_oracle(fn, n):
     return {"solves_per_s": n / dt, "signals": n, "seconds": dt, "cores": os.cpu_count(), "kind": "port"}
 
 
+def cpu_oracle_c(algo, A, Bm, n, k, l=1, eps=None):
+    """The plain-C restatement (oracle/pursuit_oracle.c), one signal per host thread, on n signals (columns of Bm,
+    cycled): the stronger CPU baseline for the Float64 omp / gomp / mp configs.  None when it cannot be built."""
+    try:
+        from oracle import c_oracle
+        c_oracle.lib()
+    except Exception as exc:
+        sys.stderr.write(f"C oracle unavailable ({exc})\n")
+        return None
+    if A.dtype != np.float64:
+        return None
+    cols = np.asfortranarray(Bm[:, [s % Bm.shape[1] for s in range(n)]])
+    t0 = time.perf_counter()
+    got = c_oracle.solve_batch(algo, A, cols, k, l=l, eps=eps)
+    dt = time.perf_counter() - t0
+    return {"solves_per_s": n / dt, "signals": n, "seconds": dt, "cores": int(got["threads"]), "kind": "port",
+            "engine": "plain-C oracle, one signal per thread"}
+
+
 def c1(cs, dev, args):
     M, N, k = 128, 256, 8
     A, Bm, idx = make_problem(M, N, k, 64, np.float64, dev)
@@ -89,6 +108,10 @@ def c1(cs, dev, args):
         from oracle import pursuit_oracle as po
         out["cpu_baseline"] = cpu_oracle(lambda s: po.omp(A, Bm[:, s % 64], k, ls="givens"), 256)
         out["cpu_baseline_us_per_solve"] = 1e6 / out["cpu_baseline"]["solves_per_s"]
+        c = cpu_oracle_c("omp", A, Bm, 1, k)                     # one signal, one thread: the latency a caller sees
+        if c:
+            c1t = min(cpu_oracle_c("omp", A, Bm[:, :1], 1, k)["seconds"] for _ in range(20))
+            out["cpu_c_oracle_us_per_solve_1thread"] = 1e6 * c1t
     return out
 
 
@@ -126,6 +149,9 @@ def c2s(cs, dev, args):
             c = cpu_oracle(lambda s: po.omp(A, Bm[:, s % 4], k), 16)
             out[name]["cpu_baseline_us_per_solve"] = 1e6 / c["solves_per_s"]
             out[name]["cpu_cores"] = c["cores"]
+            cc = cpu_oracle_c("omp", A, Bm, 1, k)
+            if cc:
+                out[name]["cpu_c_oracle_us_per_solve_1thread"] = 1e6 * cc["seconds"]
     return out
 
 
@@ -147,7 +173,8 @@ def c3(cs, dev, args):
                corr_share=corr_ms / ms, support_recovered_frac=rec, max_resnorm=float(res.max()))
     if args.cpu:
         from oracle import pursuit_oracle as po
-        out["cpu_baseline"] = cpu_oracle(lambda s: po.gomp(A, Bm[:, s], l, k, ls="givens"), 12)
+        out["cpu_baseline"] = cpu_oracle_c("gomp", A, Bm, 32, k, l=l) or \
+            cpu_oracle(lambda s: po.gomp(A, Bm[:, s], l, k, ls="givens"), 12)
     return out
 
 
@@ -218,7 +245,7 @@ def c5(cs, dev, args):
                corr_share=corr_ms / ms, median_resnorm=float(np.median(res)))
     if args.cpu:
         from oracle import pursuit_oracle as po
-        out["cpu_baseline"] = cpu_oracle(lambda s: po.mp(A, Bm[:, s], iters), 2)
+        out["cpu_baseline"] = cpu_oracle_c("mp", A, Bm, 16, iters) or cpu_oracle(lambda s: po.mp(A, Bm[:, s], iters), 2)
     return out
 
 
