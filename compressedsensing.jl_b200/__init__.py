@@ -103,6 +103,7 @@ def _load() -> ctypes.CDLL:
         "csb200_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
         "csb200_comm_destroy": (c_int, [c_void_p]),
         "csb200_comm_exchange_mode": (c_int, [c_void_p]),
+        "csb200_comm_last_timing": (c_int, [c_void_p, f64p, i64p]),
         "csb200_omp_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, i64p, f64p, i64p, f64p, i64p,
                                        f64p]),
         "csb200_debug_corr_topk": (c_int, [c_void_p, c_int, c_int64, i64p, f64p]),
@@ -125,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "csb200_assemble_csc", "csb200_comm_unique_id", "csb200_batch_fr", "csb200_fr",
     "csb200_batch_sp", "csb200_batch_oblivious", "csb200_sp", "csb200_oblivious", "csb200_dict_colnorms",
     "csb200_dict_cumbabel",
-    "csb200_comm_create", "csb200_comm_destroy", "csb200_comm_exchange_mode", "csb200_omp_sharded", "csb200_debug_corr_topk",
+    "csb200_comm_create", "csb200_comm_destroy", "csb200_comm_exchange_mode", "csb200_comm_last_timing", "csb200_omp_sharded", "csb200_debug_corr_topk",
     "csb200_debug_get_residual", "csb200_debug_graph_replays",
 ]
 
@@ -669,6 +670,14 @@ class ShardComm:
         buf = ctypes.create_string_buffer(unique_id, NCCL_ID_BYTES)
         _check(lib.csb200_comm_create(buf, rank, nranks, device, byref(h)))
         self._h, self.rank, self.nranks = h, rank, nranks
+
+    def last_timing(self) -> dict:
+        """Device-time breakdown (ms) of the last sharded solve on this rank (`csb200_comm_last_timing`)."""
+        ms = np.zeros(5, dtype=np.float64)
+        it = c_int64()
+        _check(lib.csb200_comm_last_timing(self._h, _f64p(ms), byref(it)))
+        return {"solve_ms": float(ms[0]), "corr_ms": float(ms[1]), "exchange_ms": float(ms[2]), "update_ms": float(ms[3]),
+                "gap_ms": float(ms[4]), "iters": int(it.value)}
 
     def close(self) -> None:
         if getattr(self, "_h", None):

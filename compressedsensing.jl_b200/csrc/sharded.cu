@@ -304,6 +304,11 @@ struct csb200_comm {
     unsigned char* scratch = nullptr;
     size_t scratch_bytes = 0;
     std::vector<cudaEvent_t> ev_pool;
+    // device-time breakdown of the last solve (ms): whole solve, correlation passes, exchange, update, gaps; the
+    // last three only when CSB200_SHARD_TIMING is set (1: also printed on stderr, 2: silent)
+    double last_ms[5] = {0, 0, 0, 0, 0};
+    int64_t last_iters = 0;
+    unsigned long long* d_agree = nullptr;      // [2 + 2 * nranks]: {seq, ready} send slot + gathered copies
 };
 
 namespace {
@@ -428,6 +433,7 @@ int csb200_comm_destroy(csb200_comm* c) {
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->d_agree) cudaFree(c->d_agree);
     peerbox_release(c);
     if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
     delete c;
@@ -435,6 +441,14 @@ int csb200_comm_destroy(csb200_comm* c) {
 }
 
 int csb200_comm_exchange_mode(const csb200_comm* c) { return c ? c->last_mode : CSB200_ERR_INVALID_ARG; }
+
+int csb200_comm_last_timing(csb200_comm* c, double* ms5, int64_t* iters) {
+    if (!c || !ms5) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int i = 0; i < 5; ++i) ms5[i] = c->last_ms[i];
+    if (iters) *iters = c->last_iters;
+    return CSB200_OK;
+}
 
 int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_t k, double eps, int64_t* sel_idx,
                        double* coef, int64_t* nnz_out, double* resnorm, int64_t* iters_out, double* corr_ms) {
@@ -459,6 +473,22 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
     bool peer = want_peer_exchange();
     if (peer && !c->px.tried) { rc = peerbox_setup(c, rec_bytes); if (rc) return rc; }
     peer = peer && c->px.ready && rec_bytes <= c->px.slot_bytes;
+    // The mailbox sequence number is per-rank host state: a rank that left an earlier solve early (error, timeout)
+    // would otherwise run behind its peers for good and read stale slots.  Every solve therefore starts by agreeing
+    // on {max sequence number, "all ranks take the peer path"} through one 16-byte-per-rank all-gather.
+    if (c->nranks > 1) {
+        if (!c->d_agree) CU_TRY(cudaMalloc(&c->d_agree, sizeof(unsigned long long) * (size_t)(2 + 2 * c->nranks)));
+        unsigned long long me[2] = {c->px.seq, peer ? 1ull : 0ull};
+        std::vector<unsigned long long> all(2 * (size_t)c->nranks);
+        CU_TRY(cudaMemcpyAsync(c->d_agree, me, sizeof me, cudaMemcpyHostToDevice, st));
+        NC_TRY(nccl().AllGather(c->d_agree, c->d_agree + 2, 2 * sizeof(unsigned long long), ncclChar, c->comm, st));
+        CU_TRY(cudaMemcpyAsync(all.data(), c->d_agree + 2, all.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        for (int g = 0; g < c->nranks; ++g) {
+            if (all[2 * g] > c->px.seq) c->px.seq = all[2 * g];
+            peer = peer && all[2 * g + 1] == 1ull;
+        }
+    }
     c->last_mode = peer ? 1 : 0;
     PeerArgs pa;
     memset(&pa, 0, sizeof pa);
@@ -485,9 +515,10 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
         c->scratch_bytes = o.end;
     }
     unsigned char* base = c->scratch;
-    const char* tenv = getenv("CSB200_SHARD_TIMING");           // debug: per-phase device times on stderr
-    const bool timing = tenv && tenv[0] == '1';
-    const size_t nev = (timing ? 4 : 2) * (size_t)k;
+    const char* tenv = getenv("CSB200_SHARD_TIMING");           // per-phase device times: 1 = also on stderr, 2 = silent
+    const bool timing = tenv && (tenv[0] == '1' || tenv[0] == '2');
+    const bool timing_print = tenv && tenv[0] == '1';
+    const size_t nev = (timing ? 4 : 2) * (size_t)k + 1;        // + one event after the last update
     while (c->ev_pool.size() < nev) {
         cudaEvent_t e = nullptr;
         CU_TRY(cudaEventCreate(&e));
@@ -548,6 +579,7 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
             if (e != cudaSuccess) { status = fail_cuda(e, "omp_update"); break; }
         }
         if (status) break;
+        cudaEventRecord(ev[nev - 1], st);
         std::vector<int> hsel(kcap);
         std::vector<double> hx(kcap);
         int hn = 0, hit = 0;
@@ -574,10 +606,18 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
         if (nnz_out) *nnz_out = hn;
         if (iters_out) *iters_out = hit;
         if (resnorm) *resnorm = hres;
-        if (corr_ms) {
+        {
             double tot = 0;
             for (int64_t it = 0; it < k; ++it) { float ms = 0; cudaEventElapsedTime(&ms, ev[2 * it], ev[2 * it + 1]); tot += ms; }
-            *corr_ms = tot;
+            if (corr_ms) *corr_ms = tot;
+            c->last_ms[0] = c->last_ms[2] = c->last_ms[3] = c->last_ms[4] = 0.0;
+            c->last_ms[1] = tot;
+            c->last_iters = k;
+            if (k > 0) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ev[0], ev[nev - 1]);
+                c->last_ms[0] = ms;         // first correlation pass enqueued -> last update finished
+            }
         }
         if (timing && k > 0) {
             double gemv = 0, exch = 0, upd = 0, gap = 0;
@@ -588,8 +628,10 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* c, const void* b, int64_
                 cudaEventElapsedTime(&ms, ev[2 * k + 2 * it], ev[2 * k + 2 * it + 1]); upd += ms;
                 if (it + 1 < k) { cudaEventElapsedTime(&ms, ev[2 * k + 2 * it + 1], ev[2 * (it + 1)]); gap += ms; }
             }
-            fprintf(stderr, "[csb200 shard rank %d/%d] per iteration (us): gemv %.1f  exchange[%s] %.1f  update %.1f  gap %.1f\n",
-                    c->rank, c->nranks, 1e3 * gemv / k, peer ? "peer-memory" : "local-best+allgather+pick", 1e3 * exch / k, 1e3 * upd / k, 1e3 * gap / k);
+            c->last_ms[2] = exch; c->last_ms[3] = upd; c->last_ms[4] = gap;
+            if (timing_print)
+                fprintf(stderr, "[csb200 shard rank %d/%d] per iteration (us): gemv %.1f  exchange[%s] %.1f  update %.1f  gap %.1f\n",
+                        c->rank, c->nranks, 1e3 * gemv / k, peer ? "peer-memory" : "local-best+allgather+pick", 1e3 * exch / k, 1e3 * upd / k, 1e3 * gap / k);
         }
     } while (0);
     cudaStreamSynchronize(st);

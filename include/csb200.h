@@ -193,6 +193,10 @@ int csb200_comm_unique_id(void* id_bytes);
 int csb200_comm_create(const void* id_bytes, int rank, int nranks, int device, csb200_comm** out);
 int csb200_comm_destroy(csb200_comm* comm);
 int csb200_comm_exchange_mode(const csb200_comm* comm);
+/* Device-time breakdown (CUDA events on the communicator's stream) of the last csb200_omp_sharded call on this rank:
+ * ms5 = {whole solve (first correlation pass enqueued -> last update finished), correlation passes, exchange, update,
+ * gaps}; the last three are recorded only while CSB200_SHARD_TIMING is 1 (also printed on stderr) or 2.  iters = k. */
+int csb200_comm_last_timing(csb200_comm* comm, double* ms5, int64_t* iters);
 int csb200_omp_sharded(csb200_dict* shard, csb200_comm* comm, const void* b, int64_t k, double eps,
                        int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters,
                        double* corr_ms);

@@ -59,6 +59,35 @@ def main():
             ok &= bool(np.allclose(x.nzval, x1.nzval, rtol=1e-12, atol=1e-13))     # sharded == unsharded GPU
             ok &= 7 in x.nzind.tolist() and (N - 3) not in x.nzind.tolist()
             print(f"dtype={np.dtype(dtype).name} world={world} ok={ok} exchange={info['exchange']} corr_ms={info['corr_ms']:.3f}", flush=True)
+    # the scaled-down twin of config 4 (8192 x 131072 FP32, k = 128) split over all ranks must give the
+    # single-rank result bit for bit (every c_j keeps its summation order under any column partition)
+    if os.environ.get("CSB200_SKIP_TWIN", "0") != "1":
+        M, N, k = 8192, 131072, 128
+        g = torch.Generator(device="cuda").manual_seed(100)          # same bytes on every rank
+        A_t = torch.empty(N, M, dtype=torch.float32, device="cuda")
+        for n0 in range(0, N, 16384):
+            blk = torch.randn(16384, M, dtype=torch.float32, device="cuda", generator=g)
+            blk /= blk.norm(dim=1, keepdim=True)
+            A_t[n0:n0 + 16384] = blk
+        idx = torch.randperm(N, device="cuda", generator=g)[:k]
+        b = A_t[idx].to(torch.float64).sum(dim=0).to(torch.float32).cpu().numpy()
+        lo, hi = cs.shard_range(N, world, rank)
+        A_loc = A_t[lo:hi].cpu().numpy().T
+        with cs.Dictionary(A_loc, device=local, n_offset=lo, n_total=N) as shard:
+            x, info = cs.omp_sharded(shard, comm, b, k)
+        del A_loc
+        if rank == 0:
+            A_full = A_t.cpu().numpy().T
+            solo = cs.ShardComm(cs.ShardComm.unique_id(), 0, 1, local)
+            with cs.Dictionary(A_full, device=local) as D:
+                x1, info1 = cs.omp_sharded(D, solo, b, k)
+            solo.close()
+            same = (info["order"].tolist() == info1["order"].tolist() and bool(np.array_equal(x.nzval, x1.nzval))
+                    and info["resnorm"] == info1["resnorm"])
+            ok &= same and sorted(idx.cpu().tolist()) == x.nzind.tolist()
+            print(f"twin 8192x131072 f32 k=128: {world} shards vs 1 shard bit-identical={same} exchange={info['exchange']} "
+                  f"corr_ms={info['corr_ms']:.2f} resnorm={info['resnorm']:.3e}", flush=True)
+        del A_t
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     comm.close()

@@ -902,6 +902,47 @@ def test_sharded_multi_gpu(cs):
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def _c4_twin(torch, dev, N=131072, M=8192, k=128, seed=100):
+    """SURVEY 8(d)'s scaled-down twin of BASELINE config 4: 8192 x 131072 FP32 (4 GiB), generated on the device by a
+    seeded generator and read back, so that the oracle sees the very bytes the GPU path does.  Planted: k atoms, +1."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    A_t = torch.empty(N, M, dtype=torch.float32, device=dev)
+    for n0 in range(0, N, 16384):
+        blk = torch.randn(16384, M, dtype=torch.float32, device=dev, generator=g)
+        blk /= blk.norm(dim=1, keepdim=True)
+        A_t[n0:n0 + 16384] = blk
+    idx = torch.randperm(N, device=dev, generator=g)[:k]
+    b = A_t[idx].to(torch.float64).sum(dim=0).to(torch.float32).cpu().numpy()
+    A = A_t.cpu().numpy().T                                   # (M, N) Fortran-ordered view
+    del A_t
+    torch.cuda.empty_cache()
+    return A, b, sorted(idx.cpu().tolist())
+
+
+@pytest.mark.slow
+def test_c4_scaled_down_twin_vs_oracle(cs, po):
+    """BASELINE config 4's scaled-down twin: single-signal omp, 8192 x 131072 FP32, k = 128, on one GPU
+    through the column-sharded entry point (world size 1, HBM-regime GEMV + cluster update) and through plain `omp`,
+    against the FP32 oracle on the same bytes: selection sequence exact, coefficients within 2e-5."""
+    import torch
+    k = 128
+    A, b, planted = _c4_twin(torch, torch.device("cuda", 0), k=k)
+    comm = cs.ShardComm(cs.ShardComm.unique_id(), 0, 1, 0)
+    try:
+        with cs.Dictionary(A) as D:
+            x, info = cs.omp_sharded(D, comm, b, k)
+            x1 = cs.omp(D, b, k)
+    finally:
+        comm.close()
+    t = po.Trace()
+    ref = po.omp(A, b, k, trace=t)
+    assert info["order"].tolist() == t.order(), ("selection sequence", min(t.margin))
+    assert x.nzind.tolist() == ref.nzind == planted == x1.nzind.tolist()
+    assert _close(x.nzval, ref.nzval, RTOL32) and _close(x1.nzval, ref.nzval, RTOL32)
+    assert np.array_equal(x.nzval, x1.nzval)                 # sharded entry point == unsharded GPU path, bit for bit
+    assert info["iters"] == k and abs(info["resnorm"] - t.resnorm[-1]) < 1e-4
+
+
 # ------------------------------------------------------------------ BASELINE configs 3 and 5 at their full dictionary shapes
 @pytest.mark.slow
 def test_c3_gomp_full_dictionary_shape(cs, po):

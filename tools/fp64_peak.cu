@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <algorithm>
 
@@ -105,7 +106,27 @@ static void time_it(F&& launch, double flop_per_launch, double* burst, double* s
     *sustained = flop_per_launch * n / (ms * 1e-3) / 1e12;
 }
 
+// --quick [device]: only the register-tiled DMMA measurement that defines the roofline denominator (about half a
+// second of GPU time) -- bench.py runs it inside its own clock-sampling window so that numerator and denominator come
+// from the same box, lease and clocks.  Prints {"peak_tflops": sustained, "burst_tflops": ..., "flop_per_clk_per_sm": ...}.
+static int quick(int dev) {
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
+    const int sms = prop.multiProcessorCount, iters = 4096, threads = 256;
+    double* out; CK(cudaMalloc(&out, (size_t)sms * 1024 * sizeof(double)));
+    long long* cyc; CK(cudaMalloc(&cyc, 8));
+    const double flop = (double)sms * (threads / 32) * (double)iters * 8 * 4 * 512.0;
+    double bu, su;
+    time_it([&] { dmma_tile_kernel<8, 4><<<sms, threads>>>(out, cyc, iters, 1.0); }, flop, &bu, &su, 0.4);
+    long long h; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    const double fpc = (double)(threads / 32) * iters * 8 * 4 * 512.0 / (double)h;
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"device\": %d, \"peak_tflops\": %.3f, \"burst_tflops\": %.3f, \"flop_per_clk_per_sm\": %.1f, "
+           "\"kernel\": \"DMMA.8x8x4 register-tiled 8x4, 256 threads x 1 CTA/SM, sustained 0.4 s\"}\n", prop.name, sms, dev, su, bu, fpc);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "--quick")) return quick(argc > 2 ? atoi(argv[2]) : 0);
     double sustain_s = argc > 1 ? atof(argv[1]) : 3.0;
     int dev = 0; CK(cudaSetDevice(dev));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, dev));
