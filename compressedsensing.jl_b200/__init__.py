@@ -69,6 +69,9 @@ def _load() -> ctypes.CDLL:
         "csb200_dict_create": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, POINTER(c_void_p)]),
         "csb200_dict_create_shard": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_int64,
                                              POINTER(c_void_p)]),
+        "csb200_dict_create_multi": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(c_int), c_int,
+                                             POINTER(c_void_p)]),
+        "csb200_dict_devices": (c_int, [c_void_p, POINTER(c_int), c_int]),
         "csb200_dict_destroy": (c_int, [c_void_p]),
         "csb200_dict_trim": (c_int, [c_void_p]),
         "csb200_dict_shape": (c_int, [c_void_p, i64p, i64p, POINTER(c_int), POINTER(c_int)]),
@@ -119,7 +122,7 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 EXPORTED_SYMBOLS = [
     "csb200_version", "csb200_strerror", "csb200_last_error", "csb200_device_count", "csb200_dict_create",
-    "csb200_dict_create_shard", "csb200_dict_destroy", "csb200_dict_trim", "csb200_dict_shape", "csb200_batch_create",
+    "csb200_dict_create_shard", "csb200_dict_create_multi", "csb200_dict_devices", "csb200_dict_destroy", "csb200_dict_trim", "csb200_dict_shape", "csb200_batch_create",
     "csb200_batch_destroy", "csb200_batch_upload", "csb200_batch_upload_device", "csb200_batch_omp",
     "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
     "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp",
@@ -189,20 +192,33 @@ def _as_matrix(A) -> np.ndarray:
 
 
 class Dictionary:
-    """A dictionary resident on one B200 (`csb200_dict`).  Reuse it across solves to keep A in HBM/L2."""
+    """A dictionary resident in HBM (`csb200_dict`).  Reuse it across solves to keep A in HBM/L2.
 
-    def __init__(self, A, device: int = 0, n_offset: int = 0, n_total: Optional[int] = None):
+    `devices=[...]` replicates it onto several GPUs (`csb200_dict_create_multi`): the one-shot calls (`omp(D, B, k)`
+    etc.) then split the columns of B over those GPUs inside the library, with results bit-identical to one GPU."""
+
+    def __init__(self, A, device: int = 0, n_offset: int = 0, n_total: Optional[int] = None,
+                 devices: Optional[Sequence[int]] = None):
         A = _as_matrix(A)
         self.M, self.N = int(A.shape[0]), int(A.shape[1])
         self.dtype = A.dtype
-        self.device = device
         self.n_offset = int(n_offset)
         self.n_total = int(self.N if n_total is None else n_total)
         h = c_void_p()
         lda = A.strides[1] // A.itemsize if self.N > 1 else self.M
-        _check(lib.csb200_dict_create_shard(A.ctypes.data, self.M, self.N, max(lda, self.M),
-                                            F32 if A.dtype == np.float32 else F64, device, self.n_offset,
-                                            self.n_total, byref(h)))
+        dt = F32 if A.dtype == np.float32 else F64
+        if devices is not None:
+            devs = [int(d) for d in devices]
+            if not devs or n_offset or self.n_total != self.N:
+                raise ValueError("devices= needs at least one device and an unsharded dictionary")
+            arr = (c_int * len(devs))(*devs)
+            _check(lib.csb200_dict_create_multi(A.ctypes.data, self.M, self.N, max(lda, self.M), dt, arr, len(devs),
+                                                byref(h)))
+            self.device, self.devices = devs[0], devs
+        else:
+            _check(lib.csb200_dict_create_shard(A.ctypes.data, self.M, self.N, max(lda, self.M), dt, device,
+                                                self.n_offset, self.n_total, byref(h)))
+            self.device, self.devices = device, [device]
         self._h = h
 
     def close(self) -> None:
@@ -346,6 +362,8 @@ def _eps_of(dtype) -> float:
 def _dictionary(A, device):
     if isinstance(A, Dictionary):
         return A, False
+    if isinstance(device, (list, tuple, range)):          # omp(A, B, k, device=range(8)): replicate for this call
+        return Dictionary(A, devices=list(device)), True
     return Dictionary(A, device=device), True
 
 

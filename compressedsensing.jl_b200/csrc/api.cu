@@ -15,6 +15,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -102,6 +103,9 @@ struct csb200_dict {
     std::mutex twin_mu;
     bool twin_failed = false;
     bool gram_failed = false;
+    // multi-device handle (csb200_dict_create_multi): this object is the replica of worker 0; `extra` holds the
+    // replicas of workers 1..n-1 (owned).  The one-shot entry points fan a batch out over all of them.
+    std::vector<csb200_dict*> extra;
     size_t esize() const { return dtype == CSB200_F32 ? 4 : 8; }
 };
 
@@ -621,11 +625,70 @@ int csb200_dict_create(const void* A, int64_t M, int64_t N, int64_t lda, int dty
     return csb200_dict_create_shard(A, M, N, lda, dtype, device, 0, N, out);
 }
 
+// A replica of `src` on `device` (dictionary bytes copied device to device -- NVLink when the GPUs are peers --
+// in the padded layout, so no second NaN scan or 2-D copy is needed).
+static int clone_dict_to(const csb200_dict* src, int device, csb200_dict** out) {
+    *out = nullptr;
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return CSB200_ERR_INVALID_ARG;
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { g_last_error = "replica device is not an sm_100 GPU"; return CSB200_ERR_UNSUPPORTED_ARCH; }
+    csb200_dict* d = new (std::nothrow) csb200_dict;
+    if (!d) return CSB200_ERR_OOM;
+    d->device = device; d->dtype = src->dtype; d->M = src->M; d->N = src->N; d->ld = src->ld;
+    d->n_offset = src->n_offset; d->n_total = src->n_total; d->num_sms = prop.multiProcessorCount;
+    const size_t bytes = (size_t)d->ld * d->N * d->esize();
+    cudaError_t e = cudaMalloc(&d->dA, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyPeer(d->dA, device, src->dA, src->device, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    int rc = e == cudaSuccess ? CSB200_OK : fail_cuda(e, "replicating the dictionary");
+    if (!rc && d->dtype == CSB200_F64) {
+        rc = make_operand_map(&d->mapA, d->dA, d->ld, d->N);
+        if (!rc) {
+            d->has_map = true;
+            e = corr_gemm_f64_setup();
+            if (e != cudaSuccess) rc = fail_cuda(e, "cudaFuncSetAttribute(corr_gemm_f64)");
+        }
+    }
+    if (rc) { cudaFree(d->dA); delete d; return rc; }
+    *out = d;
+    return CSB200_OK;
+}
+
+int csb200_dict_create_multi(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, const int* devices, int ndev,
+                             csb200_dict** out) {
+    if (!out || !devices || ndev < 1 || ndev > 64) return CSB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    csb200_dict* d = nullptr;
+    int rc = csb200_dict_create(A, M, N, lda, dtype, devices[0], &d);
+    if (rc) return rc;
+    for (int i = 1; i < ndev; ++i) {
+        csb200_dict* r = nullptr;
+        rc = clone_dict_to(d, devices[i], &r);
+        if (rc) { csb200_dict_destroy(d); return rc; }
+        d->extra.push_back(r);
+    }
+    cudaSetDevice(d->device);
+    *out = d;
+    return CSB200_OK;
+}
+
+int csb200_dict_devices(const csb200_dict* d, int* devices, int capacity) {
+    if (!d) return CSB200_ERR_INVALID_ARG;
+    const int n = 1 + (int)d->extra.size();
+    for (int i = 0; i < n && i < capacity && devices; ++i) devices[i] = i == 0 ? d->device : d->extra[i - 1]->device;
+    return n;
+}
+
 int csb200_dict_trim(csb200_dict* d) {
     if (!d) return CSB200_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(d->mu);
     if (d->workspace) { csb200_batch_destroy(d->workspace); d->workspace = nullptr; }
     for (auto& w : d->pipe_ws) if (w) { csb200_batch_destroy(w); w = nullptr; }
+    for (csb200_dict* r : d->extra) csb200_dict_trim(r);
     return CSB200_OK;
 }
 
@@ -635,6 +698,8 @@ int csb200_dict_destroy(csb200_dict* d) {
     if (d->workspace) csb200_batch_destroy(d->workspace);
     for (auto& w : d->pipe_ws) if (w) csb200_batch_destroy(w);
     if (d->twin64) csb200_dict_destroy(d->twin64);
+    for (csb200_dict* r : d->extra) csb200_dict_destroy(r);
+    cudaSetDevice(d->device);
     cudaFree(d->gram);
     cudaFree(d->dA);
     delete d;
@@ -1292,10 +1357,71 @@ static int64_t support_cap(const csb200_dict* d, int64_t k) {
     return d->n_total < cap ? d->n_total : cap;
 }
 
+}  // extern "C" (the fan-out helpers are templates)
+
+// ---- multi-device fan-out ------------------------------------------------------------------------
+// A handle made by csb200_dict_create_multi holds one replica of the dictionary per worker.  A one-shot call splits its
+// signals into contiguous ranges, one per worker, and runs the single-device path of each range on its own host thread
+// (own device, own workspace, own stream); outputs are per-signal arrays, so the workers write disjoint slices of the
+// caller's buffers.  Signals are independent (src/matchingpursuit.jl:73-82 keeps all state per call), so there is no
+// data-path communication.  A worker gets at least FANOUT_MIN_SIGNALS signals: smaller ranges would fall below the
+// batched (DMMA) path's threshold and could round differently from the single-device solve of the same batch.
+constexpr int64_t FANOUT_MIN_SIGNALS = 256;
+
+static int fanout_workers(const csb200_dict* d, int64_t nsig) {
+    if (d->extra.empty()) return 1;
+    int64_t w = nsig / FANOUT_MIN_SIGNALS;
+    const int64_t have = 1 + (int64_t)d->extra.size();
+    if (w > have) w = have;
+    return w < 1 ? 1 : (int)w;
+}
+
+// call(replica, first signal, signal count) runs the single-device solve of that range and returns its status
+template <class Call>
+static int fan_out(csb200_dict* d, int64_t nsig, int workers, Call call) {
+    std::vector<int> rc(workers, CSB200_OK);
+    std::vector<std::string> err(workers);
+    std::vector<std::thread> th;
+    const int64_t base = nsig / workers, extra = nsig % workers;
+    auto run = [&](int w) {
+        const int64_t s0 = w * base + (w < extra ? w : extra), ns = base + (w < extra ? 1 : 0);
+        csb200_dict* rep = w == 0 ? d : d->extra[w - 1];
+        rc[w] = call(rep, s0, ns);
+        if (rc[w]) err[w] = g_last_error;          // g_last_error is thread-local: carry the text to the caller's thread
+    };
+    for (int w = 1; w < workers; ++w) th.emplace_back(run, w);
+    run(0);
+    for (auto& t : th) t.join();
+    cudaSetDevice(d->device);
+    for (int w = 0; w < workers; ++w)
+        if (rc[w]) { g_last_error = err[w]; return rc[w]; }
+    return CSB200_OK;
+}
+template <class T> static T* off(T* p, int64_t n) { return p ? p + n : nullptr; }
+static const void* sig_off(const csb200_dict* d, const void* Bmat, int64_t ldb, int64_t s0) {
+    return Bmat ? (const char*)Bmat + (size_t)s0 * ldb * d->esize() : nullptr;
+}
+
+extern "C" {
+
+static int omp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double eps,
+                      int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+
 int csb200_omp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double eps,
                int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     if (!d || k < 0) return CSB200_ERR_INVALID_ARG;
     if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    const int workers = fanout_workers(d, nsig);
+    if (workers > 1 && Bmat && ldb >= d->M)
+        return fan_out(d, nsig, workers, [&](csb200_dict* rep, int64_t s0, int64_t ns) {
+            return omp_single(rep, sig_off(d, Bmat, ldb, s0), ldb, ns, k, eps, off(sel_idx, s0 * k), off(coef, s0 * k),
+                              off(nnz, s0), off(resnorm, s0), off(iters, s0));
+        });
+    return omp_single(d, Bmat, ldb, nsig, k, eps, sel_idx, coef, nnz, resnorm, iters);
+}
+
+static int omp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double eps,
+                      int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     std::lock_guard<std::mutex> lk(d->mu);
     if (Bmat && use_pipeline(d, nsig) && ldb >= d->M)
         return one_shot_pipelined(d, Bmat, ldb, nsig, support_cap(d, k), k,
@@ -1309,10 +1435,24 @@ int csb200_omp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int6
     return rc;
 }
 
+static int gomp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t l, int64_t k, double eps,
+                       int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+
 int csb200_gomp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t l, int64_t k, double eps,
                 int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     if (!d || k < 0 || l < 1) return CSB200_ERR_INVALID_ARG;
     if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
+    const int workers = fanout_workers(d, nsig);
+    if (workers > 1 && Bmat && ldb >= d->M)
+        return fan_out(d, nsig, workers, [&](csb200_dict* rep, int64_t s0, int64_t ns) {
+            return gomp_single(rep, sig_off(d, Bmat, ldb, s0), ldb, ns, l, k, eps, off(sel_idx, s0 * k), off(coef, s0 * k),
+                               off(nnz, s0), off(resnorm, s0), off(iters, s0));
+        });
+    return gomp_single(d, Bmat, ldb, nsig, l, k, eps, sel_idx, coef, nnz, resnorm, iters);
+}
+
+static int gomp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t l, int64_t k, double eps,
+                       int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     std::lock_guard<std::mutex> lk(d->mu);
     if (Bmat && use_pipeline(d, nsig) && ldb >= d->M)
         return one_shot_pipelined(d, Bmat, ldb, nsig, support_cap(d, k), k,
@@ -1326,9 +1466,23 @@ int csb200_gomp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int
     return rc;
 }
 
+static int fr_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double max_eps, double min_delta,
+                     int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+
 int csb200_fr(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double max_eps, double min_delta,
               int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     if (!d || k < 0) return CSB200_ERR_INVALID_ARG;
+    const int workers = fanout_workers(d, nsig);
+    if (workers > 1 && Bmat && ldb >= d->M)
+        return fan_out(d, nsig, workers, [&](csb200_dict* rep, int64_t s0, int64_t ns) {
+            return fr_single(rep, sig_off(d, Bmat, ldb, s0), ldb, ns, k, max_eps, min_delta, off(sel_idx, s0 * k),
+                             off(coef, s0 * k), off(nnz, s0), off(resnorm, s0), off(iters, s0));
+        });
+    return fr_single(d, Bmat, ldb, nsig, k, max_eps, min_delta, sel_idx, coef, nnz, resnorm, iters);
+}
+
+static int fr_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double max_eps, double min_delta,
+                     int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
     int64_t cap = support_cap(d, k);
@@ -1343,9 +1497,23 @@ int csb200_fr(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64
     return rc;
 }
 
+static int sp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double delta, int64_t maxiter,
+                     int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters);
+
 int csb200_sp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double delta, int64_t maxiter,
               int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     if (!d || k < 1 || maxiter < 0) return CSB200_ERR_INVALID_ARG;
+    const int workers = fanout_workers(d, nsig);
+    if (workers > 1 && Bmat && ldb >= d->M)
+        return fan_out(d, nsig, workers, [&](csb200_dict* rep, int64_t s0, int64_t ns) {
+            return sp_single(rep, sig_off(d, Bmat, ldb, s0), ldb, ns, k, delta, maxiter, off(sel_idx, s0 * k),
+                             off(coef, s0 * k), off(nnz, s0), off(resnorm, s0), off(iters, s0));
+        });
+    return sp_single(d, Bmat, ldb, nsig, k, delta, maxiter, sel_idx, coef, nnz, resnorm, iters);
+}
+
+static int sp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, double delta, int64_t maxiter,
+                     int64_t* sel_idx, double* coef, int64_t* nnz, double* resnorm, int64_t* iters) {
     std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, 2 * k, &b, /*allow_lazy=*/false);
@@ -1355,9 +1523,23 @@ int csb200_sp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64
     return rc;
 }
 
+static int oblivious_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, int64_t* sel_idx,
+                            double* coef, int64_t* nnz, double* resnorm);
+
 int csb200_oblivious(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, int64_t* sel_idx,
                      double* coef, int64_t* nnz, double* resnorm) {
     if (!d || k < 1) return CSB200_ERR_INVALID_ARG;
+    const int workers = fanout_workers(d, nsig);
+    if (workers > 1 && Bmat && ldb >= d->M)
+        return fan_out(d, nsig, workers, [&](csb200_dict* rep, int64_t s0, int64_t ns) {
+            return oblivious_single(rep, sig_off(d, Bmat, ldb, s0), ldb, ns, k, off(sel_idx, s0 * k), off(coef, s0 * k),
+                                    off(nnz, s0), off(resnorm, s0));
+        });
+    return oblivious_single(d, Bmat, ldb, nsig, k, sel_idx, coef, nnz, resnorm);
+}
+
+static int oblivious_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t k, int64_t* sel_idx,
+                            double* coef, int64_t* nnz, double* resnorm) {
     std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, k, &b, /*allow_lazy=*/false);
@@ -1367,10 +1549,27 @@ int csb200_oblivious(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig
     return rc;
 }
 
+static int mp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k, const int64_t* x0_idx,
+                     const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride, int64_t* sel_idx, double* coef,
+                     double* resnorm);
+
 int csb200_mp(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k, const int64_t* x0_idx,
               const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride, int64_t* sel_idx, double* coef,
               double* resnorm) {
     if (!d || iters_k < 0) return CSB200_ERR_INVALID_ARG;
+    const int workers = fanout_workers(d, nsig);
+    if (workers > 1 && Bmat && ldb >= d->M)
+        return fan_out(d, nsig, workers, [&](csb200_dict* rep, int64_t s0, int64_t ns) {
+            return mp_single(rep, sig_off(d, Bmat, ldb, s0), ldb, ns, iters_k, off(x0_idx, s0 * x0_stride),
+                             off(x0_val, s0 * x0_stride), off(x0_nnz, s0), x0_stride, off(sel_idx, s0 * iters_k),
+                             off(coef, s0 * iters_k), off(resnorm, s0));
+        });
+    return mp_single(d, Bmat, ldb, nsig, iters_k, x0_idx, x0_val, x0_nnz, x0_stride, sel_idx, coef, resnorm);
+}
+
+static int mp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t iters_k, const int64_t* x0_idx,
+                     const double* x0_val, const int64_t* x0_nnz, int64_t x0_stride, int64_t* sel_idx, double* coef,
+                     double* resnorm) {
     std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, iters_k, &b);

@@ -70,6 +70,17 @@ int csb200_dict_create(const void* A, int64_t M, int64_t N, int64_t lda, int dty
                        csb200_dict** out);
 int csb200_dict_create_shard(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, int device,
                              int64_t n_offset, int64_t n_total, csb200_dict** out);
+/* Multi-GPU handle (SURVEY.md 8b "Threading": fan-out is library-internal and invisible to the caller).  The
+ * dictionary is uploaded to devices[0] and replicated device-to-device onto devices[1..ndev-1] (an entry may repeat:
+ * each entry is one worker with its own replica, workspace and stream).  The one-shot entry points below
+ * (csb200_omp / gomp / mp / fr / sp / oblivious) split the signals of a call into contiguous ranges, one per worker
+ * (at least 256 signals each; fewer signals use fewer workers), and solve them concurrently on internal host
+ * threads; signals are independent, so there is no data-path communication and results are bit-identical to the
+ * single-device call.  Everything else (batch API, dictionary analysis) runs on devices[0].
+ * csb200_dict_devices: number of workers; fills devices[0..min(n, capacity)). */
+int csb200_dict_create_multi(const void* A, int64_t M, int64_t N, int64_t lda, int dtype, const int* devices, int ndev,
+                             csb200_dict** out);
+int csb200_dict_devices(const csb200_dict* dict, int* devices, int capacity);
 int csb200_dict_destroy(csb200_dict* dict);
 /* Release the device workspace the one-shot calls (csb200_omp/gomp/mp) keep on the handle for reuse. */
 int csb200_dict_trim(csb200_dict* dict);

@@ -406,6 +406,35 @@ def test_concurrent_host_threads(cs, po):
         D.close()
 
 
+def test_multi_device_handle_fans_out_bit_identically(cs, po):
+    """csb200_dict_create_multi (SURVEY 8b "Threading": fan-out is library-internal): ONE csb200_omp / gomp / mp call
+    on a handle with several workers -- all visible GPUs, and at least three workers (entries may repeat, which is
+    how the driver's single-GPU box exercises the fan-out) -- must equal the single-device call bit for bit."""
+    rng = np.random.default_rng(404)
+    M, N, k, B = 96, 1024, 6, 1500
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, B, noise=1e-3)
+    ndev = cs.device_count()
+    devices = list(range(ndev)) if ndev >= 3 else [i % ndev for i in range(3)]
+    with cs.Dictionary(A) as D1, cs.Dictionary(A, devices=devices) as Dn:
+        assert Dn.devices == devices
+        for call in (lambda D: cs.omp(D, Bm, k), lambda D: cs.gomp(D, Bm, 2, k), lambda D: cs.mp(D, Bm, 2 * k),
+                     lambda D: cs.fr(D, Bm, 0.0, 0.0, k), lambda D: cs.sp(D, Bm, k), lambda D: cs.oblivious(D, Bm, k)):
+            one, many = call(D1), call(Dn)
+            assert len(one) == len(many) == B
+            for s in range(B):
+                assert np.array_equal(one[s].nzind, many[s].nzind), s
+                assert np.array_equal(one[s].nzval, many[s].nzval), s
+        x = cs.omp(Dn, Bm[:, :10], k)                        # below the fan-out threshold: one worker
+        assert all(np.array_equal(x[s].nzind, cs.omp(D1, Bm[:, s], k).nzind) for s in range(10))
+    bad = np.array(Bm, copy=True)
+    bad[3, B - 1] = np.nan                                   # the error of one worker reaches the caller
+    with cs.Dictionary(A, devices=devices) as Dn:
+        with pytest.raises(cs.CSB200Error) as ei:
+            cs.omp(Dn, bad, k)
+        assert ei.value.status == -3
+
+
 def test_pipelined_one_shot_matches_single_upload(cs, po, monkeypatch):
     """Host batches of >= 32 768 signals are cut into whole-wave chunks whose uploads / downloads overlap the solves
     (csb200_omp / _gomp / _fr one-shot calls).  Results must be bit-identical to the single-upload path, ragged last
