@@ -92,6 +92,7 @@ struct csb200_dict {
     CUtensorMap mapA;
     bool has_map = false;
     int num_sms = 148;
+    bool coop = false;                   // device supports cooperative launches (whole-solve kernel of solve_persist.cu)
     std::mutex mu;
     std::mutex gram_mu;
     csb200_batch* workspace = nullptr;   // reused by the one-shot entry points (csb200_omp/gomp/mp)
@@ -136,6 +137,8 @@ struct csb200_batch {
     double* qnew = nullptr;     // [cap_sig][ld] newest orthonormal direction per signal
     double* cn2 = nullptr;      // [N] squared column norms
     int* ndone = nullptr;       // subspace pursuit: number of signals whose stopping test has fired
+    unsigned char* persist_scratch = nullptr;   // whole-solve cooperative kernel: candidates + sync words
+    size_t persist_bytes = 0;
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -176,6 +179,7 @@ int begin_solve_fwd(csb200_batch* b);
 void free_batch_mem(csb200_batch* b) {
     cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->state_blk);
     cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->stage32); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2); cudaFree(b->ndone);
+    cudaFree(b->persist_scratch);
     if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
@@ -312,6 +316,59 @@ int run_small_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double eps,
     q.x0_idx = x0_idx; q.x0_val = x0_val; q.x0_nnz = x0_nnz; q.x0_stride = x0_stride;
     cudaError_t e = launch_small_solve(state_args(b, 1, 1, eps, 0), q, b->dict->dtype == CSB200_F32, b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "small_solve");
+    b->other_launches++;
+    return CSB200_OK;
+}
+
+// Few signals (<= PERSIST_MAX_SIGNALS) on a dictionary up to about the L2 size: the whole omp / mp solve in one
+// cooperative launch (solve_persist.cu).  CSB200_PERSIST=0 disables it, =1 prefers it even where the small-dictionary
+// kernel is eligible too; an explicit CSB200_SMALL_SOLVE (tests select the path they exercise) takes precedence.
+constexpr size_t PERSIST_MAX_DICT_BYTES = (size_t)96 << 20;
+bool use_persist_solve(const csb200_batch* b, int mode) {
+    const csb200_dict* d = b->dict;
+    if (mode != 0 && mode != 2) return false;
+    const char* env = getenv("CSB200_PERSIST");
+    if (env && env[0] == '0') return false;
+    const bool forced = env && env[0] == '1';
+    if (!forced && getenv("CSB200_SMALL_SOLVE")) return false;
+    if (b->corr_impl_env != IMPL_AUTO || b->profile || b->defer_finish || !d->coop) return false;
+    for (const char* hook : {"CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM"})
+        if (getenv(hook)) return false;
+    if (b->nsig < 1 || b->nsig > PERSIST_MAX_SIGNALS || d->n_total != d->N) return false;
+    if ((size_t)d->ld * d->N * d->esize() > PERSIST_MAX_DICT_BYTES) return false;
+    return persist_plan((int)d->ld, (int)d->N, (int)b->kcap, (int)b->nsig, d->dtype == CSB200_F32, d->num_sms, nullptr, nullptr);
+}
+
+int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
+    csb200_dict* d = b->dict;
+    PersistArgs q;
+    memset(&q, 0, sizeof q);
+    size_t smem = 0;
+    if (!persist_plan((int)d->ld, (int)d->N, (int)b->kcap, (int)b->nsig, d->dtype == CSB200_F32, d->num_sms, &q, &smem)) {
+        g_last_error = "whole-solve kernel: shape does not fit";
+        return CSB200_ERR_UNSUPPORTED;
+    }
+    const size_t cand = (size_t)b->nsig * q.workers;
+    const size_t off_idx = (cand * sizeof(double) + 15) / 16 * 16, off_sync = (off_idx + cand * sizeof(int) + 15) / 16 * 16;
+    const size_t need = off_sync + PERSIST_SYNC_WORDS * sizeof(unsigned);
+    if (need > b->persist_bytes) {
+        cudaFree(b->persist_scratch);
+        b->persist_scratch = nullptr; b->persist_bytes = 0;
+        CU_TRY(cudaMalloc(&b->persist_scratch, need));
+        b->persist_bytes = need;
+    }
+    int rc = begin_solve_fwd(b);
+    if (rc) return rc;
+    q.A = d->dA; q.B = b->dB; q.R = b->dR;
+    q.M = (int)d->M; q.ld = (int)d->ld; q.N = (int)d->N; q.ns = (int)b->nsig; q.kcap = (int)b->kcap; q.idx_offset = (int)d->n_offset;
+    q.mode = mode; q.k = (int)k; q.stride = (int)b->kcap; q.eps = eps;
+    q.cand_val = reinterpret_cast<double*>(b->persist_scratch);
+    q.cand_idx = reinterpret_cast<int*>(b->persist_scratch + off_idx);
+    q.sync = reinterpret_cast<unsigned*>(b->persist_scratch + off_sync);
+    q.nnz = b->nnz; q.sel = b->sel; q.x = b->x; q.resnorm = b->resnorm; q.iters = b->iters; q.done = b->done; q.flags = b->flags;
+    CU_TRY(cudaMemsetAsync(q.sync, 0, PERSIST_SYNC_WORDS * sizeof(unsigned), b->stream));
+    cudaError_t e = launch_persist_solve(q, d->dtype == CSB200_F32, smem, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "persist_solve");
     b->other_launches++;
     return CSB200_OK;
 }
@@ -523,7 +580,7 @@ int after_upload(csb200_batch* b, int64_t nsig, bool allow_lazy) {
     b->nsig = nsig;
     b->has_map = false;
     b->cur_P = 0;
-    if (allow_lazy && use_small_solve(b)) {
+    if (allow_lazy && (use_small_solve(b) || use_persist_solve(b, 0))) {
         // one-shot call on a small dictionary: the solve kernel itself checks b for NaN/Inf and sets r = b,
         // so the upload needs no scan, no reset and no synchronisation
         b->lazy_input_check = true;
@@ -593,6 +650,7 @@ int csb200_dict_create_shard(const void* A, int64_t M, int64_t N, int64_t lda, i
     if (!d) return CSB200_ERR_OOM;
     d->device = device; d->dtype = dtype; d->M = M; d->N = N; d->ld = round_up(M, ROW_ALIGN);
     d->n_offset = n_offset; d->n_total = n_total; d->num_sms = prop.multiProcessorCount;
+    d->coop = prop.cooperativeLaunch != 0;
     const size_t es = d->esize();
     const size_t bytes = (size_t)d->ld * N * es;
     cudaError_t e = cudaMalloc(&d->dA, bytes);
@@ -640,6 +698,7 @@ static int clone_dict_to(const csb200_dict* src, int device, csb200_dict** out) 
     if (!d) return CSB200_ERR_OOM;
     d->device = device; d->dtype = src->dtype; d->M = src->M; d->N = src->N; d->ld = src->ld;
     d->n_offset = src->n_offset; d->n_total = src->n_total; d->num_sms = prop.multiProcessorCount;
+    d->coop = prop.cooperativeLaunch != 0;
     const size_t bytes = (size_t)d->ld * d->N * d->esize();
     cudaError_t e = cudaMalloc(&d->dA, bytes);
     if (e == cudaSuccess) e = cudaMemcpyPeer(d->dA, device, src->dA, src->device, bytes);
@@ -729,7 +788,7 @@ static csb200_dict* promoted_dict(csb200_dict* d) {
     csb200_dict* t = new (std::nothrow) csb200_dict;
     if (!t) return nullptr;
     t->device = d->device; t->dtype = CSB200_F64; t->M = d->M; t->N = d->N; t->ld = d->ld;
-    t->n_offset = 0; t->n_total = d->N; t->num_sms = d->num_sms;
+    t->n_offset = 0; t->n_total = d->N; t->num_sms = d->num_sms; t->coop = d->coop;
     cudaError_t e = cudaMalloc(&t->dA, bytes);
     if (e == cudaSuccess) e = launch_widen_f32(static_cast<const float*>(d->dA), d->ld, static_cast<double*>(t->dA), t->ld, (int)d->ld, d->N, nullptr);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -864,6 +923,10 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
+    if (use_persist_solve(b, 0) && !(use_small_solve(b) && getenv("CSB200_SMALL_SOLVE"))) {
+        if ((rc = run_persist_solve(b, 0, k, eps))) return rc;
+        return finish(b, true);
+    }
     if (use_small_solve(b)) {
         if ((rc = run_small_solve(b, 0, k, 1, eps, nullptr, nullptr, nullptr, 0))) return rc;
         return finish(b, true);
@@ -1094,6 +1157,10 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
         CU_TRY(cudaMemcpy(x0.val, x0_val, n * sizeof(double), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(x0.nnz, hn.data(), b->nsig * sizeof(int), cudaMemcpyHostToDevice));
     }
+    if (!warm && use_persist_solve(b, 2)) {
+        if ((rc = run_persist_solve(b, 2, iters, 0.0))) return rc;
+        return finish(b, true);
+    }
     if (use_small_solve(b)) {
         if ((rc = run_small_solve(b, 2, iters, 1, 0.0, x0.idx, x0.val, x0.nnz, (int)x0_stride))) return rc;
         return finish(b, true);
@@ -1159,6 +1226,8 @@ int csb200_batch_download(csb200_batch* b, int64_t stride, int64_t* sel_idx, dou
     if (b->lazy_input_check) {
         for (size_t s = 0; s < ns; ++s) if (hfl[s] & 4) return CSB200_ERR_NONFINITE_INPUT;
     }
+    for (size_t s = 0; s < ns; ++s)
+        if (hfl[s] & 8) { g_last_error = "whole-solve kernel: a CTA timed out waiting for its peers"; return CSB200_ERR_CUDA; }
     return convert_results(ns, kc, stride, hn, hs, hit, hx, hres, sel_idx, coef, nnz, resnorm, iters);
 }
 

@@ -99,6 +99,27 @@ struct SmallSolveArgs {
 };
 bool small_solve_eligible(int ld, int N, int kcap, int nsig, bool f32);
 cudaError_t launch_small_solve(const StateArgs& a, const SmallSolveArgs& q, bool f32, cudaStream_t st);
+// Whole-solve cooperative kernel for 1..PERSIST_MAX_SIGNALS signals (solve_persist.cu): mode 0 omp, 2 mp.
+constexpr int PERSIST_MAX_SIGNALS = 8;
+struct PersistArgs {
+    const void* A;        // dictionary, ld x N
+    const void* B;        // signals,   ld x ns
+    void* R;              // residuals, ld x ns (rewritten every update!, read by the workers)
+    int M, ld, N, ns, kcap, idx_offset;
+    int mode, k, stride;  // stride: slots per signal in sel / x
+    double eps;
+    int workers;          // GEMV CTAs; grid = ns + workers
+    int wcache;           // dictionary columns a worker keeps in shared memory for the whole solve
+    int ucache;           // active-atom columns an updater keeps in shared memory
+    double* cand_val;     // [ns][workers] per-worker arg-max of |c|
+    int* cand_idx;        // [ns][workers] its global atom index (-1: none)
+    unsigned* sync;       // [0] arrive counter, [1 .. 1 + PERSIST_MAX_SIGNALS) per-signal flags, then the error word; zeroed before launch
+    int* nnz; int* sel; double* x; double* resnorm; int* iters; int* done; int* flags;
+};
+constexpr size_t PERSIST_SYNC_WORDS = 2 + PERSIST_MAX_SIGNALS;
+// fills workers / wcache / ucache and the dynamic shared memory size; false: the shape does not fit this kernel
+bool persist_plan(int ld, int N, int kcap, int ns, bool f32, int num_sms, PersistArgs* out, size_t* smem_out);
+cudaError_t launch_persist_solve(const PersistArgs& a, bool f32, size_t smem, cudaStream_t st);
 size_t omp_update_smem_bytes(int ld, int kcap);            // dynamic shared memory the kernels above need
 bool omp_update_uses_block(int ld, int kcap, int take);    // gomp: the block-append variant (which can read dense |A'r|) runs
 size_t omp_update_cluster_smem_bytes(int ld, int kcap);

@@ -40,17 +40,26 @@ end
 
 # ---------------------------------------------------------------------------------------------
 # Dictionary handle: A stays resident in HBM; reuse it across calls.
+# `devices = 0:7` replicates it onto several GPUs (csb200_dict_create_multi): `omp(D, B, k)` etc. then split the
+# columns of B over those GPUs inside the library (internal host threads, no communication, bit-identical results).
 mutable struct Dictionary{T<:Union{Float32,Float64}}
     handle::Ptr{Cvoid}
     M::Int
     N::Int
-    function Dictionary(A::StridedMatrix{T}; device::Integer = 0) where {T<:Union{Float32,Float64}}
+    function Dictionary(A::StridedMatrix{T}; device::Integer = 0, devices = nothing) where {T<:Union{Float32,Float64}}
         stride(A, 1) == 1 || (A = Matrix(A))
         M, N = size(A)
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        GC.@preserve A check(ccall((:csb200_dict_create, libcsb200), Cint,
-            (Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Ref{Ptr{Cvoid}}),
-            pointer(A), M, N, max(stride(A, 2), M), dtype_code(T), device, h))
+        if devices === nothing
+            GC.@preserve A check(ccall((:csb200_dict_create, libcsb200), Cint,
+                (Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Ref{Ptr{Cvoid}}),
+                pointer(A), M, N, max(stride(A, 2), M), dtype_code(T), device, h))
+        else
+            devs = Cint.(collect(devices))
+            GC.@preserve A devs check(ccall((:csb200_dict_create_multi, libcsb200), Cint,
+                (Ptr{Cvoid}, Int64, Int64, Int64, Cint, Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}),
+                pointer(A), M, N, max(stride(A, 2), M), dtype_code(T), devs, length(devs), h))
+        end
         d = new{T}(h[], M, N)
         finalizer(d) do x
             x.handle == C_NULL || ccall((:csb200_dict_destroy, libcsb200), Cint, (Ptr{Cvoid},), x.handle)
@@ -65,12 +74,13 @@ Base.size(D::Dictionary, i::Int) = size(D)[i]
 Base.eltype(::Dictionary{T}) where {T} = T
 
 const MatOrDict = Union{AbstractMatrix,Dictionary}
-as_dictionary(A::Dictionary) = A
-as_dictionary(A::AbstractMatrix) = Dictionary(A)
+as_dictionary(A::Dictionary; kw...) = A
+as_dictionary(A::AbstractMatrix; kw...) = Dictionary(A; kw...)
 # A raw matrix is uploaded for this one call: its device copy is released when the call returns, not whenever Julia's
 # GC -- which does not see device memory -- gets to the finalizer (a loop of omp(A, b, k) calls would fill the GPU).
-function with_dictionary(f, A::MatOrDict)
-    D = as_dictionary(A)
+# `devices` (e.g. 0:7) replicates a raw matrix onto several GPUs for the call: omp(A, B, k; devices = 0:7).
+function with_dictionary(f, A::MatOrDict; devices = nothing)
+    D = as_dictionary(A; devices = devices)
     try
         return f(D)
     finally
@@ -128,22 +138,23 @@ end
 
 # ---------------------------------------------------------------------------------------------
 # omp  (src/matchingpursuit.jl:73-91)
-function omp(A::MatOrDict, b::AbstractVecOrMat, ε::Real, k::Int = size(A, 1); csc::Bool = false)
+function omp(A::MatOrDict, b::AbstractVecOrMat, ε::Real, k::Int = size(A, 1); csc::Bool = false, devices = nothing)
     ε ≥ 0 || throw("ε = $ε has to be non-negative")
-    with_dictionary(D -> run_omp_like(:omp, D, b, 1, ε, k; csc = csc), A)   # csc = true: N x nsig SparseMatrixCSC (additive)
+    # csc = true: N x nsig SparseMatrixCSC (additive); devices = 0:7: split the columns of b over these GPUs (additive)
+    with_dictionary(D -> run_omp_like(:omp, D, b, 1, ε, k; csc = csc), A; devices = devices)
 end
-omp(A::MatOrDict, b::AbstractVecOrMat, k::Int) = omp(A, b, eps(eltype(A)), k)
-omp(A::MatOrDict, b::AbstractVecOrMat; max_residual = eps(eltype(A)), sparsity = min(size(A)...)) =
-    omp(A, b, max_residual, sparsity)
+omp(A::MatOrDict, b::AbstractVecOrMat, k::Int; kw...) = omp(A, b, eps(eltype(A)), k; kw...)
+omp(A::MatOrDict, b::AbstractVecOrMat; max_residual = eps(eltype(A)), sparsity = min(size(A)...), kw...) =
+    omp(A, b, max_residual, sparsity; kw...)
 
 # gomp  (src/matchingpursuit.jl:126-148)
-function gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, ε::Real, k::Int = size(A, 1))
+function gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, ε::Real, k::Int = size(A, 1); csc::Bool = false, devices = nothing)
     ε ≥ 0 || throw("ε = $ε has to be non-negative")
-    with_dictionary(D -> run_omp_like(:gomp, D, b, l, ε, k), A)
+    with_dictionary(D -> run_omp_like(:gomp, D, b, l, ε, k; csc = csc), A; devices = devices)
 end
-gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, k::Int) = gomp(A, b, l, eps(eltype(A)), k)
-gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int; max_residual = eps(eltype(A)), sparsity = size(A, 2)) =
-    gomp(A, b, l, max_residual, sparsity)
+gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int, k::Int; kw...) = gomp(A, b, l, eps(eltype(A)), k; kw...)
+gomp(A::MatOrDict, b::AbstractVecOrMat, l::Int; max_residual = eps(eltype(A)), sparsity = size(A, 2), kw...) =
+    gomp(A, b, l, max_residual, sparsity; kw...)
 
 # fr == ols == oomp == ormp  (src/forward.jl:33-54): forward regression; FP64 dictionaries
 fr(A::MatOrDict, b::AbstractVecOrMat, max_ε::Real, min_δ::Real, k::Int = size(A, 1); csc::Bool = false) =
@@ -210,6 +221,115 @@ function mp_on(D::Dictionary, b::AbstractVector, k::Int, x::SparseVector)
         sel[j] ≥ 0 && (x[sel[j] + 1] += coef[j])
     end
     return x
+end
+
+# ---------------------------------------------------------------------------------------------
+# Dictionary analysis (src/util.jl:2, 59-61, 96-117) -- csb200_dict_colnorms / csb200_dict_cumbabel
+function colnorms(A::MatOrDict)
+    with_dictionary(A) do D
+        out = Vector{Float64}(undef, D.N)
+        check(ccall((:csb200_dict_colnorms, libcsb200), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), D.handle, out))
+        out
+    end
+end
+normalize!(A::StridedMatrix) = (A ./= eltype(A).(colnorms(A))'; A)            # src/util.jl:59-61
+function cumbabel(A::MatOrDict, k::Int)                                          # src/util.jl:106-117
+    with_dictionary(A) do D
+        mu = Vector{Float64}(undef, k)
+        check(ccall((:csb200_dict_cumbabel, libcsb200), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}), D.handle, k, mu))
+        eltype(D).(mu)                                                           # `zeros(eltype(A), k)` (:107)
+    end
+end
+babel(A::MatOrDict, k::Int) = cumbabel(A, k)[k]                                  # src/util.jl:101
+coherence(A::MatOrDict) = babel(A, 1)                                            # src/util.jl:98
+
+# ---------------------------------------------------------------------------------------------
+# Device-resident batch (csb200_batch_*): upload a signal matrix once, solve repeatedly with no host<->device
+# traffic, download when needed.  The stateful counterpart of the reference's `P = OMP(A, b, k)` objects
+# (src/matchingpursuit.jl:44-60) for many right-hand sides.
+mutable struct Batch{T}
+    handle::Ptr{Cvoid}
+    dict::Dictionary{T}
+    nsig::Int
+    max_sparsity::Int
+    function Batch(D::Dictionary{T}, max_signals::Integer, max_sparsity::Integer) where {T}
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:csb200_batch_create, libcsb200), Cint, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}),
+                    D.handle, max_signals, max_sparsity, h))
+        b = new{T}(h[], D, 0, max_sparsity)
+        finalizer(b) do x
+            x.handle == C_NULL || ccall((:csb200_batch_destroy, libcsb200), Cint, (Ptr{Cvoid},), x.handle)
+            x.handle = C_NULL
+        end
+        return b
+    end
+end
+function upload!(P::Batch, b::AbstractVecOrMat)
+    B = signals(P.dict, b)
+    GC.@preserve B check(ccall((:csb200_batch_upload, libcsb200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64),
+                               P.handle, pointer(B), P.dict.M, size(B, 2)))
+    P.nsig = size(B, 2)
+    return P
+end
+omp!(P::Batch, k::Int, ε::Real = eps(eltype(P.dict))) =
+    (check(ccall((:csb200_batch_omp, libcsb200), Cint, (Ptr{Cvoid}, Int64, Cdouble), P.handle, k, Float64(ε)), ε); P)
+gomp!(P::Batch, l::Int, k::Int, ε::Real = eps(eltype(P.dict))) =
+    (check(ccall((:csb200_batch_gomp, libcsb200), Cint, (Ptr{Cvoid}, Int64, Int64, Cdouble), P.handle, l, k, Float64(ε)), ε); P)
+mp!(P::Batch, iters::Int) =
+    (check(ccall((:csb200_batch_mp, libcsb200), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Int64),
+                 P.handle, iters, C_NULL, C_NULL, C_NULL, 0)); P)
+# results of the last omp! / gomp! as a vector of SparseVectors (or an N x nsig SparseMatrixCSC with csc = true)
+function download(P::Batch; csc::Bool = false)
+    stride, nsig = max(P.max_sparsity, 1), P.nsig
+    sel = Matrix{Int64}(undef, stride, nsig); coef = Matrix{Float64}(undef, stride, nsig)
+    nnz = Vector{Int64}(undef, nsig); res = Vector{Float64}(undef, nsig); its = Vector{Int64}(undef, nsig)
+    check(ccall((:csb200_batch_download, libcsb200), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}),
+        P.handle, stride, sel, coef, nnz, res, its))
+    csc && return assemble_csc(P.dict.N, sel, coef, nnz)
+    return [to_sparse(P.dict.N, view(sel, :, s), view(coef, :, s), nnz[s]) for s in 1:nsig], res, its
+end
+function last_solve_ms(P::Batch)
+    ms = Ref{Cdouble}(0)
+    check(ccall((:csb200_batch_last_solve_ms, libcsb200), Cint, (Ptr{Cvoid}, Ref{Cdouble}), P.handle, ms))
+    return ms[]
+end
+
+# ---------------------------------------------------------------------------------------------
+# Column-sharded single-dictionary mode (one Julia process per GPU, e.g. under MPI.jl): each rank holds the columns
+# [n_offset+1, n_offset+size(A_local, 2)] of a dictionary with n_total atoms; the 128-byte communicator id is created
+# on rank 0 (`comm_unique_id()`) and broadcast by the host program.
+function shard_dictionary(A::StridedMatrix{T}, n_offset::Integer, n_total::Integer; device::Integer = 0) where {T<:Union{Float32,Float64}}
+    stride(A, 1) == 1 || (A = Matrix(A))
+    M, N = size(A)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve A check(ccall((:csb200_dict_create_shard, libcsb200), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Int64, Int64, Ref{Ptr{Cvoid}}),
+        pointer(A), M, N, max(stride(A, 2), M), dtype_code(T), device, n_offset, n_total, h))
+    return (handle = h[], M = M, n_total = Int(n_total), T = T)      # release with csb200_dict_destroy
+end
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:csb200_comm_unique_id, libcsb200), Cint, (Ptr{UInt8},), id))
+    return id
+end
+function comm_create(id::Vector{UInt8}, rank::Integer, nranks::Integer, device::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:csb200_comm_create, libcsb200), Cint, (Ptr{UInt8}, Cint, Cint, Cint, Ref{Ptr{Cvoid}}), id, rank, nranks, device, h))
+    return h[]                                                            # release with csb200_comm_destroy
+end
+# `omp(A, b, k)` (src/matchingpursuit.jl:73-86) for ONE signal on the column-sharded dictionary; every rank calls it
+# with the same b and gets the same SparseVector
+function omp_sharded(shard, comm::Ptr{Cvoid}, b::AbstractVector, k::Int, ε::Real = eps(shard.T))
+    ε ≥ 0 || throw("ε = $ε has to be non-negative")
+    length(b) == shard.M || throw(DimensionMismatch("A has $(shard.M) rows, b has length $(length(b))"))
+    bb = Vector{shard.T}(b); stride = max(k, 1)
+    sel = Vector{Int64}(undef, stride); coef = Vector{Float64}(undef, stride)
+    nnz = Ref{Int64}(0); res = Ref{Cdouble}(0); its = Ref{Int64}(0); ms = Ref{Cdouble}(0)
+    GC.@preserve bb check(ccall((:csb200_omp_sharded, libcsb200), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cdouble, Ptr{Int64}, Ptr{Cdouble}, Ref{Int64}, Ref{Cdouble}, Ref{Int64}, Ref{Cdouble}),
+        shard.handle, comm, pointer(bb), k, Float64(ε), sel, coef, nnz, res, its, ms), ε)
+    return to_sparse(shard.n_total, sel, coef, nnz[])
 end
 
 end # module

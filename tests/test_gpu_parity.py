@@ -234,10 +234,16 @@ def test_golden(cs, path, impl, update, monkeypatch):
 
 
 # ------------------------------------------------------------------ reference call surface + quirks
-@pytest.fixture(params=["small_solve", "multi_launch"])
+@pytest.fixture(params=["small_solve", "multi_launch", "persist"])
 def solve_path(request, monkeypatch):
-    """Small dictionaries normally take the whole-solve kernel; CSB200_SMALL_SOLVE=0 forces the per-iteration path."""
-    monkeypatch.setenv("CSB200_SMALL_SOLVE", "1" if request.param == "small_solve" else "0")
+    """The three ways a few-signal solve on a small dictionary can run: the one-CTA-per-signal whole-solve kernel
+    (solve_small.cu), the per-iteration kernels (CSB200_SMALL_SOLVE=0), and the cooperative whole-solve kernel
+    (solve_persist.cu, the default for <= 8 signals; forced here so that nothing else can take the call)."""
+    if request.param == "persist":
+        monkeypatch.delenv("CSB200_SMALL_SOLVE", raising=False)
+        monkeypatch.setenv("CSB200_PERSIST", "1")
+    else:
+        monkeypatch.setenv("CSB200_SMALL_SOLVE", "1" if request.param == "small_solve" else "0")
     return request.param
 
 
@@ -830,6 +836,7 @@ def test_few_signal_solves_replay_a_cuda_graph(cs, po, algo, dtype, nsig, monkey
     after the key changes -- must reproduce the oracle on fresh signals."""
     for hook in ("CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM", "CSB200_GRAPH", "CSB200_CORR_IMPL"):
         monkeypatch.delenv(hook, raising=False)
+    monkeypatch.setenv("CSB200_PERSIST", "0")         # <= 8 signals would otherwise take the cooperative whole-solve kernel
     rng = np.random.default_rng(77 + nsig)
     M, N, k, l = 96, 4500, 6, 2                       # N > 4096: not the whole-solve small-dictionary kernel
     A = po.gaussian_dictionary(rng, M, N, dtype)
@@ -881,6 +888,88 @@ def test_few_signal_solves_replay_a_cuda_graph(cs, po, algo, dtype, nsig, monkey
         for rep in range(3):
             run_and_check(batch, k)
         assert batch.graph_replays() == 0
+
+
+# ------------------------------------------------------------------ cooperative whole-solve kernel (solve_persist.cu)
+@pytest.mark.parametrize("algo", ["omp", "mp"])
+@pytest.mark.parametrize("dtype,M,N,k,nsig", [(np.float64, 1024, 8192, 32, 1), (np.float32, 1024, 8192, 32, 1),
+                                              (np.float64, 1024, 8192, 16, 5), (np.float64, 1024, 8192, 12, 8),
+                                              (np.float32, 520, 3001, 9, 3), (np.float64, 70, 130, 6, 2),
+                                              (np.float64, 128, 256, 8, 1), (np.float64, 4096, 1500, 20, 1)])
+def test_persistent_whole_solve_matches_multi_launch_and_oracle(cs, po, algo, dtype, M, N, k, nsig, monkeypatch):
+    """solve_persist.cu (1..8 signals, one cooperative launch per solve: workers with a dictionary slice resident in
+    shared memory + one updater CTA per signal) against (a) the per-iteration kernels -- identical selection sequence,
+    values to rounding -- and (b) the oracle at the usual bar.  Shapes: the config-2 dictionary (L2 regime, columns
+    partly streamed), ragged sizes, config 1, a long-atom case; noisy signals keep every arg-max well posed."""
+    rng = np.random.default_rng(1000 + M + nsig)
+    A = po.gaussian_dictionary(rng, M, N, dtype)
+    X0, Bm = _planted(po, rng, A.astype(np.float64), k, nsig, noise=1e-3)
+    Bm = np.asfortranarray(Bm.astype(dtype))
+    eps = float(np.finfo(dtype).eps)
+    rtol = RTOL32 if dtype == np.float32 else RTOL64
+    iters = k if algo == "omp" else 2 * k
+    out = {}
+    with cs.Dictionary(A) as D:
+        for path, env in (("persist", {"CSB200_PERSIST": "1"}), ("multi", {"CSB200_PERSIST": "0", "CSB200_SMALL_SOLVE": "0"})):
+            for key in ("CSB200_PERSIST", "CSB200_SMALL_SOLVE"):
+                monkeypatch.delenv(key, raising=False)
+            for key, val in env.items():
+                monkeypatch.setenv(key, val)
+            with cs.Batch(D, nsig, iters) as batch:
+                for rep in range(2):                                   # the second solve reuses scratch and sync words
+                    batch.upload(Bm)
+                    batch.omp(iters, eps) if algo == "omp" else batch.mp(iters)
+                    out[path, rep] = batch.download(iters) + (batch.residual(),)
+        assert all(np.array_equal(out["persist", 0][i], out["persist", 1][i]) for i in range(6))    # deterministic
+        sel, coef, nnz, res, its, R = out["persist", 0]
+        msel, mcoef, mnnz, mres, mits, mR = out["multi", 0]
+        assert np.array_equal(sel, msel) and np.array_equal(nnz, mnnz) and np.array_equal(its, mits)
+        scale = np.abs(mcoef).max()
+        assert np.max(np.abs(coef - mcoef)) <= (1e-5 if dtype == np.float32 else 1e-12) * scale
+        assert np.allclose(res, mres, rtol=1e-4 if dtype == np.float32 else 1e-9, atol=1e-12)
+        assert np.allclose(R, mR, rtol=0, atol=(1e-5 if dtype == np.float32 else 1e-12) * np.abs(Bm).max())
+    for s in range(min(nsig, 3)):
+        t = po.Trace()
+        if algo == "omp":
+            ref = po.omp(A, Bm[:, s], iters, trace=t)
+            n = int(nnz[s])
+            assert sel[s, :n].tolist() == t.order(), (s, "selection sequence", min(t.margin))
+            idx, val = _sorted(sel[s], coef[s], n)
+            assert idx.tolist() == ref.nzind and _close(val, ref.nzval, rtol)
+            assert int(its[s]) == t.iterations and abs(res[s] - t.resnorm[-1]) <= rtol * np.linalg.norm(Bm[:, s])
+        else:
+            ref = po.mp(A, Bm[:, s], iters, trace=t)
+            assert sel[s, :iters].tolist() == t.order(), (s, "selection sequence", min(t.margin))
+            acc = {}
+            for i, c in zip(sel[s, :iters].tolist(), coef[s, :iters].tolist()):
+                acc[i] = acc.get(i, 0.0) + c
+            assert sorted(acc) == ref.nzind
+            assert _close(np.array([acc[i] for i in sorted(acc)]), ref.nzval, max(rtol, 1e-9))
+
+
+def test_persistent_whole_solve_eps_break_mixed_signals(cs, po, monkeypatch):
+    """Signals of one call stop at different update!s (eps-break): a stopped signal's updater leaves, the workers keep
+    serving the others; iteration counts and supports per signal must match the oracle."""
+    monkeypatch.setenv("CSB200_PERSIST", "1")
+    rng = np.random.default_rng(2024)
+    M, N = 200, 900
+    A = po.gaussian_dictionary(rng, M, N)
+    cols = []
+    for kk in (2, 9, 5, 1):                                            # planted sparsities: the eps-break comes at kk
+        x0 = po.sparse_vector(rng, N, kk)
+        cols.append(A[:, x0.nzind] @ np.asarray(x0.nzval))
+    Bm = np.asfortranarray(np.stack(cols, axis=1))
+    with cs.Dictionary(A) as D, cs.Batch(D, 4, 12) as batch:
+        batch.upload(Bm)
+        batch.omp(12, 1e-9)
+        sel, coef, nnz, res, its = batch.download(12)
+    for s in range(4):
+        t = po.Trace()
+        ref = po.omp(A, Bm[:, s], 12, eps=1e-9, trace=t)
+        n = int(nnz[s])
+        assert int(its[s]) == t.iterations and sel[s, :n].tolist() == t.order(), s
+        idx, val = _sorted(sel[s], coef[s], n)
+        assert idx.tolist() == ref.nzind and _close(val, ref.nzval, RTOL64)
 
 
 # ------------------------------------------------------------------ column-sharded mode
