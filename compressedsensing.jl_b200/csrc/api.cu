@@ -24,6 +24,10 @@ using namespace csb;
 namespace {
 
 thread_local std::string g_last_error;
+// Multi-device fan-out (csb200_dict_create_multi): a worker thread solves a slice of the caller's batch, but every
+// choice of kernel path that depends on the signal count (small-dictionary whole-solve kernel, Gram-matrix sweep) is
+// made for the WHOLE batch, so that the slice is computed exactly as the single-device call would compute it.
+thread_local int64_t tl_path_nsig = 0;
 
 int fail_cuda(cudaError_t e, const char* what) {
     char buf[512];
@@ -39,6 +43,7 @@ int fail_cuda(cudaError_t e, const char* what) {
     } while (0)
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+int64_t path_nsig(int64_t nsig) { return tl_path_nsig > nsig ? tl_path_nsig : nsig; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -137,8 +142,9 @@ struct csb200_batch {
     double* qnew = nullptr;     // [cap_sig][ld] newest orthonormal direction per signal
     double* cn2 = nullptr;      // [N] squared column norms
     int* ndone = nullptr;       // subspace pursuit: number of signals whose stopping test has fired
-    unsigned char* persist_scratch = nullptr;   // whole-solve cooperative kernel: candidates + sync words
+    unsigned char* persist_scratch = nullptr;   // whole-solve cooperative kernel: hand-over buffers (see run_persist_solve)
     size_t persist_bytes = 0;
+    unsigned persist_epoch = 0;                 // launches so far: sequence numbers carry its low 16 bits
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -304,7 +310,7 @@ bool use_small_solve(const csb200_batch* b) {
     if (env && !strcmp(env, "0")) return false;
     const csb200_dict* d = b->dict;
     if (b->corr_impl_env != IMPL_AUTO) return false;            // a test forced a specific correlation kernel
-    return small_solve_eligible((int)d->ld, (int)d->N, (int)b->kcap, (int)b->nsig, d->dtype == CSB200_F32);
+    return small_solve_eligible((int)d->ld, (int)d->N, (int)b->kcap, (int)path_nsig(b->nsig), d->dtype == CSB200_F32);
 }
 
 int run_small_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double eps, const int* x0_idx,
@@ -334,7 +340,7 @@ bool use_persist_solve(const csb200_batch* b, int mode) {
     if (b->corr_impl_env != IMPL_AUTO || b->profile || b->defer_finish || !d->coop) return false;
     for (const char* hook : {"CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM"})
         if (getenv(hook)) return false;
-    if (b->nsig < 1 || b->nsig > PERSIST_MAX_SIGNALS || d->n_total != d->N) return false;
+    if (b->nsig < 1 || path_nsig(b->nsig) > PERSIST_MAX_SIGNALS || d->n_total != d->N) return false;
     if ((size_t)d->ld * d->N * d->esize() > PERSIST_MAX_DICT_BYTES) return false;
     return persist_plan((int)d->ld, (int)d->N, (int)b->kcap, (int)b->nsig, d->dtype == CSB200_F32, d->num_sms, nullptr, nullptr);
 }
@@ -348,28 +354,54 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
         g_last_error = "whole-solve kernel: shape does not fit";
         return CSB200_ERR_UNSUPPORTED;
     }
-    const size_t cand = (size_t)b->nsig * q.workers;
-    const size_t off_idx = (cand * sizeof(double) + 15) / 16 * 16, off_sync = (off_idx + cand * sizeof(int) + 15) / 16 * 16;
-    const size_t need = off_sync + PERSIST_SYNC_WORDS * sizeof(unsigned);
+    // hand-over buffers: candidates [8][SMs][4] words, residuals [8][ld][2] words, control words, optional debug stamps
+    const size_t cand_bytes = (size_t)PERSIST_MAX_SIGNALS * d->num_sms * 4 * sizeof(unsigned long long);
+    const size_t res_bytes = (size_t)PERSIST_MAX_SIGNALS * d->ld * 2 * sizeof(unsigned long long);
+    const size_t ctrl_off = cand_bytes + res_bytes, dbg_off = ctrl_off + 256;
+    static const bool debug = [] { const char* e = getenv("CSB200_PERSIST_DEBUG"); return e && e[0] == '1'; }();
+    const size_t dbg_bytes = debug ? (size_t)2 * 8 * (size_t)(k > 0 ? k : 1) * sizeof(long long) : 0;
+    const size_t need = dbg_off + dbg_bytes;
     if (need > b->persist_bytes) {
         cudaFree(b->persist_scratch);
         b->persist_scratch = nullptr; b->persist_bytes = 0;
         CU_TRY(cudaMalloc(&b->persist_scratch, need));
         b->persist_bytes = need;
+        b->persist_epoch = 0;
     }
+    if ((b->persist_epoch & 0xffffu) == 0)          // fresh buffers, or the 16-bit epoch wrapped: no stale sequence numbers
+        CU_TRY(cudaMemsetAsync(b->persist_scratch, 0, b->persist_bytes, b->stream));
     int rc = begin_solve_fwd(b);
     if (rc) return rc;
     q.A = d->dA; q.B = b->dB; q.R = b->dR;
     q.M = (int)d->M; q.ld = (int)d->ld; q.N = (int)d->N; q.ns = (int)b->nsig; q.kcap = (int)b->kcap; q.idx_offset = (int)d->n_offset;
     q.mode = mode; q.k = (int)k; q.stride = (int)b->kcap; q.eps = eps;
-    q.cand_val = reinterpret_cast<double*>(b->persist_scratch);
-    q.cand_idx = reinterpret_cast<int*>(b->persist_scratch + off_idx);
-    q.sync = reinterpret_cast<unsigned*>(b->persist_scratch + off_sync);
+    q.cand_ll = reinterpret_cast<unsigned long long*>(b->persist_scratch);
+    q.r_ll = reinterpret_cast<unsigned long long*>(b->persist_scratch + cand_bytes);
+    q.ctrl = reinterpret_cast<unsigned*>(b->persist_scratch + ctrl_off);
+    q.epoch = (unsigned)(b->persist_epoch++ & 0xffffu);
+    q.dbg = debug ? reinterpret_cast<long long*>(b->persist_scratch + dbg_off) : nullptr;
     q.nnz = b->nnz; q.sel = b->sel; q.x = b->x; q.resnorm = b->resnorm; q.iters = b->iters; q.done = b->done; q.flags = b->flags;
-    CU_TRY(cudaMemsetAsync(q.sync, 0, PERSIST_SYNC_WORDS * sizeof(unsigned), b->stream));
+    if (debug) CU_TRY(cudaMemsetAsync(q.dbg, 0, dbg_bytes, b->stream));
     cudaError_t e = launch_persist_solve(q, d->dtype == CSB200_F32, smem, b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "persist_solve");
     b->other_launches++;
+    if (debug && k > 0) {                            // per-phase cycle counts of signal 0's updater and of worker 0
+        std::vector<long long> h((size_t)2 * 8 * k);
+        CU_TRY(cudaMemcpyAsync(h.data(), q.dbg, dbg_bytes, cudaMemcpyDeviceToHost, b->stream));
+        CU_TRY(cudaStreamSynchronize(b->stream));
+        double u[4] = {0, 0, 0, 0}, w[5] = {0, 0, 0, 0, 0};
+        int nu = 0, nw = 0;
+        for (int64_t it = 1; it + 1 < k; ++it) {
+            const long long* a0 = &h[(size_t)it * 8];
+            const long long* w0 = &h[(size_t)(k + it) * 8];
+            if (a0[0] && a0[4]) { u[0] += a0[1] - a0[0]; u[1] += a0[2] - a0[1]; u[2] += a0[3] ? a0[3] - a0[2] : 0; u[3] += a0[4] - (a0[3] ? a0[3] : a0[2]); ++nu; }
+            if (w0[0] && w0[4]) { w[0] += w0[1] - w0[0]; w[1] += w0[2] - w0[1]; w[2] += w0[3] - w0[2]; w[3] += w0[4] - w0[3]; w[4] += h[(size_t)(k + it + 1) * 8] ? h[(size_t)(k + it + 1) * 8] - w0[0] : 0; ++nw; }
+        }
+        if (nu && nw)
+            fprintf(stderr, "[csb200 persist] cycles per update!: updater wait-cands %.0f | pick %.0f | fetch atom %.0f | append+publish %.0f"
+                            "  ||  worker wait-r %.0f | load r %.0f | dots %.0f | publish %.0f | whole iteration %.0f\n",
+                    u[0] / nu, u[1] / nu, u[2] / nu, u[3] / nu, w[0] / nw, w[1] / nw, w[2] / nw, w[3] / nw, w[4] / nw);
+    }
     return CSB200_OK;
 }
 
@@ -384,7 +416,7 @@ void decide_gram(csb200_batch* b, int64_t k) {
     if (env && !strcmp(env, "0")) return;
     const bool force = env && !strcmp(env, "1");
     if (d->dtype != CSB200_F64 || d->n_total != d->N || d->N > GRAM_MAX_ATOMS || !d->has_map || d->gram_failed) return;
-    if (!force && (b->nsig * k < GRAM_MIN_SIGNAL_ITERS || b->nsig < CLUSTER_UPDATE_MAX_SIGNALS)) return;
+    if (!force && (path_nsig(b->nsig) * k < GRAM_MIN_SIGNAL_ITERS || b->nsig < CLUSTER_UPDATE_MAX_SIGNALS)) return;
     std::lock_guard<std::mutex> lk(d->gram_mu);
     if (!d->gram) {
         size_t free_b = 0, total_b = 0;
@@ -1455,7 +1487,9 @@ static int fan_out(csb200_dict* d, int64_t nsig, int workers, Call call) {
     auto run = [&](int w) {
         const int64_t s0 = w * base + (w < extra ? w : extra), ns = base + (w < extra ? 1 : 0);
         csb200_dict* rep = w == 0 ? d : d->extra[w - 1];
+        tl_path_nsig = nsig;
         rc[w] = call(rep, s0, ns);
+        tl_path_nsig = 0;
         if (rc[w]) err[w] = g_last_error;          // g_last_error is thread-local: carry the text to the caller's thread
     };
     for (int w = 1; w < workers; ++w) th.emplace_back(run, w);

@@ -13,13 +13,13 @@
 //     its columns as fit in shared memory for the WHOLE solve (they are read from L2/HBM once per solve instead of once
 //     per `update!`), streams the rest, and per `update!` computes c = A'r for all ns residuals in one pass over its
 //     columns (register-blocked: CG columns x NS signals per warp step), fused with the |c| arg-max.
-//   * the two roles hand over through global memory: workers publish (|c|, atom) per signal and arrive on a counter,
-//     the updater publishes the new residual and a per-signal sequence flag (release / acquire at gpu scope).  No host
-//     round trip, no kernel boundary, no grid-wide barrier: one arrive and one flag per `update!`.
+//   * the two roles hand over through global memory (L2) with self-validating 8-byte words (data + sequence number in
+//     one atomic 64-bit access): workers publish (|c|, atom) per signal, the updater publishes the new residual.  No host
+//     round trip, no kernel boundary, no grid-wide barrier, no memory fence in the loop.
 // Every c_j is reduced inside one warp in the order corr_gemv.cu uses (lane i takes the 16-byte vectors i, i + 32, ..;
 // xor-shuffle tree), so selections agree bit for bit with the multi-launch path; the update arithmetic is
 // append_atom's (same as the CTA update kernel, with this kernel's block size).
-// All spin loops are bounded (PERSIST_TIMEOUT_NS): a lost CTA turns into an error status, never a hung GPU.
+// All spin loops are bounded (SPIN_LIMIT): a lost CTA turns into an error status, never a hung GPU.
 #include "common.cuh"
 #include "gemv_loads.cuh"
 #include "update_common.cuh"
@@ -32,43 +32,76 @@ namespace {
 
 constexpr int PT = 512;                    // threads per CTA (128 registers per thread: CG x NS accumulators fit)
 constexpr int PW = PT / 32;
-constexpr unsigned FLAG_STOP = 0x7fffffffu;
-constexpr unsigned long long PERSIST_TIMEOUT_NS = 4000000000ull;      // 4 s per wait
+constexpr unsigned SPIN_LIMIT = 1u << 24;  // polls before a wait gives up (a few seconds): an error status, never a hung GPU
+constexpr int DBG_PHASES = 8;              // clock64() stamps per iteration and role (CSB200_PERSIST_DEBUG)
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+// ---- hand-over without fences: every 8-byte word carries its own sequence number ("LL" words) ----------------------
+// word = (seq << 32) | 32 data bits, written and read as ONE 64-bit scalar access (single-copy atomic in the PTX
+// memory model), so a reader that sees the expected seq sees the data that was stored with it -- no release/acquire
+// fence (MEMBAR.SC/ALL.GPU + CCTL.IVALL on this part, the dominant cost of the first version of this kernel), no
+// counter, no flag.  seq = (launch epoch << 16) | version: buffers are never cleared between launches.
+__device__ __forceinline__ unsigned long long ll_word(unsigned data, unsigned seq) {
+    return ((unsigned long long)seq << 32) | data;
+}
+__device__ __forceinline__ void ll_store(unsigned long long* p, unsigned long long w) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ll_store2(unsigned long long* p, unsigned long long w0, unsigned long long w1) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* p) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+__device__ __forceinline__ void ll_load2(const unsigned long long* p, unsigned long long& w0, unsigned long long& w1) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// Spin until *p >= want (acquire).  Returns false on timeout or when another CTA has raised the error word.
-__device__ __forceinline__ bool wait_ge(const unsigned* p, unsigned want, unsigned* err) {
-    if (ld_acquire_gpu(p) >= want) return true;
-    const unsigned long long t0 = timer_ns();
-    for (unsigned spin = 1;; ++spin) {
-        if (ld_acquire_gpu(p) >= want) return true;
-        if ((spin & 255u) == 0) {
-            if (ld_acquire_gpu(err) != 0u) return false;
-            if (timer_ns() - t0 > PERSIST_TIMEOUT_NS) { atomicExch(err, 1u); return false; }
-        }
-    }
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <typename V> __device__ __forceinline__ V ld_shared_vec(const V* p) { return *p; }
+// One element of a residual as LL words: FP64 = two words (one 16-byte vector access of two atomic halves), FP32 = one.
+template <typename T> struct ResLL;
+template <> struct ResLL<double> {
+    static constexpr int WORDS = 2;
+    static __device__ __forceinline__ void store(unsigned long long* p, double v, unsigned seq) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        ll_store2(p, ll_word((unsigned)b, seq), ll_word((unsigned)(b >> 32), seq));
+    }
+    static __device__ __forceinline__ bool load(const unsigned long long* p, unsigned seq, double& out) {
+        unsigned long long w0, w1;
+        ll_load2(p, w0, w1);
+        if ((unsigned)(w0 >> 32) != seq || (unsigned)(w1 >> 32) != seq) return false;
+        out = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+        return true;
+    }
+};
+template <> struct ResLL<float> {
+    static constexpr int WORDS = 1;
+    static __device__ __forceinline__ void store(unsigned long long* p, float v, unsigned seq) {
+        ll_store(p, ll_word(__float_as_uint(v), seq));
+    }
+    static __device__ __forceinline__ bool load(const unsigned long long* p, unsigned seq, float& out) {
+        const unsigned long long w = ll_load(p);
+        if ((unsigned)(w >> 32) != seq) return false;
+        out = __uint_as_float((unsigned)w);
+        return true;
+    }
+};
 
 // ---- worker: c = A'r for NS residuals over this CTA's atom range, fused |c| arg-max --------------------------------
 template <typename T, int NS, int CG>
 __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double (*red_v)[PW], int (*red_i)[PW],
-                               unsigned* s_flag) {
+                               int* s_state) {
     using V = typename Vec<T>::type;
     constexpr int W = Vec<T>::W;
+    constexpr int RW = ResLL<T>::WORDS;
     constexpr int UNR = CG * NS >= 32 ? 1 : (CG * NS >= 16 ? 2 : 4);   // loads in flight vs the 128-register budget
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld, ns = a.ns;
@@ -80,11 +113,11 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
     const T* A = static_cast<const T*>(a.A);
     T* rs = reinterpret_cast<T*>(smem);                                   // [NS][ld]
     T* cache = rs + (size_t)NS * ld;                                      // [ncache][ld]: columns lo .. lo + ncache
-    unsigned* arrive = a.sync;
-    unsigned* flag = a.sync + 1;
-    unsigned* err = a.sync + 1 + PERSIST_MAX_SIGNALS;
+    const unsigned epoch1 = a.epoch + 1u;
+    const unsigned seq0 = a.epoch << 16;
     const unsigned long long pol = l2_policy(L2POL_NORMAL);
     const int nvec = ld / W;                                              // ld is a multiple of 16 elements
+    long long* dbg = (a.dbg && w == 0) ? a.dbg + (size_t)DBG_PHASES * a.k : nullptr;   // worker 0's stamps follow the updater's
 
     {   // columns kept on chip for the whole solve
         const V* src = reinterpret_cast<const V*>(A + (size_t)lo * ld);
@@ -93,24 +126,49 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
         for (int i = tid; i < total; i += PT) dst[i] = ldg_stream(src + i, pol);
     }
     for (int i = tid; i < (NS - ns) * ld; i += PT) rs[(size_t)ns * ld + i] = (T)0;     // unused signal slots
+    {   // residual version 0 is b itself
+        const V* src = reinterpret_cast<const V*>(static_cast<const T*>(a.B));
+        V* dst = reinterpret_cast<V*>(rs);
+        for (int i = tid; i < ns * nvec; i += PT) dst[i] = __ldcg(src + i);
+    }
     const int gs = (nstream + CG - 1) / CG, gc = (ncache + CG - 1) / CG;
 
     for (int it = 0; it < a.k; ++it) {
-        // residual version `it` of every signal (version 0 is b itself)
-        if (tid < ns) {
-            const bool ok = wait_ge(flag + tid, (unsigned)it, err);
-            s_flag[tid] = ok ? ld_acquire_gpu(flag + tid) : FLAG_STOP;
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 0] = clock64();
+        if (it > 0) {
+            // residual version `it` of every signal: one thread per signal watches the head word (written last by the
+            // updater) so that 147 x 512 threads do not hammer the L2 while the updater is working
+            const unsigned seq = seq0 | (unsigned)it;
+            if (tid < ns) {
+                const unsigned long long* head = a.r_ll + ((size_t)tid * ld + (ld - 1)) * RW + (RW - 1);
+                int state = 2;
+                for (unsigned spin = 0; spin < SPIN_LIMIT; ++spin) {
+                    if ((unsigned)(ll_load(head) >> 32) == seq) { state = 0; break; }
+                    if ((spin & 15u) == 15u) {
+                        if (ld_relaxed_u32(a.ctrl + tid) == epoch1) { state = 1; break; }              // this signal has stopped
+                        if (ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;             // someone gave up
+                    }
+                }
+                if (state == 2) st_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS, epoch1);
+                s_state[tid] = state;
+            }
+            __syncthreads();
+            bool all_stop = true, error = false;
+            for (int s = 0; s < ns; ++s) { all_stop = all_stop && s_state[s] == 1; error = error || s_state[s] == 2; }
+            if (all_stop || error) break;
+            if (dbg && tid == 0) dbg[it * DBG_PHASES + 1] = clock64();
+            for (int e = tid; e < ns * ld; e += PT) {
+                const int s = e / ld;
+                if (s_state[s] != 0) continue;                            // a stopped signal keeps its last residual
+                const unsigned long long* p = a.r_ll + (size_t)e * RW;
+                T val;
+                unsigned spin = 0;
+                while (!ResLL<T>::load(p, seq, val) && ++spin < SPIN_LIMIT) {}
+                rs[e] = val;
+            }
         }
         __syncthreads();
-        bool all_stop = true;
-        for (int s = 0; s < ns; ++s) all_stop = all_stop && s_flag[s] == FLAG_STOP;
-        if (all_stop) break;
-        {
-            const V* src = reinterpret_cast<const V*>(static_cast<const T*>(it == 0 ? a.B : (const void*)a.R));
-            V* dst = reinterpret_cast<V*>(rs);
-            for (int i = tid; i < ns * nvec; i += PT) dst[i] = __ldcg(src + i);       // L2: the updater just wrote it
-        }
-        __syncthreads();
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 2] = clock64();
 
         double best_v[NS];
         int best_i[NS];
@@ -150,7 +208,7 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
                 for (int i = lane; i < nvec; i += 32) {
                     V x[CG];
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) x[c] = ld_shared_vec(col[c] + i);
+                    for (int c = 0; c < CG; ++c) x[c] = col[c][i];
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         double rr[W];
@@ -180,23 +238,26 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
             for (int s = 0; s < NS; ++s) { red_v[s][warp] = best_v[s]; red_i[s][warp] = best_i[s]; }
         }
         __syncthreads();
-        if (tid < ns) {
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 3] = clock64();
+        if (tid < ns) {                                                    // this worker's candidate of signal `tid`
             double bv = red_v[tid][0];
             int bi = red_i[tid][0];
             for (int q = 1; q < PW; ++q)
                 if (cand_better(red_v[tid][q], red_i[tid][q], bv, bi)) { bv = red_v[tid][q]; bi = red_i[tid][q]; }
-            a.cand_val[(size_t)tid * a.workers + w] = bv;
-            a.cand_idx[(size_t)tid * a.workers + w] = (bi == INT_MAX) ? -1 : bi + a.idx_offset;
-            __threadfence();
+            const unsigned seq = seq0 | (unsigned)(it + 1);
+            const unsigned long long b = (unsigned long long)__double_as_longlong(bv);
+            unsigned long long* rec = a.cand_ll + ((size_t)tid * a.workers + w) * 4;
+            ll_store2(rec, ll_word((unsigned)b, seq), ll_word((unsigned)(b >> 32), seq));
+            ll_store(rec + 2, ll_word((unsigned)((bi == INT_MAX) ? -1 : bi + a.idx_offset), seq));
         }
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicAdd(arrive, 1u); }
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 4] = clock64();
     }
 }
 
 // ---- updater: the loop body of `update!` for one signal, state resident in shared memory ---------------------------
 template <typename T>
 __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, double* red, int* red_i) {
+    constexpr int RW = ResLL<T>::WORDS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sig = blockIdx.x, ld = a.ld, kcap = a.kcap;
     const int ldT = kcap | 1;
@@ -215,31 +276,38 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
     T* acache = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(S.colp + kcap) + 15) & ~(uintptr_t)15);   // [ucache][ld]
     S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red;
-    __shared__ int s_j, s_ok;
+    __shared__ int s_j, s_fail;
 
     const T* A = static_cast<const T*>(a.A);
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
     T* rg = static_cast<T*>(a.R) + (size_t)sig * ld;
-    unsigned* arrive = a.sync;
-    unsigned* flag = a.sync + 1 + sig;
-    unsigned* err = a.sync + 1 + PERSIST_MAX_SIGNALS;
+    unsigned long long* rll = a.r_ll + (size_t)sig * ld * RW;
+    const unsigned epoch1 = a.epoch + 1u;
+    const unsigned seq0 = a.epoch << 16;
+    long long* dbg = (a.dbg && sig == 0) ? a.dbg : nullptr;
 
     double s2 = 0.0;
     int bad = 0;
     for (int row = tid; row < ld; row += PT) {      // r = b: the state of a freshly constructed MP / OMP object
         const T e = b[row];
-        bs[row] = (double)e; rs[row] = (double)e; rg[row] = e;
+        bs[row] = (double)e; rs[row] = (double)e;
         s2 += (double)e * (double)e;
         bad |= !isfinite((double)e);
     }
+    if (tid == 0) s_fail = 0;
     double nr = sqrt(block_sum<PT>(s2, red));
     int t = 0, flags = 0, iters = 0;
     bool done = false, failed = false;
     if (__syncthreads_or(bad)) { flags = 4; done = true; }
 
-    auto publish = [&](unsigned value) {
-        __syncthreads();                              // every thread's residual stores precede the release below
-        if (tid == 0) { __threadfence(); st_release_gpu(flag, value); }
+    // residual version `ver` for the workers: rows already stored by r_set carry it; `all` re-publishes every row (an
+    // update! that left r unchanged), and the head word goes last
+    auto publish = [&](unsigned ver, bool all) {
+        const unsigned seq = seq0 | ver;
+        if (all)
+            for (int row = tid; row < ld; row += PT) ResLL<T>::store(rll + (size_t)row * RW, (T)rs[row], seq);
+        __syncthreads();
+        if (tid == 0) ResLL<T>::store(rll + (size_t)(ld - 1) * RW, (T)rs[ld - 1], seq);
     };
 
     for (int it = 0; it < a.k && !done; ++it) {
@@ -250,17 +318,27 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             if (!(nr >= a.eps)) done = true;
             break;
         }
-        // candidates of this update! from every worker
-        if (tid == 0) s_ok = wait_ge(arrive, (unsigned)a.workers * (unsigned)(it + 1), err) ? 1 : 0;
-        __syncthreads();
-        if (!s_ok) { failed = true; break; }
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 0] = clock64();
+        // candidates of this update!: thread c waits for worker c's record
+        const unsigned cseq = seq0 | (unsigned)(it + 1);
         double bv = -1.0;
         int bi = INT_MAX;
         for (int c = tid; c < a.workers; c += PT) {
-            const double v = __ldcg(a.cand_val + (size_t)sig * a.workers + c);
-            const int i = __ldcg(a.cand_idx + (size_t)sig * a.workers + c);
+            const unsigned long long* rec = a.cand_ll + ((size_t)sig * a.workers + c) * 4;
+            unsigned long long w0 = 0, w1 = 0, w2 = 0;
+            bool ok = false;
+            for (unsigned spin = 0; spin < SPIN_LIMIT && !ok; ++spin) {
+                ll_load2(rec, w0, w1);
+                w2 = ll_load(rec + 2);
+                ok = (unsigned)(w0 >> 32) == cseq && (unsigned)(w1 >> 32) == cseq && (unsigned)(w2 >> 32) == cseq;
+                if (!ok && (spin & 63u) == 63u && ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;
+            }
+            if (!ok) { s_fail = 1; continue; }
+            const double v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+            const int i = (int)(unsigned)w2;
             if (i >= 0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; }
         }
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 1] = clock64();
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
@@ -276,7 +354,11 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             s_j = (bi == INT_MAX) ? -1 : bi;
         }
         __syncthreads();
+        if (s_fail) { failed = true; break; }
         const int j = s_j;                                               // global atom index or -1
+        const unsigned rseq = seq0 | (unsigned)(it + 1);                 // the residual version this update! produces
+        const bool more = it + 1 < a.k;                                  // somebody will read it
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 2] = clock64();
 
         if (a.mode == 2) {
             // mp: x[i] += <a_i, r>;  r <- r - <a_i, r> a_i   (:26-31); one (atom, increment) record per iteration
@@ -289,7 +371,8 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                 s2 = 0.0;
                 for (int row = tid; row < ld; row += PT) {
                     const T rr = (T)(rs[row] - c * S.v[row]);
-                    rs[row] = (double)rr; rg[row] = rr;
+                    rs[row] = (double)rr;
+                    if (more && row != ld - 1) ResLL<T>::store(rll + (size_t)row * RW, rr, rseq);
                     s2 += (double)rr * (double)rr;
                 }
                 nr = sqrt(block_sum<PT>(s2, red));
@@ -302,7 +385,8 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             }
             ++iters;
             t = iters;
-            if (it + 1 < a.k) publish((unsigned)(it + 1));
+            if (more) publish((unsigned)(it + 1), j < 0);
+            if (dbg && tid == 0) dbg[it * DBG_PHASES + 4] = clock64();
             continue;
         }
 
@@ -325,19 +409,27 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                     __syncthreads();
                     aj = slot;
                 }
+                if (dbg && tid == 0) dbg[it * DBG_PHASES + 3] = clock64();
                 double nr2 = 0.0;
                 const int dep = append_atom<T, PT>(
                     S, t, j, aj, ld, [&](int row) { return bs[row]; }, [&](int row) { return rs[row]; },
-                    [&](int row, T val) { rs[row] = (double)val; rg[row] = val; }, nr2);
+                    [&](int row, T val) {
+                        rs[row] = (double)val;
+                        if (more && row != ld - 1) ResLL<T>::store(rll + (size_t)row * RW, val, rseq);
+                    }, nr2);
                 if (dep) flags |= 1; else { changed = true; nr = sqrt(nr2); }
             }
         }
-        (void)changed;
         ++iters;
         if (!(nr >= a.eps)) done = true;                                 // `norm(residual!(P, x)) >= eps || break` (:79)
-        if (!done && it + 1 < a.k) publish((unsigned)(it + 1));
+        if (!done && more) publish((unsigned)(it + 1), !changed);
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 4] = clock64();
     }
-    publish(FLAG_STOP);                                                  // releases the workers (and covers every exit path)
+    __syncthreads();
+    if (tid == 0) {
+        st_relaxed_u32(a.ctrl + sig, epoch1);                            // releases the workers on every exit path
+        if (failed) st_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS, epoch1);
+    }
 
     // ---- results ----
     if (a.mode != 2) {
@@ -348,6 +440,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             a.sel[(size_t)sig * a.stride + i] = S.ssel[i];
         }
     }
+    for (int row = tid; row < ld; row += PT) rg[row] = (T)rs[row];       // the residual where the batch keeps it
     if (tid == 0) {
         a.nnz[sig] = t;
         a.iters[sig] = iters;
@@ -362,9 +455,9 @@ __global__ void __launch_bounds__(PT, 1) persist_solve_kernel(PersistArgs a) {
     extern __shared__ __align__(16) unsigned char psm[];
     __shared__ double red_v[NS][PW];                                     // the updater uses the first row of each
     __shared__ int red_i[NS][PW];
-    __shared__ unsigned s_flag[PERSIST_MAX_SIGNALS];
+    __shared__ int s_state[PERSIST_MAX_SIGNALS];
     if ((int)blockIdx.x < a.ns) persist_updater<T>(a, psm, &red_v[0][0], &red_i[0][0]);
-    else persist_worker<T, NS, CG>(a, psm, red_v, red_i, s_flag);
+    else persist_worker<T, NS, CG>(a, psm, red_v, red_i, s_state);
 }
 
 size_t updater_fixed_bytes(int ld, int kcap) {
