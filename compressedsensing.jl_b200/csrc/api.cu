@@ -145,6 +145,10 @@ struct csb200_batch {
     unsigned char* persist_scratch = nullptr;   // whole-solve cooperative kernel: hand-over buffers (see run_persist_solve)
     size_t persist_bytes = 0;
     unsigned persist_epoch = 0;                 // launches so far: sequence numbers carry its low 16 bits
+    // two-half overlap of large omp batches (run_omp_split): a high-priority stream for the correlation passes, a
+    // low-priority one for the updates, events tying the two together
+    cudaStream_t sp_gemm = nullptr, sp_upd = nullptr;
+    cudaEvent_t sp_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, G[2], U[2], end
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -191,6 +195,9 @@ void free_batch_mem(csb200_batch* b) {
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
     if (b->ev_solve1) cudaEventDestroy(b->ev_solve1);
     if (b->graph_exec) cudaGraphExecDestroy(b->graph_exec);
+    for (auto e : b->sp_ev) if (e) cudaEventDestroy(e);
+    if (b->sp_gemm) cudaStreamDestroy(b->sp_gemm);
+    if (b->sp_upd) cudaStreamDestroy(b->sp_upd);
     if (b->stream) cudaStreamDestroy(b->stream);
 }
 
@@ -357,7 +364,8 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
     // hand-over buffers: candidates [8][SMs][4] words, residuals [8][ld][2] words, control words, optional debug stamps
     const size_t cand_bytes = (size_t)PERSIST_MAX_SIGNALS * d->num_sms * 4 * sizeof(unsigned long long);
     const size_t res_bytes = (size_t)PERSIST_MAX_SIGNALS * d->ld * 2 * sizeof(unsigned long long);
-    const size_t ctrl_off = cand_bytes + res_bytes, dbg_off = ctrl_off + 256;
+    const size_t bell_bytes = (size_t)PERSIST_MAX_SIGNALS * d->num_sms * BELL_STRIDE * sizeof(unsigned long long);
+    const size_t bell_off = cand_bytes + res_bytes, ctrl_off = bell_off + bell_bytes, dbg_off = ctrl_off + 256;
     static const bool debug = [] { const char* e = getenv("CSB200_PERSIST_DEBUG"); return e && e[0] == '1'; }();
     const size_t dbg_bytes = debug ? (size_t)2 * 8 * (size_t)(k > 0 ? k : 1) * sizeof(long long) : 0;
     const size_t need = dbg_off + dbg_bytes;
@@ -377,6 +385,7 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
     q.mode = mode; q.k = (int)k; q.stride = (int)b->kcap; q.eps = eps;
     q.cand_ll = reinterpret_cast<unsigned long long*>(b->persist_scratch);
     q.r_ll = reinterpret_cast<unsigned long long*>(b->persist_scratch + cand_bytes);
+    q.bell = reinterpret_cast<unsigned long long*>(b->persist_scratch + bell_off);
     q.ctrl = reinterpret_cast<unsigned*>(b->persist_scratch + ctrl_off);
     q.epoch = (unsigned)(b->persist_epoch++ & 0xffffu);
     q.dbg = debug ? reinterpret_cast<long long*>(b->persist_scratch + dbg_off) : nullptr;
@@ -438,6 +447,102 @@ bool uses_cluster_update(const csb200_batch* b) {
 }
 cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
     return uses_cluster_update(b) ? launch_omp_update_cluster(a, f32, b->stream) : launch_omp_update(a, f32, b->stream);
+}
+
+// ---- two-half overlap of a large batched omp solve ---------------------------------------------------------------
+// The per-signal update (omp_update_kernel, L2-latency-bound) used to run AFTER each correlation pass (tensor-bound):
+// 4.5 % of the step at the headline config with the GPU's tensor pipes idle.  The signals are independent, so the
+// batch is cut into two halves A | B and the passes are interleaved
+//     stream G (high priority):  G(A,0) G(B,0) G(A,1) G(B,1) ...
+//     stream U (low priority):          U(A,0) U(B,0) U(A,1) ...
+// with events G(h,i) -> U(h,i) -> G(h,i+1).  The correlation kernel is capped at 224 registers and uses 193 KiB of
+// shared memory, which leaves room on every SM for exactly one 128-thread update CTA (64 registers, ~19 KiB): the
+// update of one half runs under the correlation pass of the other.  Results are bit-identical to the plain loop (same
+// kernels on the same data, only the interleaving differs).  CSB200_SPLIT=0 disables it.
+constexpr int64_t SPLIT_MIN_SIGNALS = 8192;
+bool use_omp_split(const csb200_batch* b, int64_t k) {
+    static const bool off = [] { const char* e = getenv("CSB200_SPLIT"); return e && e[0] == '0'; }();
+    const csb200_dict* d = b->dict;
+    if (off || k < 2 || b->defer_finish) return false;
+    if (d->dtype != CSB200_F64 || !d->has_map || b->nsig < SPLIT_MIN_SIGNALS) return false;
+    if (b->corr_impl_env != IMPL_AUTO && b->corr_impl_env != IMPL_GEMM) return false;
+    if (uses_cluster_update(b)) return false;
+    const size_t upd = omp_update_smem_bytes((int)d->ld, (int)b->kcap);
+    return upd + 1024 <= 28 * 1024;               // what the correlation kernel leaves of the SM's 228 KiB
+}
+
+StateArgs state_args_range(csb200_batch* b, int64_t s0, int64_t ns, int S, int take, double eps, int ignore_done) {
+    StateArgs a = state_args(b, S, take, eps, ignore_done);
+    const csb200_dict* d = b->dict;
+    const size_t es = d->esize(), kc = (size_t)b->kcap;
+    a.B = static_cast<const char*>(a.B) + (size_t)s0 * d->ld * es;
+    a.R = static_cast<char*>(a.R) + (size_t)s0 * d->ld * es;
+    a.nsig = (int)ns;
+    a.pval = a.pval + (size_t)s0 * a.P * a.S;
+    a.pidx = a.pidx + (size_t)s0 * a.P * a.S;
+    a.nnz += s0; a.sel += (size_t)s0 * kc; a.Rf += (size_t)s0 * kc * kc; a.z += (size_t)s0 * kc; a.x += (size_t)s0 * kc;
+    a.resnorm += s0; a.iters += s0; a.done += s0; a.flags += s0;
+    return a;
+}
+
+int run_omp_split(csb200_batch* b, int64_t k, double eps) {
+    csb200_dict* d = b->dict;
+    if (!b->sp_gemm) {
+        int lo = 0, hi = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));             // hi = numerically lowest = greatest priority
+        CU_TRY(cudaStreamCreateWithPriority(&b->sp_gemm, cudaStreamNonBlocking, hi));
+        CU_TRY(cudaStreamCreateWithPriority(&b->sp_upd, cudaStreamNonBlocking, lo));
+        for (auto& e : b->sp_ev) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int blk = corr_gemm_f64_block();
+    const int64_t P = (d->N + blk - 1) / blk;
+    int rc = ensure_partials(b, P, 1);
+    if (rc) return rc;
+    b->cur_P = (int)P;
+    b->cur_dense_ld = 0;
+    // halves: whole 128-signal tiles; the first half takes the extra tile
+    const int64_t tiles = (b->nsig + 127) / 128;
+    const int64_t n0 = ((tiles + 1) / 2) * 128, n1 = b->nsig - n0;
+    const int64_t start[2] = {0, n0}, count[2] = {n0, n1};
+    CUtensorMap mapR[2];
+    for (int h = 0; h < 2; ++h)
+        if ((rc = make_operand_map(&mapR[h], static_cast<char*>(b->dR) + (size_t)start[h] * d->ld * 8, d->ld, count[h]))) return rc;
+    cudaStream_t G = b->sp_gemm, U = b->sp_upd;
+    cudaEvent_t ev_start = b->sp_ev[0], *evG = &b->sp_ev[1], *evU = &b->sp_ev[3], ev_end = b->sp_ev[5];
+    cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), false, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    CU_TRY(cudaEventRecord(ev_start, b->stream));
+    CU_TRY(cudaStreamWaitEvent(G, ev_start, 0));
+    CU_TRY(cudaStreamWaitEvent(U, ev_start, 0));
+    for (int64_t it = 0; it < k; ++it) {
+        for (int h = 0; h < 2; ++h) {
+            if (it > 0) CU_TRY(cudaStreamWaitEvent(G, evU[h], 0));       // the half's residuals of this update! are in place
+            CorrArgs c;
+            c.A = d->dA; c.R = static_cast<char*>(b->dR) + (size_t)start[h] * d->ld * 8;
+            c.M = (int)d->M; c.ld = (int)d->ld; c.N = (int)d->N; c.nsig = (int)count[h]; c.S = 1; c.P = (int)P;
+            c.idx_offset = (int)d->n_offset;
+            c.pval = b->pval + (size_t)start[h] * P; c.pidx = b->pidx + (size_t)start[h] * P;
+            cudaEvent_t p0 = nullptr, p1 = nullptr;
+            if (b->profile) {
+                if (b->ev_used + 2 > b->ev.size())
+                    for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); b->ev.push_back(ev); }
+                p0 = b->ev[b->ev_used]; p1 = b->ev[b->ev_used + 1]; b->ev_used += 2;
+                CU_TRY(cudaEventRecord(p0, G));
+            }
+            e = launch_corr_gemm_f64(&d->mapA, &mapR[h], c, d->num_sms, G);
+            if (e != cudaSuccess) return fail_cuda(e, "correlation kernel launch");
+            if (b->profile) CU_TRY(cudaEventRecord(p1, G));
+            CU_TRY(cudaEventRecord(evG[h], G));
+            CU_TRY(cudaStreamWaitEvent(U, evG[h], 0));
+            e = launch_omp_update(state_args_range(b, start[h], count[h], 1, 1, eps, 0), false, U);
+            if (e != cudaSuccess) return fail_cuda(e, "omp_update");
+            CU_TRY(cudaEventRecord(evU[h], U));
+            b->other_launches++;
+        }
+    }
+    CU_TRY(cudaEventRecord(ev_end, U));                                  // U's last update follows every G launch
+    CU_TRY(cudaStreamWaitEvent(b->stream, ev_end, 0));
+    return CSB200_OK;
 }
 
 // ---- CUDA-graph replay of few-signal solves ---------------------------------------------------------------------
@@ -969,6 +1074,10 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     decide_gram(b, k);
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
+    if (use_omp_split(b, k)) {
+        if ((rc = run_omp_split(b, k, eps))) return rc;
+        return finish(b, true);
+    }
     rc = run_graphed(b, 0, k, 1, eps, k, [&]() -> int {
         cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
         if (e != cudaSuccess) return fail_cuda(e, "reset_state");

@@ -113,12 +113,14 @@ struct PersistArgs {
     int ucache;           // active-atom columns an updater keeps in shared memory
     unsigned long long* cand_ll;   // [ns][workers][4] per-worker arg-max of |c| as self-validating words {v lo, v hi, atom, -}
     unsigned long long* r_ll;      // [ns][ld][1 or 2] the residual handed to the workers, same word format
+    unsigned long long* bell;      // [ns][workers][BELL_STRIDE] one doorbell per (signal, worker): (epoch + 1) << 32 | residual version
     unsigned* ctrl;                // [0, PERSIST_MAX_SIGNALS) "signal has stopped", then "a CTA gave up"; value = epoch + 1
     unsigned epoch;                // launch number, 16 bits: sequence numbers are (epoch << 16) | version
     long long* dbg;                // optional clock64() stamps (CSB200_PERSIST_DEBUG)
     int* nnz; int* sel; double* x; double* resnorm; int* iters; int* done; int* flags;
 };
 constexpr size_t PERSIST_CTRL_WORDS = 1 + PERSIST_MAX_SIGNALS;
+constexpr int BELL_STRIDE = 32;            // words between doorbells: 256 bytes, i.e. different L2 slices
 // fills workers / wcache / ucache and the dynamic shared memory size; false: the shape does not fit this kernel
 bool persist_plan(int ld, int N, int kcap, int ns, bool f32, int num_sms, PersistArgs* out, size_t* smem_out);
 cudaError_t launch_persist_solve(const PersistArgs& a, bool f32, size_t smem, cudaStream_t st);

@@ -105,8 +105,12 @@ enum { EPI_TOPS = 0, EPI_STORE = 1, EPI_OLS = 2, EPI_ABS = 3 };
 // DUAL (EPI_OLS only): the 128 "signal" columns of a CTA tile are 64 residuals r_s (from mapR) followed by the newest
 // orthonormal directions q_s of the SAME 64 signals (from mapQ), arranged so that a thread's accumulators
 // acc[i][j] (j < NJ/2) = <a, r_s> and acc[i][j + NJ/2] = <a, q_s> belong to the same (atom, signal) pairs.
+// Register cap: 224 per thread for the 8-warp layouts instead of the 255 a (256, 1) launch bound would allow.  The
+// kernel was at 228-236 and is spill-free at 224; the 8192 registers this leaves on the SM are exactly one 128-thread x
+// 64-register CTA of omp_update_kernel, which is what lets the per-signal update of one half of a batch run UNDER the
+// correlation pass of the other half (api.cu, run_omp_split) instead of after it.
 template <int MI, int NJ, int WM, int WN, int SUB, int EPI = EPI_TOPS, bool DUAL = false>
-__global__ void __launch_bounds__(WM * WN * 32, 1)
+__global__ void __maxnreg__(WM * WN * 32 <= 256 ? 224 : 128)
 corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapR,
                      int N, int nsig, int kchunks, int tilesN, int tilesB, int band, int S, int P, int idx_offset,
                      double* __restrict__ pval, int* __restrict__ pidx, long long ldc,

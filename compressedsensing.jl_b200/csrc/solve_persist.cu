@@ -33,7 +33,8 @@ namespace {
 constexpr int PT = 512;                    // threads per CTA (128 registers per thread: CG x NS accumulators fit)
 constexpr int PW = PT / 32;
 constexpr unsigned SPIN_LIMIT = 1u << 24;  // polls before a wait gives up (a few seconds): an error status, never a hung GPU
-constexpr int DBG_PHASES = 8;              // clock64() stamps per iteration and role (CSB200_PERSIST_DEBUG)
+constexpr int DBG_PHASES = 8;
+constexpr unsigned BELL_STOP = 0xfffffffeu, BELL_ABORT = 0xffffffffu;   // doorbell values above every version number              // clock64() stamps per iteration and role (CSB200_PERSIST_DEBUG)
 
 // ---- hand-over without fences: every 8-byte word carries its own sequence number ("LL" words) ----------------------
 // word = (seq << 32) | 32 data bits, written and read as ONE 64-bit scalar access (single-copy atomic in the PTX
@@ -136,18 +137,22 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
     for (int it = 0; it < a.k; ++it) {
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 0] = clock64();
         if (it > 0) {
-            // residual version `it` of every signal: one thread per signal watches the head word (written last by the
-            // updater) so that 147 x 512 threads do not hammer the L2 while the updater is working
+            // residual version `it` of every signal: one thread per signal watches THIS worker's doorbell of that signal
+            // (the updater rings one doorbell per worker, 256 bytes apart: 147 CTAs polling one address queue up at a
+            // single L2 slice -- ~3.5k cycles per hand-over in the first version of this kernel)
             const unsigned seq = seq0 | (unsigned)it;
             if (tid < ns) {
-                const unsigned long long* head = a.r_ll + ((size_t)tid * ld + (ld - 1)) * RW + (RW - 1);
+                const unsigned long long* bell = a.bell + ((size_t)tid * a.workers + w) * BELL_STRIDE;
                 int state = 2;
                 for (unsigned spin = 0; spin < SPIN_LIMIT; ++spin) {
-                    if ((unsigned)(ll_load(head) >> 32) == seq) { state = 0; break; }
-                    if ((spin & 15u) == 15u) {
-                        if (ld_relaxed_u32(a.ctrl + tid) == epoch1) { state = 1; break; }              // this signal has stopped
-                        if (ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;             // someone gave up
+                    const unsigned long long v = ll_load(bell);
+                    if ((unsigned)(v >> 32) == epoch1) {
+                        const unsigned ver = (unsigned)v;
+                        if (ver == BELL_ABORT) break;
+                        if (ver == BELL_STOP) { state = 1; break; }
+                        if (ver >= (unsigned)it) { state = 0; break; }
                     }
+                    if ((spin & 1023u) == 1023u && ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;   // someone gave up
                 }
                 if (state == 2) st_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS, epoch1);
                 s_state[tid] = state;
@@ -255,9 +260,124 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
 }
 
 // ---- updater: the loop body of `update!` for one signal, state resident in shared memory ---------------------------
+// Block reductions of one or two values with ONE barrier each: three scratch rows used in rotation (a row is not
+// rewritten before two further barriers have passed).
+struct Red3 {
+    double* buf;      // [3][2][PW]
+    int phase;
+    __device__ __forceinline__ void sum2(double& a, double& b) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        a = warp_sum(a); b = warp_sum(b);
+        double* row = buf + (size_t)phase * 2 * PW;
+        if (lane == 0) { row[warp] = a; row[PW + warp] = b; }
+        __syncthreads();
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int q = 0; q < PW; ++q) { sa += row[q]; sb += row[PW + q]; }
+        a = sa; b = sb;
+        phase = phase == 2 ? 0 : phase + 1;
+    }
+};
+
+// `add_column!(AiQR, a, pos)` + the residual down-date for ONE atom, specialised for this kernel (reference:
+// src/util.jl:118-126, src/matchingpursuit.jl:152-176; same mathematics as append_atom in update_common.cuh: implicit Q,
+// CGS with DGKS re-orthogonalisation, R^{-1} stored).  Differences that matter when ONE signal is on the critical path
+// of 147 waiting SMs: a thread owns fixed rows of v / b / r (no barrier between the row-wise phases), the triangular
+// mat-vecs are warp-parallel dot products instead of one serial chain per output, <v, b> rides with ||v||^2, every
+// reduction costs one barrier, and the new residual leaves for the workers (store_r) before its norm is reduced.
+template <typename T, typename StoreR, typename AfterStore>
+__device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
+                                           const double* __restrict__ bs, double* __restrict__ rs, Red3& red,
+                                           StoreR store_r, AfterStore after_store, double& nr2) {
+    constexpr int W = RowVec<T>::W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double s2 = 0.0, sb = 0.0;
+    for (int row = tid * W; row < ld; row += PT * W) {
+        double e[W];
+        RowVec<T>::load(aj + row, e);
+#pragma unroll
+        for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; s2 = fma(e[q], e[q], s2); sb = fma(e[q], bs[row + q], sb); }
+    }
+    red.sum2(s2, sb);                                                // also publishes v to the whole CTA
+    const double anorm2 = s2;
+    double before2 = anorm2, rho2 = anorm2;
+    for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
+        for (int i = warp; i < t; i += PW) {                           // g = A_S' v, one warp per active atom
+            const T* ai = S.colp[i];
+            double acc = 0.0;
+#pragma unroll 4
+            for (int row = lane * W; row < ld; row += 32 * W) {
+                double e[W];
+                RowVec<T>::load(ai + row, e);
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc = fma(e[q], S.v[row + q], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) S.g[i] = acc;
+        }
+        __syncthreads();
+        for (int i = warp; i < t; i += PW) {                           // hh = R^{-T} g = Q'v: hh_i = sum_{l <= i} T[l, i] g_l
+            double acc = 0.0;
+            for (int l = lane; l <= i; l += 32) acc = fma(S.Tm[l + i * S.ldT], S.g[l], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) S.hh[i] = acc;
+        }
+        __syncthreads();
+        for (int i = warp; i < t; i += PW) {                           // y = R^{-1} hh: y_i = sum_{l >= i} T[i, l] hh_l
+            double acc = 0.0;
+            for (int l = i + lane; l < t; l += 32) acc = fma(S.Tm[i + l * S.ldT], S.hh[l], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) { S.y[i] = acc; S.ys[i] = sweep ? S.ys[i] + acc : acc; }
+        }
+        __syncthreads();
+        s2 = 0.0; sb = 0.0;
+        for (int row = tid * W; row < ld; row += PT * W) {             // v -= A_S y on this thread's rows
+            double acc[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[q] = S.v[row + q];
+#pragma unroll 4
+            for (int i = 0; i < t; ++i) {
+                double e[W];
+                RowVec<T>::load(S.colp[i] + row, e);
+                const double yi = S.y[i];
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[q] = fma(-e[q], yi, acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < W; ++q) { S.v[row + q] = acc[q]; s2 = fma(acc[q], acc[q], s2); sb = fma(acc[q], bs[row + q], sb); }
+        }
+        red.sum2(s2, sb);
+        rho2 = s2;
+        if (rho2 >= 0.5 * before2) break;                              // DGKS: one sweep was enough
+        before2 = rho2;
+    }
+    if (!(rho2 > 1e-26 * anorm2)) return 1;                            // numerically dependent atom: not appended
+    const double rho = sqrt(rho2), irho = 1.0 / rho;
+    const double zt = sb * irho;                                       // z_t = q_t' b
+    const double gam = zt * irho;
+    double s2r = 0.0, dummy = 0.0;
+    for (int row = tid * W; row < ld; row += PT * W) {                 // r <- r - q_t z_t on this thread's rows
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const T rr = (T)(rs[row + q] - gam * S.v[row + q]);
+            rs[row + q] = (double)rr;
+            store_r(row + q, rr);
+            s2r = fma((double)rr, (double)rr, s2r);
+        }
+    }
+    after_store();                                                     // the workers can start while ||r|| is being reduced
+    for (int i = tid; i < t; i += PT) S.Tsm[i + t * S.ldT] = -S.ys[i] * irho;   // R^{-1} gains [-R^{-1}h / rho; 1 / rho]
+    if (tid == 0) { S.Tsm[t + t * S.ldT] = irho; S.zs[t] = zt; S.ssel[t] = j; S.colp[t] = aj; }
+    red.sum2(s2r, dummy);                                              // barrier: the new column is visible
+    nr2 = s2r;
+    ++t;
+    return 0;
+}
+
 template <typename T>
-__device__ void persist_updater(const PersistArgs& a, unsigned char* smem, double* red, int* red_i) {
+__device__ void persist_updater(const PersistArgs& a, unsigned char* smem, double* red_buf) {
     constexpr int RW = ResLL<T>::WORDS;
+    constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sig = blockIdx.x, ld = a.ld, kcap = a.kcap;
     const int ldT = kcap | 1;
@@ -275,18 +395,21 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
     S.ssel = reinterpret_cast<int*>(p);
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
     T* acache = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(S.colp + kcap) + 15) & ~(uintptr_t)15);   // [ucache][ld]
-    S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red;
-    __shared__ int s_j, s_fail;
+    S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red_buf;
+    Red3 red{red_buf, 0};
+    __shared__ int s_j, s_fail, s_ci[PW];
+    __shared__ double s_cv[PW];
 
     const T* A = static_cast<const T*>(a.A);
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
     T* rg = static_cast<T*>(a.R) + (size_t)sig * ld;
     unsigned long long* rll = a.r_ll + (size_t)sig * ld * RW;
+    unsigned long long* bells = a.bell + (size_t)sig * a.workers * BELL_STRIDE;
     const unsigned epoch1 = a.epoch + 1u;
     const unsigned seq0 = a.epoch << 16;
     long long* dbg = (a.dbg && sig == 0) ? a.dbg : nullptr;
 
-    double s2 = 0.0;
+    double s2 = 0.0, unused = 0.0;
     int bad = 0;
     for (int row = tid; row < ld; row += PT) {      // r = b: the state of a freshly constructed MP / OMP object
         const T e = b[row];
@@ -295,19 +418,15 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
         bad |= !isfinite((double)e);
     }
     if (tid == 0) s_fail = 0;
-    double nr = sqrt(block_sum<PT>(s2, red));
+    red.sum2(s2, unused);
+    double nr = sqrt(s2);
     int t = 0, flags = 0, iters = 0;
     bool done = false, failed = false;
     if (__syncthreads_or(bad)) { flags = 4; done = true; }
 
-    // residual version `ver` for the workers: rows already stored by r_set carry it; `all` re-publishes every row (an
-    // update! that left r unchanged), and the head word goes last
-    auto publish = [&](unsigned ver, bool all) {
-        const unsigned seq = seq0 | ver;
-        if (all)
-            for (int row = tid; row < ld; row += PT) ResLL<T>::store(rll + (size_t)row * RW, (T)rs[row], seq);
-        __syncthreads();
-        if (tid == 0) ResLL<T>::store(rll + (size_t)(ld - 1) * RW, (T)rs[ld - 1], seq);
+    // one doorbell per worker: "residual version `ver` is on its way" (the data words validate themselves)
+    auto ring = [&](unsigned ver) {
+        for (int c = tid; c < a.workers; c += PT) ll_store(bells + (size_t)c * BELL_STRIDE, ll_word(ver, epoch1));
     };
 
     for (int it = 0; it < a.k && !done; ++it) {
@@ -331,7 +450,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                 ll_load2(rec, w0, w1);
                 w2 = ll_load(rec + 2);
                 ok = (unsigned)(w0 >> 32) == cseq && (unsigned)(w1 >> 32) == cseq && (unsigned)(w2 >> 32) == cseq;
-                if (!ok && (spin & 63u) == 63u && ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;
+                if (!ok && (spin & 1023u) == 1023u && ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;
             }
             if (!ok) { s_fail = 1; continue; }
             const double v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
@@ -345,17 +464,14 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
             if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
         }
-        if (lane == 0) { red[warp] = bv; red_i[warp] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            bv = red[0]; bi = red_i[0];
-            for (int q = 1; q < PW; ++q)
-                if (cand_better(red[q], red_i[q], bv, bi)) { bv = red[q]; bi = red_i[q]; }
-            s_j = (bi == INT_MAX) ? -1 : bi;
-        }
+        if (lane == 0) { s_cv[warp] = bv; s_ci[warp] = bi; }
         __syncthreads();
         if (s_fail) { failed = true; break; }
-        const int j = s_j;                                               // global atom index or -1
+        bv = s_cv[0]; bi = s_ci[0];
+#pragma unroll
+        for (int q = 1; q < PW; ++q)
+            if (cand_better(s_cv[q], s_ci[q], bv, bi)) { bv = s_cv[q]; bi = s_ci[q]; }
+        const int j = (bi == INT_MAX) ? -1 : bi;                         // global atom index or -1 (every thread has it)
         const unsigned rseq = seq0 | (unsigned)(it + 1);                 // the residual version this update! produces
         const bool more = it + 1 < a.k;                                  // somebody will read it
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 2] = clock64();
@@ -366,18 +482,33 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             if (j >= 0) {
                 const T* aj = A + (size_t)(j - a.idx_offset) * ld;
                 double s = 0.0;
-                for (int row = tid; row < ld; row += PT) { const double e = (double)aj[row]; S.v[row] = e; s += e * rs[row]; }
-                c = block_sum<PT>(s, red);                               // dot(view(A,:,i), r)  (:29)
-                s2 = 0.0;
-                for (int row = tid; row < ld; row += PT) {
-                    const T rr = (T)(rs[row] - c * S.v[row]);
-                    rs[row] = (double)rr;
-                    if (more && row != ld - 1) ResLL<T>::store(rll + (size_t)row * RW, rr, rseq);
-                    s2 += (double)rr * (double)rr;
+                for (int row = tid * W; row < ld; row += PT * W) {
+                    double e[W];
+                    RowVec<T>::load(aj + row, e);
+#pragma unroll
+                    for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; s = fma(e[q], rs[row + q], s); }
                 }
-                nr = sqrt(block_sum<PT>(s2, red));
+                red.sum2(s, unused);
+                c = s;                                                   // dot(view(A,:,i), r)  (:29)
+                s2 = 0.0;
+                for (int row = tid * W; row < ld; row += PT * W) {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) {
+                        const T rr = (T)(rs[row + q] - c * S.v[row + q]);
+                        rs[row + q] = (double)rr;
+                        if (more) ResLL<T>::store(rll + (size_t)(row + q) * RW, rr, rseq);
+                        s2 = fma((double)rr, (double)rr, s2);
+                    }
+                }
+                if (more) ring((unsigned)(it + 1));
+                red.sum2(s2, unused);
+                nr = sqrt(s2);
             } else {
                 flags |= 2;
+                if (more) {
+                    for (int row = tid; row < ld; row += PT) ResLL<T>::store(rll + (size_t)row * RW, (T)rs[row], rseq);
+                    ring((unsigned)(it + 1));
+                }
             }
             if (tid == 0) {
                 a.sel[(size_t)sig * a.stride + it] = j;
@@ -385,7 +516,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             }
             ++iters;
             t = iters;
-            if (more) publish((unsigned)(it + 1), j < 0);
+            __syncthreads();
             if (dbg && tid == 0) dbg[it * DBG_PHASES + 4] = clock64();
             continue;
         }
@@ -411,25 +542,27 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                 }
                 if (dbg && tid == 0) dbg[it * DBG_PHASES + 3] = clock64();
                 double nr2 = 0.0;
-                const int dep = append_atom<T, PT>(
-                    S, t, j, aj, ld, [&](int row) { return bs[row]; }, [&](int row) { return rs[row]; },
-                    [&](int row, T val) {
-                        rs[row] = (double)val;
-                        if (more && row != ld - 1) ResLL<T>::store(rll + (size_t)row * RW, val, rseq);
-                    }, nr2);
+                // the doorbells ring as soon as the new residual is on its way -- before its norm is known: if the eps test
+                // then ends the solve, the workers' extra pass is discarded and they leave at the STOP ring
+                const int dep = append_fast<T>(
+                    S, t, j, aj, ld, bs, rs, red,
+                    [&](int row, T val) { if (more) ResLL<T>::store(rll + (size_t)row * RW, val, rseq); },
+                    [&]() { if (more) ring((unsigned)(it + 1)); }, nr2);
                 if (dep) flags |= 1; else { changed = true; nr = sqrt(nr2); }
             }
         }
         ++iters;
         if (!(nr >= a.eps)) done = true;                                 // `norm(residual!(P, x)) >= eps || break` (:79)
-        if (!done && more) publish((unsigned)(it + 1), !changed);
+        if (!changed && !done && more) {                                 // r is unchanged: re-issue it under the new version
+            for (int row = tid; row < ld; row += PT) ResLL<T>::store(rll + (size_t)row * RW, (T)rs[row], rseq);
+            ring((unsigned)(it + 1));
+        }
+        __syncthreads();
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 4] = clock64();
     }
     __syncthreads();
-    if (tid == 0) {
-        st_relaxed_u32(a.ctrl + sig, epoch1);                            // releases the workers on every exit path
-        if (failed) st_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS, epoch1);
-    }
+    ring(failed ? BELL_ABORT : BELL_STOP);                               // releases the workers on every exit path
+    if (tid == 0 && failed) st_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS, epoch1);
 
     // ---- results ----
     if (a.mode != 2) {
@@ -453,10 +586,10 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
 template <typename T, int NS, int CG>
 __global__ void __launch_bounds__(PT, 1) persist_solve_kernel(PersistArgs a) {
     extern __shared__ __align__(16) unsigned char psm[];
-    __shared__ double red_v[NS][PW];                                     // the updater uses the first row of each
+    __shared__ double red_v[NS < 6 ? 6 : NS][PW];                        // workers: [NS][PW]; updater: Red3's [3][2][PW]
     __shared__ int red_i[NS][PW];
     __shared__ int s_state[PERSIST_MAX_SIGNALS];
-    if ((int)blockIdx.x < a.ns) persist_updater<T>(a, psm, &red_v[0][0], &red_i[0][0]);
+    if ((int)blockIdx.x < a.ns) persist_updater<T>(a, psm, &red_v[0][0]);
     else persist_worker<T, NS, CG>(a, psm, red_v, red_i, s_state);
 }
 
