@@ -461,9 +461,9 @@ cudaError_t update_launch(csb200_batch* b, const StateArgs& a, bool f32) {
 // kernels on the same data, only the interleaving differs).  CSB200_SPLIT=0 disables it.
 constexpr int64_t SPLIT_MIN_SIGNALS = 8192;
 bool use_omp_split(const csb200_batch* b, int64_t k) {
-    static const bool off = [] { const char* e = getenv("CSB200_SPLIT"); return e && e[0] == '0'; }();
+    const char* env = getenv("CSB200_SPLIT");
     const csb200_dict* d = b->dict;
-    if (off || k < 2 || b->defer_finish) return false;
+    if ((env && env[0] == '0') || k < 2 || b->defer_finish) return false;
     if (d->dtype != CSB200_F64 || !d->has_map || b->nsig < SPLIT_MIN_SIGNALS) return false;
     if (b->corr_impl_env != IMPL_AUTO && b->corr_impl_env != IMPL_GEMM) return false;
     if (uses_cluster_update(b)) return false;

@@ -441,6 +441,43 @@ def test_multi_device_handle_fans_out_bit_identically(cs, po):
         assert ei.value.status == -3
 
 
+def test_two_half_overlap_is_bit_identical(cs, po, monkeypatch):
+    """Large omp batches run as two halves on a high- and a low-priority stream so that the update of one half overlaps
+    the correlation pass of the other (api.cu run_omp_split): same kernels on the same data, so every output must equal
+    the plain loop (CSB200_SPLIT=0) bit for bit -- uneven halves, ragged last tile, eps-breaks included -- and the
+    oracle on a sample."""
+    rng = np.random.default_rng(515)
+    M, N, k, B = 100, 300, 5, 8192 + 77
+    A = po.gaussian_dictionary(rng, M, N)
+    idx = np.stack([rng.choice(N, size=k, replace=False) for _ in range(B)])
+    sign = rng.choice(np.array([-1.0, 1.0]), size=(B, k))
+    Bm = np.asfortranarray(np.einsum("msk,sk->ms", A[:, idx], sign))
+    Bm[:, 5::7] = A[:, idx[5::7, 0]] * 2.0                   # 1-sparse signals: eps-break after the first update!
+    out = {}
+    with cs.Dictionary(A) as D:
+        for mode in ("0", "1"):
+            monkeypatch.setenv("CSB200_SPLIT", mode)
+            with cs.Batch(D, B, k) as batch:
+                batch.upload(Bm)
+                batch.profile(True)
+                batch.omp(k, 1e-9)
+                ms, launches, other = batch.corr_time()
+                batch.profile(False)
+                assert launches == (2 * k if mode == "1" else k) and ms > 0
+                out[mode] = batch.download(k) + (batch.residual(),)
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b)
+    sel, coef, nnz, res, its, R = out["1"]
+    assert (its[5::7] == 1).all() and (nnz[5::7] == 1).all()
+    for s in (0, 5, 4100, 4200, B - 1):
+        t = po.Trace()
+        ref = po.omp(A, Bm[:, s], k, eps=1e-9, trace=t)
+        n = int(nnz[s])
+        assert sel[s, :n].tolist() == t.order() and int(its[s]) == t.iterations
+        i2, v2 = _sorted(sel[s], coef[s], n)
+        assert i2.tolist() == ref.nzind and _close(v2, ref.nzval, RTOL64)
+
+
 def test_pipelined_one_shot_matches_single_upload(cs, po, monkeypatch):
     """Host batches of >= 32 768 signals are cut into whole-wave chunks whose uploads / downloads overlap the solves
     (csb200_omp / _gomp / _fr one-shot calls).  Results must be bit-identical to the single-upload path, ragged last
