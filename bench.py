@@ -456,8 +456,11 @@ class C2:
         else:
             peak, peak_src = committed, committed_src + ("; re-measured in this run inside the clocks window: %.2f TFLOP/s"
                                                          % float(live["peak_tflops"]) if live else "")
-        flop_per_launch = 2.0 * M * N * B
-        achieved = flop_per_launch * corr_launches / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else 0.0
+        # every update! of every signal is one column of a correlation pass, however the passes are cut into launches
+        # (large batches run as two half-batch launches per update!, see run_omp_split): flop per launch = total / launches
+        flop_total = 2.0 * M * N * B * k * steps
+        flop_per_launch = flop_total / max(1, corr_launches)
+        achieved = flop_total / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "corr_gemm_traffic.json")
         if os.path.exists(tpath) and B == 65536:          # the ncu capture was taken at exactly this shape
@@ -467,6 +470,7 @@ class C2:
                     "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/corr_gemm_traffic.json)",
                     "kernel": "corr_gemm_f64_kernel", "launches": int(corr_launches),
                     "mean_launch_ms": corr_ms / max(1, corr_launches), "share_of_step": corr_ms / dev_ms if dev_ms else None,
+                    "launches_per_update": corr_launches / max(1, k * steps),
                     "flop_per_launch": flop_per_launch, "peak_source": peak_src, "peak_committed": committed,
                     "peak_live": live}
 

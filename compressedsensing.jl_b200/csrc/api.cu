@@ -271,11 +271,23 @@ void maybe_persist_dictionary(csb200_batch* b) {
     cudaGetLastError();
 }
 
+// The correlation kernel a pass over this batch's residuals will run.
+int corr_impl_for(const csb200_batch* b, int impl = IMPL_AUTO) {
+    if (impl == IMPL_AUTO) impl = b->corr_impl_env;
+    if (impl == IMPL_AUTO) impl = (b->dict->dtype != CSB200_F32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
+    return impl;
+}
+// Candidates per candidate block needed for an exact global top-`want`: the DMMA / naive passes emit per 64-atom (or
+// 32-atom) block, so min(want, 64) always suffices; the GEMV pass emits per CTA RANGE of up to GEMV_MAX_RANGE = 2048
+// atoms, and all of the global top-`want` may sit in one range, so there every range must report `want` candidates.
+int corr_candidates_for(const csb200_batch* b, int64_t want) {
+    return (int)(corr_impl_for(b) == IMPL_GEMV ? want : (want < PBLK ? want : PBLK));
+}
+
 int run_corr(csb200_batch* b, int S, int impl, bool allow_dense = false) {
     csb200_dict* d = b->dict;
     const bool f32 = d->dtype == CSB200_F32;
-    if (impl == IMPL_AUTO) impl = b->corr_impl_env;
-    if (impl == IMPL_AUTO) impl = (!f32 && b->nsig >= GEMM_MIN_SIGNALS) ? IMPL_GEMM : IMPL_GEMV;
+    impl = corr_impl_for(b, impl);
     if (impl == IMPL_GEMV) maybe_persist_dictionary(b);
     const int blk = impl == IMPL_GEMM ? corr_gemm_f64_block() : PBLK;
     const int64_t P = impl == IMPL_GEMV ? corr_gemv_blocks((int)d->N, (int)d->ld, f32, S, d->num_sms) : (d->N + blk - 1) / blk;
@@ -367,7 +379,7 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
     const size_t bell_bytes = (size_t)PERSIST_MAX_SIGNALS * d->num_sms * BELL_STRIDE * sizeof(unsigned long long);
     const size_t bell_off = cand_bytes + res_bytes, ctrl_off = bell_off + bell_bytes, dbg_off = ctrl_off + 256;
     static const bool debug = [] { const char* e = getenv("CSB200_PERSIST_DEBUG"); return e && e[0] == '1'; }();
-    const size_t dbg_bytes = debug ? (size_t)2 * 8 * (size_t)(k > 0 ? k : 1) * sizeof(long long) : 0;
+    const size_t dbg_bytes = debug ? (size_t)2 * 16 * (size_t)(k > 0 ? k : 1) * sizeof(long long) : 0;
     const size_t need = dbg_off + dbg_bytes;
     if (need > b->persist_bytes) {
         cudaFree(b->persist_scratch);
@@ -395,21 +407,29 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
     if (e != cudaSuccess) return fail_cuda(e, "persist_solve");
     b->other_launches++;
     if (debug && k > 0) {                            // per-phase cycle counts of signal 0's updater and of worker 0
-        std::vector<long long> h((size_t)2 * 8 * k);
+        constexpr int PH = 16;
+        std::vector<long long> h((size_t)2 * PH * k);
         CU_TRY(cudaMemcpyAsync(h.data(), q.dbg, dbg_bytes, cudaMemcpyDeviceToHost, b->stream));
         CU_TRY(cudaStreamSynchronize(b->stream));
-        double u[4] = {0, 0, 0, 0}, w[5] = {0, 0, 0, 0, 0};
-        int nu = 0, nw = 0;
+        double u[12] = {0}, w[5] = {0};
+        int nu = 0, nw = 0, n2 = 0;
         for (int64_t it = 1; it + 1 < k; ++it) {
-            const long long* a0 = &h[(size_t)it * 8];
-            const long long* w0 = &h[(size_t)(k + it) * 8];
-            if (a0[0] && a0[4]) { u[0] += a0[1] - a0[0]; u[1] += a0[2] - a0[1]; u[2] += a0[3] ? a0[3] - a0[2] : 0; u[3] += a0[4] - (a0[3] ? a0[3] : a0[2]); ++nu; }
-            if (w0[0] && w0[4]) { w[0] += w0[1] - w0[0]; w[1] += w0[2] - w0[1]; w[2] += w0[3] - w0[2]; w[3] += w0[4] - w0[3]; w[4] += h[(size_t)(k + it + 1) * 8] ? h[(size_t)(k + it + 1) * 8] - w0[0] : 0; ++nw; }
+            const long long* a0 = &h[(size_t)it * PH];
+            const long long* w0 = &h[(size_t)(k + it) * PH];
+            if (a0[0] && a0[4] && a0[3] && a0[9]) {
+                u[0] += a0[1] - a0[0]; u[1] += a0[2] - a0[1]; u[2] += a0[3] - a0[2];
+                u[3] += a0[5] - a0[3]; u[4] += a0[6] - a0[5]; u[5] += a0[7] - a0[6]; u[6] += a0[8] - a0[7];
+                if (a0[11]) { u[10] += a0[11] - a0[8]; ++n2; }
+                u[7] += a0[9] - (a0[11] ? a0[11] : a0[8]); u[8] += a0[10] - a0[9]; u[9] += a0[4] - a0[10];
+                ++nu;
+            }
+            if (w0[0] && w0[4]) { w[0] += w0[1] - w0[0]; w[1] += w0[2] - w0[1]; w[2] += w0[3] - w0[2]; w[3] += w0[4] - w0[3]; w[4] += h[(size_t)(k + it + 1) * PH] ? h[(size_t)(k + it + 1) * PH] - w0[0] : 0; ++nw; }
         }
         if (nu && nw)
-            fprintf(stderr, "[csb200 persist] cycles per update!: updater wait-cands %.0f | pick %.0f | fetch atom %.0f | append+publish %.0f"
-                            "  ||  worker wait-r %.0f | load r %.0f | dots %.0f | publish %.0f | whole iteration %.0f\n",
-                    u[0] / nu, u[1] / nu, u[2] / nu, u[3] / nu, w[0] / nw, w[1] / nw, w[2] / nw, w[3] / nw, w[4] / nw);
+            fprintf(stderr, "[csb200 persist] cycles/update!: updater wait-cands %.0f pick %.0f fetch %.0f | load-v+norm %.0f g %.0f hh,y %.0f v-=Ay+norm %.0f "
+                            "(2nd sweep in %d of %d: %.0f) r-update+ring %.0f T+norm %.0f tail %.0f || worker wait-r %.0f load-r %.0f dots %.0f publish %.0f iteration %.0f\n",
+                    u[0] / nu, u[1] / nu, u[2] / nu, u[3] / nu, u[4] / nu, u[5] / nu, u[6] / nu, n2, nu, n2 ? u[10] / n2 : 0.0, u[7] / nu, u[8] / nu,
+                    u[9] / nu, w[0] / nw, w[1] / nw, w[2] / nw, w[3] / nw, w[4] / nw);
     }
     return CSB200_OK;
 }
@@ -463,7 +483,7 @@ constexpr int64_t SPLIT_MIN_SIGNALS = 8192;
 bool use_omp_split(const csb200_batch* b, int64_t k) {
     const char* env = getenv("CSB200_SPLIT");
     const csb200_dict* d = b->dict;
-    if ((env && env[0] == '0') || k < 2 || b->defer_finish) return false;
+    if ((env && env[0] == '0') || k < 2) return false;
     if (d->dtype != CSB200_F64 || !d->has_map || b->nsig < SPLIT_MIN_SIGNALS) return false;
     if (b->corr_impl_env != IMPL_AUTO && b->corr_impl_env != IMPL_GEMM) return false;
     if (uses_cluster_update(b)) return false;
@@ -534,7 +554,9 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
             if (b->profile) CU_TRY(cudaEventRecord(p1, G));
             CU_TRY(cudaEventRecord(evG[h], G));
             CU_TRY(cudaStreamWaitEvent(U, evG[h], 0));
-            e = launch_omp_update(state_args_range(b, start[h], count[h], 1, 1, eps, 0), false, U);
+            StateArgs ua = state_args_range(b, start[h], count[h], 1, 1, eps, 0);
+            ua.max_smem_carveout = 1;
+            e = launch_omp_update(ua, false, U);
             if (e != cudaSuccess) return fail_cuda(e, "omp_update");
             CU_TRY(cudaEventRecord(evU[h], U));
             b->other_launches++;
@@ -1237,7 +1259,7 @@ static int run_sp(csb200_batch* b, int64_t k, double delta, int64_t maxiter) {
     if (!b->ndone) CU_TRY(cudaMalloc(&b->ndone, sizeof(int)));
     decide_gram(b, obl ? k : 4 * k);                          // sp: a few update!s of ~2k appends each
     const bool f32 = d->dtype == CSB200_F32;
-    const int S = (int)(k < PBLK ? k : PBLK);                 // per 64-atom block the whole top-k can sit in one block
+    const int S = corr_candidates_for(b, k);                  // the whole top-k may sit in one candidate block
     if ((rc = begin_solve(b))) return rc;
     CU_TRY(cudaMemsetAsync(b->ndone, 0, sizeof(int), b->stream));
     cudaError_t e = launch_reset_state(state_args(b, S, S, 0.0, 0), f32, b->stream);
@@ -1456,7 +1478,9 @@ static int64_t pipe_chunk_signals(const csb200_dict* d) {
     const int64_t tilesN = (d->N + 127) / 128;
     int64_t a = d->num_sms, b = tilesN;
     while (b) { const int64_t t = a % b; a = b; b = t; }
-    const int64_t q = d->num_sms / a;
+    // ... and an EVEN number of such groups, so that the two halves a chunk's solve is cut into (run_omp_split) are
+    // whole waves as well
+    const int64_t q = 2 * (d->num_sms / a);
     int64_t m = (16384 + 64 * q) / (128 * q);
     if (m < 1) m = 1;
     return 128 * q * m;
@@ -1823,7 +1847,6 @@ int csb200_dict_cumbabel(csb200_dict* d, int64_t k, double* mu_out) {
     double* dmu = nullptr;
     cudaError_t e = cudaMalloc(&dmu, (size_t)k * sizeof(double));
     if (e != cudaSuccess) { csb200_batch_destroy(b); return fail_cuda(e, "cudaMalloc"); }
-    const int S = (int)(k + 1 < PBLK ? k + 1 : PBLK);
     const csb200_dict* dd = b->dict;                 // the FP64 twin when the dictionary is FP32 and the chunk is a batch
     const size_t es = dd->esize();
     do {
@@ -1837,6 +1860,7 @@ int csb200_dict_cumbabel(csb200_dict* d, int64_t k, double* mu_out) {
             if (e != cudaSuccess) { rc = fail_cuda(e, "copy atoms"); break; }
             b->nsig = nc; b->has_map = false; b->cur_P = 0;
             if ((rc = ensure_signal_map(b))) break;
+            const int S = corr_candidates_for(b, k + 1);    // a tail chunk of < 24 atoms takes the GEMV pass
             if ((rc = run_corr(b, S, IMPL_AUTO, true))) break;
             e = launch_babel_reduce(state_args(b, S, S, 0.0, 0), (int)k, (int)c0, dmu, b->stream);
             if (e != cudaSuccess) { rc = fail_cuda(e, "babel_reduce"); break; }

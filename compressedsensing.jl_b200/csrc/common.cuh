@@ -81,6 +81,8 @@ struct StateArgs {
     int dense_ld = 0;           // > 0: pval is the dense |A'r| matrix [nsig][dense_ld] (no pidx); 0: per-block candidates
     double max_eps = 0.0;       // forward_step! returns false unless ||r|| > max_eps   (:60)
     double min_delta2 = 0.0;    // ... and unless min_delta^2 < max_j delta2_j          (:63)
+    int max_smem_carveout = 0;  // launch hint: ask for the SM's largest shared-memory carve-out, i.e. the configuration the
+                                // DMMA correlation kernel runs under, so that CTAs of both kernels can share an SM
 };
 // Acache (optional): ld x kcap buffer holding the active atoms' columns in selection order, with the
 // candidate's column already stored in slot nnz (column-sharded mode: the atom may live on a peer).

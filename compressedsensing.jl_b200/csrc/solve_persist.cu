@@ -33,7 +33,7 @@ namespace {
 constexpr int PT = 512;                    // threads per CTA (128 registers per thread: CG x NS accumulators fit)
 constexpr int PW = PT / 32;
 constexpr unsigned SPIN_LIMIT = 1u << 24;  // polls before a wait gives up (a few seconds): an error status, never a hung GPU
-constexpr int DBG_PHASES = 8;
+constexpr int DBG_PHASES = 16;
 constexpr unsigned BELL_STOP = 0xfffffffeu, BELL_ABORT = 0xffffffffu;   // doorbell values above every version number              // clock64() stamps per iteration and role (CSB200_PERSIST_DEBUG)
 
 // ---- hand-over without fences: every 8-byte word carries its own sequence number ("LL" words) ----------------------
@@ -288,9 +288,10 @@ struct Red3 {
 template <typename T, typename StoreR, typename AfterStore>
 __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
                                            const double* __restrict__ bs, double* __restrict__ rs, Red3& red,
-                                           StoreR store_r, AfterStore after_store, double& nr2) {
+                                           StoreR store_r, AfterStore after_store, double& nr2, long long* stamp = nullptr) {
     constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto mark = [&](int slot) { if (stamp && tid == 0) stamp[slot] = clock64(); };
     double s2 = 0.0, sb = 0.0;
     for (int row = tid * W; row < ld; row += PT * W) {
         double e[W];
@@ -299,6 +300,7 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
         for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; s2 = fma(e[q], e[q], s2); sb = fma(e[q], bs[row + q], sb); }
     }
     red.sum2(s2, sb);                                                // also publishes v to the whole CTA
+    mark(5);
     const double anorm2 = s2;
     double before2 = anorm2, rho2 = anorm2;
     for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
@@ -316,6 +318,7 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
             if (lane == 0) S.g[i] = acc;
         }
         __syncthreads();
+        if (sweep == 0) mark(6);
         for (int i = warp; i < t; i += PW) {                           // hh = R^{-T} g = Q'v: hh_i = sum_{l <= i} T[l, i] g_l
             double acc = 0.0;
             for (int l = lane; l <= i; l += 32) acc = fma(S.Tm[l + i * S.ldT], S.g[l], acc);
@@ -330,6 +333,7 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
             if (lane == 0) { S.y[i] = acc; S.ys[i] = sweep ? S.ys[i] + acc : acc; }
         }
         __syncthreads();
+        if (sweep == 0) mark(7);
         s2 = 0.0; sb = 0.0;
         for (int row = tid * W; row < ld; row += PT * W) {             // v -= A_S y on this thread's rows
             double acc[W];
@@ -347,6 +351,7 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
             for (int q = 0; q < W; ++q) { S.v[row + q] = acc[q]; s2 = fma(acc[q], acc[q], s2); sb = fma(acc[q], bs[row + q], sb); }
         }
         red.sum2(s2, sb);
+        if (sweep == 0) mark(8); else mark(11);
         rho2 = s2;
         if (rho2 >= 0.5 * before2) break;                              // DGKS: one sweep was enough
         before2 = rho2;
@@ -366,6 +371,7 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
         }
     }
     after_store();                                                     // the workers can start while ||r|| is being reduced
+    mark(9);
     for (int i = tid; i < t; i += PT) S.Tsm[i + t * S.ldT] = -S.ys[i] * irho;   // R^{-1} gains [-R^{-1}h / rho; 1 / rho]
     if (tid == 0) { S.Tsm[t + t * S.ldT] = irho; S.zs[t] = zt; S.ssel[t] = j; S.colp[t] = aj; }
     red.sum2(s2r, dummy);                                              // barrier: the new column is visible
@@ -547,7 +553,8 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                 const int dep = append_fast<T>(
                     S, t, j, aj, ld, bs, rs, red,
                     [&](int row, T val) { if (more) ResLL<T>::store(rll + (size_t)row * RW, val, rseq); },
-                    [&]() { if (more) ring((unsigned)(it + 1)); }, nr2);
+                    [&]() { if (more) ring((unsigned)(it + 1)); }, nr2, dbg ? dbg + it * DBG_PHASES : nullptr);
+                if (dbg && tid == 0) dbg[it * DBG_PHASES + 10] = clock64();
                 if (dep) flags |= 1; else { changed = true; nr = sqrt(nr2); }
             }
         }

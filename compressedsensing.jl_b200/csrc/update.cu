@@ -564,6 +564,11 @@ cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void*
     } else {
         e = cudaFuncSetAttribute(omp_update_kernel<T, UT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // An SM runs CTAs of two kernels side by side only under ONE shared-memory / L1 split: when this kernel is to run
+        // under the correlation kernel (which needs the largest carve-out) it must ask for the same split.
+        e = cudaFuncSetAttribute(omp_update_kernel<T, UT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 a.max_smem_carveout ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
+        if (e != cudaSuccess) return e;
         omp_update_kernel<T, UT, false><<<a.nsig, UT, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, 0);
     }
     return cudaGetLastError();

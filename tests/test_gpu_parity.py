@@ -583,6 +583,30 @@ def test_sp_and_oblivious_call_surface(cs, po):
             assert out[s].nzind.tolist() == ref.nzind and _close(out[s].nzval, ref.nzval, 1e-9)
 
 
+@pytest.mark.parametrize("k", [128, 256])
+def test_few_signal_topk_with_clustered_correlations(cs, po, k):
+    """One signal on a long dictionary takes the GEMV correlation pass, whose candidate blocks are CTA ranges of up to
+    2048 atoms -- not 64-atom blocks.  All of the global top-k sit in ONE range here (a cluster of adjacent atoms that
+    correlate with b): every one of them must come back (`partialsortperm(abs.(A'b), 1:k, rev=true)`,
+    src/oblivious.jl:4).  [Round-1 code clamped the per-range candidate count to 64 and silently lost the rest.]"""
+    rng = np.random.default_rng(4242 + k)
+    M, N = 288, 262144
+    A = rng.standard_normal((M, N))
+    u = rng.standard_normal(M)
+    lo = 70000
+    A[:, lo:lo + k + 40] = u[:, None] + 0.6 * A[:, lo:lo + k + 40]            # k + 40 adjacent atoms correlate with u
+    A /= np.sqrt((A * A).sum(axis=0, keepdims=True))
+    A = np.asfortranarray(A)
+    b = u / np.linalg.norm(u)
+    got, ref = cs.oblivious(A, b, k), po.oblivious(A, b, k)
+    assert lo <= min(ref.nzind) and max(ref.nzind) < lo + k + 40               # the premise: one cluster holds them all
+    assert got.nzind.tolist() == ref.nzind
+    assert _close(got.nzval, ref.nzval, 1e-8)
+    if 2 * k <= M:
+        got, ref = cs.sp(A, b, k, 1e-12, 2), po.sp(A, b, k, 1e-12, 2)
+        assert got.nzind.tolist() == ref.nzind and _close(got.nzval, ref.nzval, 1e-8)
+
+
 @pytest.mark.parametrize("gram", ["0", "1"])
 def test_sp_midsize_batch_vs_oracle(cs, po, gram, monkeypatch):
     monkeypatch.setenv("CSB200_GRAM", gram)
