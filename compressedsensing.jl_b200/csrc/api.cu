@@ -528,6 +528,8 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
     for (int h = 0; h < 2; ++h)
         if ((rc = make_operand_map(&mapR[h], static_cast<char*>(b->dR) + (size_t)start[h] * d->ld * 8, d->ld, count[h]))) return rc;
     cudaStream_t G = b->sp_gemm, U = b->sp_upd;
+    static const bool dbg_split = [] { const char* e = getenv("CSB200_SPLIT_DEBUG"); return e && e[0] == '1'; }();
+    std::vector<cudaEvent_t> dbg_ev;
     cudaEvent_t ev_start = b->sp_ev[0], *evG = &b->sp_ev[1], *evU = &b->sp_ev[3], ev_end = b->sp_ev[5];
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), false, b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "reset_state");
@@ -556,14 +558,27 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
             CU_TRY(cudaStreamWaitEvent(U, evG[h], 0));
             StateArgs ua = state_args_range(b, start[h], count[h], 1, 1, eps, 0);
             ua.max_smem_carveout = 1;
+            if (dbg_split) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); CU_TRY(cudaEventRecord(ev, U)); dbg_ev.push_back(ev); }
             e = launch_omp_update(ua, false, U);
             if (e != cudaSuccess) return fail_cuda(e, "omp_update");
+            if (dbg_split) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); CU_TRY(cudaEventRecord(ev, U)); dbg_ev.push_back(ev); }
             CU_TRY(cudaEventRecord(evU[h], U));
             b->other_launches++;
         }
     }
     CU_TRY(cudaEventRecord(ev_end, U));                                  // U's last update follows every G launch
     CU_TRY(cudaStreamWaitEvent(b->stream, ev_end, 0));
+    if (dbg_split) {                                                     // how long did the updates take under the passes?
+        CU_TRY(cudaStreamSynchronize(b->stream));
+        double tot = 0, mx = 0, mn = 1e30;
+        for (size_t i = 0; i + 1 < dbg_ev.size(); i += 2) {
+            float ms = 0; cudaEventElapsedTime(&ms, dbg_ev[i], dbg_ev[i + 1]);
+            tot += ms; mx = ms > mx ? ms : mx; mn = ms < mn ? ms : mn;
+        }
+        fprintf(stderr, "[csb200 split] %zu update launches: total %.2f ms, min %.3f, max %.3f ms each (alone: ~0.75 ms per half at the headline config)\n",
+                dbg_ev.size() / 2, tot, mn, mx);
+        for (auto ev : dbg_ev) cudaEventDestroy(ev);
+    }
     return CSB200_OK;
 }
 

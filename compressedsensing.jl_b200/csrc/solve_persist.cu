@@ -162,7 +162,9 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
             for (int s = 0; s < ns; ++s) { all_stop = all_stop && s_state[s] == 1; error = error || s_state[s] == 2; }
             if (all_stop || error) break;
             if (dbg && tid == 0) dbg[it * DBG_PHASES + 1] = clock64();
-            for (int e = tid; e < ns * ld; e += PT) {
+            const int total = ns * ld, shift = (int)(((long long)w * 64) % total);   // workers start at different rows: all
+            for (int e0 = tid; e0 < total; e0 += PT) {                               // 147 of them read the same words
+                const int e = e0 + shift < total ? e0 + shift : e0 + shift - total;
                 const int s = e / ld;
                 if (s_state[s] != 0) continue;                            // a stopped signal keeps its last residual
                 const unsigned long long* p = a.r_ll + (size_t)e * RW;
@@ -260,31 +262,57 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
 }
 
 // ---- updater: the loop body of `update!` for one signal, state resident in shared memory ---------------------------
-// Block reductions of one or two values with ONE barrier each: three scratch rows used in rotation (a row is not
+// FP64 add / fma results are available ~40 cycles after issue on this part, so every DEPENDENT chain in the updater is
+// kept short: block reductions are a 5-level shuffle tree plus a 4-level register tree over the 16 warp partials (not a
+// 16-long serial sum), dot products run on 4 independent accumulators, and the two triangular mat-vecs of an append
+// are done by one warp without block barriers.
+__device__ __forceinline__ double tree_sum16(const double* row) {
+    double v[PW];
+#pragma unroll
+    for (int q = 0; q < PW; ++q) v[q] = row[q];
+#pragma unroll
+    for (int w = PW / 2; w > 0; w >>= 1)
+#pragma unroll
+        for (int q = 0; q < w; ++q) v[q] += v[q + w];
+    return v[0];
+}
+// Block reductions of up to three values with ONE barrier each: three scratch rows used in rotation (a row is not
 // rewritten before two further barriers have passed).
 struct Red3 {
-    double* buf;      // [3][2][PW]
+    double* buf;      // [3][3][PW]
     int phase;
-    __device__ __forceinline__ void sum2(double& a, double& b) {
+    __device__ __forceinline__ void sum3(double& a, double& b, double& c) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        a = warp_sum(a); b = warp_sum(b);
-        double* row = buf + (size_t)phase * 2 * PW;
-        if (lane == 0) { row[warp] = a; row[PW + warp] = b; }
-        __syncthreads();
-        double sa = 0.0, sb = 0.0;
 #pragma unroll
-        for (int q = 0; q < PW; ++q) { sa += row[q]; sb += row[PW + q]; }
-        a = sa; b = sb;
+        for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+            c += __shfl_xor_sync(0xffffffffu, c, off);
+        }
+        double* row = buf + (size_t)phase * 3 * PW;
+        if (lane == 0) { row[warp] = a; row[PW + warp] = b; row[2 * PW + warp] = c; }
+        __syncthreads();
+        a = tree_sum16(row); b = tree_sum16(row + PW); c = tree_sum16(row + 2 * PW);
+        phase = phase == 2 ? 0 : phase + 1;
+    }
+    __device__ __forceinline__ void sum1(double& a) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        double* row = buf + (size_t)phase * 3 * PW;
+        if (lane == 0) row[warp] = a;
+        __syncthreads();
+        a = tree_sum16(row);
         phase = phase == 2 ? 0 : phase + 1;
     }
 };
 
 // `add_column!(AiQR, a, pos)` + the residual down-date for ONE atom, specialised for this kernel (reference:
 // src/util.jl:118-126, src/matchingpursuit.jl:152-176; same mathematics as append_atom in update_common.cuh: implicit Q,
-// CGS with DGKS re-orthogonalisation, R^{-1} stored).  Differences that matter when ONE signal is on the critical path
-// of 147 waiting SMs: a thread owns fixed rows of v / b / r (no barrier between the row-wise phases), the triangular
-// mat-vecs are warp-parallel dot products instead of one serial chain per output, <v, b> rides with ||v||^2, every
-// reduction costs one barrier, and the new residual leaves for the workers (store_r) before its norm is reduced.
+// CGS with DGKS re-orthogonalisation, R^{-1} stored).  ONE signal is on the critical path of 147 waiting SMs here, so:
+// a thread owns fixed rows of v / b / r (no barrier between the row-wise phases); ||a||^2, ||v||^2 and <v, b> share one
+// reduction; the triangular mat-vecs run in one warp (lane = output, 4 accumulators); and the new residual leaves for
+// the workers (store_r / after_store) before its norm is reduced.
 template <typename T, typename StoreR, typename AfterStore>
 __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
                                            const double* __restrict__ bs, double* __restrict__ rs, Red3& red,
@@ -292,75 +320,120 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
     constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto mark = [&](int slot) { if (stamp && tid == 0) stamp[slot] = clock64(); };
-    double s2 = 0.0, sb = 0.0;
+    double sa = 0.0, sb = 0.0, s2 = 0.0;
     for (int row = tid * W; row < ld; row += PT * W) {
         double e[W];
         RowVec<T>::load(aj + row, e);
 #pragma unroll
-        for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; s2 = fma(e[q], e[q], s2); sb = fma(e[q], bs[row + q], sb); }
+        for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; sa = fma(e[q], e[q], sa); sb = fma(e[q], bs[row + q], sb); }
     }
-    red.sum2(s2, sb);                                                // also publishes v to the whole CTA
+    double anorm2 = 0.0, rho2 = 0.0, before2 = 0.0;
+    if (t == 0) {                                                      // first atom: nothing to orthogonalise against
+        s2 = sa;
+        red.sum3(s2, sb, sa);
+        anorm2 = rho2 = sa;
+    } else {
+        __syncthreads();                                               // v is complete
+    }
     mark(5);
-    const double anorm2 = s2;
-    double before2 = anorm2, rho2 = anorm2;
     for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
         for (int i = warp; i < t; i += PW) {                           // g = A_S' v, one warp per active atom
             const T* ai = S.colp[i];
-            double acc = 0.0;
-#pragma unroll 4
-            for (int row = lane * W; row < ld; row += 32 * W) {
-                double e[W];
-                RowVec<T>::load(ai + row, e);
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            int row = lane * W;
+            for (; row + 32 * W < ld; row += 64 * W) {                 // two steps per trip, four independent chains
+                double e0[W], e1[W];
+                RowVec<T>::load(ai + row, e0);
+                RowVec<T>::load(ai + row + 32 * W, e1);
 #pragma unroll
-                for (int q = 0; q < W; ++q) acc = fma(e[q], S.v[row + q], acc);
+                for (int q = 0; q < W; ++q) {
+                    acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
+                    acc[2 + (q & 1)] = fma(e1[q], S.v[row + 32 * W + q], acc[2 + (q & 1)]);
+                }
             }
-            acc = warp_sum(acc);
-            if (lane == 0) S.g[i] = acc;
+            if (row < ld) {
+                double e0[W];
+                RowVec<T>::load(ai + row, e0);
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
+            }
+            double g = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            g = warp_sum(g);
+            if (lane == 0) S.g[i] = g;
         }
         __syncthreads();
         if (sweep == 0) mark(6);
-        for (int i = warp; i < t; i += PW) {                           // hh = R^{-T} g = Q'v: hh_i = sum_{l <= i} T[l, i] g_l
-            double acc = 0.0;
-            for (int l = lane; l <= i; l += 32) acc = fma(S.Tm[l + i * S.ldT], S.g[l], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) S.hh[i] = acc;
-        }
-        __syncthreads();
-        for (int i = warp; i < t; i += PW) {                           // y = R^{-1} hh: y_i = sum_{l >= i} T[i, l] hh_l
-            double acc = 0.0;
-            for (int l = i + lane; l < t; l += 32) acc = fma(S.Tm[i + l * S.ldT], S.hh[l], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) { S.y[i] = acc; S.ys[i] = sweep ? S.ys[i] + acc : acc; }
+        if (warp == 0) {
+            // hh = R^{-T} g = Q'v (hh_i = sum_{l <= i} T[l, i] g_l) and y = R^{-1} hh (y_i = sum_{l >= i} T[i, l] hh_l):
+            // lane = output index, no block barrier in between
+            for (int i = lane; i < t; i += 32) {
+                double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+                const double* col = S.Tm + (size_t)i * S.ldT;
+                int l = 0;
+                for (; l + 3 <= i; l += 4) {
+                    h0 = fma(col[l], S.g[l], h0); h1 = fma(col[l + 1], S.g[l + 1], h1);
+                    h2 = fma(col[l + 2], S.g[l + 2], h2); h3 = fma(col[l + 3], S.g[l + 3], h3);
+                }
+                for (; l <= i; ++l) h0 = fma(col[l], S.g[l], h0);
+                S.hh[i] = (h0 + h1) + (h2 + h3);
+            }
+            __syncwarp();
+            for (int i = lane; i < t; i += 32) {
+                double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+                const double* rowp = S.Tm + i;
+                int l = i;
+                for (; l + 3 < t; l += 4) {
+                    h0 = fma(rowp[(size_t)l * S.ldT], S.hh[l], h0); h1 = fma(rowp[(size_t)(l + 1) * S.ldT], S.hh[l + 1], h1);
+                    h2 = fma(rowp[(size_t)(l + 2) * S.ldT], S.hh[l + 2], h2); h3 = fma(rowp[(size_t)(l + 3) * S.ldT], S.hh[l + 3], h3);
+                }
+                for (; l < t; ++l) h0 = fma(rowp[(size_t)l * S.ldT], S.hh[l], h0);
+                const double y = (h0 + h1) + (h2 + h3);
+                S.y[i] = y;
+                S.ys[i] = sweep ? S.ys[i] + y : y;
+            }
         }
         __syncthreads();
         if (sweep == 0) mark(7);
         s2 = 0.0; sb = 0.0;
         for (int row = tid * W; row < ld; row += PT * W) {             // v -= A_S y on this thread's rows
-            double acc[W];
+            double acc[2][W];
 #pragma unroll
-            for (int q = 0; q < W; ++q) acc[q] = S.v[row + q];
-#pragma unroll 4
-            for (int i = 0; i < t; ++i) {
-                double e[W];
-                RowVec<T>::load(S.colp[i] + row, e);
-                const double yi = S.y[i];
+            for (int q = 0; q < W; ++q) { acc[0][q] = S.v[row + q]; acc[1][q] = 0.0; }
+            int i = 0;
+#pragma unroll 2
+            for (; i + 1 < t; i += 2) {
+                double e0[W], e1[W];
+                RowVec<T>::load(S.colp[i] + row, e0);
+                RowVec<T>::load(S.colp[i + 1] + row, e1);
+                const double y0 = S.y[i], y1 = S.y[i + 1];
 #pragma unroll
-                for (int q = 0; q < W; ++q) acc[q] = fma(-e[q], yi, acc[q]);
+                for (int q = 0; q < W; ++q) { acc[0][q] = fma(-e0[q], y0, acc[0][q]); acc[1][q] = fma(-e1[q], y1, acc[1][q]); }
+            }
+            if (i < t) {
+                double e0[W];
+                RowVec<T>::load(S.colp[i] + row, e0);
+                const double y0 = S.y[i];
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[0][q] = fma(-e0[q], y0, acc[0][q]);
             }
 #pragma unroll
-            for (int q = 0; q < W; ++q) { S.v[row + q] = acc[q]; s2 = fma(acc[q], acc[q], s2); sb = fma(acc[q], bs[row + q], sb); }
+            for (int q = 0; q < W; ++q) {
+                const double vq = acc[0][q] + acc[1][q];
+                S.v[row + q] = vq; s2 = fma(vq, vq, s2); sb = fma(vq, bs[row + q], sb);
+            }
         }
-        red.sum2(s2, sb);
-        if (sweep == 0) mark(8); else mark(11);
+        red.sum3(s2, sb, sa);                                          // ||v||^2, <v, b>, ||a||^2 (the first sweep's pass reduces it)
+        if (sweep == 0) { anorm2 = sa; before2 = sa; mark(8); } else mark(11);
         rho2 = s2;
         if (rho2 >= 0.5 * before2) break;                              // DGKS: one sweep was enough
         before2 = rho2;
+        sa = 0.0;
     }
     if (!(rho2 > 1e-26 * anorm2)) return 1;                            // numerically dependent atom: not appended
-    const double rho = sqrt(rho2), irho = 1.0 / rho;
+    const double irho = rsqrt(rho2);                                   // 1 / rho (<= 1 ulp), no division on the critical path
     const double zt = sb * irho;                                       // z_t = q_t' b
     const double gam = zt * irho;
-    double s2r = 0.0, dummy = 0.0;
+    double s2r = 0.0;
     for (int row = tid * W; row < ld; row += PT * W) {                 // r <- r - q_t z_t on this thread's rows
 #pragma unroll
         for (int q = 0; q < W; ++q) {
@@ -374,7 +447,7 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
     mark(9);
     for (int i = tid; i < t; i += PT) S.Tsm[i + t * S.ldT] = -S.ys[i] * irho;   // R^{-1} gains [-R^{-1}h / rho; 1 / rho]
     if (tid == 0) { S.Tsm[t + t * S.ldT] = irho; S.zs[t] = zt; S.ssel[t] = j; S.colp[t] = aj; }
-    red.sum2(s2r, dummy);                                              // barrier: the new column is visible
+    red.sum1(s2r);                                                     // barrier: the new column is visible
     nr2 = s2r;
     ++t;
     return 0;
@@ -415,7 +488,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
     const unsigned seq0 = a.epoch << 16;
     long long* dbg = (a.dbg && sig == 0) ? a.dbg : nullptr;
 
-    double s2 = 0.0, unused = 0.0;
+    double s2 = 0.0;
     int bad = 0;
     for (int row = tid; row < ld; row += PT) {      // r = b: the state of a freshly constructed MP / OMP object
         const T e = b[row];
@@ -424,7 +497,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
         bad |= !isfinite((double)e);
     }
     if (tid == 0) s_fail = 0;
-    red.sum2(s2, unused);
+    red.sum1(s2);
     double nr = sqrt(s2);
     int t = 0, flags = 0, iters = 0;
     bool done = false, failed = false;
@@ -494,7 +567,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
 #pragma unroll
                     for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; s = fma(e[q], rs[row + q], s); }
                 }
-                red.sum2(s, unused);
+                red.sum1(s);
                 c = s;                                                   // dot(view(A,:,i), r)  (:29)
                 s2 = 0.0;
                 for (int row = tid * W; row < ld; row += PT * W) {
@@ -507,7 +580,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                     }
                 }
                 if (more) ring((unsigned)(it + 1));
-                red.sum2(s2, unused);
+                red.sum1(s2);
                 nr = sqrt(s2);
             } else {
                 flags |= 2;
@@ -593,7 +666,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
 template <typename T, int NS, int CG>
 __global__ void __launch_bounds__(PT, 1) persist_solve_kernel(PersistArgs a) {
     extern __shared__ __align__(16) unsigned char psm[];
-    __shared__ double red_v[NS < 6 ? 6 : NS][PW];                        // workers: [NS][PW]; updater: Red3's [3][2][PW]
+    __shared__ double red_v[NS < 9 ? 9 : NS][PW];                        // workers: [NS][PW]; updater: Red3's [3][3][PW]
     __shared__ int red_i[NS][PW];
     __shared__ int s_state[PERSIST_MAX_SIGNALS];
     if ((int)blockIdx.x < a.ns) persist_updater<T>(a, psm, &red_v[0][0]);
