@@ -529,6 +529,7 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
         if ((rc = make_operand_map(&mapR[h], static_cast<char*>(b->dR) + (size_t)start[h] * d->ld * 8, d->ld, count[h]))) return rc;
     cudaStream_t G = b->sp_gemm, U = b->sp_upd;
     static const bool dbg_split = [] { const char* e = getenv("CSB200_SPLIT_DEBUG"); return e && e[0] == '1'; }();
+    static const unsigned spacer_ns = [] { const char* e = getenv("CSB200_SPLIT_SPACER_US"); return (unsigned)((e ? atof(e) : 25.0) * 1e3); }();
     std::vector<cudaEvent_t> dbg_ev;
     cudaEvent_t ev_start = b->sp_ev[0], *evG = &b->sp_ev[1], *evU = &b->sp_ev[3], ev_end = b->sp_ev[5];
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), false, b->stream);
@@ -556,6 +557,15 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
             if (b->profile) CU_TRY(cudaEventRecord(p1, G));
             CU_TRY(cudaEventRecord(evG[h], G));
             CU_TRY(cudaStreamWaitEvent(U, evG[h], 0));
+            // The update becomes runnable at the very moment the OTHER half's correlation pass does (both wait for this
+            // pass to end).  Were its 32 768 CTAs to reach the idle SMs first they would fill them eight deep and the
+            // pass's CTAs (193 KiB of shared memory each) would have to wait for seven of the eight to drain: measured
+            // 0.4 ms lost per pass.  A 25 us sleep in front of the update lets the pass place its CTAs first; the update
+            // then trickles in one CTA per SM next to them.
+            if (spacer_ns > 0 && !(it + 1 == k && h == 1)) {
+                e = launch_spacer(spacer_ns, U);
+                if (e != cudaSuccess) return fail_cuda(e, "spacer");
+            }
             StateArgs ua = state_args_range(b, start[h], count[h], 1, 1, eps, 0);
             ua.max_smem_carveout = 1;
             if (dbg_split) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); CU_TRY(cudaEventRecord(ev, U)); dbg_ev.push_back(ev); }

@@ -141,6 +141,7 @@ size_t sp_update_smem_bytes(int ld, int kcap);
 cudaError_t launch_colnorms(const void* A, bool f32, int ld, int N, double* out, cudaStream_t st);
 cudaError_t launch_babel_reduce(const StateArgs& a, int k, int col0, double* mu, cudaStream_t st);
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st);
+cudaError_t launch_spacer(unsigned ns, cudaStream_t st);   // a one-warp kernel that sleeps for ns nanoseconds
 cudaError_t launch_mp_warmstart(const StateArgs& a, bool f32, const int* x0_idx, const double* x0_val,
                                 const int* x0_nnz, int x0_stride, cudaStream_t st);
 cudaError_t launch_topk_from_partials(const StateArgs& a, int s, long long* out_idx, double* out_val,

@@ -103,7 +103,7 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
     using V = typename Vec<T>::type;
     constexpr int W = Vec<T>::W;
     constexpr int RW = ResLL<T>::WORDS;
-    constexpr int UNR = CG * NS >= 32 ? 1 : (CG * NS >= 16 ? 2 : 4);   // loads in flight vs the 128-register budget
+    constexpr int UNR = CG * NS >= 32 ? 1 : (CG * NS >= 16 ? 2 : (CG * NS >= 4 ? 4 : 8));   // loads in flight vs the 128-register budget
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld, ns = a.ns;
     const int w = (int)blockIdx.x - ns;
@@ -316,17 +316,23 @@ struct Red3 {
 template <typename T, typename StoreR, typename AfterStore>
 __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
                                            const double* __restrict__ bs, double* __restrict__ rs, Red3& red,
-                                           StoreR store_r, AfterStore after_store, double& nr2, long long* stamp = nullptr) {
+                                           StoreR store_r, AfterStore after_store, double& nr2, const T* acache, int ucache,
+                                           long long* stamp = nullptr) {
     constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto mark = [&](int slot) { if (stamp && tid == 0) stamp[slot] = clock64(); };
+    // active atom i: slot i of this CTA's shared-memory cache (address computed, so the loads are LDS -- a pointer
+    // fetched from the colp table makes them generic loads at ~3x the latency) or, beyond the cache, the dictionary
+    const int tc = t < ucache ? t : ucache;
     double sa = 0.0, sb = 0.0, s2 = 0.0;
+    const T* ajs = t < ucache ? acache + (size_t)t * ld : aj;          // the new atom sits in cache slot t when it fits
     for (int row = tid * W; row < ld; row += PT * W) {
         double e[W];
-        RowVec<T>::load(aj + row, e);
+        if (t < ucache) RowVec<T>::load(acache + (size_t)t * ld + row, e); else RowVec<T>::load(aj + row, e);
 #pragma unroll
         for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; sa = fma(e[q], e[q], sa); sb = fma(e[q], bs[row + q], sb); }
     }
+    (void)ajs;
     double anorm2 = 0.0, rho2 = 0.0, before2 = 0.0;
     if (t == 0) {                                                      // first atom: nothing to orthogonalise against
         s2 = sa;
@@ -338,25 +344,27 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
     mark(5);
     for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
         for (int i = warp; i < t; i += PW) {                           // g = A_S' v, one warp per active atom
-            const T* ai = S.colp[i];
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            int row = lane * W;
-            for (; row + 32 * W < ld; row += 64 * W) {                 // two steps per trip, four independent chains
-                double e0[W], e1[W];
-                RowVec<T>::load(ai + row, e0);
-                RowVec<T>::load(ai + row + 32 * W, e1);
+            auto dot = [&](const T* ai) {
+                int row = lane * W;
+                for (; row + 32 * W < ld; row += 64 * W) {             // two steps per trip, four independent chains
+                    double e0[W], e1[W];
+                    RowVec<T>::load(ai + row, e0);
+                    RowVec<T>::load(ai + row + 32 * W, e1);
 #pragma unroll
-                for (int q = 0; q < W; ++q) {
-                    acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
-                    acc[2 + (q & 1)] = fma(e1[q], S.v[row + 32 * W + q], acc[2 + (q & 1)]);
+                    for (int q = 0; q < W; ++q) {
+                        acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
+                        acc[2 + (q & 1)] = fma(e1[q], S.v[row + 32 * W + q], acc[2 + (q & 1)]);
+                    }
                 }
-            }
-            if (row < ld) {
-                double e0[W];
-                RowVec<T>::load(ai + row, e0);
+                if (row < ld) {
+                    double e0[W];
+                    RowVec<T>::load(ai + row, e0);
 #pragma unroll
-                for (int q = 0; q < W; ++q) acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
-            }
+                    for (int q = 0; q < W; ++q) acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
+                }
+            };
+            if (i < tc) dot(acache + (size_t)i * ld); else dot(S.colp[i]);
             double g = (acc[0] + acc[1]) + (acc[2] + acc[3]);
             g = warp_sum(g);
             if (lane == 0) S.g[i] = g;
@@ -401,15 +409,23 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
             for (int q = 0; q < W; ++q) { acc[0][q] = S.v[row + q]; acc[1][q] = 0.0; }
             int i = 0;
 #pragma unroll 2
-            for (; i + 1 < t; i += 2) {
+            for (; i + 1 < tc; i += 2) {                                // cached atoms: shared-memory loads, two chains
                 double e0[W], e1[W];
-                RowVec<T>::load(S.colp[i] + row, e0);
-                RowVec<T>::load(S.colp[i + 1] + row, e1);
+                RowVec<T>::load(acache + (size_t)i * ld + row, e0);
+                RowVec<T>::load(acache + (size_t)(i + 1) * ld + row, e1);
                 const double y0 = S.y[i], y1 = S.y[i + 1];
 #pragma unroll
                 for (int q = 0; q < W; ++q) { acc[0][q] = fma(-e0[q], y0, acc[0][q]); acc[1][q] = fma(-e1[q], y1, acc[1][q]); }
             }
-            if (i < t) {
+            if (i < tc) {
+                double e0[W];
+                RowVec<T>::load(acache + (size_t)i * ld + row, e0);
+                const double y0 = S.y[i];
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[0][q] = fma(-e0[q], y0, acc[0][q]);
+                ++i;
+            }
+            for (; i < t; ++i) {                                       // beyond the cache: from the dictionary (L2)
                 double e0[W];
                 RowVec<T>::load(S.colp[i] + row, e0);
                 const double y0 = S.y[i];
@@ -473,7 +489,11 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
     double* Tsm = p; p += (size_t)kcap * ldT;
     S.ssel = reinterpret_cast<int*>(p);
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
-    T* acache = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(S.colp + kcap) + 15) & ~(uintptr_t)15);   // [ucache][ld]
+    // [ucache][ld] after the tables, 16-byte aligned; the offset is computed arithmetically so that the compiler keeps
+    // the shared address space (LDS) for these loads
+    const size_t acache_off = (((size_t)(3 * ld + 5 * kcap + (size_t)kcap * ldT) * sizeof(double) +
+                                (size_t)((kcap + 1) & ~1) * sizeof(int) + (size_t)kcap * sizeof(void*)) + 15) & ~(size_t)15;
+    T* acache = reinterpret_cast<T*>(smem + acache_off);
     S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red_buf;
     Red3 red{red_buf, 0};
     __shared__ int s_j, s_fail, s_ci[PW];
@@ -626,7 +646,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                 const int dep = append_fast<T>(
                     S, t, j, aj, ld, bs, rs, red,
                     [&](int row, T val) { if (more) ResLL<T>::store(rll + (size_t)row * RW, val, rseq); },
-                    [&]() { if (more) ring((unsigned)(it + 1)); }, nr2, dbg ? dbg + it * DBG_PHASES : nullptr);
+                    [&]() { if (more) ring((unsigned)(it + 1)); }, nr2, acache, a.ucache, dbg ? dbg + it * DBG_PHASES : nullptr);
                 if (dbg && tid == 0) dbg[it * DBG_PHASES + 10] = clock64();
                 if (dep) flags |= 1; else { changed = true; nr = sqrt(nr2); }
             }

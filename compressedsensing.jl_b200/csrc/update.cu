@@ -645,6 +645,24 @@ cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride,
     return cudaGetLastError();
 }
 
+// One warp that sleeps for `ns` nanoseconds: keeps a stream's next kernel from becoming runnable for that long (see
+// run_omp_split in api.cu: the update of one half must not grab the SMs before the other half's correlation pass has
+// placed its CTAs).
+__global__ void spacer_kernel(unsigned ns) {
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            __nanosleep(2000);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < ns);
+    }
+}
+cudaError_t launch_spacer(unsigned ns, cudaStream_t st) {
+    spacer_kernel<<<1, 32, 0, st>>>(ns);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_reset_state(const StateArgs& a, bool f32, cudaStream_t st) {
     if (a.nsig <= 0) return cudaSuccess;
     if (f32) reset_state_kernel<float><<<a.nsig, UT, 0, st>>>(a);
