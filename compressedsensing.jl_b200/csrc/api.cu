@@ -529,7 +529,7 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
         if ((rc = make_operand_map(&mapR[h], static_cast<char*>(b->dR) + (size_t)start[h] * d->ld * 8, d->ld, count[h]))) return rc;
     cudaStream_t G = b->sp_gemm, U = b->sp_upd;
     static const bool dbg_split = [] { const char* e = getenv("CSB200_SPLIT_DEBUG"); return e && e[0] == '1'; }();
-    static const unsigned spacer_ns = [] { const char* e = getenv("CSB200_SPLIT_SPACER_US"); return (unsigned)((e ? atof(e) : 25.0) * 1e3); }();
+    static const unsigned spacer_ns = [] { const char* e = getenv("CSB200_SPLIT_SPACER_US"); return (unsigned)((e ? atof(e) : 0.0) * 1e3); }();
     std::vector<cudaEvent_t> dbg_ev;
     cudaEvent_t ev_start = b->sp_ev[0], *evG = &b->sp_ev[1], *evU = &b->sp_ev[3], ev_end = b->sp_ev[5];
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), false, b->stream);
@@ -557,11 +557,10 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
             if (b->profile) CU_TRY(cudaEventRecord(p1, G));
             CU_TRY(cudaEventRecord(evG[h], G));
             CU_TRY(cudaStreamWaitEvent(U, evG[h], 0));
-            // The update becomes runnable at the very moment the OTHER half's correlation pass does (both wait for this
-            // pass to end).  Were its 32 768 CTAs to reach the idle SMs first they would fill them eight deep and the
-            // pass's CTAs (193 KiB of shared memory each) would have to wait for seven of the eight to drain: measured
-            // 0.4 ms lost per pass.  A 25 us sleep in front of the update lets the pass place its CTAs first; the update
-            // then trickles in one CTA per SM next to them.
+            // Experiment hook (CSB200_SPLIT_SPACER_US, default 0 = off): a short sleep in front of the update so that the
+            // other half's pass places its CTAs before the update's 32 768 CTAs reach the idle SMs.  Measured: it does not
+            // help -- the update, at one CTA per SM under the pass, needs about as long as the pass itself, so the head
+            // start it gets without the spacer is worth more than the tidy placement.
             if (spacer_ns > 0 && !(it + 1 == k && h == 1)) {
                 e = launch_spacer(spacer_ns, U);
                 if (e != cudaSuccess) return fail_cuda(e, "spacer");
@@ -587,6 +586,15 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
         }
         fprintf(stderr, "[csb200 split] %zu update launches: total %.2f ms, min %.3f, max %.3f ms each (alone: ~0.75 ms per half at the headline config)\n",
                 dbg_ev.size() / 2, tot, mn, mx);
+        if (b->profile && b->ev_used >= 4) {                             // timeline of the first update!s (ms since the first pass began)
+            const size_t g0 = b->ev_used - (size_t)4 * k;                // this solve's 2k (start, stop) pairs
+            for (size_t i = 0; i < 8 && 2 * i + 1 < dbg_ev.size(); ++i) {
+                float gs = 0, ge = 0, us = 0, ue = 0;
+                cudaEventElapsedTime(&gs, b->ev[g0], b->ev[g0 + 2 * i]); cudaEventElapsedTime(&ge, b->ev[g0], b->ev[g0 + 2 * i + 1]);
+                cudaEventElapsedTime(&us, b->ev[g0], dbg_ev[2 * i]); cudaEventElapsedTime(&ue, b->ev[g0], dbg_ev[2 * i + 1]);
+                fprintf(stderr, "[csb200 split]   launch %zu (half %zu): pass %.3f .. %.3f   update %.3f .. %.3f\n", i, i & 1, gs, ge, us, ue);
+            }
+        }
         for (auto ev : dbg_ev) cudaEventDestroy(ev);
     }
     return CSB200_OK;

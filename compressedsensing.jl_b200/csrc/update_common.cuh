@@ -16,10 +16,16 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    double s = 0.0;
+    // pairwise tree over the warp partials: a dependent FP64 add costs ~50 cycles here, and a CTA that shares its SM with
+    // the correlation pass (api.cu run_omp_split) has no other warps to hide a serial chain behind
+    double p[NT / 32];
 #pragma unroll
-    for (int w = 0; w < NT / 32; ++w) s += red[w];
-    return s;
+    for (int w = 0; w < NT / 32; ++w) p[w] = red[w];
+#pragma unroll
+    for (int h = NT / 64; h > 0; h >>= 1)
+#pragma unroll
+        for (int w = 0; w < h; ++w) p[w] += p[w + h];
+    return p[0];
 }
 
 // Global top-`take` over this signal's P*S per-block candidates -> s_cand[0..take) (atom or -1).
@@ -344,17 +350,27 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
         if (sweep == 0 && gcol) {
             for (int i = tid; i < t; i += NT) S.g[i] = gcol[S.ssel[i] - idx_offset];   // g = (A'A)[S, j]
         } else {
-            for (int i = warp; i < t; i += NT / 32) {              // g = A_S' v
+            for (int i = warp; i < t; i += NT / 32) {              // g = A_S' v (four independent FMA chains per lane)
                 const T* ai = S.colp[i];
-                double s = 0.0;
-#pragma unroll 4
-                for (int row = lane * W; row < ld; row += 32 * W) {
-                    double a[W];
-                    RowVec<T>::load(ai + row, a);
+                double s0 = 0.0, s1 = 0.0, s2b = 0.0, s3 = 0.0;
+                int row = lane * W;
+                for (; row + 32 * W < ld; row += 64 * W) {
+                    double a0[W], a1[W];
+                    RowVec<T>::load(ai + row, a0);
+                    RowVec<T>::load(ai + row + 32 * W, a1);
 #pragma unroll
-                    for (int e = 0; e < W; ++e) s = fma(a[e], S.v[row + e], s);
+                    for (int e = 0; e < W; e += 2) {
+                        s0 = fma(a0[e], S.v[row + e], s0); s1 = fma(a0[e + 1], S.v[row + e + 1], s1);
+                        s2b = fma(a1[e], S.v[row + 32 * W + e], s2b); s3 = fma(a1[e + 1], S.v[row + 32 * W + e + 1], s3);
+                    }
                 }
-                s = warp_sum(s);
+                if (row < ld) {
+                    double a0[W];
+                    RowVec<T>::load(ai + row, a0);
+#pragma unroll
+                    for (int e = 0; e < W; e += 2) { s0 = fma(a0[e], S.v[row + e], s0); s1 = fma(a0[e + 1], S.v[row + e + 1], s1); }
+                }
+                double s = warp_sum((s0 + s1) + (s2b + s3));
                 if (lane == 0) S.g[i] = s;
             }
         }
@@ -362,14 +378,27 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
         // hh = R^{-T} g = Q'v and y = R^{-1} hh as two triangular mat-vecs with the stored inverse:
         // no substitution chain, every output element is an independent dot product.
         for (int i = tid; i < t; i += NT) {
-            double acc = 0.0;
-            for (int l = 0; l <= i; ++l) acc = fma(S.Tm[l + i * S.ldT], S.g[l], acc);
-            S.hh[i] = acc;
+            double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+            const double* col = S.Tm + (size_t)i * S.ldT;
+            int l = 0;
+            for (; l + 3 <= i; l += 4) {
+                h0 = fma(col[l], S.g[l], h0); h1 = fma(col[l + 1], S.g[l + 1], h1);
+                h2 = fma(col[l + 2], S.g[l + 2], h2); h3 = fma(col[l + 3], S.g[l + 3], h3);
+            }
+            for (; l <= i; ++l) h0 = fma(col[l], S.g[l], h0);
+            S.hh[i] = (h0 + h1) + (h2 + h3);
         }
         __syncthreads();
         for (int i = tid; i < t; i += NT) {
-            double acc = 0.0;
-            for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.hh[l], acc);
+            double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+            const double* rowp = S.Tm + i;
+            int l = i;
+            for (; l + 3 < t; l += 4) {
+                h0 = fma(rowp[(size_t)l * S.ldT], S.hh[l], h0); h1 = fma(rowp[(size_t)(l + 1) * S.ldT], S.hh[l + 1], h1);
+                h2 = fma(rowp[(size_t)(l + 2) * S.ldT], S.hh[l + 2], h2); h3 = fma(rowp[(size_t)(l + 3) * S.ldT], S.hh[l + 3], h3);
+            }
+            for (; l < t; ++l) h0 = fma(rowp[(size_t)l * S.ldT], S.hh[l], h0);
+            const double acc = (h0 + h1) + (h2 + h3);
             S.y[i] = acc;
             S.ys[i] = sweep ? S.ys[i] + acc : acc;
         }
@@ -379,16 +408,28 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
             double acc[W];
 #pragma unroll
             for (int e = 0; e < W; ++e) acc[e] = S.v[row + e];
-#pragma unroll 4
-            for (int i = 0; i < t; ++i) {
-                double a[W];
-                RowVec<T>::load(S.colp[i] + row, a);
-                const double yi = S.y[i];
+            double acc1[W];
 #pragma unroll
-                for (int e = 0; e < W; ++e) acc[e] = fma(-a[e], yi, acc[e]);
+            for (int e = 0; e < W; ++e) acc1[e] = 0.0;
+            int i = 0;
+#pragma unroll 2
+            for (; i + 1 < t; i += 2) {                             // two independent chains per row
+                double a0[W], a1[W];
+                RowVec<T>::load(S.colp[i] + row, a0);
+                RowVec<T>::load(S.colp[i + 1] + row, a1);
+                const double y0 = S.y[i], y1 = S.y[i + 1];
+#pragma unroll
+                for (int e = 0; e < W; ++e) { acc[e] = fma(-a0[e], y0, acc[e]); acc1[e] = fma(-a1[e], y1, acc1[e]); }
+            }
+            if (i < t) {
+                double a0[W];
+                RowVec<T>::load(S.colp[i] + row, a0);
+                const double y0 = S.y[i];
+#pragma unroll
+                for (int e = 0; e < W; ++e) acc[e] = fma(-a0[e], y0, acc[e]);
             }
 #pragma unroll
-            for (int e = 0; e < W; ++e) { S.v[row + e] = acc[e]; s2 = fma(acc[e], acc[e], s2); }
+            for (int e = 0; e < W; ++e) { acc[e] += acc1[e]; S.v[row + e] = acc[e]; s2 = fma(acc[e], acc[e], s2); }
         }
         rho2 = block_sum<NT>(s2, S.red);
         if (rho2 >= 0.5 * before2) break;                          // DGKS: one sweep was enough
