@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Secondary measurements for the BASELINE.json configs that are not the bench.py headline (C1, C3, C4, C5).
+"""Secondary measurements kept beside bench.py (which now measures every BASELINE config itself: `bench.py --config
+c1|c2s|c3|c4|c5`, and all of them inside the default line's `secondary` object).  What remains unique here: `fr2` and
+`sp2` (the widened rows at the config-2 shape) and the older per-config printouts the round-1 profiles quote.
 
     python tools/bench_configs.py --config c1|c3|c4|c5 [--scale f]
     python -m torch.distributed.run --nproc-per-node 8 ... tools/bench_configs.py --config c4     (column-sharded)
@@ -28,30 +30,15 @@ FP64_PEAK = json.load(open(os.path.join(ROOT, "profiles", "FP64_PEAK.json")))["p
 
 
 def make_problem(M, N, k, B, dtype, dev, seed=1234, noise=0.0):
-    g = torch.Generator(device=dev).manual_seed(seed)
-    A_t = torch.empty(N, M, dtype=torch.float64, device=dev)
-    for n0 in range(0, N, 65536):
-        n1 = min(N, n0 + 65536)
-        blk = torch.randn(n1 - n0, M, dtype=torch.float64, device=dev, generator=g)
-        blk -= 1e-6 * blk.mean(dim=1, keepdim=True)
-        blk /= blk.norm(dim=1, keepdim=True)
-        A_t[n0:n1] = blk
-    idx = torch.stack([torch.randperm(N, device=dev, generator=g)[:k] for _ in range(min(B, 64))])
-    if B > 64:
-        idx = torch.cat([idx, torch.randint(0, N, (B - 64, k), device=dev, generator=g)])   # rare repeats are harmless
-    sign = torch.randint(0, 2, (B, k), device=dev, generator=g).to(torch.float64) * 2 - 1
-    B_t = torch.empty(B, M, dtype=torch.float64, device=dev)
-    step = max(1, (1 << 26) // (k * M))
-    for s0 in range(0, B, step):
-        s1 = min(B, s0 + step)
-        B_t[s0:s1] = (A_t[idx[s0:s1]] * sign[s0:s1, :, None]).sum(dim=1)
-    if noise:
-        e = torch.randn(B, M, dtype=torch.float64, device=dev, generator=g)
-        B_t += e * (noise / e.norm(dim=1, keepdim=True))
-    td = torch.float32 if dtype == np.float32 else torch.float64
-    A_np = A_t.to(td).cpu().numpy().T
-    B_np = B_t.to(td).cpu().numpy().T
-    return A_np, B_np, idx.cpu().numpy()
+    """Synthetic problem generated on the device (bench.make_problem): Gaussian unit-norm atoms, planted k-sparse +-1
+    signals whose k atoms are DISTINCT (sampled without replacement, `sparse_vector`, src/util.jl:13-19)."""
+    import bench
+
+    class _Ctx:
+        pass
+    ctx = _Ctx()
+    ctx.torch, ctx.dev = torch, dev
+    return bench.make_problem(ctx, M, N, k, B, dtype, seed=seed, noise=noise)
 
 
 def cpu_oracle(fn, n):
