@@ -91,6 +91,7 @@ def _load() -> ctypes.CDLL:
         "csb200_fr": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_double, c_double, i64p, f64p, i64p, f64p,
                               i64p]),
         "csb200_batch_download": (c_int, [c_void_p, c_int64, i64p, f64p, i64p, f64p, i64p]),
+        "csb200_batch_flags": (c_int, [c_void_p, POINTER(ctypes.c_int32)]),
         "csb200_batch_profile": (c_int, [c_void_p, c_int]),
         "csb200_batch_corr_time": (c_int, [c_void_p, f64p, i64p, i64p]),
         "csb200_batch_last_solve_ms": (c_int, [c_void_p, f64p]),
@@ -124,7 +125,7 @@ EXPORTED_SYMBOLS = [
     "csb200_version", "csb200_strerror", "csb200_last_error", "csb200_device_count", "csb200_dict_create",
     "csb200_dict_create_shard", "csb200_dict_create_multi", "csb200_dict_devices", "csb200_dict_destroy", "csb200_dict_trim", "csb200_dict_shape", "csb200_batch_create",
     "csb200_batch_destroy", "csb200_batch_upload", "csb200_batch_upload_device", "csb200_batch_omp",
-    "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_profile",
+    "csb200_batch_gomp", "csb200_batch_mp", "csb200_batch_download", "csb200_batch_flags", "csb200_batch_profile",
     "csb200_batch_corr_time", "csb200_batch_last_solve_ms", "csb200_omp", "csb200_gomp", "csb200_mp",
     "csb200_assemble_csc", "csb200_comm_unique_id", "csb200_batch_fr", "csb200_fr",
     "csb200_batch_sp", "csb200_batch_oblivious", "csb200_sp", "csb200_oblivious", "csb200_dict_colnorms",
@@ -305,6 +306,13 @@ class Batch:
         its = np.empty(ns, dtype=np.int64)
         _check(lib.csb200_batch_download(self._h, stride, _i64p(sel), _f64p(coef), _i64p(nnz), _f64p(res), _i64p(its)))
         return sel, coef, nnz, res, its
+
+    def flags(self) -> np.ndarray:
+        """Per-signal diagnostic bits of the last solve (`csb200_batch_flags`): 1 dependent atom skipped, 2 no
+        candidate, 16 ill-conditioned support (coefficients refined)."""
+        out = np.zeros(self.nsig, dtype=np.int32)
+        _check(lib.csb200_batch_flags(self._h, out.ctypes.data_as(POINTER(ctypes.c_int32))))
+        return out
 
     def profile(self, enable: bool) -> None:
         _check(lib.csb200_batch_profile(self._h, 1 if enable else 0))

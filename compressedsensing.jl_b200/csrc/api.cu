@@ -1427,6 +1427,18 @@ int csb200_batch_download(csb200_batch* b, int64_t stride, int64_t* sel_idx, dou
     return convert_results(ns, kc, stride, hn, hs, hit, hx, hres, sel_idx, coef, nnz, resnorm, iters);
 }
 
+int csb200_batch_flags(csb200_batch* b, int32_t* flags) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (!flags) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    if ((rc = set_device(b->dict))) return rc;
+    static_assert(sizeof(int) == sizeof(int32_t), "flag words are 32-bit");
+    CU_TRY(cudaMemcpyAsync(flags, b->flags, (size_t)b->nsig * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CU_TRY(cudaStreamSynchronize(b->stream));
+    return CSB200_OK;
+}
+
 int csb200_batch_profile(csb200_batch* b, int enable) {
     if (!b) return CSB200_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(b->mu);

@@ -446,6 +446,7 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
         sa = 0.0;
     }
     if (!(rho2 > 1e-26 * anorm2)) return 1;                            // numerically dependent atom: not appended
+    if (rho2 < ILLCOND_RATIO * anorm2) S.illcond = 1;
     const double irho = rsqrt(rho2);                                   // 1 / rho (<= 1 ulp), no division on the critical path
     const double zt = sb * irho;                                       // z_t = q_t' b
     const double gam = zt * irho;
@@ -669,9 +670,12 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
         for (int i = tid; i < t; i += PT) {                              // x_S = R^{-1} Q'b  (`ldiv!`, :175)
             double acc = 0.0;
             for (int l = i; l < t; ++l) acc = fma(Tsm[i + l * ldT], S.zs[l], acc);
-            a.x[(size_t)sig * a.stride + i] = acc;
+            S.ys[i] = acc;
             a.sel[(size_t)sig * a.stride + i] = S.ssel[i];
         }
+        if (S.illcond) { flags |= FLAG_ILLCOND; refine_coefficients<T, PT>(S, t, ld, [&](int row) { return bs[row]; }, S.ys); }
+        else __syncthreads();
+        for (int i = tid; i < t; i += PT) a.x[(size_t)sig * a.stride + i] = S.ys[i];
     }
     for (int row = tid; row < ld; row += PT) rg[row] = (T)rs[row];       // the residual where the batch keeps it
     if (tid == 0) {

@@ -192,9 +192,12 @@ __global__ void __launch_bounds__(ST, 2) small_solve_kernel(StateArgs a, SmallSo
         for (int i = tid; i < t; i += ST) {                              // x_S = R^{-1} Q'b  (`ldiv!`, :175)
             double acc = 0.0;
             for (int l = i; l < t; ++l) acc = fma(Tsm[i + l * ldT], S.zs[l], acc);
-            a.x[(size_t)sig * q.stride + i] = acc;
+            S.ys[i] = acc;
             a.sel[(size_t)sig * q.stride + i] = S.ssel[i];
         }
+        if (S.illcond) { flags |= FLAG_ILLCOND; refine_coefficients<T, ST>(S, t, ld, [&](int row) { return bs[row]; }, S.ys); }
+        else __syncthreads();
+        for (int i = tid; i < t; i += ST) a.x[(size_t)sig * q.stride + i] = S.ys[i];
     }
     for (int row = tid; row < ld; row += ST) rg[row] = (T)rs[row];
     if (tid == 0) {

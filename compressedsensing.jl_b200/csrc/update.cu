@@ -201,13 +201,18 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
 
     double nr = a.resnorm[sig];
     if (changed) {
+        const bool ill = S.illcond || (a.flags[sig] & FLAG_ILLCOND);
+        if (S.illcond) flags |= FLAG_ILLCOND;
         for (int i = tid; i < t; i += NT) {                        // x_S = R^{-1} Q'b  (`ldiv!`, :175)
             double acc = 0.0;
             for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.zs[l], acc);
-            a.x[(size_t)sig * kcap + i] = acc;
+            S.ys[i] = acc;
             a.sel[(size_t)sig * kcap + i] = S.ssel[i];
             a.z[(size_t)sig * kcap + i] = S.zs[i];
         }
+        if (ill) refine_coefficients<T, NT>(S, t, ld, b_at, S.ys);   // CTA-uniform branch
+        else __syncthreads();
+        for (int i = tid; i < t; i += NT) a.x[(size_t)sig * kcap + i] = S.ys[i];
         nr = sqrt(nr2);
     }
     if (tid == 0) {
@@ -341,8 +346,12 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
         for (int i = tid; i < t; i += NT) {                       // x' = R^{-1} Q'b on the enlarged support
             double acc = 0.0;
             for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.zs[l], acc);
-            S.y[i] = fabs(acc);
+            S.ys[i] = acc;
         }
+        if (S.illcond) refine_coefficients<T, NT>(S, t, ld, b_at, S.ys);      // the ranking below must see accurate |x|
+        else __syncthreads();
+        for (int i = tid; i < t; i += NT) S.y[i] = fabs(S.ys[i]);
+        S.illcond = 0;                                            // the kept atoms are re-factorised from scratch
         __syncthreads();
         const int drop = t - k;
         for (int i = tid; i < t; i += NT) {                       // rank by (|x|, atom index): the `drop` smallest leave
@@ -371,10 +380,13 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
     for (int i = tid; i < t; i += NT) {                            // x_S = R^{-1} Q'b
         double acc = 0.0;
         for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.zs[l], acc);
-        a.x[(size_t)sig * kcap + i] = acc;
+        S.ys[i] = acc;
         a.sel[(size_t)sig * kcap + i] = S.ssel[i];
         a.z[(size_t)sig * kcap + i] = S.zs[i];
     }
+    if (S.illcond) { flags |= FLAG_ILLCOND; refine_coefficients<T, NT>(S, t, ld, b_at, S.ys); }   // CTA-uniform
+    else __syncthreads();
+    for (int i = tid; i < t; i += NT) a.x[(size_t)sig * kcap + i] = S.ys[i];
     if (tid == 0) {
         const double old = a.resnorm[sig], nr = sqrt(nr2);
         a.nnz[sig] = t;

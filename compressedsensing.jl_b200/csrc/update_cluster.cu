@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
                 s2 = 0.0;
             }
             if (!(rho2 > 1e-26 * anorm2)) { flags |= 1; continue; }        // numerically dependent atom
+            if (rho2 < ILLCOND_RATIO * anorm2) flags |= FLAG_ILLCOND;      // see refine_coefficients (update_common.cuh)
             const double rho = sqrt(rho2);
             const double zt = vb / rho;                                    // z_t = q_t' b
             const double gam = zt / rho;
@@ -267,13 +268,53 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
         }
     }
 
+    // cluster-uniform: every CTA saw the same appends
+    const bool ill = changed && ((flags & FLAG_ILLCOND) || (a.flags[sig] & FLAG_ILLCOND));
+    if (changed) {
+        for (int i = tid; i < t; i += CT) {                                // x_S = R^{-1} Q'b, on every CTA
+            double acc = 0.0;
+            for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], zs[l], acc);
+            ys[i] = acc;
+        }
+        __syncthreads();
+    }
+    if (ill) {
+        // ill-conditioned support: two steps of iterative refinement, x += R^{-1} R^{-T} A_S' (b - A_S x), as in
+        // refine_coefficients (update_common.cuh) with the rows split over the cluster and one all-reduce per step
+        for (int rep = 0; rep < 2; ++rep) {
+            for (int row = tid; row < Mc; row += CT) {
+                double acc = (double)b[row];
+                for (int i = 0; i < t; ++i) acc = fma(-(double)colp[i][row], ys[i], acc);
+                v[row] = acc;
+            }
+            __syncthreads();
+            for (int i = warp; i < t; i += CT / 32) {
+                const T* ai = colp[i];
+                double s = 0.0;
+                for (int row = lane; row < Mc; row += 32) s = fma((double)ai[row], v[row], s);
+                s = warp_sum(s);
+                if (lane == 0) g[i] = s;
+            }
+            cluster_allreduce<CL>(cl, ex, g, t, gs);
+            for (int i = tid; i < t; i += CT) {
+                double acc = 0.0;
+                for (int l = 0; l <= i; ++l) acc = fma(Tm[l + i * ldT], gs[l], acc);
+                hh[i] = acc;
+            }
+            __syncthreads();
+            for (int i = tid; i < t; i += CT) {
+                double acc = 0.0;
+                for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], hh[l], acc);
+                ys[i] += acc;
+            }
+            __syncthreads();
+        }
+    }
     if (crank == 0) {
         double nr = a.resnorm[sig];
         if (changed) {
-            for (int i = tid; i < t; i += CT) {                            // x_S = R^{-1} Q'b
-                double acc = 0.0;
-                for (int l = i; l < t; ++l) acc = fma(Tm[i + l * ldT], zs[l], acc);
-                a.x[(size_t)sig * kcap + i] = acc;
+            for (int i = tid; i < t; i += CT) {
+                a.x[(size_t)sig * kcap + i] = ys[i];
                 a.sel[(size_t)sig * kcap + i] = ssel[i];
                 a.z[(size_t)sig * kcap + i] = zs[i];
             }

@@ -326,7 +326,70 @@ struct PursuitSmem {
     double* Tg;       // global copy of R^{-1} (ld = kcap) or nullptr
     int kcap;
     double* red;      // [NT/32] reduction scratch
+    int illcond = 0;  // set by append_atom when an atom kept less than ILLCOND_RATIO of its squared norm (CTA-uniform)
 };
+
+// x = R^{-1} z through the STORED INVERSE has a forward error of about cond(A_S)^2 eps (x is O(1) while ||R^{-1}|| ||z|| is
+// O(cond): the products cancel), where the reference's back substitution on a Givens QR gives cond(A_S) eps.  Measured
+// (tools/conditioning_study.py): invisible on Gaussian dictionaries (cond(A_S) ~ 1.4), 4e-9 at cond 2e4, 5e-5 at 2e6.
+// A support is marked ill-conditioned when an appended atom keeps less than this fraction of its squared norm after
+// orthogonalisation (cond(A_S) >~ 30); its coefficients are then refined, see refine_coefficients.  State flag bit 16.
+constexpr double ILLCOND_RATIO = 1e-3;
+constexpr int FLAG_ILLCOND = 16;
+
+// Iterative refinement of the least-squares coefficients of an ill-conditioned support (corrected semi-normal
+// equations): with the explicit residual rr = b - A_S x,   x += R^{-1} R^{-T} A_S' rr,   twice.  Each step shrinks the
+// error by ~cond^2 eps, so two steps reach the cond eps level of a backward-stable QR for cond(A_S) up to ~1e6 (at 1e7
+// and beyond the stored inverse itself is too inaccurate to correct with; the flag stays set so the caller can tell).
+// x: [t] in shared memory (in / out); uses S.v, S.g, S.hh, S.y as scratch.  b_at(row) as in append_atom.
+template <typename T, int NT, typename BAt>
+__device__ void refine_coefficients(PursuitSmem<T>& S, int t, int ld, BAt b_at, double* x) {
+    constexpr int W = RowVec<T>::W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    for (int rep = 0; rep < 2; ++rep) {
+        for (int row = tid * W; row < ld; row += NT * W) {             // rr = b - A_S x
+            double acc[W];
+#pragma unroll
+            for (int e = 0; e < W; ++e) acc[e] = b_at(row + e);
+            for (int i = 0; i < t; ++i) {
+                double a[W];
+                RowVec<T>::load(S.colp[i] + row, a);
+                const double xi = x[i];
+#pragma unroll
+                for (int e = 0; e < W; ++e) acc[e] = fma(-a[e], xi, acc[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < W; ++e) S.v[row + e] = acc[e];
+        }
+        __syncthreads();
+        for (int i = warp; i < t; i += NT / 32) {                      // g = A_S' rr
+            const T* ai = S.colp[i];
+            double s0 = 0.0, s1 = 0.0;
+            for (int row = lane * W; row < ld; row += 32 * W) {
+                double a[W];
+                RowVec<T>::load(ai + row, a);
+#pragma unroll
+                for (int e = 0; e < W; e += 2) { s0 = fma(a[e], S.v[row + e], s0); s1 = fma(a[e + 1], S.v[row + e + 1], s1); }
+            }
+            const double s = warp_sum(s0 + s1);
+            if (lane == 0) S.g[i] = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < t; i += NT) {                            // hh = R^{-T} g
+            double acc = 0.0;
+            for (int l = 0; l <= i; ++l) acc = fma(S.Tm[l + i * S.ldT], S.g[l], acc);
+            S.hh[i] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < t; i += NT) {                            // x += R^{-1} hh
+            double acc = 0.0;
+            for (int l = i; l < t; ++l) acc = fma(S.Tm[i + l * S.ldT], S.hh[l], acc);
+            x[i] += acc;
+        }
+        __syncthreads();
+    }
+}
 
 // `add_column!(AiQR, a, pos)` + the residual part of `ldiv!!` / `residual!` for ONE new atom (reference:
 // src/util.jl:118-126, src/matchingpursuit.jl:152-176), by the whole CTA:
@@ -436,6 +499,7 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
         before2 = rho2;
     }
     if (!(rho2 > 1e-26 * anorm2)) return 1;                        // numerically dependent atom: not appended
+    if (rho2 < ILLCOND_RATIO * anorm2) S.illcond = 1;
     const double rho = sqrt(rho2);
     double sb = 0.0;
     for (int row = tid; row < ld; row += NT) sb += S.v[row] * b_at(row);

@@ -143,6 +143,15 @@ int csb200_batch_oblivious(csb200_batch* batch, int64_t k);
 int csb200_batch_download(csb200_batch* batch, int64_t stride, int64_t* sel_idx, double* coef,
                           int64_t* nnz, double* resnorm, int64_t* iters);
 
+/* Per-signal diagnostics of the last solve (nsig 32-bit words), a bit set:
+ *   1   an atom that won the arg-max was numerically dependent on the active set (rho^2 <= 1e-26 ||a||^2) and was NOT
+ *       appended -- the reference's add_column! would divide by a ~0 diagonal here;
+ *   2   the correlation pass produced no candidate (all-NaN correlations cannot happen on finite input; kept for safety);
+ *   16  the active set is ill-conditioned (an appended atom kept < 1e-3 of its squared norm after orthogonalisation,
+ *       cond(A_S) >~ 30): the coefficients were refined by two steps of iterative refinement, which restores the
+ *       ~cond(A_S) eps accuracy of a backward-stable QR up to cond ~1e6; beyond that treat them as approximate. */
+int csb200_batch_flags(csb200_batch* batch, int32_t* flags);
+
 /* Timing of the dominant kernel (the correlation pass), measured with CUDA events on the
  * batch's own stream.  enable != 0 turns per-launch event recording on and clears the
  * counters; csb200_batch_corr_time returns the summed duration (ms) and launch count since. */

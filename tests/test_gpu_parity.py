@@ -751,6 +751,8 @@ def test_gomp_block_append_and_near_dependent_atoms(cs, po, block, monkeypatch):
         batch.upload(Bm)
         batch.gomp(l, k, 0.0)
         sel, coef, nnz, res, its = batch.download(k)
+        fl = batch.flags()
+    assert fl[0] & 16 and not (fl[3:] & 16).any()      # the twin support is flagged ill-conditioned (and refined), no other
     for s in range(0, B, 3):
         t = po.Trace()
         ref = po.gomp(A, Bm[:, s], l, k, eps=0.0, trace=t)
@@ -758,7 +760,9 @@ def test_gomp_block_append_and_near_dependent_atoms(cs, po, block, monkeypatch):
         assert sel[s, :n].tolist() == t.order(), (s, sel[s, :n], t.order())
         idx, val = _sorted(sel[s], coef[s], n)
         assert idx.tolist() == ref.nzind
-        assert _close(val, ref.nzval, 1e-6 if s == 0 else RTOL64), (s, val, ref.nzval)
+        # cond(A_S) ~ 1e3 for signal 0: after the iterative refinement the coefficients are at the 1e-10 bar as well
+        # (round 1 needed 1e-6 here: x = R^{-1} z through the stored inverse alone is cond^2 eps accurate)
+        assert _close(val, ref.nzval, RTOL64), (s, val, ref.nzval)
         assert abs(res[s] - t.resnorm[-1]) < 1e-9
 
 
