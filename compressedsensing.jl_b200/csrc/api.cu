@@ -1155,13 +1155,13 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     csb200_dict* d = b->dict;
     if (k < 0 || l < 1 || l > d->n_total) return CSB200_ERR_INVALID_ARG;
     if (!(eps >= 0)) return CSB200_ERR_NEGATIVE_EPS;
-    if (l > MAX_S) { g_last_error = "l > 64 atoms per update is not supported by the fused top-s epilogue"; return CSB200_ERR_UNSUPPORTED; }
+    if (l > GOMP_MAX_L) { g_last_error = "gomp: l > 256 atoms per update is not supported"; return CSB200_ERR_UNSUPPORTED; }
     int64_t need = k < d->M ? k : d->M;
     if (d->n_total < need) need = d->n_total;
     if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
-    if (use_small_solve(b)) {
+    if (l <= MAX_S && use_small_solve(b)) {
         if ((rc = run_small_solve(b, 1, k, l, eps, nullptr, nullptr, nullptr, 0))) return rc;
         return finish(b, true);
     }
@@ -1179,16 +1179,18 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
         cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
         if (e != cudaSuccess) return fail_cuda(e, "reset_state");
         for (int64_t it = 0; it < k / l; ++it) {
-            int rc2 = run_corr(b, (int)l, IMPL_AUTO, dense_ok);
+            const int Sc = corr_candidates_for(b, l);            // candidates per candidate block (<= the block size)
+            int rc2 = run_corr(b, Sc, IMPL_AUTO, dense_ok);
             if (rc2) return rc2;
-            e = update_launch(b, state_args(b, (int)l, (int)l, eps, 0), f32);
+            e = update_launch(b, state_args(b, Sc, (int)l, eps, 0), f32);
             if (e != cudaSuccess) return fail_cuda(e, "gomp_update");
             b->other_launches++;
         }
         if (rem > 0) {                               // runs even after an eps-break (matchingpursuit.jl:134-137)
-            int rc2 = run_corr(b, rem, IMPL_AUTO, dense_ok);
+            const int Sc = corr_candidates_for(b, rem);
+            int rc2 = run_corr(b, Sc, IMPL_AUTO, dense_ok);
             if (rc2) return rc2;
-            e = update_launch(b, state_args(b, rem, rem, eps, 1), f32);
+            e = update_launch(b, state_args(b, Sc, rem, eps, 1), f32);
             if (e != cudaSuccess) return fail_cuda(e, "gomp_update(rem)");
             b->other_launches++;
         }

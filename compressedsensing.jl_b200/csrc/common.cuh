@@ -11,7 +11,8 @@ namespace csb {
 // kernel emits, per (atom block, signal), the top-s candidates of that block.  One record
 // per candidate: |c| as double (FP32 dictionaries widen) and the GLOBAL 0-based atom index.
 constexpr int PBLK = 64;
-constexpr int MAX_S = 64;          // atoms per gomp update handled by the fused epilogue
+constexpr int MAX_S = 64;          // candidates per 64-atom block the fused DMMA epilogue can emit (= the block size)
+constexpr int GOMP_MAX_L = 256;    // atoms per gomp update! (l); larger l: CSB200_ERR_UNSUPPORTED
 constexpr int ROW_ALIGN = 16;      // leading dimensions are padded to 16 elements (128 B for f64)
 
 // Candidate order shared by every kernel: larger |c| first, lower index on ties

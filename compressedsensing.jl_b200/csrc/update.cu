@@ -45,6 +45,7 @@ __host__ __device__ inline size_t block_region_elems(int bm, int ld) {
     return e < (size_t)DENSE_HIST / 2 ? (size_t)DENSE_HIST / 2 : e;
 }
 
+constexpr int MAX_TAKE = 256;       // atoms per acquisition the update kernels handle (l of gomp, k of sp / oblivious / cumbabel)
 constexpr int UT = 128;            // threads per CTA
 constexpr int UW = UT / 32;
 
@@ -80,8 +81,8 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     double* Tsm = reinterpret_cast<double*>(S.colp + kcap);        // [kcap][ldT] inverse factor (optional)
     __shared__ double red[NT / 32];
     __shared__ int red_i[NT / 32];
-    __shared__ int s_cand[MAX_S];
-    __shared__ double s_cval[MAX_S];
+    __shared__ int s_cand[MAX_TAKE];
+    __shared__ double s_cval[MAX_TAKE];
     __shared__ int s_J[BLOCK_MAX];
     __shared__ const T* s_Jcol[BLOCK_MAX];
 
@@ -128,7 +129,7 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     if (t < a.M) {                                                 // `nnz(x) < size(P.A, 1) || return x` (:63,:117)
         if constexpr (BLOCK) {
             // the block working set is idle during the selection: its first 8 KB serve as histogram, the rest as staging
-            select_any<NT>(a, sig, a.take, MAX_S, s_cand, s_cval, red, red_i, reinterpret_cast<int*>(Vb),
+            select_any<NT>(a, sig, a.take, MAX_TAKE, s_cand, s_cval, red, red_i, reinterpret_cast<int*>(Vb),
                            Vb + DENSE_HIST / 2, (int)block_region_elems(bm, ld) - DENSE_HIST / 2);
         } else {                                                   // one atom per update: always per-block candidates
             const size_t cbase = (size_t)sig * a.P * a.S;
@@ -235,7 +236,6 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
 // first = 1 is the initial `sp_acquisition!(P, x, P.k)` of `sp` (:108) -- which is also all of `oblivious`.
 // Both least-squares problems reuse the block append of gomp (two gather sweeps per 8 atoms); the pruned
 // problem is re-factorised from scratch from r = b, as the reference's `factorize!` does (qr! on a copy).
-constexpr int MAX_TAKE = 256;       // atoms per acquisition handled by this kernel (k of sp / oblivious)
 
 template <typename T, int NT, typename BAt, typename RAt, typename RSet>
 __device__ __forceinline__ int append_list(PursuitSmem<T>& S, int& t, const int* list, int count, bool skip_active,
@@ -551,14 +551,14 @@ size_t update_smem_bytes(int ld, int kcap, bool t_in_smem, int bm) {
 
 // atoms orthogonalised together by the block path for this shape (0 = block path not used)
 // Dynamic shared memory one CTA may use if two are to fit on an SM: 228 KB per SM, 1 KB reserved per CTA, minus the
-// kernel's static shared memory (ptxas -v: 960 B for the gomp block kernel, 4304 B for sp_update_kernel).
+// kernel's static shared memory (ptxas -v: 3264 B for the gomp block kernel, 4304 B for sp_update_kernel).
 constexpr size_t two_cta_dyn_smem(size_t static_bytes) { return (228 * 1024 - 2 * 1024) / 2 - static_bytes; }
 
 int block_width(int ld, int kcap, int take) {
     if (take < 2) return 0;
     const bool t_in = kcap <= T_SMEM_MAX_K;
     int bm = take < BLOCK_MAX ? take : BLOCK_MAX;
-    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > two_cta_dyn_smem(1024)) --bm;   // keep 2 CTAs per SM
+    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > two_cta_dyn_smem(3584)) --bm;   // keep 2 CTAs per SM
     return bm >= 2 ? bm : 0;
 }
 

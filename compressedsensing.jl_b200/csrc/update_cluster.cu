@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(CT, 1) omp_update_cluster_kernel(StateArgs a, 
     double* Tsm = reinterpret_cast<double*>(colp + kcap);
     __shared__ double red[CT / 32];
     __shared__ int red_i[CT / 32];
-    __shared__ int s_cand[MAX_S];
-    __shared__ double s_cval[MAX_S];
+    __shared__ int s_cand[GOMP_MAX_L];
+    __shared__ double s_cval[GOMP_MAX_L];
 
     const int sig = blockIdx.x / CL;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -766,6 +766,34 @@ def test_gomp_block_append_and_near_dependent_atoms(cs, po, block, monkeypatch):
         assert abs(res[s] - t.resnorm[-1]) < 1e-9
 
 
+@pytest.mark.parametrize("nsig", [40, 2])
+def test_gomp_many_atoms_per_update(cs, po, nsig, monkeypatch):
+    """`gomp(A, b, l, k)` takes any l (src/matchingpursuit.jl:189-193: `partialsortperm(P.Ar, 1:k, rev=true)`); round 1
+    stopped at l = 64.  l = 128 on a batch (dense |A'r| + radix select in the block-append kernel) and on two signals
+    (GEMV pass with l candidates per CTA range + cluster update) against the oracle; l = 257 is refused cleanly."""
+    monkeypatch.setenv("CSB200_SMALL_SOLVE", "0")
+    rng = np.random.default_rng(900 + nsig)
+    M, N, l, k = 384, 3000, 128, 256
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, 60, nsig, noise=1e-2)
+    with cs.Dictionary(A) as D, cs.Batch(D, nsig, k) as batch:
+        batch.upload(Bm)
+        batch.gomp(l, k, 0.0)
+        sel, coef, nnz, res, its = batch.download(k)
+        with pytest.raises(cs.CSB200Error) as ei:
+            batch.gomp(257, 257, 0.0)
+        assert ei.value.status == -7
+    for s in range(min(nsig, 4)):
+        t = po.Trace()
+        ref = po.gomp(A, Bm[:, s], l, k, eps=0.0, trace=t)
+        n = int(nnz[s])
+        assert n == ref.nnz() == k and int(its[s]) == t.iterations
+        assert sel[s, :n].tolist() == t.order(), (s, "selection sequence", min(t.margin))
+        idx, val = _sorted(sel[s], coef[s], n)
+        assert idx.tolist() == ref.nzind and _close(val, ref.nzval, 1e-9)
+        assert abs(res[s] - t.resnorm[-1]) < 1e-9
+
+
 def test_gomp_and_mp_midsize_vs_oracle(cs, po):
     rng = np.random.default_rng(77)
     M, N, k, B = 256, 2048, 16, 64
