@@ -360,6 +360,9 @@ bool use_persist_solve(const csb200_batch* b, int mode) {
     for (const char* hook : {"CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM"})
         if (getenv(hook)) return false;
     if (b->nsig < 1 || path_nsig(b->nsig) > PERSIST_MAX_SIGNALS || d->n_total != d->N) return false;
+    // dictionaries the one-CTA-per-signal kernel takes (<= 2 MiB) stay there: measured 84 us against 96 us at config 1
+    // (the hand-over through L2 costs more than the 256 KiB dictionary's correlation pass saves)
+    if (!forced && small_solve_eligible((int)d->ld, (int)d->N, (int)b->kcap, (int)path_nsig(b->nsig), d->dtype == CSB200_F32)) return false;
     if ((size_t)d->ld * d->N * d->esize() > PERSIST_MAX_DICT_BYTES) return false;
     return persist_plan((int)d->ld, (int)d->N, (int)b->kcap, (int)b->nsig, d->dtype == CSB200_F32, d->num_sms, nullptr, nullptr);
 }
