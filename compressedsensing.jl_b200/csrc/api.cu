@@ -345,6 +345,34 @@ int run_small_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double eps,
     return CSB200_OK;
 }
 
+// <= 8 signals on a dictionary that fits the shared memory of one 8-CTA cluster (config 1): the cluster-resident
+// whole-solve kernel (solve_small.cu).  CSB200_CLUSTER_SOLVE=0 disables it, =1 forces it where the shape allows; an
+// explicit CSB200_SMALL_SOLVE / CSB200_PERSIST (tests select the path they exercise) takes precedence.
+bool use_cluster_solve(const csb200_batch* b, int64_t take) {
+    const csb200_dict* d = b->dict;
+    const char* env = getenv("CSB200_CLUSTER_SOLVE");
+    if (env && env[0] == '0') return false;
+    const bool forced = env && env[0] == '1';
+    if (!forced && (getenv("CSB200_SMALL_SOLVE") || getenv("CSB200_PERSIST"))) return false;
+    if (b->corr_impl_env != IMPL_AUTO || b->profile || d->n_total != d->N) return false;
+    for (const char* hook : {"CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM"})
+        if (getenv(hook)) return false;
+    if (path_nsig(b->nsig) > 8) return false;
+    return cluster_solve_eligible((int)d->ld, (int)d->N, (int)b->kcap, (int)b->nsig, (int)take, d->dtype == CSB200_F32);
+}
+
+int run_cluster_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double eps) {
+    int rc = begin_solve_fwd(b);
+    if (rc) return rc;
+    SmallSolveArgs q;
+    q.mode = mode; q.k = (int)k; q.l = (int)l; q.eps = eps; q.stride = (int)b->kcap;
+    q.x0_idx = nullptr; q.x0_val = nullptr; q.x0_nnz = nullptr; q.x0_stride = 0;
+    cudaError_t e = launch_cluster_solve(state_args(b, 1, 1, eps, 0), q, b->dict->dtype == CSB200_F32, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "cluster_solve");
+    b->other_launches++;
+    return CSB200_OK;
+}
+
 // Few signals (<= PERSIST_MAX_SIGNALS) on a dictionary up to about the L2 size: the whole omp / mp solve in one
 // cooperative launch (solve_persist.cu).  CSB200_PERSIST=0 disables it, =1 prefers it even where the small-dictionary
 // kernel is eligible too; an explicit CSB200_SMALL_SOLVE (tests select the path they exercise) takes precedence.
@@ -775,7 +803,7 @@ int after_upload(csb200_batch* b, int64_t nsig, bool allow_lazy) {
     b->nsig = nsig;
     b->has_map = false;
     b->cur_P = 0;
-    if (allow_lazy && (use_small_solve(b) || use_persist_solve(b, 0))) {
+    if (allow_lazy && (use_small_solve(b) || use_persist_solve(b, 0) || use_cluster_solve(b, 1))) {
         // one-shot call on a small dictionary: the solve kernel itself checks b for NaN/Inf and sets r = b,
         // so the upload needs no scan, no reset and no synchronisation
         b->lazy_input_check = true;
@@ -1118,6 +1146,10 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
+    if (use_cluster_solve(b, 1)) {
+        if ((rc = run_cluster_solve(b, 0, k, 1, eps))) return rc;
+        return finish(b, true);
+    }
     if (use_persist_solve(b, 0) && !(use_small_solve(b) && getenv("CSB200_SMALL_SOLVE"))) {
         if ((rc = run_persist_solve(b, 0, k, eps))) return rc;
         return finish(b, true);
@@ -1164,6 +1196,10 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     if (need > b->kcap) { g_last_error = "k exceeds the batch's max_sparsity"; return CSB200_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
+    if (use_cluster_solve(b, l)) {
+        if ((rc = run_cluster_solve(b, 1, k, l, eps))) return rc;
+        return finish(b, true);
+    }
     if (l <= MAX_S && use_small_solve(b)) {
         if ((rc = run_small_solve(b, 1, k, l, eps, nullptr, nullptr, nullptr, 0))) return rc;
         return finish(b, true);
@@ -1357,6 +1393,10 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
         CU_TRY(cudaMemcpy(x0.idx, hi.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(x0.val, x0_val, n * sizeof(double), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(x0.nnz, hn.data(), b->nsig * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (!warm && use_cluster_solve(b, 1)) {
+        if ((rc = run_cluster_solve(b, 2, iters, 1, 0.0))) return rc;
+        return finish(b, true);
     }
     if (!warm && use_persist_solve(b, 2)) {
         if ((rc = run_persist_solve(b, 2, iters, 0.0))) return rc;

@@ -102,6 +102,9 @@ struct SmallSolveArgs {
 };
 bool small_solve_eligible(int ld, int N, int kcap, int nsig, bool f32);
 cudaError_t launch_small_solve(const StateArgs& a, const SmallSolveArgs& q, bool f32, cudaStream_t st);
+// Cluster-resident variant for <= 8 signals (dictionary split over the shared memory of an 8-CTA cluster per signal).
+bool cluster_solve_eligible(int ld, int N, int kcap, int nsig, int take, bool f32);
+cudaError_t launch_cluster_solve(const StateArgs& a, const SmallSolveArgs& q, bool f32, cudaStream_t st);
 // Whole-solve cooperative kernel for 1..PERSIST_MAX_SIGNALS signals (solve_persist.cu): mode 0 omp, 2 mp.
 constexpr int PERSIST_MAX_SIGNALS = 8;
 struct PersistArgs {

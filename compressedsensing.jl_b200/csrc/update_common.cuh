@@ -280,6 +280,7 @@ __device__ __forceinline__ void select_any(const StateArgs& a, int sig, int take
 template <typename T> struct RowVec;
 template <> struct RowVec<double> {
     static constexpr int W = 2;
+    using V16 = double2;
     static __device__ __forceinline__ void load(const double* p, double (&o)[2]) {
         const double2 x = *reinterpret_cast<const double2*>(p);
         o[0] = x.x; o[1] = x.y;
@@ -287,6 +288,7 @@ template <> struct RowVec<double> {
 };
 template <> struct RowVec<float> {
     static constexpr int W = 4;
+    using V16 = float4;
     static __device__ __forceinline__ void load(const float* p, double (&o)[4]) {
         const float4 x = *reinterpret_cast<const float4*>(p);
         o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w;

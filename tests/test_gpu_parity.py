@@ -234,14 +234,20 @@ def test_golden(cs, path, impl, update, monkeypatch):
 
 
 # ------------------------------------------------------------------ reference call surface + quirks
-@pytest.fixture(params=["small_solve", "multi_launch", "persist"])
+@pytest.fixture(params=["small_solve", "multi_launch", "persist", "cluster_solve"])
 def solve_path(request, monkeypatch):
-    """The three ways a few-signal solve on a small dictionary can run: the one-CTA-per-signal whole-solve kernel
-    (solve_small.cu), the per-iteration kernels (CSB200_SMALL_SOLVE=0), and the cooperative whole-solve kernel
-    (solve_persist.cu, the default for <= 8 signals; forced here so that nothing else can take the call)."""
+    """The ways a few-signal solve on a small dictionary can run: the one-CTA-per-signal whole-solve kernel
+    (solve_small.cu), the per-iteration kernels (CSB200_SMALL_SOLVE=0), the cooperative whole-solve kernel
+    (solve_persist.cu) and the cluster-resident whole-solve kernel (the default for <= 8 signals on dictionaries that fit
+    an 8-CTA cluster's shared memory); each forced here so that nothing else can take the call."""
     if request.param == "persist":
         monkeypatch.delenv("CSB200_SMALL_SOLVE", raising=False)
         monkeypatch.setenv("CSB200_PERSIST", "1")
+        monkeypatch.setenv("CSB200_CLUSTER_SOLVE", "0")
+    elif request.param == "cluster_solve":
+        monkeypatch.delenv("CSB200_SMALL_SOLVE", raising=False)
+        monkeypatch.delenv("CSB200_PERSIST", raising=False)
+        monkeypatch.setenv("CSB200_CLUSTER_SOLVE", "1")
     else:
         monkeypatch.setenv("CSB200_SMALL_SOLVE", "1" if request.param == "small_solve" else "0")
     return request.param
@@ -1003,8 +1009,9 @@ def test_persistent_whole_solve_matches_multi_launch_and_oracle(cs, po, algo, dt
     iters = k if algo == "omp" else 2 * k
     out = {}
     with cs.Dictionary(A) as D:
-        for path, env in (("persist", {"CSB200_PERSIST": "1"}), ("multi", {"CSB200_PERSIST": "0", "CSB200_SMALL_SOLVE": "0"})):
-            for key in ("CSB200_PERSIST", "CSB200_SMALL_SOLVE"):
+        for path, env in (("persist", {"CSB200_PERSIST": "1", "CSB200_CLUSTER_SOLVE": "0"}),
+                          ("multi", {"CSB200_PERSIST": "0", "CSB200_SMALL_SOLVE": "0", "CSB200_CLUSTER_SOLVE": "0"})):
+            for key in ("CSB200_PERSIST", "CSB200_SMALL_SOLVE", "CSB200_CLUSTER_SOLVE"):
                 monkeypatch.delenv(key, raising=False)
             for key, val in env.items():
                 monkeypatch.setenv(key, val)
@@ -1040,10 +1047,64 @@ def test_persistent_whole_solve_matches_multi_launch_and_oracle(cs, po, algo, dt
             assert _close(np.array([acc[i] for i in sorted(acc)]), ref.nzval, max(rtol, 1e-9))
 
 
+@pytest.mark.parametrize("algo", ["omp", "gomp", "mp"])
+@pytest.mark.parametrize("dtype,M,N,k,nsig", [(np.float64, 128, 256, 8, 1), (np.float64, 70, 130, 6, 3), (np.float32, 64, 160, 5, 8),
+                                              (np.float64, 96, 1500, 12, 2), (np.float32, 256, 600, 20, 1)])
+def test_cluster_resident_whole_solve_matches_multi_launch_and_oracle(cs, po, algo, dtype, M, N, k, nsig, monkeypatch):
+    """solve_small.cu cluster_solve_kernel (<= 8 signals; the dictionary lives in the shared memory of an 8-CTA cluster
+    per signal, candidates cross by distributed shared memory, every CTA runs the same update) against the
+    per-iteration kernels -- identical selection sequence, values to rounding -- and the oracle.  Includes config 1."""
+    rng = np.random.default_rng(3000 + M + nsig)
+    A = po.gaussian_dictionary(rng, M, N, dtype)
+    X0, Bm = _planted(po, rng, A.astype(np.float64), k, nsig, noise=1e-3)
+    Bm = np.asfortranarray(Bm.astype(dtype))
+    eps = float(np.finfo(dtype).eps)
+    rtol = RTOL32 if dtype == np.float32 else RTOL64
+    iters, l = (k, 3) if algo != "mp" else (2 * k, 1)
+    out = {}
+    with cs.Dictionary(A) as D:
+        for path, env in (("cluster", {"CSB200_CLUSTER_SOLVE": "1"}),
+                          ("multi", {"CSB200_CLUSTER_SOLVE": "0", "CSB200_PERSIST": "0", "CSB200_SMALL_SOLVE": "0"})):
+            for key in ("CSB200_CLUSTER_SOLVE", "CSB200_PERSIST", "CSB200_SMALL_SOLVE"):
+                monkeypatch.delenv(key, raising=False)
+            for key, val in env.items():
+                monkeypatch.setenv(key, val)
+            with cs.Batch(D, nsig, iters) as batch:
+                for rep in range(2):
+                    batch.upload(Bm)
+                    {"omp": lambda: batch.omp(iters, eps), "gomp": lambda: batch.gomp(l, iters, eps), "mp": lambda: batch.mp(iters)}[algo]()
+                    out[path, rep] = batch.download(iters) + (batch.residual(),)
+    assert all(np.array_equal(out["cluster", 0][i], out["cluster", 1][i]) for i in range(6))
+    sel, coef, nnz, res, its, R = out["cluster", 0]
+    msel, mcoef, mnnz, mres, mits, mR = out["multi", 0]
+    assert np.array_equal(sel, msel) and np.array_equal(nnz, mnnz) and np.array_equal(its, mits)
+    scale = np.abs(mcoef).max()
+    assert np.max(np.abs(coef - mcoef)) <= (1e-5 if dtype == np.float32 else 1e-12) * scale
+    assert np.allclose(R, mR, rtol=0, atol=(1e-5 if dtype == np.float32 else 1e-12) * np.abs(Bm).max())
+    for s in range(min(nsig, 3)):
+        t = po.Trace()
+        if algo == "mp":
+            ref = po.mp(A, Bm[:, s], iters, trace=t)
+            assert sel[s, :iters].tolist() == t.order(), (s, "selection sequence", min(t.margin))
+            acc = {}
+            for i, c in zip(sel[s, :iters].tolist(), coef[s, :iters].tolist()):
+                acc[i] = acc.get(i, 0.0) + c
+            assert sorted(acc) == ref.nzind
+            assert _close(np.array([acc[i] for i in sorted(acc)]), ref.nzval, max(rtol, 1e-9))
+        else:
+            ref = po.omp(A, Bm[:, s], iters, trace=t) if algo == "omp" else po.gomp(A, Bm[:, s], l, iters, trace=t)
+            n = int(nnz[s])
+            assert sel[s, :n].tolist() == t.order(), (s, "selection sequence", min(t.margin))
+            idx, val = _sorted(sel[s], coef[s], n)
+            assert idx.tolist() == ref.nzind and _close(val, ref.nzval, rtol)
+            assert int(its[s]) == t.iterations
+
+
 def test_persistent_whole_solve_eps_break_mixed_signals(cs, po, monkeypatch):
     """Signals of one call stop at different update!s (eps-break): a stopped signal's updater leaves, the workers keep
     serving the others; iteration counts and supports per signal must match the oracle."""
     monkeypatch.setenv("CSB200_PERSIST", "1")
+    monkeypatch.setenv("CSB200_CLUSTER_SOLVE", "0")
     rng = np.random.default_rng(2024)
     M, N = 200, 900
     A = po.gaussian_dictionary(rng, M, N)
