@@ -160,6 +160,7 @@ struct csb200_batch {
     bool src_f32 = false;       // the batch lives on the FP64 twin of an FP32 dictionary: uploads arrive as FP32
     float* stage32 = nullptr;   // device staging for those uploads (ld x cap_sig floats)
     bool defer_finish = false;  // pipelined one-shot path: a solve only enqueues its work, the caller synchronises later
+    bool skip_solve_sync = false;   // one-shot calls: the download that follows synchronises (one host wake-up less per call)
     // Few-signal solves are launch-bound (tens of microseconds of kernels per update!): the second solve with the same
     // shape on this batch is captured into a CUDA graph, later ones replay it (see run_graphed).
     struct SolveKey {
@@ -714,7 +715,7 @@ int begin_solve_fwd(csb200_batch* b) { return begin_solve(b); }
 
 int finish(csb200_batch* b, bool solve = false) {
     if (solve) { CU_TRY(cudaEventRecord(b->ev_solve1, b->stream)); }
-    if (solve && b->defer_finish) return CSB200_OK;
+    if (solve && (b->defer_finish || b->skip_solve_sync)) return CSB200_OK;
     cudaError_t e = cudaStreamSynchronize(b->stream);
     if (e == cudaSuccess && solve) b->solve_timed = true;
     if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
@@ -1756,7 +1757,9 @@ static int omp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsi
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
+    b->skip_solve_sync = true;                 // csb200_batch_download below synchronises
     rc = csb200_batch_omp(b, k, eps);
+    b->skip_solve_sync = false;
     if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
     return rc;
 }
@@ -1787,7 +1790,9 @@ static int gomp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t ns
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
+    b->skip_solve_sync = true;                 // csb200_batch_download below synchronises
     rc = csb200_batch_gomp(b, l, k, eps);
+    b->skip_solve_sync = false;
     if (!rc) rc = csb200_batch_download(b, k, sel_idx, coef, nnz, resnorm, iters);
     return rc;
 }
@@ -1900,7 +1905,9 @@ static int mp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig
     csb200_batch* b = nullptr;
     int rc = one_shot(d, Bmat, ldb, nsig, iters_k, &b);
     if (rc) return rc;
+    b->skip_solve_sync = !(x0_idx && x0_val && x0_nnz);   // csb200_batch_download below synchronises (a warm start's buffers are freed first)
     rc = csb200_batch_mp(b, iters_k, x0_idx, x0_val, x0_nnz, x0_stride);
+    b->skip_solve_sync = false;
     if (!rc) rc = csb200_batch_download(b, iters_k, sel_idx, coef, nullptr, resnorm, nullptr);
     return rc;
 }

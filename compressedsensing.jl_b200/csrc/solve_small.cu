@@ -301,111 +301,157 @@ __global__ void __launch_bounds__(ST, 1) cluster_solve_kernel(StateArgs a, Small
         const int take = q.mode == 1 ? (is_rem ? rem : q.l) : 1;
         if (q.mode != 2 && !(t < a.M)) { ++iters; if (!(nr >= q.eps)) done = true; continue; }   // :63,:117
 
-        // ---- c = A'r over the local slice: 4 atoms per warp at a time, lanes over rows, shared memory only ----
-        for (int j0 = warp * 4; j0 < nloc; j0 += SW * 4) {
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            const T* col[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) col[c] = Asm + (size_t)(j0 + c < nloc ? j0 + c : nloc - 1) * ld;
-            for (int row = lane; row < ld; row += 32) {
-                const double rr = rs[row];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c] = fma((double)col[c][row], rr, acc[c]);
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double s = warp_sum(acc[c]);
-                if (lane == 0 && j0 + c < nloc) cv[j0 + c] = s;
-            }
-        }
-        __syncthreads();
-
-        // ---- local top-`take` of |c| (value desc, index asc), written straight into every peer's exchange buffer ----
         XRec* mine = xch + (size_t)parity * CL * MAX_S;
-        double pv = 0.0;
-        int pi = -1;
-        for (int round = 0; round < take; ++round) {
-            double bv = -1.0;
-            int bi = INT_MAX;
-            for (int j = tid; j < nloc; j += ST) {
-                const double v = fabs(cv[j]);
-                const bool ok = (round == 0) || (v < pv) || (v == pv && j > pi);
-                if (ok && v > bv) { bv = v; bi = j; }                    // j ascends: first maximum wins; NaN never wins
-            }
+        if (take == 1) {
+            // ---- one atom per update! (omp, mp): the arg-max rides in the correlation loop, one block barrier, one
+            // cluster barrier, and every thread picks the winner from the CL records itself ----
+            double wbv = -1.0, wbc = 0.0;
+            int wbi = INT_MAX;
+            for (int j0 = warp * 4; j0 < nloc; j0 += SW * 4) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                const T* col[4];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-            }
-            __syncthreads();
-            if (lane == 0) { red[warp] = bv; red_i[warp] = bi; }
-            __syncthreads();
-            bv = red[0]; bi = red_i[0];
+                for (int c = 0; c < 4; ++c) col[c] = Asm + (size_t)(j0 + c < nloc ? j0 + c : nloc - 1) * ld;
+                for (int row = lane; row < ld; row += 32) {
+                    const double rr = rs[row];
 #pragma unroll
-            for (int w = 1; w < SW; ++w)
-                if (cand_better(red[w], red_i[w], bv, bi)) { bv = red[w]; bi = red_i[w]; }
-            pv = bv; pi = bi;
-            if (tid < CL) {                                              // thread p delivers the record to CTA p
+                    for (int c = 0; c < 4; ++c) acc[c] = fma((double)col[c][row], rr, acc[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double sc = warp_sum(acc[c]);
+                    const double v = fabs(sc);
+                    if (j0 + c < nloc && v >= 0.0 && cand_better(v, j0 + c, wbv, wbi)) { wbv = v; wbi = j0 + c; wbc = sc; }   // NaN never wins
+                }
+            }
+            if (lane == 0) { red[warp] = wbc; red_i[warp] = wbi; }
+            __syncthreads();
+            if (tid < CL) {                                              // thread p delivers this CTA's record to CTA p
+                double bc = 0.0;
+                int bi = INT_MAX;
+                for (int w = 0; w < SW; ++w)
+                    if (red_i[w] != INT_MAX && cand_better(fabs(red[w]), red_i[w], fabs(bc), bi)) { bc = red[w]; bi = red_i[w]; }
                 XRec rec;
-                rec.c = bi == INT_MAX ? 0.0 : cv[bi];
-                rec.idx = bi == INT_MAX ? -1 : lo + bi;
+                rec.c = bi == INT_MAX ? 0.0 : bc;
+                rec.idx = bi == INT_MAX ? -1 : lo + bi + a.idx_offset;
                 rec.pad = 0;
-                XRec* remote = cl.map_shared_rank(mine, tid);
-                remote[crank * MAX_S + round] = rec;
+                cl.map_shared_rank(mine, tid)[crank * MAX_S] = rec;
             }
-            if (bi == INT_MAX) {
-                if (tid < CL) {
-                    XRec* remote = cl.map_shared_rank(mine, tid);
-                    for (int r2 = round + 1; r2 < take; ++r2) { XRec rec; rec.c = 0.0; rec.idx = -1; rec.pad = 0; remote[crank * MAX_S + r2] = rec; }
-                }
-                break;
+            cl.sync();                                                   // every CTA's record is in every buffer
+            XRec win; win.c = 0.0; win.idx = -1; win.pad = 0;
+            for (int src = 0; src < CL; ++src) {
+                const XRec rec = mine[src * MAX_S];
+                if (rec.idx >= 0 && (win.idx < 0 || cand_better(fabs(rec.c), rec.idx, fabs(win.c), win.idx))) win = rec;
             }
-        }
-        cl.sync();                                                       // every CTA's candidates are in every buffer
-
-        // ---- merge: global top-`take` over the CL x take records, identically on every CTA ----
-        double mv = 0.0;
-        int mi = -1;
-        for (int round = 0; round < take; ++round) {
-            double bv = -1.0;
-            int bi = INT_MAX, bslot = -1;
-            for (int e = tid; e < CL * take; e += ST) {
-                const int src = e / take, rr = e - src * take;
-                const XRec rec = mine[src * MAX_S + rr];
-                if (rec.idx < 0) continue;
-                const double v = fabs(rec.c);
-                const bool ok = (round == 0) || (v < mv) || (v == mv && rec.idx > mi);
-                if (ok && cand_better(v, rec.idx, bv, bi)) { bv = v; bi = rec.idx; bslot = src * MAX_S + rr; }
-            }
+            if (tid == 0) merged[0] = win;
+            __syncthreads();
+            parity ^= 1;
+        } else {
+        // ---- c = A'r over the local slice: 4 atoms per warp at a time, lanes over rows, shared memory only ----
+            for (int j0 = warp * 4; j0 < nloc; j0 += SW * 4) {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                const T* col[4];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                const int os = __shfl_xor_sync(0xffffffffu, bslot, off);
-                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bslot = os; }
-            }
-            __syncthreads();
-            if (lane == 0) { red[warp] = bv; red_i[warp] = bslot; }
-            __syncthreads();
-            if (tid == 0) {
-                double wv = -1.0;
-                int wi = INT_MAX, ws = -1;
-                for (int w = 0; w < SW; ++w) {
-                    if (red_i[w] < 0) continue;
-                    const int ci = mine[red_i[w]].idx;
-                    if (cand_better(red[w], ci, wv, wi)) { wv = red[w]; wi = ci; ws = red_i[w]; }
+                for (int c = 0; c < 4; ++c) col[c] = Asm + (size_t)(j0 + c < nloc ? j0 + c : nloc - 1) * ld;
+                for (int row = lane; row < ld; row += 32) {
+                    const double rr = rs[row];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[c] = fma((double)col[c][row], rr, acc[c]);
                 }
-                XRec rec; rec.c = 0.0; rec.idx = -1; rec.pad = 0;
-                if (ws >= 0) rec = mine[ws];
-                merged[round] = rec;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double s = warp_sum(acc[c]);
+                    if (lane == 0 && j0 + c < nloc) cv[j0 + c] = s;
+                }
             }
             __syncthreads();
-            mv = fabs(merged[round].c); mi = merged[round].idx;
-            if (mi < 0) { for (int r2 = round + 1 + tid; r2 < take; r2 += ST) { XRec rec; rec.c = 0.0; rec.idx = -1; rec.pad = 0; merged[r2] = rec; } break; }
+
+            // ---- local top-`take` of |c| (value desc, index asc), written straight into every peer's exchange buffer ----
+            double pv = 0.0;
+            int pi = -1;
+            for (int round = 0; round < take; ++round) {
+                double bv = -1.0;
+                int bi = INT_MAX;
+                for (int j = tid; j < nloc; j += ST) {
+                    const double v = fabs(cv[j]);
+                    const bool ok = (round == 0) || (v < pv) || (v == pv && j > pi);
+                    if (ok && v > bv) { bv = v; bi = j; }                    // j ascends: first maximum wins; NaN never wins
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                }
+                __syncthreads();
+                if (lane == 0) { red[warp] = bv; red_i[warp] = bi; }
+                __syncthreads();
+                bv = red[0]; bi = red_i[0];
+#pragma unroll
+                for (int w = 1; w < SW; ++w)
+                    if (cand_better(red[w], red_i[w], bv, bi)) { bv = red[w]; bi = red_i[w]; }
+                pv = bv; pi = bi;
+                if (tid < CL) {                                              // thread p delivers the record to CTA p
+                    XRec rec;
+                    rec.c = bi == INT_MAX ? 0.0 : cv[bi];
+                    rec.idx = bi == INT_MAX ? -1 : lo + bi + a.idx_offset;
+                    rec.pad = 0;
+                    XRec* remote = cl.map_shared_rank(mine, tid);
+                    remote[crank * MAX_S + round] = rec;
+                }
+                if (bi == INT_MAX) {
+                    if (tid < CL) {
+                        XRec* remote = cl.map_shared_rank(mine, tid);
+                        for (int r2 = round + 1; r2 < take; ++r2) { XRec rec; rec.c = 0.0; rec.idx = -1; rec.pad = 0; remote[crank * MAX_S + r2] = rec; }
+                    }
+                    break;
+                }
+            }
+            cl.sync();                                                       // every CTA's candidates are in every buffer
+
+            // ---- merge: global top-`take` over the CL x take records, identically on every CTA ----
+            double mv = 0.0;
+            int mi = -1;
+            for (int round = 0; round < take; ++round) {
+                double bv = -1.0;
+                int bi = INT_MAX, bslot = -1;
+                for (int e = tid; e < CL * take; e += ST) {
+                    const int src = e / take, rr = e - src * take;
+                    const XRec rec = mine[src * MAX_S + rr];
+                    if (rec.idx < 0) continue;
+                    const double v = fabs(rec.c);
+                    const bool ok = (round == 0) || (v < mv) || (v == mv && rec.idx > mi);
+                    if (ok && cand_better(v, rec.idx, bv, bi)) { bv = v; bi = rec.idx; bslot = src * MAX_S + rr; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    const int os = __shfl_xor_sync(0xffffffffu, bslot, off);
+                    if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bslot = os; }
+                }
+                __syncthreads();
+                if (lane == 0) { red[warp] = bv; red_i[warp] = bslot; }
+                __syncthreads();
+                if (tid == 0) {
+                    double wv = -1.0;
+                    int wi = INT_MAX, ws = -1;
+                    for (int w = 0; w < SW; ++w) {
+                        if (red_i[w] < 0) continue;
+                        const int ci = mine[red_i[w]].idx;
+                        if (cand_better(red[w], ci, wv, wi)) { wv = red[w]; wi = ci; ws = red_i[w]; }
+                    }
+                    XRec rec; rec.c = 0.0; rec.idx = -1; rec.pad = 0;
+                    if (ws >= 0) rec = mine[ws];
+                    merged[round] = rec;
+                }
+                __syncthreads();
+                mv = fabs(merged[round].c); mi = merged[round].idx;
+                if (mi < 0) { for (int r2 = round + 1 + tid; r2 < take; r2 += ST) { XRec rec; rec.c = 0.0; rec.idx = -1; rec.pad = 0; merged[r2] = rec; } break; }
+            }
+            __syncthreads();
+            parity ^= 1;
         }
-        __syncthreads();
-        parity ^= 1;
 
         // the column of atom j from its owner's shared memory (distributed shared memory) into cache slot `slot`
         auto fetch = [&](int j, int slot) -> const T* {

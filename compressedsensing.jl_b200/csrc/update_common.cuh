@@ -335,8 +335,8 @@ struct PursuitSmem {
 // O(cond): the products cancel), where the reference's back substitution on a Givens QR gives cond(A_S) eps.  Measured
 // (tools/conditioning_study.py): invisible on Gaussian dictionaries (cond(A_S) ~ 1.4), 4e-9 at cond 2e4, 5e-5 at 2e6.
 // A support is marked ill-conditioned when an appended atom keeps less than this fraction of its squared norm after
-// orthogonalisation (cond(A_S) >~ 30); its coefficients are then refined, see refine_coefficients.  State flag bit 16.
-constexpr double ILLCOND_RATIO = 1e-3;
+// orthogonalisation (cond(A_S) >~ 10); its coefficients are then refined, see refine_coefficients.  State flag bit 16.
+constexpr double ILLCOND_RATIO = 1e-2;
 constexpr int FLAG_ILLCOND = 16;
 
 // Iterative refinement of the least-squares coefficients of an ill-conditioned support (corrected semi-normal

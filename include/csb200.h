@@ -147,9 +147,9 @@ int csb200_batch_download(csb200_batch* batch, int64_t stride, int64_t* sel_idx,
  *   1   an atom that won the arg-max was numerically dependent on the active set (rho^2 <= 1e-26 ||a||^2) and was NOT
  *       appended -- the reference's add_column! would divide by a ~0 diagonal here;
  *   2   the correlation pass produced no candidate (all-NaN correlations cannot happen on finite input; kept for safety);
- *   16  the active set is ill-conditioned (an appended atom kept < 1e-3 of its squared norm after orthogonalisation,
- *       cond(A_S) >~ 30): the coefficients were refined by two steps of iterative refinement, which restores the
- *       ~cond(A_S) eps accuracy of a backward-stable QR up to cond ~1e6; beyond that treat them as approximate. */
+ *   16  the active set is ill-conditioned (an appended atom kept < 1e-2 of its squared norm after orthogonalisation,
+ *       cond(A_S) >~ 10): the coefficients were refined by two steps of iterative refinement, which restores the
+ *       ~cond(A_S) eps accuracy of a backward-stable QR (measured for cond up to 2e8, profiles/conditioning_r02.md). */
 int csb200_batch_flags(csb200_batch* batch, int32_t* flags);
 
 /* Timing of the dominant kernel (the correlation pass), measured with CUDA events on the
