@@ -114,14 +114,15 @@ def draw_supports_np(rng, nsig, n, k):
     """k distinct atom indices per signal, uniform over k-subsets (rejection of rows with a repeat), and +-1 signs
     (`sparse_vector`, src/util.jl:13-19)."""
     idx = rng.integers(0, n, size=(nsig, k))
-    for _ in range(64):
+    for _ in range(8):
         srt = np.sort(idx, axis=1)
         bad = np.nonzero((srt[:, 1:] == srt[:, :-1]).any(axis=1))[0]
         if bad.size == 0:
             break
         idx[bad] = rng.integers(0, n, size=(bad.size, k))
-    else:
-        raise RuntimeError("support sampling did not converge")
+    else:                                   # k*k is not small against n: draw the remaining rows one by one
+        for s in bad:
+            idx[s] = rng.choice(n, size=k, replace=False)
     sign = rng.integers(0, 2, size=(nsig, k)).astype(np.float64) * 2.0 - 1.0
     return idx, sign
 
@@ -308,14 +309,16 @@ class Ctx:
 def draw_supports_torch(torch, nsig, n, k, gen, dev):
     """Device version of draw_supports_np (same distribution, torch generator)."""
     idx = torch.randint(0, n, (nsig, k), device=dev, generator=gen)
-    for _ in range(64):
+    for _ in range(8):
         srt = idx.sort(dim=1).values
         bad = (srt[:, 1:] == srt[:, :-1]).any(dim=1).nonzero().flatten()
         if bad.numel() == 0:
             break
         idx[bad] = torch.randint(0, n, (bad.numel(), k), device=dev, generator=gen)
-    else:
-        raise RuntimeError("support sampling did not converge")
+    else:                                   # k*k is not small against n: the k smallest of n uniform keys per row
+        for s0 in range(0, bad.numel(), 1024):
+            rows = bad[s0:s0 + 1024]
+            idx[rows] = torch.rand(rows.numel(), n, device=dev, generator=gen).topk(k, dim=1).indices
     sign = torch.randint(0, 2, (nsig, k), device=dev, generator=gen).to(torch.float64) * 2 - 1
     return idx, sign
 
