@@ -657,6 +657,24 @@ def run_c2s(ctx, args):
         if name == "f64":
             primary = (ms, out, Ad, Bd)
     ms, out, Ad, Bd = primary
+    # 2..8 signals share ONE pass over the dictionary per update! (multi-right-hand-side workers of solve_persist.cu)
+    idx8, sign8 = draw_supports_np(np.random.default_rng(5678 + 22), 8, N, k)
+    B8 = np.asfortranarray(np.stack([A[:, idx8[s]] @ sign8[s] for s in range(8)], axis=1))
+    multi = {}
+    with cs.Dictionary(A, device=ctx.local) as D:
+        for ns in (2, 4, 8):
+            with cs.Batch(D, ns, k) as b:
+                b.upload(B8[:, :ns])
+                for _ in range(5):
+                    b.omp(k, 1e-30)
+                t8 = []
+                for _ in range(50):
+                    b.omp(k, 1e-30)
+                    t8.append(b.last_solve_ms())
+                sel8, _, nnz8, _, _ = b.download(k)
+            ok8 = all(set(idx8[s].tolist()) == set(sel8[s, :int(nnz8[s])].tolist()) for s in range(ns))
+            multi[str(ns)] = {"us_per_call": 1e3 * float(np.mean(t8)), "vs_one_signal": float(np.mean(t8)) / ms,
+                              "supports_recovered": bool(ok8)}
     cpu, parity = None, None
     if ctx.rank == 0 and ctx.world == 1 and args.cpu_signals > 0:
         r = run_c_oracle("omp", Ad, Bd[:, :1], k, eps=1e-30, threads=1)
@@ -672,7 +690,7 @@ def run_c2s(ctx, args):
         "config": {"workload": "single-signal omp on the config-2 dictionary (64 MiB FP64 / 32 MiB FP32 < 126 MB L2)",
                    "M": M, "N": N, "k": k, "timed_solves": 100,
                    "l2": "dictionary deliberately L2-resident: this is the L2-regime single-signal path"},
-        "per_dtype": res, "gpu_launches": 100 * 2 * k,
+        "per_dtype": res, "multi_signal_f64": multi, "gpu_launches": 100 * 2 * k,
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
                      "kernel": "whole solve (corr_gemv_kernel + update per update!)", "bytes_per_launch": bytes_it,
                      "peak_source": hbm_src + "; the dictionary is served from L2, so this fraction of the HBM peak is "
