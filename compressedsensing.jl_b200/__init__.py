@@ -687,11 +687,19 @@ class ShardComm:
 
     @staticmethod
     def unique_id() -> bytes:
+        try:
+            import torch  # noqa: F401  (see __init__)
+        except ImportError:
+            pass
         buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
         _check(lib.csb200_comm_unique_id(buf))
         return buf.raw
 
     def __init__(self, unique_id: bytes, rank: int, nranks: int, device: int):
+        try:                      # let PyTorch load the NCCL it was built against first: the library then reuses that one
+            import torch  # noqa: F401
+        except ImportError:
+            pass
         h = c_void_p()
         buf = ctypes.create_string_buffer(unique_id, NCCL_ID_BYTES)
         _check(lib.csb200_comm_create(buf, rank, nranks, device, byref(h)))

@@ -1321,7 +1321,7 @@ static int run_sp(csb200_batch* b, int64_t k, double delta, int64_t maxiter) {
         return CSB200_ERR_INVALID_ARG;
     }
     if (obl && k > d->M) { g_last_error = "oblivious: k > size(A, 1) (underdetermined least squares) is not supported"; return CSB200_ERR_UNSUPPORTED; }
-    if (k > SP_MAX_K) { g_last_error = "sp / oblivious: k > 256 is not supported"; return CSB200_ERR_UNSUPPORTED; }
+    if (k > SP_MAX_K) { g_last_error = "sp / oblivious: k > 1024 is not supported"; return CSB200_ERR_UNSUPPORTED; }
     if ((obl ? k : 2 * k) > b->kcap) { g_last_error = "batch max_sparsity too small (sp needs 2k, oblivious k)"; return CSB200_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
@@ -1933,7 +1933,7 @@ int csb200_dict_cumbabel(csb200_dict* d, int64_t k, double* mu_out) {
     if (!d || !mu_out || k < 1) return CSB200_ERR_INVALID_ARG;
     if (d->n_total != d->N) { g_last_error = "cumbabel needs an unsharded dictionary"; return CSB200_ERR_UNSUPPORTED; }
     if (k > d->N) return CSB200_ERR_INVALID_ARG;                       // partialsort!(inner, 1:k) would throw
-    if (k + 1 > SP_MAX_K) { g_last_error = "cumbabel: k > 255 is not supported"; return CSB200_ERR_UNSUPPORTED; }
+    if (k + 1 > SP_MAX_K) { g_last_error = "cumbabel: k > 1023 is not supported"; return CSB200_ERR_UNSUPPORTED; }
     std::lock_guard<std::mutex> lk(d->mu);
     int rc = set_device(d);
     if (rc) return rc;

@@ -138,7 +138,7 @@ constexpr size_t MAX_DYN_SMEM = 227 * 1024;
 cudaError_t launch_ols_init(const StateArgs& a, double* colnorm2, cudaStream_t st);
 cudaError_t launch_mp_update(const StateArgs& a, bool f32, int iter, int stride, cudaStream_t st);
 // Subspace pursuit `update!` / oblivious selection (update.cu sp_update_kernel); k <= SP_MAX_K atoms per acquisition.
-constexpr int SP_MAX_K = 256;
+constexpr int SP_MAX_K = 1024;
 cudaError_t launch_sp_update(const StateArgs& a, bool f32, int k, double delta, int first, int* ndone, cudaStream_t st);
 size_t sp_update_smem_bytes(int ld, int kcap);
 // dictionary analysis (src/util.jl:2, 96-117): column 2-norms; Babel-function fold over a chunk of atoms

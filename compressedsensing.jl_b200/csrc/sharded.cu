@@ -64,10 +64,17 @@ NcclApi& nccl() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // An NCCL that the host program has loaded already (e.g. the one PyTorch bundles) is reused; otherwise the
+        // system library is loaded with RTLD_LOCAL, so that its symbols never shadow a different NCCL version another
+        // library brings along later (a RTLD_GLOBAL 2.27 made a later `import torch` fail on a 2.28-only symbol).
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* n : names) {
-            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            api.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
             if (api.handle) break;
+        }
+        for (const char* n : names) {
+            if (api.handle) break;
+            api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         }
         if (!api.handle) return;
         api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");

@@ -280,7 +280,8 @@ __device__ __forceinline__ int append_list(PursuitSmem<T>& S, int& t, const int*
     return flags;
 }
 
-template <typename T, int NT>
+// CAP: slots of the candidate / keep lists (>= k): 256 covers the usual case at 4 KiB of static shared memory, 1024 the rest
+template <typename T, int NT, int CAP>
 __global__ void __launch_bounds__(NT, 2)
 sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int first, int* __restrict__ ndone) {
     extern __shared__ double dsm[];
@@ -302,9 +303,9 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
     double* Tsm = reinterpret_cast<double*>(S.colp + kcap);
     __shared__ double red[NT / 32];
     __shared__ int red_i[NT / 32];
-    __shared__ int s_cand[MAX_TAKE];
-    __shared__ double s_cval[MAX_TAKE];
-    __shared__ int s_keep[MAX_TAKE];
+    __shared__ int s_cand[CAP];
+    __shared__ double s_cval[CAP];
+    __shared__ int s_keep[CAP];
     __shared__ int s_nkeep;
     __shared__ int s_J[BLOCK_MAX];
     __shared__ const T* s_Jcol[BLOCK_MAX];
@@ -337,7 +338,7 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
         for (int e = tid; e < t * kcap; e += NT) { const int c = e / kcap, l = e - c * kcap; if (l <= c) Tsm[l + c * S.ldT] = S.Tg[e]; }
     __syncthreads();
 
-    select_any<NT>(a, sig, k, MAX_TAKE, s_cand, s_cval, red, red_i, reinterpret_cast<int*>(Vb), Vb + DENSE_HIST / 2,
+    select_any<NT>(a, sig, k, CAP, s_cand, s_cval, red, red_i, reinterpret_cast<int*>(Vb), Vb + DENSE_HIST / 2,
                    (int)block_region_elems(bm, ld) - DENSE_HIST / 2);
     const int cap = kcap < a.M ? kcap : a.M;
     flags |= append_list<T, NT>(S, t, s_cand, k, true, bm, cap, A, a.idx_offset, ld, Vb, Gm, Ym, sc, s_J, s_Jcol,
@@ -505,14 +506,15 @@ __global__ void __launch_bounds__(256) colnorm2_kernel(const T* __restrict__ A, 
 // Babel function (`cumbabel`, src/util.jl:106-117).  "Signal" s of the batch is atom col0 + s of the dictionary and its
 // candidates are the per-block top-(k+1) of |A'a_i|: merge them, drop the atom itself (`inner[i] = 0`), keep the k
 // largest, prefix-sum them and fold into mu[0..k) with max (non-negative doubles order like their bit patterns).
+template <int CAP>
 __global__ void __launch_bounds__(UT) babel_reduce_kernel(StateArgs a, int k, int col0, unsigned long long* __restrict__ mu) {
     __shared__ double red[UW];
     __shared__ int red_i[UW];
-    __shared__ int s_cand[MAX_TAKE];
-    __shared__ double s_cval[MAX_TAKE];
+    __shared__ int s_cand[CAP];
+    __shared__ double s_cval[CAP];
     __shared__ int s_hist[DENSE_HIST];
     const int sig = blockIdx.x;
-    select_any<UT>(a, sig, k + 1, MAX_TAKE, s_cand, s_cval, red, red_i, s_hist);
+    select_any<UT>(a, sig, k + 1, CAP, s_cand, s_cval, red, red_i, s_hist);
     if (threadIdx.x == 0) {
         double run = 0.0;
         int out = 0;
@@ -603,7 +605,8 @@ cudaError_t launch_omp_update(const StateArgs& a, bool f32, cudaStream_t st, con
 int sp_block_width(int ld, int kcap) {
     const bool t_in = kcap <= T_SMEM_MAX_K;
     int bm = BLOCK_MAX;
-    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > two_cta_dyn_smem(4608)) --bm;   // 2 CTAs per SM when possible
+    const size_t stat = kcap > 2 * MAX_TAKE ? 17408 : 4608;     // static shared memory of the CAP = 1024 / 256 instantiation
+    while (bm >= 2 && update_smem_bytes(ld, kcap, t_in, bm) > two_cta_dyn_smem(stat)) --bm;   // 2 CTAs per SM when possible
     if (bm < 2) { bm = 2; }
     return bm;
 }
@@ -617,17 +620,15 @@ cudaError_t launch_sp_update(const StateArgs& a, bool f32, int k, double delta, 
     const int t_in_smem = a.kcap <= T_SMEM_MAX_K ? 1 : 0;
     const int bm = sp_block_width(a.ld, a.kcap);
     const size_t smem = update_smem_bytes(a.ld, a.kcap, t_in_smem != 0, bm);
-    cudaError_t e;
-    if (f32) {
-        e = cudaFuncSetAttribute(sp_update_kernel<float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        sp_update_kernel<float, 256><<<a.nsig, 256, smem, st>>>(a, t_in_smem, bm, k, delta, first, ndone);
-    } else {
-        e = cudaFuncSetAttribute(sp_update_kernel<double, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        sp_update_kernel<double, 256><<<a.nsig, 256, smem, st>>>(a, t_in_smem, bm, k, delta, first, ndone);
-    }
-    return cudaGetLastError();
+        kern<<<a.nsig, 256, smem, st>>>(a, t_in_smem, bm, k, delta, first, ndone);
+        return cudaGetLastError();
+    };
+    const bool big = k > MAX_TAKE;                              // the list capacity follows k; the block width the batch's kcap
+    if (f32) return big ? go(sp_update_kernel<float, 256, SP_MAX_K>) : go(sp_update_kernel<float, 256, MAX_TAKE>);
+    return big ? go(sp_update_kernel<double, 256, SP_MAX_K>) : go(sp_update_kernel<double, 256, MAX_TAKE>);
 }
 
 cudaError_t launch_colnorms(const void* A, bool f32, int ld, int N, double* out, cudaStream_t st) {
@@ -639,7 +640,8 @@ cudaError_t launch_colnorms(const void* A, bool f32, int ld, int N, double* out,
 
 cudaError_t launch_babel_reduce(const StateArgs& a, int k, int col0, double* mu, cudaStream_t st) {
     if (a.nsig <= 0) return cudaSuccess;
-    babel_reduce_kernel<<<a.nsig, UT, 0, st>>>(a, k, col0, reinterpret_cast<unsigned long long*>(mu));
+    if (k + 1 > MAX_TAKE) babel_reduce_kernel<SP_MAX_K><<<a.nsig, UT, 0, st>>>(a, k, col0, reinterpret_cast<unsigned long long*>(mu));
+    else babel_reduce_kernel<MAX_TAKE><<<a.nsig, UT, 0, st>>>(a, k, col0, reinterpret_cast<unsigned long long*>(mu));
     return cudaGetLastError();
 }
 
