@@ -613,6 +613,31 @@ def test_few_signal_topk_with_clustered_correlations(cs, po, k):
         assert got.nzind.tolist() == ref.nzind and _close(got.nzval, ref.nzval, 1e-8)
 
 
+@pytest.mark.parametrize("nsig", [2, 30])
+def test_sp_oblivious_cumbabel_beyond_256_atoms(cs, po, nsig):
+    """`sp(A, b, k)`, `oblivious(A, b, k)` and `cumbabel(A, k)` take any k in the reference (src/twostage.jl:105,
+    src/oblivious.jl:4, src/util.jl:106); round 1 stopped at 256 / 255.  k = 300 on two signals (GEMV pass, k candidates per
+    CTA range) and on a batch (dense |A'r| + radix select), against the oracle."""
+    rng = np.random.default_rng(6000 + nsig)
+    M, N, k = 640, 2000, 300
+    A = po.gaussian_dictionary(rng, M, N)
+    X0, Bm = _planted(po, rng, A, k, nsig, noise=1e-2)
+    with cs.Dictionary(A) as D:
+        xs = cs.sp(D, Bm, k, 1e-12, 3)
+        xo = cs.oblivious(D, Bm, k)
+        mu = cs.cumbabel(D, k) if nsig == 2 else None
+    for s in range(min(nsig, 2)):
+        t = po.Trace()
+        ref = po.sp(A, Bm[:, s], k, 1e-12, 3, trace=t)
+        if min(t.margin) > 1e-8:
+            assert xs[s].nzind.tolist() == ref.nzind, (s, min(t.margin))
+            assert _close(xs[s].nzval, ref.nzval, 1e-8)
+        ref = po.oblivious(A, Bm[:, s], k)
+        assert xo[s].nzind.tolist() == ref.nzind and _close(xo[s].nzval, ref.nzval, 1e-8)
+    if mu is not None:
+        assert np.allclose(mu, po.cumbabel(A, k), rtol=1e-12)
+
+
 @pytest.mark.parametrize("gram", ["0", "1"])
 def test_sp_midsize_batch_vs_oracle(cs, po, gram, monkeypatch):
     monkeypatch.setenv("CSB200_GRAM", gram)
