@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(ST, 2) small_solve_kernel(StateArgs a, SmallSo
     double* Tsm = S.zs + kcap;                   // [kcap][ldT]
     S.ssel = reinterpret_cast<int*>(Tsm + (size_t)kcap * ldT);
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
-    __shared__ double red[SW];
+    __shared__ double red[2 * SW + 2];
     __shared__ int red_i[SW];
     __shared__ int s_cand[MAX_S];
     S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(ST, 1) cluster_solve_kernel(StateArgs a, Small
         acache = reinterpret_cast<T*>(reinterpret_cast<char*>(dsm) + off);    // [kcap][ld] columns of the active atoms
     }
     T* Asm = acache + (size_t)kcap * ld;                                      // [nloc_max][ld] this CTA's dictionary slice
-    __shared__ double red[SW];
+    __shared__ double red[2 * SW + 2];
     __shared__ int red_i[SW];
     S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red;
 

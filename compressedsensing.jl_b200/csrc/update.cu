@@ -79,7 +79,7 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     S.ssel = reinterpret_cast<int*>(p);
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
     double* Tsm = reinterpret_cast<double*>(S.colp + kcap);        // [kcap][ldT] inverse factor (optional)
-    __shared__ double red[NT / 32];
+    __shared__ double red[2 * (NT / 32) + 2];
     __shared__ int red_i[NT / 32];
     __shared__ int s_cand[MAX_TAKE];
     __shared__ double s_cval[MAX_TAKE];
@@ -301,7 +301,7 @@ sp_update_kernel(StateArgs a, int t_in_smem, int bm, int k, double delta, int fi
     S.ssel = reinterpret_cast<int*>(p);
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
     double* Tsm = reinterpret_cast<double*>(S.colp + kcap);
-    __shared__ double red[NT / 32];
+    __shared__ double red[2 * (NT / 32) + 2];
     __shared__ int red_i[NT / 32];
     __shared__ int s_cand[CAP];
     __shared__ double s_cval[CAP];

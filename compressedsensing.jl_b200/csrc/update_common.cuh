@@ -28,6 +28,27 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return p[0];
 }
 
+// Two sums in one reduction (one barrier pair, interleaved shuffles); red: [2 * NT / 32].
+template <int NT>
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[NT / 32 + (threadIdx.x >> 5)] = b; }
+    __syncthreads();
+    double p[NT / 32], q[NT / 32];
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) { p[w] = red[w]; q[w] = red[NT / 32 + w]; }
+#pragma unroll
+    for (int h = NT / 64; h > 0; h >>= 1)
+#pragma unroll
+        for (int w = 0; w < h; ++w) { p[w] += p[w + h]; q[w] += q[w + h]; }
+    a = p[0]; b = q[0];
+}
+
 // Global top-`take` over this signal's P*S per-block candidates -> s_cand[0..take) (atom or -1).
 template <int NT>
 __device__ void select_candidates(const double* __restrict__ pv, const int* __restrict__ pi, int count, int take,
@@ -327,7 +348,7 @@ struct PursuitSmem {
     double* Tsm;      // shared copy of R^{-1} or nullptr
     double* Tg;       // global copy of R^{-1} (ld = kcap) or nullptr
     int kcap;
-    double* red;      // [NT/32] reduction scratch
+    double* red;      // [2 * NT/32] reduction scratch (+ 2 doubles for the one-warp sums of append_atom)
     int illcond = 0;  // set by append_atom when an atom kept less than ILLCOND_RATIO of its squared norm (CTA-uniform)
 };
 
@@ -407,10 +428,19 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
                                            const double* __restrict__ gcol = nullptr, int idx_offset = 0) {
     constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double s2 = 0.0;
-    for (int row = tid; row < ld; row += NT) { const double e = (double)aj[row]; S.v[row] = e; s2 += e * e; }
-    const double anorm2 = block_sum<NT>(s2, S.red);
+    double s2 = 0.0, sab = 0.0;
+    for (int row = tid; row < ld; row += NT) {
+        const double e = (double)aj[row];
+        S.v[row] = e; s2 = fma(e, e, s2); sab = fma(e, b_at(row), sab);
+    }
+    block_sum2<NT>(s2, sab, S.red);                                // ||a||^2 and <a, b> in one reduction
+    const double anorm2 = s2, ab = sab;
     double before2 = anorm2, rho2 = anorm2;
+    // Fast path (the common case: the atom keeps at least half of its squared norm): rho^2 = ||a||^2 - ||Q'a||^2 by
+    // Pythagoras and z_t = (<a,b> - <Q'a, Q'b>) / rho, so NO reduction of length M stands between the triangular
+    // mat-vecs and the residual update, and v = a - A_S y is formed in the same row sweep that down-dates r.  Below the
+    // threshold (where the subtraction would cancel) the explicit path with DGKS re-orthogonalisation takes over.
+    bool fast = t == 0;
     for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
         if (sweep == 0 && gcol) {
             for (int i = tid; i < t; i += NT) S.g[i] = gcol[S.ssel[i] - idx_offset];   // g = (A'A)[S, j]
@@ -467,7 +497,21 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
             S.y[i] = acc;
             S.ys[i] = sweep ? S.ys[i] + acc : acc;
         }
+        if (sweep == 0 && warp == NT / 32 - 1) {                   // ||Q'a||^2 and <Q'a, Q'b> by the last warp, same phase
+            double p = 0.0, q = 0.0;
+            for (int i = lane; i < t; i += 32) { const double h = S.hh[i]; p = fma(h, h, p); q = fma(h, S.zs[i], q); }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                p += __shfl_xor_sync(0xffffffffu, p, off);
+                q += __shfl_xor_sync(0xffffffffu, q, off);
+            }
+            if (lane == 0) { S.red[2 * (NT / 32)] = p; S.red[2 * (NT / 32) + 1] = q; }
+        }
         __syncthreads();
+        if (sweep == 0) {
+            const double hn2 = S.red[2 * (NT / 32)];
+            if (anorm2 - hn2 >= 0.5 * anorm2) { rho2 = anorm2 - hn2; fast = true; break; }
+        }
         s2 = 0.0;
         for (int row = tid * W; row < ld; row += NT * W) {         // v -= A_S y, W rows per thread per 16 B load
             double acc[W];
@@ -503,17 +547,53 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
     if (!(rho2 > 1e-26 * anorm2)) return 1;                        // numerically dependent atom: not appended
     if (rho2 < ILLCOND_RATIO * anorm2) S.illcond = 1;
     const double rho = sqrt(rho2);
-    double sb = 0.0;
-    for (int row = tid; row < ld; row += NT) sb += S.v[row] * b_at(row);
-    const double zt = block_sum<NT>(sb, S.red) / rho;              // z_t = q_t' b
-    // residual: r = b - Q Q'b gains one term, r <- r - q_t z_t.  Identical to the reference's
-    // from-scratch b - A_S x_S (x_S = R^{-1} Q'b) up to rounding, at one pass less over A_S.
-    const double gam = zt / rho;
-    double s2r = 0.0;
-    for (int row = tid; row < ld; row += NT) {
-        const T rr = (T)(r_at(row) - gam * S.v[row]);
-        r_set(row, rr);
-        s2r += (double)rr * (double)rr;
+    double zt, s2r = 0.0;
+    if (fast) {
+        // z_t = q_t'b = (<a,b> - <Q'a, Q'b>) / rho;  r <- r - (z_t / rho) (a - A_S y), v formed on the fly
+        zt = (t > 0 ? ab - S.red[2 * (NT / 32) + 1] : ab) / rho;
+        const double gam = zt / rho;
+        for (int row = tid * W; row < ld; row += NT * W) {
+            double acc[W], acc1[W];
+#pragma unroll
+            for (int e = 0; e < W; ++e) { acc[e] = S.v[row + e]; acc1[e] = 0.0; }
+            int i = 0;
+#pragma unroll 2
+            for (; i + 1 < t; i += 2) {
+                double a0[W], a1[W];
+                RowVec<T>::load(S.colp[i] + row, a0);
+                RowVec<T>::load(S.colp[i + 1] + row, a1);
+                const double y0 = S.y[i], y1 = S.y[i + 1];
+#pragma unroll
+                for (int e = 0; e < W; ++e) { acc[e] = fma(-a0[e], y0, acc[e]); acc1[e] = fma(-a1[e], y1, acc1[e]); }
+            }
+            if (i < t) {
+                double a0[W];
+                RowVec<T>::load(S.colp[i] + row, a0);
+                const double y0 = S.y[i];
+#pragma unroll
+                for (int e = 0; e < W; ++e) acc[e] = fma(-a0[e], y0, acc[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < W; ++e) {
+                const double vq = acc[e] + acc1[e];
+                S.v[row + e] = vq;                                 // q_t = v / rho is read by forward regression
+                const T rr = (T)(r_at(row + e) - gam * vq);
+                r_set(row + e, rr);
+                s2r = fma((double)rr, (double)rr, s2r);
+            }
+        }
+    } else {
+        double sb = 0.0;
+        for (int row = tid; row < ld; row += NT) sb += S.v[row] * b_at(row);
+        zt = block_sum<NT>(sb, S.red) / rho;                       // z_t = q_t' b
+        // residual: r = b - Q Q'b gains one term, r <- r - q_t z_t.  Identical to the reference's
+        // from-scratch b - A_S x_S (x_S = R^{-1} Q'b) up to rounding, at one pass less over A_S.
+        const double gam = zt / rho;
+        for (int row = tid; row < ld; row += NT) {
+            const T rr = (T)(r_at(row) - gam * S.v[row]);
+            r_set(row, rr);
+            s2r += (double)rr * (double)rr;
+        }
     }
     nr2 = block_sum<NT>(s2r, S.red);
     // append the column [h; rho] to R  <=>  append [-R^{-1}h / rho; 1/rho] to R^{-1}
