@@ -1555,6 +1555,62 @@ static int one_shot(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig,
     return upload_common(w, Bmat, ldb, nsig, cudaMemcpyHostToDevice, allow_lazy);
 }
 
+// ---- zero-copy one-shot path for a few signals on a small dictionary ----------------------------------------------
+// A config-1-sized solve is ~55 us of kernel; an H2D copy, a D2H copy, two event records and two stream synchronisations
+// around it added another ~30.  Here the signals are copied (by the CPU) into the batch's pinned staging buffer, the
+// whole-solve kernel reads them and writes its results THROUGH THE MAPPING of that buffer, and the call is one launch and
+// one synchronisation.  Returns 1 when it does not apply (the caller takes the general path).
+static int one_shot_zero_copy(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig, int64_t kcap, int mode, int64_t k,
+                              int64_t l, double eps, int64_t stride, int64_t* sel_idx, double* coef, int64_t* nnz,
+                              double* resnorm, int64_t* iters) {
+    static const bool off = [] { const char* e = getenv("CSB200_ZERO_COPY"); return e && e[0] == '0'; }();
+    if (off || !Bmat || nsig < 1 || nsig > 8 || ldb < d->M || d->n_total != d->N) return 1;
+    const int64_t cap = kcap < 1 ? 1 : kcap;
+    csb200_batch* w = d->workspace;
+    if (w && (w->cap_sig < nsig || w->kcap < cap || w->cap_sig > 4 * nsig + 1024 || w->src_f32)) return 1;   // let one_shot() resize it
+    if (!w) {
+        int rc = batch_create_ex(d, nsig, cap, false, &w);
+        if (rc) return rc;
+        d->workspace = w;
+    }
+    const size_t es = d->esize();
+    const size_t sig_off = (w->state_result_bytes + 255) / 256 * 256, sig_bytes = (size_t)d->ld * nsig * es;
+    if (!w->host_stage || sig_off + sig_bytes > w->host_stage_bytes || w->profile) return 1;
+    int rc = set_device(d);
+    if (rc) return rc;
+    w->nsig = nsig; w->has_map = false; w->cur_P = 0;
+    const int64_t take = mode == 1 ? l : 1;
+    const bool cluster = use_cluster_solve(w, take);
+    if (!cluster && !(take <= MAX_S && use_small_solve(w))) return 1;
+    unsigned char* hs = w->host_stage;
+    for (int64_t sg = 0; sg < nsig; ++sg) {                       // signals -> pinned memory, rows padded to ld with zeros
+        unsigned char* dst = hs + sig_off + (size_t)sg * d->ld * es;
+        memcpy(dst, (const unsigned char*)Bmat + (size_t)sg * ldb * es, (size_t)d->M * es);
+        if (d->ld > d->M) memset(dst + (size_t)d->M * es, 0, (size_t)(d->ld - d->M) * es);
+    }
+    unsigned char* dev = nullptr;
+    CU_TRY(cudaHostGetDevicePointer((void**)&dev, hs, 0));
+    StateArgs a = state_args(w, 1, 1, eps, 0);
+    auto remap = [&](auto* p) { return reinterpret_cast<decltype(p)>(dev + ((unsigned char*)p - w->state_blk)); };
+    a.B = dev + sig_off;
+    a.resnorm = remap(w->resnorm); a.x = remap(w->x); a.nnz = remap(w->nnz); a.iters = remap(w->iters);
+    a.flags = remap(w->flags); a.done = remap(w->done); a.sel = remap(w->sel);
+    SmallSolveArgs q;
+    q.mode = mode; q.k = (int)k; q.l = (int)l; q.eps = eps; q.stride = (int)w->kcap;
+    q.x0_idx = nullptr; q.x0_val = nullptr; q.x0_nnz = nullptr; q.x0_stride = 0;
+    const bool f32 = d->dtype == CSB200_F32;
+    cudaError_t e = cluster ? launch_cluster_solve(a, q, f32, w->stream) : launch_small_solve(a, q, f32, w->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "whole-solve kernel (zero-copy)");
+    CU_TRY(cudaStreamSynchronize(w->stream));
+    w->lazy_input_check = false; w->solve_timed = false;
+    auto at = [&](const void* p) { return hs + ((const unsigned char*)p - w->state_blk); };
+    const int* hfl = (const int*)at(w->flags);
+    for (int64_t sg = 0; sg < nsig; ++sg) if (hfl[sg] & 4) { w->nsig = 0; return CSB200_ERR_NONFINITE_INPUT; }
+    return convert_results((size_t)nsig, (size_t)w->kcap, stride, (const int*)at(w->nnz), (const int*)at(w->sel),
+                           (const int*)at(w->iters), (const double*)at(w->x), (const double*)at(w->resnorm), sel_idx, coef, nnz,
+                           resnorm, iters);
+}
+
 // ---- pipelined one-shot path -------------------------------------------------------------------
 // Large host batches are cut into chunks that ping-pong between two workspaces, each with its own stream: while chunk
 // c is being solved, chunk c+1 is uploaded (copy engine) and chunk c-1's results are downloaded and converted on the
@@ -1755,7 +1811,9 @@ static int omp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsi
                                   [&](csb200_batch* w) { return csb200_batch_omp(w, k, eps); },
                                   PipeOut{sel_idx, coef, nnz, resnorm, iters});
     csb200_batch* b = nullptr;
-    int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
+    int rc = one_shot_zero_copy(d, Bmat, ldb, nsig, support_cap(d, k), 0, k, 1, eps, k, sel_idx, coef, nnz, resnorm, iters);
+    if (rc != 1) return rc;
+    rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
     b->skip_solve_sync = true;                 // csb200_batch_download below synchronises
     rc = csb200_batch_omp(b, k, eps);
@@ -1788,7 +1846,9 @@ static int gomp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t ns
                                   [&](csb200_batch* w) { return csb200_batch_gomp(w, l, k, eps); },
                                   PipeOut{sel_idx, coef, nnz, resnorm, iters});
     csb200_batch* b = nullptr;
-    int rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
+    int rc = l <= GOMP_MAX_L ? one_shot_zero_copy(d, Bmat, ldb, nsig, support_cap(d, k), 1, k, l, eps, k, sel_idx, coef, nnz, resnorm, iters) : 1;
+    if (rc != 1) return rc;
+    rc = one_shot(d, Bmat, ldb, nsig, support_cap(d, k), &b);
     if (rc) return rc;
     b->skip_solve_sync = true;                 // csb200_batch_download below synchronises
     rc = csb200_batch_gomp(b, l, k, eps);
@@ -1903,7 +1963,10 @@ static int mp_single(csb200_dict* d, const void* Bmat, int64_t ldb, int64_t nsig
                      double* resnorm) {
     std::lock_guard<std::mutex> lk(d->mu);
     csb200_batch* b = nullptr;
-    int rc = one_shot(d, Bmat, ldb, nsig, iters_k, &b);
+    int rc = (x0_idx && x0_val && x0_nnz) ? 1
+             : one_shot_zero_copy(d, Bmat, ldb, nsig, iters_k, 2, iters_k, 1, 0.0, iters_k, sel_idx, coef, nullptr, resnorm, nullptr);
+    if (rc != 1) return rc;
+    rc = one_shot(d, Bmat, ldb, nsig, iters_k, &b);
     if (rc) return rc;
     b->skip_solve_sync = !(x0_idx && x0_val && x0_nnz);   // csb200_batch_download below synchronises (a warm start's buffers are freed first)
     rc = csb200_batch_mp(b, iters_k, x0_idx, x0_val, x0_nnz, x0_stride);
