@@ -1581,7 +1581,8 @@ static int one_shot_zero_copy(csb200_dict* d, const void* Bmat, int64_t ldb, int
     w->nsig = nsig; w->has_map = false; w->cur_P = 0;
     const int64_t take = mode == 1 ? l : 1;
     const bool cluster = use_cluster_solve(w, take);
-    if (!cluster && !(take <= MAX_S && use_small_solve(w))) return 1;
+    const char* penv = getenv("CSB200_PERSIST");                 // a test forcing the cooperative kernel: general path
+    if (!cluster && ((penv && penv[0] == '1') || !(take <= MAX_S && use_small_solve(w)))) return 1;
     unsigned char* hs = w->host_stage;
     for (int64_t sg = 0; sg < nsig; ++sg) {                       // signals -> pinned memory, rows padded to ld with zeros
         unsigned char* dst = hs + sig_off + (size_t)sg * d->ld * es;
