@@ -104,6 +104,14 @@ int csb200_batch_upload_device(csb200_batch* batch, const void* dBmat, int64_t l
  *   gomp : src/matchingpursuit.jl:126-139 (k / l update!s of l atoms, then one of k % l)
  *   mp   : src/matchingpursuit.jl:34-40   (exactly `iters` update!s; optional warm start)
  * Each call blocks until the device work has finished.
+ * Notes on arithmetic (same mathematics as the reference, rounding-level differences):
+ *   - The residual is DOWN-DATED (r -= q_t q_t'b) and its norm accumulated from it; the reference recomputes
+ *     r = b - A x.  The two agree to ~1e-16 ||b||, so an eps-break is decided identically except when eps itself lies at
+ *     that rounding level (the default eps(T) on noise-free data solved past its true sparsity): there the decision is
+ *     noise in the reference too and nnz / iters may differ by the trailing no-information updates.
+ *   - FP32 dictionaries: see csb200_dict_create -- batches of >= 24 signals compute in FP64 on exact FP32 inputs, smaller
+ *     ones in FP32 storage with FP64 accumulation; both stay inside the FP32 bound (2e-5) of the reference's Float32
+ *     arithmetic, but a signal's last bits can depend on how many signals share its batch.
  */
 int csb200_batch_omp(csb200_batch* batch, int64_t k, double eps);
 int csb200_batch_gomp(csb200_batch* batch, int64_t l, int64_t k, double eps);
