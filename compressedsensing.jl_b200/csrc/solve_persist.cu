@@ -314,66 +314,75 @@ struct Red3 {
 // reduction; the triangular mat-vecs run in one warp (lane = output, 4 accumulators); and the new residual leaves for
 // the workers (store_r / after_store) before its norm is reduced.
 template <typename T, typename StoreR, typename AfterStore>
-__device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
+__device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ ajg, int ld,
                                            const double* __restrict__ bs, double* __restrict__ rs, Red3& red,
-                                           StoreR store_r, AfterStore after_store, double& nr2, const T* acache, int ucache,
+                                           StoreR store_r, AfterStore after_store, double& nr2, T* acache, int ucache,
                                            long long* stamp = nullptr) {
     constexpr int W = RowVec<T>::W;
+    using V = typename Vec<T>::type;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto mark = [&](int slot) { if (stamp && tid == 0) stamp[slot] = clock64(); };
     // active atom i: slot i of this CTA's shared-memory cache (address computed, so the loads are LDS -- a pointer
     // fetched from the colp table makes them generic loads at ~3x the latency) or, beyond the cache, the dictionary
     const int tc = t < ucache ? t : ucache;
-    double sa = 0.0, sb = 0.0, s2 = 0.0;
-    const T* ajs = t < ucache ? acache + (size_t)t * ld : aj;          // the new atom sits in cache slot t when it fits
+    const bool cached = t < ucache;
+    T* slot = acache + (size_t)(cached ? t : 0) * ld;
+    double* sc = red.buf + 9 * PW;                                     // [4] <a,a>, <a,b>, ||Q'a||^2, <Q'a, Q'b>
+    // v = a_j straight from the dictionary (L2), and into cache slot t while it fits: one pass, one barrier
     for (int row = tid * W; row < ld; row += PT * W) {
+        const V x = *reinterpret_cast<const V*>(ajg + row);
+        if (cached) *reinterpret_cast<V*>(slot + row) = x;
         double e[W];
-        if (t < ucache) RowVec<T>::load(acache + (size_t)t * ld + row, e); else RowVec<T>::load(aj + row, e);
+        RowVec<T>::load(reinterpret_cast<const T*>(&x), e);
 #pragma unroll
-        for (int q = 0; q < W; ++q) { S.v[row + q] = e[q]; sa = fma(e[q], e[q], sa); sb = fma(e[q], bs[row + q], sb); }
+        for (int q = 0; q < W; ++q) S.v[row + q] = e[q];
     }
-    (void)ajs;
-    double anorm2 = 0.0, rho2 = 0.0, before2 = 0.0;
-    if (t == 0) {                                                      // first atom: nothing to orthogonalise against
-        s2 = sa;
-        red.sum3(s2, sb, sa);
-        anorm2 = rho2 = sa;
-    } else {
-        __syncthreads();                                               // v is complete
-    }
+    const T* aj = cached ? slot : ajg;
+    __syncthreads();
     mark(5);
-    for (int sweep = 0; sweep < 2 && t > 0; ++sweep) {
-        for (int i = warp; i < t; i += PW) {                           // g = A_S' v, one warp per active atom
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            auto dot = [&](const T* ai) {
-                int row = lane * W;
-                for (; row + 32 * W < ld; row += 64 * W) {             // two steps per trip, four independent chains
-                    double e0[W], e1[W];
-                    RowVec<T>::load(ai + row, e0);
-                    RowVec<T>::load(ai + row + 32 * W, e1);
+    // one warp per dot product of length M: g_i = <a_i, v> for the t active atoms, then <v, v> and <v, b>
+    auto dot_with_v = [&](auto load2) {                                // load2(row, e[W]): W values of the other operand
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        int row = lane * W;
+        for (; row + 32 * W < ld; row += 64 * W) {                     // two steps per trip, four independent chains
+            double e0[W], e1[W];
+            load2(row, e0);
+            load2(row + 32 * W, e1);
 #pragma unroll
-                    for (int q = 0; q < W; ++q) {
-                        acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
-                        acc[2 + (q & 1)] = fma(e1[q], S.v[row + 32 * W + q], acc[2 + (q & 1)]);
-                    }
-                }
-                if (row < ld) {
-                    double e0[W];
-                    RowVec<T>::load(ai + row, e0);
+            for (int q = 0; q < W; ++q) {
+                acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
+                acc[2 + (q & 1)] = fma(e1[q], S.v[row + 32 * W + q], acc[2 + (q & 1)]);
+            }
+        }
+        if (row < ld) {
+            double e0[W];
+            load2(row, e0);
 #pragma unroll
-                    for (int q = 0; q < W; ++q) acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
-                }
-            };
-            if (i < tc) dot(acache + (size_t)i * ld); else dot(S.colp[i]);
-            double g = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-            g = warp_sum(g);
-            if (lane == 0) S.g[i] = g;
+            for (int q = 0; q < W; ++q) acc[q & 1] = fma(e0[q], S.v[row + q], acc[q & 1]);
+        }
+        return warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    };
+    auto gather_g = [&](bool with_norms) {
+        const int n = t + (with_norms ? 2 : 0);
+        for (int i = warp; i < n; i += PW) {
+            double g;
+            if (i < tc) { const T* ai = acache + (size_t)i * ld; g = dot_with_v([&](int row, double (&e)[W]) { RowVec<T>::load(ai + row, e); }); }
+            else if (i < t) { const T* ai = S.colp[i]; g = dot_with_v([&](int row, double (&e)[W]) { RowVec<T>::load(ai + row, e); }); }
+            else if (i == t) g = dot_with_v([&](int row, double (&e)[W]) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) e[q] = S.v[row + q]; });
+            else g = dot_with_v([&](int row, double (&e)[W]) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) e[q] = bs[row + q]; });
+            if (lane == 0) { if (i < t) S.g[i] = g; else sc[i - t] = g; }
         }
         __syncthreads();
-        if (sweep == 0) mark(6);
+    };
+    // hh = R^{-T} g = Q'v (hh_i = sum_{l <= i} T[l, i] g_l), its squared norm and <hh, Q'b>, and y = R^{-1} hh
+    // (y_i = sum_{l >= i} T[i, l] hh_l): one warp, lane = output index, no block barrier in between
+    auto mat_vecs = [&](int sweep) {
         if (warp == 0) {
-            // hh = R^{-T} g = Q'v (hh_i = sum_{l <= i} T[l, i] g_l) and y = R^{-1} hh (y_i = sum_{l >= i} T[i, l] hh_l):
-            // lane = output index, no block barrier in between
+            double p = 0.0, q2 = 0.0;
             for (int i = lane; i < t; i += 32) {
                 double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
                 const double* col = S.Tm + (size_t)i * S.ldT;
@@ -383,7 +392,17 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
                     h2 = fma(col[l + 2], S.g[l + 2], h2); h3 = fma(col[l + 3], S.g[l + 3], h3);
                 }
                 for (; l <= i; ++l) h0 = fma(col[l], S.g[l], h0);
-                S.hh[i] = (h0 + h1) + (h2 + h3);
+                const double h = (h0 + h1) + (h2 + h3);
+                S.hh[i] = h;
+                p = fma(h, h, p); q2 = fma(h, S.zs[i], q2);
+            }
+            if (sweep == 0) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    p += __shfl_xor_sync(0xffffffffu, p, off);
+                    q2 += __shfl_xor_sync(0xffffffffu, q2, off);
+                }
+                if (lane == 0) { sc[2] = p; sc[3] = q2; }
             }
             __syncwarp();
             for (int i = lane; i < t; i += 32) {
@@ -401,60 +420,86 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
             }
         }
         __syncthreads();
-        if (sweep == 0) mark(7);
-        s2 = 0.0; sb = 0.0;
-        for (int row = tid * W; row < ld; row += PT * W) {             // v -= A_S y on this thread's rows
-            double acc[2][W];
+    };
+    // v_rows(row, out[W]): v - A_S y on W rows (two chains)
+    auto v_rows = [&](int row, double (&out)[W]) {
+        double acc[2][W];
 #pragma unroll
-            for (int q = 0; q < W; ++q) { acc[0][q] = S.v[row + q]; acc[1][q] = 0.0; }
-            int i = 0;
+        for (int q = 0; q < W; ++q) { acc[0][q] = S.v[row + q]; acc[1][q] = 0.0; }
+        int i = 0;
 #pragma unroll 2
-            for (; i + 1 < tc; i += 2) {                                // cached atoms: shared-memory loads, two chains
-                double e0[W], e1[W];
-                RowVec<T>::load(acache + (size_t)i * ld + row, e0);
-                RowVec<T>::load(acache + (size_t)(i + 1) * ld + row, e1);
-                const double y0 = S.y[i], y1 = S.y[i + 1];
+        for (; i + 1 < tc; i += 2) {                                    // cached atoms: shared-memory loads, two chains
+            double e0[W], e1[W];
+            RowVec<T>::load(acache + (size_t)i * ld + row, e0);
+            RowVec<T>::load(acache + (size_t)(i + 1) * ld + row, e1);
+            const double y0 = S.y[i], y1 = S.y[i + 1];
 #pragma unroll
-                for (int q = 0; q < W; ++q) { acc[0][q] = fma(-e0[q], y0, acc[0][q]); acc[1][q] = fma(-e1[q], y1, acc[1][q]); }
-            }
-            if (i < tc) {
-                double e0[W];
-                RowVec<T>::load(acache + (size_t)i * ld + row, e0);
-                const double y0 = S.y[i];
-#pragma unroll
-                for (int q = 0; q < W; ++q) acc[0][q] = fma(-e0[q], y0, acc[0][q]);
-                ++i;
-            }
-            for (; i < t; ++i) {                                       // beyond the cache: from the dictionary (L2)
-                double e0[W];
-                RowVec<T>::load(S.colp[i] + row, e0);
-                const double y0 = S.y[i];
-#pragma unroll
-                for (int q = 0; q < W; ++q) acc[0][q] = fma(-e0[q], y0, acc[0][q]);
-            }
-#pragma unroll
-            for (int q = 0; q < W; ++q) {
-                const double vq = acc[0][q] + acc[1][q];
-                S.v[row + q] = vq; s2 = fma(vq, vq, s2); sb = fma(vq, bs[row + q], sb);
-            }
+            for (int q = 0; q < W; ++q) { acc[0][q] = fma(-e0[q], y0, acc[0][q]); acc[1][q] = fma(-e1[q], y1, acc[1][q]); }
         }
-        red.sum3(s2, sb, sa);                                          // ||v||^2, <v, b>, ||a||^2 (the first sweep's pass reduces it)
-        if (sweep == 0) { anorm2 = sa; before2 = sa; mark(8); } else mark(11);
-        rho2 = s2;
-        if (rho2 >= 0.5 * before2) break;                              // DGKS: one sweep was enough
-        before2 = rho2;
-        sa = 0.0;
+        if (i < tc) {
+            double e0[W];
+            RowVec<T>::load(acache + (size_t)i * ld + row, e0);
+            const double y0 = S.y[i];
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[0][q] = fma(-e0[q], y0, acc[0][q]);
+            ++i;
+        }
+        for (; i < t; ++i) {                                           // beyond the cache: from the dictionary (L2)
+            double e0[W];
+            RowVec<T>::load(S.colp[i] + row, e0);
+            const double y0 = S.y[i];
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[0][q] = fma(-e0[q], y0, acc[0][q]);
+        }
+#pragma unroll
+        for (int q = 0; q < W; ++q) out[q] = acc[0][q] + acc[1][q];
+    };
+
+    gather_g(true);                                                    // g, <a,a>, <a,b>
+    mark(6);
+    if (t > 0) mat_vecs(0);
+    mark(7);
+    const double anorm2 = sc[0], ab = sc[1];
+    double rho2 = anorm2, vb = ab;
+    // Fast path: the atom keeps at least half of its squared norm, so rho^2 = ||a||^2 - ||Q'a||^2 (Pythagoras) and
+    // <v, b> = <a, b> - <Q'a, Q'b> are safe, and no reduction of length M stands between the mat-vecs and the doorbells
+    bool fast = t == 0;
+    if (t > 0 && anorm2 - sc[2] >= 0.5 * anorm2) { fast = true; rho2 = anorm2 - sc[2]; vb = ab - sc[3]; }
+    if (!fast) {
+        // explicit path: v -= A_S y with ||v||^2 and <v, b> reduced; a second sweep when ||v|| collapsed (DGKS)
+        double before2 = anorm2;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            if (sweep == 1) { gather_g(false); mat_vecs(1); }
+            double s2 = 0.0, sb = 0.0, unused = 0.0;
+            for (int row = tid * W; row < ld; row += PT * W) {
+                double vq[W];
+                v_rows(row, vq);
+#pragma unroll
+                for (int q = 0; q < W; ++q) { S.v[row + q] = vq[q]; s2 = fma(vq[q], vq[q], s2); sb = fma(vq[q], bs[row + q], sb); }
+            }
+            red.sum3(s2, sb, unused);
+            rho2 = s2; vb = sb;
+            mark(sweep == 0 ? 8 : 11);
+            if (rho2 >= 0.5 * before2) break;
+            before2 = rho2;
+        }
     }
     if (!(rho2 > 1e-26 * anorm2)) return 1;                            // numerically dependent atom: not appended
     if (rho2 < ILLCOND_RATIO * anorm2) S.illcond = 1;
     const double irho = rsqrt(rho2);                                   // 1 / rho (<= 1 ulp), no division on the critical path
-    const double zt = sb * irho;                                       // z_t = q_t' b
+    const double zt = vb * irho;                                       // z_t = q_t' b
     const double gam = zt * irho;
     double s2r = 0.0;
     for (int row = tid * W; row < ld; row += PT * W) {                 // r <- r - q_t z_t on this thread's rows
+        double vq[W];
+        if (fast) v_rows(row, vq);
+        else {
+#pragma unroll
+            for (int q = 0; q < W; ++q) vq[q] = S.v[row + q];
+        }
 #pragma unroll
         for (int q = 0; q < W; ++q) {
-            const T rr = (T)(rs[row + q] - gam * S.v[row + q]);
+            const T rr = (T)(rs[row + q] - gam * vq[q]);
             rs[row + q] = (double)rr;
             store_r(row + q, rr);
             s2r = fma((double)rr, (double)rr, s2r);
@@ -629,17 +674,9 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             int in = 0;
             for (int i = tid; i < t; i += PT) in |= (S.ssel[i] == j);
             if (!__syncthreads_or(in) && t < kcap) {
-                // the new atom's column: copied into this CTA's shared memory while it fits (the later sweeps over the
-                // active atoms then never leave the SM), read from the dictionary otherwise
+                // the new atom's column goes into this CTA's shared memory while it fits (inside append_fast, in the same
+                // pass that loads v): the later sweeps over the active atoms then never leave the SM
                 const T* aj = A + (size_t)(j - a.idx_offset) * ld;
-                if (t < a.ucache) {
-                    T* slot = acache + (size_t)t * ld;
-                    using V = typename Vec<T>::type;
-                    const int nvec = ld / Vec<T>::W;
-                    for (int i = tid; i < nvec; i += PT) reinterpret_cast<V*>(slot)[i] = reinterpret_cast<const V*>(aj)[i];
-                    __syncthreads();
-                    aj = slot;
-                }
                 if (dbg && tid == 0) dbg[it * DBG_PHASES + 3] = clock64();
                 double nr2 = 0.0;
                 // the doorbells ring as soon as the new residual is on its way -- before its norm is known: if the eps test
@@ -690,7 +727,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
 template <typename T, int NS, int CG>
 __global__ void __launch_bounds__(PT, 1) persist_solve_kernel(PersistArgs a) {
     extern __shared__ __align__(16) unsigned char psm[];
-    __shared__ double red_v[NS < 9 ? 9 : NS][PW];                        // workers: [NS][PW]; updater: Red3's [3][3][PW]
+    __shared__ double red_v[NS < 10 ? 10 : NS][PW];                      // workers: [NS][PW]; updater: Red3's [3][3][PW] + 4 scalars
     __shared__ int red_i[NS][PW];
     __shared__ int s_state[PERSIST_MAX_SIGNALS];
     if ((int)blockIdx.x < a.ns) persist_updater<T>(a, psm, &red_v[0][0]);

@@ -788,11 +788,25 @@ def test_gomp_block_append_and_near_dependent_atoms(cs, po, block, monkeypatch):
         t = po.Trace()
         ref = po.gomp(A, Bm[:, s], l, k, eps=0.0, trace=t)
         n = int(nnz[s])
+        if s == 0:
+            # noise-free 3-atom signal: exactly recovered after two update!s; from then on the residual is rounding noise
+            # (1e-15) and WHICH atoms the remaining update!s add is decided by that noise (SURVEY 7 "bit-exact support vs a
+            # different summation order").  Pinned: the well-posed prefix of the selection sequence, the coefficients of
+            # those atoms -- cond(A_S) ~ 1e3 here; after the iterative refinement they meet the 1e-10 bar (round 1 needed
+            # 1e-6: x = R^{-1} z through the stored inverse alone is cond^2 eps accurate) -- and that every later atom
+            # carries a rounding-level coefficient.
+            first = [j for step, m in zip(t.added, t.margin) for j in step if True][:10]
+            assert sel[s, :10].tolist() == t.order()[:10] == first
+            lut = dict(zip(sel[s, :n].tolist(), coef[s, :n].tolist()))
+            want = dict(zip(ref.nzind, ref.nzval))
+            scale = max(abs(v) for v in want.values())
+            assert all(abs(lut[j] - want[j]) <= RTOL64 * scale for j in (100, 101, 7))
+            assert all(abs(v) < 1e-9 * scale for j, v in lut.items() if j not in (100, 101, 7))
+            assert res[s] < 1e-12 and t.resnorm[-1] < 1e-12
+            continue
         assert sel[s, :n].tolist() == t.order(), (s, sel[s, :n], t.order())
         idx, val = _sorted(sel[s], coef[s], n)
         assert idx.tolist() == ref.nzind
-        # cond(A_S) ~ 1e3 for signal 0: after the iterative refinement the coefficients are at the 1e-10 bar as well
-        # (round 1 needed 1e-6 here: x = R^{-1} z through the stored inverse alone is cond^2 eps accurate)
         assert _close(val, ref.nzval, RTOL64), (s, val, ref.nzval)
         assert abs(res[s] - t.resnorm[-1]) < 1e-9
 
