@@ -795,8 +795,7 @@ def test_gomp_block_append_and_near_dependent_atoms(cs, po, block, monkeypatch):
             # those atoms -- cond(A_S) ~ 1e3 here; after the iterative refinement they meet the 1e-10 bar (round 1 needed
             # 1e-6: x = R^{-1} z through the stored inverse alone is cond^2 eps accurate) -- and that every later atom
             # carries a rounding-level coefficient.
-            first = [j for step, m in zip(t.added, t.margin) for j in step if True][:10]
-            assert sel[s, :10].tolist() == t.order()[:10] == first
+            assert len(t.order()) >= 10 and sel[s, :10].tolist() == t.order()[:10]
             lut = dict(zip(sel[s, :n].tolist(), coef[s, :n].tolist()))
             want = dict(zip(ref.nzind, ref.nzval))
             scale = max(abs(v) for v in want.values())
