@@ -145,6 +145,7 @@ struct csb200_batch {
     unsigned char* persist_scratch = nullptr;   // whole-solve cooperative kernel: hand-over buffers (see run_persist_solve)
     size_t persist_bytes = 0;
     unsigned persist_epoch = 0;                 // launches so far: sequence numbers carry its low 16 bits
+    bool persist_failed = false, cluster_failed = false;   // a launch of that kernel was refused: use the general path
     // two-half overlap of large omp batches (run_omp_split): a high-priority stream for the correlation passes, a
     // low-priority one for the updates, events tying the two together
     cudaStream_t sp_gemm = nullptr, sp_upd = nullptr;
@@ -355,7 +356,7 @@ bool use_cluster_solve(const csb200_batch* b, int64_t take) {
     if (env && env[0] == '0') return false;
     const bool forced = env && env[0] == '1';
     if (!forced && (getenv("CSB200_SMALL_SOLVE") || getenv("CSB200_PERSIST"))) return false;
-    if (b->corr_impl_env != IMPL_AUTO || b->profile || d->n_total != d->N) return false;
+    if (b->corr_impl_env != IMPL_AUTO || b->profile || d->n_total != d->N || b->cluster_failed) return false;
     for (const char* hook : {"CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM"})
         if (getenv(hook)) return false;
     if (path_nsig(b->nsig) > 8) return false;
@@ -369,7 +370,11 @@ int run_cluster_solve(csb200_batch* b, int mode, int64_t k, int64_t l, double ep
     q.mode = mode; q.k = (int)k; q.l = (int)l; q.eps = eps; q.stride = (int)b->kcap;
     q.x0_idx = nullptr; q.x0_val = nullptr; q.x0_nnz = nullptr; q.x0_stride = 0;
     cudaError_t e = launch_cluster_solve(state_args(b, 1, 1, eps, 0), q, b->dict->dtype == CSB200_F32, b->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "cluster_solve");
+    if (e != cudaSuccess) {               // e.g. the device cannot place an 8-CTA cluster right now: general path from here on
+        cudaGetLastError();
+        b->cluster_failed = true;
+        return 1;
+    }
     b->other_launches++;
     return CSB200_OK;
 }
@@ -385,7 +390,7 @@ bool use_persist_solve(const csb200_batch* b, int mode) {
     if (env && env[0] == '0') return false;
     const bool forced = env && env[0] == '1';
     if (!forced && getenv("CSB200_SMALL_SOLVE")) return false;
-    if (b->corr_impl_env != IMPL_AUTO || b->profile || b->defer_finish || !d->coop) return false;
+    if (b->corr_impl_env != IMPL_AUTO || b->profile || b->defer_finish || !d->coop || b->persist_failed) return false;
     for (const char* hook : {"CSB200_UPDATE_IMPL", "CSB200_CLUSTER", "CSB200_GEMV_L2", "CSB200_GRAM"})
         if (getenv(hook)) return false;
     if (b->nsig < 1 || path_nsig(b->nsig) > PERSIST_MAX_SIGNALS || d->n_total != d->N) return false;
@@ -436,7 +441,11 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
     q.nnz = b->nnz; q.sel = b->sel; q.x = b->x; q.resnorm = b->resnorm; q.iters = b->iters; q.done = b->done; q.flags = b->flags;
     if (debug) CU_TRY(cudaMemsetAsync(q.dbg, 0, dbg_bytes, b->stream));
     cudaError_t e = launch_persist_solve(q, d->dtype == CSB200_F32, smem, b->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "persist_solve");
+    if (e != cudaSuccess) {               // cooperative launch refused (co-residency cannot be guaranteed): general path
+        cudaGetLastError();
+        b->persist_failed = true;
+        return 1;
+    }
     b->other_launches++;
     if (debug && k > 0) {                            // per-phase cycle counts of signal 0's updater and of worker 0
         constexpr int PH = 16;
@@ -1148,12 +1157,12 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
     if (use_cluster_solve(b, 1)) {
-        if ((rc = run_cluster_solve(b, 0, k, 1, eps))) return rc;
-        return finish(b, true);
+        if ((rc = run_cluster_solve(b, 0, k, 1, eps)) == CSB200_OK) return finish(b, true);
+        if (rc != 1) return rc;
     }
     if (use_persist_solve(b, 0) && !(use_small_solve(b) && getenv("CSB200_SMALL_SOLVE"))) {
-        if ((rc = run_persist_solve(b, 0, k, eps))) return rc;
-        return finish(b, true);
+        if ((rc = run_persist_solve(b, 0, k, eps)) == CSB200_OK) return finish(b, true);
+        if (rc != 1) return rc;
     }
     if (use_small_solve(b)) {
         if ((rc = run_small_solve(b, 0, k, 1, eps, nullptr, nullptr, nullptr, 0))) return rc;
@@ -1198,8 +1207,8 @@ int csb200_batch_gomp(csb200_batch* b, int64_t l, int64_t k, double eps) {
     std::lock_guard<std::mutex> lk(b->mu);
     if ((rc = set_device(d))) return rc;
     if (use_cluster_solve(b, l)) {
-        if ((rc = run_cluster_solve(b, 1, k, l, eps))) return rc;
-        return finish(b, true);
+        if ((rc = run_cluster_solve(b, 1, k, l, eps)) == CSB200_OK) return finish(b, true);
+        if (rc != 1) return rc;
     }
     if (l <= MAX_S && use_small_solve(b)) {
         if ((rc = run_small_solve(b, 1, k, l, eps, nullptr, nullptr, nullptr, 0))) return rc;
@@ -1396,12 +1405,12 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
         CU_TRY(cudaMemcpy(x0.nnz, hn.data(), b->nsig * sizeof(int), cudaMemcpyHostToDevice));
     }
     if (!warm && use_cluster_solve(b, 1)) {
-        if ((rc = run_cluster_solve(b, 2, iters, 1, 0.0))) return rc;
-        return finish(b, true);
+        if ((rc = run_cluster_solve(b, 2, iters, 1, 0.0)) == CSB200_OK) return finish(b, true);
+        if (rc != 1) return rc;
     }
     if (!warm && use_persist_solve(b, 2)) {
-        if ((rc = run_persist_solve(b, 2, iters, 0.0))) return rc;
-        return finish(b, true);
+        if ((rc = run_persist_solve(b, 2, iters, 0.0)) == CSB200_OK) return finish(b, true);
+        if (rc != 1) return rc;
     }
     if (use_small_solve(b)) {
         if ((rc = run_small_solve(b, 2, iters, 1, 0.0, x0.idx, x0.val, x0.nnz, (int)x0_stride))) return rc;
@@ -1601,7 +1610,7 @@ static int one_shot_zero_copy(csb200_dict* d, const void* Bmat, int64_t ldb, int
     q.x0_idx = nullptr; q.x0_val = nullptr; q.x0_nnz = nullptr; q.x0_stride = 0;
     const bool f32 = d->dtype == CSB200_F32;
     cudaError_t e = cluster ? launch_cluster_solve(a, q, f32, w->stream) : launch_small_solve(a, q, f32, w->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "whole-solve kernel (zero-copy)");
+    if (e != cudaSuccess) { cudaGetLastError(); if (cluster) w->cluster_failed = true; return 1; }
     CU_TRY(cudaStreamSynchronize(w->stream));
     w->lazy_input_check = false; w->solve_timed = false;
     auto at = [&](const void* p) { return hs + ((const unsigned char*)p - w->state_blk); };
