@@ -416,7 +416,8 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
     const size_t bell_bytes = (size_t)PERSIST_MAX_SIGNALS * d->num_sms * BELL_STRIDE * sizeof(unsigned long long);
     const size_t bell_off = cand_bytes + res_bytes, ctrl_off = bell_off + bell_bytes, dbg_off = ctrl_off + 256;
     static const bool debug = [] { const char* e = getenv("CSB200_PERSIST_DEBUG"); return e && e[0] == '1'; }();
-    const size_t dbg_bytes = debug ? (size_t)2 * 16 * (size_t)(k > 0 ? k : 1) * sizeof(long long) : 0;
+    // stamps: [2][k][16] phase clocks of updater 0 and worker 0, then [k][SMs] arrival clock of every worker's candidate record
+    const size_t dbg_bytes = debug ? (size_t)(2 * 16 + d->num_sms) * (size_t)(k > 0 ? k : 1) * sizeof(long long) : 0;
     const size_t need = dbg_off + dbg_bytes;
     if (need > b->persist_bytes) {
         cudaFree(b->persist_scratch);
@@ -449,7 +450,7 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
     b->other_launches++;
     if (debug && k > 0) {                            // per-phase cycle counts of signal 0's updater and of worker 0
         constexpr int PH = 16;
-        std::vector<long long> h((size_t)2 * PH * k);
+        std::vector<long long> h((size_t)(2 * PH + d->num_sms) * k);
         CU_TRY(cudaMemcpyAsync(h.data(), q.dbg, dbg_bytes, cudaMemcpyDeviceToHost, b->stream));
         CU_TRY(cudaStreamSynchronize(b->stream));
         double u[12] = {0}, w[5] = {0};
@@ -459,18 +460,46 @@ int run_persist_solve(csb200_batch* b, int mode, int64_t k, double eps) {
             const long long* w0 = &h[(size_t)(k + it) * PH];
             if (a0[0] && a0[4] && a0[3] && a0[9]) {
                 u[0] += a0[1] - a0[0]; u[1] += a0[2] - a0[1]; u[2] += a0[3] - a0[2];
-                u[3] += a0[5] - a0[3]; u[4] += a0[6] - a0[5]; u[5] += a0[7] - a0[6]; u[6] += a0[8] - a0[7];
-                if (a0[11]) { u[10] += a0[11] - a0[8]; ++n2; }
-                u[7] += a0[9] - (a0[11] ? a0[11] : a0[8]); u[8] += a0[10] - a0[9]; u[9] += a0[4] - a0[10];
+                const long long s8 = a0[8] ? a0[8] : a0[7];             // the explicit v -= A y pass runs on the slow path only
+                u[3] += a0[5] - a0[3]; u[4] += a0[6] - a0[5]; u[5] += a0[7] - a0[6]; u[6] += s8 - a0[7];
+                if (a0[11]) { u[10] += a0[11] - s8; ++n2; }
+                u[7] += a0[9] - (a0[11] ? a0[11] : s8); u[8] += a0[10] - a0[9]; u[9] += a0[4] - a0[10];
                 ++nu;
             }
             if (w0[0] && w0[4]) { w[0] += w0[1] - w0[0]; w[1] += w0[2] - w0[1]; w[2] += w0[3] - w0[2]; w[3] += w0[4] - w0[3]; w[4] += h[(size_t)(k + it + 1) * PH] ? h[(size_t)(k + it + 1) * PH] - w0[0] : 0; ++nw; }
+        }
+        {
+            double f[3] = {0}; int nf = 0;
+            for (int64_t it = 2; it + 1 < k; ++it) {
+                const long long* a0 = &h[(size_t)it * PH];
+                if (a0[12] && a0[13] && a0[2]) { f[0] += a0[12] - a0[1]; f[1] += a0[13] - a0[12]; f[2] += a0[2] - a0[13]; ++nf; }
+            }
+            if (nf) fprintf(stderr, "[csb200 persist] pick = warp arg-max %.0f + barrier %.0f + 16-way %.0f\n", f[0] / nf, f[1] / nf, f[2] / nf);
         }
         if (nu && nw)
             fprintf(stderr, "[csb200 persist] cycles/update!: updater wait-cands %.0f pick %.0f fetch %.0f | load-v+norm %.0f g %.0f hh,y %.0f v-=Ay+norm %.0f "
                             "(2nd sweep in %d of %d: %.0f) r-update+ring %.0f T+norm %.0f tail %.0f || worker wait-r %.0f load-r %.0f dots %.0f publish %.0f iteration %.0f\n",
                     u[0] / nu, u[1] / nu, u[2] / nu, u[3] / nu, u[4] / nu, u[5] / nu, u[6] / nu, n2, nu, n2 ? u[10] / n2 : 0.0, u[7] / nu, u[8] / nu,
                     u[9] / nu, w[0] / nw, w[1] / nw, w[2] / nw, w[3] / nw, w[4] / nw);
+        // arrival of the workers' records at updater 0, relative to the start of its wait (its own clock)
+        std::vector<std::pair<double, int>> arr;
+        for (int c = 0; c < q.workers; ++c) {
+            double acc = 0.0; int n = 0;
+            for (int64_t it = 1; it + 1 < k; ++it) {
+                const long long t0 = h[(size_t)it * PH], ta = h[(size_t)2 * PH * k + (size_t)it * (q.ns + q.workers) + c];
+                if (t0 && ta) { acc += (double)(ta - t0); ++n; }
+            }
+            if (n) arr.push_back({acc / n, c});
+        }
+        if (!arr.empty()) {
+            std::sort(arr.begin(), arr.end());
+            const size_t n = arr.size();
+            fprintf(stderr, "[csb200 persist] candidate arrival (cycles after the updater starts waiting): min %.0f (worker %d) p10 %.0f median %.0f p90 %.0f "
+                            "max %.0f (worker %d); latest five:", arr[0].first, arr[0].second, arr[n / 10].first, arr[n / 2].first, arr[n * 9 / 10].first,
+                    arr[n - 1].first, arr[n - 1].second);
+            for (size_t i = n >= 5 ? n - 5 : 0; i < n; ++i) fprintf(stderr, " %d:%.0f", arr[i].second, arr[i].first);
+            fprintf(stderr, "\n");
+        }
     }
     return CSB200_OK;
 }

@@ -117,6 +117,7 @@ struct PersistArgs {
     int workers;          // GEMV CTAs; grid = ns + workers
     int wcache;           // dictionary columns a worker keeps in shared memory for the whole solve
     int ucache;           // active-atom columns an updater keeps in shared memory
+    int nvl;              // register columns of the workers: 16-byte vectors per lane and column (0: none)
     unsigned long long* cand_ll;   // [ns][workers][4] per-worker arg-max of |c| as self-validating words {v lo, v hi, atom, -}
     unsigned long long* r_ll;      // [ns][ld][1 or 2] the residual handed to the workers, same word format
     unsigned long long* bell;      // [ns][workers][BELL_STRIDE] one doorbell per (signal, worker): (epoch + 1) << 32 | residual version

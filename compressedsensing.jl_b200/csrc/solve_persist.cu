@@ -96,6 +96,51 @@ template <> struct ResLL<float> {
     }
 };
 
+// ---- dictionary columns kept in REGISTERS -------------------------------------------------------------------------
+// A worker's 512 threads own 64 K registers (256 KiB) -- more than its shared memory.  The streaming loop needs about
+// half of them, so each warp keeps REG_VECS 16-byte vectors per lane (64 registers) of dictionary for the whole solve:
+// REG_VECS / NVL whole columns, NVL = vectors per lane and column (lane i holds the vectors i, i + 32, .. of a column,
+// the same layout and summation order as every other column).  At 1024 x 8192 FP64 that is one more 8 KiB column per
+// warp: 27 (shared memory) + 16 (registers) of a worker's 55-56 columns never leave the SM, and the L2 traffic per
+// `update!` drops from 33 to 15 MiB.
+constexpr int REG_VECS = 16;
+__host__ __device__ constexpr int reg_vectors_for(int NS, bool f32) { return (NS <= 2 && !f32) ? REG_VECS : 0; }   // FP32 variants spill with it
+
+template <typename T, int NS, int RQ, int NVL>
+__device__ __forceinline__ void reg_column_dots(const typename Vec<T>::type (&regc)[RQ > 0 ? RQ : 1], const T* __restrict__ rs, int ld,
+                                                int nvec, int lane, int ncols, int atom0, double (&best_v)[NS], int (&best_i)[NS]) {
+    constexpr int W = Vec<T>::W;
+    constexpr int RC = RQ / NVL;
+#pragma unroll
+    for (int c = 0; c < RC; ++c) {
+        if (c >= ncols) break;                                            // warp-uniform
+        double acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NVL; ++q) {
+            const int i = lane + 32 * q;
+            if (i < nvec) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    double rr[W];
+#pragma unroll
+                    for (int e = 0; e < W; ++e) rr[e] = (double)rs[(size_t)s * ld + i * W + e];
+                    fma_vec(acc[s], regc[c * NVL + q], rr);
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            double sum = acc[s];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            const double v = fabs(sum);
+            if (v >= 0.0 && cand_better(v, atom0 + c, best_v[s], best_i[s])) { best_v[s] = v; best_i[s] = atom0 + c; }
+        }
+    }
+}
+
 // ---- worker: c = A'r for NS residuals over this CTA's atom range, fused |c| arg-max --------------------------------
 template <typename T, int NS, int CG>
 __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double (*red_v)[PW], int (*red_i)[PW],
@@ -103,14 +148,23 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
     using V = typename Vec<T>::type;
     constexpr int W = Vec<T>::W;
     constexpr int RW = ResLL<T>::WORDS;
-    constexpr int UNR = CG * NS >= 32 ? 1 : (CG * NS >= 16 ? 2 : (CG * NS >= 4 ? 4 : 8));   // loads in flight vs the 128-register budget
+    constexpr int RQ = reg_vectors_for(NS, sizeof(T) == 4);
+    constexpr int UNR0 = CG * NS >= 32 ? 1 : (CG * NS >= 16 ? 2 : (CG * NS >= 4 ? 4 : 8));  // loads in flight vs the 128-register budget
+    constexpr int UNR = (RQ > 0 && UNR0 > 1) ? UNR0 / 2 : UNR0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = a.ld, ns = a.ns;
     const int w = (int)blockIdx.x - ns;
     const int lo = (int)((long long)a.N * w / a.workers), hi = (int)((long long)a.N * (w + 1) / a.workers);
     const int ncol = hi - lo;
     const int ncache = ncol < a.wcache ? ncol : a.wcache;
-    const int nstream = ncol - ncache;
+    // register columns follow the shared-memory ones: warp q keeps columns ncache + q * rcw + [0, rcw) of the range
+    const int nvl = RQ > 0 ? a.nvl : 0;                                   // vectors per lane and column: 0 (off), 4, 8 or 16
+    const int rcw = nvl ? RQ / nvl : 0;
+    const int nregs = nvl ? (ncol - ncache < PW * rcw ? ncol - ncache : PW * rcw) : 0;
+    const int rfirst = ncache + warp * rcw;
+    const int nreg_w = rfirst >= ncache + nregs ? 0 : (ncache + nregs - rfirst < rcw ? ncache + nregs - rfirst : rcw);
+    const int sfirst = ncache + nregs;                                    // streamed columns: [sfirst, ncol)
+    const int nstream = ncol - sfirst;
     const T* A = static_cast<const T*>(a.A);
     T* rs = reinterpret_cast<T*>(smem);                                   // [NS][ld]
     T* cache = rs + (size_t)NS * ld;                                      // [ncache][ld]: columns lo .. lo + ncache
@@ -126,6 +180,24 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
         const int total = ncache * nvec;
         for (int i = tid; i < total; i += PT) dst[i] = ldg_stream(src + i, pol);
     }
+    V regc[RQ > 0 ? RQ : 1];
+    if constexpr (RQ > 0) {
+        const int lg = nvl == 16 ? 4 : nvl == 8 ? 3 : 2;
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            const int c = q >> lg, i = lane + 32 * (q & (nvl - 1));
+            regc[q] = V{};
+            if (nvl && c < nreg_w && i < nvec) regc[q] = ldg_stream(reinterpret_cast<const V*>(A + (size_t)(lo + rfirst + c) * ld) + i, pol);
+        }
+    }
+    auto reg_pass = [&](double (&bv)[NS], int (&bi)[NS]) {
+        if constexpr (RQ > 0) {
+            if (nreg_w <= 0) return;
+            if (nvl == 16) reg_column_dots<T, NS, RQ, 16>(regc, rs, ld, nvec, lane, nreg_w, lo + rfirst, bv, bi);
+            else if (nvl == 8) reg_column_dots<T, NS, RQ, 8>(regc, rs, ld, nvec, lane, nreg_w, lo + rfirst, bv, bi);
+            else reg_column_dots<T, NS, RQ, 4>(regc, rs, ld, nvec, lane, nreg_w, lo + rfirst, bv, bi);
+        }
+    };
     for (int i = tid; i < (NS - ns) * ld; i += PT) rs[(size_t)ns * ld + i] = (T)0;     // unused signal slots
     {   // residual version 0 is b itself
         const V* src = reinterpret_cast<const V*>(static_cast<const T*>(a.B));
@@ -181,9 +253,14 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
         int best_i[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) { best_v[s] = -1.0; best_i[s] = INT_MAX; }
-        for (int g = warp; g < gs + gc; g += PW) {
+        // even warps take their register columns first, odd warps last: the L2 pipe is busy from the start of the pass
+        // to its end, and the register columns' FMA chains run under the other warps' loads
+        if (!(warp & 1)) reg_pass(best_v, best_i);
+        for (int g0 = 0, rnd = 0; g0 < gs + gc; g0 += PW, ++rnd) {
+            const int g = g0 + ((rnd & 1) ? PW - 1 - warp : warp);          // dealt back and forth: a warp with a streamed group
+            if (g >= gs + gc) continue;                                    // gets its second group last (and a cheap one)
             const bool streamed = g < gs;                                  // streamed groups first: their loads fly longest
-            const int first = streamed ? ncache + g * CG : (g - gs) * CG;  // column offset inside the range
+            const int first = streamed ? sfirst + g * CG : (g - gs) * CG;  // column offset inside the range
             const int limit = streamed ? ncol : ncache;
             double acc[CG][NS];
             const V* col[CG];
@@ -240,6 +317,7 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
                 }
             }
         }
+        if (warp & 1) reg_pass(best_v, best_i);
         if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) { red_v[s][warp] = best_v[s]; red_i[s][warp] = best_i[s]; }
@@ -379,45 +457,44 @@ __device__ __forceinline__ int append_fast(PursuitSmem<T>& S, int& t, int j, con
         __syncthreads();
     };
     // hh = R^{-T} g = Q'v (hh_i = sum_{l <= i} T[l, i] g_l), its squared norm and <hh, Q'b>, and y = R^{-1} hh
-    // (y_i = sum_{l >= i} T[i, l] hh_l): one warp, lane = output index, no block barrier in between
+    // (y_i = sum_{l >= i} T[i, l] hh_l).  Half a warp per output: 16 lanes split the sum and fold it with four shuffles,
+    // so each mat-vec is one short step for the whole block instead of a 32-long walk of a single warp (which was the
+    // longest phase of the append: 3.3k of 15k cycles).
     auto mat_vecs = [&](int sweep) {
-        if (warp == 0) {
-            double p = 0.0, q2 = 0.0;
-            for (int i = lane; i < t; i += 32) {
-                double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
-                const double* col = S.Tm + (size_t)i * S.ldT;
-                int l = 0;
-                for (; l + 3 <= i; l += 4) {
-                    h0 = fma(col[l], S.g[l], h0); h1 = fma(col[l + 1], S.g[l + 1], h1);
-                    h2 = fma(col[l + 2], S.g[l + 2], h2); h3 = fma(col[l + 3], S.g[l + 3], h3);
-                }
-                for (; l <= i; ++l) h0 = fma(col[l], S.g[l], h0);
-                const double h = (h0 + h1) + (h2 + h3);
-                S.hh[i] = h;
-                p = fma(h, h, p); q2 = fma(h, S.zs[i], q2);
+        const int half = lane >> 4, l16 = lane & 15;
+        const int ldT = S.ldT;
+        for (int i0 = 2 * warp; i0 < t; i0 += 2 * PW) {
+            const int i = i0 + half;
+            double acc = 0.0;
+            if (i < t) {
+                const double* col = S.Tm + (size_t)i * ldT;
+                for (int l = l16; l <= i; l += 16) acc = fma(col[l], S.g[l], acc);
             }
-            if (sweep == 0) {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    p += __shfl_xor_sync(0xffffffffu, p, off);
-                    q2 += __shfl_xor_sync(0xffffffffu, q2, off);
-                }
-                if (lane == 0) { sc[2] = p; sc[3] = q2; }
-            }
-            __syncwarp();
-            for (int i = lane; i < t; i += 32) {
-                double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+            for (int off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (l16 == 0 && i < t) S.hh[i] = acc;
+        }
+        __syncthreads();
+        for (int i0 = 2 * warp; i0 < t; i0 += 2 * PW) {
+            const int i = i0 + half;
+            double acc = 0.0;
+            if (i < t) {
                 const double* rowp = S.Tm + i;
-                int l = i;
-                for (; l + 3 < t; l += 4) {
-                    h0 = fma(rowp[(size_t)l * S.ldT], S.hh[l], h0); h1 = fma(rowp[(size_t)(l + 1) * S.ldT], S.hh[l + 1], h1);
-                    h2 = fma(rowp[(size_t)(l + 2) * S.ldT], S.hh[l + 2], h2); h3 = fma(rowp[(size_t)(l + 3) * S.ldT], S.hh[l + 3], h3);
-                }
-                for (; l < t; ++l) h0 = fma(rowp[(size_t)l * S.ldT], S.hh[l], h0);
-                const double y = (h0 + h1) + (h2 + h3);
-                S.y[i] = y;
-                S.ys[i] = sweep ? S.ys[i] + y : y;
+                for (int l = i + l16; l < t; l += 16) acc = fma(rowp[(size_t)l * ldT], S.hh[l], acc);
             }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (l16 == 0 && i < t) { S.y[i] = acc; S.ys[i] = sweep ? S.ys[i] + acc : acc; }
+        }
+        if (sweep == 0 && warp == PW - 1) {                            // ||Q'a||^2 and <Q'a, Q'b> for the fast path
+            double p = 0.0, q2 = 0.0;
+            for (int i = lane; i < t; i += 32) { const double h = S.hh[i]; p = fma(h, h, p); q2 = fma(h, S.zs[i], q2); }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                p += __shfl_xor_sync(0xffffffffu, p, off);
+                q2 += __shfl_xor_sync(0xffffffffu, q2, off);
+            }
+            if (lane == 0) { sc[2] = p; sc[3] = q2; }
         }
         __syncthreads();
     };
@@ -598,6 +675,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
                 if (!ok && (spin & 1023u) == 1023u && ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;
             }
             if (!ok) { s_fail = 1; continue; }
+            if (dbg) dbg[(size_t)2 * DBG_PHASES * a.k + (size_t)it * gridDim.x + c] = clock64();
             const double v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
             const int i = (int)(unsigned)w2;
             if (i >= 0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; }
@@ -610,7 +688,9 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
         }
         if (lane == 0) { s_cv[warp] = bv; s_ci[warp] = bi; }
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 12] = clock64();
         __syncthreads();
+        if (dbg && tid == 0) dbg[it * DBG_PHASES + 13] = clock64();
         if (s_fail) { failed = true; break; }
         bv = s_cv[0]; bi = s_ci[0];
 #pragma unroll
@@ -779,12 +859,19 @@ bool persist_plan(int ld, int N, int kcap, int ns, bool f32, int num_sms, Persis
     const int per = (N + workers - 1) / workers;              // atoms of the largest worker range
     int wcache = (int)((budget - wrk) / col);
     if (wcache > per) wcache = per;
+    // register columns (reg_column_dots): whole columns of 4, 8 or 16 vectors per lane
+    int nvl = 0;
+    {
+        static const bool off = [] { const char* e = getenv("CSB200_PERSIST_REGCACHE"); return e && e[0] == '0'; }();
+        const int nvec = ld / (f32 ? 4 : 2), per_lane = (nvec + 31) / 32;
+        if (!off && reg_vectors_for(NS, f32) > 0 && per_lane <= REG_VECS && per > wcache) nvl = per_lane <= 4 ? 4 : per_lane <= 8 ? 8 : 16;
+    }
     int ucache = (int)((budget - upd) / col);
     if (ucache > kcap) ucache = kcap;
     size_t smem = wrk + (size_t)wcache * col;
     const size_t us = upd + (size_t)ucache * col;
     if (us > smem) smem = us;
-    if (out) { out->workers = workers; out->wcache = wcache; out->ucache = ucache; }
+    if (out) { out->workers = workers; out->wcache = wcache; out->ucache = ucache; out->nvl = nvl; }
     if (smem_out) *smem_out = smem;
     return true;
 }
