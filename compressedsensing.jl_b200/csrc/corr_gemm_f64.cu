@@ -414,9 +414,16 @@ cudaError_t launch_corr_gemm_f64(const CUtensorMap* mapA, const CUtensorMap* map
     if (variant == 1)
         corr_gemm_f64_kernel<4, 4, 4, 4, 1><<<grid, 512, Pipe<1>::SMEM_BYTES, st>>>(
             *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx, 0, *mapR, nullptr);
-    else if (variant == 2)
+    else if (variant == 2) {
+        // measurement hook: CSB200_GEMM_NO_EPILOGUE=1 runs the main loop only (results are garbage): the cost of the
+        // fused top-S epilogue is the difference -- 2.45 % of the pass at the C2 shape (profiles/gemm_epilogue_r02.md).
+        // Starting warps 4-7 late so that the two warps of a scheduler reach the epilogue at different times did not
+        // recover any of it (15.88 ms for every skew from 0 to 24k cycles): one warp per scheduler cannot issue DMMA
+        // faster than it already does next to its partner.
+        static const bool no_epi = [] { const char* e = getenv("CSB200_GEMM_NO_EPILOGUE"); return e && e[0] == '1'; }();
         corr_gemm_f64_kernel<8, 4, 2, 4, 2><<<grid, 256, Pipe<2>::SMEM_BYTES, st>>>(
-            *mapA, *mapR, a.N, a.nsig, (kslices + 1) / 2, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx, 0, *mapR, nullptr);
+            *mapA, *mapR, a.N, a.nsig, (kslices + 1) / 2, tilesN, tilesB, band, no_epi ? 0 : a.S, a.P, a.idx_offset, a.pval, a.pidx, 0, *mapR, nullptr);
+    }
     else
         corr_gemm_f64_kernel<8, 4, 2, 4, 1><<<grid, 256, Pipe<1>::SMEM_BYTES, st>>>(
             *mapA, *mapR, a.N, a.nsig, kslices, tilesN, tilesB, band, a.S, a.P, a.idx_offset, a.pval, a.pidx, 0, *mapR, nullptr);
