@@ -325,6 +325,68 @@ corr_gemm_f64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         // acc[i][j][e] = c[atom = wm*8*MI + i*8 + g][signal = wn*8*NJ + j*8 + 2q + e]
         const int atom0 = tn * TILE_N + wm * 8 * MI + g;
         const int p = tn * WM + wm;
+        if (NJ == 4 && S == 1 && tn * TILE_N + TILE_N <= N) {
+            // omp / mp on an interior tile (the common case): one candidate per (signal, block), no exclusion of earlier
+            // picks, no bounds test.  The 8 lanes g = 0..7 of a quad column q hold candidates for the same 8 signals
+            // (j, e); instead of eight 3-level shuffle trees, a transposing butterfly halves the signals a lane keeps at
+            // every level (g bit 2 picks j >= 2, bit 1 picks j odd, bit 0 picks e), so 7 exchanges replace 24 and every
+            // lane ends with the block winner of ONE signal and stores it itself.  FP64 compares bound this epilogue.
+            double v8[8];
+            int i8[8];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double bv = fabs(acc[0][j][e]);
+                    int bi = atom0;
+                    if (!(bv >= 0.0)) { bv = -1.0; bi = INT_MAX; }           // NaN never wins
+#pragma unroll
+                    for (int i = 1; i < MI; ++i) {
+                        const double v = fabs(acc[i][j][e]);
+                        if (v > bv) { bv = v; bi = atom0 + i * 8; }          // idx ascends with i: first max wins
+                    }
+                    v8[j * 2 + e] = bv; i8[j * 2 + e] = bi;
+                }
+            }
+            const bool h2 = (g & 4) != 0, h1 = (g & 2) != 0, h0 = (g & 1) != 0;
+            double v4[4]; int i4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                                    // keep j in {0,1} or {2,3}
+                const double mine = h2 ? v8[c + 4] : v8[c], send = h2 ? v8[c] : v8[c + 4];
+                const int mi = h2 ? i8[c + 4] : i8[c], si = h2 ? i8[c] : i8[c + 4];
+                const double ov = __shfl_xor_sync(0xffffffffu, send, 16);
+                const int oi = __shfl_xor_sync(0xffffffffu, si, 16);
+                const bool take = cand_better(ov, oi, mine, mi);
+                v4[c] = take ? ov : mine; i4[c] = take ? oi : mi;
+            }
+            double v2[2]; int i2[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {                                    // keep the even or the odd j of the pair
+                const double mine = h1 ? v4[c + 2] : v4[c], send = h1 ? v4[c] : v4[c + 2];
+                const int mi = h1 ? i4[c + 2] : i4[c], si = h1 ? i4[c] : i4[c + 2];
+                const double ov = __shfl_xor_sync(0xffffffffu, send, 8);
+                const int oi = __shfl_xor_sync(0xffffffffu, si, 8);
+                const bool take = cand_better(ov, oi, mine, mi);
+                v2[c] = take ? ov : mine; i2[c] = take ? oi : mi;
+            }
+            double bv; int bi;
+            {                                                                // keep e = 0 or 1
+                const double mine = h0 ? v2[1] : v2[0], send = h0 ? v2[0] : v2[1];
+                const int mi = h0 ? i2[1] : i2[0], si = h0 ? i2[0] : i2[1];
+                const double ov = __shfl_xor_sync(0xffffffffu, send, 4);
+                const int oi = __shfl_xor_sync(0xffffffffu, si, 4);
+                const bool take = cand_better(ov, oi, mine, mi);
+                bv = take ? ov : mine; bi = take ? oi : mi;
+            }
+            const int jk = (h2 ? 2 : 0) + (h1 ? 1 : 0), ek = h0 ? 1 : 0;
+            const int sig = tb * TILE_B + wn * 8 * NJ + jk * 8 + 2 * q + ek;
+            if (sig < nsig && p < P) {
+                const size_t o = (size_t)sig * P + p;
+                pval[o] = bv;
+                pidx[o] = (bi == INT_MAX) ? -1 : bi + idx_offset;
+            }
+            continue;
+        }
         double pv[NJ][2];
         int pi[NJ][2];
         for (int s = 0; s < S; ++s) {

@@ -234,16 +234,34 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
             for (int s = 0; s < ns; ++s) { all_stop = all_stop && s_state[s] == 1; error = error || s_state[s] == 2; }
             if (all_stop || error) break;
             if (dbg && tid == 0) dbg[it * DBG_PHASES + 1] = clock64();
-            const int total = ns * ld, shift = (int)(((long long)w * 64) % total);   // workers start at different rows: all
-            for (int e0 = tid; e0 < total; e0 += PT) {                               // 147 of them read the same words
-                const int e = e0 + shift < total ? e0 + shift : e0 + shift - total;
-                const int s = e / ld;
-                if (s_state[s] != 0) continue;                            // a stopped signal keeps its last residual
-                const unsigned long long* p = a.r_ll + (size_t)e * RW;
-                T val;
-                unsigned spin = 0;
-                while (!ResLL<T>::load(p, seq, val) && ++spin < SPIN_LIMIT) {}
-                rs[e] = val;
+            const int shift = (int)(((long long)w * 64) % ld);            // workers start at different rows: all 147 of
+            // them read the same words.  Four words in flight per thread (two signals x two rows), then the stragglers
+            for (int s = 0; s < ns; s += 2) {
+                const bool h[2] = {s_state[s] == 0, s + 1 < ns && s_state[s + 1] == 0};   // a stopped signal keeps its last residual
+                if (!h[0] && !h[1]) continue;
+                for (int e0 = tid; e0 < ld; e0 += 2 * PT) {
+                    const unsigned long long* p[4];
+                    T* d[4];
+                    bool need[4], ok[4];
+                    T val[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ss = s + (u >> 1), ee = e0 + (u & 1) * PT;
+                        const int e = ee + shift < ld ? ee + shift : ee + shift - ld;
+                        need[u] = h[u >> 1] && ee < ld;
+                        p[u] = a.r_ll + ((size_t)ss * ld + e) * RW;
+                        d[u] = rs + (size_t)ss * ld + e;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ok[u] = need[u] ? ResLL<T>::load(p[u], seq, val[u]) : true;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!need[u]) continue;
+                        unsigned spin = 0;
+                        while (!ok[u] && ++spin < SPIN_LIMIT) ok[u] = ResLL<T>::load(p[u], seq, val[u]);
+                        *d[u] = val[u];
+                    }
+                }
             }
         }
         __syncthreads();
@@ -324,16 +342,25 @@ __device__ void persist_worker(const PersistArgs& a, unsigned char* smem, double
         }
         __syncthreads();
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 3] = clock64();
-        if (tid < ns) {                                                    // this worker's candidate of signal `tid`
-            double bv = red_v[tid][0];
-            int bi = red_i[tid][0];
-            for (int q = 1; q < PW; ++q)
-                if (cand_better(red_v[tid][q], red_i[tid][q], bv, bi)) { bv = red_v[tid][q]; bi = red_i[tid][q]; }
-            const unsigned seq = seq0 | (unsigned)(it + 1);
-            const unsigned long long b = (unsigned long long)__double_as_longlong(bv);
-            unsigned long long* rec = a.cand_ll + ((size_t)tid * a.workers + w) * 4;
-            ll_store2(rec, ll_word((unsigned)b, seq), ll_word((unsigned)(b >> 32), seq));
-            ll_store(rec + 2, ll_word((unsigned)((bi == INT_MAX) ? -1 : bi + a.idx_offset), seq));
+        if (warp < ns) {                                                   // warp s folds the PW per-warp results of signal s
+            double bv = lane < PW ? red_v[warp][lane] : -1.0;
+            int bi = lane < PW ? red_i[warp][lane] : INT_MAX;
+#pragma unroll
+            for (int off = PW / 2; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                const unsigned seq = seq0 | (unsigned)(it + 1);
+                const unsigned long long b = (unsigned long long)__double_as_longlong(bv);
+                // (the record address is rebuilt here on purpose: hoisted out of the loop it was spilled to local memory)
+                int opaque_zero;
+                asm volatile("mov.u32 %0, 0;" : "=r"(opaque_zero));
+                unsigned long long* rec = a.cand_ll + ((size_t)(warp + opaque_zero) * a.workers + w) * 4;
+                ll_store2(rec, ll_word((unsigned)b, seq), ll_word((unsigned)(b >> 32), seq));
+                ll_store(rec + 2, ll_word((unsigned)((bi == INT_MAX) ? -1 : bi + a.idx_offset), seq));
+            }
         }
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 4] = clock64();
     }
@@ -619,8 +646,7 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
     T* acache = reinterpret_cast<T*>(smem + acache_off);
     S.Tm = Tsm; S.Tsm = Tsm; S.ldT = ldT; S.Tg = nullptr; S.kcap = kcap; S.red = red_buf;
     Red3 red{red_buf, 0};
-    __shared__ int s_j, s_fail, s_ci[PW];
-    __shared__ double s_cv[PW];
+    __shared__ int s_j, s_fail;
 
     const T* A = static_cast<const T*>(a.A);
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
@@ -660,43 +686,45 @@ __device__ void persist_updater(const PersistArgs& a, unsigned char* smem, doubl
             break;
         }
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 0] = clock64();
-        // candidates of this update!: thread c waits for worker c's record
+        // candidates of this update!: ONE warp collects every worker's record (lane l waits for workers l, l + 32, ..),
+        // folds them with five shuffles and hands the winner to the block through shared memory -- one barrier, no second
+        // reduction stage (a 16-way pass over per-warp results by all 512 threads cost 3.6k cycles here)
         const unsigned cseq = seq0 | (unsigned)(it + 1);
-        double bv = -1.0;
-        int bi = INT_MAX;
-        for (int c = tid; c < a.workers; c += PT) {
-            const unsigned long long* rec = a.cand_ll + ((size_t)sig * a.workers + c) * 4;
-            unsigned long long w0 = 0, w1 = 0, w2 = 0;
-            bool ok = false;
-            for (unsigned spin = 0; spin < SPIN_LIMIT && !ok; ++spin) {
-                ll_load2(rec, w0, w1);
-                w2 = ll_load(rec + 2);
-                ok = (unsigned)(w0 >> 32) == cseq && (unsigned)(w1 >> 32) == cseq && (unsigned)(w2 >> 32) == cseq;
-                if (!ok && (spin & 1023u) == 1023u && ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;
+        if (warp == 0) {
+            double bv = -1.0;
+            int bi = INT_MAX;
+            bool lost = false;
+            for (int c = lane; c < a.workers; c += 32) {
+                const unsigned long long* rec = a.cand_ll + ((size_t)sig * a.workers + c) * 4;
+                unsigned long long w0 = 0, w1 = 0, w2 = 0;
+                bool ok = false;
+                for (unsigned spin = 0; spin < SPIN_LIMIT && !ok; ++spin) {
+                    ll_load2(rec, w0, w1);
+                    w2 = ll_load(rec + 2);
+                    ok = (unsigned)(w0 >> 32) == cseq && (unsigned)(w1 >> 32) == cseq && (unsigned)(w2 >> 32) == cseq;
+                    if (!ok && (spin & 1023u) == 1023u && ld_relaxed_u32(a.ctrl + PERSIST_MAX_SIGNALS) == epoch1) break;
+                }
+                if (!ok) { lost = true; continue; }
+                if (dbg) dbg[(size_t)2 * DBG_PHASES * a.k + (size_t)it * gridDim.x + c] = clock64();
+                const double v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+                const int i = (int)(unsigned)w2;
+                if (i >= 0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; }
             }
-            if (!ok) { s_fail = 1; continue; }
-            if (dbg) dbg[(size_t)2 * DBG_PHASES * a.k + (size_t)it * gridDim.x + c] = clock64();
-            const double v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
-            const int i = (int)(unsigned)w2;
-            if (i >= 0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; }
-        }
-        if (dbg && tid == 0) dbg[it * DBG_PHASES + 1] = clock64();
+            if (dbg && tid == 0) dbg[it * DBG_PHASES + 1] = clock64();
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            lost = __any_sync(0xffffffffu, lost);
+            if (lane == 0) { s_j = (bi == INT_MAX) ? -1 : bi; s_fail = lost ? 1 : 0; }
+            if (dbg && tid == 0) dbg[it * DBG_PHASES + 12] = clock64();
         }
-        if (lane == 0) { s_cv[warp] = bv; s_ci[warp] = bi; }
-        if (dbg && tid == 0) dbg[it * DBG_PHASES + 12] = clock64();
         __syncthreads();
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 13] = clock64();
         if (s_fail) { failed = true; break; }
-        bv = s_cv[0]; bi = s_ci[0];
-#pragma unroll
-        for (int q = 1; q < PW; ++q)
-            if (cand_better(s_cv[q], s_ci[q], bv, bi)) { bv = s_cv[q]; bi = s_ci[q]; }
-        const int j = (bi == INT_MAX) ? -1 : bi;                         // global atom index or -1 (every thread has it)
+        const int j = s_j;                                               // global atom index or -1 (every thread has it)
         const unsigned rseq = seq0 | (unsigned)(it + 1);                 // the residual version this update! produces
         const bool more = it + 1 < a.k;                                  // somebody will read it
         if (dbg && tid == 0) dbg[it * DBG_PHASES + 2] = clock64();
@@ -836,7 +864,7 @@ cudaError_t persist_launch_t(const PersistArgs& a, int NS, size_t smem, cudaStre
         case 1: return persist_launch<T, 1, 2>(a, smem, st);
         case 2: return persist_launch<T, 2, 2>(a, smem, st);
         case 4: return persist_launch<T, 4, 4>(a, smem, st);
-        default: return persist_launch<T, 8, 2>(a, smem, st);
+        default: return persist_launch<T, 8, 4>(a, smem, st);
     }
 }
 
