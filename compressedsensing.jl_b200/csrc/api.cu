@@ -149,7 +149,7 @@ struct csb200_batch {
     // two-half overlap of large omp batches (run_omp_split): a high-priority stream for the correlation passes, a
     // low-priority one for the updates, events tying the two together
     cudaStream_t sp_gemm = nullptr, sp_upd = nullptr;
-    cudaEvent_t sp_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, G[2], U[2], end
+    cudaEvent_t sp_ev[2 + 2 * 4] = {};          // start, end, G[parts], U[parts]
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -590,26 +590,46 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
     if (rc) return rc;
     b->cur_P = (int)P;
     b->cur_dense_ld = 0;
-    // halves: whole 128-signal tiles; the first half takes the extra tile
+    // parts: whole 128-signal tiles, as even as possible (CSB200_SPLIT_PARTS = 2..4, default 2).  Measured at the headline
+    // config (profiles/split_r02.md): 2, 3 and 4 parts give the same 63.8k solves/s -- the 0.2-0.8 ms the correlation
+    // stream idles at every pass boundary is not an update that ran out of time but the update's backlog of small CTAs
+    // taking the SMs before the next pass's 148 large ones are placed.
+    const int parts_env = [] { const char* e = getenv("CSB200_SPLIT_PARTS"); const int v = e ? atoi(e) : 2; return v < 2 ? 2 : (v > 4 ? 4 : v); }();   // read per solve: a test hook
     const int64_t tiles = (b->nsig + 127) / 128;
-    const int64_t n0 = ((tiles + 1) / 2) * 128, n1 = b->nsig - n0;
-    const int64_t start[2] = {0, n0}, count[2] = {n0, n1};
-    CUtensorMap mapR[2];
-    for (int h = 0; h < 2; ++h)
+    const int NP = (int)(tiles < parts_env ? tiles : parts_env);
+    int64_t start[4], count[4];
+    {
+        int64_t t0 = 0;
+        for (int h = 0; h < NP; ++h) {
+            const int64_t nt = tiles / NP + (h < tiles % NP ? 1 : 0);
+            start[h] = t0 * 128;
+            const int64_t end = (t0 + nt) * 128 < b->nsig ? (t0 + nt) * 128 : b->nsig;
+            count[h] = end - start[h];
+            t0 += nt;
+        }
+    }
+    CUtensorMap mapR[4];
+    for (int h = 0; h < NP; ++h)
         if ((rc = make_operand_map(&mapR[h], static_cast<char*>(b->dR) + (size_t)start[h] * d->ld * 8, d->ld, count[h]))) return rc;
     cudaStream_t G = b->sp_gemm, U = b->sp_upd;
     static const bool dbg_split = [] { const char* e = getenv("CSB200_SPLIT_DEBUG"); return e && e[0] == '1'; }();
+    // CSB200_SPLIT_CTAS_PER_SM=1: the update under a pass as a fixed grid of one CTA per SM walking the signals.  It
+    // removes the idle time at the pass boundaries completely (0.26 ms per solve instead of 24) but the passes then run
+    // 14.6 % slower (the resident update competes for the FP64 pipe from the first cycle to the last): 57.1k instead of
+    // 63.8k solves/s.  Default 0 = one CTA per signal.
+    const int cap_per_sm = [] { const char* e = getenv("CSB200_SPLIT_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    const bool capped = cap_per_sm > 0;
     static const unsigned spacer_ns = [] { const char* e = getenv("CSB200_SPLIT_SPACER_US"); return (unsigned)((e ? atof(e) : 0.0) * 1e3); }();
     std::vector<cudaEvent_t> dbg_ev;
-    cudaEvent_t ev_start = b->sp_ev[0], *evG = &b->sp_ev[1], *evU = &b->sp_ev[3], ev_end = b->sp_ev[5];
+    cudaEvent_t ev_start = b->sp_ev[0], ev_end = b->sp_ev[1], *evG = &b->sp_ev[2], *evU = &b->sp_ev[6];
     cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), false, b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "reset_state");
     CU_TRY(cudaEventRecord(ev_start, b->stream));
     CU_TRY(cudaStreamWaitEvent(G, ev_start, 0));
     CU_TRY(cudaStreamWaitEvent(U, ev_start, 0));
     for (int64_t it = 0; it < k; ++it) {
-        for (int h = 0; h < 2; ++h) {
-            if (it > 0) CU_TRY(cudaStreamWaitEvent(G, evU[h], 0));       // the half's residuals of this update! are in place
+        for (int h = 0; h < NP; ++h) {
+            if (it > 0) CU_TRY(cudaStreamWaitEvent(G, evU[h], 0));       // the part's residuals of this update! are in place
             CorrArgs c;
             c.A = d->dA; c.R = static_cast<char*>(b->dR) + (size_t)start[h] * d->ld * 8;
             c.M = (int)d->M; c.ld = (int)d->ld; c.N = (int)d->N; c.nsig = (int)count[h]; c.S = 1; c.P = (int)P;
@@ -631,12 +651,15 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
             // other half's pass places its CTAs before the update's 32 768 CTAs reach the idle SMs.  Measured: it does not
             // help -- the update, at one CTA per SM under the pass, needs about as long as the pass itself, so the head
             // start it gets without the spacer is worth more than the tidy placement.
-            if (spacer_ns > 0 && !(it + 1 == k && h == 1)) {
+            if (spacer_ns > 0 && !(it + 1 == k && h == NP - 1)) {
                 e = launch_spacer(spacer_ns, U);
                 if (e != cudaSuccess) return fail_cuda(e, "spacer");
             }
             StateArgs ua = state_args_range(b, start[h], count[h], 1, 1, eps, 0);
             ua.max_smem_carveout = 1;
+            // under a pass: one CTA per SM walks the part's signals (no backlog at the pass boundary); the updates after
+            // the last pass have the GPU to themselves and use the full grid
+            if (capped && it + 1 < k) ua.grid_cap = d->num_sms * cap_per_sm;
             if (dbg_split) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); CU_TRY(cudaEventRecord(ev, U)); dbg_ev.push_back(ev); }
             e = launch_omp_update(ua, false, U);
             if (e != cudaSuccess) return fail_cuda(e, "omp_update");
@@ -657,12 +680,25 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
         fprintf(stderr, "[csb200 split] %zu update launches: total %.2f ms, min %.3f, max %.3f ms each (alone: ~0.75 ms per half at the headline config)\n",
                 dbg_ev.size() / 2, tot, mn, mx);
         if (b->profile && b->ev_used >= 4) {                             // timeline of the first update!s (ms since the first pass began)
-            const size_t g0 = b->ev_used - (size_t)4 * k;                // this solve's 2k (start, stop) pairs
+            const size_t g0 = b->ev_used - (size_t)2 * NP * k;           // this solve's NP k (start, stop) pairs
+            {   // idle time on the correlation stream between consecutive passes (same-stream events)
+                double gaps = 0, passes = 0; float worst = 0; size_t worst_i = 0;
+                for (size_t i = 0; i < (size_t)NP * k; ++i) {
+                    float ms = 0; cudaEventElapsedTime(&ms, b->ev[g0 + 2 * i], b->ev[g0 + 2 * i + 1]); passes += ms;
+                    if (i + 1 < (size_t)NP * k) {
+                        cudaEventElapsedTime(&ms, b->ev[g0 + 2 * i + 1], b->ev[g0 + 2 * i + 2]);
+                        gaps += ms; if (ms > worst) { worst = ms; worst_i = i; }
+                    }
+                }
+                float span = 0; cudaEventElapsedTime(&span, b->ev[g0], b->ev[g0 + 2 * NP * k - 1]);
+                fprintf(stderr, "[csb200 split] %lld passes: %.2f ms in passes, %.2f ms idle between them (largest %.3f ms after launch %zu), first start to last end %.2f ms\n",
+                        (long long)(NP * k), passes, gaps, worst, worst_i, span);
+            }
             for (size_t i = 0; i < 8 && 2 * i + 1 < dbg_ev.size(); ++i) {
                 float gs = 0, ge = 0, us = 0, ue = 0;
                 cudaEventElapsedTime(&gs, b->ev[g0], b->ev[g0 + 2 * i]); cudaEventElapsedTime(&ge, b->ev[g0], b->ev[g0 + 2 * i + 1]);
                 cudaEventElapsedTime(&us, b->ev[g0], dbg_ev[2 * i]); cudaEventElapsedTime(&ue, b->ev[g0], dbg_ev[2 * i + 1]);
-                fprintf(stderr, "[csb200 split]   launch %zu (half %zu): pass %.3f .. %.3f   update %.3f .. %.3f\n", i, i & 1, gs, ge, us, ue);
+                fprintf(stderr, "[csb200 split]   launch %zu (part %zu): pass %.3f .. %.3f   update %.3f .. %.3f\n", i, i % NP, gs, ge, us, ue);
             }
         }
         for (auto ev : dbg_ev) cudaEventDestroy(ev);

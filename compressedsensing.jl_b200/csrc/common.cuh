@@ -82,6 +82,7 @@ struct StateArgs {
     int dense_ld = 0;           // > 0: pval is the dense |A'r| matrix [nsig][dense_ld] (no pidx); 0: per-block candidates
     double max_eps = 0.0;       // forward_step! returns false unless ||r|| > max_eps   (:60)
     double min_delta2 = 0.0;    // ... and unless min_delta^2 < max_j delta2_j          (:63)
+    int grid_cap = 0;           // > 0: omp_update_kernel runs with at most this many CTAs, each walking several signals
     int max_smem_carveout = 0;  // launch hint: ask for the SM's largest shared-memory carve-out, i.e. the configuration the
                                 // DMMA correlation kernel runs under, so that CTAs of both kernels can share an SM
 };

@@ -55,8 +55,7 @@ constexpr int T_SMEM_MAX_K = 96;
 // NT = 128 threads, 8 CTAs/SM for one atom per update (omp); NT = 256 with the block-append working set
 // (BLOCK: up to `bm` new atoms orthogonalised together, update_common.cuh append_block) for gomp.
 template <typename T, int NT, bool BLOCK>
-__global__ void __launch_bounds__(NT, BLOCK ? 2 : 8)
-omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int bm) {
+__device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __restrict__ Acache, int t_in_smem, int bm, const int sig) {
     extern __shared__ double dsm[];
     const int ld = a.ld, kcap = a.kcap;
     PursuitSmem<T> S;
@@ -86,7 +85,6 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     __shared__ int s_J[BLOCK_MAX];
     __shared__ const T* s_Jcol[BLOCK_MAX];
 
-    const int sig = blockIdx.x;
     const int tid = threadIdx.x;
     if (a.done[sig] && !a.ignore_done) return;                     // the reference `break`s (:79,:132)
     // forward regression (`forward_step!`, src/forward.jl:56-67): same append / solve tail as omp, different
@@ -222,6 +220,19 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
         a.iters[sig] += 1;
         if (flags) a.flags[sig] |= flags;
         if (!(nr >= a.eps)) a.done[sig] = 1;                       // `norm(residual!(P, x)) >= eps || break`
+    }
+}
+
+// One CTA per signal (grid = nsig), or -- StateArgs::grid_cap > 0 -- a fixed number of CTAs that walk the signals with a
+// grid stride.  The capped form is what runs UNDER a correlation pass (api.cu, run_omp_split): with one CTA per SM from
+// the first signal to the last there is no backlog of small CTAs to flood the SMs the moment the pass's 148 large CTAs
+// retire, which kept the next pass from being placed for 0.2-0.8 ms at every boundary.
+template <typename T, int NT, bool BLOCK>
+__global__ void __launch_bounds__(NT, BLOCK ? 2 : 8)
+omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int bm) {
+    for (int sig = blockIdx.x; sig < a.nsig; sig += gridDim.x) {
+        omp_update_body<T, NT, BLOCK>(a, Acache, t_in_smem, bm, sig);
+        if (sig + (int)gridDim.x < a.nsig) __syncthreads();        // the shared-memory state is rebuilt per signal
     }
 }
 
@@ -583,7 +594,8 @@ cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void*
         e = cudaFuncSetAttribute(omp_update_kernel<T, UT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  a.max_smem_carveout ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
         if (e != cudaSuccess) return e;
-        omp_update_kernel<T, UT, false><<<a.nsig, UT, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, 0);
+        const int grid = a.grid_cap > 0 && a.grid_cap < a.nsig ? a.grid_cap : a.nsig;
+        omp_update_kernel<T, UT, false><<<grid, UT, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, 0);
     }
     return cudaGetLastError();
 }

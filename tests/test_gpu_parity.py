@@ -447,11 +447,15 @@ def test_multi_device_handle_fans_out_bit_identically(cs, po):
         assert ei.value.status == -3
 
 
-def test_two_half_overlap_is_bit_identical(cs, po, monkeypatch):
-    """Large omp batches run as two halves on a high- and a low-priority stream so that the update of one half overlaps
-    the correlation pass of the other (api.cu run_omp_split): same kernels on the same data, so every output must equal
-    the plain loop (CSB200_SPLIT=0) bit for bit -- uneven halves, ragged last tile, eps-breaks included -- and the
-    oracle on a sample."""
+@pytest.mark.parametrize("parts,ctas_per_sm", [(2, 0), (3, 0), (3, 1)])
+def test_two_half_overlap_is_bit_identical(cs, po, monkeypatch, parts, ctas_per_sm):
+    """Large omp batches run as two halves (or CSB200_SPLIT_PARTS parts) on a high- and a low-priority stream so that the
+    update of one part overlaps the correlation pass of the next (api.cu run_omp_split): same kernels on the same data,
+    so every output must equal the plain loop (CSB200_SPLIT=0) bit for bit -- uneven parts, ragged last tile, eps-breaks
+    included -- and the oracle on a sample.  Also with the update as a fixed grid of one CTA per SM walking the signals
+    (CSB200_SPLIT_CTAS_PER_SM=1)."""
+    monkeypatch.setenv("CSB200_SPLIT_PARTS", str(parts))
+    monkeypatch.setenv("CSB200_SPLIT_CTAS_PER_SM", str(ctas_per_sm))
     rng = np.random.default_rng(515)
     M, N, k, B = 100, 300, 5, 8192 + 77
     A = po.gaussian_dictionary(rng, M, N)
@@ -469,7 +473,7 @@ def test_two_half_overlap_is_bit_identical(cs, po, monkeypatch):
                 batch.omp(k, 1e-9)
                 ms, launches, other = batch.corr_time()
                 batch.profile(False)
-                assert launches == (2 * k if mode == "1" else k) and ms > 0
+                assert launches == (parts * k if mode == "1" else k) and ms > 0
                 out[mode] = batch.download(k) + (batch.residual(),)
     for a, b in zip(out["0"], out["1"]):
         assert np.array_equal(a, b)
