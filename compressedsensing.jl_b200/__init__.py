@@ -112,6 +112,8 @@ def _load() -> ctypes.CDLL:
                                        f64p]),
         "csb200_debug_corr_topk": (c_int, [c_void_p, c_int, c_int64, i64p, f64p]),
         "csb200_debug_get_residual": (c_int, [c_void_p, c_void_p]),
+        "csb200_debug_screen_pass": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64), POINTER(c_double)]),
+        "csb200_batch_screen_stats": (c_int, [c_void_p, POINTER(c_int64), c_void_p, c_int]),
         "csb200_debug_graph_replays": (c_int, [c_void_p, POINTER(c_int64)]),
     }
     for name, (res, args) in sig.items():
@@ -131,7 +133,7 @@ EXPORTED_SYMBOLS = [
     "csb200_batch_sp", "csb200_batch_oblivious", "csb200_sp", "csb200_oblivious", "csb200_dict_colnorms",
     "csb200_dict_cumbabel",
     "csb200_comm_create", "csb200_comm_destroy", "csb200_comm_exchange_mode", "csb200_comm_last_timing", "csb200_omp_sharded", "csb200_debug_corr_topk",
-    "csb200_debug_get_residual", "csb200_debug_graph_replays",
+    "csb200_debug_get_residual", "csb200_debug_graph_replays", "csb200_debug_screen_pass", "csb200_batch_screen_stats",
 ]
 
 
@@ -332,6 +334,26 @@ class Batch:
         val = np.empty((self.nsig, s), dtype=np.float64)
         _check(lib.csb200_debug_corr_topk(self._h, impl, s, _i64p(idx), _f64p(val)))
         return idx, val
+
+    def debug_screen_pass(self):
+        """One TF32 screening pass over the current residuals: (|c~| [nsig, chunks*8], atom [nsig, chunks*8], bound)."""
+        val = np.empty((self.nsig, 64), dtype=np.float32)
+        idx = np.empty((self.nsig, 64), dtype=np.int32)
+        chunks = c_int64()
+        bound = c_double()
+        _check(lib.csb200_debug_screen_pass(self._h, val.ctypes.data, idx.ctypes.data, byref(chunks), byref(bound)))
+        nc = int(chunks.value) * 8
+        return (val.reshape(-1)[: self.nsig * nc].reshape(self.nsig, nc).copy(),
+                idx.reshape(-1)[: self.nsig * nc].reshape(self.nsig, nc).copy(), bound.value)
+
+    def screen_stats(self, reset: bool = False) -> dict:
+        """Path of the last omp solve on this batch and the screening counters (`csb200_batch_screen_stats`)."""
+        path = c_int64()
+        st = np.zeros(3, dtype=np.uint64)
+        _check(lib.csb200_batch_screen_stats(self._h, byref(path), st.ctypes.data, 1 if reset else 0))
+        names = {0: "few-signal / gemv", 1: "dmma", 2: "dmma two-half overlap", 3: "tf32 screening + exact re-evaluation"}
+        return {"path": names.get(int(path.value), str(path.value)), "path_id": int(path.value), "signal_updates": int(st[0]),
+                "candidates_reevaluated": int(st[1]), "exact_scans": int(st[2])}
 
     def residual(self) -> np.ndarray:
         out = np.empty((self.dict.M, self.nsig), dtype=self.dict.dtype, order="F")

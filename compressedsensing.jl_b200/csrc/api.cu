@@ -83,6 +83,27 @@ int make_operand_map(CUtensorMap* map, void* base, int64_t ld, int64_t ncols, in
     return CSB200_OK;
 }
 
+// 2-D FP32 tensor map over a column-major (ld32 x ncols) matrix: box = 32 rows (128 B) x box_cols columns, SWIZZLE_128B --
+// the K-major operand tiles of corr_screen_tf32.cu.
+int make_operand_map32(CUtensorMap* map, void* base, int64_t ld32, int64_t ncols, int box_cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { g_last_error = "cuTensorMapEncodeTiled entry point not found"; return CSB200_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)ld32, (cuuint64_t)(ncols > 0 ? ncols : 1)};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld32 * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled (FP32) failed with CUresult %d", (int)r);
+        g_last_error = buf;
+        return CSB200_ERR_CUDA;
+    }
+    return CSB200_OK;
+}
+
 enum CorrImpl { IMPL_AUTO = 0, IMPL_GEMM = 1, IMPL_GEMV = 2, IMPL_NAIVE = 3 };
 constexpr int GEMM_MIN_SIGNALS = 24;
 constexpr int CLUSTER_UPDATE_MAX_SIGNALS = 24;   // below this one CTA per signal leaves the GPU idle: use a cluster per signal
@@ -109,6 +130,14 @@ struct csb200_dict {
     std::mutex twin_mu;
     bool twin_failed = false;
     bool gram_failed = false;
+    // TF32 screening pass of large omp batches (corr_screen_tf32.cu): TF32-rounded FP32 copy of the dictionary, its
+    // tensor map, and the largest column norm (the screening bound scales with it); built on first use
+    std::mutex screen_mu;
+    float* dA32 = nullptr;
+    CUtensorMap mapA32;
+    int64_t ld32 = 0;
+    double amax = 0.0;
+    bool screen_failed = false;
     // multi-device handle (csb200_dict_create_multi): this object is the replica of worker 0; `extra` holds the
     // replicas of workers 1..n-1 (owned).  The one-shot entry points fan a batch out over all of them.
     std::vector<csb200_dict*> extra;
@@ -150,6 +179,12 @@ struct csb200_batch {
     // low-priority one for the updates, events tying the two together
     cudaStream_t sp_gemm = nullptr, sp_upd = nullptr;
     cudaEvent_t sp_ev[2 + 2 * 4] = {};          // start, end, G[parts], U[parts]
+    // TF32 screening (run_omp_screen): TF32 copy of the residuals, candidate lists, counters
+    float* dR32 = nullptr;
+    float* scr_val = nullptr;
+    int* scr_idx = nullptr;
+    unsigned long long* scr_stats = nullptr;    // device: [0] signal-updates, [1] candidates re-evaluated, [2] exact scans
+    int last_path = 0;                          // 0 other, 1 DMMA loop, 2 DMMA two-half overlap, 3 TF32 screening + exact re-evaluation
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -192,6 +227,7 @@ void free_batch_mem(csb200_batch* b) {
     cudaFree(b->dB); cudaFree(b->dR); cudaFree(b->pval); cudaFree(b->pidx); cudaFree(b->state_blk);
     cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->stage32); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2); cudaFree(b->ndone);
     cudaFree(b->persist_scratch);
+    cudaFree(b->dR32); cudaFree(b->scr_val); cudaFree(b->scr_idx); cudaFree(b->scr_stats);
     if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
@@ -706,6 +742,110 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
     return CSB200_OK;
 }
 
+// ---- TF32 screening + exact FP64 re-evaluation for large omp batches ------------------------------------------------
+// The FP64 DMMA pass spends 2 M N flop per signal-update at 35 TFLOP/s to find ONE index.  Here the tcgen05 TF32 pass
+// (corr_screen_tf32.cu) leaves a short candidate list per signal with a proven error bound and omp_update_kernel decides
+// among the candidates in FP64 (update.cu, screen_select): the support is the FP64 arg-max sequence, the coefficients
+// come from the same FP64 update as before.  CSB200_SCREEN=0 keeps the DMMA pass, =1 forces screening where it is legal.
+constexpr int64_t SCREEN_MIN_SIGNALS = 4096;
+bool screen_legal(const csb200_batch* b) {
+    const csb200_dict* d = b->dict;
+    if (d->dtype != CSB200_F64 || d->n_total != d->N || d->screen_failed) return false;
+    if (d->M > SCREEN_MAX_ROWS || d->N < 256) return false;
+    if (b->corr_impl_env != IMPL_AUTO) return false;
+    return omp_update_smem_bytes((int)d->ld, (int)b->kcap) <= MAX_DYN_SMEM;
+}
+bool use_omp_screen(const csb200_batch* b, int64_t k) {
+    const char* env = getenv("CSB200_SCREEN");
+    if (env && env[0] == '0') return false;
+    if (!screen_legal(b) || uses_cluster_update(b) || k < 1) return false;
+    if (env && env[0] == '1') return true;
+    return b->nsig >= SCREEN_MIN_SIGNALS;
+}
+
+// dictionary side (once per handle): TF32 copy, tensor map, largest column norm
+int ensure_screen_dict(csb200_dict* d, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(d->screen_mu);
+    if (d->dA32) return CSB200_OK;
+    if (d->screen_failed) return 1;
+    static std::once_flag once;
+    static cudaError_t setup_err = cudaSuccess;
+    std::call_once(once, [] { setup_err = corr_screen_setup(); });
+    if (setup_err != cudaSuccess) { d->screen_failed = true; cudaGetLastError(); return 1; }
+    const int64_t ld32 = round_up(d->M, 32);
+    float* a32 = nullptr;
+    double* cn = nullptr;
+    if (cudaMalloc(&a32, (size_t)ld32 * d->N * sizeof(float)) != cudaSuccess) { cudaGetLastError(); d->screen_failed = true; return 1; }
+    if (cudaMalloc(&cn, (size_t)d->N * sizeof(double)) != cudaSuccess) { cudaGetLastError(); cudaFree(a32); d->screen_failed = true; return 1; }
+    cudaError_t e = launch_to_tf32(d->dA, false, d->ld, a32, ld32, (int)d->M, d->N, st);
+    if (e == cudaSuccess) e = launch_colnorms(d->dA, false, (int)d->ld, (int)d->N, cn, st);
+    std::vector<double> h((size_t)d->N);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.data(), cn, (size_t)d->N * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(cn);
+    double amax = 0.0;
+    for (double v : h) amax = v > amax ? v : amax;
+    // the bound is stated for FP32 operands without overflow / flush-to-zero trouble: column norms far from 1 are not screened
+    if (e != cudaSuccess || !(amax >= 1e-9 && amax <= 1e9) ||
+        make_operand_map32(&d->mapA32, a32, ld32, d->N, 256) != CSB200_OK) {
+        cudaGetLastError(); cudaFree(a32); d->screen_failed = true; return 1;
+    }
+    d->ld32 = ld32; d->amax = amax; d->dA32 = a32;
+    return CSB200_OK;
+}
+
+int ensure_screen_batch(csb200_batch* b) {
+    csb200_dict* d = b->dict;
+    if (b->dR32) return CSB200_OK;
+    const size_t rbytes = (size_t)b->cap_sig * d->ld32 * sizeof(float);
+    const size_t slots = (size_t)b->cap_sig * SCREEN_MAX_CHUNKS * SCREEN_T;
+    float* r32 = nullptr; float* sv = nullptr; int* si = nullptr; unsigned long long* stt = nullptr;
+    if (cudaMalloc(&r32, rbytes) != cudaSuccess || cudaMalloc(&sv, slots * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&si, slots * sizeof(int)) != cudaSuccess || cudaMalloc(&stt, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(r32); cudaFree(sv); cudaFree(si); cudaFree(stt);
+        return 1;
+    }
+    CU_TRY(cudaMemsetAsync(r32, 0, rbytes, b->stream));            // rows [ld, ld32) stay zero for ever
+    CU_TRY(cudaMemsetAsync(stt, 0, 4 * sizeof(unsigned long long), b->stream));
+    b->dR32 = r32; b->scr_val = sv; b->scr_idx = si; b->scr_stats = stt;
+    return CSB200_OK;
+}
+
+// returns 1 when the screening path cannot be set up (the caller then takes the DMMA path)
+int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
+    csb200_dict* d = b->dict;
+    int rc = ensure_screen_dict(d, b->stream);
+    if (rc) return rc;
+    if ((rc = ensure_screen_batch(b))) return rc;
+    const int chunks = screen_chunks_for((int)d->N, (int)b->nsig, d->num_sms);
+    CUtensorMap mapR32;
+    if ((rc = make_operand_map32(&mapR32, b->dR32, d->ld32, b->nsig, 128))) return rc;
+    StateArgs ua = state_args(b, 1, 1, eps, 0);
+    ua.scr_val = b->scr_val; ua.scr_idx = b->scr_idx; ua.scr_nc = chunks * SCREEN_T;
+    ua.scr_bound = SCREEN_KAPPA * d->amax;
+    ua.R32 = b->dR32; ua.ld32 = (int)d->ld32; ua.scr_stats = b->scr_stats;
+    cudaError_t e = launch_reset_state(ua, false, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    for (int64_t it = 0; it < k; ++it) {
+        cudaEvent_t p0 = nullptr, p1 = nullptr;
+        if (b->profile) {
+            if (b->ev_used + 2 > b->ev.size())
+                for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); b->ev.push_back(ev); }
+            p0 = b->ev[b->ev_used]; p1 = b->ev[b->ev_used + 1]; b->ev_used += 2;
+            CU_TRY(cudaEventRecord(p0, b->stream));
+        }
+        e = launch_corr_screen(&mapR32, &d->mapA32, (int)d->N, (int)b->nsig, (int)d->ld32, chunks, (int)d->n_offset,
+                               b->scr_val, b->scr_idx, d->num_sms, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "screening kernel launch");
+        if (b->profile) CU_TRY(cudaEventRecord(p1, b->stream));
+        e = launch_omp_update(ua, false, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "omp_update");
+        b->other_launches++;
+    }
+    b->last_path = 3;
+    return CSB200_OK;
+}
+
 // ---- CUDA-graph replay of few-signal solves ---------------------------------------------------------------------
 // A single-signal update! is ~10 us of GEMV plus ~10 us of cluster update; issued as individual launches (each with
 // its attribute / occupancy calls) the host cannot keep the stream fed and the solve runs at launch rate.  The loop has
@@ -1058,6 +1198,7 @@ int csb200_dict_destroy(csb200_dict* d) {
     for (csb200_dict* r : d->extra) csb200_dict_destroy(r);
     cudaSetDevice(d->device);
     cudaFree(d->gram);
+    cudaFree(d->dA32);
     cudaFree(d->dA);
     delete d;
     return CSB200_OK;
@@ -1239,10 +1380,17 @@ int csb200_batch_omp(csb200_batch* b, int64_t k, double eps) {
     decide_gram(b, k);
     const bool f32 = d->dtype == CSB200_F32;
     if ((rc = begin_solve(b))) return rc;
+    b->last_path = 0;
+    if (use_omp_screen(b, k)) {
+        if ((rc = run_omp_screen(b, k, eps)) == CSB200_OK) return finish(b, true);
+        if (rc != 1) return rc;
+    }
     if (use_omp_split(b, k)) {
         if ((rc = run_omp_split(b, k, eps))) return rc;
+        b->last_path = 2;
         return finish(b, true);
     }
+    if (corr_impl_for(b) == IMPL_GEMM) b->last_path = 1;
     rc = run_graphed(b, 0, k, 1, eps, k, [&]() -> int {
         cudaError_t e = launch_reset_state(state_args(b, 1, 1, eps, 0), f32, b->stream);
         if (e != cudaSuccess) return fail_cuda(e, "reset_state");
@@ -2151,6 +2299,52 @@ int csb200_debug_corr_topk(csb200_batch* b, int impl, int64_t s, int64_t* idx, d
     if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
     cudaFree(d_idx); cudaFree(d_val);
     if (e != cudaSuccess) return fail_cuda(e, "debug_corr_topk");
+    return CSB200_OK;
+}
+
+int csb200_debug_screen_pass(csb200_batch* b, float* val, int32_t* idx, int64_t* chunks_out, double* bound_out) {
+    int rc = check_ready(b);
+    if (rc) return rc;
+    if (!val || !idx || !chunks_out) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    csb200_dict* d = b->dict;
+    if ((rc = set_device(d))) return rc;
+    if (!screen_legal(b)) { g_last_error = "screening needs an unsharded FP64 dictionary with <= 2048 rows and >= 256 atoms"; return CSB200_ERR_UNSUPPORTED; }
+    if ((rc = settle_input(b))) return rc;
+    if (ensure_screen_dict(d, b->stream) || ensure_screen_batch(b)) { g_last_error = "screening pass could not be set up"; return CSB200_ERR_UNSUPPORTED; }
+    const int chunks = screen_chunks_for((int)d->N, (int)b->nsig, d->num_sms);
+    CUtensorMap mapR32;
+    if ((rc = make_operand_map32(&mapR32, b->dR32, d->ld32, b->nsig, 128))) return rc;
+    cudaError_t e = launch_to_tf32(b->dR, false, d->ld, b->dR32, d->ld32, (int)d->M, b->nsig, b->stream);   // the CURRENT residuals
+    if (e == cudaSuccess)
+        e = launch_corr_screen(&mapR32, &d->mapA32, (int)d->N, (int)b->nsig, (int)d->ld32, chunks, (int)d->n_offset, b->scr_val,
+                               b->scr_idx, d->num_sms, b->stream);
+    const size_t n = (size_t)b->nsig * chunks * SCREEN_T;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(val, b->scr_val, n * sizeof(float), cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx, b->scr_idx, n * sizeof(int), cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "debug_screen_pass");
+    *chunks_out = chunks;
+    if (bound_out) *bound_out = SCREEN_KAPPA * d->amax;
+    return CSB200_OK;
+}
+
+int csb200_batch_screen_stats(csb200_batch* b, int64_t* path, uint64_t* stats3, int reset) {
+    if (!b) return CSB200_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(b->mu);
+    int rc = set_device(b->dict);
+    if (rc) return rc;
+    if (path) *path = b->last_path;
+    if (stats3) {
+        stats3[0] = stats3[1] = stats3[2] = 0;
+        if (b->scr_stats) {
+            unsigned long long h[3];
+            CU_TRY(cudaStreamSynchronize(b->stream));
+            CU_TRY(cudaMemcpy(h, b->scr_stats, sizeof h, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 3; ++i) stats3[i] = h[i];
+        }
+    }
+    if (reset && b->scr_stats) CU_TRY(cudaMemset(b->scr_stats, 0, 4 * sizeof(unsigned long long)));
     return CSB200_OK;
 }
 

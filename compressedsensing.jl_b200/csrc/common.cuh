@@ -14,6 +14,23 @@ constexpr int PBLK = 64;
 constexpr int MAX_S = 64;          // candidates per 64-atom block the fused DMMA epilogue can emit (= the block size)
 constexpr int GOMP_MAX_L = 256;    // atoms per gomp update! (l); larger l: CSB200_ERR_UNSUPPORTED
 constexpr int ROW_ALIGN = 16;      // leading dimensions are padded to 16 elements (128 B for f64)
+// TF32 screening pass of the batched omp solve (corr_screen_tf32.cu): per (signal, atom chunk) the SCREEN_T largest
+// |c~|; |c~_j - <a_j, r>| <= SCREEN_KAPPA * max_j ||a_j|| * ||r||.  Operands are rounded to TF32 (2^-11 each, so
+// 2^-10 + 2^-22 per product, summed with Cauchy-Schwarz), the FP32 accumulation over K <= SCREEN_MAX_ROWS terms adds
+// at most K * 2^-22 of sum |a_i r_i| (truncating adds, two roundings per term): 0.98e-3 + 0.5e-3 at the cap.
+constexpr int SCREEN_T = 8;
+constexpr int SCREEN_MAX_CHUNKS = 8;
+constexpr int SCREEN_MAX_ROWS = 2048;
+constexpr double SCREEN_KAPPA = 1.6e-3;
+constexpr double SCREEN_NORM_MIN = 1e-18, SCREEN_NORM_MAX = 1e18;   // residual norms outside: exact scan (FP32 range)
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float tf32_round(float x) {          // round to nearest, ties away: 10 explicit mantissa bits
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+#endif
 
 // Candidate order shared by every kernel: larger |c| first, lower index on ties
 // (Julia `argmax` = first maximal index, src/matchingpursuit.jl:184;
@@ -46,6 +63,13 @@ cudaError_t launch_gemm_f64_store(const CUtensorMap* mapA, const CUtensorMap* ma
 // Forward-regression pass (EPI_OLS epilogue): candidates are (delta2, atom); mapQ == nullptr on the first step.
 cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap* mapR, const CUtensorMap* mapQ,
                                      const CorrArgs& a, double* resc, long long ldr, int num_sms, cudaStream_t st);
+// TF32 screening pass (corr_screen_tf32.cu): cval / cidx [nsig][chunks][SCREEN_T]; ld32 = rows of the FP32 operands (multiple of 32)
+int screen_chunks_for(int N, int nsig, int num_sms);
+cudaError_t corr_screen_setup();
+cudaError_t launch_corr_screen(const CUtensorMap* mapR32, const CUtensorMap* mapA32, int N, int nsig, int ld32, int chunks,
+                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st);
+cudaError_t launch_to_tf32(const void* in, bool f32, long long ld_in, float* out, long long ld_out, int rows, long long cols,
+                           cudaStream_t st);
 // GEMV pass: a.P = corr_gemv_blocks(...) CTAs per signal, each emitting the top-S of its contiguous atom range.
 int corr_gemv_blocks(int N, int ld, bool f32, int S, int num_sms);
 cudaError_t launch_corr_gemv(const CorrArgs& a, bool f32, cudaStream_t st);
@@ -85,6 +109,15 @@ struct StateArgs {
     int grid_cap = 0;           // > 0: omp_update_kernel runs with at most this many CTAs, each walking several signals
     int max_smem_carveout = 0;  // launch hint: ask for the SM's largest shared-memory carve-out, i.e. the configuration the
                                 // DMMA correlation kernel runs under, so that CTAs of both kernels can share an SM
+    // TF32 screening (corr_screen_tf32.cu): non-null scr_val switches omp_update_kernel's selection to "exact FP64
+    // re-evaluation of the screened candidates" and makes it keep the TF32 copy of the residual up to date
+    const float* scr_val = nullptr;   // [nsig][scr_nc] |c~| descending per chunk of SCREEN_T
+    const int* scr_idx = nullptr;     // [nsig][scr_nc] global atom index or -1
+    int scr_nc = 0;                   // chunks * SCREEN_T
+    double scr_bound = 0.0;           // SCREEN_KAPPA * max_j ||a_j||: E = scr_bound * ||r||
+    float* R32 = nullptr;             // [nsig][ld32] TF32-rounded residuals (the screening pass's operand)
+    int ld32 = 0;
+    unsigned long long* scr_stats = nullptr;   // optional counters: [0] signal-updates screened, [1] candidates re-evaluated, [2] exact scans
 };
 // Acache (optional): ld x kcap buffer holding the active atoms' columns in selection order, with the
 // candidate's column already stored in slot nnz (column-sharded mode: the atom may live on a peer).

@@ -1,0 +1,310 @@
+// Screening pass of the batched omp solve:  C~ = R' A  on the 5th-generation tensor cores (tcgen05, kind::tf32,
+// accumulators in tensor memory), reduced in the epilogue to the SCREEN_T largest |c~| per (signal, atom chunk).
+//
+// Why.  `argmaxinner!` (/root/reference/src/matchingpursuit.jl:181-185) needs the POSITION of max |A'r|, not the
+// N correlations.  The FP64 DMMA pass (corr_gemm_f64.cu) computes all N of them to 53 bits at 35 TFLOP/s; this pass
+// computes them to ~11 bits at tcgen05 rates and hands the update kernel a short list that provably contains the
+// FP64 arg-max: with operands rounded to TF32 (cvt.rna, relative error <= 2^-11 each) and FP32 accumulation,
+//       |c~_j - <a_j, r>|  <=  E = SCREEN_KAPPA * max_j ||a_j|| * ||r||          (Cauchy-Schwarz over the rounding errors)
+// so every atom whose |c~| lies within 2E of the largest |c~| is a possible arg-max and nothing else is.  The update
+// kernel (update.cu, screen_select) re-evaluates exactly those atoms in FP64 and picks the winner with the reference's
+// tie-break; a list that may be incomplete (its last slot still inside the window, a residual outside the FP32 range)
+// falls back to an exact FP64 scan of all atoms for that signal.  The selected support is therefore the FP64 one.
+//
+// sm_100a design (one CTA per SM, 192 threads, persistent over work units = 128 signals x one atom chunk):
+//   warp 0   TMA producer: per K-block of 32 floats one box {32 x 128 signals} of R32 and one box {32 x 256 atoms} of A32
+//            (SWIZZLE_128B, K-major for both operands: signals and atoms are columns of column-major matrices), 4-stage
+//            full/empty mbarrier ring of 48 KiB stages running ahead across tile and unit boundaries;
+//   warp 1   one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128 signals, N = 256 atoms, K = 8) four
+//            times per stage and commits the stage back to the producer; the 128 x 256 FP32 accumulator lives in TMEM,
+//            double-buffered (2 x 256 of the 512 columns) so the epilogue of tile i runs under the MMAs of tile i + 1;
+//   warps 2-5  epilogue: a TMEM lane IS a signal, so after tcgen05.ld.32x32b every thread scans the atoms of ITS signal
+//            in its own registers -- no shuffles -- and keeps a sorted top-SCREEN_T (value, atom) across all tiles of
+//            the unit; one 64-byte record per (signal, chunk) leaves the SM.  The N x B matrix is never written.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace csb {
+
+namespace {
+
+constexpr int ST_SIG = 128;                    // signals per tile  (UMMA M, TMEM lanes)
+constexpr int ST_ATOM = 256;                   // atoms per tile    (UMMA N, TMEM columns per accumulator stage)
+constexpr int ST_KB = 32;                      // floats per K-block: 128-byte swizzle rows
+constexpr int ST_STAGES = 4;
+constexpr int ST_A_BYTES = ST_SIG * ST_KB * 4;     // 16 KiB of R32
+constexpr int ST_B_BYTES = ST_ATOM * ST_KB * 4;    // 32 KiB of A32
+constexpr int ST_STAGE_BYTES = ST_A_BYTES + ST_B_BYTES;
+constexpr int ST_BAR_BYTES = 128;
+constexpr int ST_SMEM_BYTES = ST_STAGES * ST_STAGE_BYTES + ST_BAR_BYTES + 1024 /* alignment slack */;
+constexpr int ST_THREADS = 192;
+constexpr int ST_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major operand tile stored as 128-byte rows under SWIZZLE_128B (what the TMA
+// boxes above produce): start address (>> 4), leading byte offset (unused for swizzled K-major, 1), stride byte offset =
+// 1024 B between 8-row groups (>> 4), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 at bits 7 and 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ST_ATOM >> 3) << 17) | ((uint32_t)(ST_SIG >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(UMMA_IDESC), "r"(accumulate) : "memory");
+}
+// Arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed (implies fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TM_REGS(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
+// 32 lanes x 32 consecutive 32-bit columns: thread l of the warp receives columns [col, col + 32) of TMEM lane (base lane + l).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : TM_REGS(r, 0), TM_REGS(r, 8), TM_REGS(r, 16), TM_REGS(r, 24)
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Sorted insertion into the running top-SCREEN_T (descending; a later, i.e. higher-indexed, equal value stays behind).
+__device__ __forceinline__ void top_insert(float (&v)[SCREEN_T], int (&id)[SCREEN_T], float x, int idx) {
+    v[SCREEN_T - 1] = x; id[SCREEN_T - 1] = idx;
+#pragma unroll
+    for (int p = SCREEN_T - 1; p > 0; --p) {
+        const bool up = v[p] > v[p - 1];
+        const float tv = up ? v[p - 1] : v[p];
+        const int ti = up ? id[p - 1] : id[p];
+        v[p - 1] = up ? v[p] : v[p - 1];
+        id[p - 1] = up ? id[p] : id[p - 1];
+        v[p] = tv; id[p] = ti;
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1)
+corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapA,
+                        int N, int nsig, int kblocks, int tilesN, int chunks, int tiles_per_chunk, int units,
+                        int idx_offset, float* __restrict__ cval, int* __restrict__ cidx) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t pad = (1024u - (s_u32(smem_raw) & 1023u)) & 1023u;
+    uint8_t* sm = smem_raw + pad;                                  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t sm_base = s_u32(sm);
+    const uint32_t bar_full = sm_base + ST_STAGES * ST_STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + ST_STAGES * 8;
+    const uint32_t bar_tfull = bar_empty + ST_STAGES * 8;          // accumulator stage is complete (MMA -> epilogue)
+    const uint32_t bar_tempty = bar_tfull + 2 * 8;                 // accumulator stage has been read (epilogue -> MMA)
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + ST_STAGES * ST_STAGE_BYTES + 96);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST_STAGES; ++s) { bar_init(bar_full + s * 8, 1); bar_init(bar_empty + s * 8, 1); }
+        for (int s = 0; s < 2; ++s) { bar_init(bar_tfull + s * 8, 1); bar_init(bar_tempty + s * 8, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapR) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    }
+    if (warp == 1) {                                               // the allocating warp also deallocates
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(s_u32(const_cast<uint32_t*>(tmem_slot))), "r"(ST_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                           // ---- TMA producer
+            int stage = 0; uint32_t phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int sig_tile = u / chunks, chunk = u - sig_tile * chunks;
+                const int t0 = chunk * tiles_per_chunk;
+                const int t1 = t0 + tiles_per_chunk < tilesN ? t0 + tiles_per_chunk : tilesN;
+                for (int t = t0; t < t1; ++t)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        bar_wait(bar_empty + stage * 8, phase ^ 1);
+                        const uint32_t full = bar_full + stage * 8;
+                        const uint32_t dst = sm_base + stage * ST_STAGE_BYTES;
+                        bar_arrive_expect_tx(full, ST_STAGE_BYTES);
+                        tma_2d(dst, &mapR, full, kb * ST_KB, sig_tile * ST_SIG);
+                        tma_2d(dst + ST_A_BYTES, &mapA, full, kb * ST_KB, t * ST_ATOM);
+                        if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                           // ---- MMA issuer
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int sig_tile = u / chunks, chunk = u - sig_tile * chunks;
+                const int t0 = chunk * tiles_per_chunk;
+                const int t1 = t0 + tiles_per_chunk < tilesN ? t0 + tiles_per_chunk : tilesN;
+                for (int t = t0; t < t1; ++t) {
+                    bar_wait(bar_tempty + acc * 8, acc_phase ^ 1);                  // the epilogue has drained this stage
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ST_ATOM);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        bar_wait(bar_full + stage * 8, phase);
+                        tc_fence_after();
+                        const uint32_t sa = sm_base + stage * ST_STAGE_BYTES;
+                        const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + ST_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < ST_KB / 8; ++k)                         // K = 8 TF32 = 32 bytes per instruction
+                            umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (uint32_t)((kb | k) != 0));
+                        umma_commit(bar_empty + stage * 8);                         // stage free once these MMAs have read it
+                        if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull + acc * 8);
+                    acc ^= 1; if (acc == 0) acc_phase ^= 1;
+                }
+            }
+        }
+    } else {                                                       // ---- epilogue warps: TMEM lane quadrant = warp % 4
+        const int quad = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int sig_tile = u / chunks, chunk = u - sig_tile * chunks;
+            const int t0 = chunk * tiles_per_chunk;
+            const int t1 = t0 + tiles_per_chunk < tilesN ? t0 + tiles_per_chunk : tilesN;
+            float v[SCREEN_T]; int id[SCREEN_T];
+#pragma unroll
+            for (int p = 0; p < SCREEN_T; ++p) { v[p] = -1.0f; id[p] = -1; }
+            for (int t = t0; t < t1; ++t) {
+                bar_wait(bar_tfull + acc * 8, acc_phase);
+                tc_fence_after();
+                const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ST_ATOM);
+#pragma unroll 1
+                for (int c = 0; c < ST_ATOM / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(trow + (uint32_t)(c * 32), r);
+                    tmem_ld_wait();
+                    const int base = t * ST_ATOM + c * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const float x = fabsf(__uint_as_float(r[e]));
+                        if (x > v[SCREEN_T - 1] && base + e < N) top_insert(v, id, x, base + e + idx_offset);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(bar_tempty + acc * 8);
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            }
+            const int sig = sig_tile * ST_SIG + quad * 32 + lane;
+            if (sig < nsig) {
+                float4* ov = reinterpret_cast<float4*>(cval + ((size_t)sig * chunks + chunk) * SCREEN_T);
+                int4* oi = reinterpret_cast<int4*>(cidx + ((size_t)sig * chunks + chunk) * SCREEN_T);
+#pragma unroll
+                for (int p = 0; p < SCREEN_T; p += 4) {
+                    ov[p / 4] = make_float4(v[p], v[p + 1], v[p + 2], v[p + 3]);
+                    oi[p / 4] = make_int4(id[p], id[p + 1], id[p + 2], id[p + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ST_TMEM_COLS) : "memory");
+    }
+}
+
+// out[r + c * ld_out] = tf32(in[r + c * ld_in]) for r < rows, 0 for rows <= r < ld_out.
+template <typename T>
+__global__ void __launch_bounds__(256) to_tf32_kernel(const T* __restrict__ in, long long ld_in, float* __restrict__ out,
+                                                     long long ld_out, int rows, long long cols) {
+    const long long total = ld_out * cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long c = e / ld_out;
+        const int r = (int)(e - c * ld_out);
+        out[e] = r < rows ? tf32_round((float)in[r + c * ld_in]) : 0.0f;
+    }
+}
+
+}  // namespace
+
+int screen_chunks_for(int N, int nsig, int num_sms) {
+    const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
+    const long long sig_tiles = (nsig + ST_SIG - 1) / ST_SIG;
+    static const int forced = [] { const char* e = getenv("CSB200_SCREEN_CHUNKS"); return e ? atoi(e) : 0; }();
+    int best = 1;
+    double best_eff = -1.0;
+    for (int c = 1; c <= SCREEN_MAX_CHUNKS; c *= 2) {
+        if (c > tilesN) break;
+        if (forced == c) return c;
+        const int tpc = (tilesN + c - 1) / c;
+        const int cc = (tilesN + tpc - 1) / tpc;                   // chunks that actually hold tiles
+        if (cc != c) continue;
+        const long long units = sig_tiles * c;
+        const long long waves = (units + num_sms - 1) / num_sms;
+        const double eff = (double)units / (double)(waves * num_sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = c; }   // prefer fewer chunks unless the last wave fills up noticeably
+    }
+    return best;
+}
+
+cudaError_t corr_screen_setup() {
+    return cudaFuncSetAttribute(corr_screen_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
+}
+
+cudaError_t launch_corr_screen(const CUtensorMap* mapR32, const CUtensorMap* mapA32, int N, int nsig, int ld32, int chunks,
+                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st) {
+    if (nsig <= 0 || N <= 0) return cudaSuccess;
+    const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
+    const int tpc = (tilesN + chunks - 1) / chunks;
+    const int sig_tiles = (nsig + ST_SIG - 1) / ST_SIG;
+    const int units = sig_tiles * chunks;
+    const int grid = units < num_sms ? units : num_sms;
+    corr_screen_tf32_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(*mapR32, *mapA32, N, nsig, ld32 / ST_KB, tilesN, chunks, tpc,
+                                                                      units, idx_offset, cval, cidx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_to_tf32(const void* in, bool f32, long long ld_in, float* out, long long ld_out, int rows, long long cols,
+                           cudaStream_t st) {
+    if (cols <= 0) return cudaSuccess;
+    const long long total = ld_out * cols;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (f32) to_tf32_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), ld_in, out, ld_out, rows, cols);
+    else to_tf32_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(in), ld_in, out, ld_out, rows, cols);
+    return cudaGetLastError();
+}
+
+}  // namespace csb

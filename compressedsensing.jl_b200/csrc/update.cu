@@ -52,6 +52,107 @@ constexpr int UW = UT / 32;
 // Shared-memory budget for keeping the inverse factor on chip (above it the kernel works on the copy in L2).
 constexpr int T_SMEM_MAX_K = 96;
 
+// Exact <a, r> by one warp (r staged in shared memory): the loop of append_atom's g sweep.  Every lane returns the sum.
+template <typename T>
+__device__ __forceinline__ double warp_dot_col(const T* __restrict__ ai, const double* sr, int ld, int lane) {
+    constexpr int W = RowVec<T>::W;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int row = lane * W;
+    for (; row + 32 * W < ld; row += 64 * W) {
+        double a0[W], a1[W];
+        RowVec<T>::load(ai + row, a0);
+        RowVec<T>::load(ai + row + 32 * W, a1);
+#pragma unroll
+        for (int e = 0; e < W; e += 2) {
+            s0 = fma(a0[e], sr[row + e], s0); s1 = fma(a0[e + 1], sr[row + e + 1], s1);
+            s2 = fma(a1[e], sr[row + 32 * W + e], s2); s3 = fma(a1[e + 1], sr[row + 32 * W + e + 1], s3);
+        }
+    }
+    if (row < ld) {
+        double a0[W];
+        RowVec<T>::load(ai + row, a0);
+#pragma unroll
+        for (int e = 0; e < W; e += 2) { s0 = fma(a0[e], sr[row + e], s0); s1 = fma(a0[e + 1], sr[row + e + 1], s1); }
+    }
+    return warp_sum((s0 + s1) + (s2 + s3));
+}
+
+// `argmaxinner!` (/root/reference/src/matchingpursuit.jl:181-185) from the TF32 screening pass (corr_screen_tf32.cu).
+// The pass left, per atom chunk, the SCREEN_T largest |c~| of this signal with |c~_j - <a_j, r>| <= E = scr_bound ||r||.
+// Every atom within 2E of the largest |c~| may be the FP64 arg-max, no other atom can: those are re-evaluated exactly
+// (one warp per atom) and the winner is picked with the reference's tie-break.  A single atom in the window needs no
+// arithmetic at all.  If a chunk's last slot is still inside the window its list may be incomplete, and if ||r|| is
+// outside the range FP32 represents safely the bound does not hold: both fall back to an exact scan of all atoms.
+template <typename T, int NT>
+__device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__ A, const T* __restrict__ r, double* sv,
+                              int* s_cand, double* s_cval, double* red_v, int* red_i) {
+    __shared__ int s_list[SCREEN_T * SCREEN_MAX_CHUNKS];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nc = a.scr_nc, ld = a.ld;
+    const double nr = a.resnorm[sig];
+    float v = -1.0f;
+    int idx = -1;
+    if (tid < nc) { v = a.scr_val[(size_t)sig * nc + tid]; idx = a.scr_idx[(size_t)sig * nc + tid]; }
+    if (idx < 0 || !(v >= 0.0f)) { v = -1.0f; idx = -1; }
+    float m = v;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (tid == 0) s_n = 0;
+    if (lane == 0) red_v[warp] = (double)m;
+    __syncthreads();
+    double v0 = red_v[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) v0 = fmax(v0, red_v[w]);
+    const bool range_ok = nr >= SCREEN_NORM_MIN && nr <= SCREEN_NORM_MAX && v0 >= 0.0 && v0 <= 3.0e38;
+    const double thr = v0 - 2.0 * a.scr_bound * nr;
+    const bool inw = idx >= 0 && (double)v >= thr;
+    const int incomplete = __syncthreads_or(inw && (tid % SCREEN_T) == SCREEN_T - 1) || !range_ok;
+    if (inw && !incomplete) s_list[atomicAdd(&s_n, 1)] = idx;
+    __syncthreads();
+    const int n = s_n;
+    if (!incomplete && n == 1) {
+        if (tid == 0) {
+            s_cand[0] = s_list[0]; s_cval[0] = v0;
+            if (a.scr_stats) atomicAdd(&a.scr_stats[0], 1ULL);
+        }
+        __syncthreads();
+        return;
+    }
+    for (int row = tid; row < ld; row += NT) sv[row] = (double)r[row];
+    __syncthreads();
+    double bv = -1.0;
+    int bi = INT_MAX;
+    if (!incomplete) {
+        for (int c = warp; c < n; c += NT / 32) {
+            const int j = s_list[c];
+            const double d = fabs(warp_dot_col<T>(A + (size_t)(j - a.idx_offset) * ld, sv, ld, lane));
+            if (cand_better(d, j, bv, bi)) { bv = d; bi = j; }
+        }
+    } else {
+        for (int j = warp; j < a.N; j += NT / 32) {
+            const double d = fabs(warp_dot_col<T>(A + (size_t)j * ld, sv, ld, lane));
+            if (cand_better(d, j + a.idx_offset, bv, bi)) { bv = d; bi = j + a.idx_offset; }
+        }
+    }
+    __syncthreads();                                               // red_v was read above
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        bv = red_v[0]; bi = red_i[0];
+#pragma unroll
+        for (int w = 1; w < NT / 32; ++w)
+            if (cand_better(red_v[w], red_i[w], bv, bi)) { bv = red_v[w]; bi = red_i[w]; }
+        s_cand[0] = bi == INT_MAX ? -1 : bi;
+        s_cval[0] = bv;
+        if (a.scr_stats) {
+            atomicAdd(&a.scr_stats[0], 1ULL);
+            if (incomplete) atomicAdd(&a.scr_stats[2], 1ULL); else atomicAdd(&a.scr_stats[1], (unsigned long long)n);
+        }
+    }
+    __syncthreads();
+}
+
 // NT = 128 threads, 8 CTAs/SM for one atom per update (omp); NT = 256 with the block-append working set
 // (BLOCK: up to `bm` new atoms orthogonalised together, update_common.cuh append_block) for gomp.
 template <typename T, int NT, bool BLOCK>
@@ -112,7 +213,8 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
     double nr2 = 0.0;
     auto b_at = [&](int row) { return (double)b[row]; };
     auto r_at = [&](int row) { return (double)r[row]; };
-    auto r_set = [&](int row, T val) { r[row] = val; };
+    float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;   // TF32 copy read by the screening pass
+    auto r_set = [&](int row, T val) { r[row] = val; if (r32) r32[row] = tf32_round((float)val); };
 
     for (int i = tid; i < t; i += NT) {
         const int si = a.sel[(size_t)sig * kcap + i];
@@ -129,6 +231,8 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
             // the block working set is idle during the selection: its first 8 KB serve as histogram, the rest as staging
             select_any<NT>(a, sig, a.take, MAX_TAKE, s_cand, s_cval, red, red_i, reinterpret_cast<int*>(Vb),
                            Vb + DENSE_HIST / 2, (int)block_region_elems(bm, ld) - DENSE_HIST / 2);
+        } else if (a.scr_val) {                                    // screened candidates, exact FP64 decision
+            screen_select<T, NT>(a, sig, A, r, S.v, s_cand, s_cval, red, red_i);
         } else {                                                   // one atom per update: always per-block candidates
             const size_t cbase = (size_t)sig * a.P * a.S;
             select_candidates<NT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, a.take, s_cand, s_cval, red, red_i);
@@ -457,7 +561,11 @@ __global__ void __launch_bounds__(UT) reset_state_kernel(StateArgs a) {
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
     T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
     double s2 = 0.0;
-    for (int row = tid; row < ld; row += UT) { const T e = b[row]; r[row] = e; s2 += (double)e * (double)e; }
+    float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;
+    for (int row = tid; row < ld; row += UT) {
+        const T e = b[row]; r[row] = e; s2 += (double)e * (double)e;
+        if (r32) r32[row] = tf32_round((float)e);
+    }
     const double nr = sqrt(block_sum<UT>(s2, red));
     if (tid == 0) { a.nnz[sig] = 0; a.iters[sig] = 0; a.done[sig] = 0; a.flags[sig] = 0; a.resnorm[sig] = nr; }
 }

@@ -456,6 +456,7 @@ def test_two_half_overlap_is_bit_identical(cs, po, monkeypatch, parts, ctas_per_
     (CSB200_SPLIT_CTAS_PER_SM=1)."""
     monkeypatch.setenv("CSB200_SPLIT_PARTS", str(parts))
     monkeypatch.setenv("CSB200_SPLIT_CTAS_PER_SM", str(ctas_per_sm))
+    monkeypatch.setenv("CSB200_SCREEN", "0")                 # this test is about the FP64 DMMA path (the default would screen)
     rng = np.random.default_rng(515)
     M, N, k, B = 100, 300, 5, 8192 + 77
     A = po.gaussian_dictionary(rng, M, N)
