@@ -65,6 +65,8 @@ def parse(argv=None):
     ap.add_argument("--ref-signals", type=int, default=512, help="signals per step of the CPU reference arm")
     ap.add_argument("--cpu-signals", type=int, default=1024, help="signals of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
+    ap.add_argument("--fp64-steps", type=int, default=2,
+                    help="c2: timed steps of the same workload through the FP64 DMMA pass (CSB200_SCREEN=0), reported as `fp64_path` (0 = skip)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the secondary configs (smoke runs)")
     return ap.parse_args(argv)
 
@@ -92,6 +94,38 @@ def fp64_peak_live(device):
         return json.loads(r.stdout.strip().splitlines()[-1])
     except Exception:
         return None
+
+
+def tf32_peak():
+    """Dense TF32 tensor peak: half of the cuBLAS bf16 figure the driver measured on this pool (MEASURED_PEAKS.json)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["bf16_tflops"]) / 2.0, ("MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 burst, driver-written) / 2: tcgen05 "
+                                               "kind::tf32 runs at half the kind::f16 rate; sustained figure / 2 = %.0f"
+                                               % (float(d.get("bf16_tflops_sustained", 0.0)) / 2.0))
+    return 1125.0, "fallback: nominal dense TF32 1.1 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def tf32_gemm_live(torch, dev):
+    """cuBLAS TF32 GEMM (torch.matmul, allow_tf32) 8192^3 on this box in this run: the library yardstick for the screening pass."""
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device=dev, dtype=torch.float32)
+        b = torch.randn(8192, 8192, device=dev, dtype=torch.float32)
+        for _ in range(3):
+            a @ b
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(5):
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        return {"tflops": 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12, "what": "torch.matmul fp32 with allow_tf32, 8192^3, best of 5 (CUDA events)"}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def hbm_peak():
@@ -390,8 +424,23 @@ class C2:
         del B_t
         return B_pin, np.sort(idx, axis=1)
 
-    def measure(self, B, steps, warmup, e2e_steps, with_peak=False, cpu_signals=0):
-        """Device-resident throughput, e2e through csb200_omp, GEMM roofline, optional CPU sample + parity."""
+    def measure(self, B, steps, warmup, e2e_steps, with_peak=False, cpu_signals=0, screen=None):
+        """Device-resident throughput, e2e through csb200_omp, roofline of the correlation kernel, optional CPU sample +
+        parity.  screen: None = the library's default path (TF32 screening + exact FP64 re-evaluation for large batches),
+        False = the FP64 DMMA pass (CSB200_SCREEN=0)."""
+        old_env = os.environ.get("CSB200_SCREEN")
+        if screen is not None:
+            os.environ["CSB200_SCREEN"] = "1" if screen else "0"
+        try:
+            return self._measure(B, steps, warmup, e2e_steps, with_peak, cpu_signals)
+        finally:
+            if screen is not None:
+                if old_env is None:
+                    os.environ.pop("CSB200_SCREEN", None)
+                else:
+                    os.environ["CSB200_SCREEN"] = old_env
+
+    def _measure(self, B, steps, warmup, e2e_steps, with_peak, cpu_signals):
         ctx, cs, k = self.ctx, self.ctx.cs, K_SPARSE
         B_pin, idx_sorted = self.signals(B)
         B_np = B_pin.numpy().T                                   # (M, B) Fortran-ordered view of pinned memory
@@ -410,7 +459,11 @@ class C2:
             dev_ms += batch.last_solve_ms()
         ctx.barrier()
         wall = time.perf_counter() - t0
-        live = fp64_peak_live(ctx.local) if (with_peak and ctx.rank == 0) else None      # inside the clocks window
+        scr = batch.screen_stats(reset=True)
+        screened = scr["path_id"] == 3
+        live = None
+        if with_peak and ctx.rank == 0:                                                   # inside the clocks window
+            live = tf32_gemm_live(ctx.torch, ctx.dev) if screened else fp64_peak_live(ctx.local)
         ctx.barrier()
         clocks = sampler.stop()
         corr_ms, corr_launches, other_launches = batch.corr_time()
@@ -420,6 +473,8 @@ class C2:
         sel, coef, nnz, res, its = batch.download(k)
         recovered = float(np.mean((np.sort(sel, axis=1) == idx_sorted).all(axis=1)))
         max_res = float(res.max())
+        import hashlib
+        digest = hashlib.sha256(sel.tobytes() + coef.tobytes() + nnz.tobytes()).hexdigest()[:16]   # supports in selection order + coefficients
         batch.close()
 
         # ---- end to end through the C ABI with host buffers ----
@@ -449,33 +504,66 @@ class C2:
         d2h = B * (4 + 4 * k + 8 * k + 8 + 4)
         cs.lib.csb200_dict_trim(self.D._h)
 
-        # ---- roofline of the dominant kernel ----
-        committed, committed_src = fp64_peak_committed()
-        # denominator: the LARGER of the committed pool measurement and this run's own (the conservative choice; the
-        # live figure proves the box at hand is not faster than the committed peak)
-        if live and float(live["peak_tflops"]) > committed:
-            peak, peak_src = float(live["peak_tflops"]), ("measured in this run, inside the clocks window: tools/fp64_peak "
-                                                          "--quick (" + live["kernel"] + ")")
-        else:
-            peak, peak_src = committed, committed_src + ("; re-measured in this run inside the clocks window: %.2f TFLOP/s"
-                                                         % float(live["peak_tflops"]) if live else "")
-        # every update! of every signal is one column of a correlation pass, however the passes are cut into launches
-        # (large batches run as two half-batch launches per update!, see run_omp_split): flop per launch = total / launches
+        # ---- roofline of the correlation kernel ----
+        # every update! of every signal is one column of a correlation pass, however the passes are cut into launches:
+        # flop per launch = total / launches.  SURVEY 8(d): algorithmic work = 2 M N flop per signal-update.
         flop_total = 2.0 * M * N * B * k * steps
         flop_per_launch = flop_total / max(1, corr_launches)
         achieved = flop_total / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "corr_gemm_traffic.json")
-        if os.path.exists(tpath) and B == 65536:          # the ncu capture was taken at exactly this shape
-            traffic = json.load(open(tpath))["dram_bytes_per_launch"]
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic,
-                    "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/corr_gemm_traffic.json)",
-                    "kernel": "corr_gemm_f64_kernel", "launches": int(corr_launches),
-                    "mean_launch_ms": corr_ms / max(1, corr_launches), "share_of_step": corr_ms / dev_ms if dev_ms else None,
-                    "launches_per_update": corr_launches / max(1, k * steps),
-                    "flop_per_launch": flop_per_launch, "peak_source": peak_src, "peak_committed": committed,
-                    "peak_live": live}
+        share = corr_ms / dev_ms if dev_ms else None
+        if screened:
+            # TF32 screening pass (tcgen05): the flop EXECUTED are the algorithmic 2 M N B per pass (tiles 128 x 256 x K,
+            # K padded to 32: no padding at this shape), counted at TF32 -- reported against the TF32 tensor peak.
+            peak, peak_src = tf32_peak()
+            kpad = (M + 31) // 32 * 32
+            tiles = ((B + 127) // 128) * ((N + 255) // 256)
+            l2_bytes = tiles * kpad * 4.0 * (128 + 256)            # operand bytes TMA pulls from L2 per pass
+            passes = max(1, k * steps)
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                        "traffic": _traffic("corr_screen_traffic.json") if B == 65536 else None,
+                        "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/corr_screen_traffic.json)",
+                        "kernel": "corr_screen_tf32_kernel", "dtype": "tf32 operands, f32 accumulation (tcgen05.mma kind::tf32)",
+                        "launches": int(corr_launches), "mean_launch_ms": corr_ms / max(1, corr_launches), "share_of_step": share,
+                        "launches_per_update": corr_launches / passes, "flop_per_launch": flop_per_launch,
+                        "peak_source": peak_src, "peak_nominal": 1125.0, "frac_of_nominal": achieved / 1125.0,
+                        "library_gemm_live": live,
+                        "l2_operand_bytes_per_pass": l2_bytes,
+                        "l2_to_sm_tbs": l2_bytes * passes / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else None,
+                        "l2_to_sm_port_tbs": 148 * 64 * 1.965e9 / 1e12,
+                        "note": "the pass is bound by the SMs' L2 read ports (64 B/clk/SM), not by the tensor pipe: see DESIGN 4.14"}
+            # the rest of the step is omp_update_kernel (L2-gather-bound): its share and its gather rate
+            upd_ms = dev_ms - corr_ms
+            gather_bytes = sum((t + 3) for t in range(k)) * M * 8.0 * B * steps      # t active columns + a_j, b, r per update!
+            roofline_update = {"kernel": "omp_update_kernel", "bound": "l2 gather", "share_of_step": upd_ms / dev_ms if dev_ms else None,
+                               "ms_per_update": upd_ms / passes, "algorithmic_gather_bytes_per_step": gather_bytes / steps,
+                               "achieved_tbs": gather_bytes / (upd_ms * 1e-3) / 1e12 if upd_ms > 0 else None}
+            equiv = value / ctx.world * 2.0 * M * N * k / 1e12
+            fp64_equiv = {"tflops_equivalent": equiv, "of_fp64_dmma_peak": equiv / fp64_peak_committed()[0],
+                          "note": "solves/s x the reference algorithm's 2 M N k flop per solve: NOT a roofline fraction (the "
+                                  "FP64 flop are not executed: SURVEY 8d), stated separately"}
+        else:
+            committed, committed_src = fp64_peak_committed()
+            # denominator: the LARGER of the committed pool measurement and this run's own (the conservative choice; the
+            # live figure proves the box at hand is not faster than the committed peak)
+            if live and float(live["peak_tflops"]) > committed:
+                peak, peak_src = float(live["peak_tflops"]), ("measured in this run, inside the clocks window: tools/fp64_peak "
+                                                              "--quick (" + live["kernel"] + ")")
+            else:
+                peak, peak_src = committed, committed_src + ("; re-measured in this run inside the clocks window: %.2f TFLOP/s"
+                                                             % float(live["peak_tflops"]) if live else "")
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "corr_gemm_traffic.json")
+            if os.path.exists(tpath) and B == 65536:          # the ncu capture was taken at exactly this shape
+                traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                        "traffic": traffic,
+                        "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/corr_gemm_traffic.json)",
+                        "kernel": "corr_gemm_f64_kernel", "launches": int(corr_launches),
+                        "mean_launch_ms": corr_ms / max(1, corr_launches), "share_of_step": share,
+                        "launches_per_update": corr_launches / max(1, k * steps),
+                        "flop_per_launch": flop_per_launch, "peak_source": peak_src, "peak_committed": committed,
+                        "peak_live": live}
+            roofline_update, fp64_equiv = None, None
 
         # ---- CPU baseline + oracle parity (rank 0, N = 1 only) ----
         cpu, parity = None, None
@@ -492,8 +580,11 @@ class C2:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "support_recovered_frac": e2e_ok, "bit_identical_to_resident_path": e2e_same},
             "gpu_launches": int(corr_launches + other_launches + steps),
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "check": {"support_recovered_frac": recovered, "max_resnorm": max_res, "oracle_parity": parity},
+            "roofline": roofline, "roofline_update": roofline_update, "fp64_equivalent": fp64_equiv,
+            "cpu_baseline": cpu, "clocks": clocks,
+            "check": {"support_recovered_frac": recovered, "max_resnorm": max_res, "oracle_parity": parity,
+                      "result_digest": digest, "path": scr["path"], "screening": ({key: scr[key] for key in ("signal_updates", "candidates_reevaluated", "exact_scans")}
+                                                         if screened else None)},
         }
 
     def close(self):
@@ -517,6 +608,13 @@ def run_c2(ctx, args, headline=True):
                  "signals_per_gpu": o["signals_per_gpu"], "global_signals": o["signals_per_gpu"] * world,
                  "e2e": o["e2e"], "roofline_frac": o["roofline"]["frac"], "gemm_share_of_step": o["roofline"]["share_of_step"],
                  "check": o["check"]}
+    fp64_path = None
+    if args.fp64_steps > 0 and main["check"]["path"].startswith("tf32"):
+        # the same workload through the FP64 DMMA pass (CSB200_SCREEN=0): what the screening buys, and the FP64 kernel's roofline
+        o = c2.measure(sizes[first], args.fp64_steps, 1, 1, with_peak=True, screen=False)
+        fp64_path = {"value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"], "e2e": o["e2e"], "roofline": o["roofline"],
+                     "check": o["check"],
+                     "bit_identical_to_screened_path": o["check"]["result_digest"] == main["check"]["result_digest"]}
     c2.close()
     B = main.pop("signals_per_gpu")
     line = {
@@ -533,6 +631,8 @@ def run_c2(ctx, args, headline=True):
     line.update(main)
     if other is not None:
         line[second] = other
+    if fp64_path is not None:
+        line["fp64_path"] = fp64_path
     return line
 
 

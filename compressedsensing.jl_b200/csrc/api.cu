@@ -812,36 +812,109 @@ int ensure_screen_batch(csb200_batch* b) {
 }
 
 // returns 1 when the screening path cannot be set up (the caller then takes the DMMA path)
+//
+// Schedule.  Serial (the default): pass, update, pass, update ... on the batch's stream.  Overlapped (CSB200_SCREEN_PARTS =
+// 2..4, batches of >= 2 x 4096 signals): the signals are cut into parts of whole 128-signal tiles; passes run on a
+// high-priority stream, updates on a low-priority one, tied by events G(h,i) -> U(h,i) -> G(h,i+1) exactly as in
+// run_omp_split, so the update of one part runs under the screening pass of the next; for the two kernels to share an SM
+// the pass then runs with a 3-stage ring (150 KiB) and both ask for the largest shared-memory carve-out.  Same kernels on
+// the same data in either schedule: results are bit-identical.  Measured at the headline shape (profiles/screen_r02.md):
+// serial 588 k solves/s, two parts 477 k (3 stages) / 561 k (4 stages), three / four parts 480 k / 476 k -- unlike the
+// DMMA pass, the screening pass is bound by the L2 read ports, which is what the update's gathers need as well, so running
+// them together slows the pass more (0.76 -> 1.06-1.8 ms per half) than it hides of the update.  Hence serial.
 int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
     csb200_dict* d = b->dict;
     int rc = ensure_screen_dict(d, b->stream);
     if (rc) return rc;
     if ((rc = ensure_screen_batch(b))) return rc;
-    const int chunks = screen_chunks_for((int)d->N, (int)b->nsig, d->num_sms);
-    CUtensorMap mapR32;
-    if ((rc = make_operand_map32(&mapR32, b->dR32, d->ld32, b->nsig, 128))) return rc;
-    StateArgs ua = state_args(b, 1, 1, eps, 0);
-    ua.scr_val = b->scr_val; ua.scr_idx = b->scr_idx; ua.scr_nc = chunks * SCREEN_T;
-    ua.scr_bound = SCREEN_KAPPA * d->amax;
-    ua.R32 = b->dR32; ua.ld32 = (int)d->ld32; ua.scr_stats = b->scr_stats;
-    cudaError_t e = launch_reset_state(ua, false, b->stream);
-    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
-    for (int64_t it = 0; it < k; ++it) {
+    const int parts_env = [] { const char* e = getenv("CSB200_SCREEN_PARTS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+    const int64_t tiles = (b->nsig + 127) / 128;
+    int NP = b->nsig >= 2 * SCREEN_MIN_SIGNALS && k >= 2 ? parts_env : 1;
+    if (tiles < NP) NP = (int)tiles;
+    const int stages = [&] { const char* e = getenv("CSB200_SCREEN_STAGES"); const int v = e ? atoi(e) : 0; return v == 3 || v == 4 ? v : (NP > 1 ? 3 : 4); }();
+    int64_t start[4], count[4];
+    {
+        int64_t t0 = 0;
+        for (int h = 0; h < NP; ++h) {
+            const int64_t nt = tiles / NP + (h < tiles % NP ? 1 : 0);
+            start[h] = t0 * 128;
+            const int64_t end = (t0 + nt) * 128 < b->nsig ? (t0 + nt) * 128 : b->nsig;
+            count[h] = end - start[h];
+            t0 += nt;
+        }
+    }
+    const int chunks = screen_chunks_for((int)d->N, (int)count[0], d->num_sms);
+    const int nc = chunks * SCREEN_T;
+    CUtensorMap mapR32[4];
+    for (int h = 0; h < NP; ++h)
+        if ((rc = make_operand_map32(&mapR32[h], b->dR32 + (size_t)start[h] * d->ld32, d->ld32, count[h], 128))) return rc;
+    auto screen_args = [&](int h) {
+        StateArgs ua = state_args_range(b, start[h], count[h], 1, 1, eps, 0);
+        ua.scr_val = b->scr_val + (size_t)start[h] * nc; ua.scr_idx = b->scr_idx + (size_t)start[h] * nc; ua.scr_nc = nc;
+        ua.scr_bound = SCREEN_KAPPA * d->amax;
+        ua.R32 = b->dR32 + (size_t)start[h] * d->ld32; ua.ld32 = (int)d->ld32; ua.scr_stats = b->scr_stats;
+        return ua;
+    };
+    auto pass = [&](int h, cudaStream_t st) -> int {
         cudaEvent_t p0 = nullptr, p1 = nullptr;
         if (b->profile) {
             if (b->ev_used + 2 > b->ev.size())
                 for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); b->ev.push_back(ev); }
             p0 = b->ev[b->ev_used]; p1 = b->ev[b->ev_used + 1]; b->ev_used += 2;
-            CU_TRY(cudaEventRecord(p0, b->stream));
+            CU_TRY(cudaEventRecord(p0, st));
         }
-        e = launch_corr_screen(&mapR32, &d->mapA32, (int)d->N, (int)b->nsig, (int)d->ld32, chunks, (int)d->n_offset,
-                               b->scr_val, b->scr_idx, d->num_sms, b->stream);
-        if (e != cudaSuccess) return fail_cuda(e, "screening kernel launch");
-        if (b->profile) CU_TRY(cudaEventRecord(p1, b->stream));
-        e = launch_omp_update(ua, false, b->stream);
-        if (e != cudaSuccess) return fail_cuda(e, "omp_update");
-        b->other_launches++;
+        cudaError_t e2 = launch_corr_screen(&mapR32[h], &d->mapA32, (int)d->N, (int)count[h], (int)d->ld32, chunks, (int)d->n_offset,
+                                            b->scr_val + (size_t)start[h] * nc, b->scr_idx + (size_t)start[h] * nc, d->num_sms, st, stages);
+        if (e2 != cudaSuccess) return fail_cuda(e2, "screening kernel launch");
+        if (b->profile) CU_TRY(cudaEventRecord(p1, st));
+        return CSB200_OK;
+    };
+    {
+        StateArgs ra = state_args(b, 1, 1, eps, 0);
+        ra.R32 = b->dR32; ra.ld32 = (int)d->ld32;
+        cudaError_t e = launch_reset_state(ra, false, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "reset_state");
     }
+    if (NP == 1) {
+        StateArgs ua = screen_args(0);
+        ua.max_smem_carveout = 1;                                        // the pass's shared-memory configuration: no SM reconfiguration between kernels
+        for (int64_t it = 0; it < k; ++it) {
+            if ((rc = pass(0, b->stream))) return rc;
+            cudaError_t e = launch_omp_update(ua, false, b->stream);
+            if (e != cudaSuccess) return fail_cuda(e, "omp_update");
+            b->other_launches++;
+        }
+        b->last_path = 3;
+        return CSB200_OK;
+    }
+    if (!b->sp_gemm) {
+        int lo = 0, hi = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));             // hi = numerically lowest = greatest priority
+        CU_TRY(cudaStreamCreateWithPriority(&b->sp_gemm, cudaStreamNonBlocking, hi));
+        CU_TRY(cudaStreamCreateWithPriority(&b->sp_upd, cudaStreamNonBlocking, lo));
+        for (auto& e : b->sp_ev) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t G = b->sp_gemm, U = b->sp_upd;
+    cudaEvent_t ev_start = b->sp_ev[0], ev_end = b->sp_ev[1], *evG = &b->sp_ev[2], *evU = &b->sp_ev[6];
+    CU_TRY(cudaEventRecord(ev_start, b->stream));
+    CU_TRY(cudaStreamWaitEvent(G, ev_start, 0));
+    CU_TRY(cudaStreamWaitEvent(U, ev_start, 0));
+    for (int64_t it = 0; it < k; ++it) {
+        for (int h = 0; h < NP; ++h) {
+            if (it > 0) CU_TRY(cudaStreamWaitEvent(G, evU[h], 0));       // the part's residuals of this update! are in place
+            if ((rc = pass(h, G))) return rc;
+            CU_TRY(cudaEventRecord(evG[h], G));
+            CU_TRY(cudaStreamWaitEvent(U, evG[h], 0));
+            StateArgs ua = screen_args(h);
+            ua.max_smem_carveout = 1;
+            cudaError_t e = launch_omp_update(ua, false, U);
+            if (e != cudaSuccess) return fail_cuda(e, "omp_update");
+            CU_TRY(cudaEventRecord(evU[h], U));
+            b->other_launches++;
+        }
+    }
+    CU_TRY(cudaEventRecord(ev_end, U));                                  // U's last update follows every G launch
+    CU_TRY(cudaStreamWaitEvent(b->stream, ev_end, 0));
     b->last_path = 3;
     return CSB200_OK;
 }
@@ -1845,6 +1918,10 @@ constexpr int64_t PIPE_MIN_SIGNALS = 32768;     // below this a single upload is
 // waves -- (atom tiles) x (signal tiles of the chunk) a multiple of the SM count -- or chunking adds a partial wave
 // per launch.  q = signal tiles per whole-wave group; the chunk is the multiple of 128 q closest to 16 384 signals.
 static int64_t pipe_chunk_signals(const csb200_dict* d) {
+    if (const char* e = getenv("CSB200_PIPE_CHUNK")) {           // experiment hook: chunk size in signals (multiple of 128)
+        const int64_t v = atoll(e) / 128 * 128;
+        if (v >= 1024) return v;
+    }
     const int64_t tilesN = (d->N + 127) / 128;
     int64_t a = d->num_sms, b = tilesN;
     while (b) { const int64_t t = a % b; a = b; b = t; }

@@ -67,7 +67,7 @@ cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap*
 int screen_chunks_for(int N, int nsig, int num_sms);
 cudaError_t corr_screen_setup();
 cudaError_t launch_corr_screen(const CUtensorMap* mapR32, const CUtensorMap* mapA32, int N, int nsig, int ld32, int chunks,
-                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st);
+                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st, int stages = 4);
 cudaError_t launch_to_tf32(const void* in, bool f32, long long ld_in, float* out, long long ld_out, int rows, long long cols,
                            cudaStream_t st);
 // GEMV pass: a.P = corr_gemv_blocks(...) CTAs per signal, each emitting the top-S of its contiguous atom range.

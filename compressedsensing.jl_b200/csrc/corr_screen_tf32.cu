@@ -31,12 +31,13 @@ namespace {
 constexpr int ST_SIG = 128;                    // signals per tile  (UMMA M, TMEM lanes)
 constexpr int ST_ATOM = 256;                   // atoms per tile    (UMMA N, TMEM columns per accumulator stage)
 constexpr int ST_KB = 32;                      // floats per K-block: 128-byte swizzle rows
-constexpr int ST_STAGES = 4;
+// Pipeline depth: 4 stages (198 KiB) when the pass has the SM to itself; 3 stages (150 KiB) leave ~77 KiB of shared memory
+// for CTAs of omp_update_kernel, which run under the pass in the overlapped schedule (api.cu, run_omp_screen).
 constexpr int ST_A_BYTES = ST_SIG * ST_KB * 4;     // 16 KiB of R32
 constexpr int ST_B_BYTES = ST_ATOM * ST_KB * 4;    // 32 KiB of A32
 constexpr int ST_STAGE_BYTES = ST_A_BYTES + ST_B_BYTES;
 constexpr int ST_BAR_BYTES = 128;
-constexpr int ST_SMEM_BYTES = ST_STAGES * ST_STAGE_BYTES + ST_BAR_BYTES + 1024 /* alignment slack */;
+constexpr int st_smem_bytes(int stages) { return stages * ST_STAGE_BYTES + ST_BAR_BYTES + 1024 /* alignment slack */; }
 constexpr int ST_THREADS = 192;
 constexpr int ST_TMEM_COLS = 512;
 
@@ -116,6 +117,7 @@ __device__ __forceinline__ void top_insert(float (&v)[SCREEN_T], int (&id)[SCREE
     }
 }
 
+template <int ST_STAGES>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapA,
                         int N, int nsig, int kblocks, int tilesN, int chunks, int tiles_per_chunk, int units,
@@ -260,40 +262,47 @@ __global__ void __launch_bounds__(256) to_tf32_kernel(const T* __restrict__ in, 
 
 }  // namespace
 
+// Atom chunks per signal tile.  A work unit is (128 signals) x (one chunk); MANY SHORT units beat few long ones: with 148
+// units of 32 tiles each (one exact wave) a single SM that is still busy with the previous kernel's tail -- or with another
+// stream's kernel -- delays its unit by a whole pass (measured: the 18 944-signal chunks of the pipelined one-shot path ran
+// 30 % slower than 9 472-signal ones).  So: as many chunks as leave >= SCREEN_MIN_TILES tiles per unit, at most 8.
 int screen_chunks_for(int N, int nsig, int num_sms) {
+    (void)nsig; (void)num_sms;
+    constexpr int SCREEN_MIN_TILES = 4;
     const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
-    const long long sig_tiles = (nsig + ST_SIG - 1) / ST_SIG;
     static const int forced = [] { const char* e = getenv("CSB200_SCREEN_CHUNKS"); return e ? atoi(e) : 0; }();
     int best = 1;
-    double best_eff = -1.0;
     for (int c = 1; c <= SCREEN_MAX_CHUNKS; c *= 2) {
         if (c > tilesN) break;
-        if (forced == c) return c;
         const int tpc = (tilesN + c - 1) / c;
-        const int cc = (tilesN + tpc - 1) / tpc;                   // chunks that actually hold tiles
-        if (cc != c) continue;
-        const long long units = sig_tiles * c;
-        const long long waves = (units + num_sms - 1) / num_sms;
-        const double eff = (double)units / (double)(waves * num_sms);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = c; }   // prefer fewer chunks unless the last wave fills up noticeably
+        if ((tilesN + tpc - 1) / tpc != c) continue;               // a chunk count that would leave an empty chunk
+        if (forced == c) return c;
+        if (tpc >= SCREEN_MIN_TILES) best = c;
     }
     return best;
 }
 
 cudaError_t corr_screen_setup() {
-    return cudaFuncSetAttribute(corr_screen_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(corr_screen_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(4));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_screen_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(3));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_screen_tf32_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    return e;
 }
 
 cudaError_t launch_corr_screen(const CUtensorMap* mapR32, const CUtensorMap* mapA32, int N, int nsig, int ld32, int chunks,
-                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st) {
+                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st, int stages) {
     if (nsig <= 0 || N <= 0) return cudaSuccess;
     const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
     const int tpc = (tilesN + chunks - 1) / chunks;
     const int sig_tiles = (nsig + ST_SIG - 1) / ST_SIG;
     const int units = sig_tiles * chunks;
     const int grid = units < num_sms ? units : num_sms;
-    corr_screen_tf32_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(*mapR32, *mapA32, N, nsig, ld32 / ST_KB, tilesN, chunks, tpc,
-                                                                      units, idx_offset, cval, cidx);
+    if (stages == 3)
+        corr_screen_tf32_kernel<3><<<grid, ST_THREADS, st_smem_bytes(3), st>>>(*mapR32, *mapA32, N, nsig, ld32 / ST_KB, tilesN, chunks,
+                                                                               tpc, units, idx_offset, cval, cidx);
+    else
+        corr_screen_tf32_kernel<4><<<grid, ST_THREADS, st_smem_bytes(4), st>>>(*mapR32, *mapA32, N, nsig, ld32 / ST_KB, tilesN, chunks,
+                                                                               tpc, units, idx_offset, cval, cidx);
     return cudaGetLastError();
 }
 

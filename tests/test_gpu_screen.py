@@ -101,6 +101,38 @@ def test_screened_omp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch, M
         assert np.allclose(coef1[s, :n][o], ref.nzval, rtol=RTOL64, atol=RTOL64 * max(1.0, np.max(np.abs(ref.nzval))))
 
 
+@pytest.mark.parametrize("parts", [2, 3])
+def test_overlapped_screening_schedule_is_bit_identical(cs, po, monkeypatch, parts):
+    """Batches of >= 8192 signals run the screening pass of one part of the batch over the update of another (two streams,
+    3-stage pass co-resident with update CTAs): same kernels on the same data, so every output equals the serial schedule's."""
+    monkeypatch.setenv("CSB200_SCREEN", "1")
+    rng = np.random.default_rng(99 + parts)
+    M, N, k, B = 100, 300, 5, 8192 + 77
+    A = po.gaussian_dictionary(rng, M, N)
+    Bm, planted = _planted(po, rng, A, B, k, noise=1e-3)
+    Bm[:, 5::7] = A[:, planted[5::7, 0]] * 2.0
+    out = {}
+    with cs.Dictionary(A) as D:
+        for p in (1, parts):
+            monkeypatch.setenv("CSB200_SCREEN_PARTS", str(p))
+            with cs.Batch(D, B, k) as batch:
+                batch.upload(Bm)
+                batch.profile(True)
+                batch.omp(k, 1e-9)
+                ms, launches, other = batch.corr_time()
+                batch.profile(False)
+                assert launches == p * k and ms > 0 and batch.screen_stats()["path_id"] == 3
+                out[p] = batch.download(k) + (batch.residual(),)
+    for a, b in zip(out[1], out[parts]):
+        assert np.array_equal(a, b)
+    sel, coef, nnz, res, its, R = out[parts]
+    assert (its[5::7] == 1).all() and (nnz[5::7] == 1).all()
+    for s in (0, 5, 4100, B - 1):
+        t = po.Trace()
+        po.omp(A, Bm[:, s], k, eps=1e-9, trace=t)
+        assert sel[s, :int(nnz[s])].tolist() == t.order() and int(its[s]) == t.iterations
+
+
 def test_screened_omp_ties_zero_signals_and_out_of_range_norms(cs, po, monkeypatch):
     """Duplicate atoms (bit-identical |c|: the lower index must win, KAT-4), an all-zero signal (arg-max of zeros is atom 0,
     which is appended with coefficient 0: KAT-6), signals whose norm is outside the range the FP32 operands cover (exact
