@@ -866,7 +866,28 @@ def run_c5(ctx, args):
         dev_ms = b.last_solve_ms()
         corr_ms, n, other = b.corr_time()
         b.profile(False)
+        scr = b.screen_stats(reset=True)
         sel, coef, nnz, res, its = b.download(iters)
+        dev_ms64, other_leg = None, None
+        # the same workload through the other correlation pass (a few iterations, scaled): FP64 DMMA when the default
+        # screened, forced TF32 screening when the default is the DMMA pass (signals longer than 2048 rows)
+        os.environ["CSB200_SCREEN"] = "0" if scr["path_id"] == 3 else "1"
+        try:
+            it2 = max(2, min(iters, 16))
+            b.mp(it2)
+            dev_ms64 = b.last_solve_ms() * iters / it2
+            scr2 = b.screen_stats(reset=True)
+            sel2, coef2, *_ = b.download(it2)
+            same2 = bool(np.array_equal(sel2[:, :it2], sel[:, :it2]) and np.array_equal(coef2[:, :it2], coef[:, :it2]))
+            other_leg = {"value": B / (dev_ms64 * 1e-3), "unit": UNIT, "path": scr2["path"],
+                         "how": f"CSB200_SCREEN={os.environ['CSB200_SCREEN']}, the first {it2} iterations scaled to {iters} "
+                                "(later iterations run deeper into the noise, where the screening window holds more atoms)",
+                         "bit_identical_to_default_path": same2}
+        finally:
+            os.environ.pop("CSB200_SCREEN", None)
+    screened = scr["path_id"] == 3
+    if screened:
+        peak, peak_src = tf32_peak()
     tf = 2.0 * Mr * Nc * B * n / corr_ms / 1e9
     cpu, parity = None, None
     if ctx.rank == 0 and ctx.world == 1 and args.cpu_signals > 0:
@@ -899,9 +920,12 @@ def run_c5(ctx, args):
                    "iterations": iters, "signals": B, "l2": "2 GiB dictionary exceeds the 126 MB L2"},
         "gpu_launches": int(n + other + 1),
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
-                     "kernel": "corr_gemm_f64_kernel", "launches": int(n), "mean_launch_ms": corr_ms / max(1, n),
+                     "kernel": "corr_screen_tf32_kernel" if screened else "corr_gemm_f64_kernel", "launches": int(n),
+                     "mean_launch_ms": corr_ms / max(1, n),
                      "share_of_step": corr_ms / dev_ms, "flop_per_launch": 2.0 * Mr * Nc * B, "peak_source": peak_src},
-        "cpu_baseline": cpu, "check": {"median_resnorm": float(np.median(res)), "oracle_parity": parity},
+        "other_path": other_leg,
+        "cpu_baseline": cpu, "check": {"median_resnorm": float(np.median(res)), "oracle_parity": parity, "path": scr["path"],
+                                       "screening": {key: scr[key] for key in ("signal_updates", "candidates_reevaluated", "exact_scans")} if screened else None},
     }
 
 

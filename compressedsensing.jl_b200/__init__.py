@@ -337,8 +337,8 @@ class Batch:
 
     def debug_screen_pass(self):
         """One TF32 screening pass over the current residuals: (|c~| [nsig, chunks*8], atom [nsig, chunks*8], bound)."""
-        val = np.empty((self.nsig, 64), dtype=np.float32)
-        idx = np.empty((self.nsig, 64), dtype=np.int32)
+        val = np.empty((self.nsig, 128), dtype=np.float32)
+        idx = np.empty((self.nsig, 128), dtype=np.int32)
         chunks = c_int64()
         bound = c_double()
         _check(lib.csb200_debug_screen_pass(self._h, val.ctypes.data, idx.ctypes.data, byref(chunks), byref(bound)))

@@ -748,19 +748,24 @@ int run_omp_split(csb200_batch* b, int64_t k, double eps) {
 // among the candidates in FP64 (update.cu, screen_select): the support is the FP64 arg-max sequence, the coefficients
 // come from the same FP64 update as before.  CSB200_SCREEN=0 keeps the DMMA pass, =1 forces screening where it is legal.
 constexpr int64_t SCREEN_MIN_SIGNALS = 4096;
+// Signal length up to which screening is the DEFAULT.  The window holds about exp(2 kappa(M) sqrt(M) sqrt(2 ln N)) atoms
+// once a residual is noise-like (all |c| alike): 1.4 at M = 1024, 3.5 at 2048, but 12 at 4096 (measured 14 on config 5,
+// where mp's 200 steps run far into the noise: re-evaluations and whole-chunk scans eat most of what the pass saves,
+// 443 vs 333 solves/s) and ~180 at 8192.  Longer signals are screened only on request (CSB200_SCREEN=1).
+constexpr int64_t SCREEN_AUTO_MAX_ROWS = 2048;
 bool screen_legal(const csb200_batch* b) {
     const csb200_dict* d = b->dict;
     if (d->dtype != CSB200_F64 || d->n_total != d->N || d->screen_failed) return false;
     if (d->M > SCREEN_MAX_ROWS || d->N < 256) return false;
-    if (b->corr_impl_env != IMPL_AUTO) return false;
-    return omp_update_smem_bytes((int)d->ld, (int)b->kcap) <= MAX_DYN_SMEM;
+    return b->corr_impl_env == IMPL_AUTO;
 }
 bool use_omp_screen(const csb200_batch* b, int64_t k) {
     const char* env = getenv("CSB200_SCREEN");
     if (env && env[0] == '0') return false;
     if (!screen_legal(b) || uses_cluster_update(b) || k < 1) return false;
+    if (omp_update_smem_bytes((int)b->dict->ld, (int)b->kcap) > MAX_DYN_SMEM) return false;
     if (env && env[0] == '1') return true;
-    return b->nsig >= SCREEN_MIN_SIGNALS;
+    return b->nsig >= SCREEN_MIN_SIGNALS && b->dict->M <= SCREEN_AUTO_MAX_ROWS;
 }
 
 // dictionary side (once per handle): TF32 copy, tensor map, largest column norm
@@ -851,7 +856,8 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
     auto screen_args = [&](int h) {
         StateArgs ua = state_args_range(b, start[h], count[h], 1, 1, eps, 0);
         ua.scr_val = b->scr_val + (size_t)start[h] * nc; ua.scr_idx = b->scr_idx + (size_t)start[h] * nc; ua.scr_nc = nc;
-        ua.scr_bound = SCREEN_KAPPA * d->amax;
+        ua.scr_chunk_atoms = screen_chunk_atoms((int)d->N, chunks);
+        ua.scr_bound = screen_kappa((int)d->M) * d->amax;
         ua.R32 = b->dR32 + (size_t)start[h] * d->ld32; ua.ld32 = (int)d->ld32; ua.scr_stats = b->scr_stats;
         return ua;
     };
@@ -915,6 +921,44 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
     }
     CU_TRY(cudaEventRecord(ev_end, U));                                  // U's last update follows every G launch
     CU_TRY(cudaStreamWaitEvent(b->stream, ev_end, 0));
+    b->last_path = 3;
+    return CSB200_OK;
+}
+
+// Plain matching pursuit through the same screening pass (`mp`, src/matchingpursuit.jl:26-40; no warm start): per step one
+// TF32 pass + mp_update_kernel, which decides among the screened candidates in FP64, computes the winner's <a_i, r> in FP64
+// (the coefficient increment) and down-dates r and its TF32 copy.  Returns 1 when screening cannot be set up.
+int run_mp_screen(csb200_batch* b, int64_t iters) {
+    csb200_dict* d = b->dict;
+    int rc = ensure_screen_dict(d, b->stream);
+    if (rc) return rc;
+    if ((rc = ensure_screen_batch(b))) return rc;
+    const int chunks = screen_chunks_for((int)d->N, (int)b->nsig, d->num_sms);
+    CUtensorMap mapR32;
+    if ((rc = make_operand_map32(&mapR32, b->dR32, d->ld32, b->nsig, 128))) return rc;
+    StateArgs ua = state_args(b, 1, 1, 0.0, 0);
+    ua.scr_val = b->scr_val; ua.scr_idx = b->scr_idx; ua.scr_nc = chunks * SCREEN_T;
+    ua.scr_chunk_atoms = screen_chunk_atoms((int)d->N, chunks);
+    ua.scr_bound = screen_kappa((int)d->M) * d->amax;
+    ua.R32 = b->dR32; ua.ld32 = (int)d->ld32; ua.scr_stats = b->scr_stats;
+    cudaError_t e = launch_reset_state(ua, false, b->stream);
+    if (e != cudaSuccess) return fail_cuda(e, "reset_state");
+    for (int64_t it = 0; it < iters; ++it) {
+        cudaEvent_t p0 = nullptr, p1 = nullptr;
+        if (b->profile) {
+            if (b->ev_used + 2 > b->ev.size())
+                for (int i = 0; i < 2; ++i) { cudaEvent_t ev; CU_TRY(cudaEventCreate(&ev)); b->ev.push_back(ev); }
+            p0 = b->ev[b->ev_used]; p1 = b->ev[b->ev_used + 1]; b->ev_used += 2;
+            CU_TRY(cudaEventRecord(p0, b->stream));
+        }
+        e = launch_corr_screen(&mapR32, &d->mapA32, (int)d->N, (int)b->nsig, (int)d->ld32, chunks, (int)d->n_offset, b->scr_val,
+                               b->scr_idx, d->num_sms, b->stream, 4);
+        if (e != cudaSuccess) return fail_cuda(e, "screening kernel launch");
+        if (b->profile) CU_TRY(cudaEventRecord(p1, b->stream));
+        e = launch_mp_update(ua, false, (int)it, (int)b->kcap, b->stream);
+        if (e != cudaSuccess) return fail_cuda(e, "mp_update");
+        b->other_launches++;
+    }
     b->last_path = 3;
     return CSB200_OK;
 }
@@ -1705,6 +1749,15 @@ int csb200_batch_mp(csb200_batch* b, int64_t iters, const int64_t* x0_idx, const
     if ((rc = check_shape_fits(b, false))) return rc;
     if ((rc = settle_input(b))) return rc;
     if ((rc = begin_solve(b))) return rc;
+    b->last_path = corr_impl_for(b) == IMPL_GEMM ? 1 : 0;
+    {
+        const char* env = getenv("CSB200_SCREEN");
+        const bool off = env && env[0] == '0', force = env && env[0] == '1';
+        if (!warm && !off && screen_legal(b) && iters >= 1 && (force || (b->nsig >= SCREEN_MIN_SIGNALS && d->M <= SCREEN_AUTO_MAX_ROWS))) {
+            if ((rc = run_mp_screen(b, iters)) == CSB200_OK) return finish(b, true);
+            if (rc != 1) return rc;
+        }
+    }
     // a warm start reads temporary buffers: only the plain form is replayable
     rc = run_graphed(b, 2, iters, 1, 0.0, warm ? 0 : iters, [&]() -> int {
         cudaError_t e = launch_reset_state(state_args(b, 1, 1, 0.0, 0), f32, b->stream);
@@ -2402,7 +2455,7 @@ int csb200_debug_screen_pass(csb200_batch* b, float* val, int32_t* idx, int64_t*
     if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "debug_screen_pass");
     *chunks_out = chunks;
-    if (bound_out) *bound_out = SCREEN_KAPPA * d->amax;
+    if (bound_out) *bound_out = screen_kappa((int)d->M) * d->amax;
     return CSB200_OK;
 }
 

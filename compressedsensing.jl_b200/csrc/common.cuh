@@ -14,14 +14,16 @@ constexpr int PBLK = 64;
 constexpr int MAX_S = 64;          // candidates per 64-atom block the fused DMMA epilogue can emit (= the block size)
 constexpr int GOMP_MAX_L = 256;    // atoms per gomp update! (l); larger l: CSB200_ERR_UNSUPPORTED
 constexpr int ROW_ALIGN = 16;      // leading dimensions are padded to 16 elements (128 B for f64)
-// TF32 screening pass of the batched omp solve (corr_screen_tf32.cu): per (signal, atom chunk) the SCREEN_T largest
-// |c~|; |c~_j - <a_j, r>| <= SCREEN_KAPPA * max_j ||a_j|| * ||r||.  Operands are rounded to TF32 (2^-11 each, so
-// 2^-10 + 2^-22 per product, summed with Cauchy-Schwarz), the FP32 accumulation over K <= SCREEN_MAX_ROWS terms adds
-// at most K * 2^-22 of sum |a_i r_i| (truncating adds, two roundings per term): 0.98e-3 + 0.5e-3 at the cap.
+// TF32 screening pass of the batched omp / mp solves (corr_screen_tf32.cu): per (signal, atom chunk) the SCREEN_T largest
+// |c~|, with |c~_j - <a_j, r>| <= screen_kappa(M) * max_j ||a_j|| * ||r||.  Operands are rounded to TF32 (2^-11 each, so at
+// most 2^-10 + 2^-22 per product; summed with Cauchy-Schwarz: sum |a_i r_i| <= ||a|| ||r||); the FP32 accumulation of M
+// exact products adds at most M * 2^-22 of sum |a_i r_i| even if every add TRUNCATES (one ulp each); 5 % margin on top.
+// M = 1024: 1.28e-3; M = 4096: 2.05e-3.  tests/test_gpu_screen.py measures the actual error (Gaussian data: < 0.1 of the
+// bound; all-positive operands, where truncation would add up: see the test) against it.
 constexpr int SCREEN_T = 8;
-constexpr int SCREEN_MAX_CHUNKS = 8;
-constexpr int SCREEN_MAX_ROWS = 2048;
-constexpr double SCREEN_KAPPA = 1.6e-3;
+constexpr int SCREEN_MAX_CHUNKS = 16;
+constexpr int SCREEN_MAX_ROWS = 8192;
+__host__ __device__ inline double screen_kappa(int M) { return 1.05 * (9.765625e-4 + 2.384185791015625e-7 + (double)M * 2.384185791015625e-7); }
 constexpr double SCREEN_NORM_MIN = 1e-18, SCREEN_NORM_MAX = 1e18;   // residual norms outside: exact scan (FP32 range)
 
 #ifdef __CUDACC__
@@ -65,6 +67,7 @@ cudaError_t launch_corr_gemm_f64_ols(const CUtensorMap* mapA, const CUtensorMap*
                                      const CorrArgs& a, double* resc, long long ldr, int num_sms, cudaStream_t st);
 // TF32 screening pass (corr_screen_tf32.cu): cval / cidx [nsig][chunks][SCREEN_T]; ld32 = rows of the FP32 operands (multiple of 32)
 int screen_chunks_for(int N, int nsig, int num_sms);
+int screen_chunk_atoms(int N, int chunks);      // atoms covered by one chunk (whole 256-atom tiles)
 cudaError_t corr_screen_setup();
 cudaError_t launch_corr_screen(const CUtensorMap* mapR32, const CUtensorMap* mapA32, int N, int nsig, int ld32, int chunks,
                                int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st, int stages = 4);
@@ -114,7 +117,8 @@ struct StateArgs {
     const float* scr_val = nullptr;   // [nsig][scr_nc] |c~| descending per chunk of SCREEN_T
     const int* scr_idx = nullptr;     // [nsig][scr_nc] global atom index or -1
     int scr_nc = 0;                   // chunks * SCREEN_T
-    double scr_bound = 0.0;           // SCREEN_KAPPA * max_j ||a_j||: E = scr_bound * ||r||
+    int scr_chunk_atoms = 0;          // atoms per chunk: chunk c covers local atoms [c * scr_chunk_atoms, (c + 1) * scr_chunk_atoms)
+    double scr_bound = 0.0;           // screen_kappa(M) * max_j ||a_j||: E = scr_bound * ||r||
     float* R32 = nullptr;             // [nsig][ld32] TF32-rounded residuals (the screening pass's operand)
     int ld32 = 0;
     unsigned long long* scr_stats = nullptr;   // optional counters: [0] signal-updates screened, [1] candidates re-evaluated, [2] exact scans

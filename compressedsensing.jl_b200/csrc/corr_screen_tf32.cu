@@ -1,11 +1,11 @@
-// Screening pass of the batched omp solve:  C~ = R' A  on the 5th-generation tensor cores (tcgen05, kind::tf32,
+// Screening pass of the batched omp / mp solves:  C~ = R' A  on the 5th-generation tensor cores (tcgen05, kind::tf32,
 // accumulators in tensor memory), reduced in the epilogue to the SCREEN_T largest |c~| per (signal, atom chunk).
 //
 // Why.  `argmaxinner!` (/root/reference/src/matchingpursuit.jl:181-185) needs the POSITION of max |A'r|, not the
 // N correlations.  The FP64 DMMA pass (corr_gemm_f64.cu) computes all N of them to 53 bits at 35 TFLOP/s; this pass
 // computes them to ~11 bits at tcgen05 rates and hands the update kernel a short list that provably contains the
 // FP64 arg-max: with operands rounded to TF32 (cvt.rna, relative error <= 2^-11 each) and FP32 accumulation,
-//       |c~_j - <a_j, r>|  <=  E = SCREEN_KAPPA * max_j ||a_j|| * ||r||          (Cauchy-Schwarz over the rounding errors)
+//       |c~_j - <a_j, r>|  <=  E = screen_kappa(M) * max_j ||a_j|| * ||r||          (Cauchy-Schwarz over the rounding errors)
 // so every atom whose |c~| lies within 2E of the largest |c~| is a possible arg-max and nothing else is.  The update
 // kernel (update.cu, screen_select) re-evaluates exactly those atoms in FP64 and picks the winner with the reference's
 // tie-break; a list that may be incomplete (its last slot still inside the window, a residual outside the FP32 range)
@@ -262,14 +262,16 @@ __global__ void __launch_bounds__(256) to_tf32_kernel(const T* __restrict__ in, 
 
 }  // namespace
 
-// Atom chunks per signal tile.  A work unit is (128 signals) x (one chunk); MANY SHORT units beat few long ones: with 148
-// units of 32 tiles each (one exact wave) a single SM that is still busy with the previous kernel's tail -- or with another
-// stream's kernel -- delays its unit by a whole pass (measured: the 18 944-signal chunks of the pipelined one-shot path ran
-// 30 % slower than 9 472-signal ones).  So: as many chunks as leave >= SCREEN_MIN_TILES tiles per unit, at most 8.
+// Atom chunks per signal tile; a work unit is (128 signals) x (one chunk).  Two opposing effects, both measured at the
+// headline dictionary (profiles/screen_r02.md): (1) few long units are fastest per pass (2 chunks: 1.53 ms, 4: 1.68, 8: 1.85 ms
+// for 65 536 signals), but (2) a grid of about ONE wave of long units is fragile -- with 148 units of 32 tiles each, one SM
+// still busy with the previous kernel's tail (or another stream's kernel) delays its unit by a whole pass: the 18 944-signal
+// chunks of the pipelined one-shot path ran 30 % slower than 9 472-signal ones.  Rule: the smallest chunk count that gives at
+// least SCREEN_MIN_WAVES waves of units (each still >= 1 tile), else the largest possible.
 int screen_chunks_for(int N, int nsig, int num_sms) {
-    (void)nsig; (void)num_sms;
-    constexpr int SCREEN_MIN_TILES = 4;
+    constexpr int SCREEN_MIN_WAVES = 4;
     const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
+    const long long sig_tiles = (nsig + ST_SIG - 1) / ST_SIG;
     static const int forced = [] { const char* e = getenv("CSB200_SCREEN_CHUNKS"); return e ? atoi(e) : 0; }();
     int best = 1;
     for (int c = 1; c <= SCREEN_MAX_CHUNKS; c *= 2) {
@@ -277,9 +279,15 @@ int screen_chunks_for(int N, int nsig, int num_sms) {
         const int tpc = (tilesN + c - 1) / c;
         if ((tilesN + tpc - 1) / tpc != c) continue;               // a chunk count that would leave an empty chunk
         if (forced == c) return c;
-        if (tpc >= SCREEN_MIN_TILES) best = c;
+        best = c;
+        if (c >= 2 && sig_tiles * c >= (long long)SCREEN_MIN_WAVES * num_sms) break;
     }
     return best;
+}
+
+int screen_chunk_atoms(int N, int chunks) {
+    const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
+    return (tilesN + chunks - 1) / chunks * ST_ATOM;
 }
 
 cudaError_t corr_screen_setup() {

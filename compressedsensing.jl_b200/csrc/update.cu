@@ -81,15 +81,18 @@ __device__ __forceinline__ double warp_dot_col(const T* __restrict__ ai, const d
 // The pass left, per atom chunk, the SCREEN_T largest |c~| of this signal with |c~_j - <a_j, r>| <= E = scr_bound ||r||.
 // Every atom within 2E of the largest |c~| may be the FP64 arg-max, no other atom can: those are re-evaluated exactly
 // (one warp per atom) and the winner is picked with the reference's tie-break.  A single atom in the window needs no
-// arithmetic at all.  If a chunk's last slot is still inside the window its list may be incomplete, and if ||r|| is
-// outside the range FP32 represents safely the bound does not hold: both fall back to an exact scan of all atoms.
+// arithmetic at all.  A chunk whose LAST slot is still inside the window may hold more such atoms than its list shows:
+// all atoms of that chunk are re-evaluated.  If ||r|| is outside the range FP32 represents safely the bound does not
+// hold and every chunk is treated that way (an exact scan of the dictionary).
+// sv: shared staging area for the residual (ld doubles), or nullptr: the dots read r from global memory (T = double only).
 template <typename T, int NT>
 __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__ A, const T* __restrict__ r, double* sv,
                               int* s_cand, double* s_cval, double* red_v, int* red_i) {
     __shared__ int s_list[SCREEN_T * SCREEN_MAX_CHUNKS];
     __shared__ int s_n;
+    __shared__ unsigned s_inc;                                     // bit c: chunk c's list may be incomplete
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nc = a.scr_nc, ld = a.ld;
+    const int nc = a.scr_nc, ld = a.ld, nchunks = nc / SCREEN_T;
     const double nr = a.resnorm[sig];
     float v = -1.0f;
     int idx = -1;
@@ -98,7 +101,7 @@ __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__
     float m = v;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (tid == 0) s_n = 0;
+    if (tid == 0) { s_n = 0; s_inc = 0u; }
     if (lane == 0) red_v[warp] = (double)m;
     __syncthreads();
     double v0 = red_v[0];
@@ -107,11 +110,14 @@ __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__
     const bool range_ok = nr >= SCREEN_NORM_MIN && nr <= SCREEN_NORM_MAX && v0 >= 0.0 && v0 <= 3.0e38;
     const double thr = v0 - 2.0 * a.scr_bound * nr;
     const bool inw = idx >= 0 && (double)v >= thr;
-    const int incomplete = __syncthreads_or(inw && (tid % SCREEN_T) == SCREEN_T - 1) || !range_ok;
-    if (inw && !incomplete) s_list[atomicAdd(&s_n, 1)] = idx;
+    const int chunk = tid / SCREEN_T;
+    if (inw && (tid % SCREEN_T) == SCREEN_T - 1) atomicOr(&s_inc, 1u << chunk);
+    __syncthreads();
+    const unsigned inc = range_ok ? s_inc : (nchunks >= 32 ? 0xffffffffu : ((1u << nchunks) - 1u));
+    if (inw && !((inc >> chunk) & 1u)) s_list[atomicAdd(&s_n, 1)] = idx;
     __syncthreads();
     const int n = s_n;
-    if (!incomplete && n == 1) {
+    if (inc == 0u && n == 1) {
         if (tid == 0) {
             s_cand[0] = s_list[0]; s_cval[0] = v0;
             if (a.scr_stats) atomicAdd(&a.scr_stats[0], 1ULL);
@@ -119,21 +125,28 @@ __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__
         __syncthreads();
         return;
     }
-    for (int row = tid; row < ld; row += NT) sv[row] = (double)r[row];
-    __syncthreads();
+    if (sv) {
+        for (int row = tid; row < ld; row += NT) sv[row] = (double)r[row];
+        __syncthreads();
+    } else {
+        sv = const_cast<double*>(reinterpret_cast<const double*>(r));   // callers pass nullptr only for T = double
+    }
     double bv = -1.0;
     int bi = INT_MAX;
-    if (!incomplete) {
-        for (int c = warp; c < n; c += NT / 32) {
-            const int j = s_list[c];
-            const double d = fabs(warp_dot_col<T>(A + (size_t)(j - a.idx_offset) * ld, sv, ld, lane));
-            if (cand_better(d, j, bv, bi)) { bv = d; bi = j; }
-        }
-    } else {
-        for (int j = warp; j < a.N; j += NT / 32) {
+    for (int c = warp; c < n; c += NT / 32) {
+        const int j = s_list[c];
+        const double d = fabs(warp_dot_col<T>(A + (size_t)(j - a.idx_offset) * ld, sv, ld, lane));
+        if (cand_better(d, j, bv, bi)) { bv = d; bi = j; }
+    }
+    int scanned = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        if (!((inc >> c) & 1u)) continue;
+        const int j0 = c * a.scr_chunk_atoms, j1 = min(a.N, j0 + a.scr_chunk_atoms);
+        for (int j = j0 + warp; j < j1; j += NT / 32) {
             const double d = fabs(warp_dot_col<T>(A + (size_t)j * ld, sv, ld, lane));
             if (cand_better(d, j + a.idx_offset, bv, bi)) { bv = d; bi = j + a.idx_offset; }
         }
+        scanned += j1 - j0;
     }
     __syncthreads();                                               // red_v was read above
     if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
@@ -147,7 +160,8 @@ __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__
         s_cval[0] = bv;
         if (a.scr_stats) {
             atomicAdd(&a.scr_stats[0], 1ULL);
-            if (incomplete) atomicAdd(&a.scr_stats[2], 1ULL); else atomicAdd(&a.scr_stats[1], (unsigned long long)n);
+            atomicAdd(&a.scr_stats[1], (unsigned long long)(n + scanned));
+            if (inc) atomicAdd(&a.scr_stats[2], 1ULL);
         }
     }
     __syncthreads();
@@ -526,14 +540,19 @@ __global__ void __launch_bounds__(UT) mp_update_kernel(StateArgs a, int iter, in
     const int sig = blockIdx.x, tid = threadIdx.x, ld = a.ld;
     const T* A = static_cast<const T*>(a.A);
     T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
-    const size_t cbase = (size_t)sig * a.P * a.S;
-    select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, 1, s_cand, s_cval, red, red_i);
+    if (a.scr_val) {                                                   // TF32-screened candidates, exact FP64 decision
+        screen_select<T, UT>(a, sig, A, r, nullptr, s_cand, s_cval, red, red_i);
+    } else {
+        const size_t cbase = (size_t)sig * a.P * a.S;
+        select_candidates<UT>(a.pval + cbase, a.pidx + cbase, a.P * a.S, 1, s_cand, s_cval, red, red_i);
+    }
     const int j = s_cand[0];
     if (j < 0) {
         if (tid == 0) { a.flags[sig] |= 2; a.sel[(size_t)sig * stride + iter] = -1; a.x[(size_t)sig * stride + iter] = 0.0; }
         return;
     }
     const T* aj = A + (size_t)(j - a.idx_offset) * ld;
+    float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;
     double s = 0.0;
     for (int row = tid; row < ld; row += UT) s += (double)aj[row] * (double)r[row];
     const double c = block_sum<UT>(s, red);                            // dot(view(A,:,i), r)  (:29)
@@ -541,6 +560,7 @@ __global__ void __launch_bounds__(UT) mp_update_kernel(StateArgs a, int iter, in
     for (int row = tid; row < ld; row += UT) {
         const T rr = (T)((double)r[row] - c * (double)aj[row]);
         r[row] = rr;
+        if (r32) r32[row] = tf32_round((float)rr);
         s2 += (double)rr * (double)rr;
     }
     const double nr = sqrt(block_sum<UT>(s2, red));

@@ -11,6 +11,11 @@ pytestmark = pytest.mark.gpu
 RTOL64 = 1e-10
 
 
+def _kappa(M):
+    """screen_kappa(M) of csrc/common.cuh."""
+    return 1.05 * (2.0 ** -10 + 2.0 ** -22 + M * 2.0 ** -22)
+
+
 def _planted(po, rng, A, B, k, noise=0.0):
     M, N = A.shape
     idx = np.stack([rng.choice(N, size=k, replace=False) for _ in range(B)])
@@ -35,7 +40,7 @@ def test_screening_pass_respects_its_bound_and_lists_the_argmax(cs, po, M, N, B)
     nrm = np.linalg.norm(Bm, axis=0)
     nc = val.shape[1]
     chunks = nc // 8
-    assert bound == pytest.approx(1.6e-3 * np.max(np.linalg.norm(A, axis=0)))
+    assert bound == pytest.approx(_kappa(M) * np.max(np.linalg.norm(A, axis=0)))
     worst = 0.0
     for s in range(B):
         E = bound * nrm[s]
@@ -61,6 +66,63 @@ def test_screening_pass_respects_its_bound_and_lists_the_argmax(cs, po, M, N, B)
             assert C[mask, s].max() <= max(val[s, c * 8:(c + 1) * 8].min() for c in range(chunks)) + E + 1e-300
     print(f"screening {M}x{N}: worst |c~ - c| / bound = {worst:.3f}")
     assert worst < 0.5                                           # the Cauchy-Schwarz bound is far from tight on Gaussian data
+
+
+def test_screening_bound_holds_without_cancellation(cs, po):
+    """All-positive operands: every product a_i r_i has the same sign, so sum |a_i r_i| = |c| (the Cauchy-Schwarz step of the
+    bound is tight when r is parallel to an atom) and an accumulator that truncates would lose up to one ulp per add, all in
+    the same direction.  The measured error must still be inside the bound -- this is the case that pins the accumulation
+    term M * 2^-22 of screen_kappa(M)."""
+    rng = np.random.default_rng(2024)
+    M, N, B = 4096, 512, 128
+    A = np.abs(rng.standard_normal((M, N))) + 0.05
+    A /= np.linalg.norm(A, axis=0)
+    A = np.asfortranarray(A)
+    Bm = np.asfortranarray(A[:, rng.integers(0, N, size=B)] * rng.uniform(0.5, 2.0, size=B))   # r parallel to an atom
+    Bm[:, B // 2:] = np.abs(rng.standard_normal((M, B - B // 2))) + 0.05
+    with cs.Dictionary(A) as D, cs.Batch(D, B, 4) as batch:
+        batch.upload(Bm)
+        val, idx, bound = batch.debug_screen_pass()
+    C = np.abs(A.T @ Bm)
+    nrm = np.linalg.norm(Bm, axis=0)
+    worst = 0.0
+    for s in range(B):
+        ok = idx[s] >= 0
+        err = np.abs(val[s][ok] - C[idx[s][ok], s]) / (bound * nrm[s])
+        worst = max(worst, float(err.max()))
+        assert int(np.argmax(C[:, s])) in idx[s][ok].tolist() or (val[s][ok].min() >= val[s][ok].max() - 2 * bound * nrm[s])
+    print(f"all-positive operands, M = {M}: worst |c~ - c| / bound = {worst:.3f}")
+    assert worst < 1.0
+
+
+def test_screened_mp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch):
+    """Plain mp (src/matchingpursuit.jl:26-40) through the screening pass: same atom sequence and coefficient increments as
+    the FP64 DMMA path bit for bit, and the oracle's on a sample."""
+    rng = np.random.default_rng(31)
+    M, N, iters, B = 128, 1024, 12, 4096 + 5
+    A = po.gaussian_dictionary(rng, M, N)
+    Bm, _ = _planted(po, rng, A, B, 6, noise=1e-2)
+    out = {}
+    with cs.Dictionary(A) as D:
+        for mode in ("0", "1"):
+            monkeypatch.setenv("CSB200_SCREEN", mode)
+            with cs.Batch(D, B, iters) as batch:
+                batch.upload(Bm)
+                batch.mp(iters)
+                st = batch.screen_stats(reset=True)
+                assert st["path_id"] == (3 if mode == "1" else 1), st
+                out[mode] = batch.download(iters) + (batch.residual(),)
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b)
+    sel, coef, nnz, res, its, R = out["1"]
+    for s in (0, 17, B - 1):
+        t = po.Trace()
+        ref = po.mp(A, Bm[:, s], iters, trace=t)
+        assert sel[s, :iters].tolist() == t.order()
+        x = np.zeros(N)
+        np.add.at(x, sel[s, :iters], coef[s, :iters])
+        dense = np.zeros(N); dense[ref.nzind] = ref.nzval
+        assert np.allclose(x, dense, rtol=RTOL64, atol=RTOL64)
 
 
 @pytest.mark.parametrize("M,N,k,B,noise", [(256, 2048, 8, 4096 + 37, 0.0), (100, 300, 5, 4096 + 130, 5e-3),
