@@ -184,6 +184,7 @@ struct csb200_batch {
     float* scr_val = nullptr;
     int* scr_idx = nullptr;
     unsigned long long* scr_stats = nullptr;    // device: [0] signal-updates, [1] candidates re-evaluated, [2] exact scans
+    double* def_y = nullptr; double* def_gam = nullptr; int* def_t = nullptr; double* def_s2 = nullptr; int* slow = nullptr;   // deferred residual sweep (StateArgs::def_*)
     int last_path = 0;                          // 0 other, 1 DMMA loop, 2 DMMA two-half overlap, 3 TF32 screening + exact re-evaluation
     cudaStream_t stream = nullptr;
     bool profile = false;
@@ -228,6 +229,7 @@ void free_batch_mem(csb200_batch* b) {
     cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->stage32); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2); cudaFree(b->ndone);
     cudaFree(b->persist_scratch);
     cudaFree(b->dR32); cudaFree(b->scr_val); cudaFree(b->scr_idx); cudaFree(b->scr_stats);
+    cudaFree(b->def_y); cudaFree(b->def_gam); cudaFree(b->def_t); cudaFree(b->def_s2); cudaFree(b->slow);
     if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
@@ -273,6 +275,8 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
     a.resnorm = b->resnorm; a.iters = b->iters; a.done = b->done; a.flags = b->flags;
     a.gram = b->use_gram ? d->gram : nullptr;
     a.dense_ld = b->cur_dense_ld;
+    static const int hints = [] { const char* e = getenv("CSB200_UPD_HINTS"); return e ? atoi(e) : UPD_HINTS_DEFAULT; }();
+    a.upd_hints = hints;
     return a;
 }
 
@@ -816,6 +820,25 @@ int ensure_screen_batch(csb200_batch* b) {
     return CSB200_OK;
 }
 
+// Row slots per slice launch of the deferred residual sweep (0 = the update kernel down-dates r itself)
+int upd_defer_kper() {
+    static const int v = [] { const char* e = getenv("CSB200_UPD_DEFER"); const int k = e ? atoi(e) : UPD_DEFER_DEFAULT; return k < 0 ? 0 : k; }();
+    return v;
+}
+// Buffers of the deferred sweep; 1 when they cannot be had (the update then runs undeferred)
+int ensure_defer_batch(csb200_batch* b) {
+    if (b->def_y) return 0;
+    double* y = nullptr; double* g = nullptr; int* t = nullptr; double* s2 = nullptr; int* sl = nullptr;
+    if (cudaMalloc(&sl, (size_t)b->cap_sig * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&y, (size_t)b->cap_sig * b->kcap * sizeof(double)) != cudaSuccess || cudaMalloc(&g, (size_t)b->cap_sig * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&t, (size_t)b->cap_sig * sizeof(int)) != cudaSuccess || cudaMalloc(&s2, (size_t)b->cap_sig * 128 * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(y); cudaFree(g); cudaFree(t); cudaFree(s2); cudaFree(sl);
+        return 1;
+    }
+    b->def_y = y; b->def_gam = g; b->def_t = t; b->def_s2 = s2; b->slow = sl;
+    return 0;
+}
+
 // returns 1 when the screening path cannot be set up (the caller then takes the DMMA path)
 //
 // Schedule.  Serial (the default): pass, update, pass, update ... on the batch's stream.  Overlapped (CSB200_SCREEN_PARTS =
@@ -850,6 +873,7 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
     }
     const int chunks = screen_chunks_for((int)d->N, (int)count[0], d->num_sms);
     const int nc = chunks * SCREEN_T;
+    const int defer = upd_defer_kper() > 0 && ensure_defer_batch(b) == 0 ? upd_defer_kper() : 0;
     CUtensorMap mapR32[4];
     for (int h = 0; h < NP; ++h)
         if ((rc = make_operand_map32(&mapR32[h], b->dR32 + (size_t)start[h] * d->ld32, d->ld32, count[h], 128))) return rc;
@@ -859,6 +883,12 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
         ua.scr_chunk_atoms = screen_chunk_atoms((int)d->N, chunks);
         ua.scr_bound = screen_kappa((int)d->M) * d->amax;
         ua.R32 = b->dR32 + (size_t)start[h] * d->ld32; ua.ld32 = (int)d->ld32; ua.scr_stats = b->scr_stats;
+        if (defer) {
+            ua.def_y = b->def_y + (size_t)start[h] * b->kcap; ua.def_gam = b->def_gam + start[h]; ua.def_t = b->def_t + start[h];
+            ua.def_s2 = b->def_s2 + (size_t)start[h] * 128; ua.def_kper = defer;
+            static const int warp_env = [] { const char* e = getenv("CSB200_UPD_WARP"); return e ? atoi(e) : UPD_WARP_DEFAULT; }();
+            if (warp_env > 0 && ua.gram && b->kcap <= 32 && d->n_offset == 0) ua.slow = b->slow + start[h];
+        }
         return ua;
     };
     auto pass = [&](int h, cudaStream_t st) -> int {

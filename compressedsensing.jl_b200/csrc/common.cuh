@@ -20,6 +20,15 @@ constexpr int ROW_ALIGN = 16;      // leading dimensions are padded to 16 elemen
 // exact products adds at most M * 2^-22 of sum |a_i r_i| even if every add TRUNCATES (one ulp each); 5 % margin on top.
 // M = 1024: 1.28e-3; M = 4096: 2.05e-3.  tests/test_gpu_screen.py measures the actual error (Gaussian data: < 0.1 of the
 // bound; all-positive operands, where truncation would add up: see the test) against it.
+// omp_update_kernel experiments (round 2): defaults of CSB200_UPD_RING (cp.async column ring depth, 0 = register path) and
+// CSB200_UPD_HINTS (bit 0 streaming b / r / r32, bit 1 L2 evict_last on the dictionary gathers)
+constexpr int UPD_RING_DEFAULT = 0;
+constexpr int UPD_HINTS_DEFAULT = 0;
+// CSB200_UPD_DEFER: 0 = omp_update_kernel down-dates r itself; k = 1, 2, 4: the residual sweep of the screened omp loop runs as
+// separate launches over slices of k * 256 rows of ALL signals (dictionary rows of one slice stay in the L2)
+constexpr int UPD_DEFER_DEFAULT = 0;
+// CSB200_UPD_WARP=1 (needs the deferred sweep, a Gram matrix and k <= 32): selection + append by one warp per signal
+constexpr int UPD_WARP_DEFAULT = 0;
 constexpr int SCREEN_T = 8;
 constexpr int SCREEN_MAX_CHUNKS = 16;
 constexpr int SCREEN_MAX_ROWS = 8192;
@@ -109,6 +118,16 @@ struct StateArgs {
     int dense_ld = 0;           // > 0: pval is the dense |A'r| matrix [nsig][dense_ld] (no pidx); 0: per-block candidates
     double max_eps = 0.0;       // forward_step! returns false unless ||r|| > max_eps   (:60)
     double min_delta2 = 0.0;    // ... and unless min_delta^2 < max_j delta2_j          (:63)
+    // Deferred, row-sliced residual sweep of the screened omp loop (update.cu, omp_residual_slice_kernel): omp_update_kernel
+    // leaves y = R^{-1}Q'a_j, gamma = z_t / rho and the old support size here instead of down-dating r itself
+    double* def_y = nullptr;    // [nsig][kcap]
+    double* def_gam = nullptr;  // [nsig]
+    int* def_t = nullptr;       // [nsig] active columns to combine (support size before the append); -1 = nothing deferred
+    int* slow = nullptr;        // [nsig] warp-per-signal append (omp_append_warp_kernel): 1 = left to omp_update_kernel; nullptr = warp path off
+    int def_kper = 1;           // row slots of 256 rows per slice launch
+    double* def_s2 = nullptr;   // [nsig][128] per-thread running sum of squares of the new residual, carried from slice to slice
+    int upd_hints = 0;          // omp_update_kernel cache hints: bit 0 streaming loads / stores of b, r, r32; bit 1 L2 evict_last on
+                                // the dictionary gathers of the cp.async ring
     int grid_cap = 0;           // > 0: omp_update_kernel runs with at most this many CTAs, each walking several signals
     int max_smem_carveout = 0;  // launch hint: ask for the SM's largest shared-memory carve-out, i.e. the configuration the
                                 // DMMA correlation kernel runs under, so that CTAs of both kernels can share an SM

@@ -169,8 +169,12 @@ __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__
 
 // NT = 128 threads, 8 CTAs/SM for one atom per update (omp); NT = 256 with the block-append working set
 // (BLOCK: up to `bm` new atoms orthogonalised together, update_common.cuh append_block) for gomp.
-template <typename T, int NT, bool BLOCK>
+// RING_D > 0: the residual sweep of append_atom reads the active columns through a cp.async ring of RING_D columns in shared
+// memory (update_common.cuh); FP64, one atom per update, ld <= RING_MAX_SLOTS * NT * 2.  Fewer CTAs fit on an SM (the ring
+// is RING_D * ld * 8 bytes) but each keeps RING_D whole columns in flight without spending registers on them.
+template <typename T, int NT, bool BLOCK, int RING_D = 0>
 __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __restrict__ Acache, int t_in_smem, int bm, const int sig) {
+    static_assert(RING_D == 0 || (!BLOCK && sizeof(T) == 8), "the cp.async ring serves the FP64 one-atom update only");
     extern __shared__ double dsm[];
     const int ld = a.ld, kcap = a.kcap;
     PursuitSmem<T> S;
@@ -193,6 +197,17 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
     S.ssel = reinterpret_cast<int*>(p);
     S.colp = reinterpret_cast<const T**>(S.ssel + ((kcap + 1) & ~1));
     double* Tsm = reinterpret_cast<double*>(S.colp + kcap);        // [kcap][ldT] inverse factor (optional)
+    if constexpr (RING_D > 0) {
+        double* after = Tsm + (t_in_smem ? (size_t)kcap * (kcap | 1) : 0);
+        S.ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(after) + 15) & ~(uintptr_t)15);
+    }
+    if (a.upd_hints & 2) S.l2_keep = l2_evict_last_policy();
+    S.ring_r = static_cast<const T*>(a.R) + (size_t)sig * a.ld;
+    if constexpr (!BLOCK && sizeof(T) == 8) {
+        if (a.def_y && !a.resc) {
+            S.def_y = a.def_y + (size_t)sig * kcap; S.def_gam = a.def_gam + sig; S.def_t = a.def_t + sig;
+        }
+    }
     __shared__ double red[2 * (NT / 32) + 2];
     __shared__ int red_i[NT / 32];
     __shared__ int s_cand[MAX_TAKE];
@@ -201,6 +216,8 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
     __shared__ const T* s_Jcol[BLOCK_MAX];
 
     const int tid = threadIdx.x;
+    if (a.slow && !a.slow[sig]) return;                            // omp_append_warp_kernel has done this signal's update
+    if (a.def_t && tid == 0) a.def_t[sig] = -1;                    // nothing deferred yet
     if (a.done[sig] && !a.ignore_done) return;                     // the reference `break`s (:79,:132)
     // forward regression (`forward_step!`, src/forward.jl:56-67): same append / solve tail as omp, different
     // acquisition (candidates carry delta2 = <a,r>^2 / rescaling) and stopping rules
@@ -225,10 +242,16 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
     int flags = 0;
     bool changed = false;
     double nr2 = 0.0;
-    auto b_at = [&](int row) { return (double)b[row]; };
-    auto r_at = [&](int row) { return (double)r[row]; };
+    // upd_hints bit 0: signal, residual and its TF32 copy are touched once per update -> streaming loads / stores, so that
+    // they do not push the dictionary (gathered t columns per signal) out of the L2
+    const bool stream = a.upd_hints & 1;
+    auto b_at = [&](int row) { return (double)(stream ? __ldcs(b + row) : b[row]); };
+    auto r_at = [&](int row) { return (double)(stream ? __ldcs(r + row) : r[row]); };
     float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;   // TF32 copy read by the screening pass
-    auto r_set = [&](int row, T val) { r[row] = val; if (r32) r32[row] = tf32_round((float)val); };
+    auto r_set = [&](int row, T val) {
+        if (stream) { __stcs(r + row, val); if (r32) __stcs(r32 + row, tf32_round((float)val)); }
+        else { r[row] = val; if (r32) r32[row] = tf32_round((float)val); }
+    };
 
     for (int i = tid; i < t; i += NT) {
         const int si = a.sel[(size_t)sig * kcap + i];
@@ -296,7 +319,7 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
                 if (__syncthreads_or(in)) continue;                // already active: nothing to add (:66, util.jl:119)
                 if (t >= kcap || t >= a.M) break;                  // capacity of UpdatableQR(T, n, k)
                 const T* aj = Acache ? Acache + (size_t)t * ld : A + (size_t)(j - a.idx_offset) * ld;
-                const int dep = append_atom<T, NT>(
+                const int dep = append_atom<T, NT, RING_D>(
                     S, t, j, aj, ld, b_at, r_at, r_set, nr2,
                     (a.gram && !Acache) ? a.gram + (size_t)(j - a.idx_offset) * a.N : nullptr, a.idx_offset);
                 if (dep) flags |= 1; else changed = true;
@@ -337,6 +360,280 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
         a.resnorm[sig] = nr;
         a.iters[sig] += 1;
         if (flags) a.flags[sig] |= flags;
+        if (!S.deferred) {                                         // else: the last slice of the residual sweep does both
+            a.resnorm[sig] = nr;
+            if (!(nr >= a.eps)) a.done[sig] = 1;                   // `norm(residual!(P, x)) >= eps || break`
+        }
+    }
+}
+
+// Selection + append of the screened omp loop with ONE WARP PER SIGNAL (FP64 dictionary with Gram matrix, one atom per
+// update, kcap <= 32, deferred residual sweep).  The CTA-per-signal body above spends its time in a chain of ~15
+// barrier-separated phases and 6-7 dependent global round trips with 8 signals per SM in flight (ncu: 1.1 ms per launch
+// for 65 536 signals, independent of the support size, against ~0.25 ms of HBM traffic).  Here a signal is one warp: lane i
+// owns support slot i, the block reductions become shuffles, nothing waits on a CTA barrier, and 20 signals per SM are in
+// flight.  The arithmetic is the CTA path's, operation for operation -- each lane plays threads lane, lane + 32, lane + 64,
+// lane + 96 of the 128-thread block in the two M-length sums, and the triangular mat-vecs are per-slot dot products
+// anyway -- so every result is bit-identical.  Anything off the common path (exact scan, no candidate, Pythagoras test
+// failed -> DGKS, dependent or ill-conditioned atom) is left untouched and flagged in a.slow[sig]: omp_update_kernel, launched
+// right after, handles exactly those signals.
+constexpr int WPB = 4;                                             // warps (signals) per CTA
+constexpr int WK = 32;                                             // largest support capacity of the warp path
+constexpr int W_LDT = WK | 1;
+struct WarpSmem {
+    double T[WK * W_LDT];
+    double g[WK], hh[WK], zs[WK];
+    int list[SCREEN_T * SCREEN_MAX_CHUNKS];
+};
+__global__ void __launch_bounds__(WPB * 32, 5)
+omp_append_warp_kernel(StateArgs a) {
+    extern __shared__ double dsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sig = blockIdx.x * WPB + warp;
+    if (sig >= a.nsig) return;
+    WarpSmem& W = reinterpret_cast<WarpSmem*>(dsm)[warp];
+    const int ld = a.ld, kcap = a.kcap;
+    const unsigned FULL = 0xffffffffu;
+    // ---- state and candidates: independent loads, issued together
+    const int done = a.done[sig];
+    int t = a.nnz[sig];
+    const double nr = a.resnorm[sig];
+    const int oldflags = a.flags[sig];
+    if (lane == 0) { a.def_t[sig] = -1; a.slow[sig] = 0; }
+    if (done && !a.ignore_done) return;                            // the reference `break`s (:79)
+    auto leave_to_cta = [&]() { if (lane == 0) a.slow[sig] = 1; };
+    if (oldflags & FLAG_ILLCOND) { leave_to_cta(); return; }       // coefficients of this support are refined on every update
+    const double* A = static_cast<const double*>(a.A);
+    const double* b = static_cast<const double*>(a.B) + (size_t)sig * ld;
+    const double* r = static_cast<const double*>(a.R) + (size_t)sig * ld;
+    double* Tg = a.Rf + (size_t)sig * kcap * kcap;
+    int ssel = -1;
+    double zsl = 0.0;
+    if (lane < t) { ssel = a.sel[(size_t)sig * kcap + lane]; zsl = a.z[(size_t)sig * kcap + lane]; }
+    for (int c = 0; c < t; ++c)
+        if (lane <= c) W.T[lane + c * W_LDT] = Tg[lane + (size_t)c * kcap];
+    W.zs[lane] = zsl;
+    bool changed = false;
+    int stat_n = -1;                                               // atoms re-evaluated in FP64 (-1: no selection ran)
+    if (t < a.M) {                                                 // `nnz(x) < size(P.A, 1) || return x` (:63)
+        // ---- screen_select by one warp
+        const int nc = a.scr_nc;
+        float v[SCREEN_T * SCREEN_MAX_CHUNKS / 32];
+        int idx[SCREEN_T * SCREEN_MAX_CHUNKS / 32];
+        float m = -1.0f;
+#pragma unroll
+        for (int q = 0; q < SCREEN_T * SCREEN_MAX_CHUNKS / 32; ++q) {
+            const int e = lane + 32 * q;
+            v[q] = -1.0f; idx[q] = -1;
+            if (e < nc) { v[q] = a.scr_val[(size_t)sig * nc + e]; idx[q] = a.scr_idx[(size_t)sig * nc + e]; }
+            if (idx[q] < 0 || !(v[q] >= 0.0f)) { v[q] = -1.0f; idx[q] = -1; }
+            m = fmaxf(m, v[q]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, off));
+        const double v0 = (double)m;
+        const bool range_ok = nr >= SCREEN_NORM_MIN && nr <= SCREEN_NORM_MAX && v0 >= 0.0 && v0 <= 3.0e38;
+        const double thr = v0 - 2.0 * a.scr_bound * nr;
+        unsigned inc = 0u;
+        bool inw[SCREEN_T * SCREEN_MAX_CHUNKS / 32];
+#pragma unroll
+        for (int q = 0; q < SCREEN_T * SCREEN_MAX_CHUNKS / 32; ++q) {
+            const int e = lane + 32 * q;
+            inw[q] = idx[q] >= 0 && (double)v[q] >= thr;
+            if (inw[q] && (e % SCREEN_T) == SCREEN_T - 1) inc |= 1u << (e / SCREEN_T);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) inc |= __shfl_xor_sync(FULL, inc, off);
+        if (!range_ok || inc != 0u) { leave_to_cta(); return; }    // exact scan of whole chunks: the CTA path
+        int n = 0;
+#pragma unroll
+        for (int q = 0; q < SCREEN_T * SCREEN_MAX_CHUNKS / 32; ++q) {
+            const unsigned bal = __ballot_sync(FULL, inw[q]);
+            if (inw[q]) W.list[n + __popc(bal & ((1u << lane) - 1u))] = idx[q];
+            n += __popc(bal);
+        }
+        __syncwarp();
+        if (n == 0) { leave_to_cta(); return; }
+        int j;
+        if (n == 1) {
+            j = W.list[0];
+        } else {
+            double bv = -1.0;
+            int bi = INT_MAX;
+            for (int c = 0; c < n; ++c) {
+                const int jc = W.list[c];
+                const double d = fabs(warp_dot_col<double>(A + (size_t)(jc - a.idx_offset) * ld, r, ld, lane));
+                if (cand_better(d, jc, bv, bi)) { bv = d; bi = jc; }
+            }
+            j = bi;
+        }
+        stat_n = n == 1 ? 0 : n;
+        const bool in = __any_sync(FULL, lane < t && ssel == j);   // already active: nothing to add (:66, util.jl:119)
+        if (!in && t < kcap && t < a.M) {
+            // ---- append_atom, fast path
+            const double* aj = A + (size_t)(j - a.idx_offset) * ld;
+            double s2[4] = {0.0, 0.0, 0.0, 0.0}, sab[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int row0 = 0; row0 < ld; row0 += 128) {           // lane plays threads lane + 32 w of the 128-thread block
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int row = row0 + lane + 32 * w;
+                    if (row < ld) {
+                        const double e = aj[row];
+                        s2[w] = fma(e, e, s2[w]); sab[w] = fma(e, b[row], sab[w]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    s2[w] += __shfl_xor_sync(FULL, s2[w], off);
+                    sab[w] += __shfl_xor_sync(FULL, sab[w], off);
+                }
+            s2[0] += s2[2]; sab[0] += sab[2]; s2[1] += s2[3]; sab[1] += sab[3];
+            const double anorm2 = s2[0] + s2[1], ab = sab[0] + sab[1];
+            double rho2 = anorm2, yl = 0.0, qsum = 0.0;
+            if (t > 0) {
+                W.g[lane] = lane < t ? a.gram[(size_t)(j - a.idx_offset) * a.N + (ssel - a.idx_offset)] : 0.0;   // g = (A'A)[S, j]
+                __syncwarp();
+                double hl = 0.0;
+                if (lane < t) {                                    // hh = R^{-T} g
+                    double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+                    const double* col = W.T + lane * W_LDT;
+                    int l = 0;
+                    for (; l + 3 <= lane; l += 4) {
+                        h0 = fma(col[l], W.g[l], h0); h1 = fma(col[l + 1], W.g[l + 1], h1);
+                        h2 = fma(col[l + 2], W.g[l + 2], h2); h3 = fma(col[l + 3], W.g[l + 3], h3);
+                    }
+                    for (; l <= lane; ++l) h0 = fma(col[l], W.g[l], h0);
+                    hl = (h0 + h1) + (h2 + h3);
+                }
+                W.hh[lane] = hl;
+                __syncwarp();
+                if (lane < t) {                                    // y = R^{-1} hh
+                    double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+                    const double* rowp = W.T + lane;
+                    int l = lane;
+                    for (; l + 3 < t; l += 4) {
+                        h0 = fma(rowp[l * W_LDT], W.hh[l], h0); h1 = fma(rowp[(l + 1) * W_LDT], W.hh[l + 1], h1);
+                        h2 = fma(rowp[(l + 2) * W_LDT], W.hh[l + 2], h2); h3 = fma(rowp[(l + 3) * W_LDT], W.hh[l + 3], h3);
+                    }
+                    for (; l < t; ++l) h0 = fma(rowp[l * W_LDT], W.hh[l], h0);
+                    yl = (h0 + h1) + (h2 + h3);
+                }
+                double p = 0.0, q = 0.0;                           // ||Q'a||^2 and <Q'a, Q'b>
+                if (lane < t) { p = fma(hl, hl, p); q = fma(hl, zsl, q); }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    p += __shfl_xor_sync(FULL, p, off);
+                    q += __shfl_xor_sync(FULL, q, off);
+                }
+                if (!(anorm2 - p >= 0.5 * anorm2)) { leave_to_cta(); return; }   // re-orthogonalisation needed: the CTA path
+                rho2 = anorm2 - p;
+                qsum = q;
+            }
+            if (!(rho2 > 1e-26 * anorm2) || rho2 < ILLCOND_RATIO * anorm2) { leave_to_cta(); return; }
+            const double rho = sqrt(rho2);
+            const double zt = (t > 0 ? ab - qsum : ab) / rho;
+            const double gam = zt / rho;
+            if (lane < t) a.def_y[(size_t)sig * kcap + lane] = yl;
+            if (lane == 0) { a.def_gam[sig] = gam; a.def_t[sig] = t; }
+            const double irho = 1.0 / rho;
+            if (lane < t) {
+                const double e = -yl * irho;
+                Tg[lane + (size_t)t * kcap] = e;
+                W.T[lane + t * W_LDT] = e;
+            }
+            if (lane == t) { Tg[t + (size_t)t * kcap] = irho; W.T[t + t * W_LDT] = irho; W.zs[t] = zt; ssel = j; zsl = zt; }
+            ++t;
+            changed = true;
+            __syncwarp();
+        }
+    }
+    if (changed) {
+        if (lane < t) {                                            // x_S = R^{-1} Q'b  (`ldiv!`, :175)
+            double acc = 0.0;
+            for (int l = lane; l < t; ++l) acc = fma(W.T[lane + l * W_LDT], W.zs[l], acc);
+            a.sel[(size_t)sig * kcap + lane] = ssel;
+            a.z[(size_t)sig * kcap + lane] = zsl;
+            a.x[(size_t)sig * kcap + lane] = acc;
+        }
+    }
+    if (lane == 0) {
+        a.nnz[sig] = t;
+        a.iters[sig] += 1;
+        if (!changed && !(nr >= a.eps)) a.done[sig] = 1;           // unchanged residual: `norm(residual!(P, x)) >= eps || break`
+        if (a.scr_stats && stat_n >= 0) {                          // counted here: a signal left to the CTA path is counted there
+            atomicAdd(&a.scr_stats[0], 1ULL);
+            if (stat_n) atomicAdd(&a.scr_stats[1], (unsigned long long)stat_n);
+        }
+    }
+}
+
+// Deferred residual sweep of the screened omp loop:  r <- r - gamma (a_j - A_S y)  for row slots [k0, k1) of every signal
+// (slot k = rows [256 k, 256 k + 256): thread tid owns rows 2 tid + 256 k and the next, exactly the assignment of
+// append_atom's own sweep, and the per-row FMA chains -- even columns, odd columns -- and the per-thread sum of squares
+// are continued in the same order, so r, r32 and ||r|| are bit-identical to the undeferred update).
+// Why: one update! gathers t columns of 8 KiB per signal; with every signal walking whole columns the 64 MiB FP64
+// dictionary does not stay in the (two-die) L2 -- ncu: 57 % hit rate, 3 GB of dictionary re-read from DRAM per launch.
+// Launched per slice over ALL signals, the live part of the dictionary is 256 rows x N x 8 B (16 MiB at config 2).
+template <int NT>
+__global__ void __launch_bounds__(NT, 8)
+omp_residual_slice_kernel(StateArgs a, int k0, int k1, int last) {
+    extern __shared__ double dsm[];
+    __shared__ double red[NT / 32];
+    const int sig = blockIdx.x, tid = threadIdx.x;
+    const int t = a.def_t[sig];
+    if (t < 0) return;
+    const int ld = a.ld, kcap = a.kcap;
+    double* sy = dsm;                                              // [kcap]
+    const double** scol = reinterpret_cast<const double**>(sy + kcap);
+    const double* A = static_cast<const double*>(a.A);
+    for (int i = tid; i < t; i += NT) {
+        sy[i] = a.def_y[(size_t)sig * kcap + i];
+        scol[i] = A + (size_t)(a.sel[(size_t)sig * kcap + i] - a.idx_offset) * ld;
+    }
+    const double* aj = A + (size_t)(a.sel[(size_t)sig * kcap + t] - a.idx_offset) * ld;
+    const double gam = a.def_gam[sig];
+    double* r = static_cast<double*>(a.R) + (size_t)sig * ld;
+    float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;
+    double s2r = k0 == 0 ? 0.0 : a.def_s2[(size_t)sig * NT + tid];
+    __syncthreads();
+    for (int k = k0; k < k1; ++k) {
+        const int row = tid * 2 + k * NT * 2;
+        if (row < ld) {
+            const double2 rv = __ldcs(reinterpret_cast<const double2*>(r + row));
+            const double2 av = *reinterpret_cast<const double2*>(aj + row);
+            double acc[2] = {av.x, av.y}, acc1[2] = {0.0, 0.0};
+            int i = 0;
+#pragma unroll 4
+            for (; i + 1 < t; i += 2) {                            // two chains per row, as in append_atom
+                const double2 a0 = *reinterpret_cast<const double2*>(scol[i] + row);
+                const double2 a1 = *reinterpret_cast<const double2*>(scol[i + 1] + row);
+                const double y0 = sy[i], y1 = sy[i + 1];
+                acc[0] = fma(-a0.x, y0, acc[0]); acc[1] = fma(-a0.y, y0, acc[1]);
+                acc1[0] = fma(-a1.x, y1, acc1[0]); acc1[1] = fma(-a1.y, y1, acc1[1]);
+            }
+            if (i < t) {
+                const double2 a0 = *reinterpret_cast<const double2*>(scol[i] + row);
+                const double y0 = sy[i];
+                acc[0] = fma(-a0.x, y0, acc[0]); acc[1] = fma(-a0.y, y0, acc[1]);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double vq = acc[e] + acc1[e];
+                const double rr = (e ? rv.y : rv.x) - gam * vq;
+                __stcs(r + row + e, rr);
+                if (r32) __stcs(r32 + row + e, tf32_round((float)rr));
+                s2r = fma(rr, rr, s2r);
+            }
+        }
+    }
+    if (!last) { a.def_s2[(size_t)sig * NT + tid] = s2r; return; }
+    const double nr2 = block_sum<NT>(s2r, red);
+    if (tid == 0) {
+        const double nr = sqrt(nr2);
+        a.resnorm[sig] = nr;
         if (!(nr >= a.eps)) a.done[sig] = 1;                       // `norm(residual!(P, x)) >= eps || break`
     }
 }
@@ -351,6 +648,17 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     for (int sig = blockIdx.x; sig < a.nsig; sig += gridDim.x) {
         omp_update_body<T, NT, BLOCK>(a, Acache, t_in_smem, bm, sig);
         if (sig + (int)gridDim.x < a.nsig) __syncthreads();        // the shared-memory state is rebuilt per signal
+    }
+}
+
+// The same update with the cp.async column ring (FP64 dictionary, one atom per update).  MINB CTAs per SM is what the ring
+// leaves room for: 4 columns of 8 KiB + 22 KiB of state -> 4 CTAs, with 128 registers per thread available.
+template <int NT, int RING_D, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+omp_update_ring_kernel(StateArgs a, int t_in_smem) {
+    for (int sig = blockIdx.x; sig < a.nsig; sig += gridDim.x) {
+        omp_update_body<double, NT, false, RING_D>(a, nullptr, t_in_smem, 0, sig);
+        if (sig + (int)gridDim.x < a.nsig) __syncthreads();
     }
 }
 
@@ -715,6 +1023,24 @@ cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void*
         if (e != cudaSuccess) return e;
         omp_update_kernel<T, 256, true><<<a.nsig, 256, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, bm);
     } else {
+        // cp.async column ring (CSB200_UPD_RING = depth 3 / 4 / 6, 0 = off): FP64, one atom per update, short signals
+        static const int ring_env = [] { const char* r = getenv("CSB200_UPD_RING"); return r ? atoi(r) : UPD_RING_DEFAULT; }();
+        if constexpr (sizeof(T) == 8) {
+            if (ring_env > 0 && !Acache && a.ld <= RING_MAX_SLOTS * UT * 2 && a.grid_cap == 0) {
+                const int depth = ring_env >= 6 ? 6 : (ring_env >= 4 ? 4 : 3);
+                const size_t rsmem = smem + (size_t)depth * a.ld * sizeof(double) + 16;
+                auto go = [&](auto kern) -> cudaError_t {
+                    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+                    if (e2 != cudaSuccess) return e2;
+                    e2 = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+                    if (e2 != cudaSuccess) return e2;
+                    kern<<<a.nsig, UT, rsmem, st>>>(a, t_in_smem);
+                    return cudaGetLastError();
+                };
+                return depth == 6 ? go(omp_update_ring_kernel<UT, 6, 3>) : depth == 4 ? go(omp_update_ring_kernel<UT, 4, 4>)
+                                                                                      : go(omp_update_ring_kernel<UT, 3, 4>);
+            }
+        }
         e = cudaFuncSetAttribute(omp_update_kernel<T, UT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         // An SM runs CTAs of two kernels side by side only under ONE shared-memory / L1 split: when this kernel is to run
@@ -723,7 +1049,31 @@ cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void*
                                  a.max_smem_carveout ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
         if (e != cudaSuccess) return e;
         const int grid = a.grid_cap > 0 && a.grid_cap < a.nsig ? a.grid_cap : a.nsig;
+        if constexpr (sizeof(T) == 8) {
+            if (a.slow) {                                          // warp-per-signal selection + append first; the CTA kernel takes the rest
+                e = cudaFuncSetAttribute(omp_append_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WPB * sizeof(WarpSmem)));
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(omp_append_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+                if (e != cudaSuccess) return e;
+                omp_append_warp_kernel<<<(a.nsig + WPB - 1) / WPB, WPB * 32, WPB * sizeof(WarpSmem), st>>>(a);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+            }
+        }
         omp_update_kernel<T, UT, false><<<grid, UT, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, 0);
+        if constexpr (sizeof(T) == 8) {
+            if (a.def_y && !a.resc) {                              // the residual sweep, slice by slice over all signals
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+                const int slots = (a.ld + 2 * UT - 1) / (2 * UT);
+                const int kper = a.def_kper > 0 ? a.def_kper : 1;
+                const size_t ssm = (size_t)a.kcap * (sizeof(double) + sizeof(void*));
+                for (int k0 = 0; k0 < slots; k0 += kper) {
+                    const int k1 = k0 + kper < slots ? k0 + kper : slots;
+                    omp_residual_slice_kernel<UT><<<a.nsig, UT, ssm, st>>>(a, k0, k1, k1 == slots ? 1 : 0);
+                }
+            }
+        }
     }
     return cudaGetLastError();
 }

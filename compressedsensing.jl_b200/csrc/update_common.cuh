@@ -350,7 +350,30 @@ struct PursuitSmem {
     int kcap;
     double* red;      // [2 * NT/32] reduction scratch (+ 2 doubles for the one-warp sums of append_atom)
     int illcond = 0;  // set by append_atom when an atom kept less than ILLCOND_RATIO of its squared norm (CTA-uniform)
+    double* def_y = nullptr;          // deferred residual sweep (StateArgs::def_*): this signal's slots, nullptr = down-date r here
+    double* def_gam = nullptr;
+    int* def_t = nullptr;
+    bool deferred = false;            // set by append_atom when it left the residual sweep to omp_residual_slice_kernel (CTA-uniform)
+    const void* ring_r = nullptr;     // the signal's residual in global memory: rides through the ring behind the last column
+    double* ring = nullptr;           // [RING_D][ld] per-thread cp.async ring of active columns (append_atom<.., RING_D>), 16-byte aligned
+    unsigned long long l2_keep = 0;   // createpolicy L2::evict_last handle for the dictionary gathers, 0 = no hint
 };
+
+// 16-byte asynchronous copies global -> shared (LDGSTS, L1 bypassed).  Every thread copies and later reads ITS OWN rows, so
+// cp.async.wait_group is the only synchronisation the ring needs; bytes in flight cost shared memory instead of registers.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, unsigned long long pol) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst_smem));
+    if (pol) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "l"(pol) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+constexpr int RING_MAX_SLOTS = 4;     // row slots per thread of the ring path: ld <= RING_MAX_SLOTS * NT * 2
 
 // x = R^{-1} z through the STORED INVERSE has a forward error of about cond(A_S)^2 eps (x is O(1) while ||R^{-1}|| ||z|| is
 // O(cond): the products cancel), where the reference's back substitution on a Givens QR gives cond(A_S) eps.  Measured
@@ -422,12 +445,31 @@ __device__ void refine_coefficients(PursuitSmem<T>& S, int t, int ld, BAt b_at, 
 // Returns 0 when the atom was appended (t is incremented, nr2 = ||r||^2), 1 when it is numerically dependent.
 // gcol (optional): column j of the precomputed Gram matrix A'A indexed by LOCAL atom index; when given, the first
 // sweep takes g = A_S'a_j from it (t scattered 8-byte loads) instead of gathering the t active atoms.
-template <typename T, int NT, typename BAt, typename RAt, typename RSet>
+// RING_D > 0 (FP64 dictionaries, ld <= RING_MAX_SLOTS * NT * 2, S.ring set): the residual sweep of the fast path takes the
+// active columns through a RING_D-deep cp.async ring -- the first RING_D columns are requested before anything else, so
+// their latency hides behind the Gram look-up and the triangular mat-vecs -- with the same per-row FMA chains (even
+// columns / odd columns) as the register path: results are bit-identical.
+template <typename T, int NT, int RING_D = 0, typename BAt, typename RAt, typename RSet>
 __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, const T* __restrict__ aj, int ld,
                                            BAt b_at, RAt r_at, RSet r_set, double& nr2,
                                            const double* __restrict__ gcol = nullptr, int idx_offset = 0) {
     constexpr int W = RowVec<T>::W;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    [[maybe_unused]] auto ring_issue = [&](int i) {                // request column i (if there is one) and close its group
+        if constexpr (RING_D > 0) {
+            if (i <= t) {                                          // pseudo-column t is the residual itself
+                const T* col = i < t ? S.colp[i] : static_cast<const T*>(S.ring_r);
+                double* dst = S.ring + (size_t)(i % RING_D) * ld;
+                const unsigned long long pol = i < t ? S.l2_keep : 0ULL;
+                for (int row = tid * 2; row < ld; row += NT * 2) cp_async16(dst + row, col + row, pol);
+            }
+            cp_async_commit();
+        }
+    };
+    if constexpr (RING_D > 0) {
+#pragma unroll
+        for (int i = 0; i < RING_D; ++i) ring_issue(i);
+    }
     double s2 = 0.0, sab = 0.0;
     for (int row = tid; row < ld; row += NT) {
         const double e = (double)aj[row];
@@ -544,7 +586,10 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
         if (rho2 >= 0.5 * before2) break;                          // DGKS: one sweep was enough
         before2 = rho2;
     }
-    if (!(rho2 > 1e-26 * anorm2)) return 1;                        // numerically dependent atom: not appended
+    if (!(rho2 > 1e-26 * anorm2)) {                                // numerically dependent atom: not appended
+        if constexpr (RING_D > 0) cp_async_wait<0>();
+        return 1;
+    }
     if (rho2 < ILLCOND_RATIO * anorm2) S.illcond = 1;
     const double rho = sqrt(rho2);
     double zt, s2r = 0.0;
@@ -552,6 +597,53 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
         // z_t = q_t'b = (<a,b> - <Q'a, Q'b>) / rho;  r <- r - (z_t / rho) (a - A_S y), v formed on the fly
         zt = (t > 0 ? ab - S.red[2 * (NT / 32) + 1] : ab) / rho;
         const double gam = zt / rho;
+        if (S.def_y) {                                             // the sweep runs later, row slice by row slice over all signals
+            for (int i = tid; i < t; i += NT) S.def_y[i] = S.y[i];
+            if (tid == 0) { *S.def_gam = gam; *S.def_t = t; }
+            S.deferred = true;
+        } else if constexpr (RING_D > 0) {
+            double acc[RING_MAX_SLOTS][2], acc1[RING_MAX_SLOTS][2];
+#pragma unroll
+            for (int k = 0; k < RING_MAX_SLOTS; ++k) {
+                const int row = tid * 2 + k * NT * 2;
+                acc1[k][0] = acc1[k][1] = 0.0;
+                if (row < ld) { acc[k][0] = S.v[row]; acc[k][1] = S.v[row + 1]; }
+                else { acc[k][0] = acc[k][1] = 0.0; }
+            }
+            auto step = [&](int i, double (&ac)[RING_MAX_SLOTS][2]) {
+                cp_async_wait<RING_D - 1>();                       // column i has landed (RING_D - 1 younger groups may be open)
+                const double* src = S.ring + (size_t)(i % RING_D) * ld + tid * 2;
+                const double yi = S.y[i];
+                double2 c[RING_MAX_SLOTS];
+#pragma unroll
+                for (int k = 0; k < RING_MAX_SLOTS; ++k)
+                    if (tid * 2 + k * NT * 2 < ld) c[k] = *reinterpret_cast<const double2*>(src + k * NT * 2);
+#pragma unroll
+                for (int k = 0; k < RING_MAX_SLOTS; ++k)
+                    if (tid * 2 + k * NT * 2 < ld) { ac[k][0] = fma(-c[k].x, yi, ac[k][0]); ac[k][1] = fma(-c[k].y, yi, ac[k][1]); }
+                ring_issue(i + RING_D);                            // the slot just read is free again
+            };
+            int i = 0;
+            for (; i + 1 < t; i += 2) { step(i, acc); step(i + 1, acc1); }
+            if (i < t) step(i, acc);
+            cp_async_wait<0>();
+            const double* rs = S.ring + (size_t)(t % RING_D) * ld;  // the residual came in behind the last column
+#pragma unroll
+            for (int k = 0; k < RING_MAX_SLOTS; ++k) {
+                const int row = tid * 2 + k * NT * 2;
+                if (row < ld) {
+                    const double2 rv = *reinterpret_cast<const double2*>(rs + row);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double vq = acc[k][e] + acc1[k][e];
+                        S.v[row + e] = vq;
+                        const T rr = (T)((e ? rv.y : rv.x) - gam * vq);
+                        r_set(row + e, rr);
+                        s2r = fma((double)rr, (double)rr, s2r);
+                    }
+                }
+            }
+        } else
         for (int row = tid * W; row < ld; row += NT * W) {
             double acc[W], acc1[W];
 #pragma unroll
@@ -583,6 +675,7 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
             }
         }
     } else {
+        if constexpr (RING_D > 0) cp_async_wait<0>();              // the prefetched columns are not used on this path
         double sb = 0.0;
         for (int row = tid; row < ld; row += NT) sb += S.v[row] * b_at(row);
         zt = block_sum<NT>(sb, S.red) / rho;                       // z_t = q_t' b
@@ -595,7 +688,7 @@ __device__ __forceinline__ int append_atom(PursuitSmem<T>& S, int& t, int j, con
             s2r += (double)rr * (double)rr;
         }
     }
-    nr2 = block_sum<NT>(s2r, S.red);
+    if (!S.deferred) nr2 = block_sum<NT>(s2r, S.red);
     // append the column [h; rho] to R  <=>  append [-R^{-1}h / rho; 1/rho] to R^{-1}
     const double irho = 1.0 / rho;
     for (int i = tid; i < t; i += NT) {
