@@ -829,7 +829,7 @@ int upd_defer_kper() {
 int ensure_defer_batch(csb200_batch* b) {
     if (b->def_y) return 0;
     double* y = nullptr; double* g = nullptr; int* t = nullptr; double* s2 = nullptr; int* sl = nullptr;
-    if (cudaMalloc(&sl, (size_t)b->cap_sig * sizeof(int)) != cudaSuccess ||
+    if (cudaMalloc(&sl, ((size_t)2 * b->cap_sig + 4) * sizeof(int)) != cudaSuccess ||     // slow flags, slow lists, one counter per part
         cudaMalloc(&y, (size_t)b->cap_sig * b->kcap * sizeof(double)) != cudaSuccess || cudaMalloc(&g, (size_t)b->cap_sig * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&t, (size_t)b->cap_sig * sizeof(int)) != cudaSuccess || cudaMalloc(&s2, (size_t)b->cap_sig * 128 * sizeof(double)) != cudaSuccess) {
         cudaGetLastError(); cudaFree(y); cudaFree(g); cudaFree(t); cudaFree(s2); cudaFree(sl);
@@ -887,7 +887,10 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
             ua.def_y = b->def_y + (size_t)start[h] * b->kcap; ua.def_gam = b->def_gam + start[h]; ua.def_t = b->def_t + start[h];
             ua.def_s2 = b->def_s2 + (size_t)start[h] * 128; ua.def_kper = defer;
             static const int warp_env = [] { const char* e = getenv("CSB200_UPD_WARP"); return e ? atoi(e) : UPD_WARP_DEFAULT; }();
-            if (warp_env > 0 && ua.gram && b->kcap <= 32 && d->n_offset == 0) ua.slow = b->slow + start[h];
+            if (warp_env > 0 && ua.gram && b->kcap <= 32 && d->n_offset == 0) {
+                // flags for this part's signals; list and counter of part h (parts run concurrently in the overlapped schedule)
+                ua.slow = b->slow + start[h]; ua.slow_list = b->slow + b->cap_sig + start[h]; ua.slow_count = b->slow + 2 * b->cap_sig + h;
+            }
         }
         return ua;
     };

@@ -26,9 +26,9 @@ constexpr int UPD_RING_DEFAULT = 0;
 constexpr int UPD_HINTS_DEFAULT = 0;
 // CSB200_UPD_DEFER: 0 = omp_update_kernel down-dates r itself; k = 1, 2, 4: the residual sweep of the screened omp loop runs as
 // separate launches over slices of k * 256 rows of ALL signals (dictionary rows of one slice stay in the L2)
-constexpr int UPD_DEFER_DEFAULT = 0;
+constexpr int UPD_DEFER_DEFAULT = 2;
 // CSB200_UPD_WARP=1 (needs the deferred sweep, a Gram matrix and k <= 32): selection + append by one warp per signal
-constexpr int UPD_WARP_DEFAULT = 0;
+constexpr int UPD_WARP_DEFAULT = 1;
 constexpr int SCREEN_T = 8;
 constexpr int SCREEN_MAX_CHUNKS = 16;
 constexpr int SCREEN_MAX_ROWS = 8192;
@@ -124,6 +124,8 @@ struct StateArgs {
     double* def_gam = nullptr;  // [nsig]
     int* def_t = nullptr;       // [nsig] active columns to combine (support size before the append); -1 = nothing deferred
     int* slow = nullptr;        // [nsig] warp-per-signal append (omp_append_warp_kernel): 1 = left to omp_update_kernel; nullptr = warp path off
+    int* slow_list = nullptr;   // [nsig] the signals with slow[sig] == 1, in arrival order
+    int* slow_count = nullptr;  // [1] entries of slow_list (cleared before every launch of the warp kernel)
     int def_kper = 1;           // row slots of 256 rows per slice launch
     double* def_s2 = nullptr;   // [nsig][128] per-thread running sum of squares of the new residual, carried from slice to slice
     int upd_hints = 0;          // omp_update_kernel cache hints: bit 0 streaming loads / stores of b, r, r32; bit 1 L2 evict_last on

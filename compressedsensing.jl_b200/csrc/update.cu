@@ -401,7 +401,7 @@ omp_append_warp_kernel(StateArgs a) {
     const int oldflags = a.flags[sig];
     if (lane == 0) { a.def_t[sig] = -1; a.slow[sig] = 0; }
     if (done && !a.ignore_done) return;                            // the reference `break`s (:79)
-    auto leave_to_cta = [&]() { if (lane == 0) a.slow[sig] = 1; };
+    auto leave_to_cta = [&]() { if (lane == 0) { a.slow[sig] = 1; a.slow_list[atomicAdd(a.slow_count, 1)] = sig; } };
     if (oldflags & FLAG_ILLCOND) { leave_to_cta(); return; }       // coefficients of this support are refined on every update
     const double* A = static_cast<const double*>(a.A);
     const double* b = static_cast<const double*>(a.B) + (size_t)sig * ld;
@@ -648,6 +648,17 @@ omp_update_kernel(StateArgs a, const T* __restrict__ Acache, int t_in_smem, int 
     for (int sig = blockIdx.x; sig < a.nsig; sig += gridDim.x) {
         omp_update_body<T, NT, BLOCK>(a, Acache, t_in_smem, bm, sig);
         if (sig + (int)gridDim.x < a.nsig) __syncthreads();        // the shared-memory state is rebuilt per signal
+    }
+}
+
+// The signals omp_append_warp_kernel left behind (StateArgs::slow_list, a handful per launch): a small fixed grid walks the list.
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT, 8)
+omp_update_list_kernel(StateArgs a, int t_in_smem) {
+    const int n = *a.slow_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        omp_update_body<T, NT, false>(a, nullptr, t_in_smem, 0, a.slow_list[i]);
+        if (i + (int)gridDim.x < n) __syncthreads();
     }
 }
 
@@ -1055,12 +1066,18 @@ cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void*
                 if (e != cudaSuccess) return e;
                 e = cudaFuncSetAttribute(omp_append_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
                 if (e != cudaSuccess) return e;
+                e = cudaMemsetAsync(a.slow_count, 0, sizeof(int), st);
+                if (e != cudaSuccess) return e;
                 omp_append_warp_kernel<<<(a.nsig + WPB - 1) / WPB, WPB * 32, WPB * sizeof(WarpSmem), st>>>(a);
                 e = cudaGetLastError();
                 if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(omp_update_list_kernel<T, UT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                const int lgrid = a.nsig < 148 * 4 ? a.nsig : 148 * 4;
+                omp_update_list_kernel<T, UT><<<lgrid, UT, smem, st>>>(a, t_in_smem);
             }
         }
-        omp_update_kernel<T, UT, false><<<grid, UT, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, 0);
+        if (!a.slow) omp_update_kernel<T, UT, false><<<grid, UT, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, 0);
         if constexpr (sizeof(T) == 8) {
             if (a.def_y && !a.resc) {                              // the residual sweep, slice by slice over all signals
                 e = cudaGetLastError();

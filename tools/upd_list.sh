@@ -1,8 +1,6 @@
 #!/bin/bash
-# per-kernel times of the deferred update variants (ncu launch list, under gpurun)
+# per-kernel times of the update variants (ncu launch list, duration only, under gpurun)
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 1 --secondary none --cpu-signals 0 --e2e-steps 1 --fp64-steps 0"
-for v in 4 1; do
-CSB200_UPD_DEFER=$v timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_srcunit_tex.sum --clock-control none -k regex:'omp_update|omp_residual|corr_screen' -s 70 -c 200 --csv --log-file gpurun_out/upd_list_d$v.csv $B > gpurun_out/upd_list_d$v.log 2>&1
-done
+CSB200_UPD_DEFER=4 CSB200_UPD_WARP=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'omp_|corr_screen' -s 80 -c 160 --csv --log-file gpurun_out/upd_list_d4w.csv $B > gpurun_out/upd_list_d4w.log 2>&1
 ls -la gpurun_out/upd_list*

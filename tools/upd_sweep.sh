@@ -16,8 +16,8 @@ except Exception as e:
     print(tag, "FAILED", e, open(f"gpurun_out/upd_{tag}.err").read()[-600:])
 PY
 }
+run d2w
+run d4w CSB200_UPD_DEFER=4
 run base CSB200_UPD_DEFER=0
-run d4 CSB200_UPD_DEFER=4
-run d4w CSB200_UPD_DEFER=4 CSB200_UPD_WARP=1
-run d2w CSB200_UPD_DEFER=2 CSB200_UPD_WARP=1
-(CSB200_UPD_DEFER=4 CSB200_UPD_WARP=1 timeout 600 python -m pytest tests/test_gpu_screen.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4)
+run parts2 CSB200_SCREEN_PARTS=2
+(timeout 900 python -m pytest tests/test_gpu_screen.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -x -q 2>&1 | tail -4)
