@@ -107,6 +107,34 @@ def tf32_peak():
     return 1125.0, "fallback: nominal dense TF32 1.1 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
 
 
+def f16_peak():
+    """Dense FP16/BF16 tensor peak: the cuBLAS bf16 figure the driver measured on this pool (MEASURED_PEAKS.json)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["bf16_tflops"]), ("MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 burst, driver-written): tcgen05 kind::f16; "
+                                         "sustained figure %.0f" % float(d.get("bf16_tflops_sustained", 0.0)))
+    return 2250.0, "fallback: nominal dense FP16 2.25 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def f16_gemm_live(torch, dev):
+    """cuBLAS FP16 GEMM (torch.matmul) 8192^3 on this box in this run: the library yardstick for the FP16 screening pass."""
+    try:
+        a = torch.randn(8192, 8192, device=dev, dtype=torch.float16)
+        b = torch.randn(8192, 8192, device=dev, dtype=torch.float16)
+        for _ in range(3):
+            a @ b
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e30
+        for _ in range(5):
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, b
+        return {"tflops": 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12, "what": "torch.matmul fp16, 8192^3, best of 5 (CUDA events)"}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
 def tf32_gemm_live(torch, dev):
     """cuBLAS TF32 GEMM (torch.matmul, allow_tf32) 8192^3 on this box in this run: the library yardstick for the screening pass."""
     try:
@@ -460,10 +488,11 @@ class C2:
         ctx.barrier()
         wall = time.perf_counter() - t0
         scr = batch.screen_stats(reset=True)
-        screened = scr["path_id"] == 3
+        screened = scr["path_id"] in (3, 4)
+        f16 = scr["path_id"] == 4
         live = None
         if with_peak and ctx.rank == 0:                                                   # inside the clocks window
-            live = tf32_gemm_live(ctx.torch, ctx.dev) if screened else fp64_peak_live(ctx.local)
+            live = ((f16_gemm_live if f16 else tf32_gemm_live)(ctx.torch, ctx.dev)) if screened else fp64_peak_live(ctx.local)
         ctx.barrier()
         clocks = sampler.stop()
         corr_ms, corr_launches, other_launches = batch.corr_time()
@@ -514,27 +543,33 @@ class C2:
         if screened:
             # TF32 screening pass (tcgen05): the flop EXECUTED are the algorithmic 2 M N B per pass (tiles 128 x 256 x K,
             # K padded to 32: no padding at this shape), counted at TF32 -- reported against the TF32 tensor peak.
-            peak, peak_src = tf32_peak()
-            kpad = (M + 31) // 32 * 32
+            peak, peak_src = f16_peak() if f16 else tf32_peak()
+            kpad = (M + 63) // 64 * 64 if f16 else (M + 31) // 32 * 32
             tiles = ((B + 127) // 128) * ((N + 255) // 256)
-            l2_bytes = tiles * kpad * 4.0 * (128 + 256)            # operand bytes TMA pulls from L2 per pass
+            l2_bytes = tiles * kpad * (2.0 if f16 else 4.0) * (128 + 256)            # operand bytes TMA pulls from L2 per pass
+            nominal = 2250.0 if f16 else 1125.0
             passes = max(1, k * steps)
             roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                         "traffic": _traffic("corr_screen_traffic.json") if B == 65536 else None,
                         "traffic_unit": "bytes of DRAM read+write per launch (ncu, profiles/corr_screen_traffic.json)",
-                        "kernel": "corr_screen_tf32_kernel", "dtype": "tf32 operands, f32 accumulation (tcgen05.mma kind::tf32)",
+                        "kernel": "corr_screen_tf32_kernel<4, true>" if f16 else "corr_screen_tf32_kernel<4>",
+                        "dtype": ("fp16 operands scaled by powers of two, f32 accumulation (tcgen05.mma kind::f16)" if f16
+                                  else "tf32 operands, f32 accumulation (tcgen05.mma kind::tf32)"),
                         "launches": int(corr_launches), "mean_launch_ms": corr_ms / max(1, corr_launches), "share_of_step": share,
                         "launches_per_update": corr_launches / passes, "flop_per_launch": flop_per_launch,
-                        "peak_source": peak_src, "peak_nominal": 1125.0, "frac_of_nominal": achieved / 1125.0,
+                        "peak_source": peak_src, "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
                         "library_gemm_live": live,
                         "l2_operand_bytes_per_pass": l2_bytes,
                         "l2_to_sm_tbs": l2_bytes * passes / (corr_ms * 1e-3) / 1e12 if corr_ms > 0 else None,
                         "l2_to_sm_port_tbs": 148 * 64 * 1.965e9 / 1e12,
-                        "note": "the pass is bound by the SMs' L2 read ports (64 B/clk/SM), not by the tensor pipe: see DESIGN 4.14"}
+                        "note": ("FP16 operands halve the L2->SM bytes of the TF32 pass (which ran at the SMs' L2 read-port rate); "
+                                 "what bounds the FP16 pass: see DESIGN 4.14" if f16 else
+                                 "the pass is bound by the SMs' L2 read ports (64 B/clk/SM), not by the tensor pipe: see DESIGN 4.14")}
             # the rest of the step is omp_update_kernel (L2-gather-bound): its share and its gather rate
             upd_ms = dev_ms - corr_ms
             gather_bytes = sum((t + 3) for t in range(k)) * M * 8.0 * B * steps      # t active columns + a_j, b, r per update!
-            roofline_update = {"kernel": "omp_update_kernel", "bound": "l2 gather", "share_of_step": upd_ms / dev_ms if dev_ms else None,
+            roofline_update = {"kernel": "omp_append_warp_kernel + omp_residual_slice_kernel (+ omp_update_list_kernel for the few signals off the common path)",
+                               "bound": "l2 gather", "share_of_step": upd_ms / dev_ms if dev_ms else None,
                                "ms_per_update": upd_ms / passes, "algorithmic_gather_bytes_per_step": gather_bytes / steps,
                                "achieved_tbs": gather_bytes / (upd_ms * 1e-3) / 1e12 if upd_ms > 0 else None}
             equiv = value / ctx.world * 2.0 * M * N * k / 1e12
@@ -609,7 +644,7 @@ def run_c2(ctx, args, headline=True):
                  "e2e": o["e2e"], "roofline_frac": o["roofline"]["frac"], "gemm_share_of_step": o["roofline"]["share_of_step"],
                  "check": o["check"]}
     fp64_path = None
-    if args.fp64_steps > 0 and main["check"]["path"].startswith("tf32"):
+    if args.fp64_steps > 0 and ("screening" in main["check"]["path"]):
         # the same workload through the FP64 DMMA pass (CSB200_SCREEN=0): what the screening buys, and the FP64 kernel's roofline
         o = c2.measure(sizes[first], args.fp64_steps, 1, 1, with_peak=True, screen=False)
         fp64_path = {"value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"], "e2e": o["e2e"], "roofline": o["roofline"],
@@ -871,7 +906,7 @@ def run_c5(ctx, args):
         dev_ms64, other_leg = None, None
         # the same workload through the other correlation pass (a few iterations, scaled): FP64 DMMA when the default
         # screened, forced TF32 screening when the default is the DMMA pass (signals longer than 2048 rows)
-        os.environ["CSB200_SCREEN"] = "0" if scr["path_id"] == 3 else "1"
+        os.environ["CSB200_SCREEN"] = "0" if scr["path_id"] in (3, 4) else "1"
         try:
             it2 = max(2, min(iters, 16))
             b.mp(it2)
@@ -885,9 +920,9 @@ def run_c5(ctx, args):
                          "bit_identical_to_default_path": same2}
         finally:
             os.environ.pop("CSB200_SCREEN", None)
-    screened = scr["path_id"] == 3
+    screened = scr["path_id"] in (3, 4)
     if screened:
-        peak, peak_src = tf32_peak()
+        peak, peak_src = tf32_peak()                                 # mp is screened with TF32 operands (atoms need not be normalised)
     tf = 2.0 * Mr * Nc * B * n / corr_ms / 1e9
     cpu, parity = None, None
     if ctx.rank == 0 and ctx.world == 1 and args.cpu_signals > 0:

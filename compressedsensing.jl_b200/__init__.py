@@ -351,7 +351,8 @@ class Batch:
         path = c_int64()
         st = np.zeros(3, dtype=np.uint64)
         _check(lib.csb200_batch_screen_stats(self._h, byref(path), st.ctypes.data, 1 if reset else 0))
-        names = {0: "few-signal / gemv", 1: "dmma", 2: "dmma two-half overlap", 3: "tf32 screening + exact re-evaluation"}
+        names = {0: "few-signal / gemv", 1: "dmma", 2: "dmma two-half overlap", 3: "tf32 screening + exact re-evaluation",
+                 4: "fp16 screening + exact re-evaluation"}
         return {"path": names.get(int(path.value), str(path.value)), "path_id": int(path.value), "signal_updates": int(st[0]),
                 "candidates_reevaluated": int(st[1]), "exact_scans": int(st[2])}
 

@@ -85,14 +85,15 @@ int make_operand_map(CUtensorMap* map, void* base, int64_t ld, int64_t ncols, in
 
 // 2-D FP32 tensor map over a column-major (ld32 x ncols) matrix: box = 32 rows (128 B) x box_cols columns, SWIZZLE_128B --
 // the K-major operand tiles of corr_screen_tf32.cu.
-int make_operand_map32(CUtensorMap* map, void* base, int64_t ld32, int64_t ncols, int box_cols) {
+// f16: the same 128-byte rows hold 64 halves (ld32 then counts halves).
+int make_operand_map32(CUtensorMap* map, void* base, int64_t ld32, int64_t ncols, int box_cols, bool f16 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { g_last_error = "cuTensorMapEncodeTiled entry point not found"; return CSB200_ERR_CUDA; }
     cuuint64_t gdim[2] = {(cuuint64_t)ld32, (cuuint64_t)(ncols > 0 ? ncols : 1)};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld32 * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_cols};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld32 * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {f16 ? 64u : 32u, (cuuint32_t)box_cols};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -138,6 +139,11 @@ struct csb200_dict {
     int64_t ld32 = 0;
     double amax = 0.0;
     bool screen_failed = false;
+    // FP16 operands of the same pass (kind::f16): half(A * qA), qA = 2^sA with qA * amax in [2^11, 2^12)
+    void* dA16 = nullptr;
+    CUtensorMap mapA16;
+    int64_t ld16 = 0;
+    double qA = 1.0;
     // multi-device handle (csb200_dict_create_multi): this object is the replica of worker 0; `extra` holds the
     // replicas of workers 1..n-1 (owned).  The one-shot entry points fan a batch out over all of them.
     std::vector<csb200_dict*> extra;
@@ -184,8 +190,10 @@ struct csb200_batch {
     float* scr_val = nullptr;
     int* scr_idx = nullptr;
     unsigned long long* scr_stats = nullptr;    // device: [0] signal-updates, [1] candidates re-evaluated, [2] exact scans
+    double* rscale = nullptr;                   // [cap_sig] FP16 screening: power of two each stored residual is scaled by
+    int r32_mode = 0;                           // what dR32 holds: 0 floats (TF32), 1 scaled halves
     double* def_y = nullptr; double* def_gam = nullptr; int* def_t = nullptr; double* def_s2 = nullptr; int* slow = nullptr;   // deferred residual sweep (StateArgs::def_*)
-    int last_path = 0;                          // 0 other, 1 DMMA loop, 2 DMMA two-half overlap, 3 TF32 screening + exact re-evaluation
+    int last_path = 0;                          // 0 other, 1 DMMA loop, 2 DMMA two-half overlap, 3 TF32 screening + exact re-evaluation, 4 FP16 screening
     cudaStream_t stream = nullptr;
     bool profile = false;
     std::vector<cudaEvent_t> ev;     // pairs (start, stop) per correlation launch
@@ -229,7 +237,7 @@ void free_batch_mem(csb200_batch* b) {
     cudaFree(b->Rf); cudaFree(b->dflag); cudaFree(b->stage32); cudaFree(b->resc); cudaFree(b->qnew); cudaFree(b->cn2); cudaFree(b->ndone);
     cudaFree(b->persist_scratch);
     cudaFree(b->dR32); cudaFree(b->scr_val); cudaFree(b->scr_idx); cudaFree(b->scr_stats);
-    cudaFree(b->def_y); cudaFree(b->def_gam); cudaFree(b->def_t); cudaFree(b->def_s2); cudaFree(b->slow);
+    cudaFree(b->rscale); cudaFree(b->def_y); cudaFree(b->def_gam); cudaFree(b->def_t); cudaFree(b->def_s2); cudaFree(b->slow);
     if (b->host_stage) cudaFreeHost(b->host_stage);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_solve0) cudaEventDestroy(b->ev_solve0);
@@ -275,8 +283,7 @@ StateArgs state_args(csb200_batch* b, int S, int take, double eps, int ignore_do
     a.resnorm = b->resnorm; a.iters = b->iters; a.done = b->done; a.flags = b->flags;
     a.gram = b->use_gram ? d->gram : nullptr;
     a.dense_ld = b->cur_dense_ld;
-    static const int hints = [] { const char* e = getenv("CSB200_UPD_HINTS"); return e ? atoi(e) : UPD_HINTS_DEFAULT; }();
-    a.upd_hints = hints;
+    { const char* e = getenv("CSB200_UPD_HINTS"); a.upd_hints = e ? atoi(e) : UPD_HINTS_DEFAULT; }
     return a;
 }
 
@@ -773,10 +780,23 @@ bool use_omp_screen(const csb200_batch* b, int64_t k) {
 }
 
 // dictionary side (once per handle): TF32 copy, tensor map, largest column norm
-int ensure_screen_dict(csb200_dict* d, cudaStream_t st) {
+bool screen_f16() {
+    const char* e = getenv("CSB200_SCREEN_F16");
+    return (e ? atoi(e) : SCREEN_F16_DEFAULT) != 0;
+}
+int ensure_screen_dict(csb200_dict* d, cudaStream_t st, bool f16 = false) {
     std::lock_guard<std::mutex> lk(d->screen_mu);
-    if (d->dA32) return CSB200_OK;
     if (d->screen_failed) return 1;
+    if (f16 && d->dA32 && !d->dA16) {                               // the FP16 copy, once the TF32 set-up (amax) exists
+        const int64_t ld16 = round_up(d->M, 64);
+        void* a16 = nullptr;
+        if (cudaMalloc(&a16, (size_t)ld16 * d->N * 2) != cudaSuccess) { cudaGetLastError(); return 1; }
+        const double qA = ldexp(1.0, 11 - ilogb(d->amax));
+        cudaError_t e16 = launch_to_f16(static_cast<const double*>(d->dA), d->ld, a16, ld16, (int)d->M, d->N, qA, nullptr, st);
+        if (e16 != cudaSuccess || make_operand_map32(&d->mapA16, a16, ld16, d->N, 256, true) != CSB200_OK) { cudaGetLastError(); cudaFree(a16); return 1; }
+        d->ld16 = ld16; d->qA = qA; d->dA16 = a16;
+    }
+    if (d->dA32) return (f16 && !d->dA16) ? 1 : CSB200_OK;
     static std::once_flag once;
     static cudaError_t setup_err = cudaSuccess;
     std::call_once(once, [] { setup_err = corr_screen_setup(); });
@@ -800,11 +820,25 @@ int ensure_screen_dict(csb200_dict* d, cudaStream_t st) {
         cudaGetLastError(); cudaFree(a32); d->screen_failed = true; return 1;
     }
     d->ld32 = ld32; d->amax = amax; d->dA32 = a32;
+    if (f16) {                                                      // (the lock is held: build the FP16 copy inline)
+        const int64_t ld16 = round_up(d->M, 64);
+        void* a16 = nullptr;
+        if (cudaMalloc(&a16, (size_t)ld16 * d->N * 2) != cudaSuccess) { cudaGetLastError(); return 1; }
+        const double qA = ldexp(1.0, 11 - ilogb(d->amax));
+        cudaError_t e16 = launch_to_f16(static_cast<const double*>(d->dA), d->ld, a16, ld16, (int)d->M, d->N, qA, nullptr, st);
+        if (e16 != cudaSuccess || make_operand_map32(&d->mapA16, a16, ld16, d->N, 256, true) != CSB200_OK) { cudaGetLastError(); cudaFree(a16); return 1; }
+        d->ld16 = ld16; d->qA = qA; d->dA16 = a16;
+    }
     return CSB200_OK;
 }
 
-int ensure_screen_batch(csb200_batch* b) {
+int ensure_screen_batch(csb200_batch* b, bool f16 = false) {
     csb200_dict* d = b->dict;
+    if (b->dR32 && f16 && !b->rscale && cudaMalloc(&b->rscale, (size_t)b->cap_sig * sizeof(double)) != cudaSuccess) { cudaGetLastError(); b->rscale = nullptr; return 1; }
+    if (b->dR32 && b->r32_mode != (f16 ? 1 : 0)) {                  // the other layout's bytes must not show up in the padding rows
+        CU_TRY(cudaMemsetAsync(b->dR32, 0, (size_t)b->cap_sig * d->ld32 * sizeof(float), b->stream));
+        b->r32_mode = f16 ? 1 : 0;
+    }
     if (b->dR32) return CSB200_OK;
     const size_t rbytes = (size_t)b->cap_sig * d->ld32 * sizeof(float);
     const size_t slots = (size_t)b->cap_sig * SCREEN_MAX_CHUNKS * SCREEN_T;
@@ -817,13 +851,16 @@ int ensure_screen_batch(csb200_batch* b) {
     CU_TRY(cudaMemsetAsync(r32, 0, rbytes, b->stream));            // rows [ld, ld32) stay zero for ever
     CU_TRY(cudaMemsetAsync(stt, 0, 4 * sizeof(unsigned long long), b->stream));
     b->dR32 = r32; b->scr_val = sv; b->scr_idx = si; b->scr_stats = stt;
+    b->r32_mode = f16 ? 1 : 0;
+    if (f16 && !b->rscale && cudaMalloc(&b->rscale, (size_t)b->cap_sig * sizeof(double)) != cudaSuccess) { cudaGetLastError(); b->rscale = nullptr; return 1; }
     return CSB200_OK;
 }
 
 // Row slots per slice launch of the deferred residual sweep (0 = the update kernel down-dates r itself)
 int upd_defer_kper() {
-    static const int v = [] { const char* e = getenv("CSB200_UPD_DEFER"); const int k = e ? atoi(e) : UPD_DEFER_DEFAULT; return k < 0 ? 0 : k; }();
-    return v;
+    const char* e = getenv("CSB200_UPD_DEFER");                    // read per solve: the tests switch variants within one process
+    const int k = e ? atoi(e) : UPD_DEFER_DEFAULT;
+    return k < 0 ? 0 : k;
 }
 // Buffers of the deferred sweep; 1 when they cannot be had (the update then runs undeferred)
 int ensure_defer_batch(csb200_batch* b) {
@@ -852,9 +889,15 @@ int ensure_defer_batch(csb200_batch* b) {
 // them together slows the pass more (0.76 -> 1.06-1.8 ms per half) than it hides of the update.  Hence serial.
 int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
     csb200_dict* d = b->dict;
-    int rc = ensure_screen_dict(d, b->stream);
+    bool f16 = screen_f16();
+    int rc = ensure_screen_dict(d, b->stream, f16);
+    if (rc && f16) { f16 = false; rc = ensure_screen_dict(d, b->stream, false); }
     if (rc) return rc;
-    if ((rc = ensure_screen_batch(b))) return rc;
+    if ((rc = ensure_screen_batch(b, f16))) return rc;
+    const int64_t ldS = f16 ? d->ld16 : d->ld32;                       // elements per signal of the pass's residual operand
+    const size_t esz = f16 ? 2 : 4;
+    char* const r32base = reinterpret_cast<char*>(b->dR32);
+    const CUtensorMap* mapA = f16 ? &d->mapA16 : &d->mapA32;
     const int parts_env = [] { const char* e = getenv("CSB200_SCREEN_PARTS"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
     const int64_t tiles = (b->nsig + 127) / 128;
     int NP = b->nsig >= 2 * SCREEN_MIN_SIGNALS && k >= 2 ? parts_env : 1;
@@ -876,17 +919,21 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
     const int defer = upd_defer_kper() > 0 && ensure_defer_batch(b) == 0 ? upd_defer_kper() : 0;
     CUtensorMap mapR32[4];
     for (int h = 0; h < NP; ++h)
-        if ((rc = make_operand_map32(&mapR32[h], b->dR32 + (size_t)start[h] * d->ld32, d->ld32, count[h], 128))) return rc;
+        if ((rc = make_operand_map32(&mapR32[h], r32base + (size_t)start[h] * ldS * esz, ldS, count[h], 128, f16))) return rc;
     auto screen_args = [&](int h) {
         StateArgs ua = state_args_range(b, start[h], count[h], 1, 1, eps, 0);
         ua.scr_val = b->scr_val + (size_t)start[h] * nc; ua.scr_idx = b->scr_idx + (size_t)start[h] * nc; ua.scr_nc = nc;
         ua.scr_chunk_atoms = screen_chunk_atoms((int)d->N, chunks);
-        ua.scr_bound = screen_kappa((int)d->M) * d->amax;
-        ua.R32 = b->dR32 + (size_t)start[h] * d->ld32; ua.ld32 = (int)d->ld32; ua.scr_stats = b->scr_stats;
+        ua.scr_bound = (f16 ? screen_kappa_f16((int)d->ld16) : screen_kappa((int)d->M)) * d->amax;
+        ua.R32 = reinterpret_cast<float*>(r32base + (size_t)start[h] * ldS * esz); ua.ld32 = (int)ldS; ua.scr_stats = b->scr_stats;
+        if (f16) {
+            ua.scr_f16 = 1; ua.rscale = b->rscale + start[h]; ua.scr_invqA = 1.0 / d->qA;
+            ua.scr_abs = 1.05 * sqrt((double)d->ld16) * 6.103515625e-5 * d->amax;
+        }
         if (defer) {
             ua.def_y = b->def_y + (size_t)start[h] * b->kcap; ua.def_gam = b->def_gam + start[h]; ua.def_t = b->def_t + start[h];
             ua.def_s2 = b->def_s2 + (size_t)start[h] * 128; ua.def_kper = defer;
-            static const int warp_env = [] { const char* e = getenv("CSB200_UPD_WARP"); return e ? atoi(e) : UPD_WARP_DEFAULT; }();
+            const int warp_env = [] { const char* e = getenv("CSB200_UPD_WARP"); return e ? atoi(e) : UPD_WARP_DEFAULT; }();
             if (warp_env > 0 && ua.gram && b->kcap <= 32 && d->n_offset == 0) {
                 // flags for this part's signals; list and counter of part h (parts run concurrently in the overlapped schedule)
                 ua.slow = b->slow + start[h]; ua.slow_list = b->slow + b->cap_sig + start[h]; ua.slow_count = b->slow + 2 * b->cap_sig + h;
@@ -894,6 +941,13 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
         }
         return ua;
     };
+    // kernels one update! launches besides the pass: warp-per-signal append + list kernel (or the CTA kernel), residual slices
+    const int64_t upd_kernels = [&] {
+        const StateArgs probe = screen_args(0);
+        int64_t n = probe.slow ? 2 : 1;
+        if (probe.def_y) { const int slots = ((int)d->ld + 255) / 256; n += (slots + defer - 1) / defer; }
+        return n;
+    }();
     auto pass = [&](int h, cudaStream_t st) -> int {
         cudaEvent_t p0 = nullptr, p1 = nullptr;
         if (b->profile) {
@@ -902,15 +956,15 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
             p0 = b->ev[b->ev_used]; p1 = b->ev[b->ev_used + 1]; b->ev_used += 2;
             CU_TRY(cudaEventRecord(p0, st));
         }
-        cudaError_t e2 = launch_corr_screen(&mapR32[h], &d->mapA32, (int)d->N, (int)count[h], (int)d->ld32, chunks, (int)d->n_offset,
-                                            b->scr_val + (size_t)start[h] * nc, b->scr_idx + (size_t)start[h] * nc, d->num_sms, st, stages);
+        cudaError_t e2 = launch_corr_screen(&mapR32[h], mapA, (int)d->N, (int)count[h], (int)ldS, chunks, (int)d->n_offset,
+                                            b->scr_val + (size_t)start[h] * nc, b->scr_idx + (size_t)start[h] * nc, d->num_sms, st, stages, f16);
         if (e2 != cudaSuccess) return fail_cuda(e2, "screening kernel launch");
         if (b->profile) CU_TRY(cudaEventRecord(p1, st));
         return CSB200_OK;
     };
     {
         StateArgs ra = state_args(b, 1, 1, eps, 0);
-        ra.R32 = b->dR32; ra.ld32 = (int)d->ld32;
+        ra.R32 = b->dR32; ra.ld32 = (int)ldS; ra.scr_f16 = f16 ? 1 : 0; ra.rscale = b->rscale;
         cudaError_t e = launch_reset_state(ra, false, b->stream);
         if (e != cudaSuccess) return fail_cuda(e, "reset_state");
     }
@@ -921,9 +975,9 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
             if ((rc = pass(0, b->stream))) return rc;
             cudaError_t e = launch_omp_update(ua, false, b->stream);
             if (e != cudaSuccess) return fail_cuda(e, "omp_update");
-            b->other_launches++;
+            b->other_launches += upd_kernels;
         }
-        b->last_path = 3;
+        b->last_path = f16 ? 4 : 3;
         return CSB200_OK;
     }
     if (!b->sp_gemm) {
@@ -949,12 +1003,12 @@ int run_omp_screen(csb200_batch* b, int64_t k, double eps) {
             cudaError_t e = launch_omp_update(ua, false, U);
             if (e != cudaSuccess) return fail_cuda(e, "omp_update");
             CU_TRY(cudaEventRecord(evU[h], U));
-            b->other_launches++;
+            b->other_launches += upd_kernels;
         }
     }
     CU_TRY(cudaEventRecord(ev_end, U));                                  // U's last update follows every G launch
     CU_TRY(cudaStreamWaitEvent(b->stream, ev_end, 0));
-    b->last_path = 3;
+    b->last_path = f16 ? 4 : 3;
     return CSB200_OK;
 }
 
@@ -1348,7 +1402,7 @@ int csb200_dict_destroy(csb200_dict* d) {
     for (csb200_dict* r : d->extra) csb200_dict_destroy(r);
     cudaSetDevice(d->device);
     cudaFree(d->gram);
-    cudaFree(d->dA32);
+    cudaFree(d->dA32); cudaFree(d->dA16);
     cudaFree(d->dA);
     delete d;
     return CSB200_OK;
@@ -2474,21 +2528,36 @@ int csb200_debug_screen_pass(csb200_batch* b, float* val, int32_t* idx, int64_t*
     if ((rc = set_device(d))) return rc;
     if (!screen_legal(b)) { g_last_error = "screening needs an unsharded FP64 dictionary with <= 2048 rows and >= 256 atoms"; return CSB200_ERR_UNSUPPORTED; }
     if ((rc = settle_input(b))) return rc;
-    if (ensure_screen_dict(d, b->stream) || ensure_screen_batch(b)) { g_last_error = "screening pass could not be set up"; return CSB200_ERR_UNSUPPORTED; }
+    const bool f16 = screen_f16();
+    if (ensure_screen_dict(d, b->stream, f16) || ensure_screen_batch(b, f16)) { g_last_error = "screening pass could not be set up"; return CSB200_ERR_UNSUPPORTED; }
     const int chunks = screen_chunks_for((int)d->N, (int)b->nsig, d->num_sms);
+    const int64_t ldS = f16 ? d->ld16 : d->ld32;
     CUtensorMap mapR32;
-    if ((rc = make_operand_map32(&mapR32, b->dR32, d->ld32, b->nsig, 128))) return rc;
-    cudaError_t e = launch_to_tf32(b->dR, false, d->ld, b->dR32, d->ld32, (int)d->M, b->nsig, b->stream);   // the CURRENT residuals
+    if ((rc = make_operand_map32(&mapR32, b->dR32, ldS, b->nsig, 128, f16))) return rc;
+    // the CURRENT residuals, converted as the solve would have left them (FP16: scaled by the power of two of their own norm)
+    cudaError_t e = f16 ? launch_to_f16(static_cast<const double*>(b->dR), d->ld, b->dR32, ldS, (int)d->M, b->nsig, 1.0, b->rscale, b->stream)
+                        : launch_to_tf32(b->dR, false, d->ld, b->dR32, d->ld32, (int)d->M, b->nsig, b->stream);
     if (e == cudaSuccess)
-        e = launch_corr_screen(&mapR32, &d->mapA32, (int)d->N, (int)b->nsig, (int)d->ld32, chunks, (int)d->n_offset, b->scr_val,
-                               b->scr_idx, d->num_sms, b->stream);
+        e = launch_corr_screen(&mapR32, f16 ? &d->mapA16 : &d->mapA32, (int)d->N, (int)b->nsig, (int)ldS, chunks, (int)d->n_offset, b->scr_val,
+                               b->scr_idx, d->num_sms, b->stream, 4, f16);
     const size_t n = (size_t)b->nsig * chunks * SCREEN_T;
+    std::vector<double> rs;
+    if (f16) rs.resize((size_t)b->nsig);
     if (e == cudaSuccess) e = cudaMemcpyAsync(val, b->scr_val, n * sizeof(float), cudaMemcpyDeviceToHost, b->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx, b->scr_idx, n * sizeof(int), cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess && f16) e = cudaMemcpyAsync(rs.data(), b->rscale, rs.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
     if (e != cudaSuccess) return fail_cuda(e, "debug_screen_pass");
+    if (f16)                                                           // back to the units of <a_j, r>: both scales are powers of two
+        for (int64_t sg = 0; sg < b->nsig; ++sg)
+            for (int c = 0; c < chunks * SCREEN_T; ++c) {
+                float& v = val[(size_t)sg * chunks * SCREEN_T + c];
+                if (v >= 0.0f) v = (float)((double)v / (rs[(size_t)sg] * d->qA));
+            }
     *chunks_out = chunks;
-    if (bound_out) *bound_out = screen_kappa((int)d->M) * d->amax;
+    // relative part of the bound (x ||r||); the FP16 pass adds sqrt(M) 2^-14 max||a|| / rscale, < 1e-3 of it for a residual
+    // converted at its own norm
+    if (bound_out) *bound_out = (f16 ? screen_kappa_f16((int)d->ld16) * (1.0 + 2e-3) : screen_kappa((int)d->M)) * d->amax;
     return CSB200_OK;
 }
 

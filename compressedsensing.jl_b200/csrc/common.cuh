@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <limits.h>
 
@@ -29,17 +30,46 @@ constexpr int UPD_HINTS_DEFAULT = 0;
 constexpr int UPD_DEFER_DEFAULT = 2;
 // CSB200_UPD_WARP=1 (needs the deferred sweep, a Gram matrix and k <= 32): selection + append by one warp per signal
 constexpr int UPD_WARP_DEFAULT = 1;
+// CSB200_SCREEN_F16: the screening pass of batched omp on FP16 operands (kind::f16) instead of TF32
+constexpr int SCREEN_F16_DEFAULT = 1;
 constexpr int SCREEN_T = 8;
 constexpr int SCREEN_MAX_CHUNKS = 16;
 constexpr int SCREEN_MAX_ROWS = 8192;
 __host__ __device__ inline double screen_kappa(int M) { return 1.05 * (9.765625e-4 + 2.384185791015625e-7 + (double)M * 2.384185791015625e-7); }
 constexpr double SCREEN_NORM_MIN = 1e-18, SCREEN_NORM_MAX = 1e18;   // residual norms outside: exact scan (FP32 range)
 
+// FP16 screening (round 2; kind::f16: twice the tensor rate of kind::tf32, half the operand bytes, the SAME 11 significant
+// bits): the residual of a signal is stored as half(r * p) with p the power of two that puts the norm the residual had BEFORE the
+// update into [2^11, 2^12) (norms only shrink in omp, so |entries| <= 2^12 << 65504), the dictionary as half(A * 2^sA) with
+// 2^sA max_j ||a_j|| in [2^11, 2^12).  Rounding of normal halves is <= 2^-11 relative as with TF32; entries below 2^-14 are
+// charged the full 2^-14 (valid whether the tensor core keeps or flushes subnormals): on the residual side that is
+// sqrt(M) 2^-14 max||a|| / p in true units (StateArgs::scr_abs / p; 1e-3 of the relative term in a normal iteration, dominant
+// only when an update shrinks the residual by > 1e3, where it widens the window up to an exact scan), on the dictionary side
+// a relative sqrt(M) 2^-25 (folded into scr_bound).
+__host__ __device__ inline double screen_kappa_f16(int M) {
+    return screen_kappa(M) + 1.05 * sqrt((double)M) * 2.98023223876953125e-8;
+}
+__host__ __device__ inline double screen_rscale(double nr_old) {
+    if (!(nr_old >= 1e-30 && nr_old <= 1e30)) return 1.0;          // outside SCREEN_NORM_MIN..MAX anyway: exact scan
+    return ldexp(1.0, 11 - ilogb(nr_old));
+}
 #ifdef __CUDACC__
 __device__ __forceinline__ float tf32_round(float x) {          // round to nearest, ties away: 10 explicit mantissa bits
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
+}
+// one entry of the screening pass's copy of a residual: TF32-rounded float, or scaled half (base points at the signal's row 0)
+__device__ __forceinline__ void screen_store(void* base, int row, double val, int f16, double p, bool streaming) {
+    if (f16) {
+        const __half h = __double2half(val * p);
+        if (streaming) __stcs(reinterpret_cast<unsigned short*>(base) + row, __half_as_ushort(h));
+        else reinterpret_cast<__half*>(base)[row] = h;
+    } else {
+        const float f = tf32_round((float)val);
+        if (streaming) __stcs(reinterpret_cast<float*>(base) + row, f);
+        else reinterpret_cast<float*>(base)[row] = f;
+    }
 }
 #endif
 
@@ -79,7 +109,9 @@ int screen_chunks_for(int N, int nsig, int num_sms);
 int screen_chunk_atoms(int N, int chunks);      // atoms covered by one chunk (whole 256-atom tiles)
 cudaError_t corr_screen_setup();
 cudaError_t launch_corr_screen(const CUtensorMap* mapR32, const CUtensorMap* mapA32, int N, int nsig, int ld32, int chunks,
-                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st, int stages = 4);
+                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st, int stages = 4, bool f16 = false);
+cudaError_t launch_to_f16(const double* in, long long ld_in, void* out, long long ld_out, int rows, long long cols, double scale,
+                          double* per_col_scale, cudaStream_t st);
 cudaError_t launch_to_tf32(const void* in, bool f32, long long ld_in, float* out, long long ld_out, int rows, long long cols,
                            cudaStream_t st);
 // GEMV pass: a.P = corr_gemv_blocks(...) CTAs per signal, each emitting the top-S of its contiguous atom range.
@@ -140,8 +172,12 @@ struct StateArgs {
     int scr_nc = 0;                   // chunks * SCREEN_T
     int scr_chunk_atoms = 0;          // atoms per chunk: chunk c covers local atoms [c * scr_chunk_atoms, (c + 1) * scr_chunk_atoms)
     double scr_bound = 0.0;           // screen_kappa(M) * max_j ||a_j||: E = scr_bound * ||r||
-    float* R32 = nullptr;             // [nsig][ld32] TF32-rounded residuals (the screening pass's operand)
-    int ld32 = 0;
+    float* R32 = nullptr;             // [nsig][ld32] TF32-rounded residuals (the screening pass's operand); scr_f16: halves
+    int ld32 = 0;                     // elements per signal of R32 (floats, or halves when scr_f16)
+    int scr_f16 = 0;                  // 1: FP16 operands (see screen_rscale); candidates arrive scaled by rscale[sig] / scr_invqA
+    double* rscale = nullptr;         // [nsig] power of two the stored residual is scaled by
+    double scr_abs = 0.0;             // additive term of the bound: E = scr_bound ||r|| + scr_abs / rscale
+    double scr_invqA = 1.0;           // 2^-sA
     unsigned long long* scr_stats = nullptr;   // optional counters: [0] signal-updates screened, [1] candidates re-evaluated, [2] exact scans
 };
 // Acache (optional): ld x kcap buffer holding the active atoms' columns in selection order, with the

@@ -79,6 +79,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // Instruction descriptor: D = F32 (bit 4), A = B = TF32 (2 at bits 7 and 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t UMMA_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ST_ATOM >> 3) << 17) | ((uint32_t)(ST_SIG >> 4) << 24);
 
+// kind::f16 with FP16 operands (format code 0) and the same FP32 accumulator: K = 16 halves = 32 bytes per instruction
+constexpr uint32_t UMMA_IDESC_F16 = (1u << 4) | ((uint32_t)(ST_ATOM >> 3) << 17) | ((uint32_t)(ST_SIG >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(UMMA_IDESC_F16), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -117,7 +126,10 @@ __device__ __forceinline__ void top_insert(float (&v)[SCREEN_T], int (&id)[SCREE
     }
 }
 
-template <int ST_STAGES>
+// F16: the operands are FP16 (residuals scaled per signal, dictionary scaled as a whole, both by powers of two: api.cu) -- a
+// K-block is then 64 halves (the same 128-byte swizzle rows and the same stage bytes), one stage feeds four K = 16
+// instructions, and everything else is unchanged.
+template <int ST_STAGES, bool F16 = false>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapA,
                         int N, int nsig, int kblocks, int tilesN, int chunks, int tiles_per_chunk, int units,
@@ -163,8 +175,8 @@ corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_c
                         const uint32_t full = bar_full + stage * 8;
                         const uint32_t dst = sm_base + stage * ST_STAGE_BYTES;
                         bar_arrive_expect_tx(full, ST_STAGE_BYTES);
-                        tma_2d(dst, &mapR, full, kb * ST_KB, sig_tile * ST_SIG);
-                        tma_2d(dst + ST_A_BYTES, &mapA, full, kb * ST_KB, t * ST_ATOM);
+                        tma_2d(dst, &mapR, full, kb * (F16 ? 2 * ST_KB : ST_KB), sig_tile * ST_SIG);
+                        tma_2d(dst + ST_A_BYTES, &mapA, full, kb * (F16 ? 2 * ST_KB : ST_KB), t * ST_ATOM);
                         if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
                     }
             }
@@ -187,8 +199,10 @@ corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_c
                         const uint32_t sa = sm_base + stage * ST_STAGE_BYTES;
                         const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + ST_A_BYTES);
 #pragma unroll
-                        for (int k = 0; k < ST_KB / 8; ++k)                         // K = 8 TF32 = 32 bytes per instruction
-                            umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < ST_KB / 8; ++k) {                       // K = 8 TF32 (16 FP16) = 32 bytes per instruction
+                            if constexpr (F16) umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (uint32_t)((kb | k) != 0));
+                            else umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), (uint32_t)((kb | k) != 0));
+                        }
                         umma_commit(bar_empty + stage * 8);                         // stage free once these MMAs have read it
                         if (++stage == ST_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -260,6 +274,33 @@ __global__ void __launch_bounds__(256) to_tf32_kernel(const T* __restrict__ in, 
     }
 }
 
+// FP16 copy of a column-major matrix for the kind::f16 pass: out[r + c * ld_out] = half(in[r + c * ld_in] * scale_c), zero below
+// `rows`.  scale_c = `scale` for every column (the dictionary), or -- per_col_out given -- the power of two that brings the
+// column's own norm into [2^11, 2^12) (screen_rscale; residuals), stored there.  One CTA per column (grid-stride).
+__global__ void __launch_bounds__(256) to_f16_kernel(const double* __restrict__ in, long long ld_in, __half* __restrict__ out,
+                                                    long long ld_out, int rows, long long cols, double scale,
+                                                    double* __restrict__ per_col_out) {
+    __shared__ double red[8];
+    for (long long c = blockIdx.x; c < cols; c += gridDim.x) {
+        const double* x = in + c * ld_in;
+        double sc = scale;
+        if (per_col_out) {
+            double s2 = 0.0;
+            for (int r = threadIdx.x; r < rows; r += 256) s2 = fma(x[r], x[r], s2);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s2;
+            __syncthreads();
+            double tot = 0.0;
+            for (int w = 0; w < 8; ++w) tot += red[w];
+            sc = screen_rscale(sqrt(tot));
+            if (threadIdx.x == 0) per_col_out[c] = sc;
+        }
+        for (int r = threadIdx.x; r < ld_out; r += 256) out[c * ld_out + r] = r < rows ? __double2half(x[r] * sc) : __double2half(0.0);
+    }
+}
+
 }  // namespace
 
 // Atom chunks per signal tile; a work unit is (128 signals) x (one chunk).  Two opposing effects, both measured at the
@@ -294,17 +335,29 @@ cudaError_t corr_screen_setup() {
     cudaError_t e = cudaFuncSetAttribute(corr_screen_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_screen_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(3));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_screen_tf32_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_screen_tf32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(4));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_screen_tf32_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st_smem_bytes(3));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(corr_screen_tf32_kernel<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     return e;
 }
 
 cudaError_t launch_corr_screen(const CUtensorMap* mapR32, const CUtensorMap* mapA32, int N, int nsig, int ld32, int chunks,
-                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st, int stages) {
+                               int idx_offset, float* cval, int* cidx, int num_sms, cudaStream_t st, int stages, bool f16) {
     if (nsig <= 0 || N <= 0) return cudaSuccess;
     const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
     const int tpc = (tilesN + chunks - 1) / chunks;
     const int sig_tiles = (nsig + ST_SIG - 1) / ST_SIG;
     const int units = sig_tiles * chunks;
     const int grid = units < num_sms ? units : num_sms;
+    if (f16) {                                                     // ld32 counts halves here: 64 per K-block
+        if (stages == 3)
+            corr_screen_tf32_kernel<3, true><<<grid, ST_THREADS, st_smem_bytes(3), st>>>(*mapR32, *mapA32, N, nsig, ld32 / (2 * ST_KB), tilesN,
+                                                                                         chunks, tpc, units, idx_offset, cval, cidx);
+        else
+            corr_screen_tf32_kernel<4, true><<<grid, ST_THREADS, st_smem_bytes(4), st>>>(*mapR32, *mapA32, N, nsig, ld32 / (2 * ST_KB), tilesN,
+                                                                                         chunks, tpc, units, idx_offset, cval, cidx);
+        return cudaGetLastError();
+    }
     if (stages == 3)
         corr_screen_tf32_kernel<3><<<grid, ST_THREADS, st_smem_bytes(3), st>>>(*mapR32, *mapA32, N, nsig, ld32 / ST_KB, tilesN, chunks,
                                                                                tpc, units, idx_offset, cval, cidx);
@@ -321,6 +374,14 @@ cudaError_t launch_to_tf32(const void* in, bool f32, long long ld_in, float* out
     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (f32) to_tf32_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), ld_in, out, ld_out, rows, cols);
     else to_tf32_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(in), ld_in, out, ld_out, rows, cols);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_to_f16(const double* in, long long ld_in, void* out, long long ld_out, int rows, long long cols, double scale,
+                          double* per_col_scale, cudaStream_t st) {
+    if (cols <= 0) return cudaSuccess;
+    const int grid = (int)(cols < 148 * 16 ? cols : 148 * 16);
+    to_f16_kernel<<<grid, 256, 0, st>>>(in, ld_in, static_cast<__half*>(out), ld_out, rows, cols, scale, per_col_scale);
     return cudaGetLastError();
 }
 

@@ -94,6 +94,8 @@ __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nc = a.scr_nc, ld = a.ld, nchunks = nc / SCREEN_T;
     const double nr = a.resnorm[sig];
+    const double rsc = a.scr_f16 ? a.rscale[sig] : 1.0;            // FP16 operands: candidates are scaled by rsc * 2^sA
+    const double inv_q = a.scr_f16 ? a.scr_invqA / rsc : 1.0;
     float v = -1.0f;
     int idx = -1;
     if (tid < nc) { v = a.scr_val[(size_t)sig * nc + tid]; idx = a.scr_idx[(size_t)sig * nc + tid]; }
@@ -108,8 +110,9 @@ __device__ void screen_select(const StateArgs& a, int sig, const T* __restrict__
 #pragma unroll
     for (int w = 1; w < NT / 32; ++w) v0 = fmax(v0, red_v[w]);
     const bool range_ok = nr >= SCREEN_NORM_MIN && nr <= SCREEN_NORM_MAX && v0 >= 0.0 && v0 <= 3.0e38;
-    const double thr = v0 - 2.0 * a.scr_bound * nr;
-    const bool inw = idx >= 0 && (double)v >= thr;
+    v0 *= inv_q;
+    const double thr = v0 - 2.0 * (a.scr_f16 ? a.scr_bound * nr + a.scr_abs / rsc : a.scr_bound * nr);
+    const bool inw = idx >= 0 && (double)v * inv_q >= thr;
     const int chunk = tid / SCREEN_T;
     if (inw && (tid % SCREEN_T) == SCREEN_T - 1) atomicOr(&s_inc, 1u << chunk);
     __syncthreads();
@@ -247,10 +250,13 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
     const bool stream = a.upd_hints & 1;
     auto b_at = [&](int row) { return (double)(stream ? __ldcs(b + row) : b[row]); };
     auto r_at = [&](int row) { return (double)(stream ? __ldcs(r + row) : r[row]); };
-    float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;   // TF32 copy read by the screening pass
+    // TF32 (or scaled FP16) copy read by the screening pass
+    void* r32 = !a.R32 ? nullptr : a.scr_f16 ? static_cast<void*>(reinterpret_cast<__half*>(a.R32) + (size_t)sig * a.ld32)
+                                             : static_cast<void*>(a.R32 + (size_t)sig * a.ld32);
+    const double rsc_new = a.scr_f16 ? screen_rscale(a.resnorm[sig]) : 1.0;   // from the norm BEFORE this update
     auto r_set = [&](int row, T val) {
-        if (stream) { __stcs(r + row, val); if (r32) __stcs(r32 + row, tf32_round((float)val)); }
-        else { r[row] = val; if (r32) r32[row] = tf32_round((float)val); }
+        if (stream) __stcs(r + row, val); else r[row] = val;
+        if (r32) screen_store(r32, row, (double)val, a.scr_f16, rsc_new, stream);
     };
 
     for (int i = tid; i < t; i += NT) {
@@ -360,6 +366,7 @@ __device__ __forceinline__ void omp_update_body(const StateArgs& a, const T* __r
         a.resnorm[sig] = nr;
         a.iters[sig] += 1;
         if (flags) a.flags[sig] |= flags;
+        if (a.scr_f16 && changed && !S.deferred) a.rscale[sig] = rsc_new;
         if (!S.deferred) {                                         // else: the last slice of the residual sweep does both
             a.resnorm[sig] = nr;
             if (!(nr >= a.eps)) a.done[sig] = 1;                   // `norm(residual!(P, x)) >= eps || break`
@@ -431,15 +438,18 @@ omp_append_warp_kernel(StateArgs a) {
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, off));
-        const double v0 = (double)m;
+        double v0 = (double)m;
         const bool range_ok = nr >= SCREEN_NORM_MIN && nr <= SCREEN_NORM_MAX && v0 >= 0.0 && v0 <= 3.0e38;
-        const double thr = v0 - 2.0 * a.scr_bound * nr;
+        const double rsc = a.scr_f16 ? a.rscale[sig] : 1.0;
+        const double inv_q = a.scr_f16 ? a.scr_invqA / rsc : 1.0;
+        v0 *= inv_q;
+        const double thr = v0 - 2.0 * (a.scr_f16 ? a.scr_bound * nr + a.scr_abs / rsc : a.scr_bound * nr);
         unsigned inc = 0u;
         bool inw[SCREEN_T * SCREEN_MAX_CHUNKS / 32];
 #pragma unroll
         for (int q = 0; q < SCREEN_T * SCREEN_MAX_CHUNKS / 32; ++q) {
             const int e = lane + 32 * q;
-            inw[q] = idx[q] >= 0 && (double)v[q] >= thr;
+            inw[q] = idx[q] >= 0 && (double)v[q] * inv_q >= thr;
             if (inw[q] && (e % SCREEN_T) == SCREEN_T - 1) inc |= 1u << (e / SCREEN_T);
         }
 #pragma unroll
@@ -596,7 +606,9 @@ omp_residual_slice_kernel(StateArgs a, int k0, int k1, int last) {
     const double* aj = A + (size_t)(a.sel[(size_t)sig * kcap + t] - a.idx_offset) * ld;
     const double gam = a.def_gam[sig];
     double* r = static_cast<double*>(a.R) + (size_t)sig * ld;
-    float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;
+    void* r32 = !a.R32 ? nullptr : a.scr_f16 ? static_cast<void*>(reinterpret_cast<__half*>(a.R32) + (size_t)sig * a.ld32)
+                                             : static_cast<void*>(a.R32 + (size_t)sig * a.ld32);
+    const double rsc_new = a.scr_f16 ? screen_rscale(a.resnorm[sig]) : 1.0;   // resnorm still holds the norm before this update
     double s2r = k0 == 0 ? 0.0 : a.def_s2[(size_t)sig * NT + tid];
     __syncthreads();
     for (int k = k0; k < k1; ++k) {
@@ -624,7 +636,7 @@ omp_residual_slice_kernel(StateArgs a, int k0, int k1, int last) {
                 const double vq = acc[e] + acc1[e];
                 const double rr = (e ? rv.y : rv.x) - gam * vq;
                 __stcs(r + row + e, rr);
-                if (r32) __stcs(r32 + row + e, tf32_round((float)rr));
+                if (r32) screen_store(r32, row + e, rr, a.scr_f16, rsc_new, true);
                 s2r = fma(rr, rr, s2r);
             }
         }
@@ -634,6 +646,7 @@ omp_residual_slice_kernel(StateArgs a, int k0, int k1, int last) {
     if (tid == 0) {
         const double nr = sqrt(nr2);
         a.resnorm[sig] = nr;
+        if (a.scr_f16) a.rscale[sig] = rsc_new;
         if (!(nr >= a.eps)) a.done[sig] = 1;                       // `norm(residual!(P, x)) >= eps || break`
     }
 }
@@ -900,12 +913,18 @@ __global__ void __launch_bounds__(UT) reset_state_kernel(StateArgs a) {
     const T* b = static_cast<const T*>(a.B) + (size_t)sig * ld;
     T* r = static_cast<T*>(a.R) + (size_t)sig * ld;
     double s2 = 0.0;
-    float* r32 = a.R32 ? a.R32 + (size_t)sig * a.ld32 : nullptr;
+    void* r32 = !a.R32 ? nullptr : a.scr_f16 ? static_cast<void*>(reinterpret_cast<__half*>(a.R32) + (size_t)sig * a.ld32)
+                                             : static_cast<void*>(a.R32 + (size_t)sig * a.ld32);
     for (int row = tid; row < ld; row += UT) {
         const T e = b[row]; r[row] = e; s2 += (double)e * (double)e;
-        if (r32) r32[row] = tf32_round((float)e);
+        if (r32 && !a.scr_f16) screen_store(r32, row, (double)e, 0, 1.0, false);
     }
     const double nr = sqrt(block_sum<UT>(s2, red));
+    if (r32 && a.scr_f16) {                                        // the scale needs ||b|| first
+        const double p = screen_rscale(nr);
+        for (int row = tid; row < ld; row += UT) screen_store(r32, row, (double)b[row], 1, p, false);
+        if (tid == 0) a.rscale[sig] = p;
+    }
     if (tid == 0) { a.nnz[sig] = 0; a.iters[sig] = 0; a.done[sig] = 0; a.flags[sig] = 0; a.resnorm[sig] = nr; }
 }
 
@@ -1035,7 +1054,7 @@ cudaError_t launch_omp_update_t(const StateArgs& a, cudaStream_t st, const void*
         omp_update_kernel<T, 256, true><<<a.nsig, 256, smem, st>>>(a, static_cast<const T*>(Acache), t_in_smem, bm);
     } else {
         // cp.async column ring (CSB200_UPD_RING = depth 3 / 4 / 6, 0 = off): FP64, one atom per update, short signals
-        static const int ring_env = [] { const char* r = getenv("CSB200_UPD_RING"); return r ? atoi(r) : UPD_RING_DEFAULT; }();
+        const int ring_env = [] { const char* r = getenv("CSB200_UPD_RING"); return r ? atoi(r) : UPD_RING_DEFAULT; }();
         if constexpr (sizeof(T) == 8) {
             if (ring_env > 0 && !Acache && a.ld <= RING_MAX_SLOTS * UT * 2 && a.grid_cap == 0) {
                 const int depth = ring_env >= 6 ? 6 : (ring_env >= 4 ? 4 : 3);

@@ -234,13 +234,14 @@ int csb200_omp_sharded(csb200_dict* shard, csb200_comm* comm, const void* b, int
  * 1 = DMMA GEMM, 2 = GEMV) or a naive one-thread-per-dot kernel (impl 3); returns, per signal,
  * the top-`s` atoms (index, |c|) in (value desc, index asc) order.  Used by tests/ only. */
 int csb200_debug_corr_topk(csb200_batch* batch, int impl, int64_t s, int64_t* idx, double* val);
-/* One TF32 screening pass (tcgen05 kernel of corr_screen_tf32.cu, the first stage of large batched omp solves) over the
+/* One screening pass (tcgen05 kernel of corr_screen_tf32.cu, the first stage of large batched omp solves; operands in scaled FP16,
+ * or in TF32 with CSB200_SCREEN_F16=0) over the
  * current residuals: val / idx receive [nsig][chunks][8] candidates (|c~| descending per chunk, 0-based atom or -1),
  * *chunks the number of atom chunks, *bound the proven error bound per unit of ||r||: |c~_j - <a_j, r>| <= bound ||r||.
  * val and idx must hold nsig * 16 * 8 entries.  Used by tests/ only. */
 int csb200_debug_screen_pass(csb200_batch* batch, float* val, int32_t* idx, int64_t* chunks, double* bound);
 /* Which path the last csb200_batch_omp / csb200_batch_mp on this batch took (*path: 0 few-signal / GEMV paths, 1 FP64 DMMA loop, 2 FP64
- * DMMA with the two-half overlap, 3 TF32 screening + exact FP64 re-evaluation) and the screening counters since the
+ * DMMA with the two-half overlap, 3 TF32 screening + exact FP64 re-evaluation, 4 the same with scaled FP16 operands) and the screening counters since the
  * last reset: stats3[0] signal-updates decided from screened candidates, [1] candidates re-evaluated in FP64 (windows
  * holding more than one atom), [2] exact scans of all atoms (incomplete list or residual outside the FP32 range). */
 int csb200_batch_screen_stats(csb200_batch* batch, int64_t* path, uint64_t* stats3, int reset);

@@ -16,6 +16,26 @@ def _kappa(M):
     return 1.05 * (2.0 ** -10 + 2.0 ** -22 + M * 2.0 ** -22)
 
 
+def _kappa_f16(M):
+    """Relative bound csb200_debug_screen_pass reports for the FP16 pass: screen_kappa_f16(rows padded to 64) plus the
+    additive term of a residual converted at its own norm (< 2e-3 of the relative one)."""
+    ld16 = -(-M // 64) * 64
+    return (_kappa(ld16) + 1.05 * np.sqrt(ld16) * 2.0 ** -25) * (1.0 + 2e-3)
+
+
+# every variant of the screened omp loop must give the bits of the FP64 DMMA path: operand format of the pass (TF32 / scaled
+# FP16) x update (warp-per-signal append + row-sliced residual sweep / the CTA-per-signal kernel / CTA kernel + deferred sweep)
+VARIANTS = {
+    "tf32-warp": {"CSB200_SCREEN_F16": "0", "CSB200_UPD_WARP": "1", "CSB200_UPD_DEFER": "2"},
+    "f16-warp": {"CSB200_SCREEN_F16": "1", "CSB200_UPD_WARP": "1", "CSB200_UPD_DEFER": "2"},
+    "f16-warp-1slice": {"CSB200_SCREEN_F16": "1", "CSB200_UPD_WARP": "1", "CSB200_UPD_DEFER": "1"},
+    "f16-cta": {"CSB200_SCREEN_F16": "1", "CSB200_UPD_WARP": "0", "CSB200_UPD_DEFER": "0"},
+    "tf32-cta-deferred": {"CSB200_SCREEN_F16": "0", "CSB200_UPD_WARP": "0", "CSB200_UPD_DEFER": "4"},
+    "tf32-cta-ring": {"CSB200_SCREEN_F16": "0", "CSB200_UPD_WARP": "0", "CSB200_UPD_DEFER": "0", "CSB200_UPD_RING": "4",
+                      "CSB200_UPD_HINTS": "3"},
+}
+
+
 def _planted(po, rng, A, B, k, noise=0.0):
     M, N = A.shape
     idx = np.stack([rng.choice(N, size=k, replace=False) for _ in range(B)])
@@ -26,8 +46,10 @@ def _planted(po, rng, A, B, k, noise=0.0):
     return np.asfortranarray(Bm), idx
 
 
+@pytest.mark.parametrize("f16", [0, 1])
 @pytest.mark.parametrize("M,N,B", [(256, 2048, 300), (100, 300, 130), (1024, 8192, 257), (96, 4096 + 40, 128)])
-def test_screening_pass_respects_its_bound_and_lists_the_argmax(cs, po, M, N, B):
+def test_screening_pass_respects_its_bound_and_lists_the_argmax(cs, po, monkeypatch, M, N, B, f16):
+    monkeypatch.setenv("CSB200_SCREEN_F16", str(f16))
     rng = np.random.default_rng(M + N + B)
     A = po.gaussian_dictionary(rng, M, N)
     Bm, _ = _planted(po, rng, A, B, 6, noise=0.01)
@@ -40,7 +62,7 @@ def test_screening_pass_respects_its_bound_and_lists_the_argmax(cs, po, M, N, B)
     nrm = np.linalg.norm(Bm, axis=0)
     nc = val.shape[1]
     chunks = nc // 8
-    assert bound == pytest.approx(_kappa(M) * np.max(np.linalg.norm(A, axis=0)))
+    assert bound == pytest.approx((_kappa_f16(M) if f16 else _kappa(M)) * np.max(np.linalg.norm(A, axis=0)))
     worst = 0.0
     for s in range(B):
         E = bound * nrm[s]
@@ -64,15 +86,17 @@ def test_screening_pass_respects_its_bound_and_lists_the_argmax(cs, po, M, N, B)
         mask[idx[s][ok]] = False
         if mask.any():
             assert C[mask, s].max() <= max(val[s, c * 8:(c + 1) * 8].min() for c in range(chunks)) + E + 1e-300
-    print(f"screening {M}x{N}: worst |c~ - c| / bound = {worst:.3f}")
+    print(f"screening {M}x{N} ({'fp16' if f16 else 'tf32'}): worst |c~ - c| / bound = {worst:.3f}")
     assert worst < 0.5                                           # the Cauchy-Schwarz bound is far from tight on Gaussian data
 
 
-def test_screening_bound_holds_without_cancellation(cs, po):
+@pytest.mark.parametrize("f16", [0, 1])
+def test_screening_bound_holds_without_cancellation(cs, po, monkeypatch, f16):
     """All-positive operands: every product a_i r_i has the same sign, so sum |a_i r_i| = |c| (the Cauchy-Schwarz step of the
     bound is tight when r is parallel to an atom) and an accumulator that truncates would lose up to one ulp per add, all in
     the same direction.  The measured error must still be inside the bound -- this is the case that pins the accumulation
     term M * 2^-22 of screen_kappa(M)."""
+    monkeypatch.setenv("CSB200_SCREEN_F16", str(f16))
     rng = np.random.default_rng(2024)
     M, N, B = 4096, 512, 128
     A = np.abs(rng.standard_normal((M, N))) + 0.05
@@ -125,9 +149,12 @@ def test_screened_mp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch):
         assert np.allclose(x, dense, rtol=RTOL64, atol=RTOL64)
 
 
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("M,N,k,B,noise", [(256, 2048, 8, 4096 + 37, 0.0), (100, 300, 5, 4096 + 130, 5e-3),
                                             (1024, 8192, 32, 4096, 0.0)])
-def test_screened_omp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch, M, N, k, B, noise):
+def test_screened_omp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch, M, N, k, B, noise, variant):
+    for key, value in VARIANTS[variant].items():
+        monkeypatch.setenv(key, value)
     rng = np.random.default_rng(M * 3 + N + k)
     A = po.gaussian_dictionary(rng, M, N)
     Bm, planted = _planted(po, rng, A, B, k, noise)
@@ -140,7 +167,7 @@ def test_screened_omp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch, M
                 batch.upload(Bm)
                 batch.omp(k, 1e-9)
                 st = batch.screen_stats(reset=True)
-                assert st["path_id"] == (3 if mode == "1" else 2 if B >= 8192 else 1), st
+                assert st["path_id"] == ((4 if VARIANTS[variant]["CSB200_SCREEN_F16"] == "1" else 3) if mode == "1" else 2 if B >= 8192 else 1), st
                 if mode == "1":
                     assert st["signal_updates"] > 0 and st["exact_scans"] < 0.01 * st["signal_updates"], st
                     print("screen stats", st)
@@ -183,7 +210,7 @@ def test_overlapped_screening_schedule_is_bit_identical(cs, po, monkeypatch, par
                 batch.omp(k, 1e-9)
                 ms, launches, other = batch.corr_time()
                 batch.profile(False)
-                assert launches == p * k and ms > 0 and batch.screen_stats()["path_id"] == 3
+                assert launches == p * k and ms > 0 and batch.screen_stats()["path_id"] in (3, 4)
                 out[p] = batch.download(k) + (batch.residual(),)
     for a, b in zip(out[1], out[parts]):
         assert np.array_equal(a, b)
@@ -195,11 +222,14 @@ def test_overlapped_screening_schedule_is_bit_identical(cs, po, monkeypatch, par
         assert sel[s, :int(nnz[s])].tolist() == t.order() and int(its[s]) == t.iterations
 
 
-def test_screened_omp_ties_zero_signals_and_out_of_range_norms(cs, po, monkeypatch):
+@pytest.mark.parametrize("variant", ["tf32-warp", "f16-warp", "f16-cta"])
+def test_screened_omp_ties_zero_signals_and_out_of_range_norms(cs, po, monkeypatch, variant):
     """Duplicate atoms (bit-identical |c|: the lower index must win, KAT-4), an all-zero signal (arg-max of zeros is atom 0,
     which is appended with coefficient 0: KAT-6), signals whose norm is outside the range the FP32 operands cover (exact
     scan) -- all through the screening path."""
     monkeypatch.setenv("CSB200_SCREEN", "1")
+    for key, value in VARIANTS[variant].items():
+        monkeypatch.setenv(key, value)
     rng = np.random.default_rng(77)
     M, N, k, B = 64, 512, 3, 600                                # > 512 signals: not the small-dictionary whole-solve kernel
     A = po.gaussian_dictionary(rng, M, N)
@@ -215,7 +245,7 @@ def test_screened_omp_ties_zero_signals_and_out_of_range_norms(cs, po, monkeypat
         batch.omp(k, 0.0)
         st = batch.screen_stats()
         sel, coef, nnz, res, its = batch.download(k)
-    assert st["path_id"] == 3 and st["exact_scans"] >= 3
+    assert st["path_id"] == (4 if VARIANTS[variant]["CSB200_SCREEN_F16"] == "1" else 3) and st["exact_scans"] >= 3
     assert sel[0, 0] == 17 and sel[0, 1] == 300
     for s in (0, 1, 2, 3, 4, 100, B - 1):
         t = po.Trace()

@@ -16,8 +16,8 @@ except Exception as e:
     print(tag, "FAILED", e, open(f"gpurun_out/upd_{tag}.err").read()[-600:])
 PY
 }
-run d2w
-run d4w CSB200_UPD_DEFER=4
-run base CSB200_UPD_DEFER=0
-run parts2 CSB200_SCREEN_PARTS=2
-(timeout 900 python -m pytest tests/test_gpu_screen.py tests/test_gpu_parity.py tests/test_gpu_fuzz.py -m gpu -x -q 2>&1 | tail -4)
+(timeout 600 python -m pytest tests/test_gpu_screen.py -m gpu -x -q -s 2>&1 | grep -v 'screen stats' | tail -22)
+run f16d2 CSB200_SCREEN_F16=1
+run f16d4 CSB200_SCREEN_F16=1 CSB200_UPD_DEFER=4
+run f16d1 CSB200_SCREEN_F16=1 CSB200_UPD_DEFER=1
+run f16s3 CSB200_SCREEN_F16=1 CSB200_SCREEN_STAGES=3
