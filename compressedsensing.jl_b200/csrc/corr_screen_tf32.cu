@@ -37,8 +37,13 @@ constexpr int ST_A_BYTES = ST_SIG * ST_KB * 4;     // 16 KiB of R32
 constexpr int ST_B_BYTES = ST_ATOM * ST_KB * 4;    // 32 KiB of A32
 constexpr int ST_STAGE_BYTES = ST_A_BYTES + ST_B_BYTES;
 constexpr int ST_BAR_BYTES = 128;
-constexpr int st_smem_bytes(int stages) { return stages * ST_STAGE_BYTES + ST_BAR_BYTES + 1024 /* alignment slack */; }
-constexpr int ST_THREADS = 192;
+// Several epilogue warps per TMEM lane quadrant (each scans its share of a tile's 256 columns); at the end of a work unit the
+// others hand their top-SCREEN_T to the first through this area: [quadrant][warp - 1][value | index][slot][lane]
+constexpr int ST_EPI_WARPS = 8;                                    // 16 measured the same (0.946 vs 0.955 ms per pass)
+constexpr int ST_EPI_PER_QUAD = ST_EPI_WARPS / 4;                  // warps sharing a quadrant split the tile's columns evenly
+constexpr int ST_MERGE_BYTES = 4 * (ST_EPI_PER_QUAD - 1) * 2 * SCREEN_T * 32 * 4;
+constexpr int st_smem_bytes(int stages) { return stages * ST_STAGE_BYTES + ST_BAR_BYTES + ST_MERGE_BYTES + 1024 /* alignment slack */; }
+constexpr int ST_THREADS = 64 + ST_EPI_WARPS * 32;
 constexpr int ST_TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -112,18 +117,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Sorted insertion into the running top-SCREEN_T (descending; a later, i.e. higher-indexed, equal value stays behind).
-__device__ __forceinline__ void top_insert(float (&v)[SCREEN_T], int (&id)[SCREEN_T], float x, int idx) {
-    v[SCREEN_T - 1] = x; id[SCREEN_T - 1] = idx;
+// The epilogue's running top-SCREEN_T as an UNSORTED set plus its minimum.  A warp executes the insertion whenever ANY of its 32
+// signals needs it (~60 times per 256-atom tile on average, every element in the first tile of a unit); a sorted insertion
+// is a dependent chain of 7 compare-exchange steps (~225 cycles), which made the epilogue, not the MMAs, the critical
+// path once the FP16 pass halved the MMA time.  Replacing the minimum is 8 independent selects and a 3-level min tree; the
+// list is sorted once per work unit (top_sort).  Which of several EQUAL minima is evicted is immaterial to the solve: an
+// equal value left behind sits in the last sorted slot, and a last slot inside the window means an exact scan (screen_select).
+__device__ __forceinline__ void top_replace(float (&v)[SCREEN_T], int (&id)[SCREEN_T], float& vmin, float x, int idx) {
+    bool done = false;
 #pragma unroll
-    for (int p = SCREEN_T - 1; p > 0; --p) {
-        const bool up = v[p] > v[p - 1];
-        const float tv = up ? v[p - 1] : v[p];
-        const int ti = up ? id[p - 1] : id[p];
-        v[p - 1] = up ? v[p] : v[p - 1];
-        id[p - 1] = up ? id[p] : id[p - 1];
-        v[p] = tv; id[p] = ti;
+    for (int p = 0; p < SCREEN_T; ++p) {
+        const bool hit = !done && v[p] == vmin;
+        v[p] = hit ? x : v[p];
+        id[p] = hit ? idx : id[p];
+        done = done || hit;
     }
+    static_assert(SCREEN_T == 8, "min tree written for 8 slots");
+    vmin = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), fminf(fminf(v[4], v[5]), fminf(v[6], v[7])));
+}
+// descending by value, lower atom index first among equal values (the order the sorted insertion produced)
+__device__ __forceinline__ void top_sort(float (&v)[SCREEN_T], int (&id)[SCREEN_T]) {
+    auto cx = [&](int a, int b) {                                  // after: slot a holds the entry that comes first
+        const bool swap = v[b] > v[a] || (v[b] == v[a] && (unsigned)id[b] < (unsigned)id[a]);
+        const float tv = swap ? v[a] : v[b]; const int ti = swap ? id[a] : id[b];
+        v[a] = swap ? v[b] : v[a]; id[a] = swap ? id[b] : id[a];
+        v[b] = tv; id[b] = ti;
+    };
+    // 19-comparator sorting network for 8 inputs
+    cx(0, 1); cx(2, 3); cx(4, 5); cx(6, 7);
+    cx(0, 2); cx(1, 3); cx(4, 6); cx(5, 7);
+    cx(1, 2); cx(5, 6); cx(0, 4); cx(3, 7);
+    cx(1, 5); cx(2, 6);
+    cx(1, 4); cx(3, 6);
+    cx(2, 4); cx(3, 5);
+    cx(3, 4);
 }
 
 // F16: the operands are FP16 (residuals scaled per signal, dictionary scaled as a whole, both by powers of two: api.cu) -- a
@@ -147,7 +174,7 @@ corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < ST_STAGES; ++s) { bar_init(bar_full + s * 8, 1); bar_init(bar_empty + s * 8, 1); }
-        for (int s = 0; s < 2; ++s) { bar_init(bar_tfull + s * 8, 1); bar_init(bar_tempty + s * 8, 4); }
+        for (int s = 0; s < 2; ++s) { bar_init(bar_tfull + s * 8, 1); bar_init(bar_tempty + s * 8, ST_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapR) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -212,13 +239,21 @@ corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_c
             }
         }
     } else {                                                       // ---- epilogue warps: TMEM lane quadrant = warp % 4
-        const int quad = warp & 3;
+        // (a warp may only touch the 32 TMEM lanes of its quadrant.)  Warps 2-5 scan the first COLS_PER_WARP columns of every tile,
+        // warps 6-9 the next, ...: the scan -- one compare and one (rarely taken, but warp-divergent) branch per element -- is the
+        // critical path of the FP16 pass (ncu source view: ~80 % of the samples in these warps, tensor pipe 41 % active with
+        // four of them: 1.29 ms per pass; eight: 0.96 ms), so it is spread over ST_EPI_PER_QUAD warps per scheduler.
+        const int quad = warp & 3, half = (warp - 2) >> 2;             // `half`: which share of the columns (0 .. ST_EPI_PER_QUAD - 1)
+        constexpr int COLS_PER_WARP = ST_ATOM / ST_EPI_PER_QUAD;
+        float* mrg_base = reinterpret_cast<float*>(sm + ST_STAGES * ST_STAGE_BYTES + ST_BAR_BYTES) +
+                          quad * ((ST_EPI_PER_QUAD - 1) * 2 * SCREEN_T * 32);
         int acc = 0; uint32_t acc_phase = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int sig_tile = u / chunks, chunk = u - sig_tile * chunks;
             const int t0 = chunk * tiles_per_chunk;
             const int t1 = t0 + tiles_per_chunk < tilesN ? t0 + tiles_per_chunk : tilesN;
             float v[SCREEN_T]; int id[SCREEN_T];
+            float vmin = -1.0f;
 #pragma unroll
             for (int p = 0; p < SCREEN_T; ++p) { v[p] = -1.0f; id[p] = -1; }
             for (int t = t0; t < t1; ++t) {
@@ -226,7 +261,7 @@ corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_c
                 tc_fence_after();
                 const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ST_ATOM);
 #pragma unroll 1
-                for (int c = 0; c < ST_ATOM / 32; ++c) {
+                for (int c = half * (COLS_PER_WARP / 32); c < (half + 1) * (COLS_PER_WARP / 32); ++c) {
                     uint32_t r[32];
                     tmem_ld32(trow + (uint32_t)(c * 32), r);
                     tmem_ld_wait();
@@ -234,7 +269,7 @@ corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_c
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
                         const float x = fabsf(__uint_as_float(r[e]));
-                        if (x > v[SCREEN_T - 1] && base + e < N) top_insert(v, id, x, base + e + idx_offset);
+                        if (x > vmin && base + e < N) top_replace(v, id, vmin, x, base + e + idx_offset);
                     }
                 }
                 tc_fence_before();
@@ -242,6 +277,30 @@ corr_screen_tf32_kernel(const __grid_constant__ CUtensorMap mapR, const __grid_c
                 if (lane == 0) bar_arrive(bar_tempty + acc * 8);
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
             }
+            // merge the two column halves: the second warp of the quadrant publishes its set, the first absorbs it
+            if (half > 0) {
+                float* mrg_v = mrg_base + (half - 1) * (2 * SCREEN_T * 32);
+                int* mrg_i = reinterpret_cast<int*>(mrg_v + SCREEN_T * 32);
+#pragma unroll
+                for (int p = 0; p < SCREEN_T; ++p) { mrg_v[p * 32 + lane] = v[p]; mrg_i[p * 32 + lane] = id[p]; }
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * ST_EPI_PER_QUAD) : "memory");      // published
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * ST_EPI_PER_QUAD) : "memory");      // consumed: the area may be rewritten
+                continue;
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * ST_EPI_PER_QUAD) : "memory");
+#pragma unroll 1
+            for (int w = 0; w < ST_EPI_PER_QUAD - 1; ++w) {
+                const float* mrg_v = mrg_base + w * (2 * SCREEN_T * 32);
+                const int* mrg_i = reinterpret_cast<const int*>(mrg_v + SCREEN_T * 32);
+#pragma unroll
+                for (int p = 0; p < SCREEN_T; ++p) {
+                    const float x = mrg_v[p * 32 + lane];
+                    const int xi = mrg_i[p * 32 + lane];
+                    if (x > vmin) top_replace(v, id, vmin, x, xi);
+                }
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * ST_EPI_PER_QUAD) : "memory");
+            top_sort(v, id);
             const int sig = sig_tile * ST_SIG + quad * 32 + lane;
             if (sig < nsig) {
                 float4* ov = reinterpret_cast<float4*>(cval + ((size_t)sig * chunks + chunk) * SCREEN_T);

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 run() {
   tag=$1; shift
-  env "$@" timeout 300 python bench.py --steps 3 --warmup 2 --secondary none --cpu-signals 0 --e2e-steps 1 --fp64-steps 0 > gpurun_out/upd_$tag.json 2> gpurun_out/upd_$tag.err
+  env "$@" timeout 300 python bench.py --steps 3 --warmup 2 --secondary none --cpu-signals 0 --e2e-steps 3 --fp64-steps 0 > gpurun_out/upd_$tag.json 2> gpurun_out/upd_$tag.err
   python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]
@@ -16,8 +16,9 @@ except Exception as e:
     print(tag, "FAILED", e, open(f"gpurun_out/upd_{tag}.err").read()[-600:])
 PY
 }
-(timeout 600 python -m pytest tests/test_gpu_screen.py -m gpu -x -q -s 2>&1 | grep -v 'screen stats' | tail -22)
-run f16d2 CSB200_SCREEN_F16=1
-run f16d4 CSB200_SCREEN_F16=1 CSB200_UPD_DEFER=4
-run f16d1 CSB200_SCREEN_F16=1 CSB200_UPD_DEFER=1
-run f16s3 CSB200_SCREEN_F16=1 CSB200_SCREEN_STAGES=3
+run def
+run p8192 CSB200_PIPE_CHUNK=8192
+run p21888 CSB200_PIPE_CHUNK=21888
+run p32768 CSB200_PIPE_CHUNK=32768
+run p16384c4 CSB200_PIPE_CHUNK=16384 CSB200_SCREEN_CHUNKS=4
+run p32768c4 CSB200_PIPE_CHUNK=32768 CSB200_SCREEN_CHUNKS=4
