@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <new>
 #include <string>
 #include <thread>
@@ -2094,8 +2095,20 @@ static int pipe_upload_async(csb200_batch* w, const void* src, int64_t ldb, int6
 }
 static size_t caller_esize(const csb200_dict* d) { return d->dtype == CSB200_F32 ? 4 : 8; }
 
+static double host_ms_now() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static bool pipe_debug() { static const bool v = [] { const char* e = getenv("CSB200_PIPE_DEBUG"); return e && e[0] == '1'; }(); return v; }
+
 static int pipe_complete(csb200_batch* w, int64_t stride, const PipeOut& o, int64_t s0) {
+    const double t0 = pipe_debug() ? host_ms_now() : 0.0;
     CU_TRY(cudaStreamSynchronize(w->stream));
+    if (pipe_debug()) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, w->ev_solve0, w->ev_solve1);
+        fprintf(stderr, "[pipe] chunk at signal %lld (%lld signals): waited %.2f ms for it, its solve took %.2f ms on the device, host clock %.2f\n",
+                (long long)s0, (long long)w->nsig, host_ms_now() - t0, ms, host_ms_now());
+    }
     if (*reinterpret_cast<const int*>(w->host_stage + w->state_result_bytes)) return CSB200_ERR_NONFINITE_INPUT;
     const unsigned char* p = w->host_stage;
     auto at = [&](const void* dev) { return p + ((const unsigned char*)dev - w->state_blk); };
@@ -2112,10 +2125,30 @@ static int one_shot_pipelined(csb200_dict* d, const void* Bmat, int64_t ldb, int
     int rc = set_device(d);
     if (rc) return rc;
     const int64_t cap = kcap < 1 ? 1 : kcap;
-    const int64_t PIPE_CHUNK = pipe_chunk_signals(d);
+    // Chunk schedule.  Every chunk pays ~0.1 ms per update! in launch gaps and partial waves whatever its size, so few large
+    // chunks solve fastest; but the first chunk's upload is the one copy nothing hides.  Hence a SHORT first chunk (half the
+    // base size Q) and then equal chunks of about 1.5 Q.  Measured at config 2 (CSB200_PIPE_DEBUG=1): four uniform chunks
+    // 22.1 + 22.1 + 22.3 + 13.4 ms of solves against 69.9 ms for the undivided batch.  CSB200_PIPE_CHUNK forces uniform chunks.
+    const int64_t Q = pipe_chunk_signals(d);
+    const bool uniform = getenv("CSB200_PIPE_CHUNK") != nullptr || nsig <= 2 * Q;
+    std::vector<int64_t> c_start, c_size;
+    if (uniform) {
+        for (int64_t s0 = 0; s0 < nsig; s0 += Q) { c_start.push_back(s0); c_size.push_back(nsig - s0 < Q ? nsig - s0 : Q); }
+    } else {
+        const int64_t first = Q / 2 / 128 * 128 >= 1024 ? Q / 2 / 128 * 128 : Q;
+        const int64_t big = Q + first;
+        const int64_t rest = nsig - first, nrest = (rest + big - 1) / big;
+        const int64_t each = ((rest + nrest - 1) / nrest + first - 1) / first * first;      // whole multiples of the wave unit
+        c_start.push_back(0); c_size.push_back(first);
+        for (int64_t s0 = first; s0 < nsig; s0 += each) { c_start.push_back(s0); c_size.push_back(nsig - s0 < each ? nsig - s0 : each); }
+    }
+    int64_t PIPE_CHUNK = 0;
+    for (int64_t v : c_size) PIPE_CHUNK = v > PIPE_CHUNK ? v : PIPE_CHUNK;
+    if (!uniform && PIPE_CHUNK < Q + Q / 2) PIPE_CHUNK = Q + Q / 2;    // one workspace size for every large call
+    if (uniform && PIPE_CHUNK < Q && nsig > Q) PIPE_CHUNK = Q;
     for (int i = 0; i < 2; ++i) {
         csb200_batch*& w = d->pipe_ws[i];
-        if (w && (w->cap_sig != PIPE_CHUNK || w->kcap < cap)) { csb200_batch_destroy(w); w = nullptr; }
+        if (w && (w->cap_sig < PIPE_CHUNK || w->cap_sig > 2 * PIPE_CHUNK || w->kcap < cap)) { csb200_batch_destroy(w); w = nullptr; }
         if (!w) {
             if ((rc = csb200_batch_create(d, PIPE_CHUNK, cap, &w))) return rc;
             if (w->host_stage_bytes < w->state_result_bytes + 16) {      // pinned landing zone: result block + input flag
@@ -2127,7 +2160,7 @@ static int one_shot_pipelined(csb200_dict* d, const void* Bmat, int64_t ldb, int
         }
     }
     const size_t es = d->esize();
-    const int64_t nchunks = (nsig + PIPE_CHUNK - 1) / PIPE_CHUNK;
+    const int64_t nchunks = (int64_t)c_start.size();
     csb200_batch* prev = nullptr;               // the solves run one after the other; only copies overlap them
     int64_t started[2] = {-1, -1};              // first signal of the chunk in flight on each workspace
     int first_err = CSB200_OK;
@@ -2139,7 +2172,7 @@ static int one_shot_pipelined(csb200_dict* d, const void* Bmat, int64_t ldb, int
             if (rc && !first_err) first_err = rc;
         }
         if (first_err) break;
-        const int64_t s0 = c * PIPE_CHUNK, nc = nsig - s0 < PIPE_CHUNK ? nsig - s0 : PIPE_CHUNK;
+        const int64_t s0 = c_start[(size_t)c], nc = c_size[(size_t)c];
         rc = pipe_upload_async(w, (const char*)Bmat + (size_t)s0 * ldb * caller_esize(d), ldb, nc);
         if (!rc && prev) {
             cudaError_t e = cudaStreamWaitEvent(w->stream, prev->ev_solve1, 0);
@@ -2156,6 +2189,7 @@ static int one_shot_pipelined(csb200_dict* d, const void* Bmat, int64_t ldb, int
             if (e != cudaSuccess) rc = fail_cuda(e, "result download");
         }
         if (rc) { first_err = rc; cudaStreamSynchronize(w->stream); break; }
+        if (pipe_debug()) fprintf(stderr, "[pipe] chunk %lld enqueued, host clock %.2f\n", (long long)c, host_ms_now());
         started[c & 1] = s0;
         prev = w;
     }

@@ -17,8 +17,6 @@ except Exception as e:
 PY
 }
 run def
-run p8192 CSB200_PIPE_CHUNK=8192
-run p21888 CSB200_PIPE_CHUNK=21888
-run p32768 CSB200_PIPE_CHUNK=32768
-run p16384c4 CSB200_PIPE_CHUNK=16384 CSB200_SCREEN_CHUNKS=4
-run p32768c4 CSB200_PIPE_CHUNK=32768 CSB200_SCREEN_CHUNKS=4
+run p18944 CSB200_PIPE_CHUNK=18944
+run d4 CSB200_UPD_DEFER=4
+(timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_screen.py -m gpu -x -q 2>&1 | tail -3)
