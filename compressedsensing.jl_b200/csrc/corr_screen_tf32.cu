@@ -11,16 +11,19 @@
 // tie-break; a list that may be incomplete (its last slot still inside the window, a residual outside the FP32 range)
 // falls back to an exact FP64 scan of all atoms for that signal.  The selected support is therefore the FP64 one.
 //
-// sm_100a design (one CTA per SM, 192 threads, persistent over work units = 128 signals x one atom chunk):
-//   warp 0   TMA producer: per K-block of 32 floats one box {32 x 128 signals} of R32 and one box {32 x 256 atoms} of A32
-//            (SWIZZLE_128B, K-major for both operands: signals and atoms are columns of column-major matrices), 4-stage
-//            full/empty mbarrier ring of 48 KiB stages running ahead across tile and unit boundaries;
-//   warp 1   one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128 signals, N = 256 atoms, K = 8) four
-//            times per stage and commits the stage back to the producer; the 128 x 256 FP32 accumulator lives in TMEM,
-//            double-buffered (2 x 256 of the 512 columns) so the epilogue of tile i runs under the MMAs of tile i + 1;
-//   warps 2-5  epilogue: a TMEM lane IS a signal, so after tcgen05.ld.32x32b every thread scans the atoms of ITS signal
-//            in its own registers -- no shuffles -- and keeps a sorted top-SCREEN_T (value, atom) across all tiles of
-//            the unit; one 64-byte record per (signal, chunk) leaves the SM.  The N x B matrix is never written.
+// sm_100a design (one CTA per SM, 320 threads, persistent over work units = 128 signals x one atom chunk):
+//   warp 0   TMA producer: per K-block of 128 bytes (32 TF32 floats or 64 scaled FP16 halves) one box {K-block x 128 signals} of the
+//            residual copy and one box {K-block x 256 atoms} of the dictionary copy (SWIZZLE_128B, K-major for both operands:
+//            signals and atoms are columns of column-major matrices), 4-stage full/empty mbarrier ring of 48 KiB stages
+//            running ahead across tile and unit boundaries;
+//   warp 1   one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (or kind::tf32) (M = 128 signals, N = 256 atoms,
+//            32 bytes of K) four times per stage and commits the stage back to the producer; the 128 x 256 FP32 accumulator
+//            lives in TMEM, double-buffered (2 x 256 of the 512 columns) so the epilogue of tile i runs under the MMAs of tile i + 1;
+//   warps 2-9  epilogue, two warps per TMEM lane quadrant (128 columns of the tile each): a TMEM lane IS a signal, so after
+//            tcgen05.ld.32x32b every thread scans the atoms of ITS signal in its own registers -- no shuffles -- and keeps
+//            the SCREEN_T largest (value, atom) across all tiles of the unit as an unsorted set + its minimum; at the end of
+//            the unit the two warps of a quadrant merge through shared memory, sort, and one 64-byte record per
+//            (signal, chunk) leaves the SM.  The N x B matrix is never written.
 #include "common.cuh"
 #include <cstdlib>
 
