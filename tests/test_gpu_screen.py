@@ -151,7 +151,9 @@ def test_screened_mp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch):
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("M,N,k,B,noise", [(256, 2048, 8, 4096 + 37, 0.0), (100, 300, 5, 4096 + 130, 5e-3),
-                                            (1024, 8192, 32, 4096, 0.0)])
+                                            (1024, 8192, 32, 4096, 0.0),
+                                            (1500, 3000, 6, 4096 + 3, 1e-3),      # rows not a multiple of 256: ragged last row slot of the sweep
+                                            (256, 2048, 40, 4096 + 11, 5e-3)])    # support capacity > 32: no warp-per-signal append
 def test_screened_omp_equals_the_dmma_path_and_the_oracle(cs, po, monkeypatch, M, N, k, B, noise, variant):
     for key, value in VARIANTS[variant].items():
         monkeypatch.setenv(key, value)
