@@ -365,27 +365,34 @@ __global__ void __launch_bounds__(256) to_f16_kernel(const double* __restrict__ 
 
 }  // namespace
 
-// Atom chunks per signal tile; a work unit is (128 signals) x (one chunk).  Two opposing effects, both measured at the
-// headline dictionary (profiles/screen_r02.md): (1) few long units are fastest per pass (2 chunks: 1.53 ms, 4: 1.68, 8: 1.85 ms
-// for 65 536 signals), but (2) a grid of about ONE wave of long units is fragile -- with 148 units of 32 tiles each, one SM
-// still busy with the previous kernel's tail (or another stream's kernel) delays its unit by a whole pass: the 18 944-signal
-// chunks of the pipelined one-shot path ran 30 % slower than 9 472-signal ones.  Rule: the smallest chunk count that gives at
-// least SCREEN_MIN_WAVES waves of units (each still >= 1 tile), else the largest possible.
+// Atom chunks per signal tile; a work unit is (128 signals) x (one chunk), dealt round-robin to one persistent CTA per SM.
+// Cost model, fitted to config 2 (profiles/screen_f16_r02.md): a unit costs its tiles plus ~1.3 tiles' worth of overhead (the
+// insertion storm while the unit's top-8 fills up, merge, sort, store), and the pass takes ceil(units / SMs) rounds of
+// units.  65 536 signals: 2 chunks, 7 rounds of 16 tiles (0.95 ms); 8192 signals (the strong-scaling share of one of 8
+// GPUs): the earlier rule ("at least 4 rounds") took 16 chunks, 7 rounds of 2-tile units, 199 us, where 4 chunks (2 rounds
+// of 8-tile units) model at 160 us.  One chunk is never taken when two are possible: with only 8 candidates per signal
+// the update falls back to exact scans more often (measured: +0.25 ms per update!).  A single round is avoided when two
+// rounds cost within 10 % of it: with one round, an SM that is briefly busy with another stream's kernel (the next chunk's
+// input check in the pipelined one-shot call) delays the whole pass by a unit.
 int screen_chunks_for(int N, int nsig, int num_sms) {
-    constexpr int SCREEN_MIN_WAVES = 4;
     const int tilesN = (N + ST_ATOM - 1) / ST_ATOM;
     const long long sig_tiles = (nsig + ST_SIG - 1) / ST_SIG;
     static const int forced = [] { const char* e = getenv("CSB200_SCREEN_CHUNKS"); return e ? atoi(e) : 0; }();
-    int best = 1;
+    constexpr double UNIT_OVERHEAD_TILES = 1.3;
+    int best = 1, best2 = 0;                                       // best overall, best among the choices with >= 2 rounds
+    double cost = 1e300, cost2 = 1e300;
     for (int c = 1; c <= SCREEN_MAX_CHUNKS; c *= 2) {
         if (c > tilesN) break;
         const int tpc = (tilesN + c - 1) / c;
         if ((tilesN + tpc - 1) / tpc != c) continue;               // a chunk count that would leave an empty chunk
         if (forced == c) return c;
-        best = c;
-        if (c >= 2 && sig_tiles * c >= (long long)SCREEN_MIN_WAVES * num_sms) break;
+        if (c == 1 && tilesN >= 2) continue;
+        const long long rounds = (sig_tiles * c + num_sms - 1) / num_sms;
+        const double t = (double)rounds * (tpc + UNIT_OVERHEAD_TILES);
+        if (t < cost) { cost = t; best = c; }
+        if (rounds >= 2 && t < cost2) { cost2 = t; best2 = c; }
     }
-    return best;
+    return best2 && cost2 <= 1.10 * cost ? best2 : best;
 }
 
 int screen_chunk_atoms(int N, int chunks) {
