@@ -418,7 +418,7 @@ omp_append_warp_kernel(StateArgs a) {
     double zsl = 0.0;
     if (lane < t) { ssel = a.sel[(size_t)sig * kcap + lane]; zsl = a.z[(size_t)sig * kcap + lane]; }
     for (int c = 0; c < t; ++c)
-        if (lane <= c) W.T[lane + c * W_LDT] = Tg[lane + (size_t)c * kcap];
+        if (lane <= c) W.T[lane + c * W_LDT] = __ldcs(Tg + lane + (size_t)c * kcap);   // streamed once per update!: do not displace the dictionary
     W.zs[lane] = zsl;
     bool changed = false;
     int stat_n = -1;                                               // atoms re-evaluated in FP64 (-1: no selection ran)
@@ -489,7 +489,7 @@ omp_append_warp_kernel(StateArgs a) {
                     const int row = row0 + lane + 32 * w;
                     if (row < ld) {
                         const double e = aj[row];
-                        s2[w] = fma(e, e, s2[w]); sab[w] = fma(e, b[row], sab[w]);
+                        s2[w] = fma(e, e, s2[w]); sab[w] = fma(e, __ldcs(b + row), sab[w]);
                     }
                 }
             }
@@ -551,10 +551,10 @@ omp_append_warp_kernel(StateArgs a) {
             const double irho = 1.0 / rho;
             if (lane < t) {
                 const double e = -yl * irho;
-                Tg[lane + (size_t)t * kcap] = e;
+                __stcs(Tg + lane + (size_t)t * kcap, e);
                 W.T[lane + t * W_LDT] = e;
             }
-            if (lane == t) { Tg[t + (size_t)t * kcap] = irho; W.T[t + t * W_LDT] = irho; W.zs[t] = zt; ssel = j; zsl = zt; }
+            if (lane == t) { __stcs(Tg + t + (size_t)t * kcap, irho); W.T[t + t * W_LDT] = irho; W.zs[t] = zt; ssel = j; zsl = zt; }
             ++t;
             changed = true;
             __syncwarp();

@@ -17,6 +17,4 @@ except Exception as e:
 PY
 }
 run def
-run p18944 CSB200_PIPE_CHUNK=18944
-run d4 CSB200_UPD_DEFER=4
-(timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_screen.py -m gpu -x -q 2>&1 | tail -3)
+run def2
