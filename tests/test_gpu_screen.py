@@ -1,7 +1,8 @@
-"""GPU tests (`-m gpu`, B200) of the TF32 screening path of large batched omp solves: the tcgen05 screening pass
-(corr_screen_tf32.cu) must respect its proven error bound, its candidate lists must contain the FP64 arg-max, and the
-whole solve (screening + exact FP64 re-evaluation, update.cu screen_select) must select the same supports as the FP64
-DMMA path and the CPU oracle -- bit-exact selection order, coefficients within 1e-10
+"""GPU tests (`-m gpu`, B200) of the screening path of large batched omp solves: the tcgen05 screening pass
+(corr_screen_tf32.cu; operands in TF32 or in FP16 scaled by powers of two) must respect its proven error bound, its candidate
+lists must contain the FP64 arg-max, and the whole solve (screening + exact FP64 re-evaluation, update.cu screen_select /
+omp_append_warp_kernel / omp_residual_slice_kernel) must select the same supports as the FP64 DMMA path and the CPU oracle --
+bit-exact selection order, coefficients within 1e-10 -- in every combination of pass format and update variant
 (/root/reference/src/matchingpursuit.jl:62-70, 181-185)."""
 import numpy as np
 import pytest
