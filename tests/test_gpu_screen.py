@@ -257,3 +257,36 @@ def test_screened_omp_ties_zero_signals_and_out_of_range_norms(cs, po, monkeypat
         if s in (0, 1):          # once the residual is at rounding level the arg-max is ill-posed: compare the well-posed prefix
             n = min(n, 2 if s == 0 else 1)
         assert sel[s, :n].tolist() == t.order()[:n], s
+
+
+@pytest.mark.parametrize("variant", ["tf32-warp", "f16-warp"])
+def test_screened_omp_on_unnormalised_atoms(cs, po, monkeypatch, variant):
+    """The reference does not require unit-norm atoms (`argmaxinner!` compares raw |<a_j, r>|, src/matchingpursuit.jl:181-185).
+    Column norms spread over 0.05 .. 20: the bound scales with the LARGEST norm, so the windows of signals built from short atoms
+    hold many candidates -- the decision must still be the FP64 one, bit for bit, and the oracle's."""
+    monkeypatch.setenv("CSB200_SCREEN", "1")
+    for key, value in VARIANTS[variant].items():
+        monkeypatch.setenv(key, value)
+    rng = np.random.default_rng(4242)
+    M, N, k, B = 200, 1500, 6, 4096 + 9
+    A = po.gaussian_dictionary(rng, M, N) * np.exp(rng.uniform(np.log(0.05), np.log(20.0), size=N))
+    A = np.asfortranarray(A)
+    Bm, _ = _planted(po, rng, A, B, k, noise=1e-3)
+    out = {}
+    with cs.Dictionary(A) as D:
+        for mode in ("0", "1"):
+            monkeypatch.setenv("CSB200_SCREEN", mode)
+            with cs.Batch(D, B, k) as batch:
+                batch.upload(Bm)
+                batch.omp(k, 1e-9)
+                out[mode] = batch.download(k) + (batch.residual(),)
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b)
+    sel, coef, nnz, res, its, R = out["1"]
+    for s in (0, 1, 2, 3, 500, B - 1):
+        t = po.Trace()
+        ref = po.omp(A, Bm[:, s], k, eps=1e-9, trace=t)
+        n = int(nnz[s])
+        assert sel[s, :n].tolist() == t.order() and int(its[s]) == t.iterations
+        o = np.argsort(sel[s, :n], kind="stable")
+        assert np.allclose(coef[s, :n][o], ref.nzval, rtol=RTOL64, atol=RTOL64 * max(1.0, np.max(np.abs(ref.nzval))))
