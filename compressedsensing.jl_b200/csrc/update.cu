@@ -389,10 +389,14 @@ constexpr int WK = 32;                                             // largest su
 constexpr int W_LDT = WK | 1;
 struct WarpSmem {
     double T[WK * W_LDT];
-    double g[WK], hh[WK], zs[WK];
-    int list[SCREEN_T * SCREEN_MAX_CHUNKS];
+    union {                                                        // the candidate list is dead before g / hh are written
+        struct { double g[WK], hh[WK]; };
+        int list[SCREEN_T * SCREEN_MAX_CHUNKS];
+    };
+    double zs[WK];
 };
-__global__ void __launch_bounds__(WPB * 32, 5)
+static_assert(sizeof(int) * SCREEN_T * SCREEN_MAX_CHUNKS <= 2 * WK * sizeof(double), "candidate list must fit under g + hh");
+__global__ void __launch_bounds__(WPB * 32, 6)
 omp_append_warp_kernel(StateArgs a) {
     extern __shared__ double dsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
