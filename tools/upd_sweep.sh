@@ -1,6 +1,8 @@
 #!/bin/bash
-# omp_update_kernel variants at the headline shape (under gpurun): cp.async column ring depth x cache hints.
-# The result digest must be the same on every line (the variants are bit-identical by construction).
+# Variants of the screened omp loop at the headline shape (under gpurun, one B200): pass operand format x update variant x schedule.
+# profiles/upd_sweep_r02.log was collected with successive versions of this script during round 2 (each "call" there is one gpurun
+# invocation of it with that call's set of `run` lines).  The result digest must be the same on every line: all variants are
+# bit-identical by construction (tests/test_gpu_screen.py checks the same on smaller shapes).
 mkdir -p gpurun_out
 run() {
   tag=$1; shift
@@ -16,5 +18,16 @@ except Exception as e:
     print(tag, "FAILED", e, open(f"gpurun_out/upd_{tag}.err").read()[-600:])
 PY
 }
-run def
-run def2
+run default
+run tf32 CSB200_SCREEN_F16=0
+run cta CSB200_UPD_WARP=0 CSB200_UPD_DEFER=0
+run cta_deferred CSB200_UPD_WARP=0 CSB200_UPD_DEFER=4
+run warp_1slice CSB200_UPD_DEFER=4
+run warp_4slices CSB200_UPD_DEFER=1
+run ring4 CSB200_UPD_WARP=0 CSB200_UPD_DEFER=0 CSB200_UPD_RING=4 CSB200_UPD_HINTS=3
+run parts2 CSB200_SCREEN_PARTS=2
+run stages3 CSB200_SCREEN_STAGES=3
+run chunks4 CSB200_SCREEN_CHUNKS=4
+run pipe_uniform CSB200_PIPE_CHUNK=18944
+run fp64_only CSB200_SCREEN=0
+(timeout 600 python -m pytest tests/test_gpu_screen.py -m gpu -x -q 2>&1 | tail -3)
