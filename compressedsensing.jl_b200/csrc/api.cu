@@ -788,7 +788,9 @@ bool screen_f16() {
 int ensure_screen_dict(csb200_dict* d, cudaStream_t st, bool f16 = false) {
     std::lock_guard<std::mutex> lk(d->screen_mu);
     if (d->screen_failed) return 1;
-    if (f16 && d->dA32 && !d->dA16) {                               // the FP16 copy, once the TF32 set-up (amax) exists
+    // the FP16 copy half(A * qA) and its tensor map; needs amax, i.e. the TF32 set-up below
+    auto build_f16 = [&]() -> int {
+        if (d->dA16) return CSB200_OK;
         const int64_t ld16 = round_up(d->M, 64);
         void* a16 = nullptr;
         if (cudaMalloc(&a16, (size_t)ld16 * d->N * 2) != cudaSuccess) { cudaGetLastError(); return 1; }
@@ -796,8 +798,9 @@ int ensure_screen_dict(csb200_dict* d, cudaStream_t st, bool f16 = false) {
         cudaError_t e16 = launch_to_f16(static_cast<const double*>(d->dA), d->ld, a16, ld16, (int)d->M, d->N, qA, nullptr, st);
         if (e16 != cudaSuccess || make_operand_map32(&d->mapA16, a16, ld16, d->N, 256, true) != CSB200_OK) { cudaGetLastError(); cudaFree(a16); return 1; }
         d->ld16 = ld16; d->qA = qA; d->dA16 = a16;
-    }
-    if (d->dA32) return (f16 && !d->dA16) ? 1 : CSB200_OK;
+        return CSB200_OK;
+    };
+    if (d->dA32) return f16 ? build_f16() : CSB200_OK;
     static std::once_flag once;
     static cudaError_t setup_err = cudaSuccess;
     std::call_once(once, [] { setup_err = corr_screen_setup(); });
@@ -821,16 +824,7 @@ int ensure_screen_dict(csb200_dict* d, cudaStream_t st, bool f16 = false) {
         cudaGetLastError(); cudaFree(a32); d->screen_failed = true; return 1;
     }
     d->ld32 = ld32; d->amax = amax; d->dA32 = a32;
-    if (f16) {                                                      // (the lock is held: build the FP16 copy inline)
-        const int64_t ld16 = round_up(d->M, 64);
-        void* a16 = nullptr;
-        if (cudaMalloc(&a16, (size_t)ld16 * d->N * 2) != cudaSuccess) { cudaGetLastError(); return 1; }
-        const double qA = ldexp(1.0, 11 - ilogb(d->amax));
-        cudaError_t e16 = launch_to_f16(static_cast<const double*>(d->dA), d->ld, a16, ld16, (int)d->M, d->N, qA, nullptr, st);
-        if (e16 != cudaSuccess || make_operand_map32(&d->mapA16, a16, ld16, d->N, 256, true) != CSB200_OK) { cudaGetLastError(); cudaFree(a16); return 1; }
-        d->ld16 = ld16; d->qA = qA; d->dA16 = a16;
-    }
-    return CSB200_OK;
+    return f16 ? build_f16() : CSB200_OK;
 }
 
 int ensure_screen_batch(csb200_batch* b, bool f16 = false) {
