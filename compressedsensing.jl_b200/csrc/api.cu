@@ -801,10 +801,15 @@ int ensure_screen_dict(csb200_dict* d, cudaStream_t st, bool f16 = false) {
         return CSB200_OK;
     };
     if (d->dA32) return f16 ? build_f16() : CSB200_OK;
-    static std::once_flag once;
-    static cudaError_t setup_err = cudaSuccess;
-    std::call_once(once, [] { setup_err = corr_screen_setup(); });
-    if (setup_err != cudaSuccess) { d->screen_failed = true; cudaGetLastError(); return 1; }
+    {   // kernel attributes (dynamic shared memory size, carve-out) are per DEVICE: once for each device this process uses
+        static std::mutex setup_mu;
+        static std::vector<int> setup_done;
+        std::lock_guard<std::mutex> sl(setup_mu);
+        if (std::find(setup_done.begin(), setup_done.end(), d->device) == setup_done.end()) {
+            if (corr_screen_setup() != cudaSuccess) { d->screen_failed = true; cudaGetLastError(); return 1; }
+            setup_done.push_back(d->device);
+        }
+    }
     const int64_t ld32 = round_up(d->M, 32);
     float* a32 = nullptr;
     double* cn = nullptr;

@@ -290,3 +290,25 @@ def test_screened_omp_on_unnormalised_atoms(cs, po, monkeypatch, variant):
         assert sel[s, :n].tolist() == t.order() and int(its[s]) == t.iterations
         o = np.argsort(sel[s, :n], kind="stable")
         assert np.allclose(coef[s, :n][o], ref.nzval, rtol=RTOL64, atol=RTOL64 * max(1.0, np.max(np.abs(ref.nzval))))
+
+
+def test_screened_omp_through_the_multi_device_handle(cs, po, monkeypatch):
+    """ONE csb200_omp call on a handle with several workers (all visible GPUs; entries repeat on a single-GPU box), each worker's
+    share large enough for the screening path: every worker sets up the tcgen05 pass on ITS device (kernel attributes are per
+    device) and the result equals the single-device call bit for bit."""
+    monkeypatch.setenv("CSB200_SCREEN", "1")
+    rng = np.random.default_rng(808)
+    M, N, k, B = 128, 1024, 6, 3 * 4096 + 50
+    A = po.gaussian_dictionary(rng, M, N)
+    Bm, _ = _planted(po, rng, A, B, k, noise=1e-3)
+    ndev = cs.device_count()
+    devices = list(range(ndev)) if ndev >= 3 else [i % ndev for i in range(3)]
+    with cs.Dictionary(A) as D1, cs.Dictionary(A, devices=devices) as Dn:
+        one, many = cs.omp(D1, Bm, k), cs.omp(Dn, Bm, k)
+    assert len(one) == len(many) == B
+    for s in range(B):
+        assert np.array_equal(one[s].nzind, many[s].nzind) and np.array_equal(one[s].nzval, many[s].nzval), s
+    for s in (0, 4096, B - 1):
+        ref = po.omp(A, Bm[:, s], k)
+        assert many[s].nzind.tolist() == ref.nzind
+        assert np.allclose(many[s].nzval, ref.nzval, rtol=RTOL64, atol=RTOL64)
