@@ -46,3 +46,15 @@ def test_parity_check_accepts_the_oracle_and_rejects_a_perturbation():
 def test_cli_defaults_match_the_driver_contract():
     a = bench.parse([])
     assert (a.gpus, a.config, a.impl, a.scaling, a.secondary) == (1, "c2", "ours", "weak", "auto") and a.warmup >= 3
+
+
+def test_tensor_peaks_come_from_the_driver_file_or_the_stated_fallback():
+    """The roofline denominators of the screening pass: MEASURED_PEAKS.json's bf16 figure for the FP16 pass (kind::f16), half of
+    it for the TF32 pass (kind::tf32 runs at half the rate), else the nominal numbers of B200_PROFILING.md -- and the source
+    string says which."""
+    f16, f16_src = bench.f16_peak()
+    tf32, tf32_src = bench.tf32_peak()
+    assert f16 == 2.0 * tf32
+    assert 1000.0 <= f16 <= 2500.0 and 500.0 <= tf32 <= 1250.0
+    assert ("MEASURED_PEAKS.json" in f16_src) == ("MEASURED_PEAKS.json" in tf32_src)
+    assert "MEASURED_PEAKS.json" in f16_src or "fallback" in f16_src
